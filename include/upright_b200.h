@@ -1,0 +1,225 @@
+/*
+ * upright_b200 — C ABI of the batched waiter's-problem MPC solve on B200.
+ *
+ * This header is the drop-in boundary for the ONE hot path this repository
+ * accelerates: `ControllerInterface::advanceMpc()` of utiasDSL/upright
+ * (upright_control/src/pybindings.cpp:364-427 binds it; the OCP it solves is
+ * assembled in upright_control/src/controller_interface.cpp:103-393), batched
+ * over independent MPC instances.  Plain C types only; no torch / CUDA types.
+ *
+ * Conventions
+ *   - all matrices row-major; all host-facing numbers are IEEE double like the
+ *     reference (`ocs2::scalar_t`, upright_control/include/upright_control/types.h:16-35);
+ *   - state  x = [q, v, a]            (nx = 3*nq; dimensions.h:10-46)
+ *     input  u = [jerk, f_1 .. f_nc]  (nu = nq + nf*nc)
+ *   - every function returns 0 on success or a negative UB_E_* code;
+ *     `ub_last_error()` gives the message of the last failure on this thread.
+ */
+#ifndef UPRIGHT_B200_H
+#define UPRIGHT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UB_MAX_JOINTS 9
+#define UB_MAX_BODIES 8
+#define UB_MAX_CONTACTS 32
+#define UB_MAX_SPHERES 16
+#define UB_MAX_PAIRS 32
+#define UB_MAX_NX (3 * UB_MAX_JOINTS)
+#define UB_BODY_PARAMS 10 /* m, m*com(3), vech(I)(6): rigid_body.h:36-54 */
+#define UB_STATS 8
+
+enum {
+    UB_OK = 0,
+    UB_E_INVALID = -1,   /* bad argument / unsupported setting            */
+    UB_E_CUDA = -2,      /* CUDA runtime error (message in ub_last_error) */
+    UB_E_NO_DEVICE = -3, /* no CUDA device: there is NO CPU fallback       */
+    UB_E_ALLOC = -4
+};
+
+/* per-instance solve status written to `status[b]` */
+enum {
+    UB_STATUS_CONVERGED = 0,   /* QP converged, line search accepted a step */
+    UB_STATUS_QP_MAXITER = 1,  /* QP iteration cap hit (step still taken)   */
+    UB_STATUS_LS_FAILED = 2,   /* no step size accepted: iterate unchanged  */
+    UB_STATUS_NAN = 3          /* non-finite value encountered              */
+};
+
+enum { UB_JOINT_REVOLUTE = 0, UB_JOINT_PRISMATIC = 1 };
+
+/* One single-dof joint of the serial chain.  Link i is the frame after joint
+ * i.  The Pinocchio model it replaces: composite PX,PY,RZ root + URDF chain
+ * (upright_control/include/upright_control/util.h:27-63). */
+typedef struct ub_joint {
+    int32_t type; /* UB_JOINT_* */
+    int32_t reserved;
+    double R[9];    /* fixed rotation parent link -> joint frame */
+    double p[3];    /* fixed translation, parent-link coordinates */
+    double axis[3]; /* unit motion axis, joint-frame coordinates  */
+} ub_joint_t;
+
+/* upright::ContactPoint (upright_core/include/upright_core/contact.h:10-48).
+ * body index -1 = a fixture (the tray/EE) that gets no dynamics rows. */
+typedef struct ub_contact {
+    int32_t body1;
+    int32_t body2;
+    double mu;
+    double r_co_o1[3];
+    double r_co_o2[3];
+    double normal[3]; /* points into object 1 */
+    double span[6];   /* 2x3, rows orthogonal to normal */
+} ub_contact_t;
+
+/* Collision sphere rigidly attached to link `link` (0..nq-1), to the tool
+ * frame (link == nq) or to the world (link == -1).  All collision geometry of
+ * the reference is spheres (upright_assets/thing/xacro/collision_links.urdf.xacro:31-184,
+ * obstacles/simple.urdf.xacro:40-102). */
+typedef struct ub_sphere {
+    int32_t link;
+    int32_t reserved;
+    double radius;
+    double offset[3];
+} ub_sphere_t;
+
+typedef struct ub_pair {
+    int32_t a;
+    int32_t b;
+} ub_pair_t;
+
+/* HPIPM slack settings surface (upright_control/src/upright_control/wrappers.py:121-143) */
+typedef struct ub_slack_settings {
+    int32_t enabled;
+    int32_t input_box;
+    int32_t state_box;
+    int32_t poly_ineq;
+    double upper_L2_penalty;
+    double lower_L2_penalty;
+} ub_slack_settings_t;
+
+/* Immutable per-configuration data: what ControllerSettings carries into
+ * ControllerInterface (upright_control/include/upright_control/controller_settings.h:47-119). */
+typedef struct ub_problem_desc {
+    int32_t nq;        /* robot joints (6 fixed-base UR10, 9 Thing) */
+    int32_t nb;        /* balanced bodies                            */
+    int32_t nc;        /* contact points                             */
+    int32_t nf;        /* force dimension per contact: 1 or 3        */
+    int32_t N;         /* knots = time_horizon / sqp.dt              */
+    int32_t n_spheres;
+    int32_t n_pairs;
+    int32_t sqp_iteration; /* SQP iterations per solve (controller.yaml:56)  */
+    int32_t qp_iter_max;   /* sqp.hpipm.iter_max: Riccati solves per QP      */
+    int32_t balancing_enabled;
+    int32_t obstacles_enabled;
+    int32_t reserved;
+    double dt;
+
+    ub_joint_t joints[UB_MAX_JOINTS];
+    double tool_R[9]; /* last link -> end_effector_link_name frame */
+    double tool_p[3];
+
+    double gravity[3];
+    double state_weight[UB_MAX_NX];  /* diag(Q)  (controller_interface.cpp:400-420) */
+    double input_weight[UB_MAX_JOINTS]; /* diag(R) on the jerk                      */
+    double ee_weight[6];             /* diag(W); orientation part must be 0 (round 1) */
+    double force_weight;             /* balancing.force_weight                   */
+    double xd[UB_MAX_NX];            /* desired joint state                      */
+
+    double state_lb[UB_MAX_NX], state_ub[UB_MAX_NX];
+    double input_lb[UB_MAX_JOINTS], input_ub[UB_MAX_JOINTS];
+    double force_lb, force_ub; /* controller_interface.cpp:330-356 */
+
+    double body_params[UB_MAX_BODIES][UB_BODY_PARAMS]; /* map-key order   */
+    ub_contact_t contacts[UB_MAX_CONTACTS];
+
+    ub_sphere_t spheres[UB_MAX_SPHERES];
+    ub_pair_t pairs[UB_MAX_PAIRS];
+    double minimum_distance;
+
+    ub_slack_settings_t slacks;
+
+    /* QP / SQP numerics (documented choices) */
+    double rho_hard;     /* augmented-Lagrangian penalty of hard rows     */
+    double rho_growth;   /* multiplied in when a hard row stalls          */
+    double rho_max;
+    double qp_tol;       /* Newton-decrement / feasibility tolerance      */
+    double reg_input;    /* Levenberg term on the input Hessian           */
+    /* filter line search (ocs2_sqp defaults) */
+    double alpha_decay, alpha_min, g_max, g_min, gamma_c, armijo_factor;
+    double delta_tol, cost_tol; /* controller.yaml:58-59 */
+} ub_problem_desc_t;
+
+typedef struct ub_problem ub_problem_t;
+
+/* Flags for ub_solve_batch */
+#define UB_PTRS_DEVICE 0x1u /* all batch pointers are device pointers (f32)  */
+#define UB_WARM_START 0x2u  /* X/U hold the previous solution on entry       */
+#define UB_COMPUTE_F64 0x4u /* validation build: run the kernels in fp64     */
+
+const char* ub_last_error(void);
+int ub_version(void);
+
+/* Replaces: ControllerInterface::ControllerInterface(settings)
+ * (upright_control/src/controller_interface.cpp:103-393). Validates the
+ * description, uploads constants to the current CUDA device. */
+int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out);
+void ub_problem_destroy(ub_problem_t* problem);
+
+/* Dimensions helper: nx, nu, rows per knot etc. out[0..7] =
+ * {nx, nu, n_eq, n_ineq_poly, n_terminal, N, nb, nc}. */
+int ub_problem_dims(const ub_problem_t* problem, int32_t out[8]);
+
+/* Bytes of device workspace ub_solve_batch needs for a batch of B. */
+int64_t ub_workspace_bytes(const ub_problem_t* problem, int32_t B, uint32_t flags);
+
+/* Replaces: B independent calls of
+ *   mpc.setObservation(t, x, u); mpc.advanceMpc(); mpc.getMpcSolution(...)
+ * (upright_control/src/pybindings.cpp:369-377; manager.py:156-170).
+ *
+ *   x0      [B, nx]          observed state per instance
+ *   target  [B, N+1, 3]      desired EE position at each knot time
+ *                            (interpolate_end_effector_pose, reference_trajectory.h:18-47)
+ *   body_params [B, nb, 10]  per-instance inertial parameters or NULL (shared)
+ *   X  [B, N+1, nx], U [B, N, nu]  solution (in/out when UB_WARM_START)
+ *   K  [B, N, nu, nx] Riccati feedback gains or NULL
+ *   status [B] int32, stats [B, UB_STATS] or NULL
+ *      stats = {qp_iters, cost, violation, step alpha, qp_residual,
+ *               max |object-dynamics eq|, min ineq margin, reserved}
+ *
+ * Host mode (default): pointers are host `double` arrays; copies to/from the
+ * device happen inside the call (synchronous on `stream`).
+ * Device mode (UB_PTRS_DEVICE): pointers are device arrays of `float`
+ * (`double` with UB_COMPUTE_F64); the call only enqueues work on `stream`.
+ * `workspace` may be NULL in host mode (allocated and cached internally).
+ */
+int ub_solve_batch(ub_problem_t* problem, int32_t B, const void* x0, const void* target,
+                   const void* body_params, void* X, void* U, void* K, int32_t* status,
+                   void* stats, void* workspace, int64_t workspace_bytes, uint32_t flags,
+                   void* cuda_stream);
+
+/* Replaces the named probes getStateInputEqualityConstraintValue("object_dynamics"),
+ * getStateInputInequalityConstraintValue("contact_forces" | "obstacle_avoidance")
+ * and getCostValue (controller_python_interface.h:31-88), batched: evaluates
+ * at M (x,u) pairs on the device.  Host double pointers.
+ *   name in {"object_dynamics","contact_forces","obstacle_avoidance",
+ *            "end_effector_position","cost"}
+ *   out [M, rows]; rows returned through *rows_out. */
+int ub_eval(ub_problem_t* problem, const char* name, int32_t M, const double* x,
+            const double* u, const double* target /*[M,3] or NULL*/,
+            const double* body_params /*[M,nb,10] or NULL*/, double* out, int32_t out_capacity,
+            int32_t* rows_out);
+
+/* Device time of the last ub_solve_batch on this problem (CUDA events), ms.
+ * Replaces getLastSolveTime() (controller_python_interface.h:27-29). */
+float ub_last_solve_ms(const ub_problem_t* problem);
+
+/* Number of kernel launches issued by this library since load. */
+int64_t ub_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPRIGHT_B200_H */

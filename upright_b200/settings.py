@@ -1,0 +1,379 @@
+"""`ControllerSettings` / `TargetTrajectories` with the attribute surface of the
+reference's pybind structs, filled from the same YAML dictionaries.
+
+Mirrors `upright_control/src/upright_control/wrappers.py:14-399` (field names,
+defaults, assertions) and the struct tree of
+`upright_control/include/upright_control/controller_settings.h:47-119`.  The
+URDF step (`parse_and_compile_urdf`, wrappers.py:279-281) is replaced by the
+kinematic-chain fixture in `robot.py`; everything else is parsed identically.
+`to_desc()` flattens the settings into the C-ABI `ub_problem_desc_t`.
+"""
+from __future__ import annotations
+
+import xml.etree.ElementTree as ET
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import bindings as B
+from . import config as cfgmod
+from . import geometry as geo
+from . import objects, robot
+
+
+class RobotDimensions(SimpleNamespace):
+    def __init__(self):
+        super().__init__(q=0, v=0, x=0, u=0)
+
+
+class OptimizationDimensions:
+    """upright_control/include/upright_control/dimensions.h:18-46."""
+
+    def __init__(self):
+        self.robot = RobotDimensions()
+        self.o = 0
+        self.c = 0
+        self.nf = 3
+
+    def q(self):
+        return self.robot.q + 3 * self.o
+
+    def v(self):
+        return self.robot.v + 3 * self.o
+
+    def x(self):
+        return self.robot.x + 9 * self.o
+
+    def f(self):
+        return self.nf * self.c
+
+    def u(self):
+        return self.robot.u + self.f()
+
+
+class TargetTrajectories:
+    """ocs2::TargetTrajectories as wrapped by wrappers.py:14-76: each target
+    state is [r(3), quat xyzw(4), s(1)]."""
+
+    def __init__(self, ts, xs, us):
+        self.ts = [float(t) for t in ts]
+        self.xs = [np.array(x, dtype=float) for x in xs]
+        self.us = [np.array(u, dtype=float) for u in us]
+
+    @classmethod
+    def from_config(cls, config, r_ew_w, Q_we, u):
+        ts, xs, us = [], [], []
+        for wp in config["waypoints"]:
+            r = np.asarray(r_ew_w, dtype=float) + np.asarray(wp["position"], dtype=float)
+            Q = geo.quat_multiply(Q_we, np.asarray(wp["orientation"], dtype=float))
+            ts.append(wp["time"])
+            xs.append(np.concatenate((r, Q, [0.0])))
+            us.append(np.copy(u))
+        return cls(ts, xs, us)
+
+    def get_desired_state(self, t):
+        """Linear interpolation in time, clamped (ocs2 LinearInterpolation)."""
+        if len(self.xs) == 1 or t <= self.ts[0]:
+            return self.xs[0].copy()
+        if t >= self.ts[-1]:
+            return self.xs[-1].copy()
+        i = int(np.searchsorted(self.ts, t, side="right")) - 1
+        a = (self.ts[i + 1] - t) / (self.ts[i + 1] - self.ts[i])
+        return a * self.xs[i] + (1 - a) * self.xs[i + 1]
+
+    def get_desired_input(self, t):
+        return self.us[0].copy()
+
+    def get_desired_pose(self, t):
+        x = self.get_desired_state(t)
+        return x[:3], x[3:7]
+
+    def poses(self):
+        for x in self.xs:
+            yield x[:3], x[3:7]
+
+    def positions_at(self, times):
+        """Desired EE position at each time (reference_trajectory.h:18-47,
+        position part)."""
+        return np.array([self.get_desired_state(t)[:3] for t in times])
+
+
+def _read_obstacle_xacro(path):
+    """Sphere obstacles from an `obstacle_link` xacro scene such as
+    upright_assets/thing/xacro/obstacles/simple.urdf.xacro:41-102."""
+    out = {}
+    for el in ET.parse(path).getroot().iter():
+        if el.tag.endswith("obstacle_link") and "name" in el.attrib:
+            origin = el.find("origin")
+            sph = el.find("geometry/sphere")
+            if origin is None or sph is None:
+                continue
+            xyz = [float(v) for v in origin.attrib.get("xyz", "0 0 0").split()]
+            out[el.attrib["name"]] = (np.array(xyz), float(sph.attrib["radius"]))
+    return out
+
+
+def _resolve_find(path_expr):
+    # "$(find pkg)/rest" -> file path via the package roots
+    assert path_expr.startswith("$(find ")
+    pkg, rest = path_expr[len("$(find "):].split(")", 1)
+    return cfgmod.resolve_package_path({"package": pkg, "path": rest.lstrip("/")})
+
+
+class ControllerSettings:
+    def __init__(self, config, x0=None, operating_trajectory=None):
+        pn, pa = cfgmod.parse_number, cfgmod.parse_array
+        self.config = config
+        self.mpc = SimpleNamespace(
+            time_horizon=pn(config["mpc"]["time_horizon"]),
+            debug_print=config["mpc"]["debug_print"],
+            cold_start=config["mpc"]["cold_start"],
+        )
+        ro = config["rollout"]
+        self.rollout = SimpleNamespace(
+            abs_tol_ode=pn(ro["abs_tol_ode"]), rel_tol_ode=pn(ro["rel_tol_ode"]),
+            timestep=pn(ro["timestep"]),
+            max_num_steps_per_second=pn(ro["max_num_steps_per_second"], dtype=int),
+            check_numerical_stability=ro["check_numerical_stability"],
+        )
+        sq = config["sqp"]
+        sl = sq["hpipm"]["slacks"]
+        slacks = SimpleNamespace(
+            enabled=sl["enabled"], input_box=sl.get("input_box", True),
+            state_box=sl.get("state_box", True), poly_ineq=sl.get("poly_ineq", True),
+            upper_L2_penalty=sl.get("upper_L2_penalty", 100),
+            lower_L2_penalty=sl.get("lower_L2_penalty", 100),
+            upper_L1_penalty=sl.get("upper_L1_penalty", 0),
+            lower_L1_penalty=sl.get("lower_L1_penalty", 0),
+            upper_low_bound=sl.get("upper_low_bound", 0),
+            lower_low_bound=sl.get("lower_low_bound", 0),
+        )
+        self.sqp = SimpleNamespace(
+            dt=pn(sq["dt"]), sqp_iteration=sq["sqp_iteration"],
+            init_sqp_iteration=sq["init_sqp_iteration"], delta_tol=pn(sq["delta_tol"]),
+            cost_tol=pn(sq["cost_tol"]), use_feedback_policy=sq["use_feedback_policy"],
+            project_state_input_equality_constraints=sq["project_state_input_equality_constraints"],
+            print_solver_status=sq["print_solver_status"],
+            print_solver_statistics=sq["print_solver_statistics"],
+            print_line_search=sq["print_line_search"],
+            hpipm=SimpleNamespace(warm_start=sq["hpipm"]["warm_start"],
+                                  iter_max=sq["hpipm"]["iter_max"], slacks=slacks),
+        )
+        self.end_effector_link_name = config["robot"]["tool_link_name"]
+        self.robot_base_type = config["robot"]["base_type"]
+        est = config.get("estimation", {})
+        self.estimation = SimpleNamespace(**est)
+        self.tracking = SimpleNamespace(**config.get("tracking", {}))
+        self.gravity = np.array(config["gravity"], dtype=float)
+        self.recompile_libraries = config.get("recompile_libraries", True)
+        self.debug = config.get("debug", False)
+
+        self.dims = OptimizationDimensions()
+        d = config["robot"]["dims"]
+        self.dims.robot.q, self.dims.robot.v = d["q"], d["v"]
+        self.dims.robot.x, self.dims.robot.u = d["x"], d["u"]
+        rq, rx, ru = self.dims.robot.q, self.dims.robot.x, self.dims.robot.u
+
+        w = config["weights"]
+        self.input_weight = cfgmod.parse_diag_matrix_dict(w["input"])
+        self.state_weight = cfgmod.parse_diag_matrix_dict(w["state"])
+        self.end_effector_weight = cfgmod.parse_diag_matrix_dict(w["end_effector"])
+        assert self.input_weight.shape == (ru, ru)
+        assert self.state_weight.shape == (rx, rx)
+        assert self.end_effector_weight.shape == (6, 6)
+
+        lim = config["limits"]
+        self.input_limit_lower = pa(lim["input"]["lower"])
+        self.input_limit_upper = pa(lim["input"]["upper"])
+        self.state_limit_lower = pa(lim["state"]["lower"])
+        self.state_limit_upper = pa(lim["state"]["upper"])
+        assert self.input_limit_lower.shape == (ru,) and self.input_limit_upper.shape == (ru,)
+        assert self.state_limit_lower.shape == (rx,) and self.state_limit_upper.shape == (rx,)
+
+        ebc = config.get("end_effector_box_constraint", {"enabled": False})
+        self.end_effector_box_constraint_enabled = ebc["enabled"]
+        self.xyz_lower = pa(ebc.get("xyz_lower", [-1, -1, -1]))
+        self.xyz_upper = pa(ebc.get("xyz_upper", [1, 1, 1]))
+        ppc = config.get("projectile_path_constraint", {"enabled": False})
+        self.projectile_path_constraint_enabled = ppc["enabled"]
+
+        self.locked_joints = {
+            k: pn(v) for k, v in config["robot"].get("locked_joints", {}).items()
+        }
+        self.base_pose = np.array(config["robot"].get("base_pose", [0, 0, 0]), dtype=float)
+        assert self.base_pose.shape == (3,)
+        # The un-vendored URDF is replaced by the in-repo chain fixture.
+        self.robot_urdf_path = "<upright_b200.robot fixture>"
+        self.lib_folder = "/tmp/ocs2"
+        self.use_operating_points = bool(config.get("operating_points", {}).get("enabled", False))
+
+        bal = config["balancing"]
+        self.balancing_settings = SimpleNamespace(
+            enabled=bal["enabled"], arrangement_name=bal["arrangement"],
+            force_weight=bal["force_weight"], bodies={}, contacts=[],
+        )
+        bodies, contacts = objects.parse_control_objects(config)
+        self.balancing_settings.bodies = bodies
+        self.balancing_settings.contacts = contacts
+        if self.balancing_settings.enabled:
+            self.dims.c = len(contacts)
+            self.dims.nf = 1 if bal["frictionless"] else 3
+        else:
+            self.dims.c = 0
+            self.dims.nf = 0
+
+        ia = config.get("inertial_alignment", {})
+        self.inertial_alignment_settings = SimpleNamespace(
+            cost_enabled=ia.get("cost_enabled", False),
+            constraint_enabled=ia.get("constraint_enabled", False),
+        )
+
+        obs = config.get("obstacles", {"enabled": False})
+        self.obstacle_settings = SimpleNamespace(
+            enabled=obs["enabled"], collision_link_pairs=[],
+            minimum_distance=obs.get("minimum_distance", 0.1),
+            obstacle_urdf_path="", dynamic_obstacles=[], static_spheres={},
+        )
+        if self.obstacle_settings.enabled:
+            for pair in obs.get("collision_pairs") or []:
+                self.obstacle_settings.collision_link_pairs.append(tuple(pair))
+            if "spheres" in obs:  # this repo's explicit form
+                for s in obs["spheres"]:
+                    self.obstacle_settings.static_spheres[s["name"]] = (
+                        np.array(s["position"], dtype=float), float(s["radius"]))
+            elif "urdf" in obs:
+                for inc in obs["urdf"]["includes"]:
+                    path = _resolve_find(inc)
+                    self.obstacle_settings.obstacle_urdf_path = str(path)
+                    self.obstacle_settings.static_spheres.update(_read_obstacle_xacro(path))
+            if obs.get("dynamic"):
+                raise NotImplementedError(
+                    "dynamic obstacles (+9 states each) are a 'next' row (SURVEY §8f-2)")
+
+        if x0 is None:
+            x0_robot = pa(config["robot"]["x0"])
+            assert x0_robot.shape == (rx,)
+            self.initial_state = x0_robot
+        else:
+            self.initial_state = np.array(x0, dtype=float)
+        assert self.initial_state.shape == (self.dims.x(),)
+        self.xd = np.array(config.get("desired_state", np.zeros_like(self.initial_state)), dtype=float)
+
+        # kinematic chain replacing the URDF + Pinocchio model
+        self.chain = robot.build_chain(
+            "fixed" if self.robot_base_type == "fixed" else "omnidirectional", self.base_pose)
+        assert self.chain.nq == rq, f"chain has {self.chain.nq} joints, config says {rq}"
+
+    @classmethod
+    def from_config_file(cls, path):
+        return cls(cfgmod.load_config(path)["controller"])
+
+    # ------------------------------------------------------------------ C ABI
+    def body_names(self):
+        """std::map iteration order of bodies (contact_constraints.h:180)."""
+        return sorted(self.balancing_settings.bodies.keys())
+
+    def to_desc(self) -> B.ProblemDesc:
+        d = B.ProblemDesc()
+        dims = self.dims
+        nq = dims.robot.q
+        d.nq = nq
+        names = self.body_names() if self.balancing_settings.enabled else []
+        d.nb = len(names)
+        d.nc = dims.c
+        d.nf = dims.nf if dims.c > 0 else 1
+        if d.nb > B.UB_MAX_BODIES or d.nc > B.UB_MAX_CONTACTS:
+            raise ValueError("arrangement exceeds UB_MAX_BODIES / UB_MAX_CONTACTS")
+        d.dt = self.sqp.dt
+        d.N = int(round(self.mpc.time_horizon / self.sqp.dt))
+        d.sqp_iteration = int(self.sqp.sqp_iteration)
+        d.qp_iter_max = int(self.sqp.hpipm.iter_max)
+        d.balancing_enabled = int(bool(self.balancing_settings.enabled) and d.nb > 0)
+        d.obstacles_enabled = int(bool(self.obstacle_settings.enabled))
+
+        for i, j in enumerate(self.chain.joints):
+            d.joints[i].type = j.type
+            d.joints[i].R[:] = j.R.ravel()
+            d.joints[i].p[:] = j.p
+            d.joints[i].axis[:] = j.axis
+        d.tool_R[:] = self.chain.tool_R.ravel()
+        d.tool_p[:] = self.chain.tool_p
+        d.gravity[:] = self.gravity
+
+        Qd, Rd, Wd = np.diag(self.state_weight), np.diag(self.input_weight), np.diag(self.end_effector_weight)
+        for M in (self.state_weight, self.input_weight, self.end_effector_weight):
+            if np.abs(M - np.diag(np.diag(M))).max() > 0:
+                raise NotImplementedError("only diagonal weights are supported")
+        if np.abs(Wd[3:]).max() > 0:
+            raise NotImplementedError(
+                "end-effector orientation weight != 0 is a 'next' item (all shipped configs use 0)")
+        d.state_weight[: 3 * nq] = Qd
+        d.input_weight[:nq] = Rd
+        d.ee_weight[:] = Wd
+        d.force_weight = float(self.balancing_settings.force_weight)
+        d.xd[: 3 * nq] = self.xd[: 3 * nq]
+        d.state_lb[: 3 * nq] = self.state_limit_lower
+        d.state_ub[: 3 * nq] = self.state_limit_upper
+        d.input_lb[:nq] = self.input_limit_lower
+        d.input_ub[:nq] = self.input_limit_upper
+        # controller_interface.cpp:330-356
+        d.force_ub = 1e2
+        d.force_lb = 0.0 if d.nf == 1 else -1e2
+
+        index = {n: i for i, n in enumerate(names)}
+        for i, n in enumerate(names):
+            d.body_params[i][:] = self.balancing_settings.bodies[n].get_parameters()
+        if d.balancing_enabled:
+            for i, c in enumerate(self.balancing_settings.contacts):
+                dc = d.contacts[i]
+                dc.body1 = index.get(c.object1_name, -1)
+                dc.body2 = index[c.object2_name]
+                dc.mu = c.mu
+                dc.r_co_o1[:] = c.r_co_o1
+                dc.r_co_o2[:] = c.r_co_o2
+                dc.normal[:] = c.normal
+                dc.span[:] = np.asarray(c.span).ravel()
+
+        if d.obstacles_enabled:
+            spheres = list(self.chain.spheres)
+            sidx = {s.name: i for i, s in enumerate(spheres)}
+            for name, (pos, rad) in self.obstacle_settings.static_spheres.items():
+                sidx[name] = len(spheres)
+                spheres.append(robot.Sphere(name, -1, pos, rad))
+            used, pairs = {}, []
+            for a, b in self.obstacle_settings.collision_link_pairs:
+                ia, ib = (sidx[n[:-2] if n.endswith("_0") else n] for n in (a, b))
+                for k in (ia, ib):
+                    used.setdefault(k, len(used))
+                pairs.append((used[ia], used[ib]))
+            if len(used) > B.UB_MAX_SPHERES or len(pairs) > B.UB_MAX_PAIRS:
+                raise ValueError("too many collision spheres / pairs")
+            for k, slot in used.items():
+                s = spheres[k]
+                d.spheres[slot].link = s.link
+                d.spheres[slot].radius = s.radius
+                d.spheres[slot].offset[:] = s.offset
+            for i, (a, b) in enumerate(pairs):
+                d.pairs[i].a, d.pairs[i].b = a, b
+            d.n_spheres, d.n_pairs = len(used), len(pairs)
+            d.minimum_distance = float(self.obstacle_settings.minimum_distance)
+
+        s = self.sqp.hpipm.slacks
+        d.slacks.enabled = int(bool(s.enabled))
+        d.slacks.input_box = int(bool(s.input_box))
+        d.slacks.state_box = int(bool(s.state_box))
+        d.slacks.poly_ineq = int(bool(s.poly_ineq))
+        d.slacks.upper_L2_penalty = float(s.upper_L2_penalty)
+        d.slacks.lower_L2_penalty = float(s.lower_L2_penalty)
+        if s.enabled and (s.upper_L1_penalty or s.lower_L1_penalty or s.upper_low_bound or s.lower_low_bound):
+            raise NotImplementedError("only pure L2 slack penalties with zero lower bound are supported")
+        if s.enabled and s.upper_L2_penalty != s.lower_L2_penalty:
+            raise NotImplementedError("upper/lower L2 slack penalties must be equal")
+
+        # numerics: documented choices
+        d.rho_hard, d.rho_growth, d.rho_max = 1.0e3, 10.0, 1.0e5
+        d.qp_tol, d.reg_input = 1.0e-6, 1.0e-6
+        d.alpha_decay, d.alpha_min = 0.5, 1e-4
+        d.g_max, d.g_min, d.gamma_c, d.armijo_factor = 1e6, 1e-6, 1e-6, 1e-4
+        d.delta_tol, d.cost_tol = float(self.sqp.delta_tol), float(self.sqp.cost_tol)
+        return d
