@@ -114,7 +114,7 @@ typedef struct ub_problem_desc {
     int32_t qp_iter_max;   /* sqp.hpipm.iter_max: Riccati solves per QP      */
     int32_t balancing_enabled;
     int32_t obstacles_enabled;
-    int32_t reserved;
+    int32_t qp_method;     /* 0 = interior point (product), 1 = semismooth Newton (oracle cross-check only) */
     double dt;
 
     ub_joint_t joints[UB_MAX_JOINTS];
@@ -142,11 +142,12 @@ typedef struct ub_problem_desc {
     ub_slack_settings_t slacks;
 
     /* QP / SQP numerics (documented choices) */
-    double rho_hard;     /* augmented-Lagrangian penalty of hard rows     */
-    double rho_growth;   /* multiplied in when a hard row stalls          */
-    double rho_max;
-    double qp_tol;       /* Newton-decrement / feasibility tolerance      */
-    double reg_input;    /* Levenberg term on the input Hessian           */
+    double rho_hard;     /* proximal/AL penalty of hard equality rows (unit-normalised rows) */
+    double qp_mu0;       /* initial complementarity t*lambda                */
+    double qp_thr0;      /* floor of the initial inequality slacks t        */
+    double qp_mu_target; /* central-path point the QP is solved to          */
+    double qp_tol;       /* residual tolerance (inequality / equality rows) */
+    double reg_input;    /* Levenberg term on the input Hessian             */
     /* filter line search (ocs2_sqp defaults) */
     double alpha_decay, alpha_min, g_max, g_min, gamma_c, armijo_factor;
     double delta_tol, cost_tol; /* controller.yaml:58-59 */

@@ -1,0 +1,193 @@
+// TEST INFRASTRUCTURE — CPU oracle (fp64) for the upright MPC hot path.
+//
+// Scalar-templated restatement of the problem functions the reference feeds
+// to OCS2.  Each function cites the reference lines it follows.  Instantiated
+// with `double` for values and with `orc::Dual` for exact first derivatives
+// (the role CppAD plays in the reference).
+#pragma once
+#include <vector>
+
+#include "../include/upright_b200.h"
+#include "smallmath.h"
+
+namespace orc {
+
+// upright::RigidBodyState (upright_core/include/upright_core/types.h:72-85) +
+// the collision-sphere centres the obstacle constraint needs.
+template <typename S>
+struct Kinematics {
+    Vec3<S> r;       // EE (tray) origin, world
+    Mat3<S> C_we;    // EE orientation
+    Vec3<S> v, w;    // linear / angular velocity, world-aligned
+    Vec3<S> a, al;   // classical linear / angular acceleration, world-aligned
+    Vec3<S> sphere[UB_MAX_SPHERES];
+};
+
+// Forward kinematics with velocities and classical accelerations of the tool
+// frame.  Replaces ocs2::PinocchioEndEffectorKinematicsCppAd as used at
+// upright_control/src/constraint/balancing_constraints.cpp:15-30
+// (getPosition/Orientation/Velocity/AngularVelocity/Acceleration/
+// AngularAcceleration, LOCAL_WORLD_ALIGNED) on the chain built at
+// upright_control/include/upright_control/util.h:15-65; state slicing
+// x -> (q, v, a) follows dynamics/system_pinocchio_mapping.h:11-57.
+template <typename S>
+Kinematics<S> forward_kinematics(const ub_problem_desc_t& P, const S* x) {
+    const int nq = P.nq;
+    Mat3<S> R = Mat3<S>::identity();
+    Vec3<S> p, v, w, a, al;
+    Kinematics<S> K;
+    auto attach = [&](int link) {
+        for (int s = 0; s < P.n_spheres; ++s)
+            if (P.spheres[s].link == link) K.sphere[s] = p + R * vec3_from<S>(P.spheres[s].offset);
+    };
+    for (int s = 0; s < P.n_spheres; ++s)
+        if (P.spheres[s].link < 0) K.sphere[s] = vec3_from<S>(P.spheres[s].offset);
+
+    auto offset_frame = [&](const double* Rt, const double* pt) {
+        // move the frame origin by a body-fixed offset and re-orient it
+        const Vec3<S> ro = R * vec3_from<S>(pt);
+        p = p + ro;
+        v = v + cross(w, ro);
+        a = a + cross(al, ro) + cross(w, cross(w, ro));
+        R = R * Mat3<S>::from_rowmajor(Rt);
+    };
+    for (int i = 0; i < nq; ++i) {
+        const ub_joint_t& J = P.joints[i];
+        offset_frame(J.R, J.p);
+        const Vec3<S> ul = vec3_from<S>(J.axis);
+        const Vec3<S> z = R * ul;
+        const S qi = x[i], qd = x[nq + i], qdd = x[2 * nq + i];
+        if (J.type == UB_JOINT_REVOLUTE) {
+            al = al + qdd * z + qd * cross(w, z);
+            w = w + qd * z;
+            R = R * axis_angle(ul, qi);
+        } else {
+            const Vec3<S> d = qi * z;
+            a = a + qdd * z + S(2.0) * qd * cross(w, z) + cross(al, d) + cross(w, cross(w, d));
+            v = v + qd * z + cross(w, d);
+            p = p + d;
+        }
+        attach(i);
+    }
+    offset_frame(P.tool_R, P.tool_p);
+    attach(nq);
+    K.r = p;
+    K.C_we = R;
+    K.v = v;
+    K.w = w;
+    K.a = a;
+    K.al = al;
+    return K;
+}
+
+// upright::RigidBody::from_parameters (upright_core/include/upright_core/rigid_body.h:36-46)
+template <typename S>
+struct Body {
+    S mass;
+    Vec3<S> com;
+    Mat3<S> inertia;
+    static Body from_parameters(const double* p) {
+        Body b;
+        b.mass = S(p[0]);
+        b.com = Vec3<S>(S(p[1] / p[0]), S(p[2] / p[0]), S(p[3] / p[0]));
+        const double I[9] = {p[4], p[5], p[6], p[5], p[7], p[8], p[6], p[8], p[9]};
+        b.inertia = Mat3<S>::from_rowmajor(I);
+        return b;
+    }
+};
+
+template <typename S>
+struct Wrench {
+    Vec3<S> force, torque;
+};
+
+// compute_object_wrenches (upright_core/include/upright_core/contact_constraints.h:106-157):
+// contact force f acts on object1 with lever r_co_o1 - com1 and as -f on
+// object2 with lever r_co_o2 - com2; frictionless => f = f_i * normal (:111-120).
+template <typename S>
+void object_wrenches(const ub_problem_desc_t& P, const Body<S>* bodies, const S* forces, Wrench<S>* out) {
+    for (int b = 0; b < P.nb; ++b) out[b] = Wrench<S>();
+    for (int i = 0; i < P.nc; ++i) {
+        const ub_contact_t& c = P.contacts[i];
+        Vec3<S> f;
+        if (P.nf == 1) {
+            f = forces[i] * vec3_from<S>(c.normal);
+        } else {
+            f = Vec3<S>(forces[3 * i], forces[3 * i + 1], forces[3 * i + 2]);
+        }
+        if (c.body1 >= 0) {
+            const Vec3<S> lever = vec3_from<S>(c.r_co_o1) - bodies[c.body1].com;
+            out[c.body1].force = out[c.body1].force + f;
+            out[c.body1].torque = out[c.body1].torque + cross(lever, f);
+        }
+        {
+            const Vec3<S> lever = vec3_from<S>(c.r_co_o2) - bodies[c.body2].com;
+            out[c.body2].force = out[c.body2].force - f;
+            out[c.body2].torque = out[c.body2].torque + cross(lever, -f);
+        }
+    }
+}
+
+// compute_object_dynamics_constraints (contact_constraints.h:79-102,161-194)
+// scaled by 1/sqrt(6 nb) as ObjectDynamicsConstraints::constraintFunction does
+// (upright_control/src/constraint/balancing_constraints.cpp:140-151).
+// dC_dtt = (S(alpha) + S(omega) S(omega)) C_we  (upright_core/include/upright_core/util.h:37-50).
+template <typename S>
+void object_dynamics_constraints(const ub_problem_desc_t& P, const double* body_params, const Kinematics<S>& X,
+                                 const S* forces, S* g) {
+    Body<S> bodies[UB_MAX_BODIES];
+    for (int b = 0; b < P.nb; ++b) bodies[b] = Body<S>::from_parameters(body_params + UB_BODY_PARAMS * b);
+    Wrench<S> wr[UB_MAX_BODIES];
+    object_wrenches(P, bodies, forces, wr);
+
+    const Vec3<S> gravity = vec3_from<S>(P.gravity);
+    const Mat3<S> C_ew = X.C_we.transpose();
+    const Mat3<S> Sw = skew3(X.w);
+    const Mat3<S> ddC = (skew3(X.al) + Sw * Sw) * X.C_we;
+    const S scale = S(1.0 / std::sqrt(6.0 * P.nb));
+    for (int b = 0; b < P.nb; ++b) {
+        const Body<S>& body = bodies[b];
+        const Vec3<S> gi_force = body.mass * (C_ew * (X.a + ddC * body.com - gravity));
+        const Vec3<S> w_e = C_ew * X.w;
+        const Vec3<S> al_e = C_ew * X.al;
+        const Vec3<S> inertial_torque = cross(w_e, body.inertia * w_e) + body.inertia * al_e;
+        const Vec3<S> cf = (gi_force - wr[b].force);
+        const Vec3<S> ct = (inertial_torque - wr[b].torque);
+        for (int i = 0; i < 3; ++i) {
+            g[6 * b + i] = scale * cf[i] / body.mass;
+            g[6 * b + 3 + i] = scale * ct[i] / body.mass;
+        }
+    }
+}
+
+// compute_contact_force_constraints_linearized (contact_constraints.h:49-77): h >= 0
+template <typename S>
+void contact_force_constraints(const ub_problem_desc_t& P, const S* forces, S* h) {
+    for (int i = 0; i < P.nc; ++i) {
+        const ub_contact_t& c = P.contacts[i];
+        const Vec3<S> f(forces[3 * i], forces[3 * i + 1], forces[3 * i + 2]);
+        const S fn = dot(vec3_from<S>(c.normal), f);
+        const S ft0 = dot(vec3_from<S>(c.span), f);
+        const S ft1 = dot(vec3_from<S>(c.span + 3), f);
+        const S mu(c.mu);
+        h[5 * i + 0] = fn;
+        h[5 * i + 1] = mu * fn - ft0 - ft1;
+        h[5 * i + 2] = mu * fn - ft0 + ft1;
+        h[5 * i + 3] = mu * fn + ft0 - ft1;
+        h[5 * i + 4] = mu * fn + ft0 + ft1;
+    }
+}
+
+// Sphere-sphere distances minus the minimum distance, h >= 0.  Closed form of
+// ocs2::SelfCollisionConstraintCppAd + hpp-fcl for sphere pairs
+// (upright_control/src/controller_interface.cpp:450-481).
+template <typename S>
+void obstacle_constraints(const ub_problem_desc_t& P, const Kinematics<S>& X, S* h) {
+    for (int i = 0; i < P.n_pairs; ++i) {
+        const int a = P.pairs[i].a, b = P.pairs[i].b;
+        const Vec3<S> d = X.sphere[a] - X.sphere[b];
+        h[i] = sqrt(dot(d, d)) - S(P.spheres[a].radius + P.spheres[b].radius + P.minimum_distance);
+    }
+}
+
+}  // namespace orc

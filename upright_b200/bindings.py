@@ -57,7 +57,7 @@ class ProblemDesc(C.Structure):
         ("N", C.c_int32), ("n_spheres", C.c_int32), ("n_pairs", C.c_int32),
         ("sqp_iteration", C.c_int32), ("qp_iter_max", C.c_int32),
         ("balancing_enabled", C.c_int32), ("obstacles_enabled", C.c_int32),
-        ("reserved", C.c_int32),
+        ("qp_method", C.c_int32),
         ("dt", C.c_double),
         ("joints", Joint * UB_MAX_JOINTS),
         ("tool_R", C.c_double * 9), ("tool_p", C.c_double * 3),
@@ -76,8 +76,8 @@ class ProblemDesc(C.Structure):
         ("pairs", Pair * UB_MAX_PAIRS),
         ("minimum_distance", C.c_double),
         ("slacks", SlackSettings),
-        ("rho_hard", C.c_double), ("rho_growth", C.c_double), ("rho_max", C.c_double),
-        ("qp_tol", C.c_double), ("reg_input", C.c_double),
+        ("rho_hard", C.c_double), ("qp_mu0", C.c_double), ("qp_thr0", C.c_double),
+        ("qp_mu_target", C.c_double), ("qp_tol", C.c_double), ("reg_input", C.c_double),
         ("alpha_decay", C.c_double), ("alpha_min", C.c_double), ("g_max", C.c_double),
         ("g_min", C.c_double), ("gamma_c", C.c_double), ("armijo_factor", C.c_double),
         ("delta_tol", C.c_double), ("cost_tol", C.c_double),

@@ -1,0 +1,78 @@
+"""(De)serialise `ub_problem_desc_t` to JSON so that tests, smoke() and bench.py
+run on the GPU box, where the reference tree (`/root/reference`) is absent.
+The fixtures under `upright_b200/data/` are generated from the reference's own
+YAML files by `tools/gen_fixtures.py` (committed beside them)."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from pathlib import Path
+
+import numpy as np
+
+from . import bindings as B
+
+DATA_DIR = Path(__file__).resolve().parent / "data"
+
+
+def _to_py(obj):
+    if isinstance(obj, C.Structure):
+        return {name: _to_py(getattr(obj, name)) for name, _ in obj._fields_}
+    if isinstance(obj, C.Array):
+        return [_to_py(v) for v in obj]
+    return obj
+
+
+def _from_py(target, value):
+    """Fill ctypes struct/array `target` in place from nested python data."""
+    if isinstance(target, C.Structure):
+        for name, ftype in target._fields_:
+            if name not in value:
+                continue
+            cur = getattr(target, name)
+            if isinstance(cur, (C.Structure, C.Array)):
+                _from_py(cur, value[name])
+            else:
+                setattr(target, name, value[name])
+    else:  # array
+        for i, v in enumerate(value):
+            if isinstance(target[i], (C.Structure, C.Array)):
+                _from_py(target[i], v)
+            else:
+                target[i] = v
+
+
+def desc_to_dict(desc: B.ProblemDesc) -> dict:
+    return _to_py(desc)
+
+
+def desc_from_dict(d: dict) -> B.ProblemDesc:
+    desc = B.ProblemDesc()
+    _from_py(desc, d)
+    return desc
+
+
+def save_fixture(name: str, desc: B.ProblemDesc, meta: dict, directory=DATA_DIR):
+    directory.mkdir(parents=True, exist_ok=True)
+    with open(directory / f"{name}.json", "w") as f:
+        json.dump({"meta": meta, "desc": desc_to_dict(desc)}, f, indent=1)
+
+
+def load_fixture(name: str, directory=DATA_DIR):
+    """-> (desc, meta).  meta: x0 (home state), r_ee0, source, body_names, ..."""
+    with open(Path(directory) / f"{name}.json") as f:
+        doc = json.load(f)
+    meta = doc["meta"]
+    for k in ("x0", "r_ee0", "waypoint"):
+        if k in meta:
+            meta[k] = np.array(meta[k], dtype=float)
+    return desc_from_dict(doc["desc"]), meta
+
+
+FIXTURES = {
+    "cfg1_ur10_demo": "upright_cmd/config/demos/ur10_demo.yaml",
+    "cfg2_thing_demo": "upright_cmd/config/demos/thing_demo.yaml",
+    "cfg3_thing_box_arch": "upright_b200_cfg/config/thing_box_arch.yaml",
+    "cfg4_thing_obstacles2": "upright_b200_cfg/config/thing_obstacles2.yaml",
+    "cfg5_thing_robust8": "upright_b200_cfg/config/thing_robust8.yaml",
+}
