@@ -1,0 +1,577 @@
+// upright_b200 — C ABI (include/upright_b200.h) over the CUDA kernels.
+// There is no CPU fallback: without a CUDA device every call fails with
+// UB_E_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ub_solver.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define UB_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(UB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+    } while (0)
+
+template <typename T>
+void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
+    std::memset(&P, 0, sizeof(P));
+    const bool bal = d.balancing_enabled && d.nb > 0;
+    P.nq = d.nq;
+    P.nx = 3 * d.nq;
+    P.nb = bal ? d.nb : 0;
+    P.nc = bal ? d.nc : 0;
+    P.nf = d.nf;
+    P.nfc = bal ? d.nf * d.nc : 0;
+    P.nu = d.nq + P.nfc;
+    P.neq = bal ? 6 * d.nb : 0;
+    P.nfric = (bal && d.nf == 3) ? 5 * d.nc : 0;
+    P.nobs = d.obstacles_enabled ? d.n_pairs : 0;
+    P.nterm = 3 + 2 * d.nq;
+    P.N = d.N;
+    P.nsph = d.obstacles_enabled ? d.n_spheres : 0;
+    P.npairs = P.nobs;
+    P.nz = P.nu + P.nx;
+    P.nbox_u = P.nfc > 0 ? P.nu : P.nq;
+    P.nrow = P.nbox_u + P.nx + P.nfric + P.nobs;
+    P.sqp_iters = d.sqp_iteration;
+    P.qp_iter_max = d.qp_iter_max;
+    P.soft_u = d.slacks.enabled && d.slacks.input_box;
+    P.soft_x = d.slacks.enabled && d.slacks.state_box;
+    P.soft_poly = d.slacks.enabled && d.slacks.poly_ineq;
+    P.balancing = bal;
+    P.dt = T(d.dt);
+    P.Z = T(d.slacks.upper_L2_penalty > 0 ? d.slacks.upper_L2_penalty : 100.0);
+    P.rho_hard = T(d.rho_hard);
+    P.mu0 = T(d.qp_mu0);
+    P.thr0 = T(d.qp_thr0);
+    P.mu_target = T(d.qp_mu_target);
+    P.qp_tol = T(d.qp_tol);
+    P.reg_input = T(d.reg_input);
+    P.eps_hard = T(1e-6);
+    P.alpha_decay = T(d.alpha_decay);
+    P.alpha_min = T(d.alpha_min);
+    P.g_max = T(d.g_max);
+    P.g_min = T(d.g_min);
+    P.gamma_c = T(d.gamma_c);
+    P.armijo = T(d.armijo_factor);
+    P.delta_tol = T(d.delta_tol);
+    P.cost_tol = T(d.cost_tol);
+    for (int i = 0; i < d.nq; ++i) {
+        P.jtype[i] = d.joints[i].type;
+        for (int j = 0; j < 9; ++j) P.jR[i][j] = T(d.joints[i].R[j]);
+        for (int j = 0; j < 3; ++j) {
+            P.jp[i][j] = T(d.joints[i].p[j]);
+            P.jaxis[i][j] = T(d.joints[i].axis[j]);
+        }
+        P.Rd[i] = T(d.input_weight[i]);
+        P.ulb[i] = T(d.input_lb[i]);
+        P.uub[i] = T(d.input_ub[i]);
+    }
+    for (int j = 0; j < 9; ++j) P.toolR[j] = T(d.tool_R[j]);
+    for (int j = 0; j < 3; ++j) {
+        P.toolp[j] = T(d.tool_p[j]);
+        P.grav[j] = T(d.gravity[j]);
+        P.Wd[j] = T(d.ee_weight[j]);
+    }
+    for (int i = 0; i < P.nx; ++i) {
+        P.Qd[i] = T(d.state_weight[i]);
+        P.xd[i] = T(d.xd[i]);
+        P.xlb[i] = T(d.state_lb[i]);
+        P.xub[i] = T(d.state_ub[i]);
+    }
+    P.fw = T(d.force_weight);
+    P.flb = T(d.force_lb);
+    P.fub = T(d.force_ub);
+    for (int b = 0; b < d.nb; ++b)
+        for (int j = 0; j < UB_BODY_PARAMS; ++j) P.body[b][j] = T(d.body_params[b][j]);
+    for (int c = 0; c < d.nc; ++c) {
+        const ub_contact_t& cc = d.contacts[c];
+        P.cb1[c] = cc.body1;
+        P.cb2[c] = cc.body2;
+        P.cmu[c] = T(cc.mu);
+        for (int j = 0; j < 3; ++j) {
+            P.cr1[c][j] = T(cc.r_co_o1[j]);
+            P.cr2[c][j] = T(cc.r_co_o2[j]);
+            P.cn[c][j] = T(cc.normal[j]);
+        }
+        for (int j = 0; j < 6; ++j) P.cspan[c][j] = T(cc.span[j]);
+    }
+    for (int s = 0; s < d.n_spheres; ++s) {
+        P.slink[s] = d.spheres[s].link;
+        P.srad[s] = T(d.spheres[s].radius);
+        for (int j = 0; j < 3; ++j) P.soff[s][j] = T(d.spheres[s].offset[j]);
+    }
+    for (int i = 0; i < d.n_pairs; ++i) {
+        P.pa[i] = d.pairs[i].a;
+        P.pb[i] = d.pairs[i].b;
+    }
+    P.dmin = T(d.minimum_distance);
+}
+
+template <typename T>
+ub::Layout make_layout(const ub::DevProblem<T>& P) {
+    ub::Layout L;
+    std::memset(&L, 0, sizeof(L));
+    const int N = P.N, nx = P.nx, nu = P.nu, nz = P.nz, nq = P.nq;
+    int o = 0;
+    auto take = [&](int n) {
+        const int at = o;
+        o += (n + 3) / 4 * 4;
+        return at;
+    };
+    L.ldm = nz | 1;
+    L.ldf = nu | 1;
+    L.Z = take((N + 1) * nz);
+    L.DZ = take((N + 1) * nz);
+    L.GAP = take(N * nx);
+    L.LG = take(N * P.neq);
+    L.LCT = take(N * nx * P.neq);
+    L.LR = take((N + 1) * 3);
+    L.LJP = take((N + 1) * 3 * nq);
+    L.LHO = take((N + 1) * P.nobs);
+    L.LJO = take((N + 1) * P.nobs * nq);
+    L.DF = take(P.neq * P.nfc);
+    L.RHOE = take(N * P.neq);
+    L.YE = take(N * P.neq);
+    L.RHOT = take(P.nterm);
+    L.YT = take(P.nterm);
+    L.TT = take((N + 1) * P.nrow * 2);
+    L.LAM = take((N + 1) * P.nrow * 2);
+    L.DTT = take((N + 1) * P.nrow * 2);
+    L.DLAM = take((N + 1) * P.nrow * 2);
+    L.VAL = take(4);
+    L.FAC = take(N * nz * L.ldf);
+    L.WF = take(N * nu);
+    L.XN = take((N + 1) * nx);
+    L.UN = take(N * nu);
+    L.total = o;
+    int s = 0;
+    auto stake = [&](int n) {
+        const int at = s;
+        s += (n + 3) / 4 * 4;
+        return at;
+    };
+    L.sM = stake(nz * L.ldm);
+    L.sP = stake(nx * nx);
+    L.sPv = stake(nx);
+    const int sa_rows = P.neq > 3 ? P.neq : 3;
+    L.sSA = stake(sa_rows * nz);
+    L.sV = stake(5 * nz + 64);
+    L.s_total = s;
+    return L;
+}
+
+}  // namespace
+
+struct ub_problem {
+    ub_problem_desc_t desc;
+    ub::DevProblem<float> hf;
+    ub::DevProblem<double> hd;
+    ub::DevProblem<float>* df = nullptr;
+    ub::DevProblem<double>* dd = nullptr;
+    ub::Layout Lf, Ld;
+    int device = 0;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int stop_after = 0;
+    float last_ms = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // cached device buffers for host-pointer mode
+    void* dev_buf = nullptr;
+    size_t dev_buf_bytes = 0;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+namespace {
+
+template <typename T>
+struct Pick;
+template <>
+struct Pick<float> {
+    static const ub::DevProblem<float>* dev(const ub_problem* p) { return p->df; }
+    static const ub::DevProblem<float>& host(const ub_problem* p) { return p->hf; }
+    static const ub::Layout& layout(const ub_problem* p) { return p->Lf; }
+};
+template <>
+struct Pick<double> {
+    static const ub::DevProblem<double>* dev(const ub_problem* p) { return p->dd; }
+    static const ub::DevProblem<double>& host(const ub_problem* p) { return p->hd; }
+    static const ub::Layout& layout(const ub_problem* p) { return p->Ld; }
+};
+
+template <typename T>
+int launch_solve(ub_problem* p, const ub::BatchArgs<T>& A, cudaStream_t stream) {
+    const ub::Layout& L = Pick<T>::layout(p);
+    const size_t pbytes = (sizeof(ub::DevProblem<T>) + 15) / 16 * 16;
+    const size_t per_warp = size_t(L.s_total) * sizeof(T);
+    // warps per CTA: as many as fit in ~100 KB (two CTAs per SM), at most 8
+    int wpc = int((100 * 1024 - pbytes) / per_warp);
+    if (wpc < 1) wpc = 1;
+    if (wpc > 8) wpc = 8;
+    const char* env = std::getenv("UB_WARPS_PER_CTA");
+    if (env) wpc = std::max(1, std::min(8, std::atoi(env)));
+    const size_t smem = pbytes + per_warp * wpc;
+    if (smem > size_t(p->max_smem_optin)) return fail(UB_E_INVALID, "problem too large for shared memory");
+    UB_CUDA(cudaFuncSetAttribute(ub::solve_batch_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int grid = (A.B + wpc - 1) / wpc;
+    ub::solve_batch_kernel<T><<<grid, wpc * 32, smem, stream>>>(Pick<T>::dev(p), L, A, wpc);
+    ++g_launches;
+    UB_CUDA(cudaGetLastError());
+    return UB_OK;
+}
+
+template <typename T>
+int solve_device(ub_problem* p, int B, const void* x0, const void* target, const void* body, void* X, void* U, void* K,
+                 int32_t* status, void* stats, void* ws, int64_t ws_bytes, uint32_t flags, cudaStream_t stream) {
+    const ub::Layout& L = Pick<T>::layout(p);
+    if (ws_bytes < int64_t(B) * L.total * int64_t(sizeof(T))) return fail(UB_E_INVALID, "workspace too small");
+    ub::BatchArgs<T> A;
+    A.x0 = static_cast<const T*>(x0);
+    A.target = static_cast<const T*>(target);
+    A.body = static_cast<const T*>(body);
+    A.X = static_cast<T*>(X);
+    A.U = static_cast<T*>(U);
+    A.K = static_cast<T*>(K);
+    A.status = status;
+    A.stats = static_cast<T*>(stats);
+    A.ws = static_cast<T*>(ws);
+    A.B = B;
+    A.warm = (flags & UB_WARM_START) ? 1 : 0;
+    A.stop_after = p->stop_after;
+    UB_CUDA(cudaEventRecord(p->ev0, stream));
+    int rc = launch_solve<T>(p, A, stream);
+    if (rc != UB_OK) return rc;
+    UB_CUDA(cudaEventRecord(p->ev1, stream));
+    return UB_OK;
+}
+
+// Host-pointer mode: double in/out, conversion + copies inside the call.
+template <typename T>
+int solve_host(ub_problem* p, int B, const double* x0, const double* target, const double* body, double* X, double* U,
+               double* K, int32_t* status, double* stats, uint32_t flags, cudaStream_t stream) {
+    const ub::DevProblem<T>& P = Pick<T>::host(p);
+    const ub::Layout& L = Pick<T>::layout(p);
+    const size_t n_x0 = size_t(B) * P.nx, n_tg = size_t(B) * (P.N + 1) * 3, n_bd = body ? size_t(B) * P.nb * UB_BODY_PARAMS : 0;
+    const size_t n_X = size_t(B) * (P.N + 1) * P.nx, n_U = size_t(B) * P.N * P.nu;
+    const size_t n_K = K ? size_t(B) * P.N * P.nu * P.nx : 0, n_st = size_t(B) * UB_STATS;
+    const size_t n_ws = size_t(B) * L.total;
+    const size_t n_in = n_x0 + n_tg + n_bd, n_io = n_X + n_U;
+    const size_t elems = n_in + n_io + n_K + n_st + n_ws;
+    const size_t bytes = elems * sizeof(T) + size_t(B) * sizeof(int32_t) + 256;
+    if (bytes > p->dev_buf_bytes) {
+        if (p->dev_buf) cudaFree(p->dev_buf);
+        p->dev_buf = nullptr;
+        p->dev_buf_bytes = 0;
+        if (cudaMalloc(&p->dev_buf, bytes) != cudaSuccess) return fail(UB_E_ALLOC, "cudaMalloc failed for batch buffers");
+        p->dev_buf_bytes = bytes;
+    }
+    const size_t stage_elems = n_in + n_io + n_K + n_st;
+    const size_t pin_bytes = stage_elems * sizeof(T) + size_t(B) * sizeof(int32_t) + 256;
+    if (pin_bytes > p->pinned_bytes) {
+        if (p->pinned) cudaFreeHost(p->pinned);
+        p->pinned = nullptr;
+        p->pinned_bytes = 0;
+        if (cudaMallocHost(&p->pinned, pin_bytes) != cudaSuccess) return fail(UB_E_ALLOC, "cudaMallocHost failed");
+        p->pinned_bytes = pin_bytes;
+    }
+    T* h = static_cast<T*>(p->pinned);
+    T* d = static_cast<T*>(p->dev_buf);
+    // staging order: x0 | target | body | X | U | K | stats   (device adds workspace, status)
+    size_t o = 0;
+    for (size_t i = 0; i < n_x0; ++i) h[o + i] = T(x0[i]);
+    o += n_x0;
+    for (size_t i = 0; i < n_tg; ++i) h[o + i] = T(target[i]);
+    o += n_tg;
+    for (size_t i = 0; i < n_bd; ++i) h[o + i] = T(body[i]);
+    o += n_bd;
+    const size_t oX = o;
+    if (flags & UB_WARM_START) {
+        for (size_t i = 0; i < n_X; ++i) h[oX + i] = T(X[i]);
+        for (size_t i = 0; i < n_U; ++i) h[oX + n_X + i] = T(U[i]);
+        UB_CUDA(cudaMemcpyAsync(d, h, (n_in + n_io) * sizeof(T), cudaMemcpyHostToDevice, stream));
+    } else {
+        UB_CUDA(cudaMemcpyAsync(d, h, n_in * sizeof(T), cudaMemcpyHostToDevice, stream));
+    }
+    T* d_x0 = d;
+    T* d_tg = d + n_x0;
+    T* d_bd = body ? d + n_x0 + n_tg : nullptr;
+    T* d_X = d + oX;
+    T* d_U = d_X + n_X;
+    T* d_K = K ? d_U + n_U : nullptr;
+    T* d_st = d_U + n_U + n_K;
+    T* d_ws = d_st + n_st;
+    int32_t* d_status = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_ws + n_ws) + 64 - (reinterpret_cast<uintptr_t>(d_ws + n_ws) % 64));
+    int rc = solve_device<T>(p, B, d_x0, d_tg, d_bd, d_X, d_U, d_K, d_status, d_st, d_ws, int64_t(n_ws * sizeof(T)),
+                             flags | UB_PTRS_DEVICE, stream);
+    if (rc != UB_OK) return rc;
+    int32_t* h_status = reinterpret_cast<int32_t*>(h + stage_elems);
+    UB_CUDA(cudaMemcpyAsync(h + oX, d_X, (n_io + n_K + n_st) * sizeof(T), cudaMemcpyDeviceToHost, stream));
+    UB_CUDA(cudaMemcpyAsync(h_status, d_status, size_t(B) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    UB_CUDA(cudaStreamSynchronize(stream));
+    for (size_t i = 0; i < n_X; ++i) X[i] = double(h[oX + i]);
+    for (size_t i = 0; i < n_U; ++i) U[i] = double(h[oX + n_X + i]);
+    for (size_t i = 0; i < n_K; ++i) K[i] = double(h[oX + n_io + i]);
+    if (stats)
+        for (size_t i = 0; i < n_st; ++i) stats[i] = double(h[oX + n_io + n_K + i]);
+    std::memcpy(status, h_status, size_t(B) * sizeof(int32_t));
+    return UB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ub_last_error(void) { return g_err.c_str(); }
+int ub_version(void) { return 100; }
+int64_t ub_launch_count(void) { return g_launches.load(); }
+
+int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
+    if (!desc || !out) return fail(UB_E_INVALID, "null argument");
+    if (desc->nq < 1 || desc->nq > UB_MAX_JOINTS) return fail(UB_E_INVALID, "nq out of range");
+    if (desc->nb < 0 || desc->nb > UB_MAX_BODIES || desc->nc < 0 || desc->nc > UB_MAX_CONTACTS)
+        return fail(UB_E_INVALID, "too many bodies / contacts");
+    if (desc->nf != 1 && desc->nf != 3) return fail(UB_E_INVALID, "nf must be 1 or 3");
+    if (desc->N < 1 || desc->N > 128) return fail(UB_E_INVALID, "N out of range");
+    if (desc->n_spheres > UB_MAX_SPHERES || desc->n_pairs > UB_MAX_PAIRS) return fail(UB_E_INVALID, "too many spheres / pairs");
+    if (desc->ee_weight[3] != 0 || desc->ee_weight[4] != 0 || desc->ee_weight[5] != 0)
+        return fail(UB_E_INVALID, "end-effector orientation weight is not supported yet");
+    if (desc->qp_method != 0) return fail(UB_E_INVALID, "only qp_method 0 (interior point) exists on the device");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(UB_E_NO_DEVICE, "no CUDA device: upright_b200 has no CPU fallback");
+    ub_problem* p = new ub_problem();
+    p->desc = *desc;
+    convert_problem(*desc, p->hf);
+    convert_problem(*desc, p->hd);
+    p->Lf = make_layout(p->hf);
+    p->Ld = make_layout(p->hd);
+    UB_CUDA(cudaGetDevice(&p->device));
+    UB_CUDA(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
+    UB_CUDA(cudaDeviceGetAttribute(&p->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+    UB_CUDA(cudaMalloc(&p->df, sizeof(p->hf)));
+    UB_CUDA(cudaMalloc(&p->dd, sizeof(p->hd)));
+    UB_CUDA(cudaMemcpy(p->df, &p->hf, sizeof(p->hf), cudaMemcpyHostToDevice));
+    UB_CUDA(cudaMemcpy(p->dd, &p->hd, sizeof(p->hd), cudaMemcpyHostToDevice));
+    UB_CUDA(cudaEventCreate(&p->ev0));
+    UB_CUDA(cudaEventCreate(&p->ev1));
+    *out = p;
+    return UB_OK;
+}
+
+void ub_problem_destroy(ub_problem_t* p) {
+    if (!p) return;
+    if (p->df) cudaFree(p->df);
+    if (p->dd) cudaFree(p->dd);
+    if (p->dev_buf) cudaFree(p->dev_buf);
+    if (p->pinned) cudaFreeHost(p->pinned);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    delete p;
+}
+
+int ub_problem_dims(const ub_problem_t* p, int32_t out[8]) {
+    if (!p) return fail(UB_E_INVALID, "null problem");
+    out[0] = p->hf.nx; out[1] = p->hf.nu; out[2] = p->hf.neq; out[3] = p->hf.nfric + p->hf.nobs;
+    out[4] = p->hf.nterm; out[5] = p->hf.N; out[6] = p->hf.nb; out[7] = p->hf.nc;
+    return UB_OK;
+}
+
+int64_t ub_workspace_bytes(const ub_problem_t* p, int32_t B, uint32_t flags) {
+    if (!p) return 0;
+    return (flags & UB_COMPUTE_F64) ? int64_t(B) * p->Ld.total * 8 : int64_t(B) * p->Lf.total * 4;
+}
+
+// Debug/testing aids (not part of the reference surface): option "stop_after"
+// (0 full solve, 1 after the first linearisation, 2 after the first QP) and the
+// per-problem workspace layout in elements: out[0..23] = Layout offsets, out[23] = total.
+int ub_set_option(ub_problem_t* p, const char* key, int value) {
+    if (!p || !key) return fail(UB_E_INVALID, "null argument");
+    if (std::strcmp(key, "stop_after") == 0) {
+        p->stop_after = value;
+        return UB_OK;
+    }
+    return fail(UB_E_INVALID, std::string("unknown option ") + key);
+}
+int ub_workspace_layout(const ub_problem_t* p, uint32_t flags, int32_t out[32]) {
+    if (!p) return fail(UB_E_INVALID, "null problem");
+    const ub::Layout& L = (flags & UB_COMPUTE_F64) ? p->Ld : p->Lf;
+    static_assert(sizeof(ub::Layout) <= 32 * sizeof(int32_t), "layout export too small");
+    std::memset(out, 0, 32 * sizeof(int32_t));
+    std::memcpy(out, &L, sizeof(L));
+    return UB_OK;
+}
+
+int ub_solve_batch(ub_problem_t* p, int32_t B, const void* x0, const void* target, const void* body_params, void* X,
+                   void* U, void* K, int32_t* status, void* stats, void* workspace, int64_t workspace_bytes,
+                   uint32_t flags, void* cuda_stream) {
+    if (!p || !x0 || !target || !X || !U || !status) return fail(UB_E_INVALID, "null argument");
+    if (B <= 0) return fail(UB_E_INVALID, "B must be positive");
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    UB_CUDA(cudaSetDevice(p->device));
+    const bool f64 = (flags & UB_COMPUTE_F64) != 0;
+    if (flags & UB_PTRS_DEVICE) {
+        if (!workspace) return fail(UB_E_INVALID, "device mode needs a workspace");
+        return f64 ? solve_device<double>(p, B, x0, target, body_params, X, U, K, status, stats, workspace,
+                                          workspace_bytes, flags, stream)
+                   : solve_device<float>(p, B, x0, target, body_params, X, U, K, status, stats, workspace,
+                                         workspace_bytes, flags, stream);
+    }
+    return f64 ? solve_host<double>(p, B, static_cast<const double*>(x0), static_cast<const double*>(target),
+                                    static_cast<const double*>(body_params), static_cast<double*>(X),
+                                    static_cast<double*>(U), static_cast<double*>(K), status,
+                                    static_cast<double*>(stats), flags, stream)
+               : solve_host<float>(p, B, static_cast<const double*>(x0), static_cast<const double*>(target),
+                                   static_cast<const double*>(body_params), static_cast<double*>(X),
+                                   static_cast<double*>(U), static_cast<double*>(K), status,
+                                   static_cast<double*>(stats), flags, stream);
+}
+
+float ub_last_solve_ms(const ub_problem_t* p) {
+    if (!p || !p->ev0) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(p->ev1) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Named probes, batched (controller_python_interface.h:31-88).  fp64, one
+// thread per sample.
+namespace {
+
+enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4 };
+
+__global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int what, int M, int rows,
+                            const double* __restrict__ x, const double* __restrict__ u,
+                            const double* __restrict__ target, const double* __restrict__ body,
+                            double* __restrict__ out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const ub::DevProblem<double>& P = *Pg;
+    const double* xm = x + size_t(m) * P.nx;
+    const double* um = u + size_t(m) * P.nu;
+    const double* bp = body ? body + size_t(m) * P.nb * UB_BODY_PARAMS : &P.body[0][0];
+    double* o = out + size_t(m) * rows;
+    ub::Kin<double> K;
+    ub::KinTan<double> D;
+    double sph[3 * UB_MAX_SPHERES];
+    ub::forward_kinematics<double, false>(P, xm, -1, K, D, P.nobs > 0 ? sph : nullptr, nullptr);
+    const int nq = P.nq;
+    if (what == EV_EEPOS) {
+        o[0] = K.r.x; o[1] = K.r.y; o[2] = K.r.z;
+    } else if (what == EV_OBJDYN) {
+        const double scale = rsqrt(double(6 * P.nb));
+        for (int b = 0; b < P.nb; ++b) {
+            const ub::BodyP<double> Bd = ub::load_body(bp + b * UB_BODY_PARAMS);
+            ub::object_dynamics_state_part<double, false>(P, Bd, K, D, scale, o + 6 * b, nullptr);
+        }
+        // wrench part: compute_object_wrenches (contact_constraints.h:106-157)
+        for (int c = 0; c < P.nc; ++c) {
+            ub::V3<double> f;
+            if (P.nf == 1) f = um[nq + c] * ub::ld3(P.cn[c]);
+            else f = ub::V3<double>(um[nq + 3 * c], um[nq + 3 * c + 1], um[nq + 3 * c + 2]);
+            const int b1 = P.cb1[c], b2 = P.cb2[c];
+            if (b1 >= 0) {
+                const ub::BodyP<double> Bd = ub::load_body(bp + b1 * UB_BODY_PARAMS);
+                const ub::V3<double> tq = ub::cross(ub::ld3(P.cr1[c]) - Bd.com, f);
+                const double s = scale / Bd.m;
+                o[6 * b1] -= s * f.x; o[6 * b1 + 1] -= s * f.y; o[6 * b1 + 2] -= s * f.z;
+                o[6 * b1 + 3] -= s * tq.x; o[6 * b1 + 4] -= s * tq.y; o[6 * b1 + 5] -= s * tq.z;
+            }
+            const ub::BodyP<double> Bd = ub::load_body(bp + b2 * UB_BODY_PARAMS);
+            const ub::V3<double> tq = ub::cross(ub::ld3(P.cr2[c]) - Bd.com, f);
+            const double s = scale / Bd.m;
+            o[6 * b2] += s * f.x; o[6 * b2 + 1] += s * f.y; o[6 * b2 + 2] += s * f.z;
+            o[6 * b2 + 3] += s * tq.x; o[6 * b2 + 4] += s * tq.y; o[6 * b2 + 5] += s * tq.z;
+        }
+    } else if (what == EV_CONTACT) {
+        for (int c = 0; c < P.nc; ++c) {
+            const ub::V3<double> f(um[nq + 3 * c], um[nq + 3 * c + 1], um[nq + 3 * c + 2]);
+            const double fn = ub::dot(ub::ld3(P.cn[c]), f), t0 = ub::dot(ub::ld3(P.cspan[c]), f),
+                         t1 = ub::dot(ub::ld3(P.cspan[c] + 3), f), mu = P.cmu[c];
+            o[5 * c] = fn;
+            o[5 * c + 1] = mu * fn - t0 - t1;
+            o[5 * c + 2] = mu * fn - t0 + t1;
+            o[5 * c + 3] = mu * fn + t0 - t1;
+            o[5 * c + 4] = mu * fn + t0 + t1;
+        }
+    } else if (what == EV_OBST) {
+        for (int i = 0; i < P.nobs; ++i) {
+            const int a = P.pa[i], b = P.pb[i];
+            const ub::V3<double> d(sph[3 * a] - sph[3 * b], sph[3 * a + 1] - sph[3 * b + 1], sph[3 * a + 2] - sph[3 * b + 2]);
+            o[i] = sqrt(ub::dot(d, d)) - (P.srad[a] + P.srad[b] + P.dmin);
+        }
+    } else {  // intermediate cost (not scaled by dt), as ocs2 PythonInterface::cost
+        double c = 0;
+        for (int i = 0; i < P.nx; ++i) c += 0.5 * P.Qd[i] * (xm[i] - P.xd[i]) * (xm[i] - P.xd[i]);
+        for (int i = 0; i < nq; ++i) c += 0.5 * P.Rd[i] * um[i] * um[i];
+        for (int i = 0; i < P.nfc; ++i) c += 0.5 * P.fw * um[nq + i] * um[nq + i];
+        if (target)
+            for (int i = 0; i < 3; ++i) {
+                const double e = K.r[i] - target[3 * m + i];
+                c += 0.5 * P.Wd[i] * e * e;
+            }
+        o[0] = c;
+    }
+}
+
+}  // namespace
+
+extern "C" int ub_eval(ub_problem_t* p, const char* name, int32_t M, const double* x, const double* u,
+                       const double* target, const double* body_params, double* out, int32_t out_capacity,
+                       int32_t* rows_out) {
+    if (!p || !name || !x || !u || !out || M <= 0) return fail(UB_E_INVALID, "bad argument");
+    const ub::DevProblem<double>& P = p->hd;
+    int what, rows;
+    const std::string n(name);
+    if (n == "object_dynamics") { what = EV_OBJDYN; rows = P.neq; }
+    else if (n == "contact_forces") { what = EV_CONTACT; rows = P.nfric; }
+    else if (n == "obstacle_avoidance") { what = EV_OBST; rows = P.nobs; }
+    else if (n == "end_effector_position") { what = EV_EEPOS; rows = 3; }
+    else if (n == "cost") { what = EV_COST; rows = 1; }
+    else return fail(UB_E_INVALID, "unknown probe name " + n);
+    if (rows_out) *rows_out = rows;
+    if (rows == 0) return UB_OK;
+    if (out_capacity < M * rows) return fail(UB_E_INVALID, "output buffer too small");
+    UB_CUDA(cudaSetDevice(p->device));
+    const size_t nx_b = size_t(M) * P.nx * 8, nu_b = size_t(M) * P.nu * 8, tg_b = target ? size_t(M) * 24 : 0,
+                 bd_b = body_params ? size_t(M) * P.nb * UB_BODY_PARAMS * 8 : 0, out_b = size_t(M) * rows * 8;
+    char* d = nullptr;
+    UB_CUDA(cudaMalloc(&d, nx_b + nu_b + tg_b + bd_b + out_b));
+    double* dx = reinterpret_cast<double*>(d);
+    double* du = reinterpret_cast<double*>(d + nx_b);
+    double* dt = target ? reinterpret_cast<double*>(d + nx_b + nu_b) : nullptr;
+    double* db = body_params ? reinterpret_cast<double*>(d + nx_b + nu_b + tg_b) : nullptr;
+    double* dout = reinterpret_cast<double*>(d + nx_b + nu_b + tg_b + bd_b);
+    cudaMemcpy(dx, x, nx_b, cudaMemcpyHostToDevice);
+    cudaMemcpy(du, u, nu_b, cudaMemcpyHostToDevice);
+    if (target) cudaMemcpy(dt, target, tg_b, cudaMemcpyHostToDevice);
+    if (body_params) cudaMemcpy(db, body_params, bd_b, cudaMemcpyHostToDevice);
+    eval_kernel<<<(M + 127) / 128, 128>>>(p->dd, what, M, rows, dx, du, dt, db, dout);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, out_b, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(UB_E_CUDA, cudaGetErrorString(e));
+    return UB_OK;
+}

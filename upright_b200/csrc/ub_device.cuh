@@ -1,0 +1,318 @@
+// upright_b200 — device-side problem description, small vector math and the
+// forward kinematics (values and lane-parallel forward-mode tangents).
+//
+// Mapping: ONE WARP PER MPC INSTANCE.  In the linearisation, lane j of the
+// warp carries d/dx_j of every kinematic quantity (nx = 3*nq <= 27 <= 32
+// lanes), so a whole Jacobian column set is produced by one pass of the chain
+// — the role CppAD's taped Jacobians play in the reference
+// (upright_control/src/constraint/balancing_constraints.cpp:54-56,105-107).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/upright_b200.h"
+
+namespace ub {
+
+constexpr int WARP = 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+template <typename T>
+struct DevProblem {
+    int nq, nx, nu, nfc, neq, nfric, nobs, nterm, nb, nc, nf, N, nsph, npairs;
+    int nz, nbox_u, nrow, sqp_iters, qp_iter_max;
+    int soft_u, soft_x, soft_poly, balancing;
+    T dt, Z, rho_hard, mu0, thr0, mu_target, qp_tol, reg_input, eps_hard;
+    T alpha_decay, alpha_min, g_max, g_min, gamma_c, armijo, delta_tol, cost_tol;
+    int jtype[UB_MAX_JOINTS];
+    T jR[UB_MAX_JOINTS][9], jp[UB_MAX_JOINTS][3], jaxis[UB_MAX_JOINTS][3];
+    T toolR[9], toolp[3], grav[3];
+    T Qd[UB_MAX_NX], Rd[UB_MAX_JOINTS], Wd[3], fw, xd[UB_MAX_NX];
+    T xlb[UB_MAX_NX], xub[UB_MAX_NX], ulb[UB_MAX_JOINTS], uub[UB_MAX_JOINTS], flb, fub;
+    T body[UB_MAX_BODIES][UB_BODY_PARAMS];
+    int cb1[UB_MAX_CONTACTS], cb2[UB_MAX_CONTACTS];
+    T cmu[UB_MAX_CONTACTS], cr1[UB_MAX_CONTACTS][3], cr2[UB_MAX_CONTACTS][3], cn[UB_MAX_CONTACTS][3],
+        cspan[UB_MAX_CONTACTS][6];
+    int slink[UB_MAX_SPHERES];
+    T srad[UB_MAX_SPHERES], soff[UB_MAX_SPHERES][3];
+    int pa[UB_MAX_PAIRS], pb[UB_MAX_PAIRS];
+    T dmin;
+};
+
+// ------------------------------------------------------------------ vectors
+template <typename T>
+struct V3 {
+    T x, y, z;
+    __device__ __forceinline__ V3() : x(0), y(0), z(0) {}
+    __device__ __forceinline__ V3(T a, T b, T c) : x(a), y(b), z(c) {}
+    __device__ __forceinline__ T operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+template <typename T>
+__device__ __forceinline__ V3<T> operator+(const V3<T>& a, const V3<T>& b) { return V3<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T>
+__device__ __forceinline__ V3<T> operator-(const V3<T>& a, const V3<T>& b) { return V3<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T>
+__device__ __forceinline__ V3<T> operator*(T s, const V3<T>& a) { return V3<T>(s * a.x, s * a.y, s * a.z); }
+template <typename T>
+__device__ __forceinline__ T dot(const V3<T>& a, const V3<T>& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T>
+__device__ __forceinline__ V3<T> cross(const V3<T>& a, const V3<T>& b) {
+    return V3<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+template <typename T>
+__device__ __forceinline__ V3<T> ld3(const T* p) { return V3<T>(p[0], p[1], p[2]); }
+
+template <typename T>
+struct M3 {
+    T m[9];
+    __device__ __forceinline__ V3<T> mul(const V3<T>& v) const {
+        return V3<T>(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z,
+                     m[6] * v.x + m[7] * v.y + m[8] * v.z);
+    }
+    __device__ __forceinline__ V3<T> tmul(const V3<T>& v) const {  // R^T v
+        return V3<T>(m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z,
+                     m[2] * v.x + m[5] * v.y + m[8] * v.z);
+    }
+};
+template <typename T>
+__device__ __forceinline__ M3<T> matmul(const M3<T>& A, const T* B) {
+    M3<T> C;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) C.m[3 * i + j] = A.m[3 * i] * B[j] + A.m[3 * i + 1] * B[3 + j] + A.m[3 * i + 2] * B[6 + j];
+    return C;
+}
+template <typename T>
+__device__ __forceinline__ void sincos_t(T a, T* s, T* c);
+template <>
+__device__ __forceinline__ void sincos_t<float>(float a, float* s, float* c) { sincosf(a, s, c); }
+template <>
+__device__ __forceinline__ void sincos_t<double>(double a, double* s, double* c) { sincos(a, s, c); }
+
+template <typename T>
+__device__ __forceinline__ void axis_angle(const V3<T>& u, T th, T* R) {
+    T s, c;
+    sincos_t<T>(th, &s, &c);
+    const T t = T(1) - c;
+    R[0] = c + t * u.x * u.x;
+    R[1] = t * u.x * u.y - s * u.z;
+    R[2] = t * u.x * u.z + s * u.y;
+    R[3] = t * u.x * u.y + s * u.z;
+    R[4] = c + t * u.y * u.y;
+    R[5] = t * u.y * u.z - s * u.x;
+    R[6] = t * u.x * u.z - s * u.y;
+    R[7] = t * u.y * u.z + s * u.x;
+    R[8] = c + t * u.z * u.z;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_min(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// --------------------------------------------------------------- kinematics
+// Tool-frame state: upright::RigidBodyState (upright_core/include/upright_core/types.h:72-85).
+template <typename T>
+struct Kin {
+    V3<T> r, v, w, a, al;
+    M3<T> C;
+};
+// Tangent of the above along one direction; rotation tangents are world-frame
+// angular vectors dth with dC = skew(dth) C.
+template <typename T>
+struct KinTan {
+    V3<T> r, v, w, a, al, th;
+};
+
+// Forward kinematics with classical accelerations (what the reference obtains
+// from ocs2::PinocchioEndEffectorKinematicsCppAd,
+// upright_control/src/constraint/balancing_constraints.cpp:15-30) on the
+// chain of upright_control/include/upright_control/util.h:15-65.
+// If TANGENT, also propagates d/dx_dir (dir = this lane's direction; dir >= nx
+// propagates zeros).  Sphere centres (and tangents) are written to sph / dsph
+// (3 values per sphere, registers of this lane) when non-null.
+template <typename T, bool TANGENT>
+__device__ void forward_kinematics(const DevProblem<T>& P, const T* __restrict__ x, int dir, Kin<T>& K, KinTan<T>& D,
+                                   T* sph, T* dsph) {
+    const int nq = P.nq;
+    M3<T> R;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R.m[i] = (i % 4 == 0) ? T(1) : T(0);
+    V3<T> p, v, w, a, al;
+    V3<T> dp, dv, dw, da, dal, dth;
+
+    auto offset_frame = [&](const T* Rt, const T* pt) {
+        const V3<T> ro = R.mul(ld3(pt));
+        const V3<T> wro = cross(w, ro);
+        if (TANGENT) {
+            const V3<T> dro = cross(dth, ro);
+            dp = dp + dro;
+            dv = dv + cross(dw, ro) + cross(w, dro);
+            da = da + cross(dal, ro) + cross(al, dro) + cross(dw, wro) + cross(w, cross(dw, ro) + cross(w, dro));
+        }
+        p = p + ro;
+        v = v + wro;
+        a = a + cross(al, ro) + cross(w, wro);
+        R = matmul(R, Rt);
+    };
+    auto attach = [&](int link) {
+        if (sph == nullptr) return;
+        for (int s = 0; s < P.nsph; ++s) {
+            if (P.slink[s] != link) continue;
+            const V3<T> o = R.mul(ld3(P.soff[s]));
+            sph[3 * s] = p.x + o.x;
+            sph[3 * s + 1] = p.y + o.y;
+            sph[3 * s + 2] = p.z + o.z;
+            if (TANGENT) {
+                const V3<T> d = dp + cross(dth, o);
+                dsph[3 * s] = d.x;
+                dsph[3 * s + 1] = d.y;
+                dsph[3 * s + 2] = d.z;
+            }
+        }
+    };
+    if (sph != nullptr)
+        for (int s = 0; s < P.nsph; ++s)
+            if (P.slink[s] < 0) {
+                sph[3 * s] = P.soff[s][0];
+                sph[3 * s + 1] = P.soff[s][1];
+                sph[3 * s + 2] = P.soff[s][2];
+                if (TANGENT) dsph[3 * s] = dsph[3 * s + 1] = dsph[3 * s + 2] = T(0);
+            }
+
+    for (int i = 0; i < nq; ++i) {
+        offset_frame(P.jR[i], P.jp[i]);
+        const V3<T> ul = ld3(P.jaxis[i]);
+        const V3<T> z = R.mul(ul);
+        const T qi = x[i], qd = x[nq + i], qdd = x[2 * nq + i];
+        const T dq = (TANGENT && dir == i) ? T(1) : T(0);
+        const T dqd = (TANGENT && dir == nq + i) ? T(1) : T(0);
+        const T dqdd = (TANGENT && dir == 2 * nq + i) ? T(1) : T(0);
+        if (P.jtype[i] == UB_JOINT_REVOLUTE) {
+            const V3<T> wz = cross(w, z);
+            if (TANGENT) {
+                const V3<T> dz = cross(dth, z);
+                dal = dal + dqdd * z + qdd * dz + dqd * wz + qd * (cross(dw, z) + cross(w, dz));
+                dw = dw + dqd * z + qd * dz;
+                dth = dth + dq * z;
+            }
+            al = al + qdd * z + qd * wz;
+            w = w + qd * z;
+            T Rq[9];
+            axis_angle(ul, qi, Rq);
+            R = matmul(R, Rq);
+        } else {
+            const V3<T> d = qi * z;
+            const V3<T> wz = cross(w, z);
+            const V3<T> wd = cross(w, d);
+            if (TANGENT) {
+                const V3<T> dz = cross(dth, z);
+                const V3<T> dd = dq * z + qi * dz;
+                da = da + dqdd * z + qdd * dz + T(2) * (dqd * wz + qd * (cross(dw, z) + cross(w, dz))) + cross(dal, d) +
+                     cross(al, dd) + cross(dw, wd) + cross(w, cross(dw, d) + cross(w, dd));
+                dv = dv + dqd * z + qd * dz + cross(dw, d) + cross(w, dd);
+                dp = dp + dd;
+            }
+            a = a + qdd * z + T(2) * qd * wz + cross(al, d) + cross(w, wd);
+            v = v + qd * z + wd;
+            p = p + d;
+        }
+        attach(i);
+    }
+    offset_frame(P.toolR, P.toolp);
+    attach(nq);
+    K.r = p;
+    K.v = v;
+    K.w = w;
+    K.a = a;
+    K.al = al;
+    K.C = R;
+    if (TANGENT) {
+        D.r = dp;
+        D.v = dv;
+        D.w = dw;
+        D.a = da;
+        D.al = dal;
+        D.th = dth;
+    }
+}
+
+// Rigid body inertial parameters unpacked from [m, m*com, vech(I)]
+// (upright_core/include/upright_core/rigid_body.h:36-46).
+template <typename T>
+struct BodyP {
+    T m;
+    V3<T> com;
+    T I[6];  // xx xy xz yy yz zz
+    __device__ __forceinline__ V3<T> Imul(const V3<T>& v) const {
+        return V3<T>(I[0] * v.x + I[1] * v.y + I[2] * v.z, I[1] * v.x + I[3] * v.y + I[4] * v.z,
+                     I[2] * v.x + I[4] * v.y + I[5] * v.z);
+    }
+};
+template <typename T>
+__device__ __forceinline__ BodyP<T> load_body(const T* p) {
+    BodyP<T> b;
+    b.m = p[0];
+    const T inv = T(1) / p[0];
+    b.com = V3<T>(p[1] * inv, p[2] * inv, p[3] * inv);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) b.I[i] = p[4 + i];
+    return b;
+}
+
+// State-dependent part of the object-dynamics rows of one body and (if
+// TANGENT) its derivative along this lane's direction:
+//   force  rows = scale * C_ew (a + ddC com - g)          (f_sum/m added via Df)
+//   torque rows = scale * (w_e x I w_e + I al_e) / m
+// upright_core/include/upright_core/contact_constraints.h:79-102 with
+// dC_dtt of util.h:37-50 and the 1/sqrt(6 nb) of balancing_constraints.cpp:140-151.
+template <typename T, bool TANGENT>
+__device__ __forceinline__ void object_dynamics_state_part(const DevProblem<T>& P, const BodyP<T>& B, const Kin<T>& K,
+                                                           const KinTan<T>& D, T scale, T* g6, T* dg6) {
+    const V3<T> grav = ld3(P.grav);
+    const V3<T> c = K.C.mul(B.com);
+    const V3<T> wc = cross(K.w, c);
+    const V3<T> t1 = K.a + cross(K.al, c) + cross(K.w, wc) - grav;
+    const V3<T> gi = K.C.tmul(t1);
+    const V3<T> we = K.C.tmul(K.w), ale = K.C.tmul(K.al);
+    const V3<T> Iwe = B.Imul(we);
+    const V3<T> tau = cross(we, Iwe) + B.Imul(ale);
+    const T sm = scale / B.m;
+    g6[0] = scale * gi.x;
+    g6[1] = scale * gi.y;
+    g6[2] = scale * gi.z;
+    g6[3] = sm * tau.x;
+    g6[4] = sm * tau.y;
+    g6[5] = sm * tau.z;
+    if (TANGENT) {
+        const V3<T> dc = cross(D.th, c);
+        const V3<T> dt1 = D.a + cross(D.al, c) + cross(K.al, dc) + cross(D.w, wc) + cross(K.w, cross(D.w, c) + cross(K.w, dc));
+        const V3<T> dgi = K.C.tmul(dt1 - cross(D.th, t1));
+        const V3<T> dwe = K.C.tmul(D.w - cross(D.th, K.w));
+        const V3<T> dale = K.C.tmul(D.al - cross(D.th, K.al));
+        const V3<T> dtau = cross(dwe, Iwe) + cross(we, B.Imul(dwe)) + B.Imul(dale);
+        dg6[0] = scale * dgi.x;
+        dg6[1] = scale * dgi.y;
+        dg6[2] = scale * dgi.z;
+        dg6[3] = sm * dtau.x;
+        dg6[4] = sm * dtau.y;
+        dg6[5] = sm * dtau.z;
+    }
+}
+
+}  // namespace ub

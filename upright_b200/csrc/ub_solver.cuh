@@ -1,0 +1,1207 @@
+// upright_b200 — the batched MPC solve kernel: one warp per MPC instance.
+//
+// Replaces, for B independent instances, the body of
+// `ControllerInterface::advanceMpc()` (upright_control/src/pybindings.cpp:376,
+// solver constructed at upright_control/src/controller_interface.cpp:395-398):
+//   per SQP iteration:  linearise all knots (lane = d/dx_j tangent direction)
+//                       -> OCP-QP by a primal-dual interior point method whose
+//                          Newton systems are Riccati recursions held in shared
+//                          memory (structured A = A3 (x) I, B = B3 (x) I)
+//                       -> filter line search on the true nonlinear functions
+//                          (lane = knot).
+// The algorithm (row families, soft/hard handling, constants) is specified in
+// DESIGN.md §4 and is the same one oracle/oracle.cpp implements in fp64 with
+// dense linear algebra.
+#pragma once
+#include <math_constants.h>
+
+#include "ub_device.cuh"
+
+namespace ub {
+
+// Per-problem workspace layout in units of T (filled on the host).
+struct Layout {
+    int Z, DZ, GAP, LG, LCT, LR, LJP, LHO, LJO, DF, RHOE, YE, RHOT, YT, TT, LAM, DTT, DLAM, VAL, FAC, WF, XN, UN;
+    int total;
+    // shared memory (units of T, per warp)
+    int sM, sP, sPv, sSA, sV, s_total, ldm, ldf;
+};
+
+template <typename T>
+struct BatchArgs {
+    const T* x0;      // [B, nx]
+    const T* target;  // [B, N+1, 3]
+    const T* body;    // [B, nb, 10] or null
+    T* X;             // [B, N+1, nx]
+    T* U;             // [B, N, nu]
+    T* K;             // [B, N, nu, nx] or null
+    int32_t* status;  // [B]
+    T* stats;         // [B, UB_STATS] or null
+    T* ws;            // [B, layout.total]
+    int B;
+    int warm;
+    int stop_after;   // debug: 0 = full solve, 1 = stop after first linearisation, 2 = after first QP
+};
+
+template <typename T>
+__device__ __forceinline__ T tinf() { return T(1e30); }
+
+template <typename T>
+struct Perf {
+    T cost, dyn, eq, ineq, max_eq, min_margin;
+    __device__ __forceinline__ T violation() const { return sqrt(dyn + eq + ineq); }
+};
+
+template <typename T>
+struct Solver {
+    const DevProblem<T>& P;
+    const Layout& L;
+    const int lane;
+    // batch data of this instance
+    const T* x0;
+    const T* target;
+    const T* body;
+    T* X;
+    T* U;
+    T* ws;
+    // shared memory of this warp
+    T* sM;
+    T* sP;
+    T* sPv;
+    T* sSA;
+    T* sV;
+
+    __device__ Solver(const DevProblem<T>& P_, const Layout& L_, int lane_) : P(P_), L(L_), lane(lane_) {}
+
+    // ------------------------------------------------------------ row model
+    // Inequality rows of a stage, in this order:
+    //   [0, nbox_u)                    input box  (k < N)     controller_interface.cpp:165-169,330-356
+    //   [nbox_u, +nx)                  state box  (k >= 1)    controller_interface.cpp:157-163
+    //   [.., +nfric)                   friction   (k < N)     contact_constraints.h:49-77
+    //   [.., +nobs)                    obstacles  (1<=k<N)    controller_interface.cpp:450-481
+    __device__ __forceinline__ int row_family(int r) const {
+        if (r < P.nbox_u) return 0;
+        if (r < P.nbox_u + P.nx) return 1;
+        if (r < P.nbox_u + P.nx + P.nfric) return 2;
+        return 3;
+    }
+    __device__ __forceinline__ bool row_valid(int k, int fam) const {
+        switch (fam) {
+            case 0: return k < P.N;
+            case 1: return k >= 1;
+            case 2: return k < P.N;
+            default: return k >= 1 && k < P.N;
+        }
+    }
+    __device__ __forceinline__ bool row_soft(int fam) const {
+        return fam == 0 ? P.soft_u : (fam == 1 ? P.soft_x : P.soft_poly);
+    }
+    __device__ __forceinline__ T row_eps(int fam) const { return row_soft(fam) ? T(1) / P.Z : P.eps_hard; }
+    // friction row coefficients on the 3 force components of contact c
+    __device__ __forceinline__ V3<T> fric_coeff(int c, int which) const {
+        const V3<T> n = ld3(P.cn[c]), s0 = ld3(P.cspan[c]), s1 = ld3(P.cspan[c] + 3);
+        if (which == 0) return n;
+        const T a = (which >= 3) ? T(1) : T(-1), b = (which == 2 || which == 4) ? T(1) : T(-1);
+        return P.cmu[c] * n + a * s0 + b * s1;
+    }
+    // value of ineq row r of stage k at the QP iterate z (stage vector zk = [du; dx]),
+    // and bounds.  Uses the linearisation stored in the workspace.
+    __device__ T row_value(int k, int r, int fam, const T* zk, T* lb, T* ub) const {
+        const int nq = P.nq, nu = P.nu;
+        if (fam == 0) {
+            const T u = U[k * nu + r];
+            *lb = (r < nq ? P.ulb[r] : P.flb) - u;
+            *ub = (r < nq ? P.uub[r] : P.fub) - u;
+            return zk[r];
+        }
+        if (fam == 1) {
+            const int i = r - P.nbox_u;
+            const T x = X[k * P.nx + i];
+            *lb = P.xlb[i] - x;
+            *ub = P.xub[i] - x;
+            return zk[nu + i];
+        }
+        *lb = T(0);
+        *ub = tinf<T>();
+        if (fam == 2) {
+            const int i = r - P.nbox_u - P.nx, c = i / 5;
+            const V3<T> a = fric_coeff(c, i % 5);
+            const T* f = U + k * nu + nq + 3 * c;
+            const T* df = zk + nq + 3 * c;
+            return a.x * (f[0] + df[0]) + a.y * (f[1] + df[1]) + a.z * (f[2] + df[2]);
+        }
+        const int i = r - P.nbox_u - P.nx - P.nfric;
+        const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
+        T v = ws[L.LHO + k * P.nobs + i];
+        for (int j = 0; j < nq; ++j) v += J[j] * zk[nu + j];
+        return v;
+    }
+    // a_r . d  for a stage direction d = [du; dx]
+    __device__ T row_dot(int k, int r, int fam, const T* d) const {
+        const int nq = P.nq, nu = P.nu;
+        if (fam == 0) return d[r];
+        if (fam == 1) return d[nu + r - P.nbox_u];
+        if (fam == 2) {
+            const int i = r - P.nbox_u - P.nx, c = i / 5;
+            const V3<T> a = fric_coeff(c, i % 5);
+            const T* df = d + nq + 3 * c;
+            return a.x * df[0] + a.y * df[1] + a.z * df[2];
+        }
+        const int i = r - P.nbox_u - P.nx - P.nfric;
+        const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
+        T v = 0;
+        for (int j = 0; j < nq; ++j) v += J[j] * d[nu + j];
+        return v;
+    }
+    // vec += w * a_r   (vec indexed like the stage vector); called by ONE lane per row,
+    // rows may collide on entries -> atomics on shared memory
+    __device__ void row_axpy(int k, int r, int fam, T w, T* vec) const {
+        const int nq = P.nq, nu = P.nu;
+        if (fam == 0) {
+            atomicAdd(vec + r, w);
+        } else if (fam == 1) {
+            atomicAdd(vec + nu + r - P.nbox_u, w);
+        } else if (fam == 2) {
+            const int i = r - P.nbox_u - P.nx, c = i / 5;
+            const V3<T> a = fric_coeff(c, i % 5);
+            atomicAdd(vec + nq + 3 * c, w * a.x);
+            atomicAdd(vec + nq + 3 * c + 1, w * a.y);
+            atomicAdd(vec + nq + 3 * c + 2, w * a.z);
+        } else {
+            const int i = r - P.nbox_u - P.nx - P.nfric;
+            const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
+            for (int j = 0; j < nq; ++j) atomicAdd(vec + nu + j, w * J[j]);
+        }
+    }
+    __device__ __forceinline__ int nz_of(int k) const { return k < P.N ? P.nz : P.nx; }
+    // stage vectors are stored with stride nz as [du (nu); dx (nx)]; the terminal
+    // stage uses the same slots (its du part is unused and kept at zero)
+    __device__ __forceinline__ T* Zk(int k) const { return ws + L.Z + k * P.nz; }
+    __device__ __forceinline__ T* DZk(int k) const { return ws + L.DZ + k * P.nz; }
+
+    // number of equality rows of stage k and their data
+    __device__ __forceinline__ int neq_of(int k) const { return k < P.N ? P.neq : P.nterm; }
+
+    // -------------------------------------------------------- linearisation
+    // Df: d g / d f, constant in x (compute_object_wrenches, contact_constraints.h:106-157)
+    __device__ void build_Df() {
+        const T scale = rsqrt(T(6 * P.nb));
+        T* Df = ws + L.DF;
+        for (int idx = lane; idx < P.neq * P.nfc; idx += WARP) Df[idx] = T(0);
+        __syncwarp();
+        for (int j = lane; j < P.nfc; j += WARP) {
+            const int c = j / P.nf, comp = j % P.nf;
+            V3<T> e;
+            if (P.nf == 1) e = ld3(P.cn[c]);
+            else e = V3<T>(comp == 0 ? T(1) : T(0), comp == 1 ? T(1) : T(0), comp == 2 ? T(1) : T(0));
+            const int b1 = P.cb1[c], b2 = P.cb2[c];
+            if (b1 >= 0) {
+                const BodyP<T> Bd = load_body(body + b1 * UB_BODY_PARAMS);
+                const V3<T> tq = cross(ld3(P.cr1[c]) - Bd.com, e);
+                const T s = -scale / Bd.m;
+                Df[(6 * b1 + 0) * P.nfc + j] = s * e.x;
+                Df[(6 * b1 + 1) * P.nfc + j] = s * e.y;
+                Df[(6 * b1 + 2) * P.nfc + j] = s * e.z;
+                Df[(6 * b1 + 3) * P.nfc + j] = s * tq.x;
+                Df[(6 * b1 + 4) * P.nfc + j] = s * tq.y;
+                Df[(6 * b1 + 5) * P.nfc + j] = s * tq.z;
+            }
+            {
+                const BodyP<T> Bd = load_body(body + b2 * UB_BODY_PARAMS);
+                const V3<T> tq = cross(ld3(P.cr2[c]) - Bd.com, T(-1) * e);
+                const T s = -scale / Bd.m;
+                Df[(6 * b2 + 0) * P.nfc + j] = -s * e.x;
+                Df[(6 * b2 + 1) * P.nfc + j] = -s * e.y;
+                Df[(6 * b2 + 2) * P.nfc + j] = -s * e.z;
+                Df[(6 * b2 + 3) * P.nfc + j] = s * tq.x;
+                Df[(6 * b2 + 4) * P.nfc + j] = s * tq.y;
+                Df[(6 * b2 + 5) * P.nfc + j] = s * tq.z;
+            }
+        }
+        __syncwarp();
+    }
+
+    // Linearise every knot around (X, U): lane j carries d/dx_j.
+    // Writes LG [k][neq] (g value incl. Df f), LCT [k][nx][neq] (column-major C),
+    // LR [k][3], LJP [k][3][nq], LHO [k][nobs], LJO [k][nobs][nq], GAP [k][nx].
+    __device__ void linearize() {
+        const int nq = P.nq, nx = P.nx, nu = P.nu, N = P.N;
+        const T scale = rsqrt(T(6 * max(P.nb, 1)));
+        T sph[3 * UB_MAX_SPHERES], dsph[3 * UB_MAX_SPHERES];
+        for (int k = 0; k <= N; ++k) {
+            const T* x = X + k * nx;
+            Kin<T> Kn;
+            KinTan<T> D;
+            forward_kinematics<T, true>(P, x, lane, Kn, D, P.nobs > 0 ? sph : nullptr, dsph);
+            if (lane == 0) {
+                ws[L.LR + 3 * k] = Kn.r.x;
+                ws[L.LR + 3 * k + 1] = Kn.r.y;
+                ws[L.LR + 3 * k + 2] = Kn.r.z;
+            }
+            if (lane < nq) {
+                T* Jp = ws + L.LJP + k * 3 * nq;
+                Jp[lane] = D.r.x;
+                Jp[nq + lane] = D.r.y;
+                Jp[2 * nq + lane] = D.r.z;
+            }
+            if (k < N && P.neq > 0) {
+                for (int b = 0; b < P.nb; ++b) {
+                    const BodyP<T> Bd = load_body(body + b * UB_BODY_PARAMS);
+                    T g6[6], dg6[6];
+                    object_dynamics_state_part<T, true>(P, Bd, Kn, D, scale, g6, dg6);
+                    if (lane < nx) {
+                        T* CT = ws + L.LCT + (k * nx + lane) * P.neq + 6 * b;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) CT[i] = dg6[i];
+                    }
+                    if (lane < 6) {
+                        // g = state part + Df f
+                        T gv = g6[0];
+#pragma unroll
+                        for (int i = 1; i < 6; ++i) gv = (lane == i) ? g6[i] : gv;
+                        const T* Dfr = ws + L.DF + (6 * b + lane) * P.nfc;
+                        const T* f = U + k * nu + nq;
+                        for (int j = 0; j < P.nfc; ++j) gv += Dfr[j] * f[j];
+                        ws[L.LG + k * P.neq + 6 * b + lane] = gv;
+                    }
+                }
+            }
+            if (P.nobs > 0) {
+                for (int i = 0; i < P.nobs; ++i) {
+                    const int a = P.pa[i], bb = P.pb[i];
+                    const V3<T> d(sph[3 * a] - sph[3 * bb], sph[3 * a + 1] - sph[3 * bb + 1], sph[3 * a + 2] - sph[3 * bb + 2]);
+                    const T dist = sqrt(dot(d, d));
+                    const V3<T> dd(dsph[3 * a] - dsph[3 * bb], dsph[3 * a + 1] - dsph[3 * bb + 1],
+                                   dsph[3 * a + 2] - dsph[3 * bb + 2]);
+                    if (lane == 0) ws[L.LHO + k * P.nobs + i] = dist - (P.srad[a] + P.srad[bb] + P.dmin);
+                    if (lane < nq) ws[L.LJO + (k * P.nobs + i) * nq + lane] = dot(d, dd) / dist;
+                }
+            }
+            // dynamics gap b_k = A x_k + B u_k - x_{k+1}  (exact triple integrator, system_dynamics.h:15-26)
+            if (k < N && lane < nq) {
+                const T dt = P.dt;
+                const T* xn = X + (k + 1) * nx;
+                const T q = x[lane], v = x[nq + lane], a = x[2 * nq + lane], j = U[k * nu + lane];
+                T* gap = ws + L.GAP + k * nx;
+                gap[lane] = q + dt * v + T(0.5) * dt * dt * a + dt * dt * dt / T(6) * j - xn[lane];
+                gap[nq + lane] = v + dt * a + T(0.5) * dt * dt * j - xn[nq + lane];
+                gap[2 * nq + lane] = a + dt * j - xn[2 * nq + lane];
+            }
+        }
+        __syncwarp();
+    }
+
+    // --------------------------------------------------- performance index
+    // Lane k evaluates knot k (values only).  Mirrors orc::performance().
+    __device__ Perf<T> performance(const T* Xt, const T* Ut) const {
+        const int nq = P.nq, nx = P.nx, nu = P.nu, N = P.N;
+        const T dt = P.dt;
+        const T scale = rsqrt(T(6 * max(P.nb, 1)));
+        T cost = 0, dyn = 0, eq = 0, ineq = 0, max_eq = 0, min_margin = tinf<T>();
+        T sph[3 * UB_MAX_SPHERES];
+        for (int k = lane; k <= N; k += WARP) {
+            const T* x = Xt + k * nx;
+            Kin<T> Kn;
+            KinTan<T> Dn;
+            forward_kinematics<T, false>(P, x, -1, Kn, Dn, P.nobs > 0 ? sph : nullptr, nullptr);
+            const T* rd = target + 3 * k;
+            if (k == N) {
+                for (int i = 0; i < 3; ++i) {
+                    const T e = rd[i] - Kn.r[i];
+                    eq += e * e;
+                    max_eq = max(max_eq, fabs(e));
+                }
+                for (int i = nq; i < nx; ++i) {
+                    eq += x[i] * x[i];
+                    max_eq = max(max_eq, fabs(x[i]));
+                }
+            }
+            if (k >= 1)
+                for (int i = 0; i < nx; ++i) {
+                    const T lo = x[i] - P.xlb[i], hi = P.xub[i] - x[i];
+                    const T a = min(T(0), lo), b = min(T(0), hi);
+                    ineq += dt * (a * a + b * b);
+                    min_margin = min(min_margin, min(lo, hi));
+                }
+            if (k == N) continue;
+            const T* u = Ut + k * nu;
+            T c = 0;
+            for (int i = 0; i < nx; ++i) {
+                const T e = x[i] - P.xd[i];
+                c += T(0.5) * P.Qd[i] * e * e;
+            }
+            for (int i = 0; i < nq; ++i) c += T(0.5) * P.Rd[i] * u[i] * u[i];
+            for (int i = 0; i < P.nfc; ++i) c += T(0.5) * P.fw * u[nq + i] * u[nq + i];
+            for (int i = 0; i < 3; ++i) {
+                const T e = Kn.r[i] - rd[i];
+                c += T(0.5) * P.Wd[i] * e * e;
+            }
+            cost += dt * c;
+            const T* xn = Xt + (k + 1) * nx;
+            for (int i = 0; i < nq; ++i) {
+                const T q = x[i], v = x[nq + i], a = x[2 * nq + i], j = u[i];
+                const T g0 = q + dt * v + T(0.5) * dt * dt * a + dt * dt * dt / T(6) * j - xn[i];
+                const T g1 = v + dt * a + T(0.5) * dt * dt * j - xn[nq + i];
+                const T g2 = a + dt * j - xn[2 * nq + i];
+                dyn += dt * (g0 * g0 + g1 * g1 + g2 * g2);
+            }
+            const int nbox = P.nbox_u;
+            for (int i = 0; i < nbox; ++i) {
+                const T lo = u[i] - (i < nq ? P.ulb[i] : P.flb), hi = (i < nq ? P.uub[i] : P.fub) - u[i];
+                const T a = min(T(0), lo), b = min(T(0), hi);
+                ineq += dt * (a * a + b * b);
+                min_margin = min(min_margin, min(lo, hi));
+            }
+            for (int b = 0; b < (P.neq > 0 ? P.nb : 0); ++b) {
+                const BodyP<T> Bd = load_body(body + b * UB_BODY_PARAMS);
+                T g6[6];
+                object_dynamics_state_part<T, false>(P, Bd, Kn, Dn, scale, g6, nullptr);
+                for (int i = 0; i < 6; ++i) {
+                    const T* Dfr = ws + L.DF + (6 * b + i) * P.nfc;
+                    T gv = g6[i];
+                    for (int j = 0; j < P.nfc; ++j) gv += Dfr[j] * u[nq + j];
+                    eq += dt * gv * gv;
+                    max_eq = max(max_eq, fabs(gv));
+                }
+            }
+            for (int i = 0; i < P.nfric; ++i) {
+                const int cidx = i / 5;
+                const V3<T> a = fric_coeff(cidx, i % 5);
+                const T* f = u + nq + 3 * cidx;
+                const T h = a.x * f[0] + a.y * f[1] + a.z * f[2];
+                const T m = min(T(0), h);
+                ineq += dt * m * m;
+                min_margin = min(min_margin, h);
+            }
+            if (k >= 1)
+                for (int i = 0; i < P.nobs; ++i) {
+                    const int a = P.pa[i], bb = P.pb[i];
+                    const V3<T> d(sph[3 * a] - sph[3 * bb], sph[3 * a + 1] - sph[3 * bb + 1], sph[3 * a + 2] - sph[3 * bb + 2]);
+                    const T h = sqrt(dot(d, d)) - (P.srad[a] + P.srad[bb] + P.dmin);
+                    const T m = min(T(0), h);
+                    ineq += dt * m * m;
+                    min_margin = min(min_margin, h);
+                }
+        }
+        Perf<T> pf;
+        pf.cost = warp_sum(cost);
+        pf.dyn = warp_sum(dyn);
+        pf.eq = warp_sum(eq);
+        pf.ineq = warp_sum(ineq);
+        pf.max_eq = warp_max(max_eq);
+        pf.min_margin = warp_min(min_margin);
+        return pf;
+    }
+
+    // ------------------------------------------------------------ QP pieces
+    // Load the equality rows of stage k into shared memory SA [row][nz] in
+    // stage-vector index order, with their constant c, penalty rho and
+    // multiplier y in sV-side arrays (global RHOE/YE, RHOT/YT).
+    __device__ void load_eq_rows(int k) {
+        const int nq = P.nq, nx = P.nx, nu = P.nu, nz = P.nz;
+        if (k < P.N) {
+            for (int idx = lane; idx < P.neq * nz; idx += WARP) {
+                const int i = idx / nz, j = idx % nz;
+                T v = T(0);
+                if (j >= nu) v = ws[L.LCT + (k * nx + (j - nu)) * P.neq + i];
+                else if (j >= nq) v = ws[L.DF + i * P.nfc + (j - nq)];
+                sSA[idx] = v;
+            }
+        } else {
+            // terminal equality [r_d - r; v; a] = 0: three dense rows over q, the rest are unit rows
+            for (int idx = lane; idx < 3 * nz; idx += WARP) {
+                const int i = idx / nz, j = idx % nz;
+                T v = T(0);
+                if (j >= nu && j < nu + nq) v = -ws[L.LJP + (k * 3 + i) * nq + (j - nu)];
+                sSA[idx] = v;
+            }
+        }
+        __syncwarp();
+    }
+    // constant (value at z = 0) of equality row i of stage k
+    __device__ __forceinline__ T eq_const(int k, int i) const {
+        if (k < P.N) return ws[L.LG + k * P.neq + i];
+        if (i < 3) return target[3 * k + i] - ws[L.LR + 3 * k + i];
+        return X[k * P.nx + P.nq + (i - 3)];
+    }
+    __device__ __forceinline__ T* rho_eq(int k) const { return k < P.N ? ws + L.RHOE + k * P.neq : ws + L.RHOT; }
+    __device__ __forceinline__ T* y_eq(int k) const { return k < P.N ? ws + L.YE + k * P.neq : ws + L.YT; }
+    // value a_i . z + c of equality row i (dense rows from SA; terminal unit rows direct)
+    __device__ T eq_value(int k, int i, const T* zk) const {
+        if (k == P.N && i >= 3) return zk[P.nu + P.nq + (i - 3)] + eq_const(k, i);
+        const T* a = sSA + i * P.nz;
+        T v = eq_const(k, i);
+        for (int j = (k < P.N ? P.nq : P.nu); j < P.nz; ++j) v += a[j] * zk[j];
+        return v;
+    }
+
+    // Set the proximal weights of the equality rows (soft: Z; hard: rho_hard on the
+    // unit-normalised row) and reset the multipliers.
+    __device__ void init_eq_weights() {
+        for (int k = 0; k <= P.N; ++k) {
+            const int ne = neq_of(k);
+            if (ne == 0) continue;
+            load_eq_rows(k);
+            for (int i = lane; i < ne; i += WARP) {
+                T rho = P.Z;
+                if (!P.soft_poly) {
+                    T n2 = T(1);
+                    if (!(k == P.N && i >= 3)) {
+                        n2 = T(0);
+                        for (int j = 0; j < P.nz; ++j) n2 += sSA[i * P.nz + j] * sSA[i * P.nz + j];
+                    }
+                    rho = n2 > T(0) ? P.rho_hard / n2 : T(0);
+                }
+                rho_eq(k)[i] = rho;
+                y_eq(k)[i] = T(0);
+            }
+            __syncwarp();
+        }
+    }
+
+    // M (lower triangle, ld = L.ldm) += [B A]' Pn [B A] with the block structure
+    // A = A3 (x) I, B = B3 (x) I of the exact triple-integrator discretisation.
+    __device__ void add_dynamics_hessian() {
+        const int nq = P.nq, nu = P.nu, nx = P.nx, ld = L.ldm;
+        const T dt = P.dt;
+        // T3[a][I]: column 0 = B3, columns 1..3 = A3
+        const T T3[3][4] = {{dt * dt * dt / T(6), T(1), dt, T(0.5) * dt * dt},
+                            {T(0.5) * dt * dt, T(0), T(1), dt},
+                            {dt, T(0), T(0), T(1)}};
+        const int nb4 = 4 * nq;
+        for (int idx = lane; idx < nb4 * nb4; idx += WARP) {
+            const int bi = idx / nb4, bj = idx % nb4;
+            if (bj > bi) continue;
+            const int I = bi / nq, ii = bi % nq, J = bj / nq, jj = bj % nq;
+            T acc = T(0);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const T ta = T3[a][I];
+                if (ta == T(0)) continue;
+#pragma unroll
+                for (int b = 0; b < 3; ++b) {
+                    const T tb = T3[b][J];
+                    if (tb == T(0)) continue;
+                    const int r = a * nq + ii, c = b * nq + jj;
+                    acc += ta * tb * (r >= c ? sP[r * nx + c] : sP[c * nx + r]);
+                }
+            }
+            const int mi = (I == 0) ? ii : nu + (I - 1) * nq + ii;
+            const int mj = (J == 0) ? jj : nu + (J - 1) * nq + jj;
+            // block order (jerk, q, v, a) is monotone in the M index, so mi >= mj here
+            sM[mi * ld + mj] += acc;
+        }
+        __syncwarp();
+    }
+    // vec (stage layout) += [B A]' pv
+    __device__ void add_dynamics_gradient(T* vec) const {
+        const int nq = P.nq, nu = P.nu;
+        const T dt = P.dt;
+        if (lane < nq) {
+            const T p0 = sPv[lane], p1 = sPv[nq + lane], p2 = sPv[2 * nq + lane];
+            vec[lane] += dt * dt * dt / T(6) * p0 + T(0.5) * dt * dt * p1 + dt * p2;
+            vec[nu + lane] += p0;
+            vec[nu + nq + lane] += dt * p0 + p1;
+            vec[nu + 2 * nq + lane] += T(0.5) * dt * dt * p0 + dt * p1 + p2;
+        }
+        __syncwarp();
+    }
+
+    // Build the Newton matrix of stage k in sM (lower triangle): cost Hessian +
+    // equality proximal terms + barrier terms of the inequality sides.
+    __device__ void build_stage_matrix(int k) {
+        const int nq = P.nq, nu = P.nu, nx = P.nx, nz = P.nz, ld = L.ldm;
+        const T dt = P.dt;
+        for (int idx = lane; idx < nz * ld; idx += WARP) sM[idx] = T(0);
+        __syncwarp();
+        if (k < P.N) {
+            // cost (quadratic_joint_state_input_cost.h:9-33, end_effector_cost.h:48-84), scaled by dt
+            for (int i = lane; i < nz; i += WARP) {
+                T d;
+                if (i < nq) d = dt * P.Rd[i] + P.reg_input;
+                else if (i < nu) d = dt * P.fw + P.reg_input;
+                else d = dt * P.Qd[i - nu];
+                sM[i * ld + i] = d;
+            }
+            __syncwarp();
+            const T* Jp = ws + L.LJP + k * 3 * nq;
+            for (int idx = lane; idx < nq * nq; idx += WARP) {
+                const int a = idx / nq, b = idx % nq;
+                if (b > a) continue;
+                T acc = 0;
+                for (int c = 0; c < 3; ++c) acc += P.Wd[c] * Jp[c * nq + a] * Jp[c * nq + b];
+                sM[(nu + a) * ld + nu + b] += dt * acc;
+            }
+            __syncwarp();
+        }
+        // equality rows: rho a a'
+        const int ne = neq_of(k);
+        if (ne > 0) {
+            load_eq_rows(k);
+            const T* rho = rho_eq(k);
+            const int nd = (k < P.N) ? ne : 3;
+            const int j0 = (k < P.N) ? nq : nu;  // first column with non-zeros
+            const int span = nz - j0;
+            for (int idx = lane; idx < span * span; idx += WARP) {
+                const int i = j0 + idx / span, j = j0 + idx % span;
+                if (j > i) continue;
+                T acc = 0;
+                for (int r = 0; r < nd; ++r) acc += rho[r] * sSA[r * nz + i] * sSA[r * nz + j];
+                sM[i * ld + j] += acc;
+            }
+            if (k == P.N)
+                for (int i = 3 + lane; i < ne; i += WARP) {
+                    const int m = nu + nq + (i - 3);
+                    sM[m * ld + m] += rho[i];
+                }
+            __syncwarp();
+        }
+        // inequality sides: w a a', w = lam / (t + eps lam)
+        const T* TTk = ws + L.TT + k * P.nrow * 2;
+        const T* LMk = ws + L.LAM + k * P.nrow * 2;
+        const int nbx = P.nbox_u + P.nx;
+        for (int r = lane; r < nbx; r += WARP) {
+            const int fam = r < P.nbox_u ? 0 : 1;
+            if (!row_valid(k, fam)) continue;
+            const T eps = row_eps(fam);
+            const T w = LMk[2 * r] / (TTk[2 * r] + eps * LMk[2 * r]) + LMk[2 * r + 1] / (TTk[2 * r + 1] + eps * LMk[2 * r + 1]);
+            const int m = fam == 0 ? r : nu + (r - P.nbox_u);
+            sM[m * ld + m] += w;
+        }
+        __syncwarp();
+        if (P.nfric > 0 && k < P.N) {
+            const T eps = row_eps(2);
+            // one lane per (contact, 3x3 lower entry)
+            for (int idx = lane; idx < P.nc * 6; idx += WARP) {
+                const int c = idx / 6, e = idx % 6;
+                const int a = (e < 1) ? 0 : (e < 3 ? 1 : 2), b = e - (a == 0 ? 0 : (a == 1 ? 1 : 3));
+                T acc = 0;
+                for (int which = 0; which < 5; ++which) {
+                    const int r = nbx + 5 * c + which;
+                    const T w = LMk[2 * r] / (TTk[2 * r] + eps * LMk[2 * r]);
+                    const V3<T> cf = fric_coeff(c, which);
+                    acc += w * cf[a] * cf[b];
+                }
+                sM[(nq + 3 * c + a) * ld + nq + 3 * c + b] += acc;
+            }
+            __syncwarp();
+        }
+        if (P.nobs > 0 && k >= 1 && k < P.N) {
+            const T eps = row_eps(3);
+            for (int idx = lane; idx < nq * nq; idx += WARP) {
+                const int a = idx / nq, b = idx % nq;
+                if (b > a) continue;
+                T acc = 0;
+                for (int i = 0; i < P.nobs; ++i) {
+                    const int r = nbx + P.nfric + i;
+                    const T w = LMk[2 * r] / (TTk[2 * r] + eps * LMk[2 * r]);
+                    const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
+                    acc += w * J[a] * J[b];
+                }
+                sM[(nu + a) * ld + nu + b] += acc;
+            }
+            __syncwarp();
+        }
+    }
+
+    // Right-looking Cholesky of the first nu columns of sM (n x n, lower, ld):
+    // afterwards columns j < nu hold L (diagonal stored INVERTED) and the
+    // trailing block holds the Schur complement.  Lane l owns columns l, l+32, ...
+    __device__ bool partial_cholesky(int n, int npiv) {
+        const int ld = L.ldm;
+        bool ok = true;
+        for (int j = 0; j < npiv; ++j) {
+            T d = sM[j * ld + j];
+            if (!(d > T(1e-30))) {
+                ok = false;
+                d = T(1e-30);
+            }
+            const T inv = rsqrt(d);
+            for (int i = j + 1 + lane; i < n; i += WARP) sM[i * ld + j] *= inv;
+            __syncwarp();
+            if (lane == 0) sM[j * ld + j] = inv;
+            for (int l = j + 1 + lane; l < n; l += WARP) {
+                const T mlj = sM[l * ld + j];
+                for (int i = l; i < n; ++i) sM[i * ld + l] -= sM[i * ld + j] * mlj;
+            }
+            __syncwarp();
+        }
+        return ok;
+    }
+
+    // Factor sweep: for k = N..0 build the stage matrix, add the cost-to-go,
+    // factor, store the factor block FAC[k] = sM[0..nz) x [0..nu) (ld = L.ldf)
+    // and keep the new cost-to-go Hessian in sP.
+    __device__ bool factor_sweep() {
+        const int nu = P.nu, nx = P.nx, nz = P.nz, ld = L.ldm;
+        bool ok = true;
+        for (int k = P.N; k >= 0; --k) {
+            build_stage_matrix(k);
+            if (k < P.N) {
+                add_dynamics_hessian();
+                ok &= partial_cholesky(nz, nu);
+                T* F = ws + L.FAC + k * nz * L.ldf;
+                for (int idx = lane; idx < nz * nu; idx += WARP) {
+                    const int i = idx / nu, j = idx % nu;
+                    F[i * L.ldf + j] = (j <= i) ? sM[i * ld + j] : T(0);
+                }
+            }
+            // cost-to-go: trailing block (x part)
+            for (int idx = lane; idx < nx * nx; idx += WARP) {
+                const int i = idx / nx, j = idx % nx;
+                if (j <= i) sP[i * nx + j] = sM[(nu + i) * ld + nu + j];
+            }
+            __syncwarp();
+        }
+        return ok;
+    }
+
+    // Stage gradient of the barrier/proximal Lagrangian at the current iterate:
+    //   H z + g  +  sum_eq a (rho e + y)  +  sum_sides sgn a [ -lam + (rc + lam rd)/(t + eps lam) ]
+    // with rc = t lam - target (+ dt_aff dlam_aff in the corrector).  Result in vec (shared).
+    __device__ void stage_gradient(int k, bool corrector, T mu_target, T* vec) {
+        const int nq = P.nq, nu = P.nu, nx = P.nx, nz = P.nz;
+        const T dt = P.dt;
+        const T* zk = Zk(k);
+        for (int i = lane; i < nz; i += WARP) vec[i] = T(0);
+        __syncwarp();
+        if (k < P.N) {
+            const T* x = X + k * nx;
+            const T* u = U + k * nu;
+            const T* Jp = ws + L.LJP + k * 3 * nq;
+            // e = Jp dq + r - r_d
+            T e3[3];
+            for (int c = 0; c < 3; ++c) {
+                T e = ws[L.LR + 3 * k + c] - target[3 * k + c];
+                for (int j = 0; j < nq; ++j) e += Jp[c * nq + j] * zk[nu + j];
+                e3[c] = e;
+            }
+            for (int i = lane; i < nz; i += WARP) {
+                T g;
+                if (i < nq) g = dt * P.Rd[i] * (u[i] + zk[i]) + P.reg_input * zk[i];
+                else if (i < nu) g = dt * P.fw * (u[i] + zk[i]) + P.reg_input * zk[i];
+                else {
+                    const int xi = i - nu;
+                    g = dt * P.Qd[xi] * (x[xi] + zk[i] - P.xd[xi]);
+                    if (xi < nq)
+                        for (int c = 0; c < 3; ++c) g += dt * P.Wd[c] * Jp[c * nq + xi] * e3[c];
+                }
+                vec[i] = g;
+            }
+            __syncwarp();
+        }
+        const int ne = neq_of(k);
+        if (ne > 0) {
+            load_eq_rows(k);
+            const T* rho = rho_eq(k);
+            const T* y = y_eq(k);
+            // per-row multipliers m_i = rho e + y (kept in registers of lane i), then vec += sum_i m_i a_i
+            const int nd = (k < P.N) ? ne : 3;
+            T* mrow = sV + 4 * nz;  // scratch [nd]
+            for (int i = lane; i < ne; i += WARP) {
+                const T m = rho[i] * eq_value(k, i, zk) + y[i];
+                if (i < nd) mrow[i] = m;
+                else vec[nu + nq + (i - 3)] += m;  // terminal unit rows (distinct entries)
+            }
+            __syncwarp();
+            for (int j = lane; j < nz; j += WARP) {
+                T acc = 0;
+                for (int i = 0; i < nd; ++i) acc += mrow[i] * sSA[i * nz + j];
+                vec[j] += acc;
+            }
+            __syncwarp();
+        }
+        const T* TTk = ws + L.TT + k * P.nrow * 2;
+        const T* LMk = ws + L.LAM + k * P.nrow * 2;
+        const T* DTk = ws + L.DTT + k * P.nrow * 2;
+        const T* DLk = ws + L.DLAM + k * P.nrow * 2;
+        for (int r = lane; r < P.nrow; r += WARP) {
+            const int fam = row_family(r);
+            if (!row_valid(k, fam)) continue;
+            T lb, ub;
+            const T val = row_value(k, r, fam, zk, &lb, &ub);
+            const T eps = row_eps(fam);
+            T coef = T(0);
+            for (int sd = 0; sd < 2; ++sd) {
+                if (sd == 1 && fam >= 2) break;
+                const T t = TTk[2 * r + sd], lam = LMk[2 * r + sd];
+                const T sg = sd == 0 ? T(1) : T(-1);
+                const T d = sd == 0 ? val - lb : ub - val;
+                const T rd = d + eps * lam - t;
+                T rc = t * lam - mu_target;
+                if (corrector) rc += DTk[2 * r + sd] * DLk[2 * r + sd];
+                coef += sg * (-lam + (rc + lam * rd) / (t + eps * lam));
+            }
+            row_axpy(k, r, fam, coef, vec);
+        }
+        __syncwarp();
+    }
+
+    // Vector sweeps with the stored factors: backward (w_k, cost-to-go gradient)
+    // then forward (direction DZ).  `corrector`/`target_mu` select the right-hand side.
+    __device__ void solve_sweeps(bool corrector, T target_mu) {
+        const int nq = P.nq, nu = P.nu, nx = P.nx, nz = P.nz, ldf = L.ldf;
+        T* vec = sV;           // [nz] gradient
+        T* dx = sV + nz;       // [nx]
+        T* du = sV + 2 * nz;   // [nu] (also s)
+        T* F = sM;             // factor block staged in shared memory
+        // backward
+        for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
+        __syncwarp();
+        for (int k = P.N; k >= 0; --k) {
+            stage_gradient(k, corrector, target_mu, vec);
+            if (k == P.N) {
+                for (int i = lane; i < nx; i += WARP) sPv[i] = vec[nu + i];
+                __syncwarp();
+                continue;
+            }
+            add_dynamics_gradient(vec);
+            const T* Fg = ws + L.FAC + k * nz * ldf;
+            for (int idx = lane; idx < nz * ldf; idx += WARP) F[idx] = Fg[idx];
+            __syncwarp();
+            // w = L^{-1} m_u (forward substitution, column oriented)
+            for (int j = 0; j < nu; ++j) {
+                const T wj = vec[j] * F[j * ldf + j];
+                __syncwarp();
+                if (lane == 0) vec[j] = wj;
+                for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= F[i * ldf + j] * wj;
+                __syncwarp();
+            }
+            T* Wk = ws + L.WF + k * nu;
+            for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
+            // p = m_x - Y' w
+            for (int i = lane; i < nx; i += WARP) {
+                T acc = vec[nu + i];
+                const T* Fr = F + (nu + i) * ldf;
+                for (int j = 0; j < nu; ++j) acc -= Fr[j] * vec[j];
+                sPv[i] = acc;
+            }
+            __syncwarp();
+        }
+        // forward: d x_0 = 0
+        for (int i = lane; i < nx; i += WARP) dx[i] = T(0);
+        __syncwarp();
+        for (int k = 0; k < P.N; ++k) {
+            const T* Fg = ws + L.FAC + k * nz * ldf;
+            for (int idx = lane; idx < nz * ldf; idx += WARP) F[idx] = Fg[idx];
+            const T* Wk = ws + L.WF + k * nu;
+            __syncwarp();
+            // s = w + Y dx
+            for (int j = lane; j < nu; j += WARP) {
+                T acc = Wk[j];
+                for (int i = 0; i < nx; ++i) acc += F[(nu + i) * ldf + j] * dx[i];
+                du[j] = acc;
+            }
+            __syncwarp();
+            // du = -L^{-T} s (backward substitution, row oriented)
+            for (int j = nu - 1; j >= 0; --j) {
+                const T uj = -du[j] * F[j * ldf + j];
+                __syncwarp();
+                for (int i = lane; i < j; i += WARP) du[i] += F[j * ldf + i] * uj;
+                if (lane == 0) du[j] = uj;
+                __syncwarp();
+            }
+            T* D = DZk(k);
+            for (int j = lane; j < nu; j += WARP) D[j] = du[j];
+            for (int i = lane; i < nx; i += WARP) D[nu + i] = dx[i];
+            __syncwarp();
+            if (lane < nq) {
+                const T dt = P.dt;
+                const T q = dx[lane], v = dx[nq + lane], a = dx[2 * nq + lane], j = du[lane];
+                dx[lane] = q + dt * v + T(0.5) * dt * dt * a + dt * dt * dt / T(6) * j;
+                dx[nq + lane] = v + dt * a + T(0.5) * dt * dt * j;
+                dx[2 * nq + lane] = a + dt * j;
+            }
+            __syncwarp();
+        }
+        T* D = DZk(P.N);
+        for (int j = lane; j < nu; j += WARP) D[j] = T(0);
+        for (int i = lane; i < nx; i += WARP) D[nu + i] = dx[i];
+        __syncwarp();
+    }
+
+    // d lambda / d t of every side for the direction in DZ; returns the largest
+    // step in (0,1] keeping t and lambda positive, and (via *mu_aff) the mean
+    // complementarity after that step.
+    __device__ T side_steps(bool corrector, T target_mu, T* mu_after) {
+        T amax = T(1);
+        for (int k = 0; k <= P.N; ++k) {
+            const T* zk = Zk(k);
+            const T* dk = DZk(k);
+            T* TTk = ws + L.TT + k * P.nrow * 2;
+            T* LMk = ws + L.LAM + k * P.nrow * 2;
+            T* DTk = ws + L.DTT + k * P.nrow * 2;
+            T* DLk = ws + L.DLAM + k * P.nrow * 2;
+            for (int r = lane; r < P.nrow; r += WARP) {
+                const int fam = row_family(r);
+                if (!row_valid(k, fam)) continue;
+                T lb, ub;
+                const T val = row_value(k, r, fam, zk, &lb, &ub);
+                const T adz = row_dot(k, r, fam, dk);
+                const T eps = row_eps(fam);
+                for (int sd = 0; sd < 2; ++sd) {
+                    if (sd == 1 && fam >= 2) break;
+                    const T t = TTk[2 * r + sd], lam = LMk[2 * r + sd];
+                    const T sg = sd == 0 ? T(1) : T(-1);
+                    const T d = sd == 0 ? val - lb : ub - val;
+                    const T rd = d + eps * lam - t;
+                    T rc = t * lam - target_mu;
+                    if (corrector) rc += DTk[2 * r + sd] * DLk[2 * r + sd];
+                    const T den = t + eps * lam;
+                    const T dl = -(rc + lam * rd) / den - (lam / den) * sg * adz;
+                    const T dtt = sg * adz + eps * dl + rd;
+                    DLk[2 * r + sd] = dl;
+                    DTk[2 * r + sd] = dtt;
+                    if (dtt < T(0)) amax = min(amax, -t / dtt);
+                    if (dl < T(0)) amax = min(amax, -lam / dl);
+                }
+            }
+        }
+        amax = warp_min(amax);
+        __syncwarp();
+        if (mu_after) {
+            T acc = 0;
+            for (int k = 0; k <= P.N; ++k) {
+                const T* TTk = ws + L.TT + k * P.nrow * 2;
+                const T* LMk = ws + L.LAM + k * P.nrow * 2;
+                const T* DTk = ws + L.DTT + k * P.nrow * 2;
+                const T* DLk = ws + L.DLAM + k * P.nrow * 2;
+                for (int r = lane; r < P.nrow; r += WARP) {
+                    const int fam = row_family(r);
+                    if (!row_valid(k, fam)) continue;
+                    for (int sd = 0; sd < (fam >= 2 ? 1 : 2); ++sd)
+                        acc += (TTk[2 * r + sd] + amax * DTk[2 * r + sd]) * (LMk[2 * r + sd] + amax * DLk[2 * r + sd]);
+                }
+            }
+            *mu_after = warp_sum(acc);
+        }
+        return amax;
+    }
+
+    // Interior-point QP solve around the current (X, U).  Leaves the step in Z
+    // and the factors of the last iteration in FAC.  Returns iterations used;
+    // *converged, *decr as in orc::solve_qp_ipm.
+    __device__ int solve_qp(bool* converged, T* decr, bool* finite) {
+        const int nq = P.nq, nu = P.nu, nx = P.nx, nz = P.nz, N = P.N;
+        *converged = false;
+        *finite = true;
+        // dynamics-feasible start: du = 0, dx_0 = 0, dx_{k+1} = A dx_k + gap_k
+        for (int idx = lane; idx < (N + 1) * nz; idx += WARP) ws[L.Z + idx] = T(0);
+        __syncwarp();
+        if (lane < nq) {
+            const T dt = P.dt;
+            T q = 0, v = 0, a = 0;
+            for (int k = 0; k < N; ++k) {
+                const T* gap = ws + L.GAP + k * nx;
+                const T qn = q + dt * v + T(0.5) * dt * dt * a + gap[lane];
+                const T vn = v + dt * a + gap[nq + lane];
+                const T an = a + gap[2 * nq + lane];
+                q = qn; v = vn; a = an;
+                T* zn = Zk(k + 1);
+                zn[nu + lane] = q;
+                zn[nu + nq + lane] = v;
+                zn[nu + 2 * nq + lane] = a;
+            }
+        }
+        __syncwarp();
+        init_eq_weights();
+        // slack / multiplier initialisation
+        int nsides_l = 0;
+        for (int k = 0; k <= N; ++k) {
+            const T* zk = Zk(k);
+            for (int r = lane; r < P.nrow; r += WARP) {
+                const int fam = row_family(r);
+                T* TTk = ws + L.TT + (k * P.nrow + r) * 2;
+                T* LMk = ws + L.LAM + (k * P.nrow + r) * 2;
+                if (!row_valid(k, fam)) {
+                    TTk[0] = TTk[1] = T(1);
+                    LMk[0] = LMk[1] = T(0);
+                    continue;
+                }
+                T lb, ub;
+                const T val = row_value(k, r, fam, zk, &lb, &ub);
+                TTk[0] = max(val - lb, P.thr0);
+                LMk[0] = P.mu0 / TTk[0];
+                ++nsides_l;
+                if (fam < 2) {
+                    TTk[1] = max(ub - val, P.thr0);
+                    LMk[1] = P.mu0 / TTk[1];
+                    ++nsides_l;
+                } else {
+                    TTk[1] = T(1);
+                    LMk[1] = T(0);
+                }
+            }
+        }
+        const int nsides = __reduce_add_sync(FULL, nsides_l);
+        __syncwarp();
+        T last_alpha = T(0), last_step = tinf<T>();
+        int iters = 0;
+        for (int it = 0; it < P.qp_iter_max; ++it) {
+            // residual summary: mu, max |rd|, equality infeasibility
+            T mu = 0, rdmax = 0, pinf = 0;
+            for (int k = 0; k <= N; ++k) {
+                const T* zk = Zk(k);
+                const T* TTk = ws + L.TT + k * P.nrow * 2;
+                const T* LMk = ws + L.LAM + k * P.nrow * 2;
+                for (int r = lane; r < P.nrow; r += WARP) {
+                    const int fam = row_family(r);
+                    if (!row_valid(k, fam)) continue;
+                    T lb, ub;
+                    const T val = row_value(k, r, fam, zk, &lb, &ub);
+                    const T eps = row_eps(fam);
+                    for (int sd = 0; sd < (fam >= 2 ? 1 : 2); ++sd) {
+                        const T t = TTk[2 * r + sd], lam = LMk[2 * r + sd];
+                        const T d = sd == 0 ? val - lb : ub - val;
+                        rdmax = max(rdmax, fabs(d + eps * lam - t));
+                        mu += t * lam;
+                    }
+                }
+                if (!P.soft_poly && neq_of(k) > 0) {
+                    load_eq_rows(k);
+                    for (int i = lane; i < neq_of(k); i += WARP)
+                        if (rho_eq(k)[i] > T(0)) pinf = max(pinf, fabs(eq_value(k, i, zk)));
+                    __syncwarp();
+                }
+            }
+            mu = nsides > 0 ? warp_sum(mu) / T(nsides) : T(0);
+            rdmax = warp_max(rdmax);
+            pinf = warp_max(pinf);
+            if (it > 0 && mu <= T(2) * P.mu_target && rdmax <= P.qp_tol && last_alpha >= T(0.5) &&
+                (pinf <= P.qp_tol || last_step <= P.qp_tol)) {
+                *converged = true;
+                break;
+            }
+            iters = it + 1;
+            if (!factor_sweep()) *finite = false;
+            T target_mu = P.mu_target;
+            if (nsides > 0) {
+                solve_sweeps(false, T(0));
+                T mu_aff;
+                side_steps(false, T(0), &mu_aff);
+                mu_aff /= T(nsides);
+                const T ratio = mu_aff / mu;
+                target_mu = max(ratio * ratio * ratio * mu, P.mu_target);
+                solve_sweeps(true, target_mu);
+            } else {
+                solve_sweeps(false, T(0));
+            }
+            T alpha = T(1);
+            if (nsides > 0) alpha = min(T(1), T(0.995) * side_steps(true, target_mu, nullptr));
+            // update z, t, lambda, equality multipliers
+            T stepmax = 0, dec = 0;
+            for (int idx = lane; idx < (N + 1) * nz; idx += WARP) {
+                const T d = ws[L.DZ + idx];
+                ws[L.Z + idx] += alpha * d;
+                stepmax = max(stepmax, fabs(alpha * d));
+            }
+            for (int idx = lane; idx < (N + 1) * P.nrow * 2; idx += WARP) {
+                ws[L.TT + idx] += alpha * ws[L.DTT + idx];
+                ws[L.LAM + idx] += alpha * ws[L.DLAM + idx];
+            }
+            __syncwarp();
+            if (!P.soft_poly)
+                for (int k = 0; k <= N; ++k) {
+                    if (neq_of(k) == 0) continue;
+                    load_eq_rows(k);
+                    const T* zk = Zk(k);
+                    for (int i = lane; i < neq_of(k); i += WARP) {
+                        const T rho = rho_eq(k)[i];
+                        if (rho > T(0)) y_eq(k)[i] += rho * eq_value(k, i, zk);
+                    }
+                    __syncwarp();
+                }
+            last_alpha = alpha;
+            last_step = warp_max(stepmax);
+            if (!(last_step < tinf<T>())) *finite = false;
+            (void)dec;
+            if (!*finite) break;
+        }
+        *decr = last_step;
+        return iters;
+    }
+
+    // Feedback gains K_k = -Huu^{-1} Hux from the stored factors (optional output).
+    __device__ void write_gains(T* Kout) {
+        const int nu = P.nu, nx = P.nx, nz = P.nz, ldf = L.ldf;
+        T* F = sM;
+        T* col = sV;
+        for (int k = 0; k < P.N; ++k) {
+            const T* Fg = ws + L.FAC + k * nz * ldf;
+            for (int idx = lane; idx < nz * ldf; idx += WARP) F[idx] = Fg[idx];
+            __syncwarp();
+            for (int xcol = 0; xcol < nx; ++xcol) {
+                for (int j = lane; j < nu; j += WARP) col[j] = F[(nu + xcol) * ldf + j];
+                __syncwarp();
+                for (int j = nu - 1; j >= 0; --j) {
+                    const T uj = -col[j] * F[j * ldf + j];
+                    __syncwarp();
+                    for (int i = lane; i < j; i += WARP) col[i] += F[j * ldf + i] * uj;
+                    if (lane == 0) col[j] = uj;
+                    __syncwarp();
+                }
+                for (int j = lane; j < nu; j += WARP) Kout[(k * nu + j) * nx + xcol] = col[j];
+                __syncwarp();
+            }
+        }
+    }
+
+    // --------------------------------------------------------------- solve
+    __device__ void run(const BatchArgs<T>& A, int b) {
+        const int nq = P.nq, nx = P.nx, nu = P.nu, N = P.N, nz = P.nz;
+        // initial guess: DefaultInitializer = zero input, state held
+        // (controller_interface.cpp:385-386); x_0 is always the observation
+        if (!A.warm) {
+            for (int idx = lane; idx < (N + 1) * nx; idx += WARP) X[idx] = x0[idx % nx];
+            for (int idx = lane; idx < N * nu; idx += WARP) U[idx] = T(0);
+        } else {
+            for (int i = lane; i < nx; i += WARP) X[i] = x0[i];
+        }
+        __syncwarp();
+        if (P.neq > 0) build_Df();
+        Perf<T> base = performance(X, U);
+        int status = UB_STATUS_CONVERGED, qp_iters = 0, sqp_done = 0;
+        T alpha = 0, qp_res = 0;
+        T* Xn = ws + L.XN;
+        T* Un = ws + L.UN;
+        for (int it = 0; it < max(1, P.sqp_iters); ++it) {
+            ++sqp_done;
+            linearize();
+            if (A.stop_after == 1) break;
+            bool conv, fin;
+            qp_iters += solve_qp(&conv, &qp_res, &fin);
+            if (A.stop_after == 2) break;
+            if (!fin) {
+                status = UB_STATUS_NAN;
+                break;
+            }
+            if (!conv) status = UB_STATUS_QP_MAXITER;
+            // Armijo descent metric: cost gradient (at z = 0) along the step
+            T desc = 0;
+            for (int k = 0; k < N; ++k) {
+                const T* zk = Zk(k);
+                const T* x = X + k * nx;
+                const T* u = U + k * nu;
+                const T* Jp = ws + L.LJP + k * 3 * nq;
+                for (int i = lane; i < nz; i += WARP) {
+                    T g;
+                    if (i < nq) g = P.dt * P.Rd[i] * u[i];
+                    else if (i < nu) g = P.dt * P.fw * u[i];
+                    else {
+                        const int xi = i - nu;
+                        g = P.dt * P.Qd[xi] * (x[xi] - P.xd[xi]);
+                        if (xi < nq)
+                            for (int c = 0; c < 3; ++c)
+                                g += P.dt * P.Wd[c] * Jp[c * nq + xi] * (ws[L.LR + 3 * k + c] - target[3 * k + c]);
+                    }
+                    desc += g * zk[i];
+                }
+            }
+            desc = warp_sum(desc);
+            // filter line search (ocs2 FilterLinesearch [EXT])
+            const T vb = base.violation();
+            bool accepted = false;
+            Perf<T> pn = base;
+            alpha = T(1);
+            while (alpha >= P.alpha_min) {
+                for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
+                    const int k = idx / nx, i = idx % nx;
+                    Xn[idx] = X[idx] + alpha * ws[L.Z + k * nz + nu + i];
+                }
+                for (int idx = lane; idx < N * nu; idx += WARP) {
+                    const int k = idx / nu, i = idx % nu;
+                    Un[idx] = U[idx] + alpha * ws[L.Z + k * nz + i];
+                }
+                __syncwarp();
+                pn = performance(Xn, Un);
+                const T vn = pn.violation();
+                if (vn > P.g_max) accepted = false;
+                else if (vn < P.g_min) {
+                    if (vb < P.g_min && desc < T(0)) accepted = pn.cost < base.cost + P.armijo * alpha * desc;
+                    else accepted = true;
+                } else {
+                    accepted = (vn < (T(1) - P.gamma_c) * vb) || (pn.cost < base.cost - P.gamma_c * vb);
+                }
+                if (accepted) break;
+                alpha *= P.alpha_decay;
+            }
+            if (!accepted) {
+                status = UB_STATUS_LS_FAILED;
+                alpha = T(0);
+                break;
+            }
+            T dxn = 0, dun = 0;
+            for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
+                const T d = Xn[idx] - X[idx];
+                dxn += d * d;
+                X[idx] = Xn[idx];
+            }
+            for (int idx = lane; idx < N * nu; idx += WARP) {
+                const T d = Un[idx] - U[idx];
+                dun += d * d;
+                U[idx] = Un[idx];
+            }
+            dxn = sqrt(warp_sum(dxn));
+            dun = sqrt(warp_sum(dun));
+            __syncwarp();
+            const T dcost = fabs(pn.cost - base.cost);
+            base = pn;
+            if ((dxn < P.delta_tol && dun < P.delta_tol) || (dcost < P.cost_tol && base.violation() < P.g_min)) break;
+        }
+        if (A.K != nullptr && A.stop_after == 0 && status != UB_STATUS_NAN) write_gains(A.K + size_t(b) * N * nu * nx);
+        // NaN guard
+        T bad = 0;
+        for (int idx = lane; idx < (N + 1) * nx; idx += WARP) bad += isfinite(X[idx]) ? T(0) : T(1);
+        bad = warp_sum(bad);
+        if (bad > T(0)) status = UB_STATUS_NAN;
+        if (lane == 0) {
+            A.status[b] = status;
+            if (A.stats) {
+                T* s = A.stats + size_t(b) * UB_STATS;
+                s[0] = T(qp_iters);
+                s[1] = base.cost;
+                s[2] = base.violation();
+                s[3] = alpha;
+                s[4] = qp_res;
+                s[5] = base.max_eq;
+                s[6] = base.min_margin;
+                s[7] = T(sqp_done);
+            }
+        }
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) solve_batch_kernel(const DevProblem<T>* __restrict__ Pg, Layout L, BatchArgs<T> A,
+                                                          int warps_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // CTA-shared copy of the problem constants
+    DevProblem<T>* Ps = reinterpret_cast<DevProblem<T>*>(smem_raw);
+    {
+        const int nwords = sizeof(DevProblem<T>) / 4;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(Pg);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(Ps);
+        for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x / WARP, lane = threadIdx.x % WARP;
+    const int b = blockIdx.x * warps_per_cta + warp;
+    if (b >= A.B) return;
+    size_t off = (sizeof(DevProblem<T>) + 15) / 16 * 16;
+    T* sm = reinterpret_cast<T*>(smem_raw + off) + size_t(warp) * L.s_total;
+    Solver<T> S(*Ps, L, lane);
+    S.x0 = A.x0 + size_t(b) * Ps->nx;
+    S.target = A.target + size_t(b) * (Ps->N + 1) * 3;
+    S.body = A.body ? A.body + size_t(b) * Ps->nb * UB_BODY_PARAMS : &Ps->body[0][0];
+    S.X = A.X + size_t(b) * (Ps->N + 1) * Ps->nx;
+    S.U = A.U + size_t(b) * Ps->N * Ps->nu;
+    S.ws = A.ws + size_t(b) * L.total;
+    S.sM = sm + L.sM;
+    S.sP = sm + L.sP;
+    S.sPv = sm + L.sPv;
+    S.sSA = sm + L.sSA;
+    S.sV = sm + L.sV;
+    S.run(A, b);
+}
+
+}  // namespace ub

@@ -1,0 +1,145 @@
+"""Batched MPC engine: thin Python layer over the C-ABI CUDA library.
+
+`BatchedMPC.solve()` is the host-buffer path (numpy float64 in/out, copies
+inside the call — the drop-in replacement of B x `advanceMpc()`);
+`BatchedMPC.solve_device()` keeps everything in torch CUDA tensors (f32) and
+only enqueues the kernel on the current stream.  torch is plumbing here
+(device memory, streams); all arithmetic is in `csrc/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import bindings as B
+
+LAYOUT_FIELDS = ("Z", "DZ", "GAP", "LG", "LCT", "LR", "LJP", "LHO", "LJO", "DF", "RHOE", "YE", "RHOT", "YT", "TT",
+                 "LAM", "DTT", "DLAM", "VAL", "FAC", "WF", "XN", "UN", "total", "sM", "sP", "sPv", "sSA", "sV",
+                 "s_total", "ldm", "ldf")
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class BatchedMPC:
+    """One immutable problem configuration on one GPU."""
+
+    def __init__(self, desc: B.ProblemDesc, precision: str = "f32"):
+        if precision not in ("f32", "f64"):
+            raise ValueError("precision must be 'f32' or 'f64'")
+        self.lib = B.load_library()
+        self.lib.ub_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        self.lib.ub_workspace_layout.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_int32)]
+        self.desc = desc
+        self.precision = precision
+        self.flags = B.UB_COMPUTE_F64 if precision == "f64" else 0
+        handle = C.c_void_p()
+        B.check(self.lib.ub_problem_create(C.byref(desc), C.byref(handle)))
+        self.handle = handle
+        dims = (C.c_int32 * 8)()
+        B.check(self.lib.ub_problem_dims(self.handle, dims))
+        self.nx, self.nu, self.n_eq, self.n_ineq, self.n_term, self.N, self.nb, self.nc = list(dims)
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.ub_problem_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------- host path
+    def solve(self, x0, target, body_params=None, X=None, U=None, warm=False, want_gains=False):
+        """numpy float64 host buffers; returns dict(X, U, status, stats[, K])."""
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        Bn = x0.shape[0]
+        assert x0.shape == (Bn, self.nx)
+        target = np.ascontiguousarray(np.asarray(target, dtype=np.float64).reshape(Bn, self.N + 1, 3))
+        if body_params is not None:
+            body_params = np.ascontiguousarray(body_params, dtype=np.float64).reshape(Bn, self.nb, 10)
+        if warm:
+            X = np.ascontiguousarray(X, dtype=np.float64).reshape(Bn, self.N + 1, self.nx).copy()
+            U = np.ascontiguousarray(U, dtype=np.float64).reshape(Bn, self.N, self.nu).copy()
+        else:
+            X = np.zeros((Bn, self.N + 1, self.nx))
+            U = np.zeros((Bn, self.N, self.nu))
+        K = np.zeros((Bn, self.N, self.nu, self.nx)) if want_gains else None
+        status = np.zeros(Bn, dtype=np.int32)
+        stats = np.zeros((Bn, B.UB_STATS))
+        flags = self.flags | (B.UB_WARM_START if warm else 0)
+        B.check(self.lib.ub_solve_batch(self.handle, Bn, _ptr(x0), _ptr(target), _ptr(body_params), _ptr(X), _ptr(U),
+                                        _ptr(K), _ptr(status), _ptr(stats), None, 0, flags, None))
+        out = dict(X=X, U=U, status=status, stats=stats)
+        if want_gains:
+            out["K"] = K
+        return out
+
+    # ----------------------------------------------------------- device path
+    @property
+    def torch_dtype(self):
+        import torch
+        return torch.float64 if self.precision == "f64" else torch.float32
+
+    def workspace(self, Bn, device=None):
+        import torch
+        nbytes = self.lib.ub_workspace_bytes(self.handle, Bn, self.flags)
+        if self._ws is None or self._ws.numel() < nbytes or (device is not None and self._ws.device != device):
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=device or "cuda")
+        return self._ws
+
+    def solve_device(self, x0, target, body_params=None, X=None, U=None, K=None, status=None, stats=None, warm=False):
+        """torch CUDA tensors of `self.torch_dtype`; enqueues on the current stream, no sync."""
+        import torch
+        Bn = x0.shape[0]
+        dt, dev = self.torch_dtype, x0.device
+        assert x0.dtype == dt and target.dtype == dt and x0.is_contiguous() and target.is_contiguous()
+        if X is None:
+            assert not warm
+            X = torch.empty((Bn, self.N + 1, self.nx), dtype=dt, device=dev)
+            U = torch.empty((Bn, self.N, self.nu), dtype=dt, device=dev)
+        if status is None:
+            status = torch.empty(Bn, dtype=torch.int32, device=dev)
+        if stats is None:
+            stats = torch.empty((Bn, B.UB_STATS), dtype=dt, device=dev)
+        ws = self.workspace(Bn, dev)
+        flags = self.flags | B.UB_PTRS_DEVICE | (B.UB_WARM_START if warm else 0)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())  # noqa: E731
+        B.check(self.lib.ub_solve_batch(self.handle, Bn, p(x0), p(target), p(body_params), p(X), p(U), p(K),
+                                        p(status), p(stats), p(ws), ws.numel(), flags, C.c_void_p(stream)))
+        return dict(X=X, U=U, K=K, status=status, stats=stats)
+
+    def last_solve_ms(self):
+        return float(self.lib.ub_last_solve_ms(self.handle))
+
+    # -------------------------------------------------------- probes / debug
+    def eval(self, name, x, u, target=None, body_params=None):
+        """Named constraint/cost probes of the reference interface, batched."""
+        x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
+        u = np.ascontiguousarray(np.atleast_2d(u), dtype=np.float64)
+        M = x.shape[0]
+        cap = M * max(self.n_eq, 5 * self.nc, self.desc.n_pairs, 3, 1)
+        out = np.zeros(cap)
+        rows = C.c_int32()
+        tg = None if target is None else np.ascontiguousarray(target, dtype=np.float64).reshape(M, 3)
+        bp = None if body_params is None else np.ascontiguousarray(body_params, dtype=np.float64)
+        B.check(self.lib.ub_eval(self.handle, name.encode(), M, _ptr(x), _ptr(u), _ptr(tg), _ptr(bp), _ptr(out), cap,
+                                 C.byref(rows)))
+        return out[: M * rows.value].reshape(M, rows.value)
+
+    def set_option(self, key, value):
+        B.check(self.lib.ub_set_option(self.handle, key.encode(), int(value)))
+
+    def layout(self):
+        out = (C.c_int32 * 32)()
+        B.check(self.lib.ub_workspace_layout(self.handle, self.flags, out))
+        return dict(zip(LAYOUT_FIELDS, list(out)))
+
+    def workspace_view(self, Bn):
+        """Workspace of the last device solve as a [B, total] tensor (debugging / tests)."""
+        L = self.layout()
+        ws = self._ws.view(self.torch_dtype)
+        return ws[: Bn * L["total"]].view(Bn, L["total"]), L
