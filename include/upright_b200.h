@@ -213,6 +213,15 @@ int ub_eval(ub_problem_t* problem, const char* name, int32_t M, const double* x,
             const double* body_params /*[M,nb,10] or NULL*/, double* out, int32_t out_capacity,
             int32_t* rows_out);
 
+/* Runtime options: "sqp_iteration" (init_sqp_iteration vs sqp_iteration,
+ * controller.yaml:56-57) and the test aid "stop_after" (0 full solve, 1 stop
+ * after the first linearisation, 2 after the first QP). */
+int ub_set_option(ub_problem_t* problem, const char* key, int value);
+
+/* Per-instance workspace layout (offsets in elements) for tests that inspect
+ * intermediate blocks; see upright_b200/engine.py LAYOUT_FIELDS. */
+int ub_workspace_layout(const ub_problem_t* problem, uint32_t flags, int32_t out[32]);
+
 /* Device time of the last ub_solve_batch on this problem (CUDA events), ms.
  * Replaces getLastSolveTime() (controller_python_interface.h:27-29). */
 float ub_last_solve_ms(const ub_problem_t* problem);

@@ -1,0 +1,244 @@
+"""Parity of the CUDA path (through the C ABI) against the fp64 CPU oracle on
+the same seeded inputs, plus size-independent properties at the full BASELINE
+batch sizes.
+
+Stated tolerances:
+  fp64 kernels : |X - X_oracle|, |U - U_oracle| <= 1e-7 (same algorithm, same arithmetic width)
+  fp32 kernels : errors scaled by the limit range of each component
+                 (state_ub - state_lb, input_ub - input_lb, force_ub - force_lb):
+                 worst instance <= 1e-2, 95 % of instances <= 2e-3, median <= 1e-4;
+                 linearisation blocks abs 2e-5.
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+from _util import has_cuda  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+if not has_cuda():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+import torch  # noqa: E402
+
+import oracle  # noqa: E402
+from upright_b200 import problem_io, workload  # noqa: E402
+from upright_b200.engine import BatchedMPC  # noqa: E402
+
+CFGS = list(problem_io.FIXTURES)
+_cache = {}
+
+
+def engine(name, prec):
+    key = (name, prec)
+    if key not in _cache:
+        desc, meta = problem_io.load_fixture(name)
+        _cache[key] = (BatchedMPC(desc, prec), desc, meta)
+    return _cache[key]
+
+
+def batch_for(name, B, seed):
+    mpc, desc, meta = engine(name, "f64")
+    ee = lambda x: mpc.eval("end_effector_position", x, np.zeros((x.shape[0], mpc.nu)))  # noqa: E731
+    return workload.sample_batch(name, desc, meta, B, seed, ee)
+
+
+def ranges(desc):
+    nq, nx, nu = desc.nq, desc.nx, desc.nu
+    rx = np.array(desc.state_ub[:nx]) - np.array(desc.state_lb[:nx])
+    ru = np.concatenate([np.array(desc.input_ub[:nq]) - np.array(desc.input_lb[:nq]),
+                         np.full(nu - nq, desc.force_ub - desc.force_lb)])
+    return rx, ru
+
+
+@pytest.mark.parametrize("name", CFGS)
+def test_probes_match_oracle(name):
+    mpc, desc, meta = engine(name, "f64")
+    rng = np.random.default_rng(0)
+    M = 16
+    x = np.tile(meta["x0"], (M, 1)) + 0.2 * rng.standard_normal((M, desc.nx))
+    u = rng.standard_normal((M, desc.nu))
+    r = mpc.eval("end_effector_position", x, u)
+    g = mpc.eval("object_dynamics", x, u)
+    for m in range(M):
+        lin = oracle.linearize(desc, x[m], u[m])
+        assert np.allclose(r[m], lin["r"], atol=1e-12)
+        assert np.allclose(g[m], lin["g"], atol=1e-11)
+    if desc.n_fric:
+        h = mpc.eval("contact_forces", x, u)
+        assert np.allclose(h[0], oracle.linearize(desc, x[0], u[0])["hfric"], atol=1e-12)
+    if desc.n_obs:
+        h = mpc.eval("obstacle_avoidance", x, u)
+        assert np.allclose(h[3], oracle.linearize(desc, x[3], u[3])["hobs"], atol=1e-12)
+
+
+@pytest.mark.parametrize("name", CFGS)
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_linearisation_blocks(name, prec):
+    mpc, desc, meta = engine(name, prec)
+    b = batch_for(name, 4, 3)
+    dt = mpc.torch_dtype
+    mpc.set_option("stop_after", 1)
+    try:
+        mpc.solve_device(torch.tensor(b["x0"], dtype=dt, device="cuda"), torch.tensor(b["target"], dtype=dt, device="cuda"),
+                         None if b["body_params"] is None else torch.tensor(b["body_params"], dtype=dt, device="cuda"))
+        torch.cuda.synchronize()
+        ws, L = mpc.workspace_view(4)
+        ws = ws.cpu().double().numpy()
+    finally:
+        mpc.set_option("stop_after", 0)
+    tol = 1e-12 if prec == "f64" else 2e-5
+    N, nx, nq, neq = desc.N, desc.nx, desc.nq, mpc.n_eq
+    for inst in range(4):
+        bp = None if b["body_params"] is None else b["body_params"][inst]
+        lin = oracle.linearize(desc, b["x0"][inst], np.zeros(desc.nu), bp)
+        k = 5  # cold start: every knot is linearised at x0, u = 0
+        Jp = ws[inst, L["LJP"] + k * 3 * nq: L["LJP"] + (k + 1) * 3 * nq].reshape(3, nq)
+        assert np.allclose(Jp, lin["Jp"], atol=tol)
+        assert np.allclose(ws[inst, L["LR"] + 3 * k: L["LR"] + 3 * k + 3], lin["r"], atol=tol)
+        if neq:
+            CT = ws[inst, L["LCT"] + k * nx * neq: L["LCT"] + (k + 1) * nx * neq].reshape(nx, neq)
+            assert np.allclose(CT.T, lin["C"], atol=tol)
+            assert np.allclose(ws[inst, L["LG"] + k * neq: L["LG"] + (k + 1) * neq], lin["g"], atol=tol)
+            Df = ws[inst, L["DF"]: L["DF"] + neq * (desc.nu - nq)].reshape(neq, -1)
+            assert np.allclose(Df, lin["Df"], atol=tol)
+        if desc.n_obs:
+            assert np.allclose(ws[inst, L["LHO"] + k * desc.n_obs: L["LHO"] + (k + 1) * desc.n_obs], lin["hobs"], atol=tol)
+            Jo = ws[inst, L["LJO"] + k * desc.n_obs * nq: L["LJO"] + (k + 1) * desc.n_obs * nq].reshape(-1, nq)
+            assert np.allclose(Jo, lin["Jobs"], atol=tol)
+
+
+@pytest.mark.parametrize("name", CFGS)
+def test_full_solve_fp64_matches_oracle(name):
+    mpc, desc, meta = engine(name, "f64")
+    b = batch_for(name, 32, 11)
+    out = mpc.solve(b["x0"], b["target"], b["body_params"], want_gains=True)
+    ref = oracle.solve_batch(desc, b["x0"], b["target"], b["body_params"], want_gains=True)
+    assert np.array_equal(out["status"], ref["status"])
+    good = ref["status"] == 0
+    assert good.mean() >= 0.75, f"only {good.mean():.2f} of the oracle solves converged"
+    assert np.array_equal(out["stats"][good, 0], ref["stats"][good, 0])          # same IPM iteration counts
+    assert np.abs(out["X"][good] - ref["X"][good]).max() < 1e-7
+    assert np.abs(out["U"][good] - ref["U"][good]).max() < 1e-7
+    assert np.allclose(out["stats"][good, 1:4], ref["stats"][good, 1:4], rtol=1e-7, atol=1e-9)
+    assert np.abs(out["K"][good] - ref["K"][good]).max() < 1e-5 * max(1.0, np.abs(ref["K"][good]).max())
+
+
+@pytest.mark.parametrize("name", CFGS)
+def test_full_solve_fp32_within_stated_tolerance(name):
+    mpc, desc, meta = engine(name, "f32")
+    B = 128 if desc.nu <= 13 else 48
+    b = batch_for(name, B, 21)
+    out = mpc.solve(b["x0"], b["target"], b["body_params"])
+    ref = oracle.solve_batch(desc, b["x0"], b["target"], b["body_params"])
+    good = (ref["status"] == 0) & (out["status"] == 0)
+    assert good.mean() >= 0.7
+    rx, ru = ranges(desc)
+    ex = (np.abs(out["X"] - ref["X"]) / rx).reshape(B, -1).max(1)[good]
+    eu = (np.abs(out["U"] - ref["U"]) / ru).reshape(B, -1).max(1)[good]
+    e = np.maximum(ex, eu)
+    print(f"{name}: fp32 scaled error max {e.max():.2e} p95 {np.percentile(e, 95):.2e} median {np.median(e):.2e}")
+    assert e.max() <= 1e-2 and np.percentile(e, 95) <= 2e-3 and np.median(e) <= 1e-4
+    # constraint residuals of the reference's own functions on the returned trajectory
+    assert np.allclose(out["stats"][good, 2], ref["stats"][good, 2], rtol=2e-2, atol=2e-3)   # violation
+    assert np.allclose(out["stats"][good, 1], ref["stats"][good, 1], rtol=1e-2, atol=1e-3)   # cost
+
+
+def test_device_path_equals_host_path():
+    mpc, desc, meta = engine("cfg2_thing_demo", "f32")
+    b = batch_for("cfg2_thing_demo", 64, 5)
+    host = mpc.solve(b["x0"], b["target"], b["body_params"])
+    dev = mpc.solve_device(torch.tensor(b["x0"], dtype=torch.float32, device="cuda"),
+                           torch.tensor(b["target"], dtype=torch.float32, device="cuda"),
+                           torch.tensor(b["body_params"], dtype=torch.float32, device="cuda"))
+    torch.cuda.synchronize()
+    assert np.array_equal(dev["X"].cpu().numpy().astype(np.float64), host["X"])
+    assert np.array_equal(dev["U"].cpu().numpy().astype(np.float64), host["U"])
+    assert np.array_equal(dev["status"].cpu().numpy(), host["status"])
+
+
+def test_full_batch_properties_cfg2():
+    """BASELINE size (4096 instances): properties that need no oracle solve of that size."""
+    name = "cfg2_thing_demo"
+    mpc, desc, meta = engine(name, "f32")
+    B = workload.BASELINE_BATCH[name]
+    b = batch_for(name, B, 99)
+    out = mpc.solve(b["x0"], b["target"], b["body_params"])
+    again = mpc.solve(b["x0"], b["target"], b["body_params"])
+    assert np.array_equal(out["X"], again["X"]) and np.array_equal(out["U"], again["U"])    # deterministic
+    assert set(np.unique(out["status"])) <= {0, 1, 2}
+    assert (out["status"] == 0).mean() > 0.98
+    assert np.all(np.isfinite(out["X"])) and np.all(np.isfinite(out["U"]))
+    X, U = out["X"], out["U"]
+    assert np.allclose(X[:, 0], b["x0"], atol=1e-6)                                          # x_0 is the observation
+    # accepted full steps are dynamically consistent: x_{k+1} = A x_k + B u_k (exact discretisation)
+    nq, dt = desc.nq, desc.dt
+    full = out["stats"][:, 3] == 1.0
+    q, v, a, j = X[:, :-1, :nq], X[:, :-1, nq:2 * nq], X[:, :-1, 2 * nq:], U[:, :, :nq]
+    gq = q + dt * v + 0.5 * dt * dt * a + dt**3 / 6 * j - X[:, 1:, :nq]
+    gv = v + dt * a + 0.5 * dt * dt * j - X[:, 1:, nq:2 * nq]
+    ga = a + dt * j - X[:, 1:, 2 * nq:]
+    gap = np.maximum(np.abs(gq).max((1, 2)), np.maximum(np.abs(gv).max((1, 2)), np.abs(ga).max((1, 2))))
+    assert full.mean() > 0.9 and gap[full].max() < 2e-4
+    # reported cost / violation are the oracle's performance index of the returned trajectory
+    idx = np.random.default_rng(0).choice(B, 64, replace=False)
+    for i in idx:
+        pf = oracle.performance(desc, b["target"][i], X[i], U[i], b["body_params"][i])
+        assert np.isclose(pf["cost"], out["stats"][i, 1], rtol=2e-4, atol=1e-5)
+        assert np.isclose(pf["violation"], out["stats"][i, 2], rtol=2e-3, atol=1e-4)
+    # a second (warm-started) SQP iteration lowers the constraint violation on almost all instances
+    warm = mpc.solve(b["x0"], b["target"], b["body_params"], X=X, U=U, warm=True)
+    assert (warm["stats"][:, 2] < out["stats"][:, 2]).mean() > 0.9
+    # sampled instances agree with the oracle
+    sub = idx[:16]
+    ref = oracle.solve_batch(desc, b["x0"][sub], b["target"][sub], b["body_params"][sub])
+    rx, ru = ranges(desc)
+    assert (np.abs(X[sub] - ref["X"]) / rx).max() < 1e-2 and (np.abs(U[sub] - ref["U"]) / ru).max() < 1e-2
+
+
+@pytest.mark.parametrize("name", ["cfg3_thing_box_arch", "cfg5_thing_robust8"])
+def test_full_batch_runs(name):
+    mpc, desc, meta = engine(name, "f32")
+    B = 1024
+    b = batch_for(name, B, 17)
+    out = mpc.solve(b["x0"], b["target"], b["body_params"])
+    assert np.all(np.isfinite(out["X"])) and (out["status"] <= 1).mean() > 0.97
+    assert (out["status"] == 0).mean() > 0.9
+
+
+def test_controller_manager_drop_in():
+    """mpc_sim.py-style closed loop through the reference-facing surface
+    (manager.py:156-176 semantics) with the double-integrator plant of
+    mpc_sim.py:148-155."""
+    from upright_b200.manager import ControllerManager
+    from upright_b200.trajectory import DoubleIntegrator
+    desc, meta = problem_io.load_fixture("cfg2_thing_demo")
+    cfg = meta["controller_config"]
+    mgr = ControllerManager.from_config(cfg, x0=np.array(meta["x0"]))
+    dims = mgr.model.settings.dims
+    nq = dims.robot.q
+    assert mgr.mpc.getStateDim() == 27 and mgr.mpc.getInputDim() == 13
+    x = np.array(meta["x0"], dtype=float)
+    integ = DoubleIntegrator(nq)
+    dt_sim, t = 0.01, 0.0
+    r0 = mgr.mpc._engine.eval("end_effector_position", x, np.zeros(13))[0]
+    goal = r0 + np.array([-0.25, 0.5, 0.25])  # thing_demo.yaml:55
+    dist0 = np.linalg.norm(goal - r0)
+    for step in range(150):
+        xd, u = mgr.step(t, x)
+        assert np.all(np.isfinite(u))
+        q, v, a = x[:nq], x[nq:2 * nq], x[2 * nq:]
+        v_new, a_new = integ.integrate(v, a, u[:nq], dt_sim)
+        q = q + dt_sim * v + 0.5 * dt_sim**2 * a + dt_sim**3 / 6 * u[:nq]
+        x = np.concatenate((q, v_new, a_new))
+        t += dt_sim
+    assert len(mgr.replanning_times) >= 100                     # replans every min_policy_update_time
+    r = mgr.mpc._engine.eval("end_effector_position", x, np.zeros(13))[0]
+    assert np.linalg.norm(goal - r) < 0.6 * dist0               # moving toward the waypoint
+    g = mgr.mpc.getStateInputEqualityConstraintValue("object_dynamics", t, x, u)
+    assert np.abs(g).max() < 0.5                                # balancing residual stays small
+    ts, xs, us = mgr.get_mpc_trajectory()
+    assert ts.shape == (21,) and xs.shape == (21, 27) and us.shape == (21, 13)

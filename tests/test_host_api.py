@@ -1,0 +1,141 @@
+"""Host-side logic that needs no GPU: settings parsing from the reference's own
+YAML (when present) against the committed fixtures, target trajectories,
+workload generator, receding-horizon bookkeeping with a stub engine."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from upright_b200 import config, problem_io, settings, workload
+from upright_b200.settings import TargetTrajectories
+
+REF = Path("/root/reference")
+
+
+def test_fixture_dimensions_match_survey_table():
+    expect = {  # SURVEY.md §8 dimension table: nq, nx, nb, nc, nf, nu, eq, N
+        "cfg1_ur10_demo": (6, 18, 1, 4, 1, 10, 6, 20),
+        "cfg2_thing_demo": (9, 27, 1, 4, 1, 13, 6, 20),
+        "cfg3_thing_box_arch": (9, 27, 3, 16, 3, 57, 18, 20),
+        "cfg4_thing_obstacles2": (9, 27, 1, 4, 1, 13, 6, 20),
+        "cfg5_thing_robust8": (9, 27, 8, 32, 1, 41, 48, 20),
+    }
+    for name, e in expect.items():
+        d, _ = problem_io.load_fixture(name)
+        assert (d.nq, d.nx, d.nb, d.nc, d.nf, d.nu, d.n_eq, d.N) == e, name
+    d3, _ = problem_io.load_fixture("cfg3_thing_box_arch")
+    assert d3.n_fric == 80
+    d4, _ = problem_io.load_fixture("cfg4_thing_obstacles2")
+    assert d4.n_obs == 12 and d4.slacks.enabled == 0
+    d5, _ = problem_io.load_fixture("cfg5_thing_robust8")
+    assert d5.slacks.enabled == 1 and d5.slacks.input_box == 0 and d5.force_weight == 0.0
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree only in the build container")
+@pytest.mark.parametrize("name", list(problem_io.FIXTURES))
+def test_fixtures_regenerate_from_reference_yaml(name):
+    rel = problem_io.FIXTURES[name]
+    pkg, path = rel.split("/", 1)
+    cfg = config.load_config(config.resolve_package_path({"package": pkg, "path": path}))
+    s = settings.ControllerSettings(cfg["controller"])
+    fresh = problem_io.desc_to_dict(s.to_desc())
+    stored = problem_io.desc_to_dict(problem_io.load_fixture(name)[0])
+
+    def close(a, b):
+        if isinstance(a, dict):
+            return all(close(a[k], b[k]) for k in a)
+        if isinstance(a, list):
+            return all(close(x, y) for x, y in zip(a, b))
+        return np.isclose(a, b, rtol=1e-12, atol=1e-12)
+    assert close(fresh, stored)
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree only in the build container")
+def test_settings_surface_thing_demo():
+    cfg = config.load_config(REF / "upright_cmd/config/demos/thing_demo.yaml")["controller"]
+    s = settings.ControllerSettings(cfg)
+    assert s.mpc.time_horizon == 2.0 and s.sqp.dt == 0.1 and s.sqp.sqp_iteration == 1
+    assert s.sqp.hpipm.iter_max == 30 and s.sqp.hpipm.slacks.enabled is True
+    assert s.sqp.hpipm.slacks.upper_L2_penalty == 100
+    assert (s.dims.robot.q, s.dims.robot.x, s.dims.c, s.dims.nf) == (9, 27, 4, 1)
+    assert s.dims.x() == 27 and s.dims.u() == 13 and s.dims.f() == 4
+    assert np.allclose(np.diag(s.state_weight), 0.01 * np.r_[np.zeros(9), 10 * np.ones(9), np.ones(9)])
+    assert np.allclose(np.diag(s.input_weight), 0.001)
+    assert s.balancing_settings.force_weight == 0.001
+    assert np.allclose(s.gravity, [0, 0, -9.81])
+    assert np.allclose(s.initial_state[:9], [-1, 1, 0, 0.5 * np.pi, -0.25 * np.pi, 0.5 * np.pi, -0.25 * np.pi, 0.5 * np.pi, 0.417 * np.pi])
+    assert s.tracking.min_policy_update_time == 0.01
+
+
+def test_orientation_weight_is_rejected_loudly():
+    d, _ = problem_io.load_fixture("cfg2_thing_demo")
+    if REF.exists():
+        cfg = config.load_config(REF / "upright_cmd/config/demos/thing_demo.yaml")["controller"]
+        cfg["weights"]["end_effector"]["diag"] = [1, 1, 1, 1, 0, 0]
+        with pytest.raises(NotImplementedError):
+            settings.ControllerSettings(cfg).to_desc()
+
+
+def test_target_trajectories_interpolation():
+    u = np.zeros(3)
+    tt = TargetTrajectories([0.0, 2.0], [np.r_[0, 0, 0, 0, 0, 0, 1, 0], np.r_[2, 4, 6, 0, 0, 0, 1, 0]], [u, u])
+    assert np.allclose(tt.get_desired_state(1.0)[:3], [1, 2, 3])
+    assert np.allclose(tt.get_desired_state(-1.0)[:3], [0, 0, 0])
+    assert np.allclose(tt.get_desired_state(5.0)[:3], [2, 4, 6])
+    assert np.allclose(tt.positions_at([0.5, 1.5]), [[0.5, 1, 1.5], [1.5, 3, 4.5]])
+    cfg_wp = {"waypoints": [{"time": 0, "position": [-0.25, 0.5, 0.25], "orientation": [0, 0, 0, 1]}]}
+    t2 = TargetTrajectories.from_config(cfg_wp, np.array([1.0, 1, 1]), np.array([0, 0, 0, 1.0]), u)
+    assert np.allclose(t2.xs[0], [0.75, 1.5, 1.25, 0, 0, 0, 1, 0])
+
+
+def test_workload_is_seeded_and_shaped():
+    d, meta = problem_io.load_fixture("cfg2_thing_demo")
+    ee = lambda x: np.zeros((x.shape[0], 3))  # noqa: E731
+    a = workload.sample_batch("cfg2_thing_demo", d, meta, 16, 5, ee)
+    b = workload.sample_batch("cfg2_thing_demo", d, meta, 16, 5, ee)
+    assert np.array_equal(a["x0"], b["x0"]) and np.array_equal(a["target"], b["target"])
+    assert a["x0"].shape == (16, 27) and a["target"].shape == (16, 21, 3) and a["body_params"].shape == (16, 1, 10)
+    assert np.all(a["x0"][:, 9:] == 0)
+    assert workload.algorithmic_bytes_per_solve(d) == 3744  # cfg2 3 744 B
+
+
+def test_receding_horizon_shift_with_stub_engine():
+    """Warm-start shift + policy evaluation of manager._RecedingHorizon."""
+    from types import SimpleNamespace
+
+    from upright_b200.manager import _RecedingHorizon
+
+    N, nx, nu = 4, 3, 2
+
+    class Stub:
+        def __init__(self):
+            self.N, self.nx, self.nu = N, nx, nu
+            self.calls = []
+
+        def set_option(self, *a):
+            pass
+
+        def solve(self, x0, target, body, X=None, U=None, warm=False, want_gains=False):
+            self.calls.append(dict(warm=warm, X=None if X is None else X.copy(), U=None if U is None else U.copy()))
+            B = x0.shape[0]
+            Xo = np.stack([x0 + k for k in range(N + 1)], axis=1)
+            Uo = np.stack([np.full((B, nu), float(k)) for k in range(N)], axis=1)
+            return dict(X=Xo, U=Uo, status=np.zeros(B, np.int32), stats=np.zeros((B, 8)), K=np.zeros((B, N, nu, nx)))
+
+    st = SimpleNamespace(sqp=SimpleNamespace(dt=0.1, use_feedback_policy=True, init_sqp_iteration=1, sqp_iteration=1),
+                         mpc=SimpleNamespace(cold_start=False))
+    eng = Stub()
+    rh = _RecedingHorizon(eng, st, 1)
+    tt = TargetTrajectories([0.0], [np.r_[1, 2, 3, 0, 0, 0, 1, 0]], [np.zeros(nu)])
+    rh.reset([tt])
+    rh.observe(0.0, np.zeros((1, nx)))
+    rh.advance()
+    assert eng.calls[0]["warm"] is False
+    x, u = rh.evaluate(0.05, np.zeros((1, nx)))
+    assert np.allclose(x, 0.5) and np.allclose(u, 0.5)   # linear interpolation between knots 0 and 1
+    rh.observe(0.1, np.ones((1, nx)))
+    rh.advance()
+    assert eng.calls[1]["warm"] is True
+    # previous solution shifted by exactly one knot, tail held
+    assert np.allclose(eng.calls[1]["X"][0, :, 0], [1, 2, 3, 4, 4])
+    assert np.allclose(eng.calls[1]["U"][0, :, 0], [1, 2, 3, 3])

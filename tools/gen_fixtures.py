@@ -32,6 +32,9 @@ def main():
             "contact_names": [[c.object1_name, c.object2_name] for c in s.balancing_settings.contacts],
             "frictionless": bool(desc.nf == 1),
             "plane_spans": [np.asarray(c.span).tolist() for c in s.balancing_settings.contacts],
+            # merged controller dictionary (what ControllerSettings(config) consumes), so the
+            # reference-facing surface can be driven on the GPU box without the YAML tree
+            "controller_config": cfg["controller"],
         }
         problem_io.save_fixture(name, desc, meta)
         print(f"{name}: nq={desc.nq} nx={desc.nx} nu={desc.nu} nb={desc.nb} nc={desc.nc} nf={desc.nf} "

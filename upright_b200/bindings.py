@@ -152,7 +152,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "ub_last_error", "ub_version", "ub_problem_create", "ub_problem_destroy",
     "ub_problem_dims", "ub_workspace_bytes", "ub_solve_batch", "ub_eval",
-    "ub_last_solve_ms", "ub_launch_count",
+    "ub_last_solve_ms", "ub_launch_count", "ub_set_option", "ub_workspace_layout",
 ]
 
 

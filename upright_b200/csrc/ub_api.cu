@@ -408,6 +408,14 @@ int ub_set_option(ub_problem_t* p, const char* key, int value) {
         p->stop_after = value;
         return UB_OK;
     }
+    if (std::strcmp(key, "sqp_iteration") == 0) {  // sqp_iteration vs init_sqp_iteration (controller.yaml:56-57)
+        if (value < 1) return fail(UB_E_INVALID, "sqp_iteration must be >= 1");
+        if (p->hf.sqp_iters == value) return UB_OK;
+        p->desc.sqp_iteration = p->hf.sqp_iters = p->hd.sqp_iters = value;
+        UB_CUDA(cudaMemcpy(p->df, &p->hf, sizeof(p->hf), cudaMemcpyHostToDevice));
+        UB_CUDA(cudaMemcpy(p->dd, &p->hd, sizeof(p->hd), cudaMemcpyHostToDevice));
+        return UB_OK;
+    }
     return fail(UB_E_INVALID, std::string("unknown option ") + key);
 }
 int ub_workspace_layout(const ub_problem_t* p, uint32_t flags, int32_t out[32]) {

@@ -1,0 +1,313 @@
+"""Reference-facing control surface: `ControllerInterface`, `ControllerModel`,
+`ControllerManager` with the method names and semantics of the reference
+(`upright_control/src/pybindings.cpp:364-427`,
+`upright_control/src/upright_control/manager.py:14-209`), backed by the CUDA
+library through `engine.BatchedMPC`, plus `BatchedControllerManager` which
+drives B instances at once (the receding-horizon shift, policy evaluation and
+replan gate stay on the host in numpy, as they stay in Python in the
+reference).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import geometry as geo
+from .engine import BatchedMPC
+from .settings import ControllerSettings, TargetTrajectories
+from .trajectory import StateInputTrajectory, interp_rows
+
+
+class _RobotKinematics:
+    """Host-side pose queries (role of `UprightRobotKinematics`, robot.py)."""
+
+    def __init__(self, chain):
+        self.chain = chain
+        self._q = None
+
+    def forward_xu(self, x, u=None):
+        self._q = np.asarray(x)[: self.chain.nq]
+
+    def link_pose(self):
+        r, C = self.chain.tool_pose(self._q)
+        return r, geo.rot_to_quat(C)
+
+
+class ControllerModel:
+    def __init__(self, settings):
+        self.settings = settings
+        self.robot = _RobotKinematics(settings.chain)
+        self.geom = None
+
+    @classmethod
+    def from_config(cls, config, x0=None):
+        return cls(ControllerSettings(config=config, x0=x0))
+
+    def update(self, x, u=None):
+        self.robot.forward_xu(x, u)
+
+
+class ControllerInterface:
+    """Single-robot MPC object (batch of one) with the pybind method surface."""
+
+    def __init__(self, settings, precision="f32"):
+        self.settings = settings
+        self.desc = settings.to_desc()
+        self._engine = BatchedMPC(self.desc, precision)
+        self._core = _RecedingHorizon(self._engine, settings, batch=1)
+        self._last_ms = 0.0
+
+    def getStateDim(self):
+        return self._engine.nx
+
+    def getInputDim(self):
+        return self._engine.nu
+
+    def setObservation(self, t, x, u):
+        self._core.observe(t, np.asarray(x, dtype=float)[None, :])
+
+    def setTargetTrajectories(self, targets):
+        self._core.targets = [targets]
+
+    def reset(self, targets):
+        self._core.reset([targets])
+
+    def advanceMpc(self):
+        self._core.advance()
+
+    def getLastSolveTime(self):
+        return self._engine.last_solve_ms()
+
+    def getMpcSolution(self, ts, xs, us):
+        """Out-parameters like the bound std::vectors: python lists are extended."""
+        T, X, U = self._core.solution()
+        ts.extend(T.tolist())
+        xs.extend(list(X[0]))
+        us.extend(list(np.vstack((U[0], U[0][-1:]))))
+
+    def evaluateMpcSolution(self, current_time, current_state, opt_state, opt_input):
+        x, u = self._core.evaluate(current_time, np.asarray(current_state, dtype=float)[None, :])
+        opt_state[:] = x[0]
+        opt_input[:] = u[0]
+
+    def getLinearFeedbackGain(self, t):
+        return self._core.gain(t)[0]
+
+    def getBias(self, t):
+        return self._core.bias(t)[0]
+
+    def cost(self, t, x, u):
+        tgt = self._core.targets[0].get_desired_state(t)[:3]
+        return float(self._engine.eval("cost", x, u, target=tgt[None])[0, 0])
+
+    def getCostValue(self, name, t, x, u):
+        if name not in ("state_input_cost", "end_effector_cost"):
+            raise RuntimeError(f"unknown cost {name}")
+        total = self.cost(t, x, u)
+        zero_w = self._engine.eval("cost", x, u)[0, 0]  # without the EE term
+        return float(zero_w if name == "state_input_cost" else total - zero_w)
+
+    def getStateInputEqualityConstraintValue(self, name, t, x, u):
+        if name != "object_dynamics":
+            raise RuntimeError(f"unknown equality constraint {name}")
+        return self._engine.eval("object_dynamics", x, u)[0]
+
+    def getStateInputInequalityConstraintValue(self, name, t, x, u):
+        if name not in ("contact_forces", "obstacle_avoidance"):
+            raise RuntimeError(f"unknown inequality constraint {name}")
+        return self._engine.eval(name, x, u)[0]
+
+
+class _RecedingHorizon:
+    """Receding-horizon bookkeeping for B instances: observation, warm-start
+    shift of the previous solution onto the new time grid, policy evaluation.
+    Semantics of ocs2 MPC_MRT_Interface as used at manager.py:156-176 [EXT]."""
+
+    def __init__(self, engine, settings, batch):
+        self.engine, self.settings, self.B = engine, settings, batch
+        self.dt = settings.sqp.dt
+        self.N = engine.N
+        self.targets = None
+        self.t_obs, self.x_obs = 0.0, None
+        self.t0 = None
+        self.X = self.U = self.K = None
+        self.first = True
+        self.status = None
+        self.stats = None
+        self.use_feedback = bool(settings.sqp.use_feedback_policy)
+        self.body_params = None
+
+    def reset(self, targets):
+        self.targets = targets
+        self.X = self.U = self.K = None
+        self.t0 = None
+        self.first = True
+
+    def observe(self, t, x):
+        self.t_obs, self.x_obs = float(t), np.array(x, dtype=float)
+
+    def _knot_targets(self, t):
+        times = t + self.dt * np.arange(self.N + 1)
+        tg = np.empty((self.B, self.N + 1, 3))
+        for b in range(self.B):
+            tt = self.targets[b if len(self.targets) > 1 else 0]
+            tg[b] = tt.positions_at(times)
+        return tg
+
+    def advance(self):
+        t = self.t_obs
+        warm = (self.X is not None) and not self.settings.mpc.cold_start
+        X = U = None
+        if warm:
+            # previous primal solution interpolated at the new grid, tail held
+            told = self.t0 + self.dt * np.arange(self.N + 1)
+            tnew = t + self.dt * np.arange(self.N + 1)
+            X = np.empty_like(self.X)
+            U = np.empty_like(self.U)
+            Uext = np.concatenate((self.U, self.U[:, -1:, :]), axis=1)
+            for k in range(self.N + 1):
+                i = int(np.clip(np.searchsorted(told, tnew[k], side="right") - 1, 0, self.N - 1))
+                w = np.clip((tnew[k] - told[i]) / self.dt, 0.0, 1.0)
+                X[:, k] = (1 - w) * self.X[:, i] + w * self.X[:, i + 1]
+                if k < self.N:
+                    U[:, k] = (1 - w) * Uext[:, i] + w * Uext[:, i + 1]
+        iters = self.settings.sqp.init_sqp_iteration if self.first else self.settings.sqp.sqp_iteration
+        self.engine.set_option("sqp_iteration", int(iters))
+        out = self.engine.solve(self.x_obs, self._knot_targets(t), self.body_params, X=X, U=U, warm=warm,
+                                want_gains=self.use_feedback)
+        self.X, self.U = out["X"], out["U"]
+        self.K = out.get("K")
+        self.status, self.stats = out["status"], out["stats"]
+        self.t0 = t
+        self.first = False
+        if np.any(self.status == 3):
+            raise RuntimeError("MPC solve produced non-finite values")
+
+    def solution(self):
+        return self.t0 + self.dt * np.arange(self.N + 1), self.X, self.U
+
+    def _interp(self, t):
+        s = (t - self.t0) / self.dt
+        i = int(np.clip(np.floor(s), 0, self.N - 1))
+        w = float(np.clip(s - i, 0.0, 1.0))
+        return i, w
+
+    def gain(self, t):
+        if self.K is None:
+            return np.zeros((self.B, self.engine.nu, self.engine.nx))
+        i, w = self._interp(t)
+        j = min(i + 1, self.N - 1)
+        return (1 - w) * self.K[:, i] + w * self.K[:, j]
+
+    def evaluate(self, t, x):
+        i, w = self._interp(t)
+        x_nom = (1 - w) * self.X[:, i] + w * self.X[:, i + 1]
+        j = min(i + 1, self.N - 1)
+        u_ff = (1 - w) * self.U[:, i] + w * self.U[:, j]
+        if self.use_feedback and self.K is not None:
+            u = u_ff + np.einsum("bij,bj->bi", self.gain(t), x - x_nom)
+        else:
+            u = u_ff
+        return x_nom, u
+
+    def bias(self, t):
+        x_nom, _ = self.evaluate(t, np.zeros((self.B, self.engine.nx)))
+        i, w = self._interp(t)
+        j = min(i + 1, self.N - 1)
+        u_ff = (1 - w) * self.U[:, i] + w * self.U[:, j]
+        return u_ff - np.einsum("bij,bj->bi", self.gain(t), x_nom)
+
+
+class ControllerManager:
+    """manager.py:100-209 — replan gate + policy evaluation for one robot."""
+
+    def __init__(self, model, ref_trajectory, timestep, precision="f32"):
+        self.model = model
+        self.ref = ref_trajectory
+        self.timestep = timestep
+        self.mpc = ControllerInterface(self.model.settings, precision)
+        self.mpc.reset(self.ref)
+        self.last_planning_time = -np.inf
+        self.x_opt = np.zeros(self.model.settings.dims.x())
+        self.u_opt = np.zeros(self.model.settings.dims.u())
+        self.replanning_times = []
+        self.replanning_durations = []
+
+    @classmethod
+    def from_config(cls, config, x0=None, precision="f32"):
+        model = ControllerModel.from_config(config, x0=x0)
+        timestep = config["tracking"]["min_policy_update_time"]
+        model.update(x=model.settings.initial_state)
+        r_ew_w, Q_we = model.robot.link_pose()
+        ref = TargetTrajectories.from_config(config, r_ew_w, Q_we, np.zeros(model.settings.dims.u()))
+        return cls(model, ref, timestep, precision)
+
+    def update(self, ref):
+        self.ref = ref
+        self.mpc.reset(self.ref)
+
+    def warmstart(self):
+        x0 = self.model.settings.initial_state
+        self.mpc.setObservation(0, x0, np.zeros(self.model.settings.dims.u()))
+        self.mpc.advanceMpc()
+        self.last_planning_time = 0
+
+    def step(self, t, x):
+        self.mpc.setObservation(t, x, self.u_opt)
+        if t >= self.last_planning_time + self.timestep:
+            t0 = time.time()
+            self.mpc.advanceMpc()
+            t1 = time.time()
+            self.last_planning_time = t
+            self.replanning_times.append(t)
+            self.replanning_durations.append(t1 - t0)
+        self.mpc.evaluateMpcSolution(t, x, self.x_opt, self.u_opt)
+        return self.x_opt, self.u_opt
+
+    def get_mpc_trajectory(self):
+        ts, xs, us = [], [], []
+        self.mpc.getMpcSolution(ts, xs, us)
+        return np.array(ts), np.array(xs), np.array(us)
+
+    def plan(self, timestep, duration):
+        ts, xs, us = [], [], []
+        t = 0.0
+        x = self.model.settings.initial_state
+        while t <= duration:
+            x, u = self.step(t, x)
+            ts.append(t)
+            xs.append(x.copy())
+            us.append(u.copy())
+            t += timestep
+        return StateInputTrajectory(ts, xs, us)
+
+
+class BatchedControllerManager:
+    """B robots / scenarios at once: same `step(t, x)` contract with x [B, nx]."""
+
+    def __init__(self, settings, targets, timestep=None, body_params=None, precision="f32"):
+        self.settings = settings
+        self.desc = settings.to_desc()
+        self.engine = BatchedMPC(self.desc, precision)
+        self.B = len(targets)
+        self.core = _RecedingHorizon(self.engine, settings, self.B)
+        self.core.reset(list(targets))
+        self.core.body_params = body_params
+        self.timestep = settings.tracking.min_policy_update_time if timestep is None else timestep
+        self.last_planning_time = -np.inf
+        self.replanning_times, self.replanning_durations = [], []
+
+    def step(self, t, x):
+        x = np.asarray(x, dtype=float)
+        self.core.observe(t, x)
+        if t >= self.last_planning_time + self.timestep:
+            t0 = time.time()
+            self.core.advance()
+            self.replanning_durations.append(time.time() - t0)
+            self.replanning_times.append(t)
+            self.last_planning_time = t
+        return self.core.evaluate(t, x)
+
+    def get_mpc_trajectory(self):
+        return self.core.solution()
