@@ -43,7 +43,8 @@ def engine(name, prec):
 def batch_for(name, B, seed):
     mpc, desc, meta = engine(name, "f64")
     ee = lambda x: mpc.eval("end_effector_position", x, np.zeros((x.shape[0], mpc.nu)))  # noqa: E731
-    return workload.sample_batch(name, desc, meta, B, seed, ee)
+    mg = (lambda x: mpc.eval("obstacle_avoidance", x, np.zeros((x.shape[0], mpc.nu)))) if desc.obstacles_enabled else None
+    return workload.sample_batch(name, desc, meta, B, seed, ee, margin_fn=mg)
 
 
 def ranges(desc):
@@ -124,7 +125,10 @@ def test_full_solve_fp64_matches_oracle(name):
     assert np.abs(out["X"][good] - ref["X"][good]).max() < 1e-7
     assert np.abs(out["U"][good] - ref["U"][good]).max() < 1e-7
     assert np.allclose(out["stats"][good, 1:4], ref["stats"][good, 1:4], rtol=1e-7, atol=1e-9)
-    assert np.abs(out["K"][good] - ref["K"][good]).max() < 1e-5 * max(1.0, np.abs(ref["K"][good]).max())
+    # feedback gains: hard-equality configurations carry proximal weights up to rho_hard/|a|^2 ~ 1e10 in the
+    # stage Hessians, so two fp64 summation orders agree to ~1e-4 relative there
+    ktol = 1e-3 if not desc.slacks.enabled else 1e-6
+    assert np.abs(out["K"][good] - ref["K"][good]).max() < ktol * max(1.0, np.abs(ref["K"][good]).max())
 
 
 @pytest.mark.parametrize("name", CFGS)

@@ -17,7 +17,7 @@ GOAL_BOX = {
     "cfg1_ur10_demo": ([-0.25, -0.25, -0.2], [0.25, 0.25, 0.2]),
     "cfg2_thing_demo": ([-2.0, -2.0, -0.25], [2.0, 1.0, 0.25]),
     "cfg3_thing_box_arch": ([-2.0, -2.0, -0.25], [2.0, 1.0, 0.25]),
-    "cfg4_thing_obstacles2": ([-0.25, -0.25, -0.1], [0.25, 0.25, 0.1]),
+    "cfg4_thing_obstacles2": ([-0.15, -0.15, -0.1], [0.15, 0.15, 0.1]),
     "cfg5_thing_robust8": ([-2.0, -2.0, -0.25], [2.0, 1.0, 0.25]),
 }
 BASELINE_BATCH = {
@@ -29,7 +29,7 @@ BASELINE_BATCH = {
 }
 
 
-def sample_batch(name, desc, meta, B, seed, ee_position_fn, vary_bodies=True, level_tray=None):
+def sample_batch(name, desc, meta, B, seed, ee_position_fn, vary_bodies=True, level_tray=None, margin_fn=None):
     """-> dict(x0 [B,nx], target [B,N+1,3], body_params [B,nb,10] or None).
 
     `ee_position_fn(x [M,nx]) -> [M,3]` evaluates the tool position (GPU probe
@@ -49,11 +49,22 @@ def sample_batch(name, desc, meta, B, seed, ee_position_fn, vary_bodies=True, le
         free = [0, 1, 2, 3]
     else:
         free = [0]
+    if desc.obstacles_enabled and nq == 9:
+        dq[:, 0:2] *= 0.25
+        dq[:, 2] *= 0.5
     if level_tray:
         mask = np.zeros(nq, dtype=bool)
         mask[free] = True
         dq[:, ~mask] = 0.0
     x0[:, :nq] += dq
+    if desc.obstacles_enabled and margin_fn is not None:
+        home = np.asarray(meta["x0"], dtype=float)
+        for _ in range(20):
+            bad = margin_fn(x0).min(axis=1) < 0.02
+            if not bad.any():
+                break
+            scale = rng.uniform(0.0, 1.0, (int(bad.sum()), 1))
+            x0[bad, :nq] = home[:nq] + scale * (x0[bad, :nq] - home[:nq])
     lo, hi = GOAL_BOX.get(name, ([-0.5, -0.5, -0.2], [0.5, 0.5, 0.2]))
     goal = ee_position_fn(x0) + rng.uniform(lo, hi, (B, 3))
     target = np.repeat(goal[:, None, :], N + 1, axis=1)
