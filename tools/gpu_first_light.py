@@ -39,9 +39,10 @@ for name in names:
         lin = oracle.linearize(desc, X0[3], np.zeros(nu))
         neq = mpc.n_eq
         if neq:
-            CT = ws[b, L["LCT"] + 3 * nx * neq: L["LCT"] + 4 * nx * neq].reshape(nx, neq)
+            nz = nx + nu
+            rows = ws[b, L["LCT"] + 3 * neq * nz: L["LCT"] + 4 * neq * nz].reshape(neq, nz)
             g = ws[b, L["LG"] + 3 * neq: L["LG"] + 4 * neq]
-            print(name, prec, "lin: |C-C_or|", np.abs(CT.T - lin["C"]).max(), "|g-g_or|", np.abs(g - lin["g"]).max())
+            print(name, prec, "lin: |C-C_or|", np.abs(rows[:, nu:] - lin["C"]).max(), "|g-g_or|", np.abs(g - lin["g"]).max())
         Jp = ws[b, L["LJP"] + 3 * 3 * nq: L["LJP"] + 4 * 3 * nq].reshape(3, nq)
         print(name, prec, "lin: |Jp|", np.abs(Jp - lin["Jp"]).max(), "|r|", np.abs(ws[b, L["LR"] + 9: L["LR"] + 12] - lin["r"]).max())
         # 2. QP step

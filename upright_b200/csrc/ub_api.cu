@@ -142,7 +142,7 @@ ub::Layout make_layout(const ub::DevProblem<T>& P) {
     L.DZ = take((N + 1) * nz);
     L.GAP = take(N * nx);
     L.LG = take(N * P.neq);
-    L.LCT = take(N * nx * P.neq);
+    L.LCT = take(N * P.neq * nz);
     L.LR = take((N + 1) * 3);
     L.LJP = take((N + 1) * 3 * nq);
     L.LHO = take((N + 1) * P.nobs);
@@ -157,7 +157,7 @@ ub::Layout make_layout(const ub::DevProblem<T>& P) {
     L.DTT = take((N + 1) * P.nrow * 2);
     L.DLAM = take((N + 1) * P.nrow * 2);
     L.VAL = take(4);
-    L.FAC = take(N * nz * L.ldf);
+    L.FAC = take(N * ((nz * L.ldf + 3) & ~3));
     L.WF = take(N * nu);
     L.XN = take((N + 1) * nx);
     L.UN = take(N * nu);
@@ -168,7 +168,7 @@ ub::Layout make_layout(const ub::DevProblem<T>& P) {
         s += (n + 3) / 4 * 4;
         return at;
     };
-    L.sM = stake(nz * L.ldm);
+    L.sM = stake(std::max(nz * L.ldm, (nz * L.ldf + 3) & ~3));
     L.sP = stake(nx * nx);
     L.sPv = stake(nx);
     const int sa_rows = P.neq > 3 ? P.neq : 3;
@@ -230,12 +230,24 @@ int launch_solve(ub_problem* p, const ub::BatchArgs<T>& A, cudaStream_t stream) 
     if (env) wpc = std::max(1, std::min(8, std::atoi(env)));
     const size_t smem = pbytes + per_warp * wpc;
     if (smem > size_t(p->max_smem_optin)) return fail(UB_E_INVALID, "problem too large for shared memory");
-    UB_CUDA(cudaFuncSetAttribute(ub::solve_batch_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     const int grid = (A.B + wpc - 1) / wpc;
-    ub::solve_batch_kernel<T><<<grid, wpc * 32, smem, stream>>>(Pick<T>::dev(p), L, A, wpc);
-    ++g_launches;
-    UB_CUDA(cudaGetLastError());
-    return UB_OK;
+    const ub::DevProblem<T>& H = Pick<T>::host(p);
+    auto go = [&](auto kernel) -> int {
+        UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kernel<<<grid, wpc * 32, smem, stream>>>(Pick<T>::dev(p), L, A, wpc);
+        ++g_launches;
+        UB_CUDA(cudaGetLastError());
+        return UB_OK;
+    };
+    // kernels specialised on the BASELINE dimensions (nq, nf, nc, nb); anything else runs the generic one
+    const bool generic_only = std::getenv("UB_FORCE_GENERIC") != nullptr;
+    if (!generic_only && H.balancing) {
+        if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1) return go(ub::solve_batch_kernel<T, ub::StaticDims<9, 1, 4, 1>>);
+        if (H.nq == 6 && H.nf == 1 && H.nc == 4 && H.nb == 1) return go(ub::solve_batch_kernel<T, ub::StaticDims<6, 1, 4, 1>>);
+        if (H.nq == 9 && H.nf == 3 && H.nc == 16 && H.nb == 3) return go(ub::solve_batch_kernel<T, ub::StaticDims<9, 3, 16, 3>>);
+        if (H.nq == 9 && H.nf == 1 && H.nc == 32 && H.nb == 8) return go(ub::solve_batch_kernel<T, ub::StaticDims<9, 1, 32, 8>>);
+    }
+    return go(ub::solve_batch_kernel<T, ub::RuntimeDims>);
 }
 
 template <typename T>

@@ -52,11 +52,38 @@ struct Perf {
     __device__ __forceinline__ T violation() const { return sqrt(dyn + eq + ineq); }
 };
 
-template <typename T>
+// Compile-time problem dimensions (specialised kernels) or run-time ones (generic kernel).
+template <int NQ_, int NF_, int NC_, int NB_>
+struct StaticDims {
+    static constexpr bool kStatic = true;
+    static constexpr int nq = NQ_, nf = NF_, nc = NC_, nb = NB_;
+    static constexpr int nx = 3 * NQ_, nfc = NF_ * NC_, nu = NQ_ + NF_ * NC_, nz = nu + nx;
+    static constexpr int neq = 6 * NB_, nfric = (NF_ == 3) ? 5 * NC_ : 0;
+    static constexpr int nbox_u = nfc > 0 ? nu : nq;
+};
+struct RuntimeDims {
+    static constexpr bool kStatic = false;
+    static constexpr int nq = 0, nf = 0, nc = 0, nb = 0, nx = 0, nfc = 0, nu = 0, nz = 0, neq = 0, nfric = 0, nbox_u = 0;
+};
+
+template <typename T, typename D>
 struct Solver {
     const DevProblem<T>& P;
     const Layout& L;
     const int lane;
+#define UB_DIM(FN, name) \
+    __device__ __forceinline__ int FN() const { if constexpr (D::kStatic) return D::name; else return P.name; }
+    UB_DIM(NQ, nq) UB_DIM(NX, nx) UB_DIM(NU, nu) UB_DIM(NZ, nz) UB_DIM(NFC, nfc) UB_DIM(NEQ, neq) UB_DIM(NFRIC, nfric)
+    UB_DIM(NBOXU, nbox_u) UB_DIM(NB, nb) UB_DIM(NC, nc) UB_DIM(NF, nf)
+#undef UB_DIM
+    __device__ __forceinline__ int LDM() const { return NZ() | 1; }
+    __device__ __forceinline__ int LDF() const { return NU() | 1; }
+    __device__ __forceinline__ int NROW() const { return NBOXU() + NX() + NFRIC() + P.nobs; }
+    __device__ __forceinline__ int NTERM() const { return 3 + 2 * NQ(); }
+    __device__ __forceinline__ int FSTRIDE() const { return (NZ() * LDF() + 3) & ~3; }  // 16-byte aligned factor blocks
+    // small input blocks: store L^{-1} instead of L, turning the 4 triangular substitutions per
+    // interior-point iteration and stage (serial pivot chains) into matrix-vector products
+    static constexpr bool kInvL = D::kStatic && D::nu <= 16;
     // batch data of this instance
     const T* x0;
     const T* target;
@@ -80,9 +107,9 @@ struct Solver {
     //   [.., +nfric)                   friction   (k < N)     contact_constraints.h:49-77
     //   [.., +nobs)                    obstacles  (1<=k<N)    controller_interface.cpp:450-481
     __device__ __forceinline__ int row_family(int r) const {
-        if (r < P.nbox_u) return 0;
-        if (r < P.nbox_u + P.nx) return 1;
-        if (r < P.nbox_u + P.nx + P.nfric) return 2;
+        if (r < NBOXU()) return 0;
+        if (r < NBOXU() + NX()) return 1;
+        if (r < NBOXU() + NX() + NFRIC()) return 2;
         return 3;
     }
     __device__ __forceinline__ bool row_valid(int k, int fam) const {
@@ -107,7 +134,7 @@ struct Solver {
     // value of ineq row r of stage k at the QP iterate z (stage vector zk = [du; dx]),
     // and bounds.  Uses the linearisation stored in the workspace.
     __device__ T row_value(int k, int r, int fam, const T* zk, T* lb, T* ub) const {
-        const int nq = P.nq, nu = P.nu;
+        const int nq = NQ(), nu = NU();
         if (fam == 0) {
             const T u = U[k * nu + r];
             *lb = (r < nq ? P.ulb[r] : P.flb) - u;
@@ -115,8 +142,8 @@ struct Solver {
             return zk[r];
         }
         if (fam == 1) {
-            const int i = r - P.nbox_u;
-            const T x = X[k * P.nx + i];
+            const int i = r - NBOXU();
+            const T x = X[k * NX() + i];
             *lb = P.xlb[i] - x;
             *ub = P.xub[i] - x;
             return zk[nu + i];
@@ -124,13 +151,13 @@ struct Solver {
         *lb = T(0);
         *ub = tinf<T>();
         if (fam == 2) {
-            const int i = r - P.nbox_u - P.nx, c = i / 5;
+            const int i = r - NBOXU() - NX(), c = i / 5;
             const V3<T> a = fric_coeff(c, i % 5);
             const T* f = U + k * nu + nq + 3 * c;
             const T* df = zk + nq + 3 * c;
             return a.x * (f[0] + df[0]) + a.y * (f[1] + df[1]) + a.z * (f[2] + df[2]);
         }
-        const int i = r - P.nbox_u - P.nx - P.nfric;
+        const int i = r - NBOXU() - NX() - NFRIC();
         const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
         T v = ws[L.LHO + k * P.nobs + i];
         for (int j = 0; j < nq; ++j) v += J[j] * zk[nu + j];
@@ -138,16 +165,16 @@ struct Solver {
     }
     // a_r . d  for a stage direction d = [du; dx]
     __device__ T row_dot(int k, int r, int fam, const T* d) const {
-        const int nq = P.nq, nu = P.nu;
+        const int nq = NQ(), nu = NU();
         if (fam == 0) return d[r];
-        if (fam == 1) return d[nu + r - P.nbox_u];
+        if (fam == 1) return d[nu + r - NBOXU()];
         if (fam == 2) {
-            const int i = r - P.nbox_u - P.nx, c = i / 5;
+            const int i = r - NBOXU() - NX(), c = i / 5;
             const V3<T> a = fric_coeff(c, i % 5);
             const T* df = d + nq + 3 * c;
             return a.x * df[0] + a.y * df[1] + a.z * df[2];
         }
-        const int i = r - P.nbox_u - P.nx - P.nfric;
+        const int i = r - NBOXU() - NX() - NFRIC();
         const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
         T v = 0;
         for (int j = 0; j < nq; ++j) v += J[j] * d[nu + j];
@@ -156,83 +183,83 @@ struct Solver {
     // vec += w * a_r   (vec indexed like the stage vector); called by ONE lane per row,
     // rows may collide on entries -> atomics on shared memory
     __device__ void row_axpy(int k, int r, int fam, T w, T* vec) const {
-        const int nq = P.nq, nu = P.nu;
+        const int nq = NQ(), nu = NU();
         if (fam == 0) {
             atomicAdd(vec + r, w);
         } else if (fam == 1) {
-            atomicAdd(vec + nu + r - P.nbox_u, w);
+            atomicAdd(vec + nu + r - NBOXU(), w);
         } else if (fam == 2) {
-            const int i = r - P.nbox_u - P.nx, c = i / 5;
+            const int i = r - NBOXU() - NX(), c = i / 5;
             const V3<T> a = fric_coeff(c, i % 5);
             atomicAdd(vec + nq + 3 * c, w * a.x);
             atomicAdd(vec + nq + 3 * c + 1, w * a.y);
             atomicAdd(vec + nq + 3 * c + 2, w * a.z);
         } else {
-            const int i = r - P.nbox_u - P.nx - P.nfric;
+            const int i = r - NBOXU() - NX() - NFRIC();
             const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
             for (int j = 0; j < nq; ++j) atomicAdd(vec + nu + j, w * J[j]);
         }
     }
-    __device__ __forceinline__ int nz_of(int k) const { return k < P.N ? P.nz : P.nx; }
+    __device__ __forceinline__ int nz_of(int k) const { return k < P.N ? NZ() : NX(); }
     // stage vectors are stored with stride nz as [du (nu); dx (nx)]; the terminal
     // stage uses the same slots (its du part is unused and kept at zero)
-    __device__ __forceinline__ T* Zk(int k) const { return ws + L.Z + k * P.nz; }
-    __device__ __forceinline__ T* DZk(int k) const { return ws + L.DZ + k * P.nz; }
+    __device__ __forceinline__ T* Zk(int k) const { return ws + L.Z + k * NZ(); }
+    __device__ __forceinline__ T* DZk(int k) const { return ws + L.DZ + k * NZ(); }
 
     // number of equality rows of stage k and their data
-    __device__ __forceinline__ int neq_of(int k) const { return k < P.N ? P.neq : P.nterm; }
+    __device__ __forceinline__ int neq_of(int k) const { return k < P.N ? NEQ() : NTERM(); }
 
     // -------------------------------------------------------- linearisation
     // Df: d g / d f, constant in x (compute_object_wrenches, contact_constraints.h:106-157)
     __device__ void build_Df() {
-        const T scale = rsqrt(T(6 * P.nb));
+        const T scale = rsqrt(T(6 * NB()));
         T* Df = ws + L.DF;
-        for (int idx = lane; idx < P.neq * P.nfc; idx += WARP) Df[idx] = T(0);
+        for (int idx = lane; idx < NEQ() * NFC(); idx += WARP) Df[idx] = T(0);
         __syncwarp();
-        for (int j = lane; j < P.nfc; j += WARP) {
-            const int c = j / P.nf, comp = j % P.nf;
+        for (int j = lane; j < NFC(); j += WARP) {
+            const int c = j / NF(), comp = j % NF();
             V3<T> e;
-            if (P.nf == 1) e = ld3(P.cn[c]);
+            if (NF() == 1) e = ld3(P.cn[c]);
             else e = V3<T>(comp == 0 ? T(1) : T(0), comp == 1 ? T(1) : T(0), comp == 2 ? T(1) : T(0));
             const int b1 = P.cb1[c], b2 = P.cb2[c];
             if (b1 >= 0) {
                 const BodyP<T> Bd = load_body(body + b1 * UB_BODY_PARAMS);
                 const V3<T> tq = cross(ld3(P.cr1[c]) - Bd.com, e);
                 const T s = -scale / Bd.m;
-                Df[(6 * b1 + 0) * P.nfc + j] = s * e.x;
-                Df[(6 * b1 + 1) * P.nfc + j] = s * e.y;
-                Df[(6 * b1 + 2) * P.nfc + j] = s * e.z;
-                Df[(6 * b1 + 3) * P.nfc + j] = s * tq.x;
-                Df[(6 * b1 + 4) * P.nfc + j] = s * tq.y;
-                Df[(6 * b1 + 5) * P.nfc + j] = s * tq.z;
+                Df[(6 * b1 + 0) * NFC() + j] = s * e.x;
+                Df[(6 * b1 + 1) * NFC() + j] = s * e.y;
+                Df[(6 * b1 + 2) * NFC() + j] = s * e.z;
+                Df[(6 * b1 + 3) * NFC() + j] = s * tq.x;
+                Df[(6 * b1 + 4) * NFC() + j] = s * tq.y;
+                Df[(6 * b1 + 5) * NFC() + j] = s * tq.z;
             }
             {
                 const BodyP<T> Bd = load_body(body + b2 * UB_BODY_PARAMS);
                 const V3<T> tq = cross(ld3(P.cr2[c]) - Bd.com, T(-1) * e);
                 const T s = -scale / Bd.m;
-                Df[(6 * b2 + 0) * P.nfc + j] = -s * e.x;
-                Df[(6 * b2 + 1) * P.nfc + j] = -s * e.y;
-                Df[(6 * b2 + 2) * P.nfc + j] = -s * e.z;
-                Df[(6 * b2 + 3) * P.nfc + j] = s * tq.x;
-                Df[(6 * b2 + 4) * P.nfc + j] = s * tq.y;
-                Df[(6 * b2 + 5) * P.nfc + j] = s * tq.z;
+                Df[(6 * b2 + 0) * NFC() + j] = -s * e.x;
+                Df[(6 * b2 + 1) * NFC() + j] = -s * e.y;
+                Df[(6 * b2 + 2) * NFC() + j] = -s * e.z;
+                Df[(6 * b2 + 3) * NFC() + j] = s * tq.x;
+                Df[(6 * b2 + 4) * NFC() + j] = s * tq.y;
+                Df[(6 * b2 + 5) * NFC() + j] = s * tq.z;
             }
         }
         __syncwarp();
     }
 
     // Linearise every knot around (X, U): lane j carries d/dx_j.
-    // Writes LG [k][neq] (g value incl. Df f), LCT [k][nx][neq] (column-major C),
+    // Writes LG [k][neq] (g value incl. Df f), LCT [k][neq][nz] (rows [0 | Df | C] over the stage vector),
     // LR [k][3], LJP [k][3][nq], LHO [k][nobs], LJO [k][nobs][nq], GAP [k][nx].
     __device__ void linearize() {
-        const int nq = P.nq, nx = P.nx, nu = P.nu, N = P.N;
-        const T scale = rsqrt(T(6 * max(P.nb, 1)));
+        const int nq = NQ(), nx = NX(), nu = NU(), N = P.N;
+        const T scale = rsqrt(T(6 * max(NB(), 1)));
         T sph[3 * UB_MAX_SPHERES], dsph[3 * UB_MAX_SPHERES];
         for (int k = 0; k <= N; ++k) {
             const T* x = X + k * nx;
             Kin<T> Kn;
-            KinTan<T> D;
-            forward_kinematics<T, true>(P, x, lane, Kn, D, P.nobs > 0 ? sph : nullptr, dsph);
+            KinTan<T> Dt;
+            forward_kinematics<T, true>(P, x, lane, Kn, Dt, P.nobs > 0 ? sph : nullptr, dsph);
             if (lane == 0) {
                 ws[L.LR + 3 * k] = Kn.r.x;
                 ws[L.LR + 3 * k + 1] = Kn.r.y;
@@ -240,29 +267,34 @@ struct Solver {
             }
             if (lane < nq) {
                 T* Jp = ws + L.LJP + k * 3 * nq;
-                Jp[lane] = D.r.x;
-                Jp[nq + lane] = D.r.y;
-                Jp[2 * nq + lane] = D.r.z;
+                Jp[lane] = Dt.r.x;
+                Jp[nq + lane] = Dt.r.y;
+                Jp[2 * nq + lane] = Dt.r.z;
             }
-            if (k < N && P.neq > 0) {
-                for (int b = 0; b < P.nb; ++b) {
+            if (k < N && NEQ() > 0) {
+                for (int b = 0; b < NB(); ++b) {
                     const BodyP<T> Bd = load_body(body + b * UB_BODY_PARAMS);
                     T g6[6], dg6[6];
-                    object_dynamics_state_part<T, true>(P, Bd, Kn, D, scale, g6, dg6);
+                    object_dynamics_state_part<T, true>(P, Bd, Kn, Dt, scale, g6, dg6);
                     if (lane < nx) {
-                        T* CT = ws + L.LCT + (k * nx + lane) * P.neq + 6 * b;
+                        // row-major over the stage vector [du; dx]: lanes write consecutive addresses
+                        T* R = ws + L.LCT + (k * NEQ() + 6 * b) * NZ() + nu + lane;
 #pragma unroll
-                        for (int i = 0; i < 6; ++i) CT[i] = dg6[i];
+                        for (int i = 0; i < 6; ++i) R[i * NZ()] = dg6[i];
+                    }
+                    for (int idx = lane; idx < 6 * nu; idx += WARP) {
+                        const int i = idx / nu, j = idx % nu;
+                        ws[L.LCT + (k * NEQ() + 6 * b + i) * NZ() + j] = (j >= nq) ? ws[L.DF + (6 * b + i) * NFC() + (j - nq)] : T(0);
                     }
                     if (lane < 6) {
                         // g = state part + Df f
                         T gv = g6[0];
 #pragma unroll
                         for (int i = 1; i < 6; ++i) gv = (lane == i) ? g6[i] : gv;
-                        const T* Dfr = ws + L.DF + (6 * b + lane) * P.nfc;
+                        const T* Dfr = ws + L.DF + (6 * b + lane) * NFC();
                         const T* f = U + k * nu + nq;
-                        for (int j = 0; j < P.nfc; ++j) gv += Dfr[j] * f[j];
-                        ws[L.LG + k * P.neq + 6 * b + lane] = gv;
+                        for (int j = 0; j < NFC(); ++j) gv += Dfr[j] * f[j];
+                        ws[L.LG + k * NEQ() + 6 * b + lane] = gv;
                     }
                 }
             }
@@ -294,9 +326,9 @@ struct Solver {
     // --------------------------------------------------- performance index
     // Lane k evaluates knot k (values only).  Mirrors orc::performance().
     __device__ Perf<T> performance(const T* Xt, const T* Ut) const {
-        const int nq = P.nq, nx = P.nx, nu = P.nu, N = P.N;
+        const int nq = NQ(), nx = NX(), nu = NU(), N = P.N;
         const T dt = P.dt;
-        const T scale = rsqrt(T(6 * max(P.nb, 1)));
+        const T scale = rsqrt(T(6 * max(NB(), 1)));
         T cost = 0, dyn = 0, eq = 0, ineq = 0, max_eq = 0, min_margin = tinf<T>();
         T sph[3 * UB_MAX_SPHERES];
         for (int k = lane; k <= N; k += WARP) {
@@ -331,7 +363,7 @@ struct Solver {
                 c += T(0.5) * P.Qd[i] * e * e;
             }
             for (int i = 0; i < nq; ++i) c += T(0.5) * P.Rd[i] * u[i] * u[i];
-            for (int i = 0; i < P.nfc; ++i) c += T(0.5) * P.fw * u[nq + i] * u[nq + i];
+            for (int i = 0; i < NFC(); ++i) c += T(0.5) * P.fw * u[nq + i] * u[nq + i];
             for (int i = 0; i < 3; ++i) {
                 const T e = Kn.r[i] - rd[i];
                 c += T(0.5) * P.Wd[i] * e * e;
@@ -345,26 +377,26 @@ struct Solver {
                 const T g2 = a + dt * j - xn[2 * nq + i];
                 dyn += dt * (g0 * g0 + g1 * g1 + g2 * g2);
             }
-            const int nbox = P.nbox_u;
+            const int nbox = NBOXU();
             for (int i = 0; i < nbox; ++i) {
                 const T lo = u[i] - (i < nq ? P.ulb[i] : P.flb), hi = (i < nq ? P.uub[i] : P.fub) - u[i];
                 const T a = min(T(0), lo), b = min(T(0), hi);
                 ineq += dt * (a * a + b * b);
                 min_margin = min(min_margin, min(lo, hi));
             }
-            for (int b = 0; b < (P.neq > 0 ? P.nb : 0); ++b) {
+            for (int b = 0; b < (NEQ() > 0 ? NB() : 0); ++b) {
                 const BodyP<T> Bd = load_body(body + b * UB_BODY_PARAMS);
                 T g6[6];
                 object_dynamics_state_part<T, false>(P, Bd, Kn, Dn, scale, g6, nullptr);
                 for (int i = 0; i < 6; ++i) {
-                    const T* Dfr = ws + L.DF + (6 * b + i) * P.nfc;
+                    const T* Dfr = ws + L.DF + (6 * b + i) * NFC();
                     T gv = g6[i];
-                    for (int j = 0; j < P.nfc; ++j) gv += Dfr[j] * u[nq + j];
+                    for (int j = 0; j < NFC(); ++j) gv += Dfr[j] * u[nq + j];
                     eq += dt * gv * gv;
                     max_eq = max(max_eq, fabs(gv));
                 }
             }
-            for (int i = 0; i < P.nfric; ++i) {
+            for (int i = 0; i < NFRIC(); ++i) {
                 const int cidx = i / 5;
                 const V3<T> a = fric_coeff(cidx, i % 5);
                 const T* f = u + nq + 3 * cidx;
@@ -398,15 +430,10 @@ struct Solver {
     // stage-vector index order, with their constant c, penalty rho and
     // multiplier y in sV-side arrays (global RHOE/YE, RHOT/YT).
     __device__ void load_eq_rows(int k) {
-        const int nq = P.nq, nx = P.nx, nu = P.nu, nz = P.nz;
+        const int nq = NQ(), nx = NX(), nu = NU(), nz = NZ();
         if (k < P.N) {
-            for (int idx = lane; idx < P.neq * nz; idx += WARP) {
-                const int i = idx / nz, j = idx % nz;
-                T v = T(0);
-                if (j >= nu) v = ws[L.LCT + (k * nx + (j - nu)) * P.neq + i];
-                else if (j >= nq) v = ws[L.DF + i * P.nfc + (j - nq)];
-                sSA[idx] = v;
-            }
+            const T* __restrict__ R = ws + L.LCT + k * NEQ() * nz;
+            for (int idx = lane; idx < NEQ() * nz; idx += WARP) sSA[idx] = R[idx];
         } else {
             // terminal equality [r_d - r; v; a] = 0: three dense rows over q, the rest are unit rows
             for (int idx = lane; idx < 3 * nz; idx += WARP) {
@@ -420,18 +447,18 @@ struct Solver {
     }
     // constant (value at z = 0) of equality row i of stage k
     __device__ __forceinline__ T eq_const(int k, int i) const {
-        if (k < P.N) return ws[L.LG + k * P.neq + i];
+        if (k < P.N) return ws[L.LG + k * NEQ() + i];
         if (i < 3) return target[3 * k + i] - ws[L.LR + 3 * k + i];
-        return X[k * P.nx + P.nq + (i - 3)];
+        return X[k * NX() + NQ() + (i - 3)];
     }
-    __device__ __forceinline__ T* rho_eq(int k) const { return k < P.N ? ws + L.RHOE + k * P.neq : ws + L.RHOT; }
-    __device__ __forceinline__ T* y_eq(int k) const { return k < P.N ? ws + L.YE + k * P.neq : ws + L.YT; }
+    __device__ __forceinline__ T* rho_eq(int k) const { return k < P.N ? ws + L.RHOE + k * NEQ() : ws + L.RHOT; }
+    __device__ __forceinline__ T* y_eq(int k) const { return k < P.N ? ws + L.YE + k * NEQ() : ws + L.YT; }
     // value a_i . z + c of equality row i (dense rows from SA; terminal unit rows direct)
     __device__ T eq_value(int k, int i, const T* zk) const {
-        if (k == P.N && i >= 3) return zk[P.nu + P.nq + (i - 3)] + eq_const(k, i);
-        const T* a = sSA + i * P.nz;
+        if (k == P.N && i >= 3) return zk[NU() + NQ() + (i - 3)] + eq_const(k, i);
+        const T* a = sSA + i * NZ();
         T v = eq_const(k, i);
-        for (int j = (k < P.N ? P.nq : P.nu); j < P.nz; ++j) v += a[j] * zk[j];
+        for (int j = (k < P.N ? NQ() : NU()); j < NZ(); ++j) v += a[j] * zk[j];
         return v;
     }
 
@@ -448,7 +475,7 @@ struct Solver {
                     T n2 = T(1);
                     if (!(k == P.N && i >= 3)) {
                         n2 = T(0);
-                        for (int j = 0; j < P.nz; ++j) n2 += sSA[i * P.nz + j] * sSA[i * P.nz + j];
+                        for (int j = 0; j < NZ(); ++j) n2 += sSA[i * NZ() + j] * sSA[i * NZ() + j];
                     }
                     rho = n2 > T(0) ? P.rho_hard / n2 : T(0);
                 }
@@ -459,43 +486,65 @@ struct Solver {
         }
     }
 
-    // M (lower triangle, ld = L.ldm) += [B A]' Pn [B A] with the block structure
+    // M (lower triangle, ld = LDM()) += [B A]' Pn [B A] with the block structure
     // A = A3 (x) I, B = B3 (x) I of the exact triple-integrator discretisation.
     __device__ void add_dynamics_hessian() {
-        const int nq = P.nq, nu = P.nu, nx = P.nx, ld = L.ldm;
+        const int nq = NQ(), nu = NU(), nx = NX(), ld = LDM();
         const T dt = P.dt;
-        // T3[a][I]: column 0 = B3, columns 1..3 = A3
+        // T3[a][I]: column 0 = B3, columns 1..3 = A3 (block order of the stage vector: jerk, q, v, a)
         const T T3[3][4] = {{dt * dt * dt / T(6), T(1), dt, T(0.5) * dt * dt},
                             {T(0.5) * dt * dt, T(0), T(1), dt},
                             {dt, T(0), T(0), T(1)}};
-        const int nb4 = 4 * nq;
-        for (int idx = lane; idx < nb4 * nb4; idx += WARP) {
-            const int bi = idx / nb4, bj = idx % nb4;
-            if (bj > bi) continue;
-            const int I = bi / nq, ii = bi % nq, J = bj / nq, jj = bj % nq;
-            T acc = T(0);
+        if constexpr (D::kStatic) {
+            // block pairs (I >= J) unrolled at compile time: zero entries of T3 drop out, 52 products in total
 #pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const T ta = T3[a][I];
-                if (ta == T(0)) continue;
+            for (int I = 0; I < 4; ++I) {
 #pragma unroll
-                for (int b = 0; b < 3; ++b) {
-                    const T tb = T3[b][J];
-                    if (tb == T(0)) continue;
-                    const int r = a * nq + ii, c = b * nq + jj;
-                    acc += ta * tb * (r >= c ? sP[r * nx + c] : sP[c * nx + r]);
+                for (int J = 0; J <= I; ++J) {
+                    for (int e = lane; e < D::nq * D::nq; e += WARP) {
+                        const int ii = e / D::nq, jj = e % D::nq;
+                        T acc = T(0);
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            if ((I == 1 && a != 0) || (I == 2 && a == 2)) continue;
+#pragma unroll
+                            for (int b = 0; b < 3; ++b) {
+                                if ((J == 1 && b != 0) || (J == 2 && b == 2)) continue;
+                                acc += T3[a][I] * T3[b][J] * sP[(a * D::nq + ii) * D::nx + b * D::nq + jj];
+                            }
+                        }
+                        const int mi = (I == 0) ? ii : D::nu + (I - 1) * D::nq + ii;
+                        const int mj = (J == 0) ? jj : D::nu + (J - 1) * D::nq + jj;
+                        sM[mi * ld + mj] += acc;  // diagonal blocks also touch (unused) upper entries
+                    }
                 }
             }
-            const int mi = (I == 0) ? ii : nu + (I - 1) * nq + ii;
-            const int mj = (J == 0) ? jj : nu + (J - 1) * nq + jj;
-            // block order (jerk, q, v, a) is monotone in the M index, so mi >= mj here
-            sM[mi * ld + mj] += acc;
+        } else {
+            const int nb4 = 4 * nq;
+            for (int idx = lane; idx < nb4 * nb4; idx += WARP) {
+                const int bi = idx / nb4, bj = idx % nb4;
+                if (bj > bi) continue;
+                const int I = bi / nq, ii = bi % nq, J = bj / nq, jj = bj % nq;
+                T acc = T(0);
+                for (int a = 0; a < 3; ++a) {
+                    const T ta = T3[a][I];
+                    if (ta == T(0)) continue;
+                    for (int b = 0; b < 3; ++b) {
+                        const T tb = T3[b][J];
+                        if (tb == T(0)) continue;
+                        acc += ta * tb * sP[(a * nq + ii) * nx + b * nq + jj];
+                    }
+                }
+                const int mi = (I == 0) ? ii : nu + (I - 1) * nq + ii;
+                const int mj = (J == 0) ? jj : nu + (J - 1) * nq + jj;
+                sM[mi * ld + mj] += acc;
+            }
         }
         __syncwarp();
     }
     // vec (stage layout) += [B A]' pv
     __device__ void add_dynamics_gradient(T* vec) const {
-        const int nq = P.nq, nu = P.nu;
+        const int nq = NQ(), nu = NU();
         const T dt = P.dt;
         if (lane < nq) {
             const T p0 = sPv[lane], p1 = sPv[nq + lane], p2 = sPv[2 * nq + lane];
@@ -510,7 +559,7 @@ struct Solver {
     // Build the Newton matrix of stage k in sM (lower triangle): cost Hessian +
     // equality proximal terms + barrier terms of the inequality sides.
     __device__ void build_stage_matrix(int k) {
-        const int nq = P.nq, nu = P.nu, nx = P.nx, nz = P.nz, ld = L.ldm;
+        const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ld = LDM();
         const T dt = P.dt;
         for (int idx = lane; idx < nz * ld; idx += WARP) sM[idx] = T(0);
         __syncwarp();
@@ -542,12 +591,27 @@ struct Solver {
             const int nd = (k < P.N) ? ne : 3;
             const int j0 = (k < P.N) ? nq : nu;  // first column with non-zeros
             const int span = nz - j0;
-            for (int idx = lane; idx < span * span; idx += WARP) {
-                const int i = j0 + idx / span, j = j0 + idx % span;
-                if (j > i) continue;
-                T acc = 0;
-                for (int r = 0; r < nd; ++r) acc += rho[r] * sSA[r * nz + i] * sSA[r * nz + j];
-                sM[i * ld + j] += acc;
+            if (D::kStatic && D::neq <= 8 && k < P.N) {
+                constexpr int NE = D::kStatic ? (D::neq > 0 ? D::neq : 1) : 1;
+                for (int c = j0 + lane; c < nz; c += WARP) {
+                    T ac[NE];
+#pragma unroll
+                    for (int r = 0; r < NE; ++r) ac[r] = rho[r] * sSA[r * nz + c];
+                    for (int i = c; i < nz; ++i) {
+                        T acc = 0;
+#pragma unroll
+                        for (int r = 0; r < NE; ++r) acc += ac[r] * sSA[r * nz + i];
+                        sM[i * ld + c] += acc;
+                    }
+                }
+            } else {
+                for (int idx = lane; idx < span * span; idx += WARP) {
+                    const int i = j0 + idx / span, j = j0 + idx % span;
+                    if (j > i) continue;
+                    T acc = 0;
+                    for (int r = 0; r < nd; ++r) acc += rho[r] * sSA[r * nz + i] * sSA[r * nz + j];
+                    sM[i * ld + j] += acc;
+                }
             }
             if (k == P.N)
                 for (int i = 3 + lane; i < ne; i += WARP) {
@@ -557,22 +621,22 @@ struct Solver {
             __syncwarp();
         }
         // inequality sides: w a a', w = lam / (t + eps lam)
-        const T* TTk = ws + L.TT + k * P.nrow * 2;
-        const T* LMk = ws + L.LAM + k * P.nrow * 2;
-        const int nbx = P.nbox_u + P.nx;
+        const T* TTk = ws + L.TT + k * NROW() * 2;
+        const T* LMk = ws + L.LAM + k * NROW() * 2;
+        const int nbx = NBOXU() + NX();
         for (int r = lane; r < nbx; r += WARP) {
-            const int fam = r < P.nbox_u ? 0 : 1;
+            const int fam = r < NBOXU() ? 0 : 1;
             if (!row_valid(k, fam)) continue;
             const T eps = row_eps(fam);
             const T w = LMk[2 * r] / (TTk[2 * r] + eps * LMk[2 * r]) + LMk[2 * r + 1] / (TTk[2 * r + 1] + eps * LMk[2 * r + 1]);
-            const int m = fam == 0 ? r : nu + (r - P.nbox_u);
+            const int m = fam == 0 ? r : nu + (r - NBOXU());
             sM[m * ld + m] += w;
         }
         __syncwarp();
-        if (P.nfric > 0 && k < P.N) {
+        if (NFRIC() > 0 && k < P.N) {
             const T eps = row_eps(2);
             // one lane per (contact, 3x3 lower entry)
-            for (int idx = lane; idx < P.nc * 6; idx += WARP) {
+            for (int idx = lane; idx < NC() * 6; idx += WARP) {
                 const int c = idx / 6, e = idx % 6;
                 const int a = (e < 1) ? 0 : (e < 3 ? 1 : 2), b = e - (a == 0 ? 0 : (a == 1 ? 1 : 3));
                 T acc = 0;
@@ -593,7 +657,7 @@ struct Solver {
                 if (b > a) continue;
                 T acc = 0;
                 for (int i = 0; i < P.nobs; ++i) {
-                    const int r = nbx + P.nfric + i;
+                    const int r = nbx + NFRIC() + i;
                     const T w = LMk[2 * r] / (TTk[2 * r] + eps * LMk[2 * r]);
                     const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
                     acc += w * J[a] * J[b];
@@ -608,7 +672,7 @@ struct Solver {
     // afterwards columns j < nu hold L (diagonal stored INVERTED) and the
     // trailing block holds the Schur complement.  Lane l owns columns l, l+32, ...
     __device__ bool partial_cholesky(int n, int npiv) {
-        const int ld = L.ldm;
+        const int ld = LDM();
         bool ok = true;
         for (int j = 0; j < npiv; ++j) {
             T d = sM[j * ld + j];
@@ -622,7 +686,24 @@ struct Solver {
             if (lane == 0) sM[j * ld + j] = inv;
             for (int l = j + 1 + lane; l < n; l += WARP) {
                 const T mlj = sM[l * ld + j];
-                for (int i = l; i < n; ++i) sM[i * ld + l] -= sM[i * ld + j] * mlj;
+                T* __restrict__ dst = sM + l * ld + l;         // column l, rows l..n-1
+                const T* __restrict__ src = sM + l * ld + j;   // column j, rows l..n-1
+                int i = l;
+                for (; i + 4 <= n; i += 4) {
+                    const T s0 = src[0], s1 = src[ld], s2 = src[2 * ld], s3 = src[3 * ld];
+                    const T d0 = dst[0], d1 = dst[ld], d2 = dst[2 * ld], d3 = dst[3 * ld];
+                    dst[0] = d0 - s0 * mlj;
+                    dst[ld] = d1 - s1 * mlj;
+                    dst[2 * ld] = d2 - s2 * mlj;
+                    dst[3 * ld] = d3 - s3 * mlj;
+                    src += 4 * ld;
+                    dst += 4 * ld;
+                }
+                for (; i < n; ++i) {
+                    dst[0] -= src[0] * mlj;
+                    src += ld;
+                    dst += ld;
+                }
             }
             __syncwarp();
         }
@@ -630,26 +711,40 @@ struct Solver {
     }
 
     // Factor sweep: for k = N..0 build the stage matrix, add the cost-to-go,
-    // factor, store the factor block FAC[k] = sM[0..nz) x [0..nu) (ld = L.ldf)
+    // factor, store the factor block FAC[k] = sM[0..nz) x [0..nu) (ld = LDF())
     // and keep the new cost-to-go Hessian in sP.
     __device__ bool factor_sweep() {
-        const int nu = P.nu, nx = P.nx, nz = P.nz, ld = L.ldm;
+        const int nu = NU(), nx = NX(), nz = NZ(), ld = LDM();
         bool ok = true;
         for (int k = P.N; k >= 0; --k) {
             build_stage_matrix(k);
             if (k < P.N) {
                 add_dynamics_hessian();
                 ok &= partial_cholesky(nz, nu);
-                T* F = ws + L.FAC + k * nz * L.ldf;
+                if constexpr (kInvL) {
+                    // lane c builds column c of L^{-1}; stored transposed in the (free) upper triangle
+                    if (lane < nu) {
+                        const int c = lane;
+                        for (int i = c + 1; i < nu; ++i) {
+                            T acc = sM[i * ld + c] * sM[c * ld + c];  // L_ic * x_c, x_c = 1/L_cc
+                            for (int m = c + 1; m < i; ++m) acc += sM[i * ld + m] * sM[c * ld + m];
+                            sM[c * ld + i] = -acc * sM[i * ld + i];
+                        }
+                    }
+                    __syncwarp();
+                }
+                T* F = ws + L.FAC + k * FSTRIDE();
                 for (int idx = lane; idx < nz * nu; idx += WARP) {
                     const int i = idx / nu, j = idx % nu;
-                    F[i * L.ldf + j] = (j <= i) ? sM[i * ld + j] : T(0);
+                    T v = T(0);
+                    if (j <= i) v = (kInvL && i < nu && j < i) ? sM[j * ld + i] : sM[i * ld + j];
+                    F[i * LDF() + j] = v;
                 }
             }
             // cost-to-go: trailing block (x part)
             for (int idx = lane; idx < nx * nx; idx += WARP) {
                 const int i = idx / nx, j = idx % nx;
-                if (j <= i) sP[i * nx + j] = sM[(nu + i) * ld + nu + j];
+                sP[idx] = (j <= i) ? sM[(nu + i) * ld + nu + j] : sM[(nu + j) * ld + nu + i];  // full symmetric
             }
             __syncwarp();
         }
@@ -660,7 +755,7 @@ struct Solver {
     //   H z + g  +  sum_eq a (rho e + y)  +  sum_sides sgn a [ -lam + (rc + lam rd)/(t + eps lam) ]
     // with rc = t lam - target (+ dt_aff dlam_aff in the corrector).  Result in vec (shared).
     __device__ void stage_gradient(int k, bool corrector, T mu_target, T* vec) {
-        const int nq = P.nq, nu = P.nu, nx = P.nx, nz = P.nz;
+        const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ();
         const T dt = P.dt;
         const T* zk = Zk(k);
         for (int i = lane; i < nz; i += WARP) vec[i] = T(0);
@@ -711,11 +806,11 @@ struct Solver {
             }
             __syncwarp();
         }
-        const T* TTk = ws + L.TT + k * P.nrow * 2;
-        const T* LMk = ws + L.LAM + k * P.nrow * 2;
-        const T* DTk = ws + L.DTT + k * P.nrow * 2;
-        const T* DLk = ws + L.DLAM + k * P.nrow * 2;
-        for (int r = lane; r < P.nrow; r += WARP) {
+        const T* TTk = ws + L.TT + k * NROW() * 2;
+        const T* LMk = ws + L.LAM + k * NROW() * 2;
+        const T* DTk = ws + L.DTT + k * NROW() * 2;
+        const T* DLk = ws + L.DLAM + k * NROW() * 2;
+        for (int r = lane; r < NROW(); r += WARP) {
             const int fam = row_family(r);
             if (!row_valid(k, fam)) continue;
             T lb, ub;
@@ -737,10 +832,20 @@ struct Solver {
         __syncwarp();
     }
 
+    // 16-byte vectorised copy global -> shared (both 16-byte aligned; n in elements)
+    __device__ __forceinline__ void copy_block(T* __restrict__ dst, const T* __restrict__ src, int n) const {
+        constexpr int V = 16 / sizeof(T);
+        const int nv = n / V;
+        const int4* s4 = reinterpret_cast<const int4*>(src);
+        int4* d4 = reinterpret_cast<int4*>(dst);
+        for (int i = lane; i < nv; i += WARP) d4[i] = s4[i];
+        for (int i = nv * V + lane; i < n; i += WARP) dst[i] = src[i];
+    }
+
     // Vector sweeps with the stored factors: backward (w_k, cost-to-go gradient)
     // then forward (direction DZ).  `corrector`/`target_mu` select the right-hand side.
     __device__ void solve_sweeps(bool corrector, T target_mu) {
-        const int nq = P.nq, nu = P.nu, nx = P.nx, nz = P.nz, ldf = L.ldf;
+        const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ldf = LDF();
         T* vec = sV;           // [nz] gradient
         T* dx = sV + nz;       // [nx]
         T* du = sV + 2 * nz;   // [nu] (also s)
@@ -756,16 +861,26 @@ struct Solver {
                 continue;
             }
             add_dynamics_gradient(vec);
-            const T* Fg = ws + L.FAC + k * nz * ldf;
-            for (int idx = lane; idx < nz * ldf; idx += WARP) F[idx] = Fg[idx];
+            copy_block(F, ws + L.FAC + k * FSTRIDE(), nz * ldf);
             __syncwarp();
-            // w = L^{-1} m_u (forward substitution, column oriented)
-            for (int j = 0; j < nu; ++j) {
-                const T wj = vec[j] * F[j * ldf + j];
+            // w = L^{-1} m_u
+            if constexpr (kInvL) {
+                T wi = T(0);
+                if (lane < nu) {
+                    const T* Fr = F + lane * ldf;
+                    for (int j = 0; j <= lane; ++j) wi += Fr[j] * vec[j];
+                }
                 __syncwarp();
-                if (lane == 0) vec[j] = wj;
-                for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= F[i * ldf + j] * wj;
+                if (lane < nu) vec[lane] = wi;
                 __syncwarp();
+            } else {
+                for (int j = 0; j < nu; ++j) {  // forward substitution, column oriented
+                    const T wj = vec[j] * F[j * ldf + j];
+                    __syncwarp();
+                    if (lane == 0) vec[j] = wj;
+                    for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= F[i * ldf + j] * wj;
+                    __syncwarp();
+                }
             }
             T* Wk = ws + L.WF + k * nu;
             for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
@@ -782,8 +897,7 @@ struct Solver {
         for (int i = lane; i < nx; i += WARP) dx[i] = T(0);
         __syncwarp();
         for (int k = 0; k < P.N; ++k) {
-            const T* Fg = ws + L.FAC + k * nz * ldf;
-            for (int idx = lane; idx < nz * ldf; idx += WARP) F[idx] = Fg[idx];
+            copy_block(F, ws + L.FAC + k * FSTRIDE(), nz * ldf);
             const T* Wk = ws + L.WF + k * nu;
             __syncwarp();
             // s = w + Y dx
@@ -793,17 +907,26 @@ struct Solver {
                 du[j] = acc;
             }
             __syncwarp();
-            // du = -L^{-T} s (backward substitution, row oriented)
-            for (int j = nu - 1; j >= 0; --j) {
-                const T uj = -du[j] * F[j * ldf + j];
+            // du = -L^{-T} s
+            if constexpr (kInvL) {
+                T uj = T(0);
+                if (lane < nu)
+                    for (int i = lane; i < nu; ++i) uj -= F[i * ldf + lane] * du[i];
                 __syncwarp();
-                for (int i = lane; i < j; i += WARP) du[i] += F[j * ldf + i] * uj;
-                if (lane == 0) du[j] = uj;
+                if (lane < nu) du[lane] = uj;
                 __syncwarp();
+            } else {
+                for (int j = nu - 1; j >= 0; --j) {  // backward substitution, row oriented
+                    const T uj = -du[j] * F[j * ldf + j];
+                    __syncwarp();
+                    for (int i = lane; i < j; i += WARP) du[i] += F[j * ldf + i] * uj;
+                    if (lane == 0) du[j] = uj;
+                    __syncwarp();
+                }
             }
-            T* D = DZk(k);
-            for (int j = lane; j < nu; j += WARP) D[j] = du[j];
-            for (int i = lane; i < nx; i += WARP) D[nu + i] = dx[i];
+            T* Dk = DZk(k);
+            for (int j = lane; j < nu; j += WARP) Dk[j] = du[j];
+            for (int i = lane; i < nx; i += WARP) Dk[nu + i] = dx[i];
             __syncwarp();
             if (lane < nq) {
                 const T dt = P.dt;
@@ -814,9 +937,9 @@ struct Solver {
             }
             __syncwarp();
         }
-        T* D = DZk(P.N);
-        for (int j = lane; j < nu; j += WARP) D[j] = T(0);
-        for (int i = lane; i < nx; i += WARP) D[nu + i] = dx[i];
+        T* Dn = DZk(P.N);
+        for (int j = lane; j < nu; j += WARP) Dn[j] = T(0);
+        for (int i = lane; i < nx; i += WARP) Dn[nu + i] = dx[i];
         __syncwarp();
     }
 
@@ -828,11 +951,11 @@ struct Solver {
         for (int k = 0; k <= P.N; ++k) {
             const T* zk = Zk(k);
             const T* dk = DZk(k);
-            T* TTk = ws + L.TT + k * P.nrow * 2;
-            T* LMk = ws + L.LAM + k * P.nrow * 2;
-            T* DTk = ws + L.DTT + k * P.nrow * 2;
-            T* DLk = ws + L.DLAM + k * P.nrow * 2;
-            for (int r = lane; r < P.nrow; r += WARP) {
+            T* TTk = ws + L.TT + k * NROW() * 2;
+            T* LMk = ws + L.LAM + k * NROW() * 2;
+            T* DTk = ws + L.DTT + k * NROW() * 2;
+            T* DLk = ws + L.DLAM + k * NROW() * 2;
+            for (int r = lane; r < NROW(); r += WARP) {
                 const int fam = row_family(r);
                 if (!row_valid(k, fam)) continue;
                 T lb, ub;
@@ -862,11 +985,11 @@ struct Solver {
         if (mu_after) {
             T acc = 0;
             for (int k = 0; k <= P.N; ++k) {
-                const T* TTk = ws + L.TT + k * P.nrow * 2;
-                const T* LMk = ws + L.LAM + k * P.nrow * 2;
-                const T* DTk = ws + L.DTT + k * P.nrow * 2;
-                const T* DLk = ws + L.DLAM + k * P.nrow * 2;
-                for (int r = lane; r < P.nrow; r += WARP) {
+                const T* TTk = ws + L.TT + k * NROW() * 2;
+                const T* LMk = ws + L.LAM + k * NROW() * 2;
+                const T* DTk = ws + L.DTT + k * NROW() * 2;
+                const T* DLk = ws + L.DLAM + k * NROW() * 2;
+                for (int r = lane; r < NROW(); r += WARP) {
                     const int fam = row_family(r);
                     if (!row_valid(k, fam)) continue;
                     for (int sd = 0; sd < (fam >= 2 ? 1 : 2); ++sd)
@@ -882,7 +1005,7 @@ struct Solver {
     // and the factors of the last iteration in FAC.  Returns iterations used;
     // *converged, *decr as in orc::solve_qp_ipm.
     __device__ int solve_qp(bool* converged, T* decr, bool* finite) {
-        const int nq = P.nq, nu = P.nu, nx = P.nx, nz = P.nz, N = P.N;
+        const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), N = P.N;
         *converged = false;
         *finite = true;
         // dynamics-feasible start: du = 0, dx_0 = 0, dx_{k+1} = A dx_k + gap_k
@@ -909,10 +1032,10 @@ struct Solver {
         int nsides_l = 0;
         for (int k = 0; k <= N; ++k) {
             const T* zk = Zk(k);
-            for (int r = lane; r < P.nrow; r += WARP) {
+            for (int r = lane; r < NROW(); r += WARP) {
                 const int fam = row_family(r);
-                T* TTk = ws + L.TT + (k * P.nrow + r) * 2;
-                T* LMk = ws + L.LAM + (k * P.nrow + r) * 2;
+                T* TTk = ws + L.TT + (k * NROW() + r) * 2;
+                T* LMk = ws + L.LAM + (k * NROW() + r) * 2;
                 if (!row_valid(k, fam)) {
                     TTk[0] = TTk[1] = T(1);
                     LMk[0] = LMk[1] = T(0);
@@ -942,9 +1065,9 @@ struct Solver {
             T mu = 0, rdmax = 0, pinf = 0;
             for (int k = 0; k <= N; ++k) {
                 const T* zk = Zk(k);
-                const T* TTk = ws + L.TT + k * P.nrow * 2;
-                const T* LMk = ws + L.LAM + k * P.nrow * 2;
-                for (int r = lane; r < P.nrow; r += WARP) {
+                const T* TTk = ws + L.TT + k * NROW() * 2;
+                const T* LMk = ws + L.LAM + k * NROW() * 2;
+                for (int r = lane; r < NROW(); r += WARP) {
                     const int fam = row_family(r);
                     if (!row_valid(k, fam)) continue;
                     T lb, ub;
@@ -995,7 +1118,7 @@ struct Solver {
                 ws[L.Z + idx] += alpha * d;
                 stepmax = max(stepmax, fabs(alpha * d));
             }
-            for (int idx = lane; idx < (N + 1) * P.nrow * 2; idx += WARP) {
+            for (int idx = lane; idx < (N + 1) * NROW() * 2; idx += WARP) {
                 ws[L.TT + idx] += alpha * ws[L.DTT + idx];
                 ws[L.LAM + idx] += alpha * ws[L.DLAM + idx];
             }
@@ -1023,22 +1146,31 @@ struct Solver {
 
     // Feedback gains K_k = -Huu^{-1} Hux from the stored factors (optional output).
     __device__ void write_gains(T* Kout) {
-        const int nu = P.nu, nx = P.nx, nz = P.nz, ldf = L.ldf;
+        const int nu = NU(), nx = NX(), nz = NZ(), ldf = LDF();
         T* F = sM;
         T* col = sV;
         for (int k = 0; k < P.N; ++k) {
-            const T* Fg = ws + L.FAC + k * nz * ldf;
+            const T* Fg = ws + L.FAC + k * FSTRIDE();
             for (int idx = lane; idx < nz * ldf; idx += WARP) F[idx] = Fg[idx];
             __syncwarp();
             for (int xcol = 0; xcol < nx; ++xcol) {
                 for (int j = lane; j < nu; j += WARP) col[j] = F[(nu + xcol) * ldf + j];
                 __syncwarp();
-                for (int j = nu - 1; j >= 0; --j) {
-                    const T uj = -col[j] * F[j * ldf + j];
+                if constexpr (kInvL) {
+                    T uj = T(0);
+                    if (lane < nu)
+                        for (int i = lane; i < nu; ++i) uj -= F[i * ldf + lane] * col[i];
                     __syncwarp();
-                    for (int i = lane; i < j; i += WARP) col[i] += F[j * ldf + i] * uj;
-                    if (lane == 0) col[j] = uj;
+                    if (lane < nu) col[lane] = uj;
                     __syncwarp();
+                } else {
+                    for (int j = nu - 1; j >= 0; --j) {
+                        const T uj = -col[j] * F[j * ldf + j];
+                        __syncwarp();
+                        for (int i = lane; i < j; i += WARP) col[i] += F[j * ldf + i] * uj;
+                        if (lane == 0) col[j] = uj;
+                        __syncwarp();
+                    }
                 }
                 for (int j = lane; j < nu; j += WARP) Kout[(k * nu + j) * nx + xcol] = col[j];
                 __syncwarp();
@@ -1048,7 +1180,7 @@ struct Solver {
 
     // --------------------------------------------------------------- solve
     __device__ void run(const BatchArgs<T>& A, int b) {
-        const int nq = P.nq, nx = P.nx, nu = P.nu, N = P.N, nz = P.nz;
+        const int nq = NQ(), nx = NX(), nu = NU(), N = P.N, nz = NZ();
         // initial guess: DefaultInitializer = zero input, state held
         // (controller_interface.cpp:385-386); x_0 is always the observation
         if (!A.warm) {
@@ -1058,7 +1190,7 @@ struct Solver {
             for (int i = lane; i < nx; i += WARP) X[i] = x0[i];
         }
         __syncwarp();
-        if (P.neq > 0) build_Df();
+        if (NEQ() > 0) build_Df();
         Perf<T> base = performance(X, U);
         int status = UB_STATUS_CONVERGED, qp_iters = 0, sqp_done = 0;
         T alpha = 0, qp_res = 0;
@@ -1171,8 +1303,8 @@ struct Solver {
     }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(256) solve_batch_kernel(const DevProblem<T>* __restrict__ Pg, Layout L, BatchArgs<T> A,
+template <typename T, typename D>
+__global__ void __launch_bounds__(256, 2) solve_batch_kernel(const DevProblem<T>* __restrict__ Pg, Layout L, BatchArgs<T> A,
                                                           int warps_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // CTA-shared copy of the problem constants
@@ -1189,7 +1321,7 @@ __global__ void __launch_bounds__(256) solve_batch_kernel(const DevProblem<T>* _
     if (b >= A.B) return;
     size_t off = (sizeof(DevProblem<T>) + 15) / 16 * 16;
     T* sm = reinterpret_cast<T*>(smem_raw + off) + size_t(warp) * L.s_total;
-    Solver<T> S(*Ps, L, lane);
+    Solver<T, D> S(*Ps, L, lane);
     S.x0 = A.x0 + size_t(b) * Ps->nx;
     S.target = A.target + size_t(b) * (Ps->N + 1) * 3;
     S.body = A.body ? A.body + size_t(b) * Ps->nb * UB_BODY_PARAMS : &Ps->body[0][0];
