@@ -255,6 +255,7 @@ int solve_device(ub_problem* p, int B, const void* x0, const void* target, const
                  int32_t* status, void* stats, void* ws, int64_t ws_bytes, uint32_t flags, cudaStream_t stream) {
     const ub::Layout& L = Pick<T>::layout(p);
     if (ws_bytes < int64_t(B) * L.total * int64_t(sizeof(T))) return fail(UB_E_INVALID, "workspace too small");
+    if (reinterpret_cast<uintptr_t>(ws) % 16 != 0) return fail(UB_E_INVALID, "workspace must be 16-byte aligned");
     ub::BatchArgs<T> A;
     A.x0 = static_cast<const T*>(x0);
     A.target = static_cast<const T*>(target);
@@ -286,7 +287,7 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
     const size_t n_K = K ? size_t(B) * P.N * P.nu * P.nx : 0, n_st = size_t(B) * UB_STATS;
     const size_t n_ws = size_t(B) * L.total;
     const size_t n_in = n_x0 + n_tg + n_bd, n_io = n_X + n_U;
-    const size_t elems = n_in + n_io + n_K + n_st + n_ws;
+    const size_t elems = n_in + n_io + n_K + n_st + n_ws + 8;  // +8: 16-byte alignment pad of the workspace
     const size_t bytes = elems * sizeof(T) + size_t(B) * sizeof(int32_t) + 256;
     if (bytes > p->dev_buf_bytes) {
         if (p->dev_buf) cudaFree(p->dev_buf);
@@ -330,6 +331,7 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
     T* d_K = K ? d_U + n_U : nullptr;
     T* d_st = d_U + n_U + n_K;
     T* d_ws = d_st + n_st;
+    while (reinterpret_cast<uintptr_t>(d_ws) % 16 != 0) ++d_ws;  // vectorised factor copies need 16-byte alignment
     int32_t* d_status = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_ws + n_ws) + 64 - (reinterpret_cast<uintptr_t>(d_ws + n_ws) % 64));
     int rc = solve_device<T>(p, B, d_x0, d_tg, d_bd, d_X, d_U, d_K, d_status, d_st, d_ws, int64_t(n_ws * sizeof(T)),
                              flags | UB_PTRS_DEVICE, stream);
