@@ -1,0 +1,30 @@
+"""Per-phase cycle breakdown of the solve kernel (profile mode, stop_after=9)."""
+import sys
+from pathlib import Path
+import numpy as np
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from upright_b200 import workload
+from upright_b200.engine import BatchedMPC
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg2_thing_demo"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+desc, meta = workload.load(name)
+mpc = BatchedMPC(desc, "f32")
+ee = lambda x: mpc.eval("end_effector_position", x, np.zeros((x.shape[0], mpc.nu)))
+b = workload.sample_batch(name, desc, meta, B, 1234, ee)
+dev = lambda a: None if a is None else torch.tensor(a, dtype=torch.float32, device="cuda")
+x0, tg, bp = dev(b["x0"]), dev(b["target"]), dev(b["body_params"])
+for _ in range(2):
+    out = mpc.solve_device(x0, tg, bp)
+torch.cuda.synchronize()
+print("normal ms", mpc.last_solve_ms())
+mpc.set_option("stop_after", 9)
+out = mpc.solve_device(x0, tg, bp)
+torch.cuda.synchronize()
+st = out["stats"].double().cpu().numpy()
+names = ["qp_iters", "sweep:gradient", "resid+ls", "fac:build", "fac:dynamics", "fac:cholesky", "sweeps(total)", "fac:store+P"]
+tot = st[:, 2:].sum(1)
+print("profile-mode ms", mpc.last_solve_ms(), "mean iters", st[:, 0].mean(), "max iters", st[:, 0].max())
+for i in range(1, 8):
+    print(f"  {names[i]:14s} mean {st[:, i].mean() / 1e6:8.3f} Mcyc  ({100 * st[:, i].mean() / tot.mean():5.1f} %)  per-iter {st[:, i].mean() / st[:, 0].mean() / 1e3:8.1f} kcyc")
+print("  total per warp %.2f Mcyc" % (tot.mean() / 1e6))

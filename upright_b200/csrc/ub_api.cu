@@ -152,11 +152,8 @@ ub::Layout make_layout(const ub::DevProblem<T>& P) {
     L.YE = take(N * P.neq);
     L.RHOT = take(P.nterm);
     L.YT = take(P.nterm);
-    L.TT = take((N + 1) * P.nrow * 2);
-    L.LAM = take((N + 1) * P.nrow * 2);
-    L.DTT = take((N + 1) * P.nrow * 2);
-    L.DLAM = take((N + 1) * P.nrow * 2);
-    L.VAL = take(4);
+    L.TT = take((N + 1) * P.nrow * 8);  // interleaved side records {t, lam, dt, dlam} x {lo, hi}
+    L.LAM = L.DTT = L.DLAM = L.TT;
     L.FAC = take(N * ((nz * L.ldf + 3) & ~3));
     L.WF = take(N * nu);
     L.XN = take((N + 1) * nx);
@@ -173,7 +170,8 @@ ub::Layout make_layout(const ub::DevProblem<T>& P) {
     L.sPv = stake(nx);
     const int sa_rows = P.neq > 3 ? P.neq : 3;
     L.sSA = stake(sa_rows * nz);
-    L.sV = stake(5 * nz + 64);
+    L.sV = stake(5 * nz + 64);  // [4 nz, ...) doubles as per-row scratch (>= max(neq, nobs, 3) entries)
+    L.sBar = stake(32 / int(sizeof(T)));  // three 8-byte mbarriers (+pad)
     L.s_total = s;
     return L;
 }

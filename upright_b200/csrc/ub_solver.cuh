@@ -17,11 +17,15 @@
 
 #include "ub_device.cuh"
 
+#ifndef UB_USE_TMA
+#define UB_USE_TMA 0
+#endif
+
 namespace ub {
 
 // Per-problem workspace layout in units of T (filled on the host).
 struct Layout {
-    int Z, DZ, GAP, LG, LCT, LR, LJP, LHO, LJO, DF, RHOE, YE, RHOT, YT, TT, LAM, DTT, DLAM, VAL, FAC, WF, XN, UN;
+    int Z, DZ, GAP, LG, LCT, LR, LJP, LHO, LJO, DF, RHOE, YE, RHOT, YT, TT, LAM, DTT, DLAM, sBar, FAC, WF, XN, UN;
     int total;
     // shared memory (units of T, per warp)
     int sM, sP, sPv, sSA, sV, s_total, ldm, ldf;
@@ -42,6 +46,32 @@ struct BatchArgs {
     int warm;
     int stop_after;   // debug: 0 = full solve, 1 = stop after first linearisation, 2 = after first QP
 };
+
+
+// ---- TMA (cp.async.bulk, 1-D) global -> shared with mbarrier completion -----------------
+// One elected lane arms the barrier with the byte count and issues the bulk copy; every lane
+// then waits on the barrier phase.  Used to stage the next stage's Riccati factor block while
+// the current stage is being processed (SASS: UBLKCP / SYNCS).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok = 0;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(phase)
+                     : "memory");
+    } while (!ok);
+}
 
 template <typename T>
 __device__ __forceinline__ T tinf() { return T(1e30); }
@@ -97,6 +127,10 @@ struct Solver {
     T* sPv;
     T* sSA;
     T* sV;
+    uint64_t* sBar;      // mbarriers of the factor-block ring
+    long long t_lin = 0, t_fac = 0, t_swp = 0, t_side = 0, t_ls = 0, t_res = 0;
+    long long t_f1 = 0, t_f2 = 0, t_f3 = 0, t_f4 = 0, t_g = 0;  // finer: build / dynamics / cholesky / store ; gradient  // phase cycle counters (profile mode)
+    uint32_t bar_phase[3];
 
     __device__ Solver(const DevProblem<T>& P_, const Layout& L_, int lane_) : P(P_), L(L_), lane(lane_) {}
 
@@ -201,6 +235,21 @@ struct Solver {
         }
     }
     __device__ __forceinline__ int nz_of(int k) const { return k < P.N ? NZ() : NX(); }
+    // Slack/multiplier record of one inequality row: {t_lo, t_hi, lam_lo, lam_hi} and the step
+    // {dt_lo, dt_hi, dlam_lo, dlam_hi}, 8 consecutive values (two 16-byte quads) per row so that a warp
+    // reads the rows of a stage with fully coalesced vector loads.
+    struct alignas(16) Quad {
+        T v[4];
+    };
+    __device__ __forceinline__ Quad* side_tl(int k, int r) const { return reinterpret_cast<Quad*>(ws + L.TT) + (k * NROW() + r) * 2; }
+    __device__ __forceinline__ Quad* side_dd(int k, int r) const { return side_tl(k, r) + 1; }
+    // Newton data of one side: returns the barrier weight and the coefficient that multiplies sgn*a in the
+    // stage gradient;  d = signed distance to the bound at the current iterate
+    __device__ __forceinline__ T side_coef(T t, T lam, T d, T eps, T target, T corr) const {
+        const T rd = d + eps * lam - t;
+        const T rc = t * lam - target + corr;
+        return -lam + (rc + lam * rd) / (t + eps * lam);
+    }
     // stage vectors are stored with stride nz as [du (nu); dx (nx)]; the terminal
     // stage uses the same slots (its du part is unused and kept at zero)
     __device__ __forceinline__ T* Zk(int k) const { return ws + L.Z + k * NZ(); }
@@ -621,46 +670,58 @@ struct Solver {
             __syncwarp();
         }
         // inequality sides: w a a', w = lam / (t + eps lam)
-        const T* TTk = ws + L.TT + k * NROW() * 2;
-        const T* LMk = ws + L.LAM + k * NROW() * 2;
         const int nbx = NBOXU() + NX();
         for (int r = lane; r < nbx; r += WARP) {
             const int fam = r < NBOXU() ? 0 : 1;
             if (!row_valid(k, fam)) continue;
             const T eps = row_eps(fam);
-            const T w = LMk[2 * r] / (TTk[2 * r] + eps * LMk[2 * r]) + LMk[2 * r + 1] / (TTk[2 * r + 1] + eps * LMk[2 * r + 1]);
+            const Quad q = *side_tl(k, r);
+            const T w = q.v[2] / (q.v[0] + eps * q.v[2]) + q.v[3] / (q.v[1] + eps * q.v[3]);
             const int m = fam == 0 ? r : nu + (r - NBOXU());
             sM[m * ld + m] += w;
         }
         __syncwarp();
         if (NFRIC() > 0 && k < P.N) {
             const T eps = row_eps(2);
-            // one lane per (contact, 3x3 lower entry)
-            for (int idx = lane; idx < NC() * 6; idx += WARP) {
-                const int c = idx / 6, e = idx % 6;
-                const int a = (e < 1) ? 0 : (e < 3 ? 1 : 2), b = e - (a == 0 ? 0 : (a == 1 ? 1 : 3));
-                T acc = 0;
+            // one lane per contact: its five pyramid rows give a symmetric 3x3 block
+            for (int c = lane; c < NC(); c += WARP) {
+                T blk[6] = {0, 0, 0, 0, 0, 0};
                 for (int which = 0; which < 5; ++which) {
-                    const int r = nbx + 5 * c + which;
-                    const T w = LMk[2 * r] / (TTk[2 * r] + eps * LMk[2 * r]);
+                    const Quad q = *side_tl(k, nbx + 5 * c + which);
+                    const T w = q.v[2] / (q.v[0] + eps * q.v[2]);
                     const V3<T> cf = fric_coeff(c, which);
-                    acc += w * cf[a] * cf[b];
+                    blk[0] += w * cf.x * cf.x;
+                    blk[1] += w * cf.y * cf.x;
+                    blk[2] += w * cf.y * cf.y;
+                    blk[3] += w * cf.z * cf.x;
+                    blk[4] += w * cf.z * cf.y;
+                    blk[5] += w * cf.z * cf.z;
                 }
-                sM[(nq + 3 * c + a) * ld + nq + 3 * c + b] += acc;
+                T* Mb = sM + (nq + 3 * c) * ld + nq + 3 * c;
+                Mb[0] += blk[0];
+                Mb[ld] += blk[1];
+                Mb[ld + 1] += blk[2];
+                Mb[2 * ld] += blk[3];
+                Mb[2 * ld + 1] += blk[4];
+                Mb[2 * ld + 2] += blk[5];
             }
             __syncwarp();
         }
         if (P.nobs > 0 && k >= 1 && k < P.N) {
             const T eps = row_eps(3);
+            T* wrow = sV + 4 * nz;  // barrier weights of the obstacle rows
+            for (int i = lane; i < P.nobs; i += WARP) {
+                const Quad q = *side_tl(k, nbx + NFRIC() + i);
+                wrow[i] = q.v[2] / (q.v[0] + eps * q.v[2]);
+            }
+            __syncwarp();
             for (int idx = lane; idx < nq * nq; idx += WARP) {
                 const int a = idx / nq, b = idx % nq;
                 if (b > a) continue;
                 T acc = 0;
                 for (int i = 0; i < P.nobs; ++i) {
-                    const int r = nbx + NFRIC() + i;
-                    const T w = LMk[2 * r] / (TTk[2 * r] + eps * LMk[2 * r]);
                     const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
-                    acc += w * J[a] * J[b];
+                    acc += wrow[i] * J[a] * J[b];
                 }
                 sM[(nu + a) * ld + nu + b] += acc;
             }
@@ -716,11 +777,23 @@ struct Solver {
     __device__ bool factor_sweep() {
         const int nu = NU(), nx = NX(), nz = NZ(), ld = LDM();
         bool ok = true;
+        struct FenceAtExit {  // generic-proxy writes of FAC must be visible to the TMA reads of the sweeps
+            __device__ ~FenceAtExit() {
+                if (UB_USE_TMA) asm volatile("fence.proxy.async;" ::: "memory");
+            }
+        } fence_at_exit;
         for (int k = P.N; k >= 0; --k) {
+            long long f0 = clock64();
             build_stage_matrix(k);
+            long long f1 = clock64();
+            t_f1 += f1 - f0;
             if (k < P.N) {
                 add_dynamics_hessian();
+                long long f2 = clock64();
+                t_f2 += f2 - f1;
                 ok &= partial_cholesky(nz, nu);
+                t_f3 += clock64() - f2;
+                f0 = clock64();
                 if constexpr (kInvL) {
                     // lane c builds column c of L^{-1}; stored transposed in the (free) upper triangle
                     if (lane < nu) {
@@ -747,6 +820,7 @@ struct Solver {
                 sP[idx] = (j <= i) ? sM[(nu + i) * ld + nu + j] : sM[(nu + j) * ld + nu + i];  // full symmetric
             }
             __syncwarp();
+            t_f4 += clock64() - f0;
         }
         return ok;
     }
@@ -754,22 +828,23 @@ struct Solver {
     // Stage gradient of the barrier/proximal Lagrangian at the current iterate:
     //   H z + g  +  sum_eq a (rho e + y)  +  sum_sides sgn a [ -lam + (rc + lam rd)/(t + eps lam) ]
     // with rc = t lam - target (+ dt_aff dlam_aff in the corrector).  Result in vec (shared).
+    // Every row family accumulates into distinct entries per lane (no atomics).
     __device__ void stage_gradient(int k, bool corrector, T mu_target, T* vec) {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ();
         const T dt = P.dt;
         const T* zk = Zk(k);
-        for (int i = lane; i < nz; i += WARP) vec[i] = T(0);
-        __syncwarp();
+        const T cm = corrector ? T(1) : T(0);
+        // cost part (zero at the terminal stage)
         if (k < P.N) {
             const T* x = X + k * nx;
             const T* u = U + k * nu;
             const T* Jp = ws + L.LJP + k * 3 * nq;
-            // e = Jp dq + r - r_d
+            // e = Jp dq + r - r_d, reduced over the warp
             T e3[3];
+#pragma unroll
             for (int c = 0; c < 3; ++c) {
-                T e = ws[L.LR + 3 * k + c] - target[3 * k + c];
-                for (int j = 0; j < nq; ++j) e += Jp[c * nq + j] * zk[nu + j];
-                e3[c] = e;
+                const T part = lane < nq ? Jp[c * nq + lane] * zk[nu + lane] : T(0);
+                e3[c] = warp_sum(part) + ws[L.LR + 3 * k + c] - target[3 * k + c];
             }
             for (int i = lane; i < nz; i += WARP) {
                 T g;
@@ -778,25 +853,63 @@ struct Solver {
                 else {
                     const int xi = i - nu;
                     g = dt * P.Qd[xi] * (x[xi] + zk[i] - P.xd[xi]);
-                    if (xi < nq)
-                        for (int c = 0; c < 3; ++c) g += dt * P.Wd[c] * Jp[c * nq + xi] * e3[c];
+                    if (xi < nq) g += dt * (P.Wd[0] * Jp[xi] * e3[0] + P.Wd[1] * Jp[nq + xi] * e3[1] + P.Wd[2] * Jp[2 * nq + xi] * e3[2]);
                 }
                 vec[i] = g;
             }
-            __syncwarp();
+        } else {
+            for (int i = lane; i < nz; i += WARP) vec[i] = T(0);
         }
+        __syncwarp();
+        // box rows: one entry each
+        for (int r = lane; r < NBOXU() + nx; r += WARP) {
+            const int fam = r < NBOXU() ? 0 : 1;
+            if (!row_valid(k, fam)) continue;
+            const int m = fam == 0 ? r : nu + (r - NBOXU());
+            T lb, ub;
+            const T val = zk[m];
+            if (fam == 0) {
+                const T uu = U[k * nu + r];
+                lb = (r < nq ? P.ulb[r] : P.flb) - uu;
+                ub = (r < nq ? P.uub[r] : P.fub) - uu;
+            } else {
+                const int i = r - NBOXU();
+                const T xx = X[k * nx + i];
+                lb = P.xlb[i] - xx;
+                ub = P.xub[i] - xx;
+            }
+            const T eps = row_eps(fam);
+            const Quad q = *side_tl(k, r);
+            Quad dd;
+            if (corrector) dd = *side_dd(k, r);
+            else dd.v[0] = dd.v[1] = dd.v[2] = dd.v[3] = T(0);
+            const T c0 = side_coef(q.v[0], q.v[2], val - lb, eps, mu_target, cm * dd.v[0] * dd.v[2]);
+            const T c1 = side_coef(q.v[1], q.v[3], ub - val, eps, mu_target, cm * dd.v[1] * dd.v[3]);
+            vec[m] += c0 - c1;
+        }
+        __syncwarp();
+        // equality rows
         const int ne = neq_of(k);
         if (ne > 0) {
             load_eq_rows(k);
             const T* rho = rho_eq(k);
             const T* y = y_eq(k);
-            // per-row multipliers m_i = rho e + y (kept in registers of lane i), then vec += sum_i m_i a_i
             const int nd = (k < P.N) ? ne : 3;
-            T* mrow = sV + 4 * nz;  // scratch [nd]
-            for (int i = lane; i < ne; i += WARP) {
-                const T m = rho[i] * eq_value(k, i, zk) + y[i];
-                if (i < nd) mrow[i] = m;
-                else vec[nu + nq + (i - 3)] += m;  // terminal unit rows (distinct entries)
+            T* mrow = sV + 4 * nz;  // per-row multiplier estimate m_i = rho e_i + y_i
+            if (D::kStatic && D::neq <= 8 && k < P.N) {
+                // few dense rows: every row value as a warp-wide dot product
+                for (int i = 0; i < nd; ++i) {
+                    T part = T(0);
+                    for (int j = nq + lane; j < nz; j += WARP) part += sSA[i * nz + j] * zk[j];
+                    const T e = warp_sum(part) + eq_const(k, i);
+                    if (lane == 0) mrow[i] = rho[i] * e + y[i];
+                }
+            } else {
+                for (int i = lane; i < ne; i += WARP) {
+                    const T m = rho[i] * eq_value(k, i, zk) + y[i];
+                    if (i < nd) mrow[i] = m;
+                    else vec[nu + nq + (i - 3)] += m;  // terminal unit rows (distinct entries)
+                }
             }
             __syncwarp();
             for (int j = lane; j < nz; j += WARP) {
@@ -806,30 +919,60 @@ struct Solver {
             }
             __syncwarp();
         }
-        const T* TTk = ws + L.TT + k * NROW() * 2;
-        const T* LMk = ws + L.LAM + k * NROW() * 2;
-        const T* DTk = ws + L.DTT + k * NROW() * 2;
-        const T* DLk = ws + L.DLAM + k * NROW() * 2;
-        for (int r = lane; r < NROW(); r += WARP) {
-            const int fam = row_family(r);
-            if (!row_valid(k, fam)) continue;
-            T lb, ub;
-            const T val = row_value(k, r, fam, zk, &lb, &ub);
-            const T eps = row_eps(fam);
-            T coef = T(0);
-            for (int sd = 0; sd < 2; ++sd) {
-                if (sd == 1 && fam >= 2) break;
-                const T t = TTk[2 * r + sd], lam = LMk[2 * r + sd];
-                const T sg = sd == 0 ? T(1) : T(-1);
-                const T d = sd == 0 ? val - lb : ub - val;
-                const T rd = d + eps * lam - t;
-                T rc = t * lam - mu_target;
-                if (corrector) rc += DTk[2 * r + sd] * DLk[2 * r + sd];
-                coef += sg * (-lam + (rc + lam * rd) / (t + eps * lam));
+        const int nbx = NBOXU() + nx;
+        if (NFRIC() > 0 && k < P.N) {
+            // one lane per contact: five pyramid rows -> three force entries
+            const T eps = row_eps(2);
+            for (int c = lane; c < NC(); c += WARP) {
+                const T* f = U + k * nu + nq + 3 * c;
+                const T* df = zk + nq + 3 * c;
+                const T f0 = f[0] + df[0], f1 = f[1] + df[1], f2 = f[2] + df[2];
+                T g0 = 0, g1 = 0, g2 = 0;
+                for (int which = 0; which < 5; ++which) {
+                    const int r = nbx + 5 * c + which;
+                    const V3<T> a = fric_coeff(c, which);
+                    const T val = a.x * f0 + a.y * f1 + a.z * f2;
+                    const Quad q = *side_tl(k, r);
+                    T corr = T(0);
+                    if (corrector) {
+                        const Quad dd = *side_dd(k, r);
+                        corr = dd.v[0] * dd.v[2];
+                    }
+                    const T cf = side_coef(q.v[0], q.v[2], val, eps, mu_target, corr);
+                    g0 += cf * a.x;
+                    g1 += cf * a.y;
+                    g2 += cf * a.z;
+                }
+                vec[nq + 3 * c] += g0;
+                vec[nq + 3 * c + 1] += g1;
+                vec[nq + 3 * c + 2] += g2;
             }
-            row_axpy(k, r, fam, coef, vec);
+            __syncwarp();
         }
-        __syncwarp();
+        if (P.nobs > 0 && k >= 1 && k < P.N) {
+            const T eps = row_eps(3);
+            T* crow = sV + 4 * nz;
+            for (int i = lane; i < P.nobs; i += WARP) {
+                const int r = nbx + NFRIC() + i;
+                const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
+                T val = ws[L.LHO + k * P.nobs + i];
+                for (int j = 0; j < nq; ++j) val += J[j] * zk[nu + j];
+                const Quad q = *side_tl(k, r);
+                T corr = T(0);
+                if (corrector) {
+                    const Quad dd = *side_dd(k, r);
+                    corr = dd.v[0] * dd.v[2];
+                }
+                crow[i] = side_coef(q.v[0], q.v[2], val, eps, mu_target, corr);
+            }
+            __syncwarp();
+            if (lane < nq) {
+                T acc = 0;
+                for (int i = 0; i < P.nobs; ++i) acc += crow[i] * ws[L.LJO + (k * P.nobs + i) * nq + lane];
+                vec[nu + lane] += acc;
+            }
+            __syncwarp();
+        }
     }
 
     // 16-byte vectorised copy global -> shared (both 16-byte aligned; n in elements)
@@ -844,25 +987,53 @@ struct Solver {
 
     // Vector sweeps with the stored factors: backward (w_k, cost-to-go gradient)
     // then forward (direction DZ).  `corrector`/`target_mu` select the right-hand side.
+    // Double-buffered staging of the factor blocks: when two blocks fit into the (idle) stage
+    // matrix buffer, stage k+-1 is fetched by TMA while stage k is processed.
+    // Measured on B200 (cfg2, B = 4096): TMA ring 42.1 ms vs plain vectorised copies 38.2 ms per batch — the
+    // factor-block fetch is not the latency that binds, and the proxy fence after every factor sweep costs
+    // more than the prefetch hides.  Kept behind UB_USE_TMA (default off) with the measurement in DESIGN.md.
+    static constexpr int kFacRing = 3;  // ring depth of the factor-block staging
+    __device__ __forceinline__ bool fac_double_buffered() const { return UB_USE_TMA && kFacRing * FSTRIDE() <= NZ() * LDM(); }
+    __device__ __forceinline__ void fac_issue(int k, int buf) {
+        if (lane == 0) tma_load_1d(sM + buf * FSTRIDE(), ws + L.FAC + k * FSTRIDE(), uint32_t(FSTRIDE() * sizeof(T)), sBar + buf);
+    }
+    __device__ __forceinline__ const T* fac_wait(int buf) {
+        mbar_wait(sBar + buf, bar_phase[buf]);
+        bar_phase[buf] ^= 1u;
+        return sM + buf * FSTRIDE();
+    }
+
     __device__ void solve_sweeps(bool corrector, T target_mu) {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ldf = LDF();
         T* vec = sV;           // [nz] gradient
         T* dx = sV + nz;       // [nx]
         T* du = sV + 2 * nz;   // [nu] (also s)
-        T* F = sM;             // factor block staged in shared memory
+        const bool dbuf = fac_double_buffered();
         // backward
         for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
         __syncwarp();
+        if (dbuf)
+            for (int d = 0; d < kFacRing - 1; ++d)
+                if (P.N - 1 - d >= 0) fac_issue(P.N - 1 - d, (P.N - 1 - d) % kFacRing);
         for (int k = P.N; k >= 0; --k) {
+            const long long g0 = clock64();
             stage_gradient(k, corrector, target_mu, vec);
+            t_g += clock64() - g0;
             if (k == P.N) {
                 for (int i = lane; i < nx; i += WARP) sPv[i] = vec[nu + i];
                 __syncwarp();
                 continue;
             }
             add_dynamics_gradient(vec);
-            copy_block(F, ws + L.FAC + k * FSTRIDE(), nz * ldf);
-            __syncwarp();
+            const T* F;
+            if (dbuf) {
+                if (k - (kFacRing - 1) >= 0) fac_issue(k - (kFacRing - 1), (k - (kFacRing - 1)) % kFacRing);  // slot last read at stage k+1
+                F = fac_wait(k % kFacRing);
+            } else {
+                copy_block(sM, ws + L.FAC + k * FSTRIDE(), nz * ldf);
+                F = sM;
+                __syncwarp();
+            }
             // w = L^{-1} m_u
             if constexpr (kInvL) {
                 T wi = T(0);
@@ -896,10 +1067,20 @@ struct Solver {
         // forward: d x_0 = 0
         for (int i = lane; i < nx; i += WARP) dx[i] = T(0);
         __syncwarp();
+        if (dbuf)
+            for (int d = 0; d < kFacRing - 1; ++d)
+                if (d < P.N) fac_issue(d, d % kFacRing);
         for (int k = 0; k < P.N; ++k) {
-            copy_block(F, ws + L.FAC + k * FSTRIDE(), nz * ldf);
+            const T* F;
+            if (dbuf) {
+                if (k + kFacRing - 1 < P.N) fac_issue(k + kFacRing - 1, (k + kFacRing - 1) % kFacRing);
+                F = fac_wait(k % kFacRing);
+            } else {
+                copy_block(sM, ws + L.FAC + k * FSTRIDE(), nz * ldf);
+                F = sM;
+                __syncwarp();
+            }
             const T* Wk = ws + L.WF + k * nu;
-            __syncwarp();
             // s = w + Y dx
             for (int j = lane; j < nu; j += WARP) {
                 T acc = Wk[j];
@@ -944,17 +1125,14 @@ struct Solver {
     }
 
     // d lambda / d t of every side for the direction in DZ; returns the largest
-    // step in (0,1] keeping t and lambda positive, and (via *mu_aff) the mean
+    // step in (0,1] keeping t and lambda positive, and (via *mu_after) the summed
     // complementarity after that step.
     __device__ T side_steps(bool corrector, T target_mu, T* mu_after) {
         T amax = T(1);
+        const T cm = corrector ? T(1) : T(0);
         for (int k = 0; k <= P.N; ++k) {
             const T* zk = Zk(k);
             const T* dk = DZk(k);
-            T* TTk = ws + L.TT + k * NROW() * 2;
-            T* LMk = ws + L.LAM + k * NROW() * 2;
-            T* DTk = ws + L.DTT + k * NROW() * 2;
-            T* DLk = ws + L.DLAM + k * NROW() * 2;
             for (int r = lane; r < NROW(); r += WARP) {
                 const int fam = row_family(r);
                 if (!row_valid(k, fam)) continue;
@@ -962,40 +1140,39 @@ struct Solver {
                 const T val = row_value(k, r, fam, zk, &lb, &ub);
                 const T adz = row_dot(k, r, fam, dk);
                 const T eps = row_eps(fam);
-                for (int sd = 0; sd < 2; ++sd) {
-                    if (sd == 1 && fam >= 2) break;
-                    const T t = TTk[2 * r + sd], lam = LMk[2 * r + sd];
+                const Quad q = *side_tl(k, r);
+                Quad dd = *side_dd(k, r);
+                const int nsd = fam >= 2 ? 1 : 2;
+                for (int sd = 0; sd < nsd; ++sd) {
+                    const T t = q.v[sd], lam = q.v[2 + sd];
                     const T sg = sd == 0 ? T(1) : T(-1);
                     const T d = sd == 0 ? val - lb : ub - val;
                     const T rd = d + eps * lam - t;
-                    T rc = t * lam - target_mu;
-                    if (corrector) rc += DTk[2 * r + sd] * DLk[2 * r + sd];
+                    const T rc = t * lam - target_mu + cm * dd.v[sd] * dd.v[2 + sd];
                     const T den = t + eps * lam;
                     const T dl = -(rc + lam * rd) / den - (lam / den) * sg * adz;
                     const T dtt = sg * adz + eps * dl + rd;
-                    DLk[2 * r + sd] = dl;
-                    DTk[2 * r + sd] = dtt;
+                    dd.v[sd] = dtt;
+                    dd.v[2 + sd] = dl;
                     if (dtt < T(0)) amax = min(amax, -t / dtt);
                     if (dl < T(0)) amax = min(amax, -lam / dl);
                 }
+                *side_dd(k, r) = dd;
             }
         }
         amax = warp_min(amax);
         __syncwarp();
         if (mu_after) {
             T acc = 0;
-            for (int k = 0; k <= P.N; ++k) {
-                const T* TTk = ws + L.TT + k * NROW() * 2;
-                const T* LMk = ws + L.LAM + k * NROW() * 2;
-                const T* DTk = ws + L.DTT + k * NROW() * 2;
-                const T* DLk = ws + L.DLAM + k * NROW() * 2;
+            for (int k = 0; k <= P.N; ++k)
                 for (int r = lane; r < NROW(); r += WARP) {
                     const int fam = row_family(r);
                     if (!row_valid(k, fam)) continue;
-                    for (int sd = 0; sd < (fam >= 2 ? 1 : 2); ++sd)
-                        acc += (TTk[2 * r + sd] + amax * DTk[2 * r + sd]) * (LMk[2 * r + sd] + amax * DLk[2 * r + sd]);
+                    const Quad q = *side_tl(k, r);
+                    const Quad dd = *side_dd(k, r);
+                    acc += (q.v[0] + amax * dd.v[0]) * (q.v[2] + amax * dd.v[2]);
+                    if (fam < 2) acc += (q.v[1] + amax * dd.v[1]) * (q.v[3] + amax * dd.v[3]);
                 }
-            }
             *mu_after = warp_sum(acc);
         }
         return amax;
@@ -1034,26 +1211,24 @@ struct Solver {
             const T* zk = Zk(k);
             for (int r = lane; r < NROW(); r += WARP) {
                 const int fam = row_family(r);
-                T* TTk = ws + L.TT + (k * NROW() + r) * 2;
-                T* LMk = ws + L.LAM + (k * NROW() + r) * 2;
-                if (!row_valid(k, fam)) {
-                    TTk[0] = TTk[1] = T(1);
-                    LMk[0] = LMk[1] = T(0);
-                    continue;
-                }
-                T lb, ub;
-                const T val = row_value(k, r, fam, zk, &lb, &ub);
-                TTk[0] = max(val - lb, P.thr0);
-                LMk[0] = P.mu0 / TTk[0];
-                ++nsides_l;
-                if (fam < 2) {
-                    TTk[1] = max(ub - val, P.thr0);
-                    LMk[1] = P.mu0 / TTk[1];
+                Quad q, dd;
+                q.v[0] = q.v[1] = T(1);
+                q.v[2] = q.v[3] = T(0);
+                dd.v[0] = dd.v[1] = dd.v[2] = dd.v[3] = T(0);
+                if (row_valid(k, fam)) {
+                    T lb, ub;
+                    const T val = row_value(k, r, fam, zk, &lb, &ub);
+                    q.v[0] = max(val - lb, P.thr0);
+                    q.v[2] = P.mu0 / q.v[0];
                     ++nsides_l;
-                } else {
-                    TTk[1] = T(1);
-                    LMk[1] = T(0);
+                    if (fam < 2) {
+                        q.v[1] = max(ub - val, P.thr0);
+                        q.v[3] = P.mu0 / q.v[1];
+                        ++nsides_l;
+                    }
                 }
+                *side_tl(k, r) = q;
+                *side_dd(k, r) = dd;
             }
         }
         const int nsides = __reduce_add_sync(FULL, nsides_l);
@@ -1061,23 +1236,23 @@ struct Solver {
         T last_alpha = T(0), last_step = tinf<T>();
         int iters = 0;
         for (int it = 0; it < P.qp_iter_max; ++it) {
+            const long long c_it = clock64();
             // residual summary: mu, max |rd|, equality infeasibility
             T mu = 0, rdmax = 0, pinf = 0;
             for (int k = 0; k <= N; ++k) {
                 const T* zk = Zk(k);
-                const T* TTk = ws + L.TT + k * NROW() * 2;
-                const T* LMk = ws + L.LAM + k * NROW() * 2;
                 for (int r = lane; r < NROW(); r += WARP) {
                     const int fam = row_family(r);
                     if (!row_valid(k, fam)) continue;
                     T lb, ub;
                     const T val = row_value(k, r, fam, zk, &lb, &ub);
                     const T eps = row_eps(fam);
-                    for (int sd = 0; sd < (fam >= 2 ? 1 : 2); ++sd) {
-                        const T t = TTk[2 * r + sd], lam = LMk[2 * r + sd];
-                        const T d = sd == 0 ? val - lb : ub - val;
-                        rdmax = max(rdmax, fabs(d + eps * lam - t));
-                        mu += t * lam;
+                    const Quad q = *side_tl(k, r);
+                    rdmax = max(rdmax, fabs(val - lb + eps * q.v[2] - q.v[0]));
+                    mu += q.v[0] * q.v[2];
+                    if (fam < 2) {
+                        rdmax = max(rdmax, fabs(ub - val + eps * q.v[3] - q.v[1]));
+                        mu += q.v[1] * q.v[3];
                     }
                 }
                 if (!P.soft_poly && neq_of(k) > 0) {
@@ -1096,21 +1271,32 @@ struct Solver {
                 break;
             }
             iters = it + 1;
+            long long c1 = clock64();
+            t_res += c1 - c_it;
             if (!factor_sweep()) *finite = false;
+            long long c2 = clock64();
+            t_fac += c2 - c1;
             T target_mu = P.mu_target;
             if (nsides > 0) {
                 solve_sweeps(false, T(0));
+                long long c3 = clock64();
+                t_swp += c3 - c2;
                 T mu_aff;
                 side_steps(false, T(0), &mu_aff);
                 mu_aff /= T(nsides);
                 const T ratio = mu_aff / mu;
                 target_mu = max(ratio * ratio * ratio * mu, P.mu_target);
+                long long c4 = clock64();
+                t_side += c4 - c3;
                 solve_sweeps(true, target_mu);
+                c2 = clock64();
+                t_swp += c2 - c4;
             } else {
                 solve_sweeps(false, T(0));
             }
             T alpha = T(1);
             if (nsides > 0) alpha = min(T(1), T(0.995) * side_steps(true, target_mu, nullptr));
+            t_side += clock64() - c2;
             // update z, t, lambda, equality multipliers
             T stepmax = 0, dec = 0;
             for (int idx = lane; idx < (N + 1) * nz; idx += WARP) {
@@ -1118,9 +1304,13 @@ struct Solver {
                 ws[L.Z + idx] += alpha * d;
                 stepmax = max(stepmax, fabs(alpha * d));
             }
-            for (int idx = lane; idx < (N + 1) * NROW() * 2; idx += WARP) {
-                ws[L.TT + idx] += alpha * ws[L.DTT + idx];
-                ws[L.LAM + idx] += alpha * ws[L.DLAM + idx];
+            for (int idx = lane; idx < (N + 1) * NROW(); idx += WARP) {
+                Quad* rec = reinterpret_cast<Quad*>(ws + L.TT) + 2 * idx;
+                Quad q = rec[0];
+                const Quad dd = rec[1];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) q.v[c] += alpha * dd.v[c];
+                rec[0] = q;
             }
             __syncwarp();
             if (!P.soft_poly)
@@ -1198,7 +1388,9 @@ struct Solver {
         T* Un = ws + L.UN;
         for (int it = 0; it < max(1, P.sqp_iters); ++it) {
             ++sqp_done;
+            long long c0 = clock64();
             linearize();
+            t_lin += clock64() - c0;
             if (A.stop_after == 1) break;
             bool conv, fin;
             qp_iters += solve_qp(&conv, &qp_res, &fin);
@@ -1230,6 +1422,7 @@ struct Solver {
                 }
             }
             desc = warp_sum(desc);
+            const long long c_ls = clock64();
             // filter line search (ocs2 FilterLinesearch [EXT])
             const T vb = base.violation();
             bool accepted = false;
@@ -1257,6 +1450,7 @@ struct Solver {
                 if (accepted) break;
                 alpha *= P.alpha_decay;
             }
+            t_ls += clock64() - c_ls;
             if (!accepted) {
                 status = UB_STATUS_LS_FAILED;
                 alpha = T(0);
@@ -1298,6 +1492,18 @@ struct Solver {
                 s[5] = base.max_eq;
                 s[6] = base.min_margin;
                 s[7] = T(sqp_done);
+                if (A.stop_after == 9) {  // profile mode: phase cycle counters instead of the last four entries
+                    s[0] = T(qp_iters) + T(1e-3) * T(0);
+                    s[1] = T(t_g);
+                    s[2] = T(t_res + t_ls);
+                    s[3] = T(t_f1) ;
+                    T* s2 = s;  // second half encoded below
+                    (void)s2;
+                    s[4] = T(t_f2);
+                    s[5] = T(t_f3);
+                    s[6] = T(t_swp);
+                    s[7] = T(t_f4);
+                }
             }
         }
     }
@@ -1333,6 +1539,15 @@ __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const DevProblem<T>
     S.sPv = sm + L.sPv;
     S.sSA = sm + L.sSA;
     S.sV = sm + L.sV;
+    S.sBar = reinterpret_cast<uint64_t*>(sm + L.sBar);
+    S.bar_phase[0] = S.bar_phase[1] = S.bar_phase[2] = 0u;
+    if (lane == 0) {
+        mbar_init(S.sBar, 1);
+        mbar_init(S.sBar + 1, 1);
+        mbar_init(S.sBar + 2, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
     S.run(A, b);
 }
 

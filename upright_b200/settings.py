@@ -373,7 +373,7 @@ class ControllerSettings:
         # numerics: documented choices
         d.qp_method = 0
         d.rho_hard = 1.0e3
-        d.qp_mu0, d.qp_thr0, d.qp_mu_target = 1.0e-2, 3.0, 1.0e-7
+        d.qp_mu0, d.qp_thr0, d.qp_mu_target = 1.0e-1, 3.0, 1.0e-7
         d.qp_tol, d.reg_input = 1.0e-5, 1.0e-6
         d.alpha_decay, d.alpha_min = 0.5, 1e-4
         d.g_max, d.g_min, d.gamma_c, d.armijo_factor = 1e6, 1e-6, 1e-6, 1e-4
