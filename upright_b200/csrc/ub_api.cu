@@ -153,7 +153,8 @@ ub::Layout make_layout(const ub::DevProblem<T>& P) {
     L.RHOT = take(P.nterm);
     L.YT = take(P.nterm);
     L.TT = take((N + 1) * P.nrow * 8);  // interleaved side records {t, lam, dt, dlam} x {lo, hi}
-    L.LAM = L.DTT = L.DLAM = L.TT;
+    L.LAM = take((N + 1) * nz);  // GP: predictor stage gradients kept for the corrector
+    L.DTT = L.DLAM = L.TT;
     L.FAC = take(N * ((nz * L.ldf + 3) & ~3));
     L.WF = take(N * nu);
     L.XN = take((N + 1) * nx);

@@ -607,7 +607,7 @@ struct Solver {
 
     // Build the Newton matrix of stage k in sM (lower triangle): cost Hessian +
     // equality proximal terms + barrier terms of the inequality sides.
-    __device__ void build_stage_matrix(int k) {
+    __device__ void build_stage_matrix(int k, bool rows_loaded = false) {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ld = LDM();
         const T dt = P.dt;
         for (int idx = lane; idx < nz * ld; idx += WARP) sM[idx] = T(0);
@@ -635,7 +635,7 @@ struct Solver {
         // equality rows: rho a a'
         const int ne = neq_of(k);
         if (ne > 0) {
-            load_eq_rows(k);
+            if (!rows_loaded) load_eq_rows(k);
             const T* rho = rho_eq(k);
             const int nd = (k < P.N) ? ne : 3;
             const int j0 = (k < P.N) ? nq : nu;  // first column with non-zeros
@@ -1178,6 +1178,290 @@ struct Solver {
         return amax;
     }
 
+    // ---------------------------------------------------------------- fused IPM passes
+    // Pass A (backward): per stage load the equality rows once, form the predictor gradient
+    // (sigma = 0), keep it in GP for the corrector, build and factor the stage matrix and do the
+    // backward vector step with the factor still in shared memory.
+    __device__ bool pass_factor_predict() {
+        const int nu = NU(), nx = NX(), nz = NZ(), ld = LDM(), ldf = LDF();
+        T* vec = sV;
+        bool ok = true;
+        for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
+        __syncwarp();
+        for (int k = P.N; k >= 0; --k) {
+            long long f0 = clock64();
+            stage_gradient(k, false, T(0), vec);            // loads the equality rows of stage k into sSA
+            T* GPk = ws + L.LAM + k * nz;
+            for (int i = lane; i < nz; i += WARP) GPk[i] = vec[i];
+            long long f1 = clock64();
+            t_g += f1 - f0;
+            build_stage_matrix(k, true);
+            long long f2 = clock64();
+            t_f1 += f2 - f1;
+            if (k < P.N) {
+                add_dynamics_hessian();
+                add_dynamics_gradient(vec);                  // uses p_{k+1} in sPv
+                long long f3 = clock64();
+                t_f2 += f3 - f2;
+                ok &= partial_cholesky(nz, nu);
+                long long f4 = clock64();
+                t_f3 += f4 - f3;
+                if constexpr (kInvL) {
+                    // lane c builds column c of L^{-1}; stored transposed in the (free) upper triangle
+                    if (lane < nu) {
+                        const int c = lane;
+                        for (int i = c + 1; i < nu; ++i) {
+                            T acc = sM[i * ld + c] * sM[c * ld + c];
+                            for (int m = c + 1; m < i; ++m) acc += sM[i * ld + m] * sM[c * ld + m];
+                            sM[c * ld + i] = -acc * sM[i * ld + i];
+                        }
+                    }
+                    __syncwarp();
+                    // w = L^{-1} m_u straight from the stage matrix buffer
+                    T wi = T(0);
+                    if (lane < nu) {
+                        for (int j = 0; j < lane; ++j) wi += sM[j * ld + lane] * vec[j];
+                        wi += sM[lane * ld + lane] * vec[lane];
+                    }
+                    __syncwarp();
+                    if (lane < nu) vec[lane] = wi;
+                    __syncwarp();
+                } else {
+                    for (int j = 0; j < nu; ++j) {  // forward substitution, column oriented
+                        const T wj = vec[j] * sM[j * ld + j];
+                        __syncwarp();
+                        if (lane == 0) vec[j] = wj;
+                        for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= sM[i * ld + j] * wj;
+                        __syncwarp();
+                    }
+                }
+                T* Wk = ws + L.WF + k * nu;
+                for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
+                // p = m_x - Y' w
+                for (int i = lane; i < nx; i += WARP) {
+                    T acc = vec[nu + i];
+                    const T* Mr = sM + (nu + i) * ld;
+                    for (int j = 0; j < nu; ++j) acc -= Mr[j] * vec[j];
+                    sPv[i] = acc;
+                }
+                // factor block [L or L^{-1}; Y] -> global for the forward / corrector passes
+                T* F = ws + L.FAC + k * FSTRIDE();
+                for (int idx = lane; idx < nz * nu; idx += WARP) {
+                    const int i = idx / nu, j = idx % nu;
+                    T v = T(0);
+                    if (j <= i) v = (kInvL && i < nu && j < i) ? sM[j * ld + i] : sM[i * ld + j];
+                    F[i * ldf + j] = v;
+                }
+            } else {
+                for (int i = lane; i < nx; i += WARP) sPv[i] = vec[nu + i];
+            }
+            // cost-to-go Hessian: trailing block, full symmetric
+            for (int idx = lane; idx < nx * nx; idx += WARP) {
+                const int i = idx / nx, j = idx % nx;
+                sP[idx] = (j <= i) ? sM[(nu + i) * ld + nu + j] : sM[(nu + j) * ld + nu + i];
+            }
+            __syncwarp();
+        }
+        if (UB_USE_TMA) asm volatile("fence.proxy.async;" ::: "memory");
+        return ok;
+    }
+
+    // Pass C (backward, corrector): gradient = stored predictor gradient + the side terms that change
+    // with the centring target and the second-order correction; backward vector step with stored factors.
+    __device__ void pass_backward_corrector(T target_mu) {
+        const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ldf = LDF();
+        T* vec = sV;
+        for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
+        __syncwarp();
+        const int nbx = NBOXU() + nx;
+        for (int k = P.N; k >= 0; --k) {
+            const T* GPk = ws + L.LAM + k * nz;
+            for (int i = lane; i < nz; i += WARP) vec[i] = GPk[i];
+            __syncwarp();
+            // (corr - target) / (t + eps lam) per side
+            for (int r = lane; r < nbx; r += WARP) {
+                const int fam = r < NBOXU() ? 0 : 1;
+                if (!row_valid(k, fam)) continue;
+                const int m = fam == 0 ? r : nu + (r - NBOXU());
+                const T eps = row_eps(fam);
+                const Quad q = *side_tl(k, r);
+                const Quad dd = *side_dd(k, r);
+                vec[m] += (dd.v[0] * dd.v[2] - target_mu) / (q.v[0] + eps * q.v[2]) -
+                          (dd.v[1] * dd.v[3] - target_mu) / (q.v[1] + eps * q.v[3]);
+            }
+            __syncwarp();
+            if (NFRIC() > 0 && k < P.N) {
+                const T eps = row_eps(2);
+                for (int c = lane; c < NC(); c += WARP) {
+                    T g0 = 0, g1 = 0, g2 = 0;
+                    for (int which = 0; which < 5; ++which) {
+                        const int r = nbx + 5 * c + which;
+                        const V3<T> a = fric_coeff(c, which);
+                        const Quad q = *side_tl(k, r);
+                        const Quad dd = *side_dd(k, r);
+                        const T cf = (dd.v[0] * dd.v[2] - target_mu) / (q.v[0] + eps * q.v[2]);
+                        g0 += cf * a.x;
+                        g1 += cf * a.y;
+                        g2 += cf * a.z;
+                    }
+                    vec[nq + 3 * c] += g0;
+                    vec[nq + 3 * c + 1] += g1;
+                    vec[nq + 3 * c + 2] += g2;
+                }
+                __syncwarp();
+            }
+            if (P.nobs > 0 && k >= 1 && k < P.N) {
+                const T eps = row_eps(3);
+                T* crow = sV + 4 * nz;
+                for (int i = lane; i < P.nobs; i += WARP) {
+                    const int r = nbx + NFRIC() + i;
+                    const Quad q = *side_tl(k, r);
+                    const Quad dd = *side_dd(k, r);
+                    crow[i] = (dd.v[0] * dd.v[2] - target_mu) / (q.v[0] + eps * q.v[2]);
+                }
+                __syncwarp();
+                if (lane < nq) {
+                    T acc = 0;
+                    for (int i = 0; i < P.nobs; ++i) acc += crow[i] * ws[L.LJO + (k * P.nobs + i) * nq + lane];
+                    vec[nu + lane] += acc;
+                }
+                __syncwarp();
+            }
+            if (k == P.N) {
+                for (int i = lane; i < nx; i += WARP) sPv[i] = vec[nu + i];
+                __syncwarp();
+                continue;
+            }
+            add_dynamics_gradient(vec);
+            copy_block(sM, ws + L.FAC + k * FSTRIDE(), nz * ldf);
+            const T* F = sM;
+            __syncwarp();
+            if constexpr (kInvL) {
+                T wi = T(0);
+                if (lane < nu) {
+                    const T* Fr = F + lane * ldf;
+                    for (int j = 0; j <= lane; ++j) wi += Fr[j] * vec[j];
+                }
+                __syncwarp();
+                if (lane < nu) vec[lane] = wi;
+                __syncwarp();
+            } else {
+                for (int j = 0; j < nu; ++j) {
+                    const T wj = vec[j] * F[j * ldf + j];
+                    __syncwarp();
+                    if (lane == 0) vec[j] = wj;
+                    for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= F[i * ldf + j] * wj;
+                    __syncwarp();
+                }
+            }
+            T* Wk = ws + L.WF + k * nu;
+            for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
+            for (int i = lane; i < nx; i += WARP) {
+                T acc = vec[nu + i];
+                const T* Fr = F + (nu + i) * ldf;
+                for (int j = 0; j < nu; ++j) acc -= Fr[j] * vec[j];
+                sPv[i] = acc;
+            }
+            __syncwarp();
+        }
+    }
+
+    // Side steps of the rows of ONE stage for the stage direction d = [du; dx] (shared memory):
+    // d lambda, d t per side, and the running maximum feasible step.
+    __device__ __forceinline__ void stage_side_steps(int k, const T* d, bool corrector, T target_mu, T& amax) {
+        const T* zk = Zk(k);
+        const T cm = corrector ? T(1) : T(0);
+        for (int r = lane; r < NROW(); r += WARP) {
+            const int fam = row_family(r);
+            if (!row_valid(k, fam)) continue;
+            T lb, ub;
+            const T val = row_value(k, r, fam, zk, &lb, &ub);
+            const T adz = row_dot(k, r, fam, d);
+            const T eps = row_eps(fam);
+            const Quad q = *side_tl(k, r);
+            Quad dd = *side_dd(k, r);
+            const int nsd = fam >= 2 ? 1 : 2;
+            for (int sd = 0; sd < nsd; ++sd) {
+                const T t = q.v[sd], lam = q.v[2 + sd];
+                const T sg = sd == 0 ? T(1) : T(-1);
+                const T dist = sd == 0 ? val - lb : ub - val;
+                const T rd = dist + eps * lam - t;
+                const T rc = t * lam - target_mu + cm * dd.v[sd] * dd.v[2 + sd];
+                const T den = t + eps * lam;
+                const T dl = -(rc + lam * rd) / den - (lam / den) * sg * adz;
+                const T dtt = sg * adz + eps * dl + rd;
+                dd.v[sd] = dtt;
+                dd.v[2 + sd] = dl;
+                if (dtt < T(0)) amax = min(amax, -t / dtt);
+                if (dl < T(0)) amax = min(amax, -lam / dl);
+            }
+            *side_dd(k, r) = dd;
+        }
+    }
+
+    // Passes B / D (forward): direction from the stored factors and w, written to DZ, with the side
+    // steps of every stage fused in.  Returns the largest feasible step in (0, 1].
+    __device__ T pass_forward(bool corrector, T target_mu) {
+        const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ldf = LDF();
+        T* dxn = sV + nz;       // [nx] next state direction
+        T* dst = sV + 2 * nz;   // [nz] stage direction [du; dx]
+        T* du = dst;
+        T* dx = dst + nu;
+        T amax = T(1);
+        for (int i = lane; i < nz; i += WARP) dst[i] = T(0);
+        __syncwarp();
+        for (int k = 0; k <= P.N; ++k) {
+            if (k < P.N) {
+                copy_block(sM, ws + L.FAC + k * FSTRIDE(), nz * ldf);
+                const T* F = sM;
+                const T* Wk = ws + L.WF + k * nu;
+                __syncwarp();
+                // s = w + Y dx
+                for (int j = lane; j < nu; j += WARP) {
+                    T acc = Wk[j];
+                    for (int i = 0; i < nx; ++i) acc += F[(nu + i) * ldf + j] * dx[i];
+                    du[j] = acc;
+                }
+                __syncwarp();
+                if constexpr (kInvL) {
+                    T uj = T(0);
+                    if (lane < nu)
+                        for (int i = lane; i < nu; ++i) uj -= F[i * ldf + lane] * du[i];
+                    __syncwarp();
+                    if (lane < nu) du[lane] = uj;
+                    __syncwarp();
+                } else {
+                    for (int j = nu - 1; j >= 0; --j) {
+                        const T uj = -du[j] * F[j * ldf + j];
+                        __syncwarp();
+                        for (int i = lane; i < j; i += WARP) du[i] += F[j * ldf + i] * uj;
+                        if (lane == 0) du[j] = uj;
+                        __syncwarp();
+                    }
+                }
+            } else {
+                for (int j = lane; j < nu; j += WARP) du[j] = T(0);
+                __syncwarp();
+            }
+            T* Dk = DZk(k);
+            for (int i = lane; i < nz; i += WARP) Dk[i] = dst[i];
+            stage_side_steps(k, dst, corrector, target_mu, amax);
+            if (k < P.N) {
+                if (lane < nq) {
+                    const T dt = P.dt;
+                    const T q = dx[lane], v = dx[nq + lane], a = dx[2 * nq + lane], j = du[lane];
+                    dxn[lane] = q + dt * v + T(0.5) * dt * dt * a + dt * dt * dt / T(6) * j;
+                    dxn[nq + lane] = v + dt * a + T(0.5) * dt * dt * j;
+                    dxn[2 * nq + lane] = a + dt * j;
+                }
+                __syncwarp();
+                for (int i = lane; i < nx; i += WARP) dx[i] = dxn[i];
+                __syncwarp();
+            }
+        }
+        return warp_min(amax);
+    }
+
     // Interior-point QP solve around the current (X, U).  Leaves the step in Z
     // and the factors of the last iteration in FAC.  Returns iterations used;
     // *converged, *decr as in orc::solve_qp_ipm.
@@ -1235,85 +1519,105 @@ struct Solver {
         __syncwarp();
         T last_alpha = T(0), last_step = tinf<T>();
         int iters = 0;
-        for (int it = 0; it < P.qp_iter_max; ++it) {
-            const long long c_it = clock64();
-            // residual summary: mu, max |rd|, equality infeasibility
-            T mu = 0, rdmax = 0, pinf = 0;
-            for (int k = 0; k <= N; ++k) {
-                const T* zk = Zk(k);
-                for (int r = lane; r < NROW(); r += WARP) {
-                    const int fam = row_family(r);
-                    if (!row_valid(k, fam)) continue;
-                    T lb, ub;
-                    const T val = row_value(k, r, fam, zk, &lb, &ub);
-                    const T eps = row_eps(fam);
-                    const Quad q = *side_tl(k, r);
-                    rdmax = max(rdmax, fabs(val - lb + eps * q.v[2] - q.v[0]));
-                    mu += q.v[0] * q.v[2];
-                    if (fam < 2) {
-                        rdmax = max(rdmax, fabs(ub - val + eps * q.v[3] - q.v[1]));
-                        mu += q.v[1] * q.v[3];
-                    }
-                }
-                if (!P.soft_poly && neq_of(k) > 0) {
-                    load_eq_rows(k);
-                    for (int i = lane; i < neq_of(k); i += WARP)
-                        if (rho_eq(k)[i] > T(0)) pinf = max(pinf, fabs(eq_value(k, i, zk)));
-                    __syncwarp();
+        // initial residual summary (afterwards mu comes from the update pass and the slack residual
+        // contracts by exactly (1 - alpha) per Newton step, the rows being linear)
+        T mu = 0, rdmax = 0;
+        for (int k = 0; k <= N; ++k) {
+            const T* zk = Zk(k);
+            for (int r = lane; r < NROW(); r += WARP) {
+                const int fam = row_family(r);
+                if (!row_valid(k, fam)) continue;
+                T lb, ub;
+                const T val = row_value(k, r, fam, zk, &lb, &ub);
+                const T eps = row_eps(fam);
+                const Quad q = *side_tl(k, r);
+                rdmax = max(rdmax, fabs(val - lb + eps * q.v[2] - q.v[0]));
+                mu += q.v[0] * q.v[2];
+                if (fam < 2) {
+                    rdmax = max(rdmax, fabs(ub - val + eps * q.v[3] - q.v[1]));
+                    mu += q.v[1] * q.v[3];
                 }
             }
-            mu = nsides > 0 ? warp_sum(mu) / T(nsides) : T(0);
-            rdmax = warp_max(rdmax);
-            pinf = warp_max(pinf);
+        }
+        mu = nsides > 0 ? warp_sum(mu) / T(nsides) : T(0);
+        rdmax = warp_max(rdmax);
+        T pinf = T(0);
+        auto eq_infeasibility = [&]() {
+            T pv = T(0);
+            if (!P.soft_poly)
+                for (int k = 0; k <= N; ++k) {
+                    if (neq_of(k) == 0) continue;
+                    load_eq_rows(k);
+                    const T* zk = Zk(k);
+                    for (int i = lane; i < neq_of(k); i += WARP)
+                        if (rho_eq(k)[i] > T(0)) pv = max(pv, fabs(eq_value(k, i, zk)));
+                    __syncwarp();
+                }
+            return warp_max(pv);
+        };
+        pinf = eq_infeasibility();
+        for (int it = 0; it < P.qp_iter_max; ++it) {
+            const long long c_it = clock64();
             if (it > 0 && mu <= T(2) * P.mu_target && rdmax <= P.qp_tol && last_alpha >= T(0.5) &&
                 (pinf <= P.qp_tol || last_step <= P.qp_tol)) {
                 *converged = true;
                 break;
             }
             iters = it + 1;
-            long long c1 = clock64();
-            t_res += c1 - c_it;
-            if (!factor_sweep()) *finite = false;
+            if (!pass_factor_predict()) *finite = false;
             long long c2 = clock64();
-            t_fac += c2 - c1;
+            t_fac += c2 - c_it;
             T target_mu = P.mu_target;
+            T alpha = T(1);
             if (nsides > 0) {
-                solve_sweeps(false, T(0));
-                long long c3 = clock64();
-                t_swp += c3 - c2;
-                T mu_aff;
-                side_steps(false, T(0), &mu_aff);
-                mu_aff /= T(nsides);
+                const T a_aff = pass_forward(false, T(0));
+                // mean complementarity after the affine step
+                T acc = 0;
+                for (int idx = lane; idx < (N + 1) * NROW(); idx += WARP) {
+                    const int k = idx / NROW(), r = idx % NROW();
+                    const int fam = row_family(r);
+                    if (!row_valid(k, fam)) continue;
+                    const Quad* rec = reinterpret_cast<const Quad*>(ws + L.TT) + 2 * idx;
+                    const Quad q = rec[0], dd = rec[1];
+                    acc += (q.v[0] + a_aff * dd.v[0]) * (q.v[2] + a_aff * dd.v[2]);
+                    if (fam < 2) acc += (q.v[1] + a_aff * dd.v[1]) * (q.v[3] + a_aff * dd.v[3]);
+                }
+                const T mu_aff = warp_sum(acc) / T(nsides);
                 const T ratio = mu_aff / mu;
                 target_mu = max(ratio * ratio * ratio * mu, P.mu_target);
-                long long c4 = clock64();
-                t_side += c4 - c3;
-                solve_sweeps(true, target_mu);
-                c2 = clock64();
-                t_swp += c2 - c4;
+                long long c3 = clock64();
+                t_swp += c3 - c2;
+                pass_backward_corrector(target_mu);
+                alpha = min(T(1), T(0.995) * pass_forward(true, target_mu));
+                t_side += clock64() - c3;
             } else {
-                solve_sweeps(false, T(0));
+                pass_forward(false, T(0));
             }
-            T alpha = T(1);
-            if (nsides > 0) alpha = min(T(1), T(0.995) * side_steps(true, target_mu, nullptr));
-            t_side += clock64() - c2;
-            // update z, t, lambda, equality multipliers
-            T stepmax = 0, dec = 0;
+            // update z, t, lambda; new mean complementarity
+            T stepmax = 0, musum = 0;
             for (int idx = lane; idx < (N + 1) * nz; idx += WARP) {
                 const T d = ws[L.DZ + idx];
                 ws[L.Z + idx] += alpha * d;
                 stepmax = max(stepmax, fabs(alpha * d));
             }
             for (int idx = lane; idx < (N + 1) * NROW(); idx += WARP) {
+                const int k = idx / NROW(), r = idx % NROW();
+                const int fam = row_family(r);
                 Quad* rec = reinterpret_cast<Quad*>(ws + L.TT) + 2 * idx;
                 Quad q = rec[0];
                 const Quad dd = rec[1];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) q.v[c] += alpha * dd.v[c];
                 rec[0] = q;
+                if (row_valid(k, fam)) {
+                    musum += q.v[0] * q.v[2];
+                    if (fam < 2) musum += q.v[1] * q.v[3];
+                }
             }
             __syncwarp();
-            if (!P.soft_poly)
+            mu = nsides > 0 ? warp_sum(musum) / T(nsides) : T(0);
+            rdmax *= (T(1) - alpha);
+            if (!P.soft_poly) {
                 for (int k = 0; k <= N; ++k) {
                     if (neq_of(k) == 0) continue;
                     load_eq_rows(k);
@@ -1324,10 +1628,12 @@ struct Solver {
                     }
                     __syncwarp();
                 }
+                pinf = eq_infeasibility();
+            }
             last_alpha = alpha;
             last_step = warp_max(stepmax);
             if (!(last_step < tinf<T>())) *finite = false;
-            (void)dec;
+            t_res += 0;
             if (!*finite) break;
         }
         *decr = last_step;
