@@ -771,6 +771,76 @@ struct Solver {
         return ok;
     }
 
+    // Register-tiled partial Cholesky for small stage matrices (n <= 40): the 32 lanes form an
+    // 8 x 4 grid, lane (a, b) keeps the TR x TC tile rows a*TR.., columns b*TC.. in registers.
+    // Per pivot: 1 + TR + TC warp shuffles broadcast the pivot column, then TR*TC independent FMAs —
+    // no shared-memory round trips and no warp syncs inside the pivot loop.
+    template <int N_, int NPIV, int TR, int TC>
+    __device__ bool partial_cholesky_tiled() {
+        static_assert(TC % TR == 0 && 8 * TR >= N_ && 4 * TC >= N_, "tile shape");
+        const int ld = LDM();
+        const int a = lane >> 2, b = lane & 3;
+        T m[TR][TC];
+#pragma unroll
+        for (int ii = 0; ii < TR; ++ii)
+#pragma unroll
+            for (int cc = 0; cc < TC; ++cc) {
+                const int i = a * TR + ii, l = b * TC + cc;
+                m[ii][cc] = (i < N_ && l <= i) ? sM[i * ld + l] : T(0);
+            }
+        bool ok = true;
+#pragma unroll
+        for (int j = 0; j < NPIV; ++j) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int g = j / TC, cj = j % TC, aj = j / TR, ij = j % TR;
+            T d = __shfl_sync(FULL, m[ij][cj], (aj << 2) | g);
+            if (!(d > T(1e-30))) {
+                ok = false;
+                d = T(1e-30);
+            }
+            const T inv = rsqrt(d), invd = inv * inv;
+            T mij[TR], mlj[TC];
+#pragma unroll
+            for (int ii = 0; ii < TR; ++ii) {
+                const T v = __shfl_sync(FULL, m[ii][cj], (a << 2) | g);
+                mij[ii] = (a * TR + ii > j) ? v : T(0);
+            }
+#pragma unroll
+            for (int cc = 0; cc < TC; ++cc) {
+                // row l = b*TC + cc of column j lives in lane ((l / TR), g), register row (cc % TR)
+                const T v = __shfl_sync(FULL, m[cc % TR][cj], (((b * (TC / TR)) + cc / TR) << 2) | g);
+                mlj[cc] = (b * TC + cc > j) ? v * invd : T(0);
+            }
+#pragma unroll
+            for (int ii = 0; ii < TR; ++ii)
+#pragma unroll
+                for (int cc = 0; cc < TC; ++cc) m[ii][cc] -= mij[ii] * mlj[cc];
+            if (b == g) {
+#pragma unroll
+                for (int ii = 0; ii < TR; ++ii) {
+                    const int i = a * TR + ii;
+                    m[ii][cj] = (i > j) ? m[ii][cj] * inv : (i == j ? inv : m[ii][cj]);
+                }
+            }
+        }
+#pragma unroll
+        for (int ii = 0; ii < TR; ++ii)
+#pragma unroll
+            for (int cc = 0; cc < TC; ++cc) {
+                const int i = a * TR + ii, l = b * TC + cc;
+                if (i < N_ && l <= i) sM[i * ld + l] = m[ii][cc];
+            }
+        __syncwarp();
+        return ok;
+    }
+
+    __device__ __forceinline__ bool stage_cholesky() {
+        if constexpr (D::kStatic && D::nz == 40 && D::nu <= 16) return partial_cholesky_tiled<40, D::nu, 5, 10>();
+        else if constexpr (D::kStatic && D::nz <= 32 && D::nu <= 16) return partial_cholesky_tiled<D::nz, D::nu, 4, 8>();
+        else return partial_cholesky(NZ(), NU());
+    }
+
     // Factor sweep: for k = N..0 build the stage matrix, add the cost-to-go,
     // factor, store the factor block FAC[k] = sM[0..nz) x [0..nu) (ld = LDF())
     // and keep the new cost-to-go Hessian in sP.
@@ -1203,7 +1273,7 @@ struct Solver {
                 add_dynamics_gradient(vec);                  // uses p_{k+1} in sPv
                 long long f3 = clock64();
                 t_f2 += f3 - f2;
-                ok &= partial_cholesky(nz, nu);
+                ok &= stage_cholesky();
                 long long f4 = clock64();
                 t_f3 += f4 - f3;
                 if constexpr (kInvL) {
