@@ -22,8 +22,8 @@ mpc.set_option("stop_after", 9)
 out = mpc.solve_device(x0, tg, bp)
 torch.cuda.synchronize()
 st = out["stats"].double().cpu().numpy()
-names = ["qp_iters", "sweep:gradient", "resid+ls", "fac:build", "fac:dynamics", "fac:cholesky", "sweeps(total)", "fac:store+P"]
-tot = st[:, 2:].sum(1)
+names = ["qp_iters", "A:gradient", "A:build", "A:dynamics", "A:cholesky", "A total (factor+predict bwd)", "B fwd predictor + mu_aff", "C+D corrector bwd+fwd"]
+tot = st[:, 5:].sum(1)
 print("profile-mode ms", mpc.last_solve_ms(), "mean iters", st[:, 0].mean(), "max iters", st[:, 0].max())
 for i in range(1, 8):
     print(f"  {names[i]:14s} mean {st[:, i].mean() / 1e6:8.3f} Mcyc  ({100 * st[:, i].mean() / tot.mean():5.1f} %)  per-iter {st[:, i].mean() / st[:, 0].mean() / 1e3:8.1f} kcyc")

@@ -113,7 +113,7 @@ struct Solver {
     __device__ __forceinline__ int FSTRIDE() const { return (NZ() * LDF() + 3) & ~3; }  // 16-byte aligned factor blocks
     // small input blocks: store L^{-1} instead of L, turning the 4 triangular substitutions per
     // interior-point iteration and stage (serial pivot chains) into matrix-vector products
-    static constexpr bool kInvL = D::kStatic && D::nu <= 16;
+    static constexpr bool kInvL = false && D::kStatic && D::nu <= 16;
     // batch data of this instance
     const T* x0;
     const T* target;
@@ -1868,17 +1868,14 @@ struct Solver {
                 s[5] = base.max_eq;
                 s[6] = base.min_margin;
                 s[7] = T(sqp_done);
-                if (A.stop_after == 9) {  // profile mode: phase cycle counters instead of the last four entries
-                    s[0] = T(qp_iters) + T(1e-3) * T(0);
+                if (A.stop_after == 9) {  // profile mode: phase cycle counters replace stats[1..7]
                     s[1] = T(t_g);
-                    s[2] = T(t_res + t_ls);
-                    s[3] = T(t_f1) ;
-                    T* s2 = s;  // second half encoded below
-                    (void)s2;
-                    s[4] = T(t_f2);
-                    s[5] = T(t_f3);
+                    s[2] = T(t_f1);
+                    s[3] = T(t_f2);
+                    s[4] = T(t_f3);
+                    s[5] = T(t_fac);
                     s[6] = T(t_swp);
-                    s[7] = T(t_f4);
+                    s[7] = T(t_side);
                 }
             }
         }
