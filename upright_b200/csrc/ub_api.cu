@@ -11,7 +11,7 @@
 #include <string>
 #include <vector>
 
-#include "ub_solver.cuh"
+#include "ub_launch.cuh"
 
 namespace {
 
@@ -127,54 +127,7 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
 
 template <typename T>
 ub::Layout make_layout(const ub::DevProblem<T>& P) {
-    ub::Layout L;
-    std::memset(&L, 0, sizeof(L));
-    const int N = P.N, nx = P.nx, nu = P.nu, nz = P.nz, nq = P.nq;
-    int o = 0;
-    auto take = [&](int n) {
-        const int at = o;
-        o += (n + 3) / 4 * 4;
-        return at;
-    };
-    L.ldm = nz | 1;
-    L.ldf = nu | 1;
-    L.Z = take((N + 1) * nz);
-    L.DZ = take((N + 1) * nz);
-    L.GAP = take(N * nx);
-    L.LG = take(N * P.neq);
-    L.LCT = take(N * P.neq * nz);
-    L.LR = take((N + 1) * 3);
-    L.LJP = take((N + 1) * 3 * nq);
-    L.LHO = take((N + 1) * P.nobs);
-    L.LJO = take((N + 1) * P.nobs * nq);
-    L.DF = take(P.neq * P.nfc);
-    L.RHOE = take(N * P.neq);
-    L.YE = take(N * P.neq);
-    L.RHOT = take(P.nterm);
-    L.YT = take(P.nterm);
-    L.TT = take((N + 1) * P.nrow * 8);  // interleaved side records {t, lam, dt, dlam} x {lo, hi}
-    L.LAM = take((N + 1) * nz);  // GP: predictor stage gradients kept for the corrector
-    L.DTT = L.DLAM = L.TT;
-    L.FAC = take(N * ((nz * L.ldf + 3) & ~3));
-    L.WF = take(N * nu);
-    L.XN = take((N + 1) * nx);
-    L.UN = take(N * nu);
-    L.total = o;
-    int s = 0;
-    auto stake = [&](int n) {
-        const int at = s;
-        s += (n + 3) / 4 * 4;
-        return at;
-    };
-    L.sM = stake(std::max(nz * L.ldm, (nz * L.ldf + 3) & ~3));
-    L.sP = stake(nx * nx);
-    L.sPv = stake(nx);
-    const int sa_rows = P.neq > 3 ? P.neq : 3;
-    L.sSA = stake(sa_rows * nz);
-    L.sV = stake(5 * nz + 64);  // [4 nz, ...) doubles as per-row scratch (>= max(neq, nobs, 3) entries)
-    L.sBar = stake(32 / int(sizeof(T)));  // three 8-byte mbarriers (+pad)
-    L.s_total = s;
-    return L;
+    return ub::compute_layout(ub::LayoutDims{P.N, P.nq, P.nx, P.nu, P.neq, P.nfc, P.nterm, P.nrow, P.nobs, int(sizeof(T))});
 }
 
 }  // namespace
@@ -208,12 +161,24 @@ struct Pick<float> {
     static const ub::DevProblem<float>* dev(const ub_problem* p) { return p->df; }
     static const ub::DevProblem<float>& host(const ub_problem* p) { return p->hf; }
     static const ub::Layout& layout(const ub_problem* p) { return p->Lf; }
+    static ub::LaunchFn<float> generic() { return ub::launch_generic_f32; }
+    static ub::LaunchFn<float> thing_1obj() { return ub::launch_thing_1obj_f32; }
+    static ub::LaunchFn<float> thing_obs12() { return ub::launch_thing_obs12_f32; }
+    static ub::LaunchFn<float> ur10_1obj() { return ub::launch_ur10_1obj_f32; }
+    static ub::LaunchFn<float> thing_arch() { return ub::launch_thing_arch_f32; }
+    static ub::LaunchFn<float> thing_robust8() { return ub::launch_thing_robust8_f32; }
 };
 template <>
 struct Pick<double> {
     static const ub::DevProblem<double>* dev(const ub_problem* p) { return p->dd; }
     static const ub::DevProblem<double>& host(const ub_problem* p) { return p->hd; }
     static const ub::Layout& layout(const ub_problem* p) { return p->Ld; }
+    static ub::LaunchFn<double> generic() { return ub::launch_generic_f64; }
+    static ub::LaunchFn<double> thing_1obj() { return ub::launch_thing_1obj_f64; }
+    static ub::LaunchFn<double> thing_obs12() { return ub::launch_thing_obs12_f64; }
+    static ub::LaunchFn<double> ur10_1obj() { return ub::launch_ur10_1obj_f64; }
+    static ub::LaunchFn<double> thing_arch() { return ub::launch_thing_arch_f64; }
+    static ub::LaunchFn<double> thing_robust8() { return ub::launch_thing_robust8_f64; }
 };
 
 template <typename T>
@@ -231,22 +196,20 @@ int launch_solve(ub_problem* p, const ub::BatchArgs<T>& A, cudaStream_t stream) 
     if (smem > size_t(p->max_smem_optin)) return fail(UB_E_INVALID, "problem too large for shared memory");
     const int grid = (A.B + wpc - 1) / wpc;
     const ub::DevProblem<T>& H = Pick<T>::host(p);
-    auto go = [&](auto kernel) -> int {
-        UB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        kernel<<<grid, wpc * 32, smem, stream>>>(Pick<T>::dev(p), L, A, wpc);
-        ++g_launches;
-        UB_CUDA(cudaGetLastError());
-        return UB_OK;
-    };
     // kernels specialised on the BASELINE dimensions (nq, nf, nc, nb); anything else runs the generic one
     const bool generic_only = std::getenv("UB_FORCE_GENERIC") != nullptr;
-    if (!generic_only && H.balancing) {
-        if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1) return go(ub::solve_batch_kernel<T, ub::StaticDims<9, 1, 4, 1>>);
-        if (H.nq == 6 && H.nf == 1 && H.nc == 4 && H.nb == 1) return go(ub::solve_batch_kernel<T, ub::StaticDims<6, 1, 4, 1>>);
-        if (H.nq == 9 && H.nf == 3 && H.nc == 16 && H.nb == 3) return go(ub::solve_batch_kernel<T, ub::StaticDims<9, 3, 16, 3>>);
-        if (H.nq == 9 && H.nf == 1 && H.nc == 32 && H.nb == 8) return go(ub::solve_batch_kernel<T, ub::StaticDims<9, 1, 32, 8>>);
+    ub::LaunchFn<T> fn = Pick<T>::generic();
+    if (!generic_only && H.balancing && H.N == 20) {
+        const bool no_obs = H.nobs == 0;
+        if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::thing_1obj();
+        if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12) fn = Pick<T>::thing_obs12();
+        if (H.nq == 6 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::ur10_1obj();
+        if (H.nq == 9 && H.nf == 3 && H.nc == 16 && H.nb == 3 && no_obs) fn = Pick<T>::thing_arch();
+        if (H.nq == 9 && H.nf == 1 && H.nc == 32 && H.nb == 8 && no_obs) fn = Pick<T>::thing_robust8();
     }
-    return go(ub::solve_batch_kernel<T, ub::RuntimeDims>);
+    UB_CUDA(fn(Pick<T>::dev(p), L, A, wpc, grid, smem, stream));
+    ++g_launches;
+    return UB_OK;
 }
 
 template <typename T>

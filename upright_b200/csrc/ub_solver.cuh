@@ -23,13 +23,59 @@
 
 namespace ub {
 
-// Per-problem workspace layout in units of T (filled on the host).
+// Per-problem workspace layout in units of T.  One constexpr function serves the host (make_layout in
+// ub_api.cu) and the kernels specialised on compile-time dimensions, where every offset becomes an
+// immediate of the load/store instruction.
 struct Layout {
     int Z, DZ, GAP, LG, LCT, LR, LJP, LHO, LJO, DF, RHOE, YE, RHOT, YT, TT, LAM, DTT, DLAM, sBar, FAC, WF, XN, UN;
     int total;
     // shared memory (units of T, per warp)
     int sM, sP, sPv, sSA, sV, s_total, ldm, ldf;
 };
+struct LayoutDims {
+    int N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, tsize;
+};
+__host__ __device__ constexpr int ub_round4(int n) { return (n + 3) / 4 * 4; }
+__host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
+    Layout L{};
+    const int N = d.N, nx = d.nx, nu = d.nu, nz = d.nu + d.nx, nq = d.nq;
+    int o = 0;
+    L.ldm = nz | 1;
+    L.ldf = nu | 1;
+    L.Z = o;    o += ub_round4((N + 1) * nz);
+    L.DZ = o;   o += ub_round4((N + 1) * nz);
+    L.GAP = o;  o += ub_round4(N * nx);
+    L.LG = o;   o += ub_round4(N * d.neq);
+    L.LCT = o;  o += ub_round4(N * d.neq * nz);
+    L.LR = o;   o += ub_round4((N + 1) * 3);
+    L.LJP = o;  o += ub_round4((N + 1) * 3 * nq);
+    L.LHO = o;  o += ub_round4((N + 1) * d.nobs);
+    L.LJO = o;  o += ub_round4((N + 1) * d.nobs * nq);
+    L.DF = o;   o += ub_round4(d.neq * d.nfc);
+    L.RHOE = o; o += ub_round4(N * d.neq);
+    L.YE = o;   o += ub_round4(N * d.neq);
+    L.RHOT = o; o += ub_round4(d.nterm);
+    L.YT = o;   o += ub_round4(d.nterm);
+    L.TT = o;   o += ub_round4((N + 1) * d.nrow * 8);  // interleaved side records {t, lam, dt, dlam} x {lo, hi}
+    L.LAM = o;  o += ub_round4((N + 1) * nz);          // GP: predictor stage gradients kept for the corrector
+    L.DTT = L.TT;
+    L.DLAM = L.TT;
+    const int fstride = (nz * L.ldf + 3) & ~3;
+    L.FAC = o;  o += ub_round4(N * fstride);
+    L.WF = o;   o += ub_round4(N * nu);
+    L.XN = o;   o += ub_round4((N + 1) * nx);
+    L.UN = o;   o += ub_round4(N * nu);
+    L.total = o;
+    int s = 0;
+    L.sM = s;   s += ub_round4(nz * L.ldm > fstride ? nz * L.ldm : fstride);
+    L.sP = s;   s += ub_round4(nx * nx);
+    L.sPv = s;  s += ub_round4(nx);
+    L.sSA = s;  s += ub_round4((d.neq > 3 ? d.neq : 3) * nz);
+    L.sV = s;   s += ub_round4(5 * nz + 64);  // [4 nz, ...) doubles as per-row scratch (>= max(neq, nobs, 3) entries)
+    L.sBar = s; s += ub_round4(32 / d.tsize);  // three 8-byte mbarriers (+pad)
+    L.s_total = s;
+    return L;
+}
 
 template <typename T>
 struct BatchArgs {
@@ -83,17 +129,25 @@ struct Perf {
 };
 
 // Compile-time problem dimensions (specialised kernels) or run-time ones (generic kernel).
-template <int NQ_, int NF_, int NC_, int NB_>
+template <int NQ_, int NF_, int NC_, int NB_, int NOBS_ = 0, int N_ = 20>
 struct StaticDims {
     static constexpr bool kStatic = true;
-    static constexpr int nq = NQ_, nf = NF_, nc = NC_, nb = NB_;
+    static constexpr int nq = NQ_, nf = NF_, nc = NC_, nb = NB_, nobs = NOBS_, N = N_;
     static constexpr int nx = 3 * NQ_, nfc = NF_ * NC_, nu = NQ_ + NF_ * NC_, nz = nu + nx;
     static constexpr int neq = 6 * NB_, nfric = (NF_ == 3) ? 5 * NC_ : 0;
     static constexpr int nbox_u = nfc > 0 ? nu : nq;
+    static constexpr int nterm = 3 + 2 * NQ_, nrow = nbox_u + nx + nfric + NOBS_;
+    template <typename T>
+    __host__ __device__ static constexpr Layout layout() {
+        return compute_layout(LayoutDims{N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, int(sizeof(T))});
+    }
 };
 struct RuntimeDims {
     static constexpr bool kStatic = false;
     static constexpr int nq = 0, nf = 0, nc = 0, nb = 0, nx = 0, nfc = 0, nu = 0, nz = 0, neq = 0, nfric = 0, nbox_u = 0;
+    static constexpr int nobs = 0, N = 0, nterm = 0, nrow = 0;
+    template <typename T>
+    __host__ __device__ static constexpr Layout layout() { return Layout{}; }
 };
 
 template <typename T, typename D>
@@ -104,11 +158,17 @@ struct Solver {
 #define UB_DIM(FN, name) \
     __device__ __forceinline__ int FN() const { if constexpr (D::kStatic) return D::name; else return P.name; }
     UB_DIM(NQ, nq) UB_DIM(NX, nx) UB_DIM(NU, nu) UB_DIM(NZ, nz) UB_DIM(NFC, nfc) UB_DIM(NEQ, neq) UB_DIM(NFRIC, nfric)
-    UB_DIM(NBOXU, nbox_u) UB_DIM(NB, nb) UB_DIM(NC, nc) UB_DIM(NF, nf)
+    UB_DIM(NBOXU, nbox_u) UB_DIM(NB, nb) UB_DIM(NC, nc) UB_DIM(NF, nf) UB_DIM(NN, N) UB_DIM(NOBS, nobs)
 #undef UB_DIM
+    // workspace / shared-memory offsets: immediates for the specialised kernels
+#define UB_OFF(name) \
+    __device__ __forceinline__ int o##name() const { if constexpr (D::kStatic) { constexpr Layout l = D::template layout<T>(); return l.name; } else return L.name; }
+    UB_OFF(Z) UB_OFF(DZ) UB_OFF(GAP) UB_OFF(LG) UB_OFF(LCT) UB_OFF(LR) UB_OFF(LJP) UB_OFF(LHO) UB_OFF(LJO) UB_OFF(DF)
+    UB_OFF(RHOE) UB_OFF(YE) UB_OFF(RHOT) UB_OFF(YT) UB_OFF(TT) UB_OFF(LAM) UB_OFF(FAC) UB_OFF(WF) UB_OFF(XN) UB_OFF(UN)
+#undef UB_OFF
     __device__ __forceinline__ int LDM() const { return NZ() | 1; }
     __device__ __forceinline__ int LDF() const { return NU() | 1; }
-    __device__ __forceinline__ int NROW() const { return NBOXU() + NX() + NFRIC() + P.nobs; }
+    __device__ __forceinline__ int NROW() const { return NBOXU() + NX() + NFRIC() + NOBS(); }
     __device__ __forceinline__ int NTERM() const { return 3 + 2 * NQ(); }
     __device__ __forceinline__ int FSTRIDE() const { return (NZ() * LDF() + 3) & ~3; }  // 16-byte aligned factor blocks
     // small input blocks: store L^{-1} instead of L, turning the 4 triangular substitutions per
@@ -148,10 +208,10 @@ struct Solver {
     }
     __device__ __forceinline__ bool row_valid(int k, int fam) const {
         switch (fam) {
-            case 0: return k < P.N;
+            case 0: return k < NN();
             case 1: return k >= 1;
-            case 2: return k < P.N;
-            default: return k >= 1 && k < P.N;
+            case 2: return k < NN();
+            default: return k >= 1 && k < NN();
         }
     }
     __device__ __forceinline__ bool row_soft(int fam) const {
@@ -192,8 +252,8 @@ struct Solver {
             return a.x * (f[0] + df[0]) + a.y * (f[1] + df[1]) + a.z * (f[2] + df[2]);
         }
         const int i = r - NBOXU() - NX() - NFRIC();
-        const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
-        T v = ws[L.LHO + k * P.nobs + i];
+        const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
+        T v = ws[oLHO() + k * NOBS() + i];
         for (int j = 0; j < nq; ++j) v += J[j] * zk[nu + j];
         return v;
     }
@@ -209,7 +269,7 @@ struct Solver {
             return a.x * df[0] + a.y * df[1] + a.z * df[2];
         }
         const int i = r - NBOXU() - NX() - NFRIC();
-        const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
+        const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
         T v = 0;
         for (int j = 0; j < nq; ++j) v += J[j] * d[nu + j];
         return v;
@@ -230,18 +290,18 @@ struct Solver {
             atomicAdd(vec + nq + 3 * c + 2, w * a.z);
         } else {
             const int i = r - NBOXU() - NX() - NFRIC();
-            const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
+            const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
             for (int j = 0; j < nq; ++j) atomicAdd(vec + nu + j, w * J[j]);
         }
     }
-    __device__ __forceinline__ int nz_of(int k) const { return k < P.N ? NZ() : NX(); }
+    __device__ __forceinline__ int nz_of(int k) const { return k < NN() ? NZ() : NX(); }
     // Slack/multiplier record of one inequality row: {t_lo, t_hi, lam_lo, lam_hi} and the step
     // {dt_lo, dt_hi, dlam_lo, dlam_hi}, 8 consecutive values (two 16-byte quads) per row so that a warp
     // reads the rows of a stage with fully coalesced vector loads.
     struct alignas(16) Quad {
         T v[4];
     };
-    __device__ __forceinline__ Quad* side_tl(int k, int r) const { return reinterpret_cast<Quad*>(ws + L.TT) + (k * NROW() + r) * 2; }
+    __device__ __forceinline__ Quad* side_tl(int k, int r) const { return reinterpret_cast<Quad*>(ws + oTT()) + (k * NROW() + r) * 2; }
     __device__ __forceinline__ Quad* side_dd(int k, int r) const { return side_tl(k, r) + 1; }
     // Newton data of one side: returns the barrier weight and the coefficient that multiplies sgn*a in the
     // stage gradient;  d = signed distance to the bound at the current iterate
@@ -252,17 +312,17 @@ struct Solver {
     }
     // stage vectors are stored with stride nz as [du (nu); dx (nx)]; the terminal
     // stage uses the same slots (its du part is unused and kept at zero)
-    __device__ __forceinline__ T* Zk(int k) const { return ws + L.Z + k * NZ(); }
-    __device__ __forceinline__ T* DZk(int k) const { return ws + L.DZ + k * NZ(); }
+    __device__ __forceinline__ T* Zk(int k) const { return ws + oZ() + k * NZ(); }
+    __device__ __forceinline__ T* DZk(int k) const { return ws + oDZ() + k * NZ(); }
 
     // number of equality rows of stage k and their data
-    __device__ __forceinline__ int neq_of(int k) const { return k < P.N ? NEQ() : NTERM(); }
+    __device__ __forceinline__ int neq_of(int k) const { return k < NN() ? NEQ() : NTERM(); }
 
     // -------------------------------------------------------- linearisation
     // Df: d g / d f, constant in x (compute_object_wrenches, contact_constraints.h:106-157)
     __device__ void build_Df() {
         const T scale = rsqrt(T(6 * NB()));
-        T* Df = ws + L.DF;
+        T* Df = ws + oDF();
         for (int idx = lane; idx < NEQ() * NFC(); idx += WARP) Df[idx] = T(0);
         __syncwarp();
         for (int j = lane; j < NFC(); j += WARP) {
@@ -301,21 +361,21 @@ struct Solver {
     // Writes LG [k][neq] (g value incl. Df f), LCT [k][neq][nz] (rows [0 | Df | C] over the stage vector),
     // LR [k][3], LJP [k][3][nq], LHO [k][nobs], LJO [k][nobs][nq], GAP [k][nx].
     __device__ void linearize() {
-        const int nq = NQ(), nx = NX(), nu = NU(), N = P.N;
+        const int nq = NQ(), nx = NX(), nu = NU(), N = NN();
         const T scale = rsqrt(T(6 * max(NB(), 1)));
         T sph[3 * UB_MAX_SPHERES], dsph[3 * UB_MAX_SPHERES];
         for (int k = 0; k <= N; ++k) {
             const T* x = X + k * nx;
             Kin<T> Kn;
             KinTan<T> Dt;
-            forward_kinematics<T, true>(P, x, lane, Kn, Dt, P.nobs > 0 ? sph : nullptr, dsph);
+            forward_kinematics<T, true>(P, x, lane, Kn, Dt, NOBS() > 0 ? sph : nullptr, dsph);
             if (lane == 0) {
-                ws[L.LR + 3 * k] = Kn.r.x;
-                ws[L.LR + 3 * k + 1] = Kn.r.y;
-                ws[L.LR + 3 * k + 2] = Kn.r.z;
+                ws[oLR() + 3 * k] = Kn.r.x;
+                ws[oLR() + 3 * k + 1] = Kn.r.y;
+                ws[oLR() + 3 * k + 2] = Kn.r.z;
             }
             if (lane < nq) {
-                T* Jp = ws + L.LJP + k * 3 * nq;
+                T* Jp = ws + oLJP() + k * 3 * nq;
                 Jp[lane] = Dt.r.x;
                 Jp[nq + lane] = Dt.r.y;
                 Jp[2 * nq + lane] = Dt.r.z;
@@ -327,35 +387,35 @@ struct Solver {
                     object_dynamics_state_part<T, true>(P, Bd, Kn, Dt, scale, g6, dg6);
                     if (lane < nx) {
                         // row-major over the stage vector [du; dx]: lanes write consecutive addresses
-                        T* R = ws + L.LCT + (k * NEQ() + 6 * b) * NZ() + nu + lane;
+                        T* R = ws + oLCT() + (k * NEQ() + 6 * b) * NZ() + nu + lane;
 #pragma unroll
                         for (int i = 0; i < 6; ++i) R[i * NZ()] = dg6[i];
                     }
                     for (int idx = lane; idx < 6 * nu; idx += WARP) {
                         const int i = idx / nu, j = idx % nu;
-                        ws[L.LCT + (k * NEQ() + 6 * b + i) * NZ() + j] = (j >= nq) ? ws[L.DF + (6 * b + i) * NFC() + (j - nq)] : T(0);
+                        ws[oLCT() + (k * NEQ() + 6 * b + i) * NZ() + j] = (j >= nq) ? ws[oDF() + (6 * b + i) * NFC() + (j - nq)] : T(0);
                     }
                     if (lane < 6) {
                         // g = state part + Df f
                         T gv = g6[0];
 #pragma unroll
                         for (int i = 1; i < 6; ++i) gv = (lane == i) ? g6[i] : gv;
-                        const T* Dfr = ws + L.DF + (6 * b + lane) * NFC();
+                        const T* Dfr = ws + oDF() + (6 * b + lane) * NFC();
                         const T* f = U + k * nu + nq;
                         for (int j = 0; j < NFC(); ++j) gv += Dfr[j] * f[j];
-                        ws[L.LG + k * NEQ() + 6 * b + lane] = gv;
+                        ws[oLG() + k * NEQ() + 6 * b + lane] = gv;
                     }
                 }
             }
-            if (P.nobs > 0) {
-                for (int i = 0; i < P.nobs; ++i) {
+            if (NOBS() > 0) {
+                for (int i = 0; i < NOBS(); ++i) {
                     const int a = P.pa[i], bb = P.pb[i];
                     const V3<T> d(sph[3 * a] - sph[3 * bb], sph[3 * a + 1] - sph[3 * bb + 1], sph[3 * a + 2] - sph[3 * bb + 2]);
                     const T dist = sqrt(dot(d, d));
                     const V3<T> dd(dsph[3 * a] - dsph[3 * bb], dsph[3 * a + 1] - dsph[3 * bb + 1],
                                    dsph[3 * a + 2] - dsph[3 * bb + 2]);
-                    if (lane == 0) ws[L.LHO + k * P.nobs + i] = dist - (P.srad[a] + P.srad[bb] + P.dmin);
-                    if (lane < nq) ws[L.LJO + (k * P.nobs + i) * nq + lane] = dot(d, dd) / dist;
+                    if (lane == 0) ws[oLHO() + k * NOBS() + i] = dist - (P.srad[a] + P.srad[bb] + P.dmin);
+                    if (lane < nq) ws[oLJO() + (k * NOBS() + i) * nq + lane] = dot(d, dd) / dist;
                 }
             }
             // dynamics gap b_k = A x_k + B u_k - x_{k+1}  (exact triple integrator, system_dynamics.h:15-26)
@@ -363,7 +423,7 @@ struct Solver {
                 const T dt = P.dt;
                 const T* xn = X + (k + 1) * nx;
                 const T q = x[lane], v = x[nq + lane], a = x[2 * nq + lane], j = U[k * nu + lane];
-                T* gap = ws + L.GAP + k * nx;
+                T* gap = ws + oGAP() + k * nx;
                 gap[lane] = q + dt * v + T(0.5) * dt * dt * a + dt * dt * dt / T(6) * j - xn[lane];
                 gap[nq + lane] = v + dt * a + T(0.5) * dt * dt * j - xn[nq + lane];
                 gap[2 * nq + lane] = a + dt * j - xn[2 * nq + lane];
@@ -375,7 +435,7 @@ struct Solver {
     // --------------------------------------------------- performance index
     // Lane k evaluates knot k (values only).  Mirrors orc::performance().
     __device__ Perf<T> performance(const T* Xt, const T* Ut) const {
-        const int nq = NQ(), nx = NX(), nu = NU(), N = P.N;
+        const int nq = NQ(), nx = NX(), nu = NU(), N = NN();
         const T dt = P.dt;
         const T scale = rsqrt(T(6 * max(NB(), 1)));
         T cost = 0, dyn = 0, eq = 0, ineq = 0, max_eq = 0, min_margin = tinf<T>();
@@ -384,7 +444,7 @@ struct Solver {
             const T* x = Xt + k * nx;
             Kin<T> Kn;
             KinTan<T> Dn;
-            forward_kinematics<T, false>(P, x, -1, Kn, Dn, P.nobs > 0 ? sph : nullptr, nullptr);
+            forward_kinematics<T, false>(P, x, -1, Kn, Dn, NOBS() > 0 ? sph : nullptr, nullptr);
             const T* rd = target + 3 * k;
             if (k == N) {
                 for (int i = 0; i < 3; ++i) {
@@ -438,7 +498,7 @@ struct Solver {
                 T g6[6];
                 object_dynamics_state_part<T, false>(P, Bd, Kn, Dn, scale, g6, nullptr);
                 for (int i = 0; i < 6; ++i) {
-                    const T* Dfr = ws + L.DF + (6 * b + i) * NFC();
+                    const T* Dfr = ws + oDF() + (6 * b + i) * NFC();
                     T gv = g6[i];
                     for (int j = 0; j < NFC(); ++j) gv += Dfr[j] * u[nq + j];
                     eq += dt * gv * gv;
@@ -455,7 +515,7 @@ struct Solver {
                 min_margin = min(min_margin, h);
             }
             if (k >= 1)
-                for (int i = 0; i < P.nobs; ++i) {
+                for (int i = 0; i < NOBS(); ++i) {
                     const int a = P.pa[i], bb = P.pb[i];
                     const V3<T> d(sph[3 * a] - sph[3 * bb], sph[3 * a + 1] - sph[3 * bb + 1], sph[3 * a + 2] - sph[3 * bb + 2]);
                     const T h = sqrt(dot(d, d)) - (P.srad[a] + P.srad[bb] + P.dmin);
@@ -480,15 +540,15 @@ struct Solver {
     // multiplier y in sV-side arrays (global RHOE/YE, RHOT/YT).
     __device__ void load_eq_rows(int k) {
         const int nq = NQ(), nx = NX(), nu = NU(), nz = NZ();
-        if (k < P.N) {
-            const T* __restrict__ R = ws + L.LCT + k * NEQ() * nz;
+        if (k < NN()) {
+            const T* __restrict__ R = ws + oLCT() + k * NEQ() * nz;
             for (int idx = lane; idx < NEQ() * nz; idx += WARP) sSA[idx] = R[idx];
         } else {
             // terminal equality [r_d - r; v; a] = 0: three dense rows over q, the rest are unit rows
             for (int idx = lane; idx < 3 * nz; idx += WARP) {
                 const int i = idx / nz, j = idx % nz;
                 T v = T(0);
-                if (j >= nu && j < nu + nq) v = -ws[L.LJP + (k * 3 + i) * nq + (j - nu)];
+                if (j >= nu && j < nu + nq) v = -ws[oLJP() + (k * 3 + i) * nq + (j - nu)];
                 sSA[idx] = v;
             }
         }
@@ -496,25 +556,25 @@ struct Solver {
     }
     // constant (value at z = 0) of equality row i of stage k
     __device__ __forceinline__ T eq_const(int k, int i) const {
-        if (k < P.N) return ws[L.LG + k * NEQ() + i];
-        if (i < 3) return target[3 * k + i] - ws[L.LR + 3 * k + i];
+        if (k < NN()) return ws[oLG() + k * NEQ() + i];
+        if (i < 3) return target[3 * k + i] - ws[oLR() + 3 * k + i];
         return X[k * NX() + NQ() + (i - 3)];
     }
-    __device__ __forceinline__ T* rho_eq(int k) const { return k < P.N ? ws + L.RHOE + k * NEQ() : ws + L.RHOT; }
-    __device__ __forceinline__ T* y_eq(int k) const { return k < P.N ? ws + L.YE + k * NEQ() : ws + L.YT; }
+    __device__ __forceinline__ T* rho_eq(int k) const { return k < NN() ? ws + oRHOE() + k * NEQ() : ws + oRHOT(); }
+    __device__ __forceinline__ T* y_eq(int k) const { return k < NN() ? ws + oYE() + k * NEQ() : ws + oYT(); }
     // value a_i . z + c of equality row i (dense rows from SA; terminal unit rows direct)
     __device__ T eq_value(int k, int i, const T* zk) const {
-        if (k == P.N && i >= 3) return zk[NU() + NQ() + (i - 3)] + eq_const(k, i);
+        if (k == NN() && i >= 3) return zk[NU() + NQ() + (i - 3)] + eq_const(k, i);
         const T* a = sSA + i * NZ();
         T v = eq_const(k, i);
-        for (int j = (k < P.N ? NQ() : NU()); j < NZ(); ++j) v += a[j] * zk[j];
+        for (int j = (k < NN() ? NQ() : NU()); j < NZ(); ++j) v += a[j] * zk[j];
         return v;
     }
 
     // Set the proximal weights of the equality rows (soft: Z; hard: rho_hard on the
     // unit-normalised row) and reset the multipliers.
     __device__ void init_eq_weights() {
-        for (int k = 0; k <= P.N; ++k) {
+        for (int k = 0; k <= NN(); ++k) {
             const int ne = neq_of(k);
             if (ne == 0) continue;
             load_eq_rows(k);
@@ -522,7 +582,7 @@ struct Solver {
                 T rho = P.Z;
                 if (!P.soft_poly) {
                     T n2 = T(1);
-                    if (!(k == P.N && i >= 3)) {
+                    if (!(k == NN() && i >= 3)) {
                         n2 = T(0);
                         for (int j = 0; j < NZ(); ++j) n2 += sSA[i * NZ() + j] * sSA[i * NZ() + j];
                     }
@@ -612,7 +672,7 @@ struct Solver {
         const T dt = P.dt;
         for (int idx = lane; idx < nz * ld; idx += WARP) sM[idx] = T(0);
         __syncwarp();
-        if (k < P.N) {
+        if (k < NN()) {
             // cost (quadratic_joint_state_input_cost.h:9-33, end_effector_cost.h:48-84), scaled by dt
             for (int i = lane; i < nz; i += WARP) {
                 T d;
@@ -622,7 +682,7 @@ struct Solver {
                 sM[i * ld + i] = d;
             }
             __syncwarp();
-            const T* Jp = ws + L.LJP + k * 3 * nq;
+            const T* Jp = ws + oLJP() + k * 3 * nq;
             for (int idx = lane; idx < nq * nq; idx += WARP) {
                 const int a = idx / nq, b = idx % nq;
                 if (b > a) continue;
@@ -637,10 +697,10 @@ struct Solver {
         if (ne > 0) {
             if (!rows_loaded) load_eq_rows(k);
             const T* rho = rho_eq(k);
-            const int nd = (k < P.N) ? ne : 3;
-            const int j0 = (k < P.N) ? nq : nu;  // first column with non-zeros
+            const int nd = (k < NN()) ? ne : 3;
+            const int j0 = (k < NN()) ? nq : nu;  // first column with non-zeros
             const int span = nz - j0;
-            if (D::kStatic && D::neq <= 8 && k < P.N) {
+            if (D::kStatic && D::neq <= 8 && k < NN()) {
                 constexpr int NE = D::kStatic ? (D::neq > 0 ? D::neq : 1) : 1;
                 for (int c = j0 + lane; c < nz; c += WARP) {
                     T ac[NE];
@@ -662,7 +722,7 @@ struct Solver {
                     sM[i * ld + j] += acc;
                 }
             }
-            if (k == P.N)
+            if (k == NN())
                 for (int i = 3 + lane; i < ne; i += WARP) {
                     const int m = nu + nq + (i - 3);
                     sM[m * ld + m] += rho[i];
@@ -681,7 +741,7 @@ struct Solver {
             sM[m * ld + m] += w;
         }
         __syncwarp();
-        if (NFRIC() > 0 && k < P.N) {
+        if (NFRIC() > 0 && k < NN()) {
             const T eps = row_eps(2);
             // one lane per contact: its five pyramid rows give a symmetric 3x3 block
             for (int c = lane; c < NC(); c += WARP) {
@@ -707,10 +767,10 @@ struct Solver {
             }
             __syncwarp();
         }
-        if (P.nobs > 0 && k >= 1 && k < P.N) {
+        if (NOBS() > 0 && k >= 1 && k < NN()) {
             const T eps = row_eps(3);
             T* wrow = sV + 4 * nz;  // barrier weights of the obstacle rows
-            for (int i = lane; i < P.nobs; i += WARP) {
+            for (int i = lane; i < NOBS(); i += WARP) {
                 const Quad q = *side_tl(k, nbx + NFRIC() + i);
                 wrow[i] = q.v[2] / (q.v[0] + eps * q.v[2]);
             }
@@ -719,8 +779,8 @@ struct Solver {
                 const int a = idx / nq, b = idx % nq;
                 if (b > a) continue;
                 T acc = 0;
-                for (int i = 0; i < P.nobs; ++i) {
-                    const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
+                for (int i = 0; i < NOBS(); ++i) {
+                    const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
                     acc += wrow[i] * J[a] * J[b];
                 }
                 sM[(nu + a) * ld + nu + b] += acc;
@@ -771,128 +831,119 @@ struct Solver {
         return ok;
     }
 
-    // Register-tiled partial Cholesky for small stage matrices (n <= 40): the 32 lanes form an
-    // 8 x 4 grid, lane (a, b) keeps the TR x TC tile rows a*TR.., columns b*TC.. in registers.
-    // Per pivot: 1 + TR + TC warp shuffles broadcast the pivot column, then TR*TC independent FMAs —
-    // no shared-memory round trips and no warp syncs inside the pivot loop.
-    template <int N_, int NPIV, int TR, int TC>
-    __device__ bool partial_cholesky_tiled() {
-        static_assert(TC % TR == 0 && 8 * TR >= N_ && 4 * TC >= N_, "tile shape");
+    // Blocked factorisation of the stage matrix for small input blocks (nu <= 16, nz <= 64):
+    //   panel   [L; Y] = M[:, 0:nu] L^{-T}   right-looking, lane = matrix row (rows in registers, the pivot
+    //                                        column travels by warp shuffle), diagonal stored INVERTED;
+    //   Schur   P = Mxx - Y Y'               8 x 4 lane grid, TR x TC accumulator tile per lane, operands read
+    //                                        from the finished panel in shared memory, written straight to sP
+    //                                        as the full symmetric cost-to-go Hessian.
+    // Compact code (about 0.9 k instructions against 3.5 k for the fully unrolled register-tiled version it
+    // replaces) — the kernel is instruction-fetch sensitive (profiles/r1_v2_solve_batch_kernel.md).
+    template <int NU_, int NX_>
+    __device__ bool stage_factor_blocked() {
+        constexpr int NZ_ = NU_ + NX_;
+        constexpr int R = (NZ_ + WARP - 1) / WARP;
+        constexpr int TR = (NX_ + 7) / 8, TC = (NX_ + 3) / 4;
+        static_assert(NU_ <= 16 && R <= 2, "blocked factorisation is for small stage matrices");
         const int ld = LDM();
-        const int a = lane >> 2, b = lane & 3;
-        T m[TR][TC];
+        T row[R][NU_];
 #pragma unroll
-        for (int ii = 0; ii < TR; ++ii)
+        for (int r = 0; r < R; ++r) {
+            const int i = min(lane + WARP * r, NZ_ - 1);
 #pragma unroll
-            for (int cc = 0; cc < TC; ++cc) {
-                const int i = a * TR + ii, l = b * TC + cc;
-                m[ii][cc] = (i < N_ && l <= i) ? sM[i * ld + l] : T(0);
-            }
+            for (int c = 0; c < NU_; ++c) row[r][c] = sM[i * ld + c];
+        }
         bool ok = true;
 #pragma unroll
-        for (int j = 0; j < NPIV; ++j) {
-            constexpr int dummy = 0;
-            (void)dummy;
-            const int g = j / TC, cj = j % TC, aj = j / TR, ij = j % TR;
-            T d = __shfl_sync(FULL, m[ij][cj], (aj << 2) | g);
+        for (int j = 0; j < NU_; ++j) {
+            T d = __shfl_sync(FULL, row[0][j], j);
             if (!(d > T(1e-30))) {
                 ok = false;
                 d = T(1e-30);
             }
-            const T inv = rsqrt(d), invd = inv * inv;
-            T mij[TR], mlj[TC];
+            const T inv = rsqrt(d);
+            T lij[R];
 #pragma unroll
-            for (int ii = 0; ii < TR; ++ii) {
-                const T v = __shfl_sync(FULL, m[ii][cj], (a << 2) | g);
-                mij[ii] = (a * TR + ii > j) ? v : T(0);
+            for (int r = 0; r < R; ++r) {
+                const int i = lane + WARP * r;
+                lij[r] = (i > j) ? row[r][j] * inv : T(0);
             }
 #pragma unroll
-            for (int cc = 0; cc < TC; ++cc) {
-                // row l = b*TC + cc of column j lives in lane ((l / TR), g), register row (cc % TR)
-                const T v = __shfl_sync(FULL, m[cc % TR][cj], (((b * (TC / TR)) + cc / TR) << 2) | g);
-                mlj[cc] = (b * TC + cc > j) ? v * invd : T(0);
+            for (int c = j + 1; c < NU_; ++c) {
+                const T lcj = __shfl_sync(FULL, lij[0], c);
+#pragma unroll
+                for (int r = 0; r < R; ++r) row[r][c] -= lij[r] * lcj;
             }
 #pragma unroll
-            for (int ii = 0; ii < TR; ++ii)
-#pragma unroll
-                for (int cc = 0; cc < TC; ++cc) m[ii][cc] -= mij[ii] * mlj[cc];
-            if (b == g) {
-#pragma unroll
-                for (int ii = 0; ii < TR; ++ii) {
-                    const int i = a * TR + ii;
-                    m[ii][cj] = (i > j) ? m[ii][cj] * inv : (i == j ? inv : m[ii][cj]);
-                }
+            for (int r = 0; r < R; ++r) {
+                const int i = lane + WARP * r;
+                row[r][j] = (i > j) ? lij[r] : (i == j ? inv : row[r][j]);
             }
         }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = lane + WARP * r;
+            if (i < NZ_) {
+#pragma unroll
+                for (int c = 0; c < NU_; ++c) sM[i * ld + c] = row[r][c];
+            }
+        }
+        __syncwarp();
+        // Schur complement tile of lane (a, b): rows a*TR.., columns b*TC.. of the state block
+        const int a = lane >> 2, b = lane & 3;
+        int ri[TR], ci[TC];
+#pragma unroll
+        for (int ii = 0; ii < TR; ++ii) ri[ii] = min(a * TR + ii, NX_ - 1);
+#pragma unroll
+        for (int cc = 0; cc < TC; ++cc) ci[cc] = min(b * TC + cc, NX_ - 1);
+        T acc[TR][TC];
 #pragma unroll
         for (int ii = 0; ii < TR; ++ii)
 #pragma unroll
             for (int cc = 0; cc < TC; ++cc) {
-                const int i = a * TR + ii, l = b * TC + cc;
-                if (i < N_ && l <= i) sM[i * ld + l] = m[ii][cc];
+                const int hi = max(ri[ii], ci[cc]), lo = min(ri[ii], ci[cc]);
+                acc[ii][cc] = sM[(NU_ + hi) * ld + NU_ + lo];
             }
+#pragma unroll
+        for (int m = 0; m < NU_; ++m) {
+            T yr[TR], yc[TC];
+#pragma unroll
+            for (int ii = 0; ii < TR; ++ii) yr[ii] = sM[(NU_ + ri[ii]) * ld + m];
+#pragma unroll
+            for (int cc = 0; cc < TC; ++cc) yc[cc] = sM[(NU_ + ci[cc]) * ld + m];
+#pragma unroll
+            for (int ii = 0; ii < TR; ++ii)
+#pragma unroll
+                for (int cc = 0; cc < TC; ++cc) acc[ii][cc] -= yr[ii] * yc[cc];
+        }
+#pragma unroll
+        for (int ii = 0; ii < TR; ++ii)
+#pragma unroll
+            for (int cc = 0; cc < TC; ++cc)
+                if (a * TR + ii < NX_ && b * TC + cc < NX_) sP[(a * TR + ii) * NX_ + b * TC + cc] = acc[ii][cc];
         __syncwarp();
         return ok;
     }
+    static constexpr bool kBlocked = D::kStatic && D::nu <= 16 && D::nz <= 64;
 
+    // factor the stage matrix in sM; leaves [L; Y] in its first nu columns and the new cost-to-go Hessian in sP
     __device__ __forceinline__ bool stage_cholesky() {
-        if constexpr (D::kStatic && D::nz == 40 && D::nu <= 16) return partial_cholesky_tiled<40, D::nu, 5, 10>();
-        else if constexpr (D::kStatic && D::nz <= 32 && D::nu <= 16) return partial_cholesky_tiled<D::nz, D::nu, 4, 8>();
-        else return partial_cholesky(NZ(), NU());
-    }
-
-    // Factor sweep: for k = N..0 build the stage matrix, add the cost-to-go,
-    // factor, store the factor block FAC[k] = sM[0..nz) x [0..nu) (ld = LDF())
-    // and keep the new cost-to-go Hessian in sP.
-    __device__ bool factor_sweep() {
-        const int nu = NU(), nx = NX(), nz = NZ(), ld = LDM();
-        bool ok = true;
-        struct FenceAtExit {  // generic-proxy writes of FAC must be visible to the TMA reads of the sweeps
-            __device__ ~FenceAtExit() {
-                if (UB_USE_TMA) asm volatile("fence.proxy.async;" ::: "memory");
-            }
-        } fence_at_exit;
-        for (int k = P.N; k >= 0; --k) {
-            long long f0 = clock64();
-            build_stage_matrix(k);
-            long long f1 = clock64();
-            t_f1 += f1 - f0;
-            if (k < P.N) {
-                add_dynamics_hessian();
-                long long f2 = clock64();
-                t_f2 += f2 - f1;
-                ok &= partial_cholesky(nz, nu);
-                t_f3 += clock64() - f2;
-                f0 = clock64();
-                if constexpr (kInvL) {
-                    // lane c builds column c of L^{-1}; stored transposed in the (free) upper triangle
-                    if (lane < nu) {
-                        const int c = lane;
-                        for (int i = c + 1; i < nu; ++i) {
-                            T acc = sM[i * ld + c] * sM[c * ld + c];  // L_ic * x_c, x_c = 1/L_cc
-                            for (int m = c + 1; m < i; ++m) acc += sM[i * ld + m] * sM[c * ld + m];
-                            sM[c * ld + i] = -acc * sM[i * ld + i];
-                        }
-                    }
-                    __syncwarp();
-                }
-                T* F = ws + L.FAC + k * FSTRIDE();
-                for (int idx = lane; idx < nz * nu; idx += WARP) {
-                    const int i = idx / nu, j = idx % nu;
-                    T v = T(0);
-                    if (j <= i) v = (kInvL && i < nu && j < i) ? sM[j * ld + i] : sM[i * ld + j];
-                    F[i * LDF() + j] = v;
-                }
-            }
-            // cost-to-go: trailing block (x part)
-            for (int idx = lane; idx < nx * nx; idx += WARP) {
-                const int i = idx / nx, j = idx % nx;
-                sP[idx] = (j <= i) ? sM[(nu + i) * ld + nu + j] : sM[(nu + j) * ld + nu + i];  // full symmetric
-            }
-            __syncwarp();
-            t_f4 += clock64() - f0;
+        if constexpr (kBlocked) {
+            return stage_factor_blocked<D::nu, D::nx>();
+        } else {
+            const bool ok = partial_cholesky(NZ(), NU());
+            copy_cost_to_go();
+            return ok;
         }
-        return ok;
+    }
+    // cost-to-go Hessian = trailing block of sM, expanded to the full symmetric matrix
+    __device__ __forceinline__ void copy_cost_to_go() {
+        const int nu = NU(), nx = NX(), ld = LDM();
+        for (int idx = lane; idx < nx * nx; idx += WARP) {
+            const int i = idx / nx, j = idx % nx;
+            sP[idx] = (j <= i) ? sM[(nu + i) * ld + nu + j] : sM[(nu + j) * ld + nu + i];
+        }
+        __syncwarp();
     }
 
     // Stage gradient of the barrier/proximal Lagrangian at the current iterate:
@@ -905,16 +956,16 @@ struct Solver {
         const T* zk = Zk(k);
         const T cm = corrector ? T(1) : T(0);
         // cost part (zero at the terminal stage)
-        if (k < P.N) {
+        if (k < NN()) {
             const T* x = X + k * nx;
             const T* u = U + k * nu;
-            const T* Jp = ws + L.LJP + k * 3 * nq;
+            const T* Jp = ws + oLJP() + k * 3 * nq;
             // e = Jp dq + r - r_d, reduced over the warp
             T e3[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const T part = lane < nq ? Jp[c * nq + lane] * zk[nu + lane] : T(0);
-                e3[c] = warp_sum(part) + ws[L.LR + 3 * k + c] - target[3 * k + c];
+                e3[c] = warp_sum(part) + ws[oLR() + 3 * k + c] - target[3 * k + c];
             }
             for (int i = lane; i < nz; i += WARP) {
                 T g;
@@ -964,9 +1015,9 @@ struct Solver {
             load_eq_rows(k);
             const T* rho = rho_eq(k);
             const T* y = y_eq(k);
-            const int nd = (k < P.N) ? ne : 3;
+            const int nd = (k < NN()) ? ne : 3;
             T* mrow = sV + 4 * nz;  // per-row multiplier estimate m_i = rho e_i + y_i
-            if (D::kStatic && D::neq <= 8 && k < P.N) {
+            if (D::kStatic && D::neq <= 8 && k < NN()) {
                 // few dense rows: every row value as a warp-wide dot product
                 for (int i = 0; i < nd; ++i) {
                     T part = T(0);
@@ -990,7 +1041,7 @@ struct Solver {
             __syncwarp();
         }
         const int nbx = NBOXU() + nx;
-        if (NFRIC() > 0 && k < P.N) {
+        if (NFRIC() > 0 && k < NN()) {
             // one lane per contact: five pyramid rows -> three force entries
             const T eps = row_eps(2);
             for (int c = lane; c < NC(); c += WARP) {
@@ -1019,13 +1070,13 @@ struct Solver {
             }
             __syncwarp();
         }
-        if (P.nobs > 0 && k >= 1 && k < P.N) {
+        if (NOBS() > 0 && k >= 1 && k < NN()) {
             const T eps = row_eps(3);
             T* crow = sV + 4 * nz;
-            for (int i = lane; i < P.nobs; i += WARP) {
+            for (int i = lane; i < NOBS(); i += WARP) {
                 const int r = nbx + NFRIC() + i;
-                const T* J = ws + L.LJO + (k * P.nobs + i) * nq;
-                T val = ws[L.LHO + k * P.nobs + i];
+                const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
+                T val = ws[oLHO() + k * NOBS() + i];
                 for (int j = 0; j < nq; ++j) val += J[j] * zk[nu + j];
                 const Quad q = *side_tl(k, r);
                 T corr = T(0);
@@ -1038,7 +1089,7 @@ struct Solver {
             __syncwarp();
             if (lane < nq) {
                 T acc = 0;
-                for (int i = 0; i < P.nobs; ++i) acc += crow[i] * ws[L.LJO + (k * P.nobs + i) * nq + lane];
+                for (int i = 0; i < NOBS(); ++i) acc += crow[i] * ws[oLJO() + (k * NOBS() + i) * nq + lane];
                 vec[nu + lane] += acc;
             }
             __syncwarp();
@@ -1055,199 +1106,6 @@ struct Solver {
         for (int i = nv * V + lane; i < n; i += WARP) dst[i] = src[i];
     }
 
-    // Vector sweeps with the stored factors: backward (w_k, cost-to-go gradient)
-    // then forward (direction DZ).  `corrector`/`target_mu` select the right-hand side.
-    // Double-buffered staging of the factor blocks: when two blocks fit into the (idle) stage
-    // matrix buffer, stage k+-1 is fetched by TMA while stage k is processed.
-    // Measured on B200 (cfg2, B = 4096): TMA ring 42.1 ms vs plain vectorised copies 38.2 ms per batch — the
-    // factor-block fetch is not the latency that binds, and the proxy fence after every factor sweep costs
-    // more than the prefetch hides.  Kept behind UB_USE_TMA (default off) with the measurement in DESIGN.md.
-    static constexpr int kFacRing = 3;  // ring depth of the factor-block staging
-    __device__ __forceinline__ bool fac_double_buffered() const { return UB_USE_TMA && kFacRing * FSTRIDE() <= NZ() * LDM(); }
-    __device__ __forceinline__ void fac_issue(int k, int buf) {
-        if (lane == 0) tma_load_1d(sM + buf * FSTRIDE(), ws + L.FAC + k * FSTRIDE(), uint32_t(FSTRIDE() * sizeof(T)), sBar + buf);
-    }
-    __device__ __forceinline__ const T* fac_wait(int buf) {
-        mbar_wait(sBar + buf, bar_phase[buf]);
-        bar_phase[buf] ^= 1u;
-        return sM + buf * FSTRIDE();
-    }
-
-    __device__ void solve_sweeps(bool corrector, T target_mu) {
-        const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ldf = LDF();
-        T* vec = sV;           // [nz] gradient
-        T* dx = sV + nz;       // [nx]
-        T* du = sV + 2 * nz;   // [nu] (also s)
-        const bool dbuf = fac_double_buffered();
-        // backward
-        for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
-        __syncwarp();
-        if (dbuf)
-            for (int d = 0; d < kFacRing - 1; ++d)
-                if (P.N - 1 - d >= 0) fac_issue(P.N - 1 - d, (P.N - 1 - d) % kFacRing);
-        for (int k = P.N; k >= 0; --k) {
-            const long long g0 = clock64();
-            stage_gradient(k, corrector, target_mu, vec);
-            t_g += clock64() - g0;
-            if (k == P.N) {
-                for (int i = lane; i < nx; i += WARP) sPv[i] = vec[nu + i];
-                __syncwarp();
-                continue;
-            }
-            add_dynamics_gradient(vec);
-            const T* F;
-            if (dbuf) {
-                if (k - (kFacRing - 1) >= 0) fac_issue(k - (kFacRing - 1), (k - (kFacRing - 1)) % kFacRing);  // slot last read at stage k+1
-                F = fac_wait(k % kFacRing);
-            } else {
-                copy_block(sM, ws + L.FAC + k * FSTRIDE(), nz * ldf);
-                F = sM;
-                __syncwarp();
-            }
-            // w = L^{-1} m_u
-            if constexpr (kInvL) {
-                T wi = T(0);
-                if (lane < nu) {
-                    const T* Fr = F + lane * ldf;
-                    for (int j = 0; j <= lane; ++j) wi += Fr[j] * vec[j];
-                }
-                __syncwarp();
-                if (lane < nu) vec[lane] = wi;
-                __syncwarp();
-            } else {
-                for (int j = 0; j < nu; ++j) {  // forward substitution, column oriented
-                    const T wj = vec[j] * F[j * ldf + j];
-                    __syncwarp();
-                    if (lane == 0) vec[j] = wj;
-                    for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= F[i * ldf + j] * wj;
-                    __syncwarp();
-                }
-            }
-            T* Wk = ws + L.WF + k * nu;
-            for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
-            // p = m_x - Y' w
-            for (int i = lane; i < nx; i += WARP) {
-                T acc = vec[nu + i];
-                const T* Fr = F + (nu + i) * ldf;
-                for (int j = 0; j < nu; ++j) acc -= Fr[j] * vec[j];
-                sPv[i] = acc;
-            }
-            __syncwarp();
-        }
-        // forward: d x_0 = 0
-        for (int i = lane; i < nx; i += WARP) dx[i] = T(0);
-        __syncwarp();
-        if (dbuf)
-            for (int d = 0; d < kFacRing - 1; ++d)
-                if (d < P.N) fac_issue(d, d % kFacRing);
-        for (int k = 0; k < P.N; ++k) {
-            const T* F;
-            if (dbuf) {
-                if (k + kFacRing - 1 < P.N) fac_issue(k + kFacRing - 1, (k + kFacRing - 1) % kFacRing);
-                F = fac_wait(k % kFacRing);
-            } else {
-                copy_block(sM, ws + L.FAC + k * FSTRIDE(), nz * ldf);
-                F = sM;
-                __syncwarp();
-            }
-            const T* Wk = ws + L.WF + k * nu;
-            // s = w + Y dx
-            for (int j = lane; j < nu; j += WARP) {
-                T acc = Wk[j];
-                for (int i = 0; i < nx; ++i) acc += F[(nu + i) * ldf + j] * dx[i];
-                du[j] = acc;
-            }
-            __syncwarp();
-            // du = -L^{-T} s
-            if constexpr (kInvL) {
-                T uj = T(0);
-                if (lane < nu)
-                    for (int i = lane; i < nu; ++i) uj -= F[i * ldf + lane] * du[i];
-                __syncwarp();
-                if (lane < nu) du[lane] = uj;
-                __syncwarp();
-            } else {
-                for (int j = nu - 1; j >= 0; --j) {  // backward substitution, row oriented
-                    const T uj = -du[j] * F[j * ldf + j];
-                    __syncwarp();
-                    for (int i = lane; i < j; i += WARP) du[i] += F[j * ldf + i] * uj;
-                    if (lane == 0) du[j] = uj;
-                    __syncwarp();
-                }
-            }
-            T* Dk = DZk(k);
-            for (int j = lane; j < nu; j += WARP) Dk[j] = du[j];
-            for (int i = lane; i < nx; i += WARP) Dk[nu + i] = dx[i];
-            __syncwarp();
-            if (lane < nq) {
-                const T dt = P.dt;
-                const T q = dx[lane], v = dx[nq + lane], a = dx[2 * nq + lane], j = du[lane];
-                dx[lane] = q + dt * v + T(0.5) * dt * dt * a + dt * dt * dt / T(6) * j;
-                dx[nq + lane] = v + dt * a + T(0.5) * dt * dt * j;
-                dx[2 * nq + lane] = a + dt * j;
-            }
-            __syncwarp();
-        }
-        T* Dn = DZk(P.N);
-        for (int j = lane; j < nu; j += WARP) Dn[j] = T(0);
-        for (int i = lane; i < nx; i += WARP) Dn[nu + i] = dx[i];
-        __syncwarp();
-    }
-
-    // d lambda / d t of every side for the direction in DZ; returns the largest
-    // step in (0,1] keeping t and lambda positive, and (via *mu_after) the summed
-    // complementarity after that step.
-    __device__ T side_steps(bool corrector, T target_mu, T* mu_after) {
-        T amax = T(1);
-        const T cm = corrector ? T(1) : T(0);
-        for (int k = 0; k <= P.N; ++k) {
-            const T* zk = Zk(k);
-            const T* dk = DZk(k);
-            for (int r = lane; r < NROW(); r += WARP) {
-                const int fam = row_family(r);
-                if (!row_valid(k, fam)) continue;
-                T lb, ub;
-                const T val = row_value(k, r, fam, zk, &lb, &ub);
-                const T adz = row_dot(k, r, fam, dk);
-                const T eps = row_eps(fam);
-                const Quad q = *side_tl(k, r);
-                Quad dd = *side_dd(k, r);
-                const int nsd = fam >= 2 ? 1 : 2;
-                for (int sd = 0; sd < nsd; ++sd) {
-                    const T t = q.v[sd], lam = q.v[2 + sd];
-                    const T sg = sd == 0 ? T(1) : T(-1);
-                    const T d = sd == 0 ? val - lb : ub - val;
-                    const T rd = d + eps * lam - t;
-                    const T rc = t * lam - target_mu + cm * dd.v[sd] * dd.v[2 + sd];
-                    const T den = t + eps * lam;
-                    const T dl = -(rc + lam * rd) / den - (lam / den) * sg * adz;
-                    const T dtt = sg * adz + eps * dl + rd;
-                    dd.v[sd] = dtt;
-                    dd.v[2 + sd] = dl;
-                    if (dtt < T(0)) amax = min(amax, -t / dtt);
-                    if (dl < T(0)) amax = min(amax, -lam / dl);
-                }
-                *side_dd(k, r) = dd;
-            }
-        }
-        amax = warp_min(amax);
-        __syncwarp();
-        if (mu_after) {
-            T acc = 0;
-            for (int k = 0; k <= P.N; ++k)
-                for (int r = lane; r < NROW(); r += WARP) {
-                    const int fam = row_family(r);
-                    if (!row_valid(k, fam)) continue;
-                    const Quad q = *side_tl(k, r);
-                    const Quad dd = *side_dd(k, r);
-                    acc += (q.v[0] + amax * dd.v[0]) * (q.v[2] + amax * dd.v[2]);
-                    if (fam < 2) acc += (q.v[1] + amax * dd.v[1]) * (q.v[3] + amax * dd.v[3]);
-                }
-            *mu_after = warp_sum(acc);
-        }
-        return amax;
-    }
-
     // ---------------------------------------------------------------- fused IPM passes
     // Pass A (backward): per stage load the equality rows once, form the predictor gradient
     // (sigma = 0), keep it in GP for the corrector, build and factor the stage matrix and do the
@@ -1258,17 +1116,17 @@ struct Solver {
         bool ok = true;
         for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
         __syncwarp();
-        for (int k = P.N; k >= 0; --k) {
+        for (int k = NN(); k >= 0; --k) {
             long long f0 = clock64();
             stage_gradient(k, false, T(0), vec);            // loads the equality rows of stage k into sSA
-            T* GPk = ws + L.LAM + k * nz;
+            T* GPk = ws + oLAM() + k * nz;
             for (int i = lane; i < nz; i += WARP) GPk[i] = vec[i];
             long long f1 = clock64();
             t_g += f1 - f0;
             build_stage_matrix(k, true);
             long long f2 = clock64();
             t_f1 += f2 - f1;
-            if (k < P.N) {
+            if (k < NN()) {
                 add_dynamics_hessian();
                 add_dynamics_gradient(vec);                  // uses p_{k+1} in sPv
                 long long f3 = clock64();
@@ -1305,7 +1163,7 @@ struct Solver {
                         __syncwarp();
                     }
                 }
-                T* Wk = ws + L.WF + k * nu;
+                T* Wk = ws + oWF() + k * nu;
                 for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
                 // p = m_x - Y' w
                 for (int i = lane; i < nx; i += WARP) {
@@ -1315,7 +1173,7 @@ struct Solver {
                     sPv[i] = acc;
                 }
                 // factor block [L or L^{-1}; Y] -> global for the forward / corrector passes
-                T* F = ws + L.FAC + k * FSTRIDE();
+                T* F = ws + oFAC() + k * FSTRIDE();
                 for (int idx = lane; idx < nz * nu; idx += WARP) {
                     const int i = idx / nu, j = idx % nu;
                     T v = T(0);
@@ -1324,11 +1182,7 @@ struct Solver {
                 }
             } else {
                 for (int i = lane; i < nx; i += WARP) sPv[i] = vec[nu + i];
-            }
-            // cost-to-go Hessian: trailing block, full symmetric
-            for (int idx = lane; idx < nx * nx; idx += WARP) {
-                const int i = idx / nx, j = idx % nx;
-                sP[idx] = (j <= i) ? sM[(nu + i) * ld + nu + j] : sM[(nu + j) * ld + nu + i];
+                copy_cost_to_go();
             }
             __syncwarp();
         }
@@ -1344,8 +1198,8 @@ struct Solver {
         for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
         __syncwarp();
         const int nbx = NBOXU() + nx;
-        for (int k = P.N; k >= 0; --k) {
-            const T* GPk = ws + L.LAM + k * nz;
+        for (int k = NN(); k >= 0; --k) {
+            const T* GPk = ws + oLAM() + k * nz;
             for (int i = lane; i < nz; i += WARP) vec[i] = GPk[i];
             __syncwarp();
             // (corr - target) / (t + eps lam) per side
@@ -1360,7 +1214,7 @@ struct Solver {
                           (dd.v[1] * dd.v[3] - target_mu) / (q.v[1] + eps * q.v[3]);
             }
             __syncwarp();
-            if (NFRIC() > 0 && k < P.N) {
+            if (NFRIC() > 0 && k < NN()) {
                 const T eps = row_eps(2);
                 for (int c = lane; c < NC(); c += WARP) {
                     T g0 = 0, g1 = 0, g2 = 0;
@@ -1380,10 +1234,10 @@ struct Solver {
                 }
                 __syncwarp();
             }
-            if (P.nobs > 0 && k >= 1 && k < P.N) {
+            if (NOBS() > 0 && k >= 1 && k < NN()) {
                 const T eps = row_eps(3);
                 T* crow = sV + 4 * nz;
-                for (int i = lane; i < P.nobs; i += WARP) {
+                for (int i = lane; i < NOBS(); i += WARP) {
                     const int r = nbx + NFRIC() + i;
                     const Quad q = *side_tl(k, r);
                     const Quad dd = *side_dd(k, r);
@@ -1392,18 +1246,18 @@ struct Solver {
                 __syncwarp();
                 if (lane < nq) {
                     T acc = 0;
-                    for (int i = 0; i < P.nobs; ++i) acc += crow[i] * ws[L.LJO + (k * P.nobs + i) * nq + lane];
+                    for (int i = 0; i < NOBS(); ++i) acc += crow[i] * ws[oLJO() + (k * NOBS() + i) * nq + lane];
                     vec[nu + lane] += acc;
                 }
                 __syncwarp();
             }
-            if (k == P.N) {
+            if (k == NN()) {
                 for (int i = lane; i < nx; i += WARP) sPv[i] = vec[nu + i];
                 __syncwarp();
                 continue;
             }
             add_dynamics_gradient(vec);
-            copy_block(sM, ws + L.FAC + k * FSTRIDE(), nz * ldf);
+            copy_block(sM, ws + oFAC() + k * FSTRIDE(), nz * ldf);
             const T* F = sM;
             __syncwarp();
             if constexpr (kInvL) {
@@ -1424,7 +1278,7 @@ struct Solver {
                     __syncwarp();
                 }
             }
-            T* Wk = ws + L.WF + k * nu;
+            T* Wk = ws + oWF() + k * nu;
             for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
             for (int i = lane; i < nx; i += WARP) {
                 T acc = vec[nu + i];
@@ -1480,11 +1334,11 @@ struct Solver {
         T amax = T(1);
         for (int i = lane; i < nz; i += WARP) dst[i] = T(0);
         __syncwarp();
-        for (int k = 0; k <= P.N; ++k) {
-            if (k < P.N) {
-                copy_block(sM, ws + L.FAC + k * FSTRIDE(), nz * ldf);
+        for (int k = 0; k <= NN(); ++k) {
+            if (k < NN()) {
+                copy_block(sM, ws + oFAC() + k * FSTRIDE(), nz * ldf);
                 const T* F = sM;
-                const T* Wk = ws + L.WF + k * nu;
+                const T* Wk = ws + oWF() + k * nu;
                 __syncwarp();
                 // s = w + Y dx
                 for (int j = lane; j < nu; j += WARP) {
@@ -1516,7 +1370,7 @@ struct Solver {
             T* Dk = DZk(k);
             for (int i = lane; i < nz; i += WARP) Dk[i] = dst[i];
             stage_side_steps(k, dst, corrector, target_mu, amax);
-            if (k < P.N) {
+            if (k < NN()) {
                 if (lane < nq) {
                     const T dt = P.dt;
                     const T q = dx[lane], v = dx[nq + lane], a = dx[2 * nq + lane], j = du[lane];
@@ -1536,17 +1390,17 @@ struct Solver {
     // and the factors of the last iteration in FAC.  Returns iterations used;
     // *converged, *decr as in orc::solve_qp_ipm.
     __device__ int solve_qp(bool* converged, T* decr, bool* finite) {
-        const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), N = P.N;
+        const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), N = NN();
         *converged = false;
         *finite = true;
         // dynamics-feasible start: du = 0, dx_0 = 0, dx_{k+1} = A dx_k + gap_k
-        for (int idx = lane; idx < (N + 1) * nz; idx += WARP) ws[L.Z + idx] = T(0);
+        for (int idx = lane; idx < (N + 1) * nz; idx += WARP) ws[oZ() + idx] = T(0);
         __syncwarp();
         if (lane < nq) {
             const T dt = P.dt;
             T q = 0, v = 0, a = 0;
             for (int k = 0; k < N; ++k) {
-                const T* gap = ws + L.GAP + k * nx;
+                const T* gap = ws + oGAP() + k * nx;
                 const T qn = q + dt * v + T(0.5) * dt * dt * a + gap[lane];
                 const T vn = v + dt * a + gap[nq + lane];
                 const T an = a + gap[2 * nq + lane];
@@ -1647,7 +1501,7 @@ struct Solver {
                     const int k = idx / NROW(), r = idx % NROW();
                     const int fam = row_family(r);
                     if (!row_valid(k, fam)) continue;
-                    const Quad* rec = reinterpret_cast<const Quad*>(ws + L.TT) + 2 * idx;
+                    const Quad* rec = reinterpret_cast<const Quad*>(ws + oTT()) + 2 * idx;
                     const Quad q = rec[0], dd = rec[1];
                     acc += (q.v[0] + a_aff * dd.v[0]) * (q.v[2] + a_aff * dd.v[2]);
                     if (fam < 2) acc += (q.v[1] + a_aff * dd.v[1]) * (q.v[3] + a_aff * dd.v[3]);
@@ -1666,14 +1520,14 @@ struct Solver {
             // update z, t, lambda; new mean complementarity
             T stepmax = 0, musum = 0;
             for (int idx = lane; idx < (N + 1) * nz; idx += WARP) {
-                const T d = ws[L.DZ + idx];
-                ws[L.Z + idx] += alpha * d;
+                const T d = ws[oDZ() + idx];
+                ws[oZ() + idx] += alpha * d;
                 stepmax = max(stepmax, fabs(alpha * d));
             }
             for (int idx = lane; idx < (N + 1) * NROW(); idx += WARP) {
                 const int k = idx / NROW(), r = idx % NROW();
                 const int fam = row_family(r);
-                Quad* rec = reinterpret_cast<Quad*>(ws + L.TT) + 2 * idx;
+                Quad* rec = reinterpret_cast<Quad*>(ws + oTT()) + 2 * idx;
                 Quad q = rec[0];
                 const Quad dd = rec[1];
 #pragma unroll
@@ -1715,8 +1569,8 @@ struct Solver {
         const int nu = NU(), nx = NX(), nz = NZ(), ldf = LDF();
         T* F = sM;
         T* col = sV;
-        for (int k = 0; k < P.N; ++k) {
-            const T* Fg = ws + L.FAC + k * FSTRIDE();
+        for (int k = 0; k < NN(); ++k) {
+            const T* Fg = ws + oFAC() + k * FSTRIDE();
             for (int idx = lane; idx < nz * ldf; idx += WARP) F[idx] = Fg[idx];
             __syncwarp();
             for (int xcol = 0; xcol < nx; ++xcol) {
@@ -1746,7 +1600,7 @@ struct Solver {
 
     // --------------------------------------------------------------- solve
     __device__ void run(const BatchArgs<T>& A, int b) {
-        const int nq = NQ(), nx = NX(), nu = NU(), N = P.N, nz = NZ();
+        const int nq = NQ(), nx = NX(), nu = NU(), N = NN(), nz = NZ();
         // initial guess: DefaultInitializer = zero input, state held
         // (controller_interface.cpp:385-386); x_0 is always the observation
         if (!A.warm) {
@@ -1760,8 +1614,8 @@ struct Solver {
         Perf<T> base = performance(X, U);
         int status = UB_STATUS_CONVERGED, qp_iters = 0, sqp_done = 0;
         T alpha = 0, qp_res = 0;
-        T* Xn = ws + L.XN;
-        T* Un = ws + L.UN;
+        T* Xn = ws + oXN();
+        T* Un = ws + oUN();
         for (int it = 0; it < max(1, P.sqp_iters); ++it) {
             ++sqp_done;
             long long c0 = clock64();
@@ -1782,7 +1636,7 @@ struct Solver {
                 const T* zk = Zk(k);
                 const T* x = X + k * nx;
                 const T* u = U + k * nu;
-                const T* Jp = ws + L.LJP + k * 3 * nq;
+                const T* Jp = ws + oLJP() + k * 3 * nq;
                 for (int i = lane; i < nz; i += WARP) {
                     T g;
                     if (i < nq) g = P.dt * P.Rd[i] * u[i];
@@ -1792,7 +1646,7 @@ struct Solver {
                         g = P.dt * P.Qd[xi] * (x[xi] - P.xd[xi]);
                         if (xi < nq)
                             for (int c = 0; c < 3; ++c)
-                                g += P.dt * P.Wd[c] * Jp[c * nq + xi] * (ws[L.LR + 3 * k + c] - target[3 * k + c]);
+                                g += P.dt * P.Wd[c] * Jp[c * nq + xi] * (ws[oLR() + 3 * k + c] - target[3 * k + c]);
                     }
                     desc += g * zk[i];
                 }
@@ -1807,11 +1661,11 @@ struct Solver {
             while (alpha >= P.alpha_min) {
                 for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
                     const int k = idx / nx, i = idx % nx;
-                    Xn[idx] = X[idx] + alpha * ws[L.Z + k * nz + nu + i];
+                    Xn[idx] = X[idx] + alpha * ws[oZ() + k * nz + nu + i];
                 }
                 for (int idx = lane; idx < N * nu; idx += WARP) {
                     const int k = idx / nu, i = idx % nu;
-                    Un[idx] = U[idx] + alpha * ws[L.Z + k * nz + i];
+                    Un[idx] = U[idx] + alpha * ws[oZ() + k * nz + i];
                 }
                 __syncwarp();
                 pn = performance(Xn, Un);
@@ -1898,21 +1752,24 @@ __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const DevProblem<T>
     const int warp = threadIdx.x / WARP, lane = threadIdx.x % WARP;
     const int b = blockIdx.x * warps_per_cta + warp;
     if (b >= A.B) return;
-    size_t off = (sizeof(DevProblem<T>) + 15) / 16 * 16;
-    T* sm = reinterpret_cast<T*>(smem_raw + off) + size_t(warp) * L.s_total;
+    constexpr size_t off = (sizeof(DevProblem<T>) + 15) / 16 * 16;
+    Layout Lk = L;
+    if constexpr (D::kStatic) Lk = D::template layout<T>();  // compile-time offsets (host passes the same numbers)
+    T* sm = reinterpret_cast<T*>(smem_raw + off) + size_t(warp) * Lk.s_total;
     Solver<T, D> S(*Ps, L, lane);
-    S.x0 = A.x0 + size_t(b) * Ps->nx;
-    S.target = A.target + size_t(b) * (Ps->N + 1) * 3;
-    S.body = A.body ? A.body + size_t(b) * Ps->nb * UB_BODY_PARAMS : &Ps->body[0][0];
-    S.X = A.X + size_t(b) * (Ps->N + 1) * Ps->nx;
-    S.U = A.U + size_t(b) * Ps->N * Ps->nu;
-    S.ws = A.ws + size_t(b) * L.total;
-    S.sM = sm + L.sM;
-    S.sP = sm + L.sP;
-    S.sPv = sm + L.sPv;
-    S.sSA = sm + L.sSA;
-    S.sV = sm + L.sV;
-    S.sBar = reinterpret_cast<uint64_t*>(sm + L.sBar);
+    const int nx = S.NX(), nu = S.NU(), N = S.NN();
+    S.x0 = A.x0 + size_t(b) * nx;
+    S.target = A.target + size_t(b) * (N + 1) * 3;
+    S.body = A.body ? A.body + size_t(b) * S.NB() * UB_BODY_PARAMS : &Ps->body[0][0];
+    S.X = A.X + size_t(b) * (N + 1) * nx;
+    S.U = A.U + size_t(b) * N * nu;
+    S.ws = A.ws + size_t(b) * Lk.total;
+    S.sM = sm + Lk.sM;
+    S.sP = sm + Lk.sP;
+    S.sPv = sm + Lk.sPv;
+    S.sSA = sm + Lk.sSA;
+    S.sV = sm + Lk.sV;
+    S.sBar = reinterpret_cast<uint64_t*>(sm + Lk.sBar);
     S.bar_phase[0] = S.bar_phase[1] = S.bar_phase[2] = 0u;
     if (lane == 0) {
         mbar_init(S.sBar, 1);
