@@ -142,6 +142,7 @@ struct ub_problem {
     int device = 0;
     int sm_count = 0;
     int max_smem_optin = 0;
+    int max_smem_sm = 0;
     int stop_after = 0;
     float last_ms = 0.f;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -186,8 +187,10 @@ int launch_solve(ub_problem* p, const ub::BatchArgs<T>& A, cudaStream_t stream) 
     const ub::Layout& L = Pick<T>::layout(p);
     const size_t pbytes = (sizeof(ub::DevProblem<T>) + 15) / 16 * 16;
     const size_t per_warp = size_t(L.s_total) * sizeof(T);
-    // warps per CTA: as many as fit in ~100 KB (two CTAs per SM), at most 8
-    int wpc = int((100 * 1024 - pbytes) / per_warp);
+    // warps per CTA: two CTAs per SM (the 128-register kernels allow 16 warps per SM), each taking half of the
+    // SM's shared memory minus the 1 KB the driver reserves per CTA; at most 8 warps
+    const size_t cta_budget = size_t(p->max_smem_sm) / 2 - 1024;
+    int wpc = int((cta_budget - pbytes) / per_warp);
     if (wpc < 1) wpc = 1;
     if (wpc > 8) wpc = 8;
     const char* env = std::getenv("UB_WARPS_PER_CTA");
@@ -342,6 +345,7 @@ int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
     UB_CUDA(cudaGetDevice(&p->device));
     UB_CUDA(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, p->device));
     UB_CUDA(cudaDeviceGetAttribute(&p->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, p->device));
+    UB_CUDA(cudaDeviceGetAttribute(&p->max_smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, p->device));
     UB_CUDA(cudaMalloc(&p->df, sizeof(p->hf)));
     UB_CUDA(cudaMalloc(&p->dd, sizeof(p->hd)));
     UB_CUDA(cudaMemcpy(p->df, &p->hf, sizeof(p->hf), cudaMemcpyHostToDevice));

@@ -17,21 +17,19 @@
 
 #include "ub_device.cuh"
 
-#ifndef UB_USE_TMA
-#define UB_USE_TMA 0
-#endif
-
 namespace ub {
 
 // Per-problem workspace layout in units of T.  One constexpr function serves the host (make_layout in
 // ub_api.cu) and the kernels specialised on compile-time dimensions, where every offset becomes an
 // immediate of the load/store instruction.
 struct Layout {
-    int Z, DZ, GAP, LG, LCT, LR, LJP, LHO, LJO, DF, RHOE, YE, RHOT, YT, TT, LAM, DTT, DLAM, sBar, FAC, WF, XN, UN;
+    int Z, DZ, GAP, LG, LCT, LR, LJP, LHO, LJO, DF, RHOE, YE, RHOT, YT, TT, LAM, DTT, DLAM, sTT, FAC, WF, XN, UN;
     int total;
     // shared memory (units of T, per warp)
     int sM, sP, sPv, sSA, sV, s_total, ldm, ldf;
 };
+// side records of a stage are staged in shared memory (cp.async, one stage ahead) up to this many rows
+#define UB_STAGE_ROWS_MAX 64
 struct LayoutDims {
     int N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, tsize;
 };
@@ -72,7 +70,7 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.sPv = s;  s += ub_round4(nx);
     L.sSA = s;  s += ub_round4((d.neq > 3 ? d.neq : 3) * nz);
     L.sV = s;   s += ub_round4(5 * nz + 64);  // [4 nz, ...) doubles as per-row scratch (>= max(neq, nobs, 3) entries)
-    L.sBar = s; s += ub_round4(32 / d.tsize);  // three 8-byte mbarriers (+pad)
+    L.sTT = s;  s += (d.nrow <= UB_STAGE_ROWS_MAX) ? ub_round4(d.nrow * 8) : 0;  // staged side records of one stage
     L.s_total = s;
     return L;
 }
@@ -94,30 +92,7 @@ struct BatchArgs {
 };
 
 
-// ---- TMA (cp.async.bulk, 1-D) global -> shared with mbarrier completion -----------------
-// One elected lane arms the barrier with the byte count and issues the bulk copy; every lane
-// then waits on the barrier phase.  Used to stage the next stage's Riccati factor block while
-// the current stage is being processed (SASS: UBLKCP / SYNCS).
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    uint32_t ok = 0;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok)
-                     : "r"(smem_u32(bar)), "r"(phase)
-                     : "memory");
-    } while (!ok);
-}
 
 template <typename T>
 __device__ __forceinline__ T tinf() { return T(1e30); }
@@ -171,9 +146,6 @@ struct Solver {
     __device__ __forceinline__ int NROW() const { return NBOXU() + NX() + NFRIC() + NOBS(); }
     __device__ __forceinline__ int NTERM() const { return 3 + 2 * NQ(); }
     __device__ __forceinline__ int FSTRIDE() const { return (NZ() * LDF() + 3) & ~3; }  // 16-byte aligned factor blocks
-    // small input blocks: store L^{-1} instead of L, turning the 4 triangular substitutions per
-    // interior-point iteration and stage (serial pivot chains) into matrix-vector products
-    static constexpr bool kInvL = false && D::kStatic && D::nu <= 16;
     // batch data of this instance
     const T* x0;
     const T* target;
@@ -187,10 +159,9 @@ struct Solver {
     T* sPv;
     T* sSA;
     T* sV;
-    uint64_t* sBar;      // mbarriers of the factor-block ring
+    T* sTT;
     long long t_lin = 0, t_fac = 0, t_swp = 0, t_side = 0, t_ls = 0, t_res = 0;
     long long t_f1 = 0, t_f2 = 0, t_f3 = 0, t_f4 = 0, t_g = 0;  // finer: build / dynamics / cholesky / store ; gradient  // phase cycle counters (profile mode)
-    uint32_t bar_phase[3];
 
     __device__ Solver(const DevProblem<T>& P_, const Layout& L_, int lane_) : P(P_), L(L_), lane(lane_) {}
 
@@ -303,6 +274,34 @@ struct Solver {
     };
     __device__ __forceinline__ Quad* side_tl(int k, int r) const { return reinterpret_cast<Quad*>(ws + oTT()) + (k * NROW() + r) * 2; }
     __device__ __forceinline__ Quad* side_dd(int k, int r) const { return side_tl(k, r) + 1; }
+    // Staging of the side records: the records of the stage a pass visits NEXT are copied into shared memory
+    // with cp.async while the current stage computes; readers take them from `recs(k)` ([2r] = {t, lam},
+    // [2r+1] = {dt, dlam}).  Writers always store to the workspace.
+    static constexpr bool kStageTT = D::kStatic && D::nrow <= UB_STAGE_ROWS_MAX;
+    __device__ __forceinline__ const Quad* recs(int k) const {
+        if constexpr (kStageTT) return reinterpret_cast<const Quad*>(sTT);
+        else return reinterpret_cast<const Quad*>(ws + oTT()) + k * NROW() * 2;
+    }
+    __device__ __forceinline__ void cp_async16(void* dst, const void* src) const {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    }
+    __device__ __forceinline__ void cp_commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    template <int NYOUNGER>
+    __device__ __forceinline__ void cp_wait() const {
+        asm volatile("cp.async.wait_group %0;" ::"n"(NYOUNGER) : "memory");
+        __syncwarp();
+    }
+    // issue (no commit) the copy of the records of stage k; k outside [0, N] issues nothing
+    __device__ __forceinline__ void tt_issue(int k) const {
+        if constexpr (kStageTT) {
+            if (k < 0 || k > NN()) return;
+            constexpr int CH = NROW_STATIC * 8 * int(sizeof(T)) / 16;
+            const char* src = reinterpret_cast<const char*>(ws + oTT() + k * NROW() * 8);
+            char* dst = reinterpret_cast<char*>(sTT);
+            for (int i = lane; i < CH; i += WARP) cp_async16(dst + 16 * i, src + 16 * i);
+        }
+    }
+    static constexpr int NROW_STATIC = D::nrow;
     // Newton data of one side: returns the barrier weight and the coefficient that multiplies sgn*a in the
     // stage gradient;  d = signed distance to the bound at the current iterate
     __device__ __forceinline__ T side_coef(T t, T lam, T d, T eps, T target, T corr) const {
@@ -735,7 +734,7 @@ struct Solver {
             const int fam = r < NBOXU() ? 0 : 1;
             if (!row_valid(k, fam)) continue;
             const T eps = row_eps(fam);
-            const Quad q = *side_tl(k, r);
+            const Quad q = recs(k)[2 * r];
             const T w = q.v[2] / (q.v[0] + eps * q.v[2]) + q.v[3] / (q.v[1] + eps * q.v[3]);
             const int m = fam == 0 ? r : nu + (r - NBOXU());
             sM[m * ld + m] += w;
@@ -747,7 +746,7 @@ struct Solver {
             for (int c = lane; c < NC(); c += WARP) {
                 T blk[6] = {0, 0, 0, 0, 0, 0};
                 for (int which = 0; which < 5; ++which) {
-                    const Quad q = *side_tl(k, nbx + 5 * c + which);
+                    const Quad q = recs(k)[2 * (nbx + 5 * c + which)];
                     const T w = q.v[2] / (q.v[0] + eps * q.v[2]);
                     const V3<T> cf = fric_coeff(c, which);
                     blk[0] += w * cf.x * cf.x;
@@ -771,7 +770,7 @@ struct Solver {
             const T eps = row_eps(3);
             T* wrow = sV + 4 * nz;  // barrier weights of the obstacle rows
             for (int i = lane; i < NOBS(); i += WARP) {
-                const Quad q = *side_tl(k, nbx + NFRIC() + i);
+                const Quad q = recs(k)[2 * (nbx + NFRIC() + i)];
                 wrow[i] = q.v[2] / (q.v[0] + eps * q.v[2]);
             }
             __syncwarp();
@@ -950,7 +949,7 @@ struct Solver {
     //   H z + g  +  sum_eq a (rho e + y)  +  sum_sides sgn a [ -lam + (rc + lam rd)/(t + eps lam) ]
     // with rc = t lam - target (+ dt_aff dlam_aff in the corrector).  Result in vec (shared).
     // Every row family accumulates into distinct entries per lane (no atomics).
-    __device__ void stage_gradient(int k, bool corrector, T mu_target, T* vec) {
+    __device__ void stage_gradient(int k, bool corrector, T mu_target, T* vec, bool rows_loaded = false) {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ();
         const T dt = P.dt;
         const T* zk = Zk(k);
@@ -1000,9 +999,9 @@ struct Solver {
                 ub = P.xub[i] - xx;
             }
             const T eps = row_eps(fam);
-            const Quad q = *side_tl(k, r);
+            const Quad q = recs(k)[2 * r];
             Quad dd;
-            if (corrector) dd = *side_dd(k, r);
+            if (corrector) dd = recs(k)[2 * r + 1];
             else dd.v[0] = dd.v[1] = dd.v[2] = dd.v[3] = T(0);
             const T c0 = side_coef(q.v[0], q.v[2], val - lb, eps, mu_target, cm * dd.v[0] * dd.v[2]);
             const T c1 = side_coef(q.v[1], q.v[3], ub - val, eps, mu_target, cm * dd.v[1] * dd.v[3]);
@@ -1012,7 +1011,7 @@ struct Solver {
         // equality rows
         const int ne = neq_of(k);
         if (ne > 0) {
-            load_eq_rows(k);
+            if (!rows_loaded) load_eq_rows(k);
             const T* rho = rho_eq(k);
             const T* y = y_eq(k);
             const int nd = (k < NN()) ? ne : 3;
@@ -1053,10 +1052,10 @@ struct Solver {
                     const int r = nbx + 5 * c + which;
                     const V3<T> a = fric_coeff(c, which);
                     const T val = a.x * f0 + a.y * f1 + a.z * f2;
-                    const Quad q = *side_tl(k, r);
+                    const Quad q = recs(k)[2 * r];
                     T corr = T(0);
                     if (corrector) {
-                        const Quad dd = *side_dd(k, r);
+                        const Quad dd = recs(k)[2 * r + 1];
                         corr = dd.v[0] * dd.v[2];
                     }
                     const T cf = side_coef(q.v[0], q.v[2], val, eps, mu_target, corr);
@@ -1078,10 +1077,10 @@ struct Solver {
                 const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
                 T val = ws[oLHO() + k * NOBS() + i];
                 for (int j = 0; j < nq; ++j) val += J[j] * zk[nu + j];
-                const Quad q = *side_tl(k, r);
+                const Quad q = recs(k)[2 * r];
                 T corr = T(0);
                 if (corrector) {
-                    const Quad dd = *side_dd(k, r);
+                    const Quad dd = recs(k)[2 * r + 1];
                     corr = dd.v[0] * dd.v[2];
                 }
                 crow[i] = side_coef(q.v[0], q.v[2], val, eps, mu_target, corr);
@@ -1096,6 +1095,47 @@ struct Solver {
         }
     }
 
+    // L1 prefetch of a span of the instance workspace: issued one stage ahead of its use so that the loads of
+    // the next stage hit L1 instead of waiting on L2 / HBM behind only four warps per scheduler.
+    __device__ __forceinline__ void prefetch_span(const T* p, int nelem) const {
+        constexpr int LINE = 128 / sizeof(T);
+        for (int i = lane * LINE; i < nelem + LINE; i += WARP * LINE)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + min(i, nelem - 1)));
+    }
+    // everything the factor pass reads for stage k
+    __device__ __forceinline__ void prefetch_factor_stage(int k) const {
+        if (k < 0) return;
+        prefetch_span(ws + oTT() + k * NROW() * 8, NROW() * 8);
+        prefetch_span(Zk(k), NZ());
+        prefetch_span(X + k * NX(), NX());
+        if (k < NN()) {
+            prefetch_span(U + k * NU(), NU());
+            if (NEQ() > 0) prefetch_span(ws + oLCT() + k * NEQ() * NZ(), NEQ() * NZ());
+            prefetch_span(ws + oLJP() + k * 3 * NQ(), 3 * NQ());
+        }
+    }
+    // Factor-block staging: the block of the NEXT stage is fetched with cp.async (LDGSTS, generic proxy — no
+    // proxy fence against the plain stores of the factor pass) into the other half of the idle stage-matrix
+    // buffer while the current stage is processed.
+    static constexpr bool kFacDouble = D::kStatic && 2 * ((D::nz * (D::nu | 1) + 3) & ~3) <= D::nz * (D::nz | 1);
+    static_assert(!kStageTT || kFacDouble, "side-record staging shares the cp.async group schedule of the factor ring");
+    __device__ __forceinline__ void fac_issue(int k, int buf) {
+        if (k < 0 || k >= NN()) return;
+        constexpr int V = 16 / sizeof(T);
+        const T* src = ws + oFAC() + k * FSTRIDE();
+        T* dst = sM + buf * FSTRIDE();
+        for (int i = lane; i < FSTRIDE() / V; i += WARP) cp_async16(dst + i * V, src + i * V);
+    }
+    // equality rows of stage k (k < N) straight into sSA
+    static constexpr bool kStageEQ = kStageTT && D::neq > 0 && (D::neq * D::nz) % 4 == 0;
+    __device__ __forceinline__ void eq_issue(int k) const {
+        if constexpr (kStageEQ) {
+            if (k < 0 || k >= NN()) return;
+            constexpr int V = 16 / sizeof(T);
+            const T* src = ws + oLCT() + k * NEQ() * NZ();
+            for (int i = lane; i < NEQ() * NZ() / V; i += WARP) cp_async16(sSA + i * V, src + i * V);
+        }
+    }
     // 16-byte vectorised copy global -> shared (both 16-byte aligned; n in elements)
     __device__ __forceinline__ void copy_block(T* __restrict__ dst, const T* __restrict__ src, int n) const {
         constexpr int V = 16 / sizeof(T);
@@ -1116,14 +1156,25 @@ struct Solver {
         bool ok = true;
         for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
         __syncwarp();
+        if constexpr (kStageTT) {
+            tt_issue(NN());
+            cp_commit();
+        }
         for (int k = NN(); k >= 0; --k) {
             long long f0 = clock64();
-            stage_gradient(k, false, T(0), vec);            // loads the equality rows of stage k into sSA
+            if constexpr (kStageTT) cp_wait<0>();           // side records (and equality rows) of stage k are staged
+            stage_gradient(k, false, T(0), vec, kStageEQ && k < NN());  // equality rows of stage k in sSA afterwards
             T* GPk = ws + oLAM() + k * nz;
             for (int i = lane; i < nz; i += WARP) GPk[i] = vec[i];
             long long f1 = clock64();
             t_g += f1 - f0;
             build_stage_matrix(k, true);
+            if constexpr (kStageTT) {                       // next stage's records / rows arrive during the factorisation
+                tt_issue(k - 1);
+                eq_issue(k - 1);
+                cp_commit();
+            }
+            prefetch_factor_stage(k - 1);
             long long f2 = clock64();
             t_f1 += f2 - f1;
             if (k < NN()) {
@@ -1134,35 +1185,14 @@ struct Solver {
                 ok &= stage_cholesky();
                 long long f4 = clock64();
                 t_f3 += f4 - f3;
-                if constexpr (kInvL) {
-                    // lane c builds column c of L^{-1}; stored transposed in the (free) upper triangle
-                    if (lane < nu) {
-                        const int c = lane;
-                        for (int i = c + 1; i < nu; ++i) {
-                            T acc = sM[i * ld + c] * sM[c * ld + c];
-                            for (int m = c + 1; m < i; ++m) acc += sM[i * ld + m] * sM[c * ld + m];
-                            sM[c * ld + i] = -acc * sM[i * ld + i];
-                        }
-                    }
+                for (int j = 0; j < nu; ++j) {  // forward substitution, column oriented
+                    const T wj = vec[j] * sM[j * ld + j];
                     __syncwarp();
-                    // w = L^{-1} m_u straight from the stage matrix buffer
-                    T wi = T(0);
-                    if (lane < nu) {
-                        for (int j = 0; j < lane; ++j) wi += sM[j * ld + lane] * vec[j];
-                        wi += sM[lane * ld + lane] * vec[lane];
-                    }
+                    if (lane == 0) vec[j] = wj;
+                    for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= sM[i * ld + j] * wj;
                     __syncwarp();
-                    if (lane < nu) vec[lane] = wi;
-                    __syncwarp();
-                } else {
-                    for (int j = 0; j < nu; ++j) {  // forward substitution, column oriented
-                        const T wj = vec[j] * sM[j * ld + j];
-                        __syncwarp();
-                        if (lane == 0) vec[j] = wj;
-                        for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= sM[i * ld + j] * wj;
-                        __syncwarp();
-                    }
                 }
+            
                 T* Wk = ws + oWF() + k * nu;
                 for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
                 // p = m_x - Y' w
@@ -1172,12 +1202,12 @@ struct Solver {
                     for (int j = 0; j < nu; ++j) acc -= Mr[j] * vec[j];
                     sPv[i] = acc;
                 }
-                // factor block [L or L^{-1}; Y] -> global for the forward / corrector passes
+                // factor block [L; Y] -> global for the forward / corrector passes
                 T* F = ws + oFAC() + k * FSTRIDE();
                 for (int idx = lane; idx < nz * nu; idx += WARP) {
                     const int i = idx / nu, j = idx % nu;
                     T v = T(0);
-                    if (j <= i) v = (kInvL && i < nu && j < i) ? sM[j * ld + i] : sM[i * ld + j];
+                    if (j <= i) v = sM[i * ld + j];
                     F[i * ldf + j] = v;
                 }
             } else {
@@ -1186,7 +1216,6 @@ struct Solver {
             }
             __syncwarp();
         }
-        if (UB_USE_TMA) asm volatile("fence.proxy.async;" ::: "memory");
         return ok;
     }
 
@@ -1198,18 +1227,29 @@ struct Solver {
         for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
         __syncwarp();
         const int nbx = NBOXU() + nx;
+        // cp.async group schedule: TT(k) is committed before FAC(k); every wait leaves exactly one younger group
+        // in flight (none at the terminal stage)
+        if constexpr (kFacDouble) {
+            tt_issue(NN());
+            cp_commit();
+        }
         for (int k = NN(); k >= 0; --k) {
             const T* GPk = ws + oLAM() + k * nz;
             for (int i = lane; i < nz; i += WARP) vec[i] = GPk[i];
-            __syncwarp();
+            if constexpr (kFacDouble) {
+                if (k == NN()) cp_wait<0>();
+                else cp_wait<1>();
+            } else {
+                __syncwarp();
+            }
             // (corr - target) / (t + eps lam) per side
             for (int r = lane; r < nbx; r += WARP) {
                 const int fam = r < NBOXU() ? 0 : 1;
                 if (!row_valid(k, fam)) continue;
                 const int m = fam == 0 ? r : nu + (r - NBOXU());
                 const T eps = row_eps(fam);
-                const Quad q = *side_tl(k, r);
-                const Quad dd = *side_dd(k, r);
+                const Quad q = recs(k)[2 * r];
+                const Quad dd = recs(k)[2 * r + 1];
                 vec[m] += (dd.v[0] * dd.v[2] - target_mu) / (q.v[0] + eps * q.v[2]) -
                           (dd.v[1] * dd.v[3] - target_mu) / (q.v[1] + eps * q.v[3]);
             }
@@ -1221,8 +1261,8 @@ struct Solver {
                     for (int which = 0; which < 5; ++which) {
                         const int r = nbx + 5 * c + which;
                         const V3<T> a = fric_coeff(c, which);
-                        const Quad q = *side_tl(k, r);
-                        const Quad dd = *side_dd(k, r);
+                        const Quad q = recs(k)[2 * r];
+                        const Quad dd = recs(k)[2 * r + 1];
                         const T cf = (dd.v[0] * dd.v[2] - target_mu) / (q.v[0] + eps * q.v[2]);
                         g0 += cf * a.x;
                         g1 += cf * a.y;
@@ -1239,8 +1279,8 @@ struct Solver {
                 T* crow = sV + 4 * nz;
                 for (int i = lane; i < NOBS(); i += WARP) {
                     const int r = nbx + NFRIC() + i;
-                    const Quad q = *side_tl(k, r);
-                    const Quad dd = *side_dd(k, r);
+                    const Quad q = recs(k)[2 * r];
+                    const Quad dd = recs(k)[2 * r + 1];
                     crow[i] = (dd.v[0] * dd.v[2] - target_mu) / (q.v[0] + eps * q.v[2]);
                 }
                 __syncwarp();
@@ -1251,33 +1291,39 @@ struct Solver {
                 }
                 __syncwarp();
             }
+            if constexpr (kFacDouble) {
+                __syncwarp();
+                tt_issue(k - 1);
+                cp_commit();
+            }
             if (k == NN()) {
                 for (int i = lane; i < nx; i += WARP) sPv[i] = vec[nu + i];
+                if constexpr (kFacDouble) {
+                    fac_issue(k - 1, (k - 1) & 1);
+                    cp_commit();
+                }
                 __syncwarp();
                 continue;
             }
             add_dynamics_gradient(vec);
-            copy_block(sM, ws + oFAC() + k * FSTRIDE(), nz * ldf);
             const T* F = sM;
-            __syncwarp();
-            if constexpr (kInvL) {
-                T wi = T(0);
-                if (lane < nu) {
-                    const T* Fr = F + lane * ldf;
-                    for (int j = 0; j <= lane; ++j) wi += Fr[j] * vec[j];
-                }
-                __syncwarp();
-                if (lane < nu) vec[lane] = wi;
-                __syncwarp();
+            if constexpr (kFacDouble) {
+                cp_wait<1>();
+                fac_issue(k - 1, (k - 1) & 1);
+                cp_commit();
+                F = sM + (k & 1) * FSTRIDE();
             } else {
-                for (int j = 0; j < nu; ++j) {
-                    const T wj = vec[j] * F[j * ldf + j];
-                    __syncwarp();
-                    if (lane == 0) vec[j] = wj;
-                    for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= F[i * ldf + j] * wj;
-                    __syncwarp();
-                }
+                copy_block(sM, ws + oFAC() + k * FSTRIDE(), nz * ldf);
+                __syncwarp();
             }
+            for (int j = 0; j < nu; ++j) {
+                const T wj = vec[j] * F[j * ldf + j];
+                __syncwarp();
+                if (lane == 0) vec[j] = wj;
+                for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= F[i * ldf + j] * wj;
+                __syncwarp();
+            }
+        
             T* Wk = ws + oWF() + k * nu;
             for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
             for (int i = lane; i < nx; i += WARP) {
@@ -1288,6 +1334,7 @@ struct Solver {
             }
             __syncwarp();
         }
+        if constexpr (kFacDouble) cp_wait<0>();
     }
 
     // Side steps of the rows of ONE stage for the stage direction d = [du; dx] (shared memory):
@@ -1302,8 +1349,8 @@ struct Solver {
             const T val = row_value(k, r, fam, zk, &lb, &ub);
             const T adz = row_dot(k, r, fam, d);
             const T eps = row_eps(fam);
-            const Quad q = *side_tl(k, r);
-            Quad dd = *side_dd(k, r);
+            const Quad q = recs(k)[2 * r];
+            Quad dd = recs(k)[2 * r + 1];
             const int nsd = fam >= 2 ? 1 : 2;
             for (int sd = 0; sd < nsd; ++sd) {
                 const T t = q.v[sd], lam = q.v[2 + sd];
@@ -1334,12 +1381,27 @@ struct Solver {
         T amax = T(1);
         for (int i = lane; i < nz; i += WARP) dst[i] = T(0);
         __syncwarp();
+        // cp.async group schedule: FAC(k) is committed before TT(k); every wait leaves exactly one younger group
+        // in flight (none for the records of the terminal stage)
+        if constexpr (kFacDouble) {
+            fac_issue(0, 0);
+            cp_commit();
+            tt_issue(0);
+            cp_commit();
+        }
         for (int k = 0; k <= NN(); ++k) {
             if (k < NN()) {
-                copy_block(sM, ws + oFAC() + k * FSTRIDE(), nz * ldf);
                 const T* F = sM;
                 const T* Wk = ws + oWF() + k * nu;
-                __syncwarp();
+                if constexpr (kFacDouble) {
+                    cp_wait<1>();
+                    fac_issue(k + 1, (k + 1) & 1);
+                    cp_commit();
+                    F = sM + (k & 1) * FSTRIDE();
+                } else {
+                    copy_block(sM, ws + oFAC() + k * FSTRIDE(), nz * ldf);
+                    __syncwarp();
+                }
                 // s = w + Y dx
                 for (int j = lane; j < nu; j += WARP) {
                     T acc = Wk[j];
@@ -1347,29 +1409,30 @@ struct Solver {
                     du[j] = acc;
                 }
                 __syncwarp();
-                if constexpr (kInvL) {
-                    T uj = T(0);
-                    if (lane < nu)
-                        for (int i = lane; i < nu; ++i) uj -= F[i * ldf + lane] * du[i];
+                for (int j = nu - 1; j >= 0; --j) {
+                    const T uj = -du[j] * F[j * ldf + j];
                     __syncwarp();
-                    if (lane < nu) du[lane] = uj;
+                    for (int i = lane; i < j; i += WARP) du[i] += F[j * ldf + i] * uj;
+                    if (lane == 0) du[j] = uj;
                     __syncwarp();
-                } else {
-                    for (int j = nu - 1; j >= 0; --j) {
-                        const T uj = -du[j] * F[j * ldf + j];
-                        __syncwarp();
-                        for (int i = lane; i < j; i += WARP) du[i] += F[j * ldf + i] * uj;
-                        if (lane == 0) du[j] = uj;
-                        __syncwarp();
-                    }
                 }
+            
             } else {
                 for (int j = lane; j < nu; j += WARP) du[j] = T(0);
                 __syncwarp();
             }
             T* Dk = DZk(k);
             for (int i = lane; i < nz; i += WARP) Dk[i] = dst[i];
+            if constexpr (kFacDouble) {
+                if (k == NN()) cp_wait<0>();
+                else cp_wait<1>();
+            }
             stage_side_steps(k, dst, corrector, target_mu, amax);
+            if constexpr (kFacDouble) {
+                __syncwarp();
+                tt_issue(k + 1);
+                cp_commit();
+            }
             if (k < NN()) {
                 if (lane < nq) {
                     const T dt = P.dt;
@@ -1383,6 +1446,7 @@ struct Solver {
                 __syncwarp();
             }
         }
+        if constexpr (kFacDouble) cp_wait<0>();
         return warp_min(amax);
     }
 
@@ -1576,22 +1640,14 @@ struct Solver {
             for (int xcol = 0; xcol < nx; ++xcol) {
                 for (int j = lane; j < nu; j += WARP) col[j] = F[(nu + xcol) * ldf + j];
                 __syncwarp();
-                if constexpr (kInvL) {
-                    T uj = T(0);
-                    if (lane < nu)
-                        for (int i = lane; i < nu; ++i) uj -= F[i * ldf + lane] * col[i];
+                for (int j = nu - 1; j >= 0; --j) {
+                    const T uj = -col[j] * F[j * ldf + j];
                     __syncwarp();
-                    if (lane < nu) col[lane] = uj;
+                    for (int i = lane; i < j; i += WARP) col[i] += F[j * ldf + i] * uj;
+                    if (lane == 0) col[j] = uj;
                     __syncwarp();
-                } else {
-                    for (int j = nu - 1; j >= 0; --j) {
-                        const T uj = -col[j] * F[j * ldf + j];
-                        __syncwarp();
-                        for (int i = lane; i < j; i += WARP) col[i] += F[j * ldf + i] * uj;
-                        if (lane == 0) col[j] = uj;
-                        __syncwarp();
-                    }
                 }
+            
                 for (int j = lane; j < nu; j += WARP) Kout[(k * nu + j) * nx + xcol] = col[j];
                 __syncwarp();
             }
@@ -1769,15 +1825,7 @@ __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const DevProblem<T>
     S.sPv = sm + Lk.sPv;
     S.sSA = sm + Lk.sSA;
     S.sV = sm + Lk.sV;
-    S.sBar = reinterpret_cast<uint64_t*>(sm + Lk.sBar);
-    S.bar_phase[0] = S.bar_phase[1] = S.bar_phase[2] = 0u;
-    if (lane == 0) {
-        mbar_init(S.sBar, 1);
-        mbar_init(S.sBar + 1, 1);
-        mbar_init(S.sBar + 2, 1);
-        mbar_fence_init();
-    }
-    __syncwarp();
+    S.sTT = sm + Lk.sTT;
     S.run(A, b);
 }
 
