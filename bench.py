@@ -27,6 +27,19 @@ METRIC = "MPC solves/sec (9-DoF Thing, 1 object, 20-knot horizon)"
 UNIT = "solves/s"
 
 
+def measured_traffic(config, batch):
+    """DRAM bytes per launch of the solve kernel from the committed `ncu --set full` capture of this round
+    (profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum), or None."""
+    try:
+        with open(ROOT / "profiles" / "traffic.json") as f:
+            t = json.load(f).get(config)
+        if t and int(t.get("batch", -1)) == int(batch):
+            return float(t["dram_bytes_per_launch"]), t.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peaks():
     try:
         with open(ROOT / "MEASURED_PEAKS.json") as f:
@@ -49,7 +62,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -237,14 +250,15 @@ def main():
 
     # end-to-end through the host-buffer C-ABI call (H2D + D2H inside)
     e2e_steps = max(3, min(args.steps, 10))
+    res = None
     for s in range(2):
-        mpc.solve(sets[s]["x0"], sets[s]["target"], sets[s]["body_params"])
+        res = mpc.solve(sets[s]["x0"], sets[s]["target"], sets[s]["body_params"], out=res)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for s in range(e2e_steps):
         b = sets[(args.warmup + s) % nsets]
-        res = mpc.solve(b["x0"], b["target"], b["body_params"])
+        res = mpc.solve(b["x0"], b["target"], b["body_params"], out=res)  # caller-owned output buffers, reused
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -266,8 +280,9 @@ def main():
     mean_iters = float(np.mean(iters))
     flops = workload.algorithmic_flops_per_solve(desc, mean_iters, desc.sqp_iteration) * B
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal CUDA-core FMA peak, TFLOP/s
+    traffic, traffic_src = measured_traffic(args.config, B)
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                 "kernel": "ub::solve_batch_kernel", "kernel_ms": kms, "algorithmic_bytes_per_launch": abytes,
                 "note": "compulsory I/O is ~3.7 KB/solve: the kernel is on-chip (FP32 pipe / shared memory) bound by "
                         "construction (SURVEY.md §8d); fp32 figures below use the algorithmic flop count",

@@ -213,6 +213,36 @@ int ub_eval(ub_problem_t* problem, const char* name, int32_t M, const double* x,
             const double* body_params /*[M,nb,10] or NULL*/, double* out, int32_t out_capacity,
             int32_t* rows_out);
 
+/* Closed-loop rollout settings: the knobs of the simulation loop
+ * upright_cmd/scripts/simulations/mpc_sim.py:118-160 around ControllerManager.step
+ * (upright_control/src/upright_control/manager.py:156-176). */
+typedef struct ub_closed_loop_params {
+    double sim_dt;              /* simulation step (upright_cmd/config/simulation.yaml:7)           */
+    double replan_period;       /* tracking.min_policy_update_time (controller.yaml:33)             */
+    int32_t n_steps;            /* simulation steps to run                                          */
+    int32_t log_stride;         /* keep every log_stride-th step in xs / us (>= 1)                   */
+    int32_t use_feedback;       /* sqp.use_feedback_policy (controller.yaml:60)                     */
+    int32_t cold_start;         /* mpc.cold_start: no warm start between replans                    */
+    int32_t init_sqp_iteration; /* SQP iterations of the first solve (controller.yaml:57)           */
+    int32_t sqp_iteration;      /* SQP iterations of every later solve (controller.yaml:56)         */
+    double kp, kv, ka;          /* tracking gains Kx = [kp I, kv I, ka I] (mpc_sim.py:101-108)      */
+} ub_closed_loop_params_t;
+
+/* Replaces, for B robots at once, the closed loop
+ *     for each simulation step:  xd, u = ctrl_manager.step(t, x);  u_cmd = Kx (xd - x) + u;  integrate
+ * (mpc_sim.py:118-160): replan gate `t >= last_planning_time + replan_period`, warm start from the previous
+ * solution shifted to the new time grid, desired end-effector position interpolated between the waypoints
+ * (reference_trajectory.h:18-47), policy evaluation u_ff(t) + K(t)(x - x_nom(t)) with linear interpolation
+ * (pybindings.cpp:378-381), and the model's own triple integrator as the plant.  Everything stays on the
+ * device between the first upload and the final download.  Host double pointers.
+ *   x0 [B, nx]; target_times [M] increasing; target_pos [B, M, 3]; body_params [B, nb, 10] or NULL
+ *   xs [B, n_log, nx], us [B, n_log, nq] (n_log = ceil(n_steps / log_stride)) or both NULL
+ *   x_final [B, nx] or NULL; *n_replans or NULL; status_counts [B, 4] (solves per UB_STATUS_*) or NULL */
+int ub_closed_loop(ub_problem_t* problem, int32_t B, const double* x0, const double* target_times,
+                   const double* target_pos, int32_t M, const double* body_params,
+                   const ub_closed_loop_params_t* params, double* xs, double* us, double* x_final,
+                   int32_t* n_replans, int32_t* status_counts, uint32_t flags, void* cuda_stream);
+
 /* Runtime options: "sqp_iteration" (init_sqp_iteration vs sqp_iteration,
  * controller.yaml:56-57) and the test aid "stop_after" (0 full solve, 1 stop
  * after the first linearisation, 2 after the first QP). */

@@ -248,3 +248,80 @@ def test_controller_manager_drop_in():
     assert np.abs(g).max() < 0.5                                # balancing residual stays small
     ts, xs, us = mgr.get_mpc_trajectory()
     assert ts.shape == (21,) and xs.shape == (21, 27) and us.shape == (21, 13)
+
+
+def _host_closed_loop(settings, targets, x0, n_steps, sim_dt, body_params=None):
+    """numpy mirror of the device rollout: BatchedControllerManager.step (replan gate, warm-start shift,
+    policy evaluation in manager._RecedingHorizon) + the tracking law and exact triple-integrator plant."""
+    from upright_b200.manager import BatchedControllerManager
+    mgr = BatchedControllerManager(settings, targets, body_params=body_params)
+    nq = settings.dims.robot.q
+    tr = settings.tracking
+    x = np.array(x0, dtype=float)
+    xs, us = [], []
+    for s in range(n_steps):
+        t = sim_dt * s
+        xd, u = mgr.step(t, x)
+        q, v, a = x[:, :nq], x[:, nq:2 * nq], x[:, 2 * nq:]
+        e = xd - x
+        ucmd = tr.kp * e[:, :nq] + tr.kv * e[:, nq:2 * nq] + tr.ka * e[:, 2 * nq:] + u[:, :nq]
+        xs.append(x.copy())
+        us.append(ucmd.copy())
+        h = sim_dt
+        x = np.hstack((q + h * v + 0.5 * h * h * a + h**3 / 6 * ucmd, v + h * a + 0.5 * h * h * ucmd, a + h * ucmd))
+    return np.stack(xs, 1), np.stack(us, 1), x, len(mgr.replanning_times)
+
+
+@pytest.mark.parametrize("feedback", [True, False])
+def test_device_closed_loop_matches_host_manager(feedback):
+    """ub_closed_loop (targets, warm-start shift, policy evaluation, plant on the device) against the
+    host-side numpy mirror of manager.py:156-176 / mpc_sim.py:118-160 driving the same solve kernel."""
+    from upright_b200.manager import BatchedControllerManager
+    from upright_b200.settings import ControllerSettings, TargetTrajectories
+    desc, meta = problem_io.load_fixture("cfg2_thing_demo")
+    cfg = meta["controller_config"]
+    settings = ControllerSettings(config=cfg, x0=np.array(meta["x0"]))
+    settings.sqp.use_feedback_policy = feedback
+    B, sim_dt, n_steps = 5, 0.005, 50
+    rng = np.random.default_rng(3)
+    x0 = np.tile(np.array(meta["x0"], dtype=float), (B, 1))
+    x0[:, :9] += rng.uniform(-0.1, 0.1, (B, 9))
+    probe = BatchedControllerManager(settings, [None] * B)
+    r0 = probe.engine.eval("end_effector_position", x0, np.zeros((B, 13)))
+    quat = np.array([0.0, 0.0, 0.0, 1.0])
+    targets = []
+    for b in range(B):
+        wp = [np.r_[r0[b] + d, quat, 0.0] for d in ([0.0, 0.0, 0.0], [-0.25, 0.5, 0.25], [0.2, -0.3, 0.1])]
+        targets.append(TargetTrajectories([0.0, 0.12, 0.5], wp, [np.zeros(13)] * 3))
+    xs_h, us_h, xf_h, nrep_h = _host_closed_loop(settings, targets, x0, n_steps, sim_dt)
+    mgr = BatchedControllerManager(settings, targets)
+    out = mgr.rollout(x0, n_steps * sim_dt, sim_dt)
+    assert out["n_replans"] == nrep_h and 20 <= nrep_h <= 25   # same double comparisons on both sides
+    assert out["status_counts"].sum() == nrep_h * B and (out["status_counts"][:, 3] == 0).all()
+    assert np.isfinite(out["xs"]).all() and np.isfinite(out["us"]).all()
+    # same fp32 solver on both sides; the only differences are float vs double bookkeeping between replans
+    scale = np.abs(us_h).max()
+    assert np.abs(out["us"] - us_h).max() <= 2e-2 * scale, np.abs(out["us"] - us_h).max() / scale
+    assert np.abs(out["xs"] - xs_h).max() <= 1e-3
+    assert np.abs(out["x_final"] - xf_h).max() <= 1e-3
+    # the robot actually moves toward the waypoint
+    assert np.abs(out["x_final"][:, :9] - x0[:, :9]).max() > 1e-3
+
+
+def test_device_closed_loop_log_stride_and_errors():
+    from upright_b200.engine import BatchedMPC
+    desc, meta = problem_io.load_fixture("cfg2_thing_demo")
+    mpc = BatchedMPC(desc, "f32")
+    x0 = np.tile(np.array(meta["x0"], dtype=float), (3, 1))
+    r0 = mpc.eval("end_effector_position", x0, np.zeros((3, 13)))
+    goal = (r0 + np.array([-0.25, 0.5, 0.25]))[:, None, :]
+    full = mpc.closed_loop(x0, [0.0], goal, 40, 0.005, 0.01)
+    thin = mpc.closed_loop(x0, [0.0], goal, 40, 0.005, 0.01, log_stride=4)
+    assert thin["xs"].shape == (3, 10, 27) and thin["us"].shape == (3, 10, 9)
+    assert np.array_equal(thin["xs"], full["xs"][:, ::4]) and np.array_equal(thin["x_final"], full["x_final"])
+    nolog = mpc.closed_loop(x0, [0.0], goal, 40, 0.005, 0.01, log=False)
+    assert nolog["xs"] is None and np.array_equal(nolog["x_final"], full["x_final"])
+    with pytest.raises(RuntimeError):
+        mpc.closed_loop(x0, [0.0, 0.0], np.repeat(goal, 2, axis=1), 10, 0.005, 0.01)   # times must increase
+    with pytest.raises(RuntimeError):
+        mpc.closed_loop(x0, [0.0], goal, 0, 0.005, 0.01)

@@ -51,6 +51,14 @@ class SlackSettings(C.Structure):
                 ("lower_L2_penalty", C.c_double)]
 
 
+class ClosedLoopParams(C.Structure):
+    """ub_closed_loop_params_t"""
+    _fields_ = [("sim_dt", C.c_double), ("replan_period", C.c_double), ("n_steps", C.c_int32),
+                ("log_stride", C.c_int32), ("use_feedback", C.c_int32), ("cold_start", C.c_int32),
+                ("init_sqp_iteration", C.c_int32), ("sqp_iteration", C.c_int32),
+                ("kp", C.c_double), ("kv", C.c_double), ("ka", C.c_double)]
+
+
 class ProblemDesc(C.Structure):
     _fields_ = [
         ("nq", C.c_int32), ("nb", C.c_int32), ("nc", C.c_int32), ("nf", C.c_int32),
@@ -142,6 +150,9 @@ def load_library():
     lib.ub_eval.argtypes = [vp, C.c_char_p, C.c_int32, vp, vp, vp, vp, vp, C.c_int32,
                             C.POINTER(C.c_int32)]
     lib.ub_eval.restype = C.c_int
+    lib.ub_closed_loop.argtypes = [vp, C.c_int32, vp, vp, vp, C.c_int32, vp, C.POINTER(ClosedLoopParams), vp, vp, vp,
+                                   C.POINTER(C.c_int32), vp, C.c_uint32, vp]
+    lib.ub_closed_loop.restype = C.c_int
     lib.ub_last_solve_ms.argtypes = [vp]
     lib.ub_last_solve_ms.restype = C.c_float
     lib.ub_launch_count.restype = C.c_int64
@@ -152,7 +163,7 @@ def load_library():
 EXPORTED_SYMBOLS = [
     "ub_last_error", "ub_version", "ub_problem_create", "ub_problem_destroy",
     "ub_problem_dims", "ub_workspace_bytes", "ub_solve_batch", "ub_eval",
-    "ub_last_solve_ms", "ub_launch_count", "ub_set_option", "ub_workspace_layout",
+    "ub_last_solve_ms", "ub_launch_count", "ub_set_option", "ub_workspace_layout", "ub_closed_loop",
 ]
 
 

@@ -3,15 +3,21 @@
 // UB_E_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ub_launch.cuh"
+#include "ub_receding.cuh"
+
+extern "C" int ub_set_option(ub_problem_t* p, const char* key, int value);
 
 namespace {
 
@@ -28,6 +34,42 @@ int fail(int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                          \
             return fail(UB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
     } while (0)
+
+// Host-side conversion between the caller's double arrays and the pinned staging buffer, split over a few
+// threads (the D2H side of a 4096-instance batch is 3.4 M values; one thread would cost as much as a third of
+// the solve kernel).
+int conversion_threads() {
+    static const int n = [] {
+        const char* env = std::getenv("UB_HOST_THREADS");
+        int v = env ? std::atoi(env) : int(std::thread::hardware_concurrency());
+        return std::max(1, std::min(v, 16));
+    }();
+    return n;
+}
+template <typename Fn>
+void parallel_chunks(size_t n, Fn fn) {
+    const size_t min_chunk = 1 << 16;
+    int nt = int(std::min<size_t>(conversion_threads(), (n + min_chunk - 1) / min_chunk));
+    if (nt <= 1) {
+        fn(size_t(0), n);
+        return;
+    }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    const size_t per = (n + nt - 1) / nt;
+    for (int t = 1; t < nt; ++t) {
+        const size_t a = std::min(n, per * t), b = std::min(n, per * (t + 1));
+        th.emplace_back([=] { fn(a, b); });
+    }
+    fn(size_t(0), std::min(n, per));
+    for (auto& t : th) t.join();
+}
+template <typename Dst, typename Src>
+void convert_array(Dst* dst, const Src* src, size_t n) {
+    parallel_chunks(n, [=](size_t a, size_t b) {
+        for (size_t i = a; i < b; ++i) dst[i] = Dst(src[i]);
+    });
+}
 
 template <typename T>
 void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
@@ -217,7 +259,8 @@ int launch_solve(ub_problem* p, const ub::BatchArgs<T>& A, cudaStream_t stream) 
 
 template <typename T>
 int solve_device(ub_problem* p, int B, const void* x0, const void* target, const void* body, void* X, void* U, void* K,
-                 int32_t* status, void* stats, void* ws, int64_t ws_bytes, uint32_t flags, cudaStream_t stream) {
+                 int32_t* status, void* stats, void* ws, int64_t ws_bytes, uint32_t flags, cudaStream_t stream,
+                 int gain_stages = -1) {
     const ub::Layout& L = Pick<T>::layout(p);
     if (ws_bytes < int64_t(B) * L.total * int64_t(sizeof(T))) return fail(UB_E_INVALID, "workspace too small");
     if (reinterpret_cast<uintptr_t>(ws) % 16 != 0) return fail(UB_E_INVALID, "workspace must be 16-byte aligned");
@@ -234,6 +277,7 @@ int solve_device(ub_problem* p, int B, const void* x0, const void* target, const
     A.B = B;
     A.warm = (flags & UB_WARM_START) ? 1 : 0;
     A.stop_after = p->stop_after;
+    A.gain_stages = gain_stages < 0 ? Pick<T>::host(p).N : gain_stages;
     UB_CUDA(cudaEventRecord(p->ev0, stream));
     int rc = launch_solve<T>(p, A, stream);
     if (rc != UB_OK) return rc;
@@ -274,16 +318,16 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
     T* d = static_cast<T*>(p->dev_buf);
     // staging order: x0 | target | body | X | U | K | stats   (device adds workspace, status)
     size_t o = 0;
-    for (size_t i = 0; i < n_x0; ++i) h[o + i] = T(x0[i]);
+    convert_array(h + o, x0, n_x0);
     o += n_x0;
-    for (size_t i = 0; i < n_tg; ++i) h[o + i] = T(target[i]);
+    convert_array(h + o, target, n_tg);
     o += n_tg;
-    for (size_t i = 0; i < n_bd; ++i) h[o + i] = T(body[i]);
+    if (n_bd) convert_array(h + o, body, n_bd);
     o += n_bd;
     const size_t oX = o;
     if (flags & UB_WARM_START) {
-        for (size_t i = 0; i < n_X; ++i) h[oX + i] = T(X[i]);
-        for (size_t i = 0; i < n_U; ++i) h[oX + n_X + i] = T(U[i]);
+        convert_array(h + oX, X, n_X);
+        convert_array(h + oX + n_X, U, n_U);
         UB_CUDA(cudaMemcpyAsync(d, h, (n_in + n_io) * sizeof(T), cudaMemcpyHostToDevice, stream));
     } else {
         UB_CUDA(cudaMemcpyAsync(d, h, n_in * sizeof(T), cudaMemcpyHostToDevice, stream));
@@ -305,12 +349,145 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
     UB_CUDA(cudaMemcpyAsync(h + oX, d_X, (n_io + n_K + n_st) * sizeof(T), cudaMemcpyDeviceToHost, stream));
     UB_CUDA(cudaMemcpyAsync(h_status, d_status, size_t(B) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     UB_CUDA(cudaStreamSynchronize(stream));
-    for (size_t i = 0; i < n_X; ++i) X[i] = double(h[oX + i]);
-    for (size_t i = 0; i < n_U; ++i) U[i] = double(h[oX + n_X + i]);
-    for (size_t i = 0; i < n_K; ++i) K[i] = double(h[oX + n_io + i]);
-    if (stats)
-        for (size_t i = 0; i < n_st; ++i) stats[i] = double(h[oX + n_io + n_K + i]);
+    convert_array(X, h + oX, n_X);
+    convert_array(U, h + oX + n_X, n_U);
+    if (n_K) convert_array(K, h + oX + n_io, n_K);
+    if (stats) convert_array(stats, h + oX + n_io + n_K, n_st);
     std::memcpy(status, h_status, size_t(B) * sizeof(int32_t));
+    return UB_OK;
+}
+
+
+// Closed-loop rollout of B instances on the device (ub_closed_loop): the host keeps only the replan gate of
+// ControllerManager.step (manager.py:156-170) — time comparisons in double exactly as there — and enqueues
+// {knot targets, warm-start shift, solve} at every replan and one rollout kernel for the simulation steps up
+// to the next replan.
+template <typename T>
+int closed_loop(ub_problem* p, int B, const double* x0, const double* target_times, const double* target_pos, int M,
+                const double* body, const ub_closed_loop_params_t& prm, double* xs, double* us, double* x_final,
+                int32_t* n_replans, int32_t* status_counts, uint32_t flags, cudaStream_t stream) {
+    const ub::DevProblem<T>& P = Pick<T>::host(p);
+    const ub::Layout& L = Pick<T>::layout(p);
+    const int N = P.N, nx = P.nx, nu = P.nu, nq = P.nq;
+    const int stride = std::max(1, prm.log_stride);
+    const int n_log = (xs || us) ? (prm.n_steps + stride - 1) / stride : 0;
+    const int gain_stages = prm.use_feedback ? std::min(N, int(std::floor(prm.replan_period / P.dt + 1e-9)) + 2) : 0;
+    struct Dev {
+        std::vector<void*> ptrs;
+        ~Dev() {
+            for (void* q : ptrs) cudaFree(q);
+        }
+        void* bytes(size_t n) {
+            void* q = nullptr;
+            if (cudaMalloc(&q, std::max<size_t>(n, 16)) != cudaSuccess) return nullptr;
+            ptrs.push_back(q);
+            return q;
+        }
+    } dev;
+    const size_t nX = size_t(B) * (N + 1) * nx, nU = size_t(B) * N * nu;
+    T* d_x = static_cast<T*>(dev.bytes((size_t(B) * nx) * sizeof(T)));
+    T* d_pos = static_cast<T*>(dev.bytes((size_t(B) * M * 3) * sizeof(T)));
+    double* d_times = static_cast<double*>(dev.bytes((M) * sizeof(double)));
+    T* d_body = body ? static_cast<T*>(dev.bytes((size_t(B) * P.nb * UB_BODY_PARAMS) * sizeof(T))) : nullptr;
+    T* d_target = static_cast<T*>(dev.bytes((size_t(B) * (N + 1) * 3) * sizeof(T)));
+    T* d_X[2] = {static_cast<T*>(dev.bytes((nX) * sizeof(T))), static_cast<T*>(dev.bytes((nX) * sizeof(T)))};
+    T* d_U[2] = {static_cast<T*>(dev.bytes((nU) * sizeof(T))), static_cast<T*>(dev.bytes((nU) * sizeof(T)))};
+    T* d_K = gain_stages ? static_cast<T*>(dev.bytes((size_t(B) * gain_stages * nu * nx) * sizeof(T))) : nullptr;
+    T* d_stats = static_cast<T*>(dev.bytes((size_t(B) * UB_STATS) * sizeof(T)));
+    int32_t* d_status = static_cast<int32_t*>(dev.bytes((B) * sizeof(int32_t)));
+    int32_t* d_counts = static_cast<int32_t*>(dev.bytes((size_t(B) * 4) * sizeof(int32_t)));
+    T* d_ws = static_cast<T*>(dev.bytes((size_t(B) * L.total + 8) * sizeof(T)));
+    T* d_xs = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nx) * sizeof(T))) : nullptr;
+    T* d_us = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nq) * sizeof(T))) : nullptr;
+    if (!d_x || !d_pos || !d_times || (body && !d_body) || !d_target || !d_X[0] || !d_X[1] || !d_U[0] || !d_U[1] ||
+        (gain_stages && !d_K) || !d_stats || !d_status || !d_counts || !d_ws || (n_log && (!d_xs || !d_us)))
+        return fail(UB_E_ALLOC, "cudaMalloc failed for the closed-loop buffers");
+    while (reinterpret_cast<uintptr_t>(d_ws) % 16 != 0) ++d_ws;
+    {
+        std::vector<T> h(std::max(std::max(size_t(B) * nx, size_t(B) * M * 3), body ? size_t(B) * P.nb * UB_BODY_PARAMS : size_t(0)));
+        convert_array(h.data(), x0, size_t(B) * nx);
+        UB_CUDA(cudaMemcpyAsync(d_x, h.data(), size_t(B) * nx * sizeof(T), cudaMemcpyHostToDevice, stream));
+        UB_CUDA(cudaStreamSynchronize(stream));
+        convert_array(h.data(), target_pos, size_t(B) * M * 3);
+        UB_CUDA(cudaMemcpyAsync(d_pos, h.data(), size_t(B) * M * 3 * sizeof(T), cudaMemcpyHostToDevice, stream));
+        UB_CUDA(cudaStreamSynchronize(stream));
+        if (body) {
+            convert_array(h.data(), body, size_t(B) * P.nb * UB_BODY_PARAMS);
+            UB_CUDA(cudaMemcpyAsync(d_body, h.data(), size_t(B) * P.nb * UB_BODY_PARAMS * sizeof(T), cudaMemcpyHostToDevice, stream));
+            UB_CUDA(cudaStreamSynchronize(stream));
+        }
+        UB_CUDA(cudaMemcpyAsync(d_times, target_times, size_t(M) * sizeof(double), cudaMemcpyHostToDevice, stream));
+        UB_CUDA(cudaMemsetAsync(d_counts, 0, size_t(B) * 4 * sizeof(int32_t), stream));
+    }
+    const int saved_sqp = Pick<T>::host(p).sqp_iters;
+    auto set_sqp = [&](int iters) -> int {
+        if (Pick<T>::host(p).sqp_iters == std::max(1, iters)) return UB_OK;
+        UB_CUDA(cudaStreamSynchronize(stream));  // the constants are re-uploaded: nothing may be in flight
+        return ub_set_option(p, "sqp_iteration", std::max(1, iters));
+    };
+    int cur = 0, replans = 0, rc = UB_OK;
+    bool have_plan = false;
+    double last_plan = -INFINITY, t0 = 0.0;
+    int step = 0;
+    while (step < prm.n_steps) {
+        const double t = prm.sim_dt * step;
+        if (t >= last_plan + prm.replan_period) {
+            const bool warm = have_plan && !prm.cold_start;
+            const int iters = have_plan ? prm.sqp_iteration : prm.init_sqp_iteration;
+            if ((rc = set_sqp(iters)) != UB_OK) break;
+            ub::rh_targets_kernel<T><<<(B * (N + 1) + 255) / 256, 256, 0, stream>>>(B, N, double(P.dt), t, d_times, M, d_pos, d_target);
+            ++g_launches;
+            if (warm) {
+                const size_t tot = nX + nU;
+                ub::rh_shift_kernel<T><<<unsigned((tot + 255) / 256), 256, 0, stream>>>(B, N, nx, nu, double(P.dt), t0, t, d_X[cur],
+                                                                                   d_U[cur], d_X[cur ^ 1], d_U[cur ^ 1]);
+                ++g_launches;
+                cur ^= 1;
+            }
+            rc = solve_device<T>(p, B, d_x, d_target, d_body, d_X[cur], d_U[cur], d_K, d_status, d_stats, d_ws,
+                                 int64_t(size_t(B) * L.total * sizeof(T)), (flags & UB_COMPUTE_F64) | UB_PTRS_DEVICE |
+                                 (warm ? UB_WARM_START : 0u), stream, gain_stages);
+            if (rc != UB_OK) break;
+            ub::rh_count_status_kernel<<<(B + 255) / 256, 256, 0, stream>>>(B, d_status, d_counts);
+            ++g_launches;
+            have_plan = true;
+            last_plan = t;
+            t0 = t;
+            ++replans;
+        }
+        // simulation steps until the next replan is due (same comparison as above)
+        int n_sub = 1;
+        while (step + n_sub < prm.n_steps && !(prm.sim_dt * (step + n_sub) >= last_plan + prm.replan_period)) ++n_sub;
+        ub::RolloutArgs<T> R;
+        R.B = B; R.N = N; R.nq = nq; R.nx = nx; R.nu = nu;
+        R.dt = double(P.dt); R.t0 = t0; R.t_first = t; R.sim_dt = prm.sim_dt;
+        R.n_sub = n_sub; R.step0 = step; R.log_stride = stride; R.n_log = n_log;
+        R.use_feedback = prm.use_feedback; R.gain_stages = gain_stages;
+        R.kp = T(prm.kp); R.kv = T(prm.kv); R.ka = T(prm.ka);
+        R.X = d_X[cur]; R.U = d_U[cur]; R.K = d_K; R.x = d_x; R.xs = d_xs; R.us = d_us;
+        ub::rh_rollout_kernel<T><<<(B * 32 + 127) / 128, 128, 0, stream>>>(R);
+        ++g_launches;
+        UB_CUDA(cudaGetLastError());
+        step += n_sub;
+    }
+    {
+        const int rc2 = set_sqp(saved_sqp);
+        if (rc == UB_OK) rc = rc2;
+    }
+    if (rc != UB_OK) return rc;
+    UB_CUDA(cudaStreamSynchronize(stream));
+    auto fetch = [&](double* dst, const T* src, size_t n) -> int {
+        if (!dst || !n) return UB_OK;
+        std::vector<T> h(n);
+        UB_CUDA(cudaMemcpy(h.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost));
+        convert_array(dst, h.data(), n);
+        return UB_OK;
+    };
+    if ((rc = fetch(xs, d_xs, size_t(B) * n_log * nx)) != UB_OK) return rc;
+    if ((rc = fetch(us, d_us, size_t(B) * n_log * nq)) != UB_OK) return rc;
+    if ((rc = fetch(x_final, d_x, size_t(B) * nx)) != UB_OK) return rc;
+    if (status_counts) UB_CUDA(cudaMemcpy(status_counts, d_counts, size_t(B) * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (n_replans) *n_replans = replans;
     return UB_OK;
 }
 
@@ -430,6 +607,25 @@ int ub_solve_batch(ub_problem_t* p, int32_t B, const void* x0, const void* targe
                                    static_cast<const double*>(body_params), static_cast<double*>(X),
                                    static_cast<double*>(U), static_cast<double*>(K), status,
                                    static_cast<double*>(stats), flags, stream);
+}
+
+int ub_closed_loop(ub_problem_t* p, int32_t B, const double* x0, const double* target_times, const double* target_pos,
+                   int32_t M, const double* body_params, const ub_closed_loop_params_t* params, double* xs, double* us,
+                   double* x_final, int32_t* n_replans, int32_t* status_counts, uint32_t flags, void* cuda_stream) {
+    if (!p || !x0 || !target_times || !target_pos || !params) return fail(UB_E_INVALID, "null argument");
+    if (B <= 0 || M <= 0) return fail(UB_E_INVALID, "B and M must be positive");
+    if (!(params->sim_dt > 0) || !(params->replan_period > 0) || params->n_steps <= 0)
+        return fail(UB_E_INVALID, "sim_dt, replan_period and n_steps must be positive");
+    if ((xs == nullptr) != (us == nullptr)) return fail(UB_E_INVALID, "xs and us are logged together");
+    for (int i = 1; i < M; ++i)
+        if (!(target_times[i] > target_times[i - 1])) return fail(UB_E_INVALID, "target times must increase");
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    UB_CUDA(cudaSetDevice(p->device));
+    return (flags & UB_COMPUTE_F64)
+               ? closed_loop<double>(p, B, x0, target_times, target_pos, M, body_params, *params, xs, us, x_final,
+                                     n_replans, status_counts, flags, stream)
+               : closed_loop<float>(p, B, x0, target_times, target_pos, M, body_params, *params, xs, us, x_final,
+                                    n_replans, status_counts, flags, stream);
 }
 
 float ub_last_solve_ms(const ub_problem_t* p) {

@@ -89,6 +89,7 @@ struct BatchArgs {
     int B;
     int warm;
     int stop_after;   // debug: 0 = full solve, 1 = stop after first linearisation, 2 = after first QP
+    int gain_stages;  // K holds the gains of stages [0, gain_stages) only: [B, gain_stages, nu, nx]
 };
 
 
@@ -1629,11 +1630,11 @@ struct Solver {
     }
 
     // Feedback gains K_k = -Huu^{-1} Hux from the stored factors (optional output).
-    __device__ void write_gains(T* Kout) {
+    __device__ void write_gains(T* Kout, int stages) {
         const int nu = NU(), nx = NX(), nz = NZ(), ldf = LDF();
         T* F = sM;
         T* col = sV;
-        for (int k = 0; k < NN(); ++k) {
+        for (int k = 0; k < stages; ++k) {
             const T* Fg = ws + oFAC() + k * FSTRIDE();
             for (int idx = lane; idx < nz * ldf; idx += WARP) F[idx] = Fg[idx];
             __syncwarp();
@@ -1760,7 +1761,8 @@ struct Solver {
             base = pn;
             if ((dxn < P.delta_tol && dun < P.delta_tol) || (dcost < P.cost_tol && base.violation() < P.g_min)) break;
         }
-        if (A.K != nullptr && A.stop_after == 0 && status != UB_STATUS_NAN) write_gains(A.K + size_t(b) * N * nu * nx);
+        if (A.K != nullptr && A.stop_after == 0 && status != UB_STATUS_NAN)
+            write_gains(A.K + size_t(b) * A.gain_stages * nu * nx, A.gain_stages);
         // NaN guard
         T bad = 0;
         for (int idx = lane; idx < (N + 1) * nx; idx += WARP) bad += isfinite(X[idx]) ? T(0) : T(1);

@@ -52,30 +52,47 @@ class BatchedMPC:
             pass
 
     # ------------------------------------------------------------- host path
-    def solve(self, x0, target, body_params=None, X=None, U=None, warm=False, want_gains=False):
-        """numpy float64 host buffers; returns dict(X, U, status, stats[, K])."""
+    def solve(self, x0, target, body_params=None, X=None, U=None, warm=False, want_gains=False, out=None):
+        """numpy float64 host buffers; returns dict(X, U, status, stats[, K]).
+
+        `out`: a dict returned by an earlier call with the same batch size — its arrays are overwritten and
+        returned again (what a C caller does with its own buffers; saves the page faults of fresh arrays)."""
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
         Bn = x0.shape[0]
         assert x0.shape == (Bn, self.nx)
         target = np.ascontiguousarray(np.asarray(target, dtype=np.float64).reshape(Bn, self.N + 1, 3))
         if body_params is not None:
             body_params = np.ascontiguousarray(body_params, dtype=np.float64).reshape(Bn, self.nb, 10)
+        reuse = out is not None and out["X"].shape == (Bn, self.N + 1, self.nx) and (("K" in out) == bool(want_gains))
         if warm:
-            X = np.ascontiguousarray(X, dtype=np.float64).reshape(Bn, self.N + 1, self.nx).copy()
-            U = np.ascontiguousarray(U, dtype=np.float64).reshape(Bn, self.N, self.nu).copy()
+            Xw = np.ascontiguousarray(X, dtype=np.float64).reshape(Bn, self.N + 1, self.nx)
+            Uw = np.ascontiguousarray(U, dtype=np.float64).reshape(Bn, self.N, self.nu)
+            if reuse:
+                X, U = out["X"], out["U"]
+                if X is not Xw:
+                    X[...] = Xw
+                if U is not Uw:
+                    U[...] = Uw
+            else:
+                X, U = Xw.copy(), Uw.copy()
+        elif reuse:
+            X, U = out["X"], out["U"]
         else:
-            X = np.zeros((Bn, self.N + 1, self.nx))
-            U = np.zeros((Bn, self.N, self.nu))
-        K = np.zeros((Bn, self.N, self.nu, self.nx)) if want_gains else None
-        status = np.zeros(Bn, dtype=np.int32)
-        stats = np.zeros((Bn, B.UB_STATS))
+            X = np.empty((Bn, self.N + 1, self.nx))
+            U = np.empty((Bn, self.N, self.nu))
+        if reuse:
+            K, status, stats = out.get("K"), out["status"], out["stats"]
+        else:
+            K = np.empty((Bn, self.N, self.nu, self.nx)) if want_gains else None
+            status = np.empty(Bn, dtype=np.int32)
+            stats = np.empty((Bn, B.UB_STATS))
         flags = self.flags | (B.UB_WARM_START if warm else 0)
         B.check(self.lib.ub_solve_batch(self.handle, Bn, _ptr(x0), _ptr(target), _ptr(body_params), _ptr(X), _ptr(U),
                                         _ptr(K), _ptr(status), _ptr(stats), None, 0, flags, None))
-        out = dict(X=X, U=U, status=status, stats=stats)
+        res = dict(X=X, U=U, status=status, stats=stats)
         if want_gains:
-            out["K"] = K
-        return out
+            res["K"] = K
+        return res
 
     # ----------------------------------------------------------- device path
     @property
@@ -111,6 +128,35 @@ class BatchedMPC:
         B.check(self.lib.ub_solve_batch(self.handle, Bn, p(x0), p(target), p(body_params), p(X), p(U), p(K),
                                         p(status), p(stats), p(ws), ws.numel(), flags, C.c_void_p(stream)))
         return dict(X=X, U=U, K=K, status=status, stats=stats)
+
+    # ----------------------------------------------------------- closed loop
+    def closed_loop(self, x0, target_times, target_pos, n_steps, sim_dt, replan_period, body_params=None,
+                    use_feedback=True, cold_start=False, init_sqp_iteration=1, sqp_iteration=1, gains=(0.0, 0.0, 0.0),
+                    log_stride=1, log=True):
+        """B closed-loop rollouts on the device (`ub_closed_loop`): replan gate, warm-start shift, policy
+        evaluation and the triple-integrator plant as in `mpc_sim.py:118-160`.
+
+        x0 [B, nx]; target_times [M]; target_pos [B, M, 3].  Returns dict(xs [B, n_log, nx], us [B, n_log, nq],
+        x_final [B, nx], n_replans, status_counts [B, 4])."""
+        x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
+        Bn = x0.shape[0]
+        tt = np.ascontiguousarray(np.atleast_1d(target_times), dtype=np.float64)
+        M = tt.shape[0]
+        tp = np.ascontiguousarray(np.asarray(target_pos, dtype=np.float64).reshape(Bn, M, 3))
+        bp = None if body_params is None else np.ascontiguousarray(body_params, dtype=np.float64).reshape(Bn, self.nb, 10)
+        prm = B.ClosedLoopParams(float(sim_dt), float(replan_period), int(n_steps), int(log_stride), int(bool(use_feedback)),
+                                 int(bool(cold_start)), int(init_sqp_iteration), int(sqp_iteration), float(gains[0]),
+                                 float(gains[1]), float(gains[2]))
+        nq = self.nx // 3
+        n_log = (int(n_steps) + int(log_stride) - 1) // int(log_stride) if log else 0
+        xs = np.empty((Bn, n_log, self.nx)) if log else None
+        us = np.empty((Bn, n_log, nq)) if log else None
+        xf = np.empty((Bn, self.nx))
+        counts = np.zeros((Bn, 4), dtype=np.int32)
+        nrep = C.c_int32()
+        B.check(self.lib.ub_closed_loop(self.handle, Bn, _ptr(x0), _ptr(tt), _ptr(tp), M, _ptr(bp), C.byref(prm), _ptr(xs),
+                                        _ptr(us), _ptr(xf), C.byref(nrep), _ptr(counts), self.flags, None))
+        return dict(xs=xs, us=us, x_final=xf, n_replans=int(nrep.value), status_counts=counts)
 
     def last_solve_ms(self):
         return float(self.lib.ub_last_solve_ms(self.handle))

@@ -311,3 +311,22 @@ class BatchedControllerManager:
 
     def get_mpc_trajectory(self):
         return self.core.solution()
+
+    def rollout(self, x0, duration, sim_timestep, log_stride=1, log=True):
+        """Closed loop for `duration` seconds entirely on the device (`ub_closed_loop`): the loop of
+        `mpc_sim.py:118-160` — `step(t, x)`, `u_cmd = Kx (xd - x) + u`, integrate — for all B robots, with the
+        model's triple integrator as the plant.  The waypoint times must be shared by all targets."""
+        tr = self.settings.tracking
+        tt = self.core.targets[0].ts
+        for tg in self.core.targets:
+            if list(tg.ts) != list(tt):
+                raise ValueError("rollout needs the same waypoint times for every instance")
+        pos = np.array([[x[:3] for x in tg.xs] for tg in self.core.targets])
+        if pos.shape[0] == 1 and self.B > 1:
+            pos = np.repeat(pos, self.B, axis=0)
+        n_steps = int(round(duration / sim_timestep))
+        return self.engine.closed_loop(
+            x0, tt, pos, n_steps, sim_timestep, self.timestep, body_params=self.core.body_params,
+            use_feedback=bool(self.settings.sqp.use_feedback_policy), cold_start=bool(self.settings.mpc.cold_start),
+            init_sqp_iteration=self.settings.sqp.init_sqp_iteration, sqp_iteration=self.settings.sqp.sqp_iteration,
+            gains=(getattr(tr, "kp", 0.0), getattr(tr, "kv", 0.0), getattr(tr, "ka", 0.0)), log_stride=log_stride, log=log)
