@@ -268,6 +268,22 @@ def main():
     h2d = B * (mpc.nx + 3 * (mpc.N + 1) + (mpc.nb * 10 if sets[0]["body_params"] is not None else 0)) * esz
     d2h = B * ((mpc.N + 1) * mpc.nx + mpc.N * mpc.nu + 8) * esz + B * 4
 
+    # receding-horizon closed loop on the device: 0.1 s of simulated time at the reference's
+    # rates (1 kHz plant, 100 Hz replanning, warm starts, Riccati feedback policy); second, informational number
+    closed_loop = None
+    if world == 1:
+        b0 = sets[0]
+        goal = b0["target"][:, :1, :]
+        kw = dict(n_steps=100, sim_dt=0.001, replan_period=0.01, body_params=b0["body_params"], log=False)
+        mpc.closed_loop(b0["x0"], [0.0], goal, **dict(kw, n_steps=20))
+        t0 = time.perf_counter()
+        out = mpc.closed_loop(b0["x0"], [0.0], goal, **kw)
+        el = time.perf_counter() - t0
+        closed_loop = {"warm_solves_per_s": B * out["n_replans"] / el, "sim_steps_per_s": B * kw["n_steps"] / el,
+                       "replans": out["n_replans"], "sim_steps": kw["n_steps"], "wall_s": el,
+                       "status_counts": out["status_counts"].sum(axis=0).tolist(),
+                       "api": "BatchedMPC.closed_loop -> ub_closed_loop (host x0 in, final state out, everything else on the device)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -298,6 +314,8 @@ def main():
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "roofline": roofline,
             "converged_fraction": float(np.mean(ok)), "mean_qp_iterations": mean_iters}
+    if closed_loop is not None:
+        line["closed_loop"] = closed_loop
     if cpu_rate is not None:
         line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{cpu_n} instances of the same workload in {cpu_el:.1f} s, oracle-CPU "
