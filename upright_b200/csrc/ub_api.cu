@@ -169,7 +169,7 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
 
 template <typename T>
 ub::Layout make_layout(const ub::DevProblem<T>& P) {
-    return ub::compute_layout(ub::LayoutDims{P.N, P.nq, P.nx, P.nu, P.neq, P.nfc, P.nterm, P.nrow, P.nobs, int(sizeof(T))});
+    return ub::compute_layout(ub::LayoutDims{P.N, P.nq, P.nx, P.nu, P.neq, P.nfc, P.nterm, P.nrow, P.nobs, P.nb, int(sizeof(T))});
 }
 
 }  // namespace
@@ -252,7 +252,7 @@ int launch_solve(ub_problem* p, const ub::BatchArgs<T>& A, cudaStream_t stream) 
         if (H.nq == 9 && H.nf == 3 && H.nc == 16 && H.nb == 3 && no_obs) fn = Pick<T>::thing_arch();
         if (H.nq == 9 && H.nf == 1 && H.nc == 32 && H.nb == 8 && no_obs) fn = Pick<T>::thing_robust8();
     }
-    UB_CUDA(fn(Pick<T>::dev(p), L, A, wpc, grid, smem, stream));
+    UB_CUDA(fn(H, Pick<T>::dev(p), L, A, wpc, grid, smem, stream));
     ++g_launches;
     return UB_OK;
 }

@@ -8,28 +8,28 @@
 namespace ub {
 
 template <typename T>
-using LaunchFn = cudaError_t (*)(const DevProblem<T>*, const Layout&, const BatchArgs<T>&, int warps_per_cta, int grid,
-                                 size_t smem, cudaStream_t);
+using LaunchFn = cudaError_t (*)(const DevProblem<T>& host_copy, const DevProblem<T>* device_copy, const Layout&,
+                                 const BatchArgs<T>&, int warps_per_cta, int grid, size_t smem, cudaStream_t);
 
 template <typename T, typename D>
-cudaError_t launch_solve_kernel(const DevProblem<T>* Pg, const Layout& L, const BatchArgs<T>& A, int wpc, int grid, size_t smem,
-                                cudaStream_t stream) {
+cudaError_t launch_solve_kernel(const DevProblem<T>& Ph, const DevProblem<T>* Pg, const Layout& L, const BatchArgs<T>& A, int wpc,
+                                int grid, size_t smem, cudaStream_t stream) {
     auto kernel = solve_batch_kernel<T, D>;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
-    kernel<<<grid, wpc * 32, smem, stream>>>(Pg, L, A, wpc);
+    kernel<<<grid, wpc * 32, smem, stream>>>(Ph, Pg, L, A, wpc);
     return cudaGetLastError();
 }
 
 #define UB_DECLARE_LAUNCHER(NAME)                                                                                       \
-    cudaError_t launch_##NAME##_f32(const DevProblem<float>*, const Layout&, const BatchArgs<float>&, int, int, size_t,  \
-                                    cudaStream_t);                                                                      \
-    cudaError_t launch_##NAME##_f64(const DevProblem<double>*, const Layout&, const BatchArgs<double>&, int, int, size_t, \
-                                    cudaStream_t);
+    cudaError_t launch_##NAME##_f32(const DevProblem<float>&, const DevProblem<float>*, const Layout&,                  \
+                                    const BatchArgs<float>&, int, int, size_t, cudaStream_t);                           \
+    cudaError_t launch_##NAME##_f64(const DevProblem<double>&, const DevProblem<double>*, const Layout&,                \
+                                    const BatchArgs<double>&, int, int, size_t, cudaStream_t);
 #define UB_DEFINE_LAUNCHER(NAME, T, SUFFIX, ...)                                                                        \
-    cudaError_t launch_##NAME##_##SUFFIX(const DevProblem<T>* Pg, const Layout& L, const BatchArgs<T>& A, int wpc, int grid, \
-                                         size_t smem, cudaStream_t stream) {                                            \
-        return launch_solve_kernel<T, __VA_ARGS__>(Pg, L, A, wpc, grid, smem, stream);                                 \
+    cudaError_t launch_##NAME##_##SUFFIX(const DevProblem<T>& Ph, const DevProblem<T>* Pg, const Layout& L,             \
+                                         const BatchArgs<T>& A, int wpc, int grid, size_t smem, cudaStream_t stream) {  \
+        return launch_solve_kernel<T, __VA_ARGS__>(Ph, Pg, L, A, wpc, grid, smem, stream);                             \
     }
 
 UB_DECLARE_LAUNCHER(generic)

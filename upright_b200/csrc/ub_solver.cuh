@@ -23,23 +23,24 @@ namespace ub {
 // ub_api.cu) and the kernels specialised on compile-time dimensions, where every offset becomes an
 // immediate of the load/store instruction.
 struct Layout {
-    int Z, DZ, GAP, LG, LCT, LR, LJP, LHO, LJO, DF, RHOE, YE, RHOT, YT, TT, LAM, DTT, DLAM, sTT, FAC, WF, XN, UN;
+    int Z, DZ, GAP, LG, LCT, LR, LJP, LHO, LJO, DF, RHOE, YE, RHOT, YT, TT, LAM, XW, UW, sTT, FAC, WF, XN, UN;
     int total;
     // shared memory (units of T, per warp)
-    int sM, sP, sPv, sSA, sV, s_total, ldm, ldf;
+    int sM, sP, sPv, sSA, sV, s_total;
+    // instance-local copies of the desired positions [N+1, 3] and the body parameters [nb, 10]
+    int TG, BD;
 };
 // side records of a stage are staged in shared memory (cp.async, one stage ahead) up to this many rows
 #define UB_STAGE_ROWS_MAX 64
 struct LayoutDims {
-    int N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, tsize;
+    int N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, nb, tsize;
 };
 __host__ __device__ constexpr int ub_round4(int n) { return (n + 3) / 4 * 4; }
 __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     Layout L{};
     const int N = d.N, nx = d.nx, nu = d.nu, nz = d.nu + d.nx, nq = d.nq;
     int o = 0;
-    L.ldm = nz | 1;
-    L.ldf = nu | 1;
+    const int ldm = nz | 1, ldf = nu | 1;
     L.Z = o;    o += ub_round4((N + 1) * nz);
     L.DZ = o;   o += ub_round4((N + 1) * nz);
     L.GAP = o;  o += ub_round4(N * nx);
@@ -56,16 +57,20 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.YT = o;   o += ub_round4(d.nterm);
     L.TT = o;   o += ub_round4((N + 1) * d.nrow * 8);  // interleaved side records {t, lam, dt, dlam} x {lo, hi}
     L.LAM = o;  o += ub_round4((N + 1) * nz);          // GP: predictor stage gradients kept for the corrector
-    L.DTT = L.TT;
-    L.DLAM = L.TT;
-    const int fstride = (nz * L.ldf + 3) & ~3;
+    const int fstride = (nz * ldf + 3) & ~3;
     L.FAC = o;  o += ub_round4(N * fstride);
     L.WF = o;   o += ub_round4(N * nu);
     L.XN = o;   o += ub_round4((N + 1) * nx);
     L.UN = o;   o += ub_round4(N * nu);
+    // the iterate, the desired positions and the body parameters live in the instance workspace too, so that
+    // the solve needs ONE per-instance base address (the batch arrays are touched at entry and exit only)
+    L.XW = o;   o += ub_round4((N + 1) * nx);
+    L.UW = o;   o += ub_round4(N * nu);
+    L.TG = o;   o += ub_round4((N + 1) * 3);
+    L.BD = o;   o += ub_round4((d.nb > 0 ? d.nb : 1) * 10);
     L.total = o;
     int s = 0;
-    L.sM = s;   s += ub_round4(nz * L.ldm > fstride ? nz * L.ldm : fstride);
+    L.sM = s;   s += ub_round4(nz * ldm > fstride ? nz * ldm : fstride);
     L.sP = s;   s += ub_round4(nx * nx);
     L.sPv = s;  s += ub_round4(nx);
     L.sSA = s;  s += ub_round4((d.neq > 3 ? d.neq : 3) * nz);
@@ -115,7 +120,7 @@ struct StaticDims {
     static constexpr int nterm = 3 + 2 * NQ_, nrow = nbox_u + nx + nfric + NOBS_;
     template <typename T>
     __host__ __device__ static constexpr Layout layout() {
-        return compute_layout(LayoutDims{N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, int(sizeof(T))});
+        return compute_layout(LayoutDims{N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, nb, int(sizeof(T))});
     }
 };
 struct RuntimeDims {
@@ -128,7 +133,8 @@ struct RuntimeDims {
 
 template <typename T, typename D>
 struct Solver {
-    const DevProblem<T>& P;
+    const DevProblem<T>& P;   // shared-memory copy: arrays indexed per lane
+    const DevProblem<T>& C;   // kernel-parameter copy (constant bank): scalars and uniformly indexed entries
     const Layout& L;
     const int lane;
 #define UB_DIM(FN, name) \
@@ -141,6 +147,7 @@ struct Solver {
     __device__ __forceinline__ int o##name() const { if constexpr (D::kStatic) { constexpr Layout l = D::template layout<T>(); return l.name; } else return L.name; }
     UB_OFF(Z) UB_OFF(DZ) UB_OFF(GAP) UB_OFF(LG) UB_OFF(LCT) UB_OFF(LR) UB_OFF(LJP) UB_OFF(LHO) UB_OFF(LJO) UB_OFF(DF)
     UB_OFF(RHOE) UB_OFF(YE) UB_OFF(RHOT) UB_OFF(YT) UB_OFF(TT) UB_OFF(LAM) UB_OFF(FAC) UB_OFF(WF) UB_OFF(XN) UB_OFF(UN)
+    UB_OFF(XW) UB_OFF(UW) UB_OFF(TG) UB_OFF(BD)
 #undef UB_OFF
     __device__ __forceinline__ int LDM() const { return NZ() | 1; }
     __device__ __forceinline__ int LDF() const { return NU() | 1; }
@@ -148,12 +155,11 @@ struct Solver {
     __device__ __forceinline__ int NTERM() const { return 3 + 2 * NQ(); }
     __device__ __forceinline__ int FSTRIDE() const { return (NZ() * LDF() + 3) & ~3; }  // 16-byte aligned factor blocks
     // batch data of this instance
-    const T* x0;
-    const T* target;
-    const T* body;
+    T* ws;   // the one per-instance base address; X, U, target, body are instance-local blocks of it
     T* X;
     T* U;
-    T* ws;
+    const T* target;
+    const T* body;
     // shared memory of this warp
     T* sM;
     T* sP;
@@ -164,7 +170,8 @@ struct Solver {
     long long t_lin = 0, t_fac = 0, t_swp = 0, t_side = 0, t_ls = 0, t_res = 0;
     long long t_f1 = 0, t_f2 = 0, t_f3 = 0, t_f4 = 0, t_g = 0;  // finer: build / dynamics / cholesky / store ; gradient  // phase cycle counters (profile mode)
 
-    __device__ Solver(const DevProblem<T>& P_, const Layout& L_, int lane_) : P(P_), L(L_), lane(lane_) {}
+    __device__ Solver(const DevProblem<T>& P_, const DevProblem<T>& C_, const Layout& L_, int lane_)
+        : P(P_), C(C_), L(L_), lane(lane_) {}
 
     // ------------------------------------------------------------ row model
     // Inequality rows of a stage, in this order:
@@ -187,9 +194,9 @@ struct Solver {
         }
     }
     __device__ __forceinline__ bool row_soft(int fam) const {
-        return fam == 0 ? P.soft_u : (fam == 1 ? P.soft_x : P.soft_poly);
+        return fam == 0 ? C.soft_u : (fam == 1 ? C.soft_x : C.soft_poly);
     }
-    __device__ __forceinline__ T row_eps(int fam) const { return row_soft(fam) ? T(1) / P.Z : P.eps_hard; }
+    __device__ __forceinline__ T row_eps(int fam) const { return row_soft(fam) ? T(1) / C.Z : C.eps_hard; }
     // friction row coefficients on the 3 force components of contact c
     __device__ __forceinline__ V3<T> fric_coeff(int c, int which) const {
         const V3<T> n = ld3(P.cn[c]), s0 = ld3(P.cspan[c]), s1 = ld3(P.cspan[c] + 3);
@@ -203,8 +210,8 @@ struct Solver {
         const int nq = NQ(), nu = NU();
         if (fam == 0) {
             const T u = U[k * nu + r];
-            *lb = (r < nq ? P.ulb[r] : P.flb) - u;
-            *ub = (r < nq ? P.uub[r] : P.fub) - u;
+            *lb = (r < nq ? P.ulb[r] : C.flb) - u;
+            *ub = (r < nq ? P.uub[r] : C.fub) - u;
             return zk[r];
         }
         if (fam == 1) {
@@ -414,13 +421,13 @@ struct Solver {
                     const T dist = sqrt(dot(d, d));
                     const V3<T> dd(dsph[3 * a] - dsph[3 * bb], dsph[3 * a + 1] - dsph[3 * bb + 1],
                                    dsph[3 * a + 2] - dsph[3 * bb + 2]);
-                    if (lane == 0) ws[oLHO() + k * NOBS() + i] = dist - (P.srad[a] + P.srad[bb] + P.dmin);
+                    if (lane == 0) ws[oLHO() + k * NOBS() + i] = dist - (P.srad[a] + P.srad[bb] + C.dmin);
                     if (lane < nq) ws[oLJO() + (k * NOBS() + i) * nq + lane] = dot(d, dd) / dist;
                 }
             }
             // dynamics gap b_k = A x_k + B u_k - x_{k+1}  (exact triple integrator, system_dynamics.h:15-26)
             if (k < N && lane < nq) {
-                const T dt = P.dt;
+                const T dt = C.dt;
                 const T* xn = X + (k + 1) * nx;
                 const T q = x[lane], v = x[nq + lane], a = x[2 * nq + lane], j = U[k * nu + lane];
                 T* gap = ws + oGAP() + k * nx;
@@ -436,7 +443,7 @@ struct Solver {
     // Lane k evaluates knot k (values only).  Mirrors orc::performance().
     __device__ Perf<T> performance(const T* Xt, const T* Ut) const {
         const int nq = NQ(), nx = NX(), nu = NU(), N = NN();
-        const T dt = P.dt;
+        const T dt = C.dt;
         const T scale = rsqrt(T(6 * max(NB(), 1)));
         T cost = 0, dyn = 0, eq = 0, ineq = 0, max_eq = 0, min_margin = tinf<T>();
         T sph[3 * UB_MAX_SPHERES];
@@ -472,7 +479,7 @@ struct Solver {
                 c += T(0.5) * P.Qd[i] * e * e;
             }
             for (int i = 0; i < nq; ++i) c += T(0.5) * P.Rd[i] * u[i] * u[i];
-            for (int i = 0; i < NFC(); ++i) c += T(0.5) * P.fw * u[nq + i] * u[nq + i];
+            for (int i = 0; i < NFC(); ++i) c += T(0.5) * C.fw * u[nq + i] * u[nq + i];
             for (int i = 0; i < 3; ++i) {
                 const T e = Kn.r[i] - rd[i];
                 c += T(0.5) * P.Wd[i] * e * e;
@@ -488,7 +495,7 @@ struct Solver {
             }
             const int nbox = NBOXU();
             for (int i = 0; i < nbox; ++i) {
-                const T lo = u[i] - (i < nq ? P.ulb[i] : P.flb), hi = (i < nq ? P.uub[i] : P.fub) - u[i];
+                const T lo = u[i] - (i < nq ? P.ulb[i] : C.flb), hi = (i < nq ? P.uub[i] : C.fub) - u[i];
                 const T a = min(T(0), lo), b = min(T(0), hi);
                 ineq += dt * (a * a + b * b);
                 min_margin = min(min_margin, min(lo, hi));
@@ -518,7 +525,7 @@ struct Solver {
                 for (int i = 0; i < NOBS(); ++i) {
                     const int a = P.pa[i], bb = P.pb[i];
                     const V3<T> d(sph[3 * a] - sph[3 * bb], sph[3 * a + 1] - sph[3 * bb + 1], sph[3 * a + 2] - sph[3 * bb + 2]);
-                    const T h = sqrt(dot(d, d)) - (P.srad[a] + P.srad[bb] + P.dmin);
+                    const T h = sqrt(dot(d, d)) - (P.srad[a] + P.srad[bb] + C.dmin);
                     const T m = min(T(0), h);
                     ineq += dt * m * m;
                     min_margin = min(min_margin, h);
@@ -579,14 +586,14 @@ struct Solver {
             if (ne == 0) continue;
             load_eq_rows(k);
             for (int i = lane; i < ne; i += WARP) {
-                T rho = P.Z;
-                if (!P.soft_poly) {
+                T rho = C.Z;
+                if (!C.soft_poly) {
                     T n2 = T(1);
                     if (!(k == NN() && i >= 3)) {
                         n2 = T(0);
                         for (int j = 0; j < NZ(); ++j) n2 += sSA[i * NZ() + j] * sSA[i * NZ() + j];
                     }
-                    rho = n2 > T(0) ? P.rho_hard / n2 : T(0);
+                    rho = n2 > T(0) ? C.rho_hard / n2 : T(0);
                 }
                 rho_eq(k)[i] = rho;
                 y_eq(k)[i] = T(0);
@@ -599,7 +606,7 @@ struct Solver {
     // A = A3 (x) I, B = B3 (x) I of the exact triple-integrator discretisation.
     __device__ void add_dynamics_hessian() {
         const int nq = NQ(), nu = NU(), nx = NX(), ld = LDM();
-        const T dt = P.dt;
+        const T dt = C.dt;
         // T3[a][I]: column 0 = B3, columns 1..3 = A3 (block order of the stage vector: jerk, q, v, a)
         const T T3[3][4] = {{dt * dt * dt / T(6), T(1), dt, T(0.5) * dt * dt},
                             {T(0.5) * dt * dt, T(0), T(1), dt},
@@ -654,7 +661,7 @@ struct Solver {
     // vec (stage layout) += [B A]' pv
     __device__ void add_dynamics_gradient(T* vec) const {
         const int nq = NQ(), nu = NU();
-        const T dt = P.dt;
+        const T dt = C.dt;
         if (lane < nq) {
             const T p0 = sPv[lane], p1 = sPv[nq + lane], p2 = sPv[2 * nq + lane];
             vec[lane] += dt * dt * dt / T(6) * p0 + T(0.5) * dt * dt * p1 + dt * p2;
@@ -669,15 +676,15 @@ struct Solver {
     // equality proximal terms + barrier terms of the inequality sides.
     __device__ void build_stage_matrix(int k, bool rows_loaded = false) {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ld = LDM();
-        const T dt = P.dt;
+        const T dt = C.dt;
         for (int idx = lane; idx < nz * ld; idx += WARP) sM[idx] = T(0);
         __syncwarp();
         if (k < NN()) {
             // cost (quadratic_joint_state_input_cost.h:9-33, end_effector_cost.h:48-84), scaled by dt
             for (int i = lane; i < nz; i += WARP) {
                 T d;
-                if (i < nq) d = dt * P.Rd[i] + P.reg_input;
-                else if (i < nu) d = dt * P.fw + P.reg_input;
+                if (i < nq) d = dt * P.Rd[i] + C.reg_input;
+                else if (i < nu) d = dt * C.fw + C.reg_input;
                 else d = dt * P.Qd[i - nu];
                 sM[i * ld + i] = d;
             }
@@ -687,7 +694,7 @@ struct Solver {
                 const int a = idx / nq, b = idx % nq;
                 if (b > a) continue;
                 T acc = 0;
-                for (int c = 0; c < 3; ++c) acc += P.Wd[c] * Jp[c * nq + a] * Jp[c * nq + b];
+                for (int c = 0; c < 3; ++c) acc += C.Wd[c] * Jp[c * nq + a] * Jp[c * nq + b];
                 sM[(nu + a) * ld + nu + b] += dt * acc;
             }
             __syncwarp();
@@ -952,7 +959,7 @@ struct Solver {
     // Every row family accumulates into distinct entries per lane (no atomics).
     __device__ void stage_gradient(int k, bool corrector, T mu_target, T* vec, bool rows_loaded = false) {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ();
-        const T dt = P.dt;
+        const T dt = C.dt;
         const T* zk = Zk(k);
         const T cm = corrector ? T(1) : T(0);
         // cost part (zero at the terminal stage)
@@ -969,12 +976,12 @@ struct Solver {
             }
             for (int i = lane; i < nz; i += WARP) {
                 T g;
-                if (i < nq) g = dt * P.Rd[i] * (u[i] + zk[i]) + P.reg_input * zk[i];
-                else if (i < nu) g = dt * P.fw * (u[i] + zk[i]) + P.reg_input * zk[i];
+                if (i < nq) g = dt * P.Rd[i] * (u[i] + zk[i]) + C.reg_input * zk[i];
+                else if (i < nu) g = dt * C.fw * (u[i] + zk[i]) + C.reg_input * zk[i];
                 else {
                     const int xi = i - nu;
                     g = dt * P.Qd[xi] * (x[xi] + zk[i] - P.xd[xi]);
-                    if (xi < nq) g += dt * (P.Wd[0] * Jp[xi] * e3[0] + P.Wd[1] * Jp[nq + xi] * e3[1] + P.Wd[2] * Jp[2 * nq + xi] * e3[2]);
+                    if (xi < nq) g += dt * (C.Wd[0] * Jp[xi] * e3[0] + C.Wd[1] * Jp[nq + xi] * e3[1] + C.Wd[2] * Jp[2 * nq + xi] * e3[2]);
                 }
                 vec[i] = g;
             }
@@ -991,8 +998,8 @@ struct Solver {
             const T val = zk[m];
             if (fam == 0) {
                 const T uu = U[k * nu + r];
-                lb = (r < nq ? P.ulb[r] : P.flb) - uu;
-                ub = (r < nq ? P.uub[r] : P.fub) - uu;
+                lb = (r < nq ? P.ulb[r] : C.flb) - uu;
+                ub = (r < nq ? P.uub[r] : C.fub) - uu;
             } else {
                 const int i = r - NBOXU();
                 const T xx = X[k * nx + i];
@@ -1436,7 +1443,7 @@ struct Solver {
             }
             if (k < NN()) {
                 if (lane < nq) {
-                    const T dt = P.dt;
+                    const T dt = C.dt;
                     const T q = dx[lane], v = dx[nq + lane], a = dx[2 * nq + lane], j = du[lane];
                     dxn[lane] = q + dt * v + T(0.5) * dt * dt * a + dt * dt * dt / T(6) * j;
                     dxn[nq + lane] = v + dt * a + T(0.5) * dt * dt * j;
@@ -1462,7 +1469,7 @@ struct Solver {
         for (int idx = lane; idx < (N + 1) * nz; idx += WARP) ws[oZ() + idx] = T(0);
         __syncwarp();
         if (lane < nq) {
-            const T dt = P.dt;
+            const T dt = C.dt;
             T q = 0, v = 0, a = 0;
             for (int k = 0; k < N; ++k) {
                 const T* gap = ws + oGAP() + k * nx;
@@ -1491,12 +1498,12 @@ struct Solver {
                 if (row_valid(k, fam)) {
                     T lb, ub;
                     const T val = row_value(k, r, fam, zk, &lb, &ub);
-                    q.v[0] = max(val - lb, P.thr0);
-                    q.v[2] = P.mu0 / q.v[0];
+                    q.v[0] = max(val - lb, C.thr0);
+                    q.v[2] = C.mu0 / q.v[0];
                     ++nsides_l;
                     if (fam < 2) {
-                        q.v[1] = max(ub - val, P.thr0);
-                        q.v[3] = P.mu0 / q.v[1];
+                        q.v[1] = max(ub - val, C.thr0);
+                        q.v[3] = C.mu0 / q.v[1];
                         ++nsides_l;
                     }
                 }
@@ -1533,7 +1540,7 @@ struct Solver {
         T pinf = T(0);
         auto eq_infeasibility = [&]() {
             T pv = T(0);
-            if (!P.soft_poly)
+            if (!C.soft_poly)
                 for (int k = 0; k <= N; ++k) {
                     if (neq_of(k) == 0) continue;
                     load_eq_rows(k);
@@ -1545,10 +1552,10 @@ struct Solver {
             return warp_max(pv);
         };
         pinf = eq_infeasibility();
-        for (int it = 0; it < P.qp_iter_max; ++it) {
+        for (int it = 0; it < C.qp_iter_max; ++it) {
             const long long c_it = clock64();
-            if (it > 0 && mu <= T(2) * P.mu_target && rdmax <= P.qp_tol && last_alpha >= T(0.5) &&
-                (pinf <= P.qp_tol || last_step <= P.qp_tol)) {
+            if (it > 0 && mu <= T(2) * C.mu_target && rdmax <= C.qp_tol && last_alpha >= T(0.5) &&
+                (pinf <= C.qp_tol || last_step <= C.qp_tol)) {
                 *converged = true;
                 break;
             }
@@ -1556,7 +1563,7 @@ struct Solver {
             if (!pass_factor_predict()) *finite = false;
             long long c2 = clock64();
             t_fac += c2 - c_it;
-            T target_mu = P.mu_target;
+            T target_mu = C.mu_target;
             T alpha = T(1);
             if (nsides > 0) {
                 const T a_aff = pass_forward(false, T(0));
@@ -1573,7 +1580,7 @@ struct Solver {
                 }
                 const T mu_aff = warp_sum(acc) / T(nsides);
                 const T ratio = mu_aff / mu;
-                target_mu = max(ratio * ratio * ratio * mu, P.mu_target);
+                target_mu = max(ratio * ratio * ratio * mu, C.mu_target);
                 long long c3 = clock64();
                 t_swp += c3 - c2;
                 pass_backward_corrector(target_mu);
@@ -1606,7 +1613,7 @@ struct Solver {
             __syncwarp();
             mu = nsides > 0 ? warp_sum(musum) / T(nsides) : T(0);
             rdmax *= (T(1) - alpha);
-            if (!P.soft_poly) {
+            if (!C.soft_poly) {
                 for (int k = 0; k <= N; ++k) {
                     if (neq_of(k) == 0) continue;
                     load_eq_rows(k);
@@ -1660,11 +1667,23 @@ struct Solver {
         const int nq = NQ(), nx = NX(), nu = NU(), N = NN(), nz = NZ();
         // initial guess: DefaultInitializer = zero input, state held
         // (controller_interface.cpp:385-386); x_0 is always the observation
-        if (!A.warm) {
-            for (int idx = lane; idx < (N + 1) * nx; idx += WARP) X[idx] = x0[idx % nx];
-            for (int idx = lane; idx < N * nu; idx += WARP) U[idx] = T(0);
-        } else {
-            for (int i = lane; i < nx; i += WARP) X[i] = x0[i];
+        {
+            const T* x0 = A.x0 + size_t(b) * nx;
+            if (!A.warm) {
+                for (int idx = lane; idx < (N + 1) * nx; idx += WARP) X[idx] = x0[idx % nx];
+                for (int idx = lane; idx < N * nu; idx += WARP) U[idx] = T(0);
+            } else {
+                const T* Xin = A.X + size_t(b) * (N + 1) * nx;
+                const T* Uin = A.U + size_t(b) * N * nu;
+                for (int idx = lane; idx < (N + 1) * nx; idx += WARP) X[idx] = idx < nx ? x0[idx] : Xin[idx];
+                for (int idx = lane; idx < N * nu; idx += WARP) U[idx] = Uin[idx];
+            }
+            const T* tg = A.target + size_t(b) * (N + 1) * 3;
+            T* tgl = ws + oTG();
+            for (int idx = lane; idx < (N + 1) * 3; idx += WARP) tgl[idx] = tg[idx];
+            const T* bd = A.body ? A.body + size_t(b) * NB() * UB_BODY_PARAMS : &P.body[0][0];
+            T* bdl = ws + oBD();
+            for (int idx = lane; idx < NB() * UB_BODY_PARAMS; idx += WARP) bdl[idx] = bd[idx];
         }
         __syncwarp();
         if (NEQ() > 0) build_Df();
@@ -1673,7 +1692,7 @@ struct Solver {
         T alpha = 0, qp_res = 0;
         T* Xn = ws + oXN();
         T* Un = ws + oUN();
-        for (int it = 0; it < max(1, P.sqp_iters); ++it) {
+        for (int it = 0; it < max(1, C.sqp_iters); ++it) {
             ++sqp_done;
             long long c0 = clock64();
             linearize();
@@ -1696,14 +1715,14 @@ struct Solver {
                 const T* Jp = ws + oLJP() + k * 3 * nq;
                 for (int i = lane; i < nz; i += WARP) {
                     T g;
-                    if (i < nq) g = P.dt * P.Rd[i] * u[i];
-                    else if (i < nu) g = P.dt * P.fw * u[i];
+                    if (i < nq) g = C.dt * P.Rd[i] * u[i];
+                    else if (i < nu) g = C.dt * C.fw * u[i];
                     else {
                         const int xi = i - nu;
-                        g = P.dt * P.Qd[xi] * (x[xi] - P.xd[xi]);
+                        g = C.dt * P.Qd[xi] * (x[xi] - P.xd[xi]);
                         if (xi < nq)
                             for (int c = 0; c < 3; ++c)
-                                g += P.dt * P.Wd[c] * Jp[c * nq + xi] * (ws[oLR() + 3 * k + c] - target[3 * k + c]);
+                                g += C.dt * C.Wd[c] * Jp[c * nq + xi] * (ws[oLR() + 3 * k + c] - target[3 * k + c]);
                     }
                     desc += g * zk[i];
                 }
@@ -1715,7 +1734,7 @@ struct Solver {
             bool accepted = false;
             Perf<T> pn = base;
             alpha = T(1);
-            while (alpha >= P.alpha_min) {
+            while (alpha >= C.alpha_min) {
                 for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
                     const int k = idx / nx, i = idx % nx;
                     Xn[idx] = X[idx] + alpha * ws[oZ() + k * nz + nu + i];
@@ -1727,15 +1746,15 @@ struct Solver {
                 __syncwarp();
                 pn = performance(Xn, Un);
                 const T vn = pn.violation();
-                if (vn > P.g_max) accepted = false;
-                else if (vn < P.g_min) {
-                    if (vb < P.g_min && desc < T(0)) accepted = pn.cost < base.cost + P.armijo * alpha * desc;
+                if (vn > C.g_max) accepted = false;
+                else if (vn < C.g_min) {
+                    if (vb < C.g_min && desc < T(0)) accepted = pn.cost < base.cost + C.armijo * alpha * desc;
                     else accepted = true;
                 } else {
-                    accepted = (vn < (T(1) - P.gamma_c) * vb) || (pn.cost < base.cost - P.gamma_c * vb);
+                    accepted = (vn < (T(1) - C.gamma_c) * vb) || (pn.cost < base.cost - C.gamma_c * vb);
                 }
                 if (accepted) break;
-                alpha *= P.alpha_decay;
+                alpha *= C.alpha_decay;
             }
             t_ls += clock64() - c_ls;
             if (!accepted) {
@@ -1759,13 +1778,22 @@ struct Solver {
             __syncwarp();
             const T dcost = fabs(pn.cost - base.cost);
             base = pn;
-            if ((dxn < P.delta_tol && dun < P.delta_tol) || (dcost < P.cost_tol && base.violation() < P.g_min)) break;
+            if ((dxn < C.delta_tol && dun < C.delta_tol) || (dcost < C.cost_tol && base.violation() < C.g_min)) break;
         }
         if (A.K != nullptr && A.stop_after == 0 && status != UB_STATUS_NAN)
             write_gains(A.K + size_t(b) * A.gain_stages * nu * nx, A.gain_stages);
-        // NaN guard
+        // solution out + NaN guard
         T bad = 0;
-        for (int idx = lane; idx < (N + 1) * nx; idx += WARP) bad += isfinite(X[idx]) ? T(0) : T(1);
+        {
+            T* Xo = A.X + size_t(b) * (N + 1) * nx;
+            T* Uo = A.U + size_t(b) * N * nu;
+            for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
+                const T v = X[idx];
+                bad += isfinite(v) ? T(0) : T(1);
+                Xo[idx] = v;
+            }
+            for (int idx = lane; idx < N * nu; idx += WARP) Uo[idx] = U[idx];
+        }
         bad = warp_sum(bad);
         if (bad > T(0)) status = UB_STATUS_NAN;
         if (lane == 0) {
@@ -1795,8 +1823,8 @@ struct Solver {
 };
 
 template <typename T, typename D>
-__global__ void __launch_bounds__(256, 2) solve_batch_kernel(const DevProblem<T>* __restrict__ Pg, Layout L, BatchArgs<T> A,
-                                                          int warps_per_cta) {
+__global__ void __launch_bounds__(256, 2) solve_batch_kernel(const __grid_constant__ DevProblem<T> Pc, const DevProblem<T>* __restrict__ Pg,
+                                                          Layout L, BatchArgs<T> A, int warps_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // CTA-shared copy of the problem constants
     DevProblem<T>* Ps = reinterpret_cast<DevProblem<T>*>(smem_raw);
@@ -1807,21 +1835,21 @@ __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const DevProblem<T>
         for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const int warp = threadIdx.x / WARP, lane = threadIdx.x % WARP;
+    // the warp index is broadcast from lane 0 so that the compiler knows it is warp-uniform and keeps the
+    // per-warp shared-memory / workspace base addresses in uniform registers instead of recomputing them
+    const int warp = __shfl_sync(FULL, int(threadIdx.x) / WARP, 0), lane = threadIdx.x % WARP;
     const int b = blockIdx.x * warps_per_cta + warp;
     if (b >= A.B) return;
     constexpr size_t off = (sizeof(DevProblem<T>) + 15) / 16 * 16;
     Layout Lk = L;
     if constexpr (D::kStatic) Lk = D::template layout<T>();  // compile-time offsets (host passes the same numbers)
     T* sm = reinterpret_cast<T*>(smem_raw + off) + size_t(warp) * Lk.s_total;
-    Solver<T, D> S(*Ps, L, lane);
-    const int nx = S.NX(), nu = S.NU(), N = S.NN();
-    S.x0 = A.x0 + size_t(b) * nx;
-    S.target = A.target + size_t(b) * (N + 1) * 3;
-    S.body = A.body ? A.body + size_t(b) * S.NB() * UB_BODY_PARAMS : &Ps->body[0][0];
-    S.X = A.X + size_t(b) * (N + 1) * nx;
-    S.U = A.U + size_t(b) * N * nu;
+    Solver<T, D> S(*Ps, Pc, L, lane);
     S.ws = A.ws + size_t(b) * Lk.total;
+    S.X = S.ws + Lk.XW;
+    S.U = S.ws + Lk.UW;
+    S.target = S.ws + Lk.TG;
+    S.body = S.ws + Lk.BD;
     S.sM = sm + Lk.sM;
     S.sP = sm + Lk.sP;
     S.sPv = sm + Lk.sPv;

@@ -15,8 +15,8 @@ import numpy as np
 from . import bindings as B
 
 LAYOUT_FIELDS = ("Z", "DZ", "GAP", "LG", "LCT", "LR", "LJP", "LHO", "LJO", "DF", "RHOE", "YE", "RHOT", "YT", "TT",
-                 "LAM", "DTT", "DLAM", "sTT", "FAC", "WF", "XN", "UN", "total", "sM", "sP", "sPv", "sSA", "sV",
-                 "s_total", "ldm", "ldf")
+                 "LAM", "XW", "UW", "sTT", "FAC", "WF", "XN", "UN", "total", "sM", "sP", "sPv", "sSA", "sV",
+                 "s_total", "TG", "BD")
 
 
 def _ptr(a):
