@@ -70,9 +70,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def wait_first(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the samples taken in [t_begin, t_end] (the timed region); nvidia-smi needs ~0.1 s to deliver
+        its first sample, so the sampler is started before the warm-up."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -82,7 +92,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        inside = [s for (ts, s) in self.samples if (t_begin is None or ts >= t_begin) and (t_end is None or ts <= t_end + 0.03)]
+        window = "timed region"
+        if not inside:
+            inside, window = [s for (_, s) in self.samples], "warm-up + timed region (timed region shorter than one sample)"
+        for s in inside:
             parts = [p.strip() for p in s.split(",")]
             if len(parts) < 7:
                 continue
@@ -95,7 +109,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def oracle_rate(desc, batch, threads, min_seconds=10.0, max_instances=None):
@@ -213,18 +227,20 @@ def main():
             dist.all_gather_into_tensor(Xall, X)
             dist.all_gather_into_tensor(Uall, U)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_first()
     for s in range(args.warmup):
         step(s)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = lib.ub_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms, iters, ok = [], [], []
     torch.cuda.synchronize()
+    t_begin = sampler.mark()
     ev0.record()
     for s in range(args.warmup, nsets):
         step(s)
@@ -234,7 +250,8 @@ def main():
         dist.barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = lib.ub_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = sampler.mark()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     # per-launch kernel duration + iteration statistics (outside the timed region)
     for s in range(args.warmup, min(nsets, args.warmup + 5)):
         step(s)

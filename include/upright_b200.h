@@ -250,7 +250,7 @@ int ub_set_option(ub_problem_t* problem, const char* key, int value);
 
 /* Per-instance workspace layout (offsets in elements) for tests that inspect
  * intermediate blocks; see upright_b200/engine.py LAYOUT_FIELDS. */
-int ub_workspace_layout(const ub_problem_t* problem, uint32_t flags, int32_t out[32]);
+int ub_workspace_layout(const ub_problem_t* problem, uint32_t flags, int32_t out[40]);
 
 /* Device time of the last ub_solve_batch on this problem (CUDA events), ms.
  * Replaces getLastSolveTime() (controller_python_interface.h:27-29). */

@@ -575,11 +575,11 @@ int ub_set_option(ub_problem_t* p, const char* key, int value) {
     }
     return fail(UB_E_INVALID, std::string("unknown option ") + key);
 }
-int ub_workspace_layout(const ub_problem_t* p, uint32_t flags, int32_t out[32]) {
+int ub_workspace_layout(const ub_problem_t* p, uint32_t flags, int32_t out[40]) {
     if (!p) return fail(UB_E_INVALID, "null problem");
     const ub::Layout& L = (flags & UB_COMPUTE_F64) ? p->Ld : p->Lf;
-    static_assert(sizeof(ub::Layout) <= 32 * sizeof(int32_t), "layout export too small");
-    std::memset(out, 0, 32 * sizeof(int32_t));
+    static_assert(sizeof(ub::Layout) <= 40 * sizeof(int32_t), "layout export too small");
+    std::memset(out, 0, 40 * sizeof(int32_t));
     std::memcpy(out, &L, sizeof(L));
     return UB_OK;
 }

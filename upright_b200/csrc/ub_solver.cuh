@@ -27,6 +27,7 @@ struct Layout {
     int total;
     // shared memory (units of T, per warp)
     int sM, sP, sPv, sSA, sV, s_total;
+    int sSm;  // staged per-stage vectors [z | x | u | Jp | w] (with the staged side records)
     // instance-local copies of the desired positions [N+1, 3] and the body parameters [nb, 10]
     int TG, BD;
 };
@@ -76,6 +77,8 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.sSA = s;  s += ub_round4((d.neq > 3 ? d.neq : 3) * nz);
     L.sV = s;   s += ub_round4(5 * nz + 64);  // [4 nz, ...) doubles as per-row scratch (>= max(neq, nobs, 3) entries)
     L.sTT = s;  s += (d.nrow <= UB_STAGE_ROWS_MAX) ? ub_round4(d.nrow * 8) : 0;  // staged side records of one stage
+    L.sSm = s;
+    s += (d.nrow <= UB_STAGE_ROWS_MAX) ? ub_round4(nz) + ub_round4(nx) + 2 * ub_round4(nu) + ub_round4(3 * nq) : 0;
     L.s_total = s;
     return L;
 }
@@ -167,6 +170,7 @@ struct Solver {
     T* sSA;
     T* sV;
     T* sTT;
+    T* sSm;
     long long t_lin = 0, t_fac = 0, t_swp = 0, t_side = 0, t_ls = 0, t_res = 0;
     long long t_f1 = 0, t_f2 = 0, t_f3 = 0, t_f4 = 0, t_g = 0;  // finer: build / dynamics / cholesky / store ; gradient  // phase cycle counters (profile mode)
 
@@ -206,17 +210,17 @@ struct Solver {
     }
     // value of ineq row r of stage k at the QP iterate z (stage vector zk = [du; dx]),
     // and bounds.  Uses the linearisation stored in the workspace.
-    __device__ T row_value(int k, int r, int fam, const T* zk, T* lb, T* ub) const {
+    __device__ T row_value(int k, int r, int fam, const T* zk, const T* xk, const T* uk, T* lb, T* ub) const {
         const int nq = NQ(), nu = NU();
         if (fam == 0) {
-            const T u = U[k * nu + r];
+            const T u = uk[r];
             *lb = (r < nq ? P.ulb[r] : C.flb) - u;
             *ub = (r < nq ? P.uub[r] : C.fub) - u;
             return zk[r];
         }
         if (fam == 1) {
             const int i = r - NBOXU();
-            const T x = X[k * NX() + i];
+            const T x = xk[i];
             *lb = P.xlb[i] - x;
             *ub = P.xub[i] - x;
             return zk[nu + i];
@@ -226,7 +230,7 @@ struct Solver {
         if (fam == 2) {
             const int i = r - NBOXU() - NX(), c = i / 5;
             const V3<T> a = fric_coeff(c, i % 5);
-            const T* f = U + k * nu + nq + 3 * c;
+            const T* f = uk + nq + 3 * c;
             const T* df = zk + nq + 3 * c;
             return a.x * (f[0] + df[0]) + a.y * (f[1] + df[1]) + a.z * (f[2] + df[2]);
         }
@@ -310,6 +314,42 @@ struct Solver {
         }
     }
     static constexpr int NROW_STATIC = D::nrow;
+    // staged per-stage vectors (same schedule as the side records): the QP iterate z_k (or, in the corrector
+    // pass, the stored predictor gradient), the linearisation point x_k, u_k, the position Jacobian and w_k
+    static constexpr int kSmX = (D::nz + 3) / 4 * 4, kSmU = kSmX + (D::nx + 3) / 4 * 4, kSmJ = kSmU + (D::nu + 3) / 4 * 4,
+                         kSmW = kSmJ + (3 * D::nq + 3) / 4 * 4;
+    __device__ __forceinline__ const T* st_z(int k) const { if constexpr (kStageTT) return sSm; else return Zk(k); }
+    __device__ __forceinline__ const T* st_gp(int k) const { if constexpr (kStageTT) return sSm; else return ws + oLAM() + k * NZ(); }
+    __device__ __forceinline__ const T* st_x(int k) const { if constexpr (kStageTT) return sSm + kSmX; else return X + k * NX(); }
+    __device__ __forceinline__ const T* st_u(int k) const { if constexpr (kStageTT) return sSm + kSmU; else return U + k * NU(); }
+    __device__ __forceinline__ const T* st_jp(int k) const { if constexpr (kStageTT) return sSm + kSmJ; else return ws + oLJP() + k * 3 * NQ(); }
+    __device__ __forceinline__ const T* st_w(int k) const { if constexpr (kStageTT) return sSm + kSmW; else return ws + oWF() + k * NU(); }
+    __device__ __forceinline__ void cp_async_elems(T* dst, const T* src, int n) const {
+        for (int i = lane; i < n; i += WARP) {
+            if constexpr (sizeof(T) == 4)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + i)), "l"(src + i) : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst + i)), "l"(src + i) : "memory");
+        }
+    }
+    // z_k (gp = false) or the predictor gradient of stage k (gp = true), x_k, u_k and optionally Jp_k
+    __device__ __forceinline__ void sm_issue(int k, bool gp, bool jp) const {
+        if constexpr (kStageTT) {
+            if (k < 0 || k > NN()) return;
+            cp_async_elems(sSm, gp ? ws + oLAM() + k * NZ() : Zk(k), NZ());
+            if (!gp) {
+                cp_async_elems(sSm + kSmX, X + k * NX(), NX());
+                if (k < NN()) cp_async_elems(sSm + kSmU, U + k * NU(), NU());
+            }
+            if (jp) cp_async_elems(sSm + kSmJ, ws + oLJP() + k * 3 * NQ(), 3 * NQ());
+        }
+    }
+    __device__ __forceinline__ void w_issue(int k) const {
+        if constexpr (kStageTT) {
+            if (k < 0 || k >= NN()) return;
+            cp_async_elems(sSm + kSmW, ws + oWF() + k * NU(), NU());
+        }
+    }
     // Newton data of one side: returns the barrier weight and the coefficient that multiplies sgn*a in the
     // stage gradient;  d = signed distance to the bound at the current iterate
     __device__ __forceinline__ T side_coef(T t, T lam, T d, T eps, T target, T corr) const {
@@ -689,7 +729,7 @@ struct Solver {
                 sM[i * ld + i] = d;
             }
             __syncwarp();
-            const T* Jp = ws + oLJP() + k * 3 * nq;
+            const T* Jp = st_jp(k);
             for (int idx = lane; idx < nq * nq; idx += WARP) {
                 const int a = idx / nq, b = idx % nq;
                 if (b > a) continue;
@@ -960,13 +1000,13 @@ struct Solver {
     __device__ void stage_gradient(int k, bool corrector, T mu_target, T* vec, bool rows_loaded = false) {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ();
         const T dt = C.dt;
-        const T* zk = Zk(k);
+        const T* zk = st_z(k);
         const T cm = corrector ? T(1) : T(0);
         // cost part (zero at the terminal stage)
         if (k < NN()) {
-            const T* x = X + k * nx;
-            const T* u = U + k * nu;
-            const T* Jp = ws + oLJP() + k * 3 * nq;
+            const T* x = st_x(k);
+            const T* u = st_u(k);
+            const T* Jp = st_jp(k);
             // e = Jp dq + r - r_d, reduced over the warp
             T e3[3];
 #pragma unroll
@@ -997,12 +1037,12 @@ struct Solver {
             T lb, ub;
             const T val = zk[m];
             if (fam == 0) {
-                const T uu = U[k * nu + r];
+                const T uu = st_u(k)[r];
                 lb = (r < nq ? P.ulb[r] : C.flb) - uu;
                 ub = (r < nq ? P.uub[r] : C.fub) - uu;
             } else {
                 const int i = r - NBOXU();
-                const T xx = X[k * nx + i];
+                const T xx = st_x(k)[i];
                 lb = P.xlb[i] - xx;
                 ub = P.xub[i] - xx;
             }
@@ -1052,7 +1092,7 @@ struct Solver {
             // one lane per contact: five pyramid rows -> three force entries
             const T eps = row_eps(2);
             for (int c = lane; c < NC(); c += WARP) {
-                const T* f = U + k * nu + nq + 3 * c;
+                const T* f = st_u(k) + nq + 3 * c;
                 const T* df = zk + nq + 3 * c;
                 const T f0 = f[0] + df[0], f1 = f[1] + df[1], f2 = f[2] + df[2];
                 T g0 = 0, g1 = 0, g2 = 0;
@@ -1103,25 +1143,6 @@ struct Solver {
         }
     }
 
-    // L1 prefetch of a span of the instance workspace: issued one stage ahead of its use so that the loads of
-    // the next stage hit L1 instead of waiting on L2 / HBM behind only four warps per scheduler.
-    __device__ __forceinline__ void prefetch_span(const T* p, int nelem) const {
-        constexpr int LINE = 128 / sizeof(T);
-        for (int i = lane * LINE; i < nelem + LINE; i += WARP * LINE)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(p + min(i, nelem - 1)));
-    }
-    // everything the factor pass reads for stage k
-    __device__ __forceinline__ void prefetch_factor_stage(int k) const {
-        if (k < 0) return;
-        prefetch_span(ws + oTT() + k * NROW() * 8, NROW() * 8);
-        prefetch_span(Zk(k), NZ());
-        prefetch_span(X + k * NX(), NX());
-        if (k < NN()) {
-            prefetch_span(U + k * NU(), NU());
-            if (NEQ() > 0) prefetch_span(ws + oLCT() + k * NEQ() * NZ(), NEQ() * NZ());
-            prefetch_span(ws + oLJP() + k * 3 * NQ(), 3 * NQ());
-        }
-    }
     // Factor-block staging: the block of the NEXT stage is fetched with cp.async (LDGSTS, generic proxy — no
     // proxy fence against the plain stores of the factor pass) into the other half of the idle stage-matrix
     // buffer while the current stage is processed.
@@ -1166,6 +1187,7 @@ struct Solver {
         __syncwarp();
         if constexpr (kStageTT) {
             tt_issue(NN());
+            sm_issue(NN(), false, true);
             cp_commit();
         }
         for (int k = NN(); k >= 0; --k) {
@@ -1180,9 +1202,9 @@ struct Solver {
             if constexpr (kStageTT) {                       // next stage's records / rows arrive during the factorisation
                 tt_issue(k - 1);
                 eq_issue(k - 1);
+                sm_issue(k - 1, false, true);
                 cp_commit();
             }
-            prefetch_factor_stage(k - 1);
             long long f2 = clock64();
             t_f1 += f2 - f1;
             if (k < NN()) {
@@ -1239,17 +1261,17 @@ struct Solver {
         // in flight (none at the terminal stage)
         if constexpr (kFacDouble) {
             tt_issue(NN());
+            sm_issue(NN(), true, false);
             cp_commit();
         }
         for (int k = NN(); k >= 0; --k) {
-            const T* GPk = ws + oLAM() + k * nz;
-            for (int i = lane; i < nz; i += WARP) vec[i] = GPk[i];
             if constexpr (kFacDouble) {
                 if (k == NN()) cp_wait<0>();
                 else cp_wait<1>();
-            } else {
-                __syncwarp();
             }
+            const T* GPk = st_gp(k);
+            for (int i = lane; i < nz; i += WARP) vec[i] = GPk[i];
+            __syncwarp();
             // (corr - target) / (t + eps lam) per side
             for (int r = lane; r < nbx; r += WARP) {
                 const int fam = r < NBOXU() ? 0 : 1;
@@ -1302,6 +1324,7 @@ struct Solver {
             if constexpr (kFacDouble) {
                 __syncwarp();
                 tt_issue(k - 1);
+                sm_issue(k - 1, true, false);
                 cp_commit();
             }
             if (k == NN()) {
@@ -1348,13 +1371,13 @@ struct Solver {
     // Side steps of the rows of ONE stage for the stage direction d = [du; dx] (shared memory):
     // d lambda, d t per side, and the running maximum feasible step.
     __device__ __forceinline__ void stage_side_steps(int k, const T* d, bool corrector, T target_mu, T& amax) {
-        const T* zk = Zk(k);
+        const T* zk = st_z(k);
         const T cm = corrector ? T(1) : T(0);
         for (int r = lane; r < NROW(); r += WARP) {
             const int fam = row_family(r);
             if (!row_valid(k, fam)) continue;
             T lb, ub;
-            const T val = row_value(k, r, fam, zk, &lb, &ub);
+            const T val = row_value(k, r, fam, zk, st_x(k), st_u(k), &lb, &ub);
             const T adz = row_dot(k, r, fam, d);
             const T eps = row_eps(fam);
             const Quad q = recs(k)[2 * r];
@@ -1393,17 +1416,26 @@ struct Solver {
         // in flight (none for the records of the terminal stage)
         if constexpr (kFacDouble) {
             fac_issue(0, 0);
+            w_issue(0);
             cp_commit();
             tt_issue(0);
+            sm_issue(0, false, false);
             cp_commit();
         }
         for (int k = 0; k <= NN(); ++k) {
             if (k < NN()) {
                 const T* F = sM;
                 const T* Wk = ws + oWF() + k * nu;
+                T wreg = T(0);
                 if constexpr (kFacDouble) {
                     cp_wait<1>();
+                    if constexpr (kStageTT) {   // w_k leaves its (single) staging slot before w_{k+1} is requested
+                        static_assert(D::nu <= WARP, "one register per lane holds the staged w");
+                        if (lane < nu) wreg = st_w(k)[lane];
+                        __syncwarp();
+                    }
                     fac_issue(k + 1, (k + 1) & 1);
+                    w_issue(k + 1);
                     cp_commit();
                     F = sM + (k & 1) * FSTRIDE();
                 } else {
@@ -1412,7 +1444,7 @@ struct Solver {
                 }
                 // s = w + Y dx
                 for (int j = lane; j < nu; j += WARP) {
-                    T acc = Wk[j];
+                    T acc = kStageTT ? wreg : Wk[j];
                     for (int i = 0; i < nx; ++i) acc += F[(nu + i) * ldf + j] * dx[i];
                     du[j] = acc;
                 }
@@ -1439,6 +1471,7 @@ struct Solver {
             if constexpr (kFacDouble) {
                 __syncwarp();
                 tt_issue(k + 1);
+                sm_issue(k + 1, false, false);
                 cp_commit();
             }
             if (k < NN()) {
@@ -1497,7 +1530,7 @@ struct Solver {
                 dd.v[0] = dd.v[1] = dd.v[2] = dd.v[3] = T(0);
                 if (row_valid(k, fam)) {
                     T lb, ub;
-                    const T val = row_value(k, r, fam, zk, &lb, &ub);
+                    const T val = row_value(k, r, fam, zk, X + k * NX(), U + k * NU(), &lb, &ub);
                     q.v[0] = max(val - lb, C.thr0);
                     q.v[2] = C.mu0 / q.v[0];
                     ++nsides_l;
@@ -1524,7 +1557,7 @@ struct Solver {
                 const int fam = row_family(r);
                 if (!row_valid(k, fam)) continue;
                 T lb, ub;
-                const T val = row_value(k, r, fam, zk, &lb, &ub);
+                const T val = row_value(k, r, fam, zk, X + k * NX(), U + k * NU(), &lb, &ub);
                 const T eps = row_eps(fam);
                 const Quad q = *side_tl(k, r);
                 rdmax = max(rdmax, fabs(val - lb + eps * q.v[2] - q.v[0]));
@@ -1856,6 +1889,7 @@ __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const __grid_consta
     S.sSA = sm + Lk.sSA;
     S.sV = sm + Lk.sV;
     S.sTT = sm + Lk.sTT;
+    S.sSm = sm + Lk.sSm;
     S.run(A, b);
 }
 

@@ -16,7 +16,7 @@ from . import bindings as B
 
 LAYOUT_FIELDS = ("Z", "DZ", "GAP", "LG", "LCT", "LR", "LJP", "LHO", "LJO", "DF", "RHOE", "YE", "RHOT", "YT", "TT",
                  "LAM", "XW", "UW", "sTT", "FAC", "WF", "XN", "UN", "total", "sM", "sP", "sPv", "sSA", "sV",
-                 "s_total", "TG", "BD")
+                 "s_total", "sSm", "TG", "BD")
 
 
 def _ptr(a):
@@ -180,7 +180,7 @@ class BatchedMPC:
         B.check(self.lib.ub_set_option(self.handle, key.encode(), int(value)))
 
     def layout(self):
-        out = (C.c_int32 * 32)()
+        out = (C.c_int32 * 40)()
         B.check(self.lib.ub_workspace_layout(self.handle, self.flags, out))
         return dict(zip(LAYOUT_FIELDS, list(out)))
 
