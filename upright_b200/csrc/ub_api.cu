@@ -224,22 +224,54 @@ struct Pick<double> {
     static ub::LaunchFn<double> thing_robust8() { return ub::launch_thing_robust8_f64; }
 };
 
+// Launch geometry: warps per CTA — two CTAs per SM (the 128-register kernels allow 16 warps per SM), each taking
+// half of the SM's shared memory minus the 1 KB the driver reserves per CTA; at most 8 warps.
 template <typename T>
-int launch_solve(ub_problem* p, const ub::BatchArgs<T>& A, cudaStream_t stream) {
+int warps_per_cta(const ub_problem* p) {
     const ub::Layout& L = Pick<T>::layout(p);
     const size_t pbytes = (sizeof(ub::DevProblem<T>) + 15) / 16 * 16;
     const size_t per_warp = size_t(L.s_total) * sizeof(T);
-    // warps per CTA: two CTAs per SM (the 128-register kernels allow 16 warps per SM), each taking half of the
-    // SM's shared memory minus the 1 KB the driver reserves per CTA; at most 8 warps
     const size_t cta_budget = size_t(p->max_smem_sm) / 2 - 1024;
-    int wpc = int((cta_budget - pbytes) / per_warp);
+    int wpc = cta_budget > pbytes ? int((cta_budget - pbytes) / per_warp) : 1;
     if (wpc < 1) wpc = 1;
     if (wpc > 8) wpc = 8;
     const char* env = std::getenv("UB_WARPS_PER_CTA");
     if (env) wpc = std::max(1, std::min(8, std::atoi(env)));
+    return wpc;
+}
+// Workspace slots of a batch of B: the persistent grid holds one slot per resident warp; the static test mode
+// (option stop_after != 0) one per instance.
+template <typename T>
+int64_t workspace_slots(const ub_problem* p, int B) {
+    const int64_t resident = int64_t(p->sm_count) * 2 * warps_per_cta<T>(p);
+    return std::max<int64_t>(1, std::min<int64_t>(B, resident));
+}
+template <typename T>
+int64_t workspace_bytes(const ub_problem* p, int B) {
+    const int64_t slots = p->stop_after != 0 ? B : workspace_slots<T>(p, B);
+    return slots * Pick<T>::layout(p).total * int64_t(sizeof(T)) + 256;  // + the work-queue counter
+}
+
+template <typename T>
+int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
+    const ub::Layout& L = Pick<T>::layout(p);
+    const size_t pbytes = (sizeof(ub::DevProblem<T>) + 15) / 16 * 16;
+    const size_t per_warp = size_t(L.s_total) * sizeof(T);
+    const int wpc = warps_per_cta<T>(p);
     const size_t smem = pbytes + per_warp * wpc;
     if (smem > size_t(p->max_smem_optin)) return fail(UB_E_INVALID, "problem too large for shared memory");
-    const int grid = (A.B + wpc - 1) / wpc;
+    const bool persistent = p->stop_after == 0;
+    const int64_t slots = persistent ? workspace_slots<T>(p, A.B) : A.B;
+    if (persistent) {
+        // the counter sits behind the last slot
+        A.queue = reinterpret_cast<int*>(reinterpret_cast<char*>(A.ws) + slots * L.total * int64_t(sizeof(T)) + 128);
+        A.queue = reinterpret_cast<int*>(reinterpret_cast<uintptr_t>(A.queue) & ~uintptr_t(63));
+        UB_CUDA(cudaMemsetAsync(A.queue, 0, sizeof(int), stream));
+    } else {
+        A.queue = nullptr;
+    }
+    A.n_slots = int(slots);
+    const int grid = int((slots + wpc - 1) / wpc);
     const ub::DevProblem<T>& H = Pick<T>::host(p);
     // kernels specialised on the BASELINE dimensions (nq, nf, nc, nb); anything else runs the generic one
     const bool generic_only = std::getenv("UB_FORCE_GENERIC") != nullptr;
@@ -262,7 +294,7 @@ int solve_device(ub_problem* p, int B, const void* x0, const void* target, const
                  int32_t* status, void* stats, void* ws, int64_t ws_bytes, uint32_t flags, cudaStream_t stream,
                  int gain_stages = -1) {
     const ub::Layout& L = Pick<T>::layout(p);
-    if (ws_bytes < int64_t(B) * L.total * int64_t(sizeof(T))) return fail(UB_E_INVALID, "workspace too small");
+    if (ws_bytes < workspace_bytes<T>(p, B)) return fail(UB_E_INVALID, "workspace too small (see ub_workspace_bytes)");
     if (reinterpret_cast<uintptr_t>(ws) % 16 != 0) return fail(UB_E_INVALID, "workspace must be 16-byte aligned");
     ub::BatchArgs<T> A;
     A.x0 = static_cast<const T*>(x0);
@@ -294,7 +326,7 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
     const size_t n_x0 = size_t(B) * P.nx, n_tg = size_t(B) * (P.N + 1) * 3, n_bd = body ? size_t(B) * P.nb * UB_BODY_PARAMS : 0;
     const size_t n_X = size_t(B) * (P.N + 1) * P.nx, n_U = size_t(B) * P.N * P.nu;
     const size_t n_K = K ? size_t(B) * P.N * P.nu * P.nx : 0, n_st = size_t(B) * UB_STATS;
-    const size_t n_ws = size_t(B) * L.total;
+    const size_t n_ws = size_t(workspace_bytes<T>(p, B)) / sizeof(T);
     const size_t n_in = n_x0 + n_tg + n_bd, n_io = n_X + n_U;
     const size_t elems = n_in + n_io + n_K + n_st + n_ws + 8;  // +8: 16-byte alignment pad of the workspace
     const size_t bytes = elems * sizeof(T) + size_t(B) * sizeof(int32_t) + 256;
@@ -396,7 +428,7 @@ int closed_loop(ub_problem* p, int B, const double* x0, const double* target_tim
     T* d_stats = static_cast<T*>(dev.bytes((size_t(B) * UB_STATS) * sizeof(T)));
     int32_t* d_status = static_cast<int32_t*>(dev.bytes((B) * sizeof(int32_t)));
     int32_t* d_counts = static_cast<int32_t*>(dev.bytes((size_t(B) * 4) * sizeof(int32_t)));
-    T* d_ws = static_cast<T*>(dev.bytes((size_t(B) * L.total + 8) * sizeof(T)));
+    T* d_ws = static_cast<T*>(dev.bytes(size_t(workspace_bytes<T>(p, B)) + 64));
     T* d_xs = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nx) * sizeof(T))) : nullptr;
     T* d_us = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nq) * sizeof(T))) : nullptr;
     if (!d_x || !d_pos || !d_times || (body && !d_body) || !d_target || !d_X[0] || !d_X[1] || !d_U[0] || !d_U[1] ||
@@ -445,7 +477,7 @@ int closed_loop(ub_problem* p, int B, const double* x0, const double* target_tim
                 cur ^= 1;
             }
             rc = solve_device<T>(p, B, d_x, d_target, d_body, d_X[cur], d_U[cur], d_K, d_status, d_stats, d_ws,
-                                 int64_t(size_t(B) * L.total * sizeof(T)), (flags & UB_COMPUTE_F64) | UB_PTRS_DEVICE |
+                                 workspace_bytes<T>(p, B), (flags & UB_COMPUTE_F64) | UB_PTRS_DEVICE |
                                  (warm ? UB_WARM_START : 0u), stream, gain_stages);
             if (rc != UB_OK) break;
             ub::rh_count_status_kernel<<<(B + 255) / 256, 256, 0, stream>>>(B, d_status, d_counts);
@@ -553,7 +585,7 @@ int ub_problem_dims(const ub_problem_t* p, int32_t out[8]) {
 
 int64_t ub_workspace_bytes(const ub_problem_t* p, int32_t B, uint32_t flags) {
     if (!p) return 0;
-    return (flags & UB_COMPUTE_F64) ? int64_t(B) * p->Ld.total * 8 : int64_t(B) * p->Lf.total * 4;
+    return (flags & UB_COMPUTE_F64) ? workspace_bytes<double>(p, B) : workspace_bytes<float>(p, B);
 }
 
 // Debug/testing aids (not part of the reference surface): option "stop_after"
