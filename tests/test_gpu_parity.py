@@ -325,3 +325,21 @@ def test_device_closed_loop_log_stride_and_errors():
         mpc.closed_loop(x0, [0.0, 0.0], np.repeat(goal, 2, axis=1), 10, 0.005, 0.01)   # times must increase
     with pytest.raises(RuntimeError):
         mpc.closed_loop(x0, [0.0], goal, 0, 0.005, 0.01)
+
+
+def test_fp64_rescue_of_fp32_breakdowns():
+    """UB_RESCUE_F64: the few instances whose fp32 factorisation breaks down (status NAN) are re-solved by the
+    fp64 kernels inside the same host call and then agree with the oracle."""
+    name = "cfg3_thing_box_arch"
+    mpc, desc, meta = engine(name, "f32")
+    b = batch_for(name, 2048, 1234)
+    plain = mpc.solve(b["x0"], b["target"], b["body_params"])
+    nan = np.nonzero(plain["status"] == 3)[0]
+    resc = mpc.solve(b["x0"], b["target"], b["body_params"], rescue=True)
+    assert (resc["status"] != 3).all()
+    keep = plain["status"] != 3
+    assert np.array_equal(resc["X"][keep], plain["X"][keep])       # untouched instances are bit-identical
+    if len(nan):
+        idx = nan[:4]
+        ref = oracle.solve_batch(desc, b["x0"][idx], b["target"][idx], b["body_params"][idx])
+        assert np.abs(resc["X"][idx] - ref["X"]).max() < 1e-7 and (resc["status"][idx] == ref["status"]).all()

@@ -115,7 +115,7 @@ def test_receding_horizon_shift_with_stub_engine():
         def set_option(self, *a):
             pass
 
-        def solve(self, x0, target, body, X=None, U=None, warm=False, want_gains=False):
+        def solve(self, x0, target, body, X=None, U=None, warm=False, want_gains=False, **kw):
             self.calls.append(dict(warm=warm, X=None if X is None else X.copy(), U=None if U is None else U.copy()))
             B = x0.shape[0]
             Xo = np.stack([x0 + k for k in range(N + 1)], axis=1)

@@ -21,6 +21,7 @@ UB_STATS = 8
 UB_PTRS_DEVICE = 0x1
 UB_WARM_START = 0x2
 UB_COMPUTE_F64 = 0x4
+UB_RESCUE_F64 = 0x8
 
 STATUS_NAMES = {0: "converged", 1: "qp_maxiter", 2: "linesearch_failed", 3: "nan"}
 

@@ -386,6 +386,39 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
     if (n_K) convert_array(K, h + oX + n_io, n_K);
     if (stats) convert_array(stats, h + oX + n_io + n_K, n_st);
     std::memcpy(status, h_status, size_t(B) * sizeof(int32_t));
+    if constexpr (sizeof(T) == 4) {
+        if (flags & UB_RESCUE_F64) {
+            // fp32 breakdown (a factorisation that lost positive definiteness to roundoff): the few instances
+            // concerned go through the fp64 kernels, cold-started, and replace their rows
+            std::vector<int> idx;
+            for (int b = 0; b < B; ++b)
+                if (status[b] == UB_STATUS_NAN) idx.push_back(b);
+            if (!idx.empty()) {
+                const int n = int(idx.size());
+                const size_t sx0 = P.nx, stg = size_t(P.N + 1) * 3, sbd = size_t(P.nb) * UB_BODY_PARAMS,
+                             sX = size_t(P.N + 1) * P.nx, sU = size_t(P.N) * P.nu, sK = size_t(P.N) * P.nu * P.nx;
+                std::vector<double> rx0(n * sx0), rtg(n * stg), rbd(body ? n * sbd : 0), rX(n * sX), rU(n * sU),
+                    rK(K ? n * sK : 0), rst(n * UB_STATS);
+                std::vector<int32_t> rstatus(n);
+                for (int i = 0; i < n; ++i) {
+                    std::memcpy(&rx0[i * sx0], x0 + idx[i] * sx0, sx0 * sizeof(double));
+                    std::memcpy(&rtg[i * stg], target + idx[i] * stg, stg * sizeof(double));
+                    if (body) std::memcpy(&rbd[i * sbd], body + idx[i] * sbd, sbd * sizeof(double));
+                }
+                const uint32_t f2 = (flags & ~(UB_RESCUE_F64 | UB_WARM_START | UB_PTRS_DEVICE)) | UB_COMPUTE_F64;
+                const int rc2 = solve_host<double>(p, n, rx0.data(), rtg.data(), body ? rbd.data() : nullptr, rX.data(), rU.data(),
+                                                   K ? rK.data() : nullptr, rstatus.data(), rst.data(), f2, stream);
+                if (rc2 != UB_OK) return rc2;
+                for (int i = 0; i < n; ++i) {
+                    std::memcpy(X + idx[i] * sX, &rX[i * sX], sX * sizeof(double));
+                    std::memcpy(U + idx[i] * sU, &rU[i * sU], sU * sizeof(double));
+                    if (K) std::memcpy(K + idx[i] * sK, &rK[i * sK], sK * sizeof(double));
+                    if (stats) std::memcpy(stats + idx[i] * UB_STATS, &rst[i * UB_STATS], UB_STATS * sizeof(double));
+                    status[idx[i]] = rstatus[i];
+                }
+            }
+        }
+    }
     return UB_OK;
 }
 

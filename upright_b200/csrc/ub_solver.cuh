@@ -192,6 +192,7 @@ struct Solver {
     T* sV;
     T* sTT;
     T* sSm;
+    int nan_reason = 0;  // where a solve first went non-finite: 1 factorisation, 2 step, 4 complementarity, 5 step size, 3 iterate
     long long t_lin = 0, t_fac = 0, t_swp = 0, t_side = 0, t_ls = 0, t_res = 0;
     long long t_f1 = 0, t_f2 = 0, t_f3 = 0, t_f4 = 0, t_g = 0;  // finer: build / dynamics / cholesky / store ; gradient  // phase cycle counters (profile mode)
 
@@ -865,10 +866,8 @@ struct Solver {
         bool ok = true;
         for (int j = 0; j < npiv; ++j) {
             T d = sM[j * ld + j];
-            if (!(d > T(1e-30))) {
-                ok = false;
-                d = T(1e-30);
-            }
+            if (d != d) ok = false;
+            if (!(d > C.reg_input)) d = C.reg_input;   // see stage_factor_blocked
             const T inv = rsqrt(d);
             for (int i = j + 1 + lane; i < n; i += WARP) sM[i * ld + j] *= inv;
             __syncwarp();
@@ -927,11 +926,12 @@ struct Solver {
         bool ok = true;
 #pragma unroll
         for (int j = 0; j < NU_; ++j) {
+            // The exact pivot is bounded below by reg_input (M_uu >= reg_input I); one that roundoff pushed under
+            // the bound is raised to it, which keeps the fp32 factorisation finite (the Newton step is then inexact
+            // and the interior-point iteration corrects it).  A NaN pivot still fails the solve.
             T d = __shfl_sync(FULL, row[0][j], j);
-            if (!(d > T(1e-30))) {
-                ok = false;
-                d = T(1e-30);
-            }
+            if (d != d) ok = false;
+            if (!(d > C.reg_input)) d = C.reg_input;
             const T inv = rsqrt(d);
             T lij[R];
 #pragma unroll
@@ -1231,6 +1231,21 @@ struct Solver {
             stage_gradient(k, false, T(0), vec, kStageEQ && k < NN());  // equality rows of stage k in sSA afterwards
             T* GPk = ws + oLAM() + k * nz;
             for (int i = lane; i < nz; i += WARP) GPk[i] = vec[i];
+#ifdef UB_DEBUG_NAN
+            {
+                T bad = 0, badr = 0;
+                for (int i = lane; i < nz; i += WARP) bad += (vec[i] == vec[i]) ? T(0) : T(1);
+                for (int r = lane; r < NROW(); r += WARP) {
+                    const Quad q = recs(k)[2 * r];
+                    for (int c = 0; c < 4; ++c) badr += (q.v[c] == q.v[c] && fabs(q.v[c]) < T(1e30)) ? T(0) : T(1);
+                    if (row_valid(k, row_family(r)) && (!(q.v[0] > T(0)) || !(q.v[2] > T(0)))) badr += T(100);
+                }
+                bad = warp_sum(bad);
+                badr = warp_sum(badr);
+                if (nan_reason == 0 && badr > T(0)) nan_reason = 20000 + 100 * k + int(badr > T(99));
+                if (nan_reason == 0 && bad > T(0)) nan_reason = 10000 + 100 * k;
+            }
+#endif
             long long f1 = clock64();
             t_g += f1 - f0;
             build_stage_matrix(k, true);
@@ -1632,7 +1647,10 @@ struct Solver {
                 break;
             }
             iters = it + 1;
-            if (!pass_factor_predict()) *finite = false;
+            if (!pass_factor_predict()) {
+                *finite = false;
+                if (nan_reason == 0) nan_reason = 1;
+            }
             long long c2 = clock64();
             t_fac += c2 - c_it;
             T target_mu = C.mu_target;
@@ -1700,7 +1718,10 @@ struct Solver {
             }
             last_alpha = alpha;
             last_step = warp_max(stepmax);
-            if (!(last_step < tinf<T>())) *finite = false;
+            if (!(last_step < tinf<T>())) {
+                *finite = false;
+                if (nan_reason == 0) nan_reason = !(mu < tinf<T>()) ? 4 : (!(alpha <= T(1)) ? 5 : 2);
+            }
             t_res += 0;
             if (!*finite) break;
         }
@@ -1738,6 +1759,7 @@ struct Solver {
     __device__ void run(const BatchArgs<T>& A, int b) {
         const int nq = NQ(), nx = NX(), nu = NU(), N = NN(), nz = NZ();
         t_lin = t_fac = t_swp = t_side = t_ls = t_res = t_f1 = t_f2 = t_f3 = t_f4 = t_g = 0;
+        nan_reason = 0;
         // initial guess: DefaultInitializer = zero input, state held
         // (controller_interface.cpp:385-386); x_0 is always the observation
         {
@@ -1868,7 +1890,10 @@ struct Solver {
             for (int idx = lane; idx < N * nu; idx += WARP) Uo[idx] = U[idx];
         }
         bad = warp_sum(bad);
-        if (bad > T(0)) status = UB_STATUS_NAN;
+        if (bad > T(0)) {
+            status = UB_STATUS_NAN;
+            if (nan_reason == 0) nan_reason = 3;
+        }
         if (lane == 0) {
             A.status[b] = status;
             if (A.stats) {
@@ -1876,7 +1901,7 @@ struct Solver {
                 s[0] = T(qp_iters);
                 s[1] = base.cost;
                 s[2] = base.violation();
-                s[3] = alpha;
+                s[3] = status == UB_STATUS_NAN ? T(nan_reason) : alpha;   // NaN status: where it first appeared
                 s[4] = qp_res;
                 s[5] = base.max_eq;
                 s[6] = base.min_margin;

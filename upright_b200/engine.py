@@ -52,11 +52,13 @@ class BatchedMPC:
             pass
 
     # ------------------------------------------------------------- host path
-    def solve(self, x0, target, body_params=None, X=None, U=None, warm=False, want_gains=False, out=None):
+    def solve(self, x0, target, body_params=None, X=None, U=None, warm=False, want_gains=False, out=None, rescue=False):
         """numpy float64 host buffers; returns dict(X, U, status, stats[, K]).
 
         `out`: a dict returned by an earlier call with the same batch size — its arrays are overwritten and
-        returned again (what a C caller does with its own buffers; saves the page faults of fresh arrays)."""
+        returned again (what a C caller does with its own buffers; saves the page faults of fresh arrays).
+        `rescue`: instances the fp32 kernels end with status NAN are solved again by the fp64 kernels
+        (`UB_RESCUE_F64`)."""
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
         Bn = x0.shape[0]
         assert x0.shape == (Bn, self.nx)
@@ -86,7 +88,7 @@ class BatchedMPC:
             K = np.empty((Bn, self.N, self.nu, self.nx)) if want_gains else None
             status = np.empty(Bn, dtype=np.int32)
             stats = np.empty((Bn, B.UB_STATS))
-        flags = self.flags | (B.UB_WARM_START if warm else 0)
+        flags = self.flags | (B.UB_WARM_START if warm else 0) | (B.UB_RESCUE_F64 if rescue else 0)
         B.check(self.lib.ub_solve_batch(self.handle, Bn, _ptr(x0), _ptr(target), _ptr(body_params), _ptr(X), _ptr(U),
                                         _ptr(K), _ptr(status), _ptr(stats), None, 0, flags, None))
         res = dict(X=X, U=U, status=status, stats=stats)

@@ -175,7 +175,7 @@ class _RecedingHorizon:
         iters = self.settings.sqp.init_sqp_iteration if self.first else self.settings.sqp.sqp_iteration
         self.engine.set_option("sqp_iteration", int(iters))
         out = self.engine.solve(self.x_obs, self._knot_targets(t), self.body_params, X=X, U=U, warm=warm,
-                                want_gains=self.use_feedback)
+                                want_gains=self.use_feedback, rescue=True)
         self.X, self.U = out["X"], out["U"]
         self.K = out.get("K")
         self.status, self.stats = out["status"], out["stats"]
