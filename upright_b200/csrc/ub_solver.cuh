@@ -674,13 +674,21 @@ struct Solver {
                             {T(0.5) * dt * dt, T(0), T(1), dt},
                             {dt, T(0), T(0), T(1)}};
         if constexpr (D::kStatic) {
-            // block pairs (I >= J) unrolled at compile time: zero entries of T3 drop out, 52 products in total
+            // One pass over the nq x nq entry positions (rolled: the body stays in the instruction cache): the nine
+            // P_ab(ii, jj) are loaded once and feed all ten block pairs (I >= J); zero entries of T3 drop out at
+            // compile time (52 products per position).
+#pragma unroll 1
+            for (int e = lane; e < D::nq * D::nq; e += WARP) {
+                const int ii = e / D::nq, jj = e % D::nq;
+                T pab[3][3];
 #pragma unroll
-            for (int I = 0; I < 4; ++I) {
+                for (int a = 0; a < 3; ++a)
 #pragma unroll
-                for (int J = 0; J <= I; ++J) {
-                    for (int e = lane; e < D::nq * D::nq; e += WARP) {
-                        const int ii = e / D::nq, jj = e % D::nq;
+                    for (int b = 0; b < 3; ++b) pab[a][b] = sP[(a * D::nq + ii) * D::nx + b * D::nq + jj];
+#pragma unroll
+                for (int I = 0; I < 4; ++I) {
+#pragma unroll
+                    for (int J = 0; J <= I; ++J) {
                         T acc = T(0);
 #pragma unroll
                         for (int a = 0; a < 3; ++a) {
@@ -688,7 +696,7 @@ struct Solver {
 #pragma unroll
                             for (int b = 0; b < 3; ++b) {
                                 if ((J == 1 && b != 0) || (J == 2 && b == 2)) continue;
-                                acc += T3[a][I] * T3[b][J] * sP[(a * D::nq + ii) * D::nx + b * D::nq + jj];
+                                acc += T3[a][I] * T3[b][J] * pab[a][b];
                             }
                         }
                         const int mi = (I == 0) ? ii : D::nu + (I - 1) * D::nq + ii;
@@ -984,8 +992,8 @@ struct Solver {
                 acc[ii][cc] = (c == NX_) ? vec[NU_ + ri[ii]] : sM[(NU_ + hi) * ld + NU_ + lo];
             }
         }
-#pragma unroll
-        for (int m = 0; m < NU_; ++m) {
+#pragma unroll 1
+        for (int m = 0; m < NU_; ++m) {   // rolled: 39 instructions that stay in the instruction cache
             T yr[TR], yc[TC];
 #pragma unroll
             for (int ii = 0; ii < TR; ++ii) yr[ii] = sM[(NU_ + ri[ii]) * ld + m];
@@ -1655,30 +1663,35 @@ struct Solver {
             t_fac += c2 - c_it;
             T target_mu = C.mu_target;
             T alpha = T(1);
-            if (nsides > 0) {
-                const T a_aff = pass_forward(false, T(0));
-                // mean complementarity after the affine step
-                T acc = 0;
-                for (int idx = lane; idx < (N + 1) * NROW(); idx += WARP) {
-                    const int k = idx / NROW(), r = idx % NROW();
-                    const int fam = row_family(r);
-                    if (!row_valid(k, fam)) continue;
-                    const Quad* rec = reinterpret_cast<const Quad*>(ws + oTT()) + 2 * idx;
-                    const Quad q = rec[0], dd = rec[1];
-                    acc += (q.v[0] + a_aff * dd.v[0]) * (q.v[2] + a_aff * dd.v[2]);
-                    if (fam < 2) acc += (q.v[1] + a_aff * dd.v[1]) * (q.v[3] + a_aff * dd.v[3]);
+            // predictor (pass 0) and corrector (pass 1) share ONE inlined copy of the forward pass
+            T a_fwd = T(1);
+#pragma unroll 1
+            for (int pass = 0; pass < (nsides > 0 ? 2 : 1); ++pass) {
+                if (pass == 1) {
+                    // mean complementarity after the affine step -> centring target (Mehrotra)
+                    const T a_aff = a_fwd;
+                    T acc = 0;
+                    for (int idx = lane; idx < (N + 1) * NROW(); idx += WARP) {
+                        const int k = idx / NROW(), r = idx % NROW();
+                        const int fam = row_family(r);
+                        if (!row_valid(k, fam)) continue;
+                        const Quad* rec = reinterpret_cast<const Quad*>(ws + oTT()) + 2 * idx;
+                        const Quad q = rec[0], dd = rec[1];
+                        acc += (q.v[0] + a_aff * dd.v[0]) * (q.v[2] + a_aff * dd.v[2]);
+                        if (fam < 2) acc += (q.v[1] + a_aff * dd.v[1]) * (q.v[3] + a_aff * dd.v[3]);
+                    }
+                    const T mu_aff = warp_sum(acc) / T(nsides);
+                    const T ratio = mu_aff / mu;
+                    target_mu = max(ratio * ratio * ratio * mu, C.mu_target);
+                    long long c3 = clock64();
+                    t_swp += c3 - c2;
+                    c2 = c3;
+                    pass_backward_corrector(target_mu);
                 }
-                const T mu_aff = warp_sum(acc) / T(nsides);
-                const T ratio = mu_aff / mu;
-                target_mu = max(ratio * ratio * ratio * mu, C.mu_target);
-                long long c3 = clock64();
-                t_swp += c3 - c2;
-                pass_backward_corrector(target_mu);
-                alpha = min(T(1), T(0.995) * pass_forward(true, target_mu));
-                t_side += clock64() - c3;
-            } else {
-                pass_forward(false, T(0));
+                a_fwd = pass_forward(pass == 1, pass == 1 ? target_mu : T(0));
             }
+            if (nsides > 0) alpha = min(T(1), T(0.995) * a_fwd);
+            t_side += clock64() - c2;
             // update z, t, lambda; new mean complementarity
             T stepmax = 0, musum = 0;
             for (int idx = lane; idx < (N + 1) * nz; idx += WARP) {
@@ -1960,7 +1973,7 @@ __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const __grid_consta
     S.sV = sm + Lk.sV;
     S.sTT = sm + Lk.sTT;
     S.sSm = sm + Lk.sSm;
-    if (A.queue == nullptr) {
+    if (A.queue == nullptr) {   // static mode (test aid)
         S.run(A, slot);
         return;
     }
