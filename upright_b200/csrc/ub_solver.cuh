@@ -666,6 +666,9 @@ struct Solver {
 
     // M (lower triangle, ld = LDM()) += [B A]' Pn [B A] with the block structure
     // A = A3 (x) I, B = B3 (x) I of the exact triple-integrator discretisation.
+    // ASSIGN: the stage matrix has not been initialised — every (I >= J) block entry is assigned and the force
+    // rows / columns, which the dynamics do not touch, are zeroed (saves the separate zero fill of the buffer)
+    template <bool ASSIGN = false>
     __device__ void add_dynamics_hessian() {
         const int nq = NQ(), nu = NU(), nx = NX(), ld = LDM();
         const T dt = C.dt;
@@ -701,9 +704,15 @@ struct Solver {
                         }
                         const int mi = (I == 0) ? ii : D::nu + (I - 1) * D::nq + ii;
                         const int mj = (J == 0) ? jj : D::nu + (J - 1) * D::nq + jj;
-                        sM[mi * ld + mj] += acc;  // diagonal blocks also touch (unused) upper entries
+                        if constexpr (ASSIGN) sM[mi * ld + mj] = acc;
+                        else sM[mi * ld + mj] += acc;  // diagonal blocks also touch (unused) upper entries
                     }
                 }
+            }
+            if constexpr (ASSIGN && D::nfc > 0) {
+                // force rows (all columns up to the diagonal) and force columns of the state rows
+                for (int idx = lane; idx < D::nfc * D::nu; idx += WARP) sM[(D::nq + idx / D::nu) * ld + idx % D::nu] = T(0);
+                for (int idx = lane; idx < D::nx * D::nfc; idx += WARP) sM[(D::nu + idx / D::nfc) * ld + D::nq + idx % D::nfc] = T(0);
             }
         } else {
             const int nb4 = 4 * nq;
@@ -744,11 +753,14 @@ struct Solver {
 
     // Build the Newton matrix of stage k in sM (lower triangle): cost Hessian +
     // equality proximal terms + barrier terms of the inequality sides.
-    __device__ void build_stage_matrix(int k, bool rows_loaded = false) {
+    // `initialised`: the dynamics term has already been ASSIGNED to the buffer (add_dynamics_hessian<true>)
+    __device__ void build_stage_matrix(int k, bool rows_loaded = false, bool initialised = false) {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ld = LDM();
         const T dt = C.dt;
-        for (int idx = lane; idx < nz * ld; idx += WARP) sM[idx] = T(0);
-        __syncwarp();
+        if (!initialised) {
+            for (int idx = lane; idx < nz * ld; idx += WARP) sM[idx] = T(0);
+            __syncwarp();
+        }
         if (k < NN()) {
             // cost (quadratic_joint_state_input_cost.h:9-33, end_effector_cost.h:48-84), scaled by dt
             for (int i = lane; i < nz; i += WARP) {
@@ -756,7 +768,7 @@ struct Solver {
                 if (i < nq) d = dt * P.Rd[i] + C.reg_input;
                 else if (i < nu) d = dt * C.fw + C.reg_input;
                 else d = dt * P.Qd[i - nu];
-                sM[i * ld + i] = d;
+                sM[i * ld + i] += d;
             }
             __syncwarp();
             const T* Jp = st_jp(k);
@@ -799,11 +811,13 @@ struct Solver {
                     sM[i * ld + j] += acc;
                 }
             }
-            if (k == NN())
+            if (k == NN()) {
+                __syncwarp();   // the dense-row loop above adds (zeros) to the same diagonal entries
                 for (int i = 3 + lane; i < ne; i += WARP) {
                     const int m = nu + nq + (i - 3);
                     sM[m * ld + m] += rho[i];
                 }
+            }
             __syncwarp();
         }
         // inequality sides: w a a', w = lam / (t + eps lam)
@@ -959,6 +973,7 @@ struct Solver {
                 row[r][j] = (i > j) ? lij[r] : (i == j ? inv : T(0));
             }
         }
+        __syncwarp();   // lanes beyond the last row read a clamped (real) row above
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int i = lane + WARP * r;
@@ -1256,7 +1271,9 @@ struct Solver {
 #endif
             long long f1 = clock64();
             t_g += f1 - f0;
-            build_stage_matrix(k, true);
+            constexpr bool kAssignDyn = D::kStatic;         // dynamics term first (assigned), the rest added on top
+            if (kAssignDyn && k < NN()) add_dynamics_hessian<true>();
+            build_stage_matrix(k, true, kAssignDyn && k < NN());
             if constexpr (kStageTT) {                       // next stage's records / rows arrive during the factorisation
                 tt_issue(k - 1);
                 eq_issue(k - 1);
@@ -1266,7 +1283,7 @@ struct Solver {
             long long f2 = clock64();
             t_f1 += f2 - f1;
             if (k < NN()) {
-                add_dynamics_hessian();
+                if (!kAssignDyn) add_dynamics_hessian<false>();
                 add_dynamics_gradient(vec);                  // uses p_{k+1} in sPv
                 long long f3 = clock64();
                 t_f2 += f3 - f2;
