@@ -151,6 +151,13 @@ typedef struct ub_problem_desc {
     /* filter line search (ocs2_sqp defaults) */
     double alpha_decay, alpha_min, g_max, g_min, gamma_c, armijo_factor;
     double delta_tol, cost_tol; /* controller.yaml:58-59 */
+
+    /* EndEffectorBoxConstraint (constraint/end_effector_box_constraint.h:12-88; controller.yaml:92-95):
+     * xyz_lower <= r(x) - r_d(t) <= xyz_upper at every intermediate knot, an inequality of the
+     * "poly_ineq" family (softened with it) */
+    int32_t ee_box_enabled;
+    int32_t reserved0;
+    double ee_box_lower[3], ee_box_upper[3];
 } ub_problem_desc_t;
 
 typedef struct ub_problem ub_problem_t;
@@ -208,7 +215,7 @@ int ub_solve_batch(ub_problem_t* problem, int32_t B, const void* x0, const void*
  * and getCostValue (controller_python_interface.h:31-88), batched: evaluates
  * at M (x,u) pairs on the device.  Host double pointers.
  *   name in {"object_dynamics","contact_forces","obstacle_avoidance",
- *            "end_effector_position","cost"}
+ *            "end_effector_box_constraint" (needs target),"end_effector_position","cost"}
  *   out [M, rows]; rows returned through *rows_out. */
 int ub_eval(ub_problem_t* problem, const char* name, int32_t M, const double* x,
             const double* u, const double* target /*[M,3] or NULL*/,

@@ -53,7 +53,7 @@ struct Mat {
 };
 
 struct Dims {
-    int nq, nx, nu, nfc, neq, nfric, nobs, nterm, N, nz;
+    int nq, nx, nu, nfc, neq, nfric, nobs, npairs, nterm, N, nz;
 };
 
 static Dims make_dims(const ub_problem_desc_t& P) {
@@ -65,7 +65,8 @@ static Dims make_dims(const ub_problem_desc_t& P) {
     D.nu = P.nq + D.nfc;
     D.neq = bal ? 6 * P.nb : 0;
     D.nfric = (bal && P.nf == 3) ? 5 * P.nc : 0;
-    D.nobs = P.obstacles_enabled ? P.n_pairs : 0;
+    D.npairs = P.obstacles_enabled ? P.n_pairs : 0;
+    D.nobs = D.npairs + (P.ee_box_enabled ? 6 : 0);  // end-effector box rows follow the sphere-pair rows
     D.nterm = 3 + 2 * P.nq;  // stationary_desired_position_constraint.h:39-41
     D.N = P.N;
     D.nz = D.nu + D.nx;
@@ -153,12 +154,12 @@ static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const doub
             for (int i = 0; i < D.nfric; ++i) L.Ffric(i, j) = h1[i] - h0[i];
         }
     }
-    L.hobs.assign(D.nobs, 0.0);
-    L.Jobs = Mat(D.nobs, nq);
-    if (D.nobs > 0) {
-        std::vector<Dual> h(D.nobs);
+    L.hobs.assign(D.npairs, 0.0);
+    L.Jobs = Mat(D.npairs, nq);
+    if (D.npairs > 0) {
+        std::vector<Dual> h(D.npairs);
         obstacle_constraints<Dual>(P, K, h.data());
-        for (int i = 0; i < D.nobs; ++i) {
+        for (int i = 0; i < D.npairs; ++i) {
             L.hobs[i] = h[i].v;
             for (int j = 0; j < nq; ++j) L.Jobs(i, j) = h[i].d[j];
         }
@@ -270,13 +271,19 @@ static Perf performance(const ub_problem_desc_t& P, const Dims& D, const Mat& A,
                 pf.min_margin = std::min(pf.min_margin, h[i]);
             }
         }
-        if (D.nobs > 0 && k >= 1) {
+        if (D.npairs > 0 && k >= 1) {
             obstacle_constraints<double>(P, K, h.data());
-            for (int i = 0; i < D.nobs; ++i) {
+            for (int i = 0; i < D.npairs; ++i) {
                 pf.ineq_sse += dt * sq(std::min(0.0, h[i]));
                 pf.min_margin = std::min(pf.min_margin, h[i]);
             }
         }
+        if (P.ee_box_enabled && k >= 1)   // constraint/end_effector_box_constraint.h:46-58
+            for (int c = 0; c < 3; ++c) {
+                const double hu = rd[c] + P.ee_box_upper[c] - K.r[c], hl = K.r[c] - rd[c] - P.ee_box_lower[c];
+                pf.ineq_sse += dt * (sq(std::min(0.0, hu)) + sq(std::min(0.0, hl)));
+                pf.min_margin = std::min(pf.min_margin, std::min(hu, hl));
+            }
     }
     return pf;
 }
@@ -393,8 +400,8 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
                 s.rows.push_back(r);
             }
         // obstacle rows, nodes 1..N-1 (state-only; constant at node 0)
-        if (k >= 1 && k < N)
-            for (int i = 0; i < D.nobs; ++i) {
+        if (k >= 1 && k < N) {
+            for (int i = 0; i < D.npairs; ++i) {
                 Row r;
                 r.a.assign(s.nz, 0.0);
                 for (int j = 0; j < nq; ++j) r.a[xo + j] = L.Jobs(i, j);
@@ -403,6 +410,22 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
                 finish(r, soft_poly);
                 s.rows.push_back(r);
             }
+            // end-effector box (constraint/end_effector_box_constraint.h:46-76): three "upper" rows
+            // r_d + upper - r >= 0 (Jacobian -J_p), then three "lower" rows r - r_d - lower >= 0 (+J_p)
+            if (P.ee_box_enabled)
+                for (int side = 0; side < 2; ++side)
+                    for (int c = 0; c < 3; ++c) {
+                        Row r;
+                        r.a.assign(s.nz, 0.0);
+                        const double sg = side == 0 ? -1.0 : 1.0;
+                        for (int j = 0; j < nq; ++j) r.a[xo + j] = sg * L.Jp(c, j);
+                        r.c = side == 0 ? target[3 * k + c] + P.ee_box_upper[c] - L.r[c]
+                                        : L.r[c] - target[3 * k + c] - P.ee_box_lower[c];
+                        r.lb = 0.0;
+                        finish(r, soft_poly);
+                        s.rows.push_back(r);
+                    }
+        }
         if (k == N) {
             // terminal equality [r_d - r; v; a] = 0 (stationary_desired_position_constraint.h:43-74)
             for (int i = 0; i < 3; ++i) {

@@ -343,3 +343,38 @@ def test_fp64_rescue_of_fp32_breakdowns():
         idx = nan[:4]
         ref = oracle.solve_batch(desc, b["x0"][idx], b["target"][idx], b["body_params"][idx])
         assert np.abs(resc["X"][idx] - ref["X"]).max() < 1e-7 and (resc["status"][idx] == ref["status"]).all()
+
+
+def test_end_effector_box_constraint_parity():
+    """EndEffectorBoxConstraint rows (end_effector_box_constraint.h:46-76): probe values, fp64 kernels against
+    the oracle to 1e-7, fp32 within the stated tolerance, and the rows are active."""
+    import copy
+    base, meta = problem_io.load_fixture("cfg2_thing_demo")
+    desc = copy.deepcopy(base)
+    desc.ee_box_enabled = 1
+    desc.ee_box_lower[:] = [-5.0, -5.0, -0.02]
+    desc.ee_box_upper[:] = [5.0, 5.0, 0.02]
+    b = batch_for("cfg2_thing_demo", 12, 77)
+    m64, m32, mfree = BatchedMPC(desc, "f64"), BatchedMPC(desc, "f32"), BatchedMPC(base, "f64")
+    assert m64.n_ineq == mfree.n_ineq + 6
+    # probe
+    tg0 = b["target"][:, 0, :]
+    r0 = m64.eval("end_effector_position", b["x0"], np.zeros((12, 13)))
+    h = m64.eval("end_effector_box_constraint", b["x0"], np.zeros((12, 13)), target=tg0)
+    assert h.shape == (12, 6)
+    assert np.allclose(h[:, :3], tg0 + np.array([5.0, 5.0, 0.02]) - r0, atol=1e-12)
+    assert np.allclose(h[:, 3:], r0 - tg0 - np.array([-5.0, -5.0, -0.02]), atol=1e-12)
+    assert mfree.eval("end_effector_box_constraint", b["x0"], np.zeros((12, 13)), target=tg0).shape == (12, 0)
+    ref = oracle.solve_batch(desc, b["x0"], b["target"], b["body_params"])
+    o64 = m64.solve(b["x0"], b["target"], b["body_params"])
+    assert (o64["status"] == ref["status"]).all()
+    assert np.abs(o64["X"] - ref["X"]).max() < 1e-7 and np.abs(o64["U"] - ref["U"]).max() < 1e-7
+    free = mfree.solve(b["x0"], b["target"], b["body_params"])
+    moved = np.abs(o64["X"] - free["X"]).reshape(12, -1).max(axis=1)
+    assert (moved > 1e-3).sum() >= 6          # goals with |dz| > 0.02 make the rows active
+    o32 = m32.solve(b["x0"], b["target"], b["body_params"])
+    rx, ru = ranges(desc)
+    ex = (np.abs(o32["X"] - ref["X"]) / rx).reshape(12, -1).max(axis=1)
+    eu = (np.abs(o32["U"] - ref["U"]) / ru).reshape(12, -1).max(axis=1)
+    ok = o32["status"] == ref["status"]
+    assert ok.mean() >= 0.9 and np.median(ex[ok]) <= 3e-4 and ex[ok].max() <= 1e-2 and eu[ok].max() <= 1e-2

@@ -139,3 +139,25 @@ def test_receding_horizon_shift_with_stub_engine():
     # previous solution shifted by exactly one knot, tail held
     assert np.allclose(eng.calls[1]["X"][0, :, 0], [1, 2, 3, 4, 4])
     assert np.allclose(eng.calls[1]["U"][0, :, 0], [1, 2, 3, 3])
+
+
+def test_end_effector_box_and_next_rows():
+    """EndEffectorBoxConstraint settings reach the C description; the 'next' rows are rejected loudly."""
+    import copy
+    d, meta = problem_io.load_fixture("cfg2_thing_demo")
+    cfg = copy.deepcopy(meta["controller_config"])
+    cfg["end_effector_box_constraint"] = {"enabled": True, "xyz_lower": [-1.0, -1.0, -0.05], "xyz_upper": [1.0, 1.0, 0.05]}
+    desc = settings.ControllerSettings(cfg, x0=np.array(meta["x0"])).to_desc()
+    assert desc.ee_box_enabled == 1
+    assert list(desc.ee_box_lower) == [-1.0, -1.0, -0.05] and list(desc.ee_box_upper) == [1.0, 1.0, 0.05]
+    bad = copy.deepcopy(cfg)
+    bad["end_effector_box_constraint"]["xyz_lower"] = [2.0, -1.0, -0.05]
+    with pytest.raises(ValueError):
+        settings.ControllerSettings(bad, x0=np.array(meta["x0"])).to_desc()
+    for key, patch in (("inertial_alignment", {"cost_enabled": True, "constraint_enabled": False}),
+                       ("projectile_path_constraint", {"enabled": True}),
+                       ("operating_points", {"enabled": True})):
+        c2 = copy.deepcopy(meta["controller_config"])
+        c2[key] = dict(c2.get(key, {}), **patch)
+        with pytest.raises(NotImplementedError):
+            settings.ControllerSettings(c2, x0=np.array(meta["x0"])).to_desc()

@@ -139,3 +139,32 @@ def test_full_solve_reduces_violation_and_is_deterministic(oracle_lib, name):
     # second SQP iteration (warm) reduces the equality violation
     c = oracle_lib.solve_batch(desc, meta["x0"], target[None], X=a["X"], U=a["U"], warm=True, nthreads=1)
     assert c["stats"][0, 2] < a["stats"][0, 2]
+
+
+def test_end_effector_box_rows_in_the_oracle():
+    """end_effector_box_constraint.h:46-76 — six rows r_d + upper - r >= 0, r - r_d - lower >= 0 at the
+    intermediate knots: dims, the performance index and the solve all see them; a box that excludes the
+    unconstrained motion changes the solution and keeps the vertical excursion (softly) inside."""
+    import copy
+    import oracle
+    desc, target, X, U = _setup("cfg2_thing_demo")
+    free = oracle.solve_batch(desc, X[0], target)
+    z_free = np.array([oracle.fk(desc, x)["r"][2] for x in free["X"][0]]) - target[:, 2]
+    boxed = copy.deepcopy(desc)
+    boxed.ee_box_enabled = 1
+    boxed.ee_box_lower[:] = [-5.0, -5.0, -0.02]
+    boxed.ee_box_upper[:] = [5.0, 5.0, 0.02]
+    assert oracle.dims(boxed)["n_ineq"] == oracle.dims(desc)["n_ineq"] + 6
+    # the target sits ~0.25 m above the start: the initial guess violates the lower z row at every knot
+    pf = oracle.performance(boxed, target, X, U)
+    z0 = oracle.fk(boxed, X[0])["r"][2]
+    assert pf["min_margin"] == pytest.approx(z0 - target[0, 2] + 0.02, abs=1e-9) and pf["min_margin"] < -0.1
+    assert pf["ineq_sse"] == pytest.approx(desc.dt * (desc.N - 1) * pf["min_margin"] ** 2, rel=1e-9)
+    out = oracle.solve_batch(boxed, X[0], target)
+    assert out["status"][0] in (0, 1)
+    z_box = np.array([oracle.fk(boxed, x)["r"][2] for x in out["X"][0]]) - target[:, 2]
+    assert np.abs(out["X"] - free["X"]).max() > 1e-2          # the rows are active
+    # pulled into the box as fast as the jerk / acceleration limits allow (soft rows, one SQP step)
+    viol = lambda z: float(np.sum(np.minimum(0.0, z[1:-1] + 0.02) ** 2))  # noqa: E731
+    assert viol(z_box) < 0.3 * viol(z_free)
+    assert z_box[4:-1].min() > -0.05 and z_free[4] < -0.12

@@ -90,6 +90,8 @@ class ProblemDesc(C.Structure):
         ("alpha_decay", C.c_double), ("alpha_min", C.c_double), ("g_max", C.c_double),
         ("g_min", C.c_double), ("gamma_c", C.c_double), ("armijo_factor", C.c_double),
         ("delta_tol", C.c_double), ("cost_tol", C.c_double),
+        ("ee_box_enabled", C.c_int32), ("reserved0", C.c_int32),
+        ("ee_box_lower", C.c_double * 3), ("ee_box_upper", C.c_double * 3),
     ]
 
     # convenience

@@ -84,11 +84,12 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
     P.nu = d.nq + P.nfc;
     P.neq = bal ? 6 * d.nb : 0;
     P.nfric = (bal && d.nf == 3) ? 5 * d.nc : 0;
-    P.nobs = d.obstacles_enabled ? d.n_pairs : 0;
+    P.npairs = d.obstacles_enabled ? d.n_pairs : 0;
+    P.eebox = d.ee_box_enabled ? 1 : 0;
+    P.nobs = P.npairs + (P.eebox ? 6 : 0);   // end-effector box rows ride behind the sphere-pair rows
     P.nterm = 3 + 2 * d.nq;
     P.N = d.N;
     P.nsph = d.obstacles_enabled ? d.n_spheres : 0;
-    P.npairs = P.nobs;
     P.nz = P.nu + P.nx;
     P.nbox_u = P.nfc > 0 ? P.nu : P.nq;
     P.nrow = P.nbox_u + P.nx + P.nfric + P.nobs;
@@ -165,6 +166,10 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
         P.pb[i] = d.pairs[i].b;
     }
     P.dmin = T(d.minimum_distance);
+    for (int c = 0; c < 3; ++c) {
+        P.eb_lo[c] = T(d.ee_box_lower[c]);
+        P.eb_hi[c] = T(d.ee_box_upper[c]);
+    }
 }
 
 template <typename T>
@@ -279,7 +284,7 @@ int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
     if (!generic_only && H.balancing && H.N == 20) {
         const bool no_obs = H.nobs == 0;
         if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::thing_1obj();
-        if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12) fn = Pick<T>::thing_obs12();
+        if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12 && !H.eebox) fn = Pick<T>::thing_obs12();
         if (H.nq == 6 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::ur10_1obj();
         if (H.nq == 9 && H.nf == 3 && H.nc == 16 && H.nb == 3 && no_obs) fn = Pick<T>::thing_arch();
         if (H.nq == 9 && H.nf == 1 && H.nc == 32 && H.nb == 8 && no_obs) fn = Pick<T>::thing_robust8();
@@ -572,6 +577,10 @@ int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
     if (desc->nf != 1 && desc->nf != 3) return fail(UB_E_INVALID, "nf must be 1 or 3");
     if (desc->N < 1 || desc->N > 128) return fail(UB_E_INVALID, "N out of range");
     if (desc->n_spheres > UB_MAX_SPHERES || desc->n_pairs > UB_MAX_PAIRS) return fail(UB_E_INVALID, "too many spheres / pairs");
+    if (desc->ee_box_enabled)
+        for (int c = 0; c < 3; ++c)
+            if (!(desc->ee_box_lower[c] < desc->ee_box_upper[c]))
+                return fail(UB_E_INVALID, "end-effector box: xyz_lower must be below xyz_upper");
     if (desc->ee_weight[3] != 0 || desc->ee_weight[4] != 0 || desc->ee_weight[5] != 0)
         return fail(UB_E_INVALID, "end-effector orientation weight is not supported yet");
     if (desc->qp_method != 0) return fail(UB_E_INVALID, "only qp_method 0 (interior point) exists on the device");
@@ -708,7 +717,7 @@ float ub_last_solve_ms(const ub_problem_t* p) {
 // thread per sample.
 namespace {
 
-enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4 };
+enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4, EV_EEBOX = 5 };
 
 __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int what, int M, int rows,
                             const double* __restrict__ x, const double* __restrict__ u,
@@ -724,7 +733,7 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
     ub::Kin<double> K;
     ub::KinTan<double> D;
     double sph[3 * UB_MAX_SPHERES];
-    ub::forward_kinematics<double, false>(P, xm, -1, K, D, P.nobs > 0 ? sph : nullptr, nullptr);
+    ub::forward_kinematics<double, false>(P, xm, -1, K, D, P.npairs > 0 ? sph : nullptr, nullptr);
     const int nq = P.nq;
     if (what == EV_EEPOS) {
         o[0] = K.r.x; o[1] = K.r.y; o[2] = K.r.z;
@@ -764,8 +773,13 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
             o[5 * c + 3] = mu * fn + t0 - t1;
             o[5 * c + 4] = mu * fn + t0 + t1;
         }
+    } else if (what == EV_EEBOX) {   // end_effector_box_constraint.h:46-58
+        for (int c = 0; c < 3; ++c) {
+            o[c] = target[3 * m + c] + P.eb_hi[c] - K.r[c];
+            o[3 + c] = K.r[c] - target[3 * m + c] - P.eb_lo[c];
+        }
     } else if (what == EV_OBST) {
-        for (int i = 0; i < P.nobs; ++i) {
+        for (int i = 0; i < P.npairs; ++i) {
             const int a = P.pa[i], b = P.pb[i];
             const ub::V3<double> d(sph[3 * a] - sph[3 * b], sph[3 * a + 1] - sph[3 * b + 1], sph[3 * a + 2] - sph[3 * b + 2]);
             o[i] = sqrt(ub::dot(d, d)) - (P.srad[a] + P.srad[b] + P.dmin);
@@ -795,7 +809,12 @@ extern "C" int ub_eval(ub_problem_t* p, const char* name, int32_t M, const doubl
     const std::string n(name);
     if (n == "object_dynamics") { what = EV_OBJDYN; rows = P.neq; }
     else if (n == "contact_forces") { what = EV_CONTACT; rows = P.nfric; }
-    else if (n == "obstacle_avoidance") { what = EV_OBST; rows = P.nobs; }
+    else if (n == "obstacle_avoidance") { what = EV_OBST; rows = P.npairs; }
+    else if (n == "end_effector_box_constraint") {
+        what = EV_EEBOX;
+        rows = P.eebox ? 6 : 0;
+        if (rows && !target) return fail(UB_E_INVALID, "end_effector_box_constraint needs the desired position (target)");
+    }
     else if (n == "end_effector_position") { what = EV_EEPOS; rows = 3; }
     else if (n == "cost") { what = EV_COST; rows = 1; }
     else return fail(UB_E_INVALID, "unknown probe name " + n);

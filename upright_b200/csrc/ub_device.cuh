@@ -37,6 +37,9 @@ struct DevProblem {
     T srad[UB_MAX_SPHERES], soff[UB_MAX_SPHERES][3];
     int pa[UB_MAX_PAIRS], pb[UB_MAX_PAIRS];
     T dmin;
+    // end-effector box rows (end_effector_box_constraint.h): appended to the obstacle rows, nobs = npairs + 6
+    int eebox;
+    T eb_lo[3], eb_hi[3];
 };
 
 // ------------------------------------------------------------------ vectors

@@ -154,6 +154,10 @@ struct Solver {
     UB_DIM(NQ, nq) UB_DIM(NX, nx) UB_DIM(NU, nu) UB_DIM(NZ, nz) UB_DIM(NFC, nfc) UB_DIM(NEQ, neq) UB_DIM(NFRIC, nfric)
     UB_DIM(NBOXU, nbox_u) UB_DIM(NB, nb) UB_DIM(NC, nc) UB_DIM(NF, nf) UB_DIM(NN, N) UB_DIM(NOBS, nobs)
 #undef UB_DIM
+    // end-effector box rows exist only in the run-time-dimension kernel (the specialised ones are not dispatched
+    // for such problems)
+    __device__ __forceinline__ bool EEBOX() const { if constexpr (D::kStatic) return false; else return P.eebox != 0; }
+    __device__ __forceinline__ int NPAIRS() const { if constexpr (D::kStatic) return D::nobs; else return P.npairs; }
     // workspace / shared-memory offsets: immediates for the specialised kernels
 #define UB_OFF(name) \
     __device__ __forceinline__ int o##name() const { if constexpr (D::kStatic) { constexpr Layout l = D::template layout<T>(); return l.name; } else return L.name; }
@@ -437,7 +441,7 @@ struct Solver {
             const T* x = X + k * nx;
             Kin<T> Kn;
             KinTan<T> Dt;
-            forward_kinematics<T, true>(P, x, lane, Kn, Dt, NOBS() > 0 ? sph : nullptr, dsph);
+            forward_kinematics<T, true>(P, x, lane, Kn, Dt, NPAIRS() > 0 ? sph : nullptr, dsph);
             if (lane == 0) {
                 ws[oLR() + 3 * k] = Kn.r.x;
                 ws[oLR() + 3 * k + 1] = Kn.r.y;
@@ -477,7 +481,7 @@ struct Solver {
                 }
             }
             if (NOBS() > 0) {
-                for (int i = 0; i < NOBS(); ++i) {
+                for (int i = 0; i < NPAIRS(); ++i) {
                     const int a = P.pa[i], bb = P.pb[i];
                     const V3<T> d(sph[3 * a] - sph[3 * bb], sph[3 * a + 1] - sph[3 * bb + 1], sph[3 * a + 2] - sph[3 * bb + 2]);
                     const T dist = sqrt(dot(d, d));
@@ -485,6 +489,22 @@ struct Solver {
                                    dsph[3 * a + 2] - dsph[3 * bb + 2]);
                     if (lane == 0) ws[oLHO() + k * NOBS() + i] = dist - (P.srad[a] + P.srad[bb] + C.dmin);
                     if (lane < nq) ws[oLJO() + (k * NOBS() + i) * nq + lane] = dot(d, dd) / dist;
+                }
+                if (EEBOX()) {
+                    // rows npairs..+2: r_d + upper - r >= 0; rows npairs+3..+5: r - r_d - lower >= 0
+                    // (end_effector_box_constraint.h:46-76)
+                    const T* tg = target + 3 * k;
+                    for (int c = 0; c < 3; ++c) {
+                        const int iu = NPAIRS() + c, il = NPAIRS() + 3 + c;
+                        if (lane == 0) {
+                            ws[oLHO() + k * NOBS() + iu] = tg[c] + P.eb_hi[c] - Kn.r[c];
+                            ws[oLHO() + k * NOBS() + il] = Kn.r[c] - tg[c] - P.eb_lo[c];
+                        }
+                        if (lane < nq) {
+                            ws[oLJO() + (k * NOBS() + iu) * nq + lane] = -Dt.r[c];
+                            ws[oLJO() + (k * NOBS() + il) * nq + lane] = Dt.r[c];
+                        }
+                    }
                 }
             }
             // dynamics gap b_k = A x_k + B u_k - x_{k+1}  (exact triple integrator, system_dynamics.h:15-26)
@@ -513,7 +533,7 @@ struct Solver {
             const T* x = Xt + k * nx;
             Kin<T> Kn;
             KinTan<T> Dn;
-            forward_kinematics<T, false>(P, x, -1, Kn, Dn, NOBS() > 0 ? sph : nullptr, nullptr);
+            forward_kinematics<T, false>(P, x, -1, Kn, Dn, NPAIRS() > 0 ? sph : nullptr, nullptr);
             const T* rd = target + 3 * k;
             if (k == N) {
                 for (int i = 0; i < 3; ++i) {
@@ -584,7 +604,8 @@ struct Solver {
                 min_margin = min(min_margin, h);
             }
             if (k >= 1)
-                for (int i = 0; i < NOBS(); ++i) {
+            {
+                for (int i = 0; i < NPAIRS(); ++i) {
                     const int a = P.pa[i], bb = P.pb[i];
                     const V3<T> d(sph[3 * a] - sph[3 * bb], sph[3 * a + 1] - sph[3 * bb + 1], sph[3 * a + 2] - sph[3 * bb + 2]);
                     const T h = sqrt(dot(d, d)) - (P.srad[a] + P.srad[bb] + C.dmin);
@@ -592,6 +613,14 @@ struct Solver {
                     ineq += dt * m * m;
                     min_margin = min(min_margin, h);
                 }
+                if (EEBOX())
+                    for (int c = 0; c < 3; ++c) {
+                        const T hu = rd[c] + P.eb_hi[c] - Kn.r[c], hl = Kn.r[c] - rd[c] - P.eb_lo[c];
+                        const T mu_ = min(T(0), hu), ml = min(T(0), hl);
+                        ineq += dt * (mu_ * mu_ + ml * ml);
+                        min_margin = min(min_margin, min(hu, hl));
+                    }
+            }
         }
         Perf<T> pf;
         pf.cost = warp_sum(cost);

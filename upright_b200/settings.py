@@ -300,6 +300,24 @@ class ControllerSettings:
         d.tool_p[:] = self.chain.tool_p
         d.gravity[:] = self.gravity
 
+        # features of the reference that are 'next' rows are rejected loudly, never ignored
+        if self.projectile_path_constraint_enabled:
+            raise NotImplementedError("projectile_path_constraint is a 'next' row (SURVEY §8f-2)")
+        ia = self.inertial_alignment_settings
+        if ia.cost_enabled or ia.constraint_enabled:
+            raise NotImplementedError("inertial_alignment cost / constraint is a 'next' row (SURVEY §8f-3)")
+        if self.use_operating_points:
+            raise NotImplementedError("the operating-point initializer is not supported (DefaultInitializer only)")
+        # EndEffectorBoxConstraint (end_effector_box_constraint.h; wrappers.py:240-250)
+        d.ee_box_enabled = int(bool(self.end_effector_box_constraint_enabled))
+        if d.ee_box_enabled:
+            lo, hi = np.asarray(self.xyz_lower, dtype=float), np.asarray(self.xyz_upper, dtype=float)
+            assert lo.shape == (3,) and hi.shape == (3,)
+            if not np.all(lo < hi):
+                raise ValueError("end_effector_box_constraint: xyz_lower must be below xyz_upper")
+            d.ee_box_lower[:] = lo
+            d.ee_box_upper[:] = hi
+
         Qd, Rd, Wd = np.diag(self.state_weight), np.diag(self.input_weight), np.diag(self.end_effector_weight)
         for M in (self.state_weight, self.input_weight, self.end_effector_weight):
             if np.abs(M - np.diag(np.diag(M))).max() > 0:
