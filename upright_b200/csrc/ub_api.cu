@@ -101,6 +101,7 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
     P.balancing = bal;
     P.dt = T(d.dt);
     P.Z = T(d.slacks.upper_L2_penalty > 0 ? d.slacks.upper_L2_penalty : 100.0);
+    P.invZ = T(1) / P.Z;
     P.rho_hard = T(d.rho_hard);
     P.mu0 = T(d.qp_mu0);
     P.thr0 = T(d.qp_thr0);

@@ -22,7 +22,7 @@ struct DevProblem {
     int nq, nx, nu, nfc, neq, nfric, nobs, nterm, nb, nc, nf, N, nsph, npairs;
     int nz, nbox_u, nrow, sqp_iters, qp_iter_max;
     int soft_u, soft_x, soft_poly, balancing;
-    T dt, Z, rho_hard, mu0, thr0, mu_target, qp_tol, reg_input, eps_hard;
+    T dt, Z, invZ, rho_hard, mu0, thr0, mu_target, qp_tol, reg_input, eps_hard;
     T alpha_decay, alpha_min, g_max, g_min, gamma_c, armijo, delta_tol, cost_tol;
     int jtype[UB_MAX_JOINTS];
     T jR[UB_MAX_JOINTS][9], jp[UB_MAX_JOINTS][3], jaxis[UB_MAX_JOINTS][3];
@@ -41,6 +41,12 @@ struct DevProblem {
     int eebox;
     T eb_lo[3], eb_hi[3];
 };
+
+// Division in the interior-point row updates (eight per inequality row and pass): the fp32 kernels use the
+// approximate reciprocal path (2 ulp, two instructions instead of ~nine); the Newton residuals themselves are
+// formed with exact operations, so this only perturbs the step at rounding level.
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double fdiv(double a, double b) { return a / b; }
 
 // ------------------------------------------------------------------ vectors
 template <typename T>

@@ -226,7 +226,7 @@ struct Solver {
     __device__ __forceinline__ bool row_soft(int fam) const {
         return fam == 0 ? C.soft_u : (fam == 1 ? C.soft_x : C.soft_poly);
     }
-    __device__ __forceinline__ T row_eps(int fam) const { return row_soft(fam) ? T(1) / C.Z : C.eps_hard; }
+    __device__ __forceinline__ T row_eps(int fam) const { return row_soft(fam) ? C.invZ : C.eps_hard; }
     // friction row coefficients on the 3 force components of contact c
     __device__ __forceinline__ V3<T> fric_coeff(int c, int which) const {
         const V3<T> n = ld3(P.cn[c]), s0 = ld3(P.cspan[c]), s1 = ld3(P.cspan[c] + 3);
@@ -381,7 +381,7 @@ struct Solver {
     __device__ __forceinline__ T side_coef(T t, T lam, T d, T eps, T target, T corr) const {
         const T rd = d + eps * lam - t;
         const T rc = t * lam - target + corr;
-        return -lam + (rc + lam * rd) / (t + eps * lam);
+        return -lam + fdiv(rc + lam * rd, t + eps * lam);
     }
     // stage vectors are stored with stride nz as [du (nu); dx (nx)]; the terminal
     // stage uses the same slots (its du part is unused and kept at zero)
@@ -856,7 +856,7 @@ struct Solver {
             if (!row_valid(k, fam)) continue;
             const T eps = row_eps(fam);
             const Quad q = recs(k)[2 * r];
-            const T w = q.v[2] / (q.v[0] + eps * q.v[2]) + q.v[3] / (q.v[1] + eps * q.v[3]);
+            const T w = fdiv(q.v[2], q.v[0] + eps * q.v[2]) + fdiv(q.v[3], q.v[1] + eps * q.v[3]);
             const int m = fam == 0 ? r : nu + (r - NBOXU());
             sM[m * ld + m] += w;
         }
@@ -868,7 +868,7 @@ struct Solver {
                 T blk[6] = {0, 0, 0, 0, 0, 0};
                 for (int which = 0; which < 5; ++which) {
                     const Quad q = recs(k)[2 * (nbx + 5 * c + which)];
-                    const T w = q.v[2] / (q.v[0] + eps * q.v[2]);
+                    const T w = fdiv(q.v[2], q.v[0] + eps * q.v[2]);
                     const V3<T> cf = fric_coeff(c, which);
                     blk[0] += w * cf.x * cf.x;
                     blk[1] += w * cf.y * cf.x;
@@ -892,7 +892,7 @@ struct Solver {
             T* wrow = sV + 4 * nz;  // barrier weights of the obstacle rows
             for (int i = lane; i < NOBS(); i += WARP) {
                 const Quad q = recs(k)[2 * (nbx + NFRIC() + i)];
-                wrow[i] = q.v[2] / (q.v[0] + eps * q.v[2]);
+                wrow[i] = fdiv(q.v[2], q.v[0] + eps * q.v[2]);
             }
             __syncwarp();
             for (int idx = lane; idx < nq * nq; idx += WARP) {
@@ -1389,8 +1389,8 @@ struct Solver {
                 const T eps = row_eps(fam);
                 const Quad q = recs(k)[2 * r];
                 const Quad dd = recs(k)[2 * r + 1];
-                vec[m] += (dd.v[0] * dd.v[2] - target_mu) / (q.v[0] + eps * q.v[2]) -
-                          (dd.v[1] * dd.v[3] - target_mu) / (q.v[1] + eps * q.v[3]);
+                vec[m] += fdiv(dd.v[0] * dd.v[2] - target_mu, q.v[0] + eps * q.v[2]) -
+                          fdiv(dd.v[1] * dd.v[3] - target_mu, q.v[1] + eps * q.v[3]);
             }
             __syncwarp();
             if (NFRIC() > 0 && k < NN()) {
@@ -1402,7 +1402,7 @@ struct Solver {
                         const V3<T> a = fric_coeff(c, which);
                         const Quad q = recs(k)[2 * r];
                         const Quad dd = recs(k)[2 * r + 1];
-                        const T cf = (dd.v[0] * dd.v[2] - target_mu) / (q.v[0] + eps * q.v[2]);
+                        const T cf = fdiv(dd.v[0] * dd.v[2] - target_mu, q.v[0] + eps * q.v[2]);
                         g0 += cf * a.x;
                         g1 += cf * a.y;
                         g2 += cf * a.z;
@@ -1420,7 +1420,7 @@ struct Solver {
                     const int r = nbx + NFRIC() + i;
                     const Quad q = recs(k)[2 * r];
                     const Quad dd = recs(k)[2 * r + 1];
-                    crow[i] = (dd.v[0] * dd.v[2] - target_mu) / (q.v[0] + eps * q.v[2]);
+                    crow[i] = fdiv(dd.v[0] * dd.v[2] - target_mu, q.v[0] + eps * q.v[2]);
                 }
                 __syncwarp();
                 if (lane < nq) {
@@ -1498,12 +1498,13 @@ struct Solver {
                 const T rd = dist + eps * lam - t;
                 const T rc = t * lam - target_mu + cm * dd.v[sd] * dd.v[2 + sd];
                 const T den = t + eps * lam;
-                const T dl = -(rc + lam * rd) / den - (lam / den) * sg * adz;
+                const T iden = fdiv(T(1), den);
+                const T dl = -(rc + lam * rd) * iden - (lam * iden) * sg * adz;
                 const T dtt = sg * adz + eps * dl + rd;
                 dd.v[sd] = dtt;
                 dd.v[2 + sd] = dl;
-                if (dtt < T(0)) amax = min(amax, -t / dtt);
-                if (dl < T(0)) amax = min(amax, -lam / dl);
+                if (dtt < T(0)) amax = min(amax, fdiv(-t, dtt));
+                if (dl < T(0)) amax = min(amax, fdiv(-lam, dl));
             }
             *side_dd(k, r) = dd;
         }
