@@ -154,7 +154,7 @@ def main():
                           f"N={desc.N} knots, nx={desc.nx}, nu={desc.nu}",
               "global_batch": B * world, "per_gpu_batch": B, "seed": 1234,
               "parallelism": f"dp{world} (independent instances sharded, one NCCL all-gather of X,U)" if world > 1 else "dp1",
-              "l2": "no explicit flush: per-step working set (workspace) exceeds the 126 MB L2; inputs differ every step"}
+              "l2": "no explicit flush: the per-step working set (246 MB of workspace slots, rewritten every interior-point iteration) exceeds the 126 MB L2; inputs differ every step"}
 
     # ------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -327,7 +327,7 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "upright_b200.engine.BatchedMPC.solve -> ub_solve_batch (host double buffers)",
+                    "api": "upright_b200.engine.BatchedMPC.solve -> ub_solve_batch (host double buffers in/out; inputs H2D from pinned staging, every solved instance written home by the kernel through mapped pinned memory, float<->double conversion on host threads)",
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "roofline": roofline,
             "converged_fraction": float(np.mean(ok)), "mean_qp_iterations": mean_iters}

@@ -5,11 +5,15 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstddef>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -18,6 +22,7 @@
 #include "ub_receding.cuh"
 
 extern "C" int ub_set_option(ub_problem_t* p, const char* key, int value);
+extern "C" float ub_last_solve_ms(const ub_problem_t* p);
 
 namespace {
 
@@ -46,29 +51,99 @@ int conversion_threads() {
     }();
     return n;
 }
-template <typename Fn>
-void parallel_chunks(size_t n, Fn fn) {
-    const size_t min_chunk = 1 << 16;
-    int nt = int(std::min<size_t>(conversion_threads(), (n + min_chunk - 1) / min_chunk));
-    if (nt <= 1) {
-        fn(size_t(0), n);
-        return;
+// A small persistent worker pool (threads are created once per process): parallel_for(n_tasks, fn) runs
+// fn(task) for task in [0, n_tasks) on the workers plus the calling thread and returns when all are done.
+class WorkerPool {
+  public:
+    static WorkerPool& get() {
+        static WorkerPool pool(conversion_threads() - 1);
+        return pool;
     }
-    std::vector<std::thread> th;
-    th.reserve(nt - 1);
-    const size_t per = (n + nt - 1) / nt;
-    for (int t = 1; t < nt; ++t) {
-        const size_t a = std::min(n, per * t), b = std::min(n, per * (t + 1));
-        th.emplace_back([=] { fn(a, b); });
+    void parallel_for(int n_tasks, const std::function<void(int)>& fn) {
+        if (n_tasks <= 1 || workers_.empty()) {
+            for (int t = 0; t < n_tasks; ++t) fn(t);
+            return;
+        }
+        std::unique_lock<std::mutex> call_lock(call_mutex_);   // one parallel region at a time
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn;
+            n_tasks_ = n_tasks;
+            next_.store(0);
+            pending_ = n_tasks;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        run_tasks();
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
     }
-    fn(size_t(0), std::min(n, per));
-    for (auto& t : th) t.join();
+
+  private:
+    explicit WorkerPool(int n) {
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { worker(); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void run_tasks() {
+        for (;;) {
+            const int t = next_.fetch_add(1);
+            if (t >= n_tasks_) break;
+            (*fn_)(t);
+            std::lock_guard<std::mutex> lk(m_);
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+    void worker() {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
+                if (stop_) return;
+                seen = epoch_;
+            }
+            run_tasks();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_, call_mutex_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_tasks_ = 0, pending_ = 0;
+    unsigned long long epoch_ = 0;
+    bool stop_ = false;
+};
+
+// Element-wise conversion of several (dst, src, n) segments in ONE parallel region
+template <typename Dst, typename Src>
+struct Segment {
+    Dst* dst;
+    const Src* src;
+    size_t n;
+};
+template <typename Dst, typename Src>
+void convert_segments(const std::vector<Segment<Dst, Src>>& segs) {
+    const size_t chunk = 1 << 15;
+    std::vector<Segment<Dst, Src>> tasks;
+    for (const auto& sg : segs)
+        for (size_t o = 0; o < sg.n; o += chunk) tasks.push_back({sg.dst + o, sg.src + o, std::min(chunk, sg.n - o)});
+    WorkerPool::get().parallel_for(int(tasks.size()), [&](int t) {
+        const auto& k = tasks[t];
+        for (size_t i = 0; i < k.n; ++i) k.dst[i] = Dst(k.src[i]);
+    });
 }
 template <typename Dst, typename Src>
 void convert_array(Dst* dst, const Src* src, size_t n) {
-    parallel_chunks(n, [=](size_t a, size_t b) {
-        for (size_t i = a; i < b; ++i) dst[i] = Dst(src[i]);
-    });
+    if (n) convert_segments<Dst, Src>({{dst, src, n}});
 }
 
 template <typename T>
@@ -298,7 +373,7 @@ int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
 template <typename T>
 int solve_device(ub_problem* p, int B, const void* x0, const void* target, const void* body, void* X, void* U, void* K,
                  int32_t* status, void* stats, void* ws, int64_t ws_bytes, uint32_t flags, cudaStream_t stream,
-                 int gain_stages = -1) {
+                 int gain_stages = -1, const void* Xin = nullptr, const void* Uin = nullptr) {
     const ub::Layout& L = Pick<T>::layout(p);
     if (ws_bytes < workspace_bytes<T>(p, B)) return fail(UB_E_INVALID, "workspace too small (see ub_workspace_bytes)");
     if (reinterpret_cast<uintptr_t>(ws) % 16 != 0) return fail(UB_E_INVALID, "workspace must be 16-byte aligned");
@@ -308,6 +383,8 @@ int solve_device(ub_problem* p, int B, const void* x0, const void* target, const
     A.body = static_cast<const T*>(body);
     A.X = static_cast<T*>(X);
     A.U = static_cast<T*>(U);
+    A.Xin = Xin ? static_cast<const T*>(Xin) : A.X;
+    A.Uin = Uin ? static_cast<const T*>(Uin) : A.U;
     A.K = static_cast<T*>(K);
     A.status = status;
     A.stats = static_cast<T*>(stats);
@@ -352,20 +429,24 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
         if (cudaMallocHost(&p->pinned, pin_bytes) != cudaSuccess) return fail(UB_E_ALLOC, "cudaMallocHost failed");
         p->pinned_bytes = pin_bytes;
     }
+    static const bool timing = std::getenv("UB_HOST_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    const auto t_start = now();
     T* h = static_cast<T*>(p->pinned);
     T* d = static_cast<T*>(p->dev_buf);
     // staging order: x0 | target | body | X | U | K | stats   (device adds workspace, status)
-    size_t o = 0;
-    convert_array(h + o, x0, n_x0);
-    o += n_x0;
-    convert_array(h + o, target, n_tg);
-    o += n_tg;
-    if (n_bd) convert_array(h + o, body, n_bd);
-    o += n_bd;
-    const size_t oX = o;
+
+    const size_t oX = n_in;
+    {
+        std::vector<Segment<T, double>> in = {{h, x0, n_x0}, {h + n_x0, target, n_tg}};
+        if (n_bd) in.push_back({h + n_x0 + n_tg, body, n_bd});
+        if (flags & UB_WARM_START) {
+            in.push_back({h + oX, X, n_X});
+            in.push_back({h + oX + n_X, U, n_U});
+        }
+        convert_segments(in);
+    }
     if (flags & UB_WARM_START) {
-        convert_array(h + oX, X, n_X);
-        convert_array(h + oX + n_X, U, n_U);
         UB_CUDA(cudaMemcpyAsync(d, h, (n_in + n_io) * sizeof(T), cudaMemcpyHostToDevice, stream));
     } else {
         UB_CUDA(cudaMemcpyAsync(d, h, n_in * sizeof(T), cudaMemcpyHostToDevice, stream));
@@ -375,23 +456,31 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
     T* d_bd = body ? d + n_x0 + n_tg : nullptr;
     T* d_X = d + oX;
     T* d_U = d_X + n_X;
-    T* d_K = K ? d_U + n_U : nullptr;
-    T* d_st = d_U + n_U + n_K;
-    T* d_ws = d_st + n_st;
+    T* d_ws = d_U + n_U + n_K + n_st;   // (the K / stats slots of the device buffer stay unused: results go home directly)
     while (reinterpret_cast<uintptr_t>(d_ws) % 16 != 0) ++d_ws;  // vectorised factor copies need 16-byte alignment
-    int32_t* d_status = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_ws + n_ws) + 64 - (reinterpret_cast<uintptr_t>(d_ws + n_ws) % 64));
-    int rc = solve_device<T>(p, B, d_x0, d_tg, d_bd, d_X, d_U, d_K, d_status, d_st, d_ws, int64_t(n_ws * sizeof(T)),
-                             flags | UB_PTRS_DEVICE, stream);
-    if (rc != UB_OK) return rc;
+    // The kernel writes X, U, K, stats and status of every instance straight into the (mapped) pinned staging
+    // buffer as soon as that instance is solved: the results cross PCIe while the rest of the batch is still being
+    // solved and no device->host copy follows the kernel.  The warm-start inputs are read from the device copy.
     int32_t* h_status = reinterpret_cast<int32_t*>(h + stage_elems);
-    UB_CUDA(cudaMemcpyAsync(h + oX, d_X, (n_io + n_K + n_st) * sizeof(T), cudaMemcpyDeviceToHost, stream));
-    UB_CUDA(cudaMemcpyAsync(h_status, d_status, size_t(B) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    const auto t_in = now();
+    int rc = solve_device<T>(p, B, d_x0, d_tg, d_bd, h + oX, h + oX + n_X, K ? h + oX + n_io : nullptr, h_status,
+                             h + oX + n_io + n_K, d_ws, int64_t(n_ws * sizeof(T)), flags | UB_PTRS_DEVICE, stream, -1,
+                             d_X, d_U);
+    if (rc != UB_OK) return rc;
     UB_CUDA(cudaStreamSynchronize(stream));
-    convert_array(X, h + oX, n_X);
-    convert_array(U, h + oX + n_X, n_U);
-    if (n_K) convert_array(K, h + oX + n_io, n_K);
-    if (stats) convert_array(stats, h + oX + n_io + n_K, n_st);
+    const auto t_sync = now();
+    {
+        std::vector<Segment<double, T>> outs = {{X, h + oX, n_X}, {U, h + oX + n_X, n_U}};
+        if (n_K) outs.push_back({K, h + oX + n_io, n_K});
+        if (stats) outs.push_back({stats, h + oX + n_io + n_K, n_st});
+        convert_segments(outs);
+    }
     std::memcpy(status, h_status, size_t(B) * sizeof(int32_t));
+    if (timing) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[ub host] convert-in+H2D issue %.3f ms, kernel+copies %.3f ms (kernel %.3f), convert-out %.3f ms\n",
+                     ms(t_start, t_in), ms(t_in, t_sync), double(ub_last_solve_ms(p)), ms(t_sync, now()));
+    }
     if constexpr (sizeof(T) == 4) {
         if (flags & UB_RESCUE_F64) {
             // fp32 breakdown (a factorisation that lost positive definiteness to roundoff): the few instances

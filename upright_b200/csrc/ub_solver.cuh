@@ -91,8 +91,10 @@ struct BatchArgs {
     const T* x0;      // [B, nx]
     const T* target;  // [B, N+1, 3]
     const T* body;    // [B, nb, 10] or null
-    T* X;             // [B, N+1, nx]
-    T* U;             // [B, N, nu]
+    T* X;             // [B, N+1, nx]  solution out (device memory, or mapped pinned host memory: the host path lets
+    T* U;             // [B, N, nu]    the kernel write results home while other instances are still being solved)
+    const T* Xin;     // warm start in (UB_WARM_START); may alias X
+    const T* Uin;
     T* K;             // [B, N, nu, nx] or null
     int32_t* status;  // [B]
     T* stats;         // [B, UB_STATS] or null
@@ -1828,8 +1830,8 @@ struct Solver {
                 for (int idx = lane; idx < (N + 1) * nx; idx += WARP) X[idx] = x0[idx % nx];
                 for (int idx = lane; idx < N * nu; idx += WARP) U[idx] = T(0);
             } else {
-                const T* Xin = A.X + size_t(b) * (N + 1) * nx;
-                const T* Uin = A.U + size_t(b) * N * nu;
+                const T* Xin = A.Xin + size_t(b) * (N + 1) * nx;
+                const T* Uin = A.Uin + size_t(b) * N * nu;
                 for (int idx = lane; idx < (N + 1) * nx; idx += WARP) X[idx] = idx < nx ? x0[idx] : Xin[idx];
                 for (int idx = lane; idx < N * nu; idx += WARP) U[idx] = Uin[idx];
             }
