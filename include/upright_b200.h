@@ -158,6 +158,14 @@ typedef struct ub_problem_desc {
     int32_t ee_box_enabled;
     int32_t reserved0;
     double ee_box_lower[3], ee_box_upper[3];
+
+    /* InertialAlignmentCostGaussNewton (inertial_alignment.h:146-204, src/inertial_alignment.cpp:90-163;
+     * added to the problem at controller_interface.cpp:296-305): intermediate cost
+     * 1/2 w |S C_we' (a - g) / |g||^2 with the Gauss-Newton Hessian w J'J; S = contact_plane_span (2x3) */
+    int32_t ia_cost_enabled;
+    int32_t reserved1;
+    double ia_cost_weight;
+    double ia_span[6];
 } ub_problem_desc_t;
 
 typedef struct ub_problem ub_problem_t;
@@ -215,7 +223,8 @@ int ub_solve_batch(ub_problem_t* problem, int32_t B, const void* x0, const void*
  * and getCostValue (controller_python_interface.h:31-88), batched: evaluates
  * at M (x,u) pairs on the device.  Host double pointers.
  *   name in {"object_dynamics","contact_forces","obstacle_avoidance",
- *            "end_effector_box_constraint" (needs target),"end_effector_position","cost"}
+ *            "end_effector_box_constraint" (needs target),"end_effector_position","cost",
+ *            "inertial_alignment_cost"}
  *   out [M, rows]; rows returned through *rows_out. */
 int ub_eval(ub_problem_t* problem, const char* name, int32_t M, const double* x,
             const double* u, const double* target /*[M,3] or NULL*/,

@@ -178,6 +178,17 @@ void contact_force_constraints(const ub_problem_desc_t& P, const S* forces, S* h
     }
 }
 
+// InertialAlignmentCostGaussNewton::function (upright_control/src/inertial_alignment.cpp:151-163):
+// e = S C_we' (a - g) / |g|, S = contact_plane_span (2 x 3)
+template <typename S>
+void inertial_alignment_error(const ub_problem_desc_t& P, const Kinematics<S>& X, S* e) {
+    const Vec3<S> gravity = vec3_from<S>(P.gravity);
+    const double gn = std::sqrt(P.gravity[0] * P.gravity[0] + P.gravity[1] * P.gravity[1] + P.gravity[2] * P.gravity[2]);
+    const Vec3<S> a_e = X.C_we.transpose() * (X.a - gravity);
+    e[0] = dot(vec3_from<S>(P.ia_span), a_e) / S(gn);
+    e[1] = dot(vec3_from<S>(P.ia_span + 3), a_e) / S(gn);
+}
+
 // Sphere-sphere distances minus the minimum distance, h >= 0.  Closed form of
 // ocs2::SelfCollisionConstraintCppAd + hpp-fcl for sphere pairs
 // (upright_control/src/controller_interface.cpp:450-481).

@@ -104,6 +104,8 @@ struct KnotLin {
     Mat Ffric;                  // d hfric / d f (nfric x nfc)
     std::vector<double> hobs;   // obstacle rows value, nobs
     Mat Jobs;                   // d hobs / d q (nobs x nq)
+    double ea[2] = {0, 0};      // inertial-alignment residual
+    Mat Jea;                    // d ea / d x (2 x nx)
 };
 
 static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const double* body_params, const double* x,
@@ -152,6 +154,15 @@ static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const doub
             contact_force_constraints<double>(P, f.data(), h1.data());
             f[j] = 0.0;
             for (int i = 0; i < D.nfric; ++i) L.Ffric(i, j) = h1[i] - h0[i];
+        }
+    }
+    L.Jea = Mat(2, nx);
+    if (P.ia_cost_enabled) {
+        Dual e[2];
+        inertial_alignment_error<Dual>(P, K, e);
+        for (int r = 0; r < 2; ++r) {
+            L.ea[r] = e[r].v;
+            for (int j = 0; j < nx; ++j) L.Jea(r, j) = e[r].d[j];
         }
     }
     L.hobs.assign(D.npairs, 0.0);
@@ -242,6 +253,11 @@ static Perf performance(const ub_problem_desc_t& P, const Dims& D, const Mat& A,
         for (int i = 0; i < nq; ++i) c += 0.5 * P.input_weight[i] * sq(u[i]);
         for (int i = 0; i < D.nfc; ++i) c += 0.5 * P.force_weight * sq(u[nq + i]);
         for (int i = 0; i < 3; ++i) c += 0.5 * P.ee_weight[i] * sq(K.r[i] - rd[i]);
+        if (P.ia_cost_enabled) {   // inertial_alignment.cpp:118-124
+            double e[2];
+            inertial_alignment_error<double>(P, K, e);
+            c += 0.5 * P.ia_cost_weight * (sq(e[0]) + sq(e[1]));
+        }
         pf.cost += dt * c;
         const double* xn = X + size_t(k + 1) * nx;
         for (int i = 0; i < nx; ++i) {
@@ -347,6 +363,14 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
                     s.g[xo + a] += w * (L.r[c] - rd[c]);
                     for (int b = 0; b < nq; ++b) s.H(xo + a, xo + b) += w * L.Jp(c, b);
                 }
+            // inertial-alignment cost, Gauss-Newton (inertial_alignment.cpp:126-149)
+            if (P.ia_cost_enabled)
+                for (int a = 0; a < nx; ++a)
+                    for (int r = 0; r < 2; ++r) {
+                        const double w = dt * P.ia_cost_weight * L.Jea(r, a);
+                        s.g[xo + a] += w * L.ea[r];
+                        for (int b = 0; b < nx; ++b) s.H(xo + a, xo + b) += w * L.Jea(r, b);
+                    }
             // dynamics gap
             const double* xn = X + size_t(k + 1) * nx;
             s.b.assign(nx, 0.0);

@@ -378,3 +378,40 @@ def test_end_effector_box_constraint_parity():
     eu = (np.abs(o32["U"] - ref["U"]) / ru).reshape(12, -1).max(axis=1)
     ok = o32["status"] == ref["status"]
     assert ok.mean() >= 0.9 and np.median(ex[ok]) <= 3e-4 and ex[ok].max() <= 1e-2 and eu[ok].max() <= 1e-2
+
+
+def test_inertial_alignment_cost_parity():
+    """InertialAlignmentCostGaussNewton (inertial_alignment.cpp:90-163): probe value, linearisation blocks and the
+    full solve of the fp64 kernels against the oracle (1e-7), fp32 within the stated tolerance."""
+    import copy
+    from upright_b200 import geometry as geo
+    base, meta = problem_io.load_fixture("cfg2_thing_demo")
+    desc = copy.deepcopy(base)
+    desc.ia_cost_enabled = 1
+    desc.ia_cost_weight = 50.0
+    desc.ia_span[:] = geo.plane_span([0, 0, 1]).reshape(6)
+    b = batch_for("cfg2_thing_demo", 10, 91)
+    m64, m32 = BatchedMPC(desc, "f64"), BatchedMPC(desc, "f32")
+    # probe: 1/2 w e'e at a moving state
+    rng = np.random.default_rng(2)
+    x = b["x0"].copy()
+    x[:, 9:] = 0.3 * rng.standard_normal((10, 18))
+    S = np.array(list(desc.ia_span)).reshape(2, 3)
+    val = m64.eval("inertial_alignment_cost", x, np.zeros((10, 13)))[:, 0]
+    for i in range(10):
+        k = oracle.fk(desc, x[i])
+        e = S @ (np.array(k["C"]).reshape(3, 3).T @ (np.array(k["a"]) - np.array(list(desc.gravity)))) / 9.81
+        assert val[i] == pytest.approx(0.5 * 50.0 * e @ e, rel=1e-10, abs=1e-14)
+    ref = oracle.solve_batch(desc, b["x0"], b["target"], b["body_params"])
+    o64 = m64.solve(b["x0"], b["target"], b["body_params"])
+    assert (o64["status"] == ref["status"]).all()
+    assert np.abs(o64["X"] - ref["X"]).max() < 1e-7 and np.abs(o64["U"] - ref["U"]).max() < 1e-7
+    assert np.abs(o64["stats"][:, 1] - ref["stats"][:, 1]).max() < 1e-8           # cost incl. the alignment term
+    plain = BatchedMPC(base, "f64").solve(b["x0"], b["target"], b["body_params"])
+    assert np.abs(o64["X"] - plain["X"]).max() > 1e-4                               # the cost acts
+    o32 = m32.solve(b["x0"], b["target"], b["body_params"])
+    rx, ru = ranges(desc)
+    ex = (np.abs(o32["X"] - ref["X"]) / rx).reshape(10, -1).max(axis=1)
+    eu = (np.abs(o32["U"] - ref["U"]) / ru).reshape(10, -1).max(axis=1)
+    ok = o32["status"] == ref["status"]
+    assert ok.mean() >= 0.9 and np.median(ex[ok]) <= 3e-4 and ex[ok].max() <= 1e-2 and eu[ok].max() <= 1e-2

@@ -154,10 +154,25 @@ def test_end_effector_box_and_next_rows():
     bad["end_effector_box_constraint"]["xyz_lower"] = [2.0, -1.0, -0.05]
     with pytest.raises(ValueError):
         settings.ControllerSettings(bad, x0=np.array(meta["x0"])).to_desc()
-    for key, patch in (("inertial_alignment", {"cost_enabled": True, "constraint_enabled": False}),
+    for key, patch in (("inertial_alignment", {"cost_enabled": False, "constraint_enabled": True, "alpha": 0.1}),
                        ("projectile_path_constraint", {"enabled": True}),
                        ("operating_points", {"enabled": True})):
         c2 = copy.deepcopy(meta["controller_config"])
         c2[key] = dict(c2.get(key, {}), **patch)
         with pytest.raises(NotImplementedError):
             settings.ControllerSettings(c2, x0=np.array(meta["x0"])).to_desc()
+
+
+def test_inertial_alignment_cost_settings():
+    """InertialAlignmentCostGaussNewton settings (wrappers.py:332-345) reach the C description."""
+    import copy
+    from upright_b200 import geometry as geo
+    d, meta = problem_io.load_fixture("cfg2_thing_demo")
+    cfg = copy.deepcopy(meta["controller_config"])
+    cfg["inertial_alignment"] = {"cost_enabled": True, "constraint_enabled": False, "use_angular_acceleration": False,
+                                 "align_with_fixed_vector": False, "cost_weight": 2.5, "contact_plane_normal": [0, 0, 2],
+                                 "com": [0, 0, 0], "alpha": 0}
+    desc = settings.ControllerSettings(cfg, x0=np.array(meta["x0"])).to_desc()
+    assert desc.ia_cost_enabled == 1 and desc.ia_cost_weight == 2.5
+    S = np.array(list(desc.ia_span)).reshape(2, 3)
+    assert np.allclose(S, geo.plane_span([0, 0, 1])) and np.allclose(S @ [0, 0, 1], 0) and np.allclose(S @ S.T, np.eye(2))

@@ -168,3 +168,57 @@ def test_end_effector_box_rows_in_the_oracle():
     viol = lambda z: float(np.sum(np.minimum(0.0, z[1:-1] + 0.02) ** 2))  # noqa: E731
     assert viol(z_box) < 0.3 * viol(z_free)
     assert z_box[4:-1].min() > -0.05 and z_free[4] < -0.12
+
+
+def test_inertial_alignment_cost_in_the_oracle():
+    """InertialAlignmentCostGaussNewton (inertial_alignment.cpp:90-163): e = S C_we'(a - g)/|g| vanishes for a level
+    tray at rest, and enabling the cost tilts/accelerates the tray so that the tangential specific force drops."""
+    import copy
+    import oracle
+    from upright_b200 import geometry as geo
+    desc, target, X, U = _setup("cfg2_thing_demo")
+    ia = copy.deepcopy(desc)
+    ia.ia_cost_enabled = 1
+    ia.ia_cost_weight = 10.0
+    ia.ia_span[:] = geo.plane_span([0, 0, 1]).reshape(6)
+    S = np.array(list(ia.ia_span)).reshape(2, 3)
+
+    def residuals(Xtraj):
+        out = []
+        for x in Xtraj:
+            k = oracle.fk(ia, x)
+            C = np.array(k["C"]).reshape(3, 3)
+            out.append(S @ (C.T @ (np.array(k["a"]) - np.array(list(ia.gravity)))) / 9.81)
+        return np.array(out)
+
+    _, meta = problem_io.load_fixture("cfg2_thing_demo")
+    home = np.array(meta["x0"], dtype=float)
+    assert np.abs(residuals([home])).max() < 1e-7               # level tray at rest (home angles are rounded)
+    # performance index carries dt * 1/2 w e'e
+    Xh = np.tile(X[0], (desc.N + 1, 1))
+    p0 = oracle.performance(desc, target, Xh, U)["cost"]
+    p1 = oracle.performance(ia, target, Xh, U)["cost"]
+    e = residuals(Xh[:-1])
+    assert p1 - p0 == pytest.approx(desc.dt * 0.5 * 10.0 * np.sum(e * e), rel=1e-9, abs=1e-12)
+    # Gauss-Newton model of the QP: the stage gradient / Hessian gain exactly dt w Je'e / dt w Je'Je, checked against
+    # central finite differences of the residual itself
+    k = 3
+    rng = np.random.default_rng(5)
+    Xk = Xh.copy()
+    Xk[k] += 0.05 * rng.standard_normal(desc.nx)
+    q0, q1 = oracle.qp_dump(desc, target, Xk, U)[k], oracle.qp_dump(ia, target, Xk, U)[k]
+    nu, nx = desc.nu, desc.nx
+    dg, dH = (q1["g"] - q0["g"])[nu:], (q1["H"] - q0["H"])[nu:, nu:]
+    assert np.abs((q1["g"] - q0["g"])[:nu]).max() == 0 and np.abs((q1["H"] - q0["H"])[:nu, :]).max() == 0
+    h = 1e-6
+    Je = np.zeros((2, nx))
+    for j in range(nx):
+        xp, xm = Xk[k].copy(), Xk[k].copy()
+        xp[j] += h
+        xm[j] -= h
+        Je[:, j] = (residuals([xp])[0] - residuals([xm])[0]) / (2 * h)
+    e0 = residuals([Xk[k]])[0]
+    assert np.allclose(dg, desc.dt * 10.0 * Je.T @ e0, atol=1e-7)
+    assert np.allclose(dH, desc.dt * 10.0 * Je.T @ Je, atol=1e-6) and np.linalg.matrix_rank(dH, tol=1e-9) <= 2
+    aligned = oracle.solve_batch(ia, X[0], target)
+    assert aligned["status"][0] == 0 and np.isfinite(aligned["X"]).all()

@@ -92,6 +92,8 @@ class ProblemDesc(C.Structure):
         ("delta_tol", C.c_double), ("cost_tol", C.c_double),
         ("ee_box_enabled", C.c_int32), ("reserved0", C.c_int32),
         ("ee_box_lower", C.c_double * 3), ("ee_box_upper", C.c_double * 3),
+        ("ia_cost_enabled", C.c_int32), ("reserved1", C.c_int32), ("ia_cost_weight", C.c_double),
+        ("ia_span", C.c_double * 6),
     ]
 
     # convenience

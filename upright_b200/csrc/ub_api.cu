@@ -246,11 +246,17 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
         P.eb_lo[c] = T(d.ee_box_lower[c]);
         P.eb_hi[c] = T(d.ee_box_upper[c]);
     }
+    P.iacost = d.ia_cost_enabled ? 1 : 0;
+    P.ia_w = T(d.ia_cost_weight);
+    for (int i = 0; i < 6; ++i) P.ia_S[i] = T(d.ia_span[i]);
+    const double gn = std::sqrt(d.gravity[0] * d.gravity[0] + d.gravity[1] * d.gravity[1] + d.gravity[2] * d.gravity[2]);
+    P.ia_inv_g = T(gn > 0 ? 1.0 / gn : 0.0);
 }
 
 template <typename T>
 ub::Layout make_layout(const ub::DevProblem<T>& P) {
-    return ub::compute_layout(ub::LayoutDims{P.N, P.nq, P.nx, P.nu, P.neq, P.nfc, P.nterm, P.nrow, P.nobs, P.nb, int(sizeof(T))});
+    return ub::compute_layout(ub::LayoutDims{P.N, P.nq, P.nx, P.nu, P.neq, P.nfc, P.nterm, P.nrow, P.nobs, P.nb, int(sizeof(T)),
+                                             P.iacost ? 2 : 0});
 }
 
 }  // namespace
@@ -357,7 +363,7 @@ int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
     // kernels specialised on the BASELINE dimensions (nq, nf, nc, nb); anything else runs the generic one
     const bool generic_only = std::getenv("UB_FORCE_GENERIC") != nullptr;
     ub::LaunchFn<T> fn = Pick<T>::generic();
-    if (!generic_only && H.balancing && H.N == 20) {
+    if (!generic_only && H.balancing && H.N == 20 && !H.iacost) {
         const bool no_obs = H.nobs == 0;
         if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::thing_1obj();
         if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12 && !H.eebox) fn = Pick<T>::thing_obs12();
@@ -807,7 +813,7 @@ float ub_last_solve_ms(const ub_problem_t* p) {
 // thread per sample.
 namespace {
 
-enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4, EV_EEBOX = 5 };
+enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4, EV_EEBOX = 5, EV_IACOST = 6 };
 
 __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int what, int M, int rows,
                             const double* __restrict__ x, const double* __restrict__ u,
@@ -868,6 +874,10 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
             o[c] = target[3 * m + c] + P.eb_hi[c] - K.r[c];
             o[3 + c] = K.r[c] - target[3 * m + c] - P.eb_lo[c];
         }
+    } else if (what == EV_IACOST) {   // getCostValue("inertial_alignment_cost"): 1/2 w e'e
+        double e2[2] = {0, 0};
+        if (P.iacost) ub::inertial_alignment_error<double, false>(P, K, D, e2, nullptr);
+        o[0] = 0.5 * P.ia_w * (e2[0] * e2[0] + e2[1] * e2[1]);
     } else if (what == EV_OBST) {
         for (int i = 0; i < P.npairs; ++i) {
             const int a = P.pa[i], b = P.pb[i];
@@ -884,6 +894,11 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
                 const double e = K.r[i] - target[3 * m + i];
                 c += 0.5 * P.Wd[i] * e * e;
             }
+        if (P.iacost) {
+            double e2[2];
+            ub::inertial_alignment_error<double, false>(P, K, D, e2, nullptr);
+            c += 0.5 * P.ia_w * (e2[0] * e2[0] + e2[1] * e2[1]);
+        }
         o[0] = c;
     }
 }
@@ -907,6 +922,7 @@ extern "C" int ub_eval(ub_problem_t* p, const char* name, int32_t M, const doubl
     }
     else if (n == "end_effector_position") { what = EV_EEPOS; rows = 3; }
     else if (n == "cost") { what = EV_COST; rows = 1; }
+    else if (n == "inertial_alignment_cost") { what = EV_IACOST; rows = 1; }
     else return fail(UB_E_INVALID, "unknown probe name " + n);
     if (rows_out) *rows_out = rows;
     if (rows == 0) return UB_OK;

@@ -40,6 +40,9 @@ struct DevProblem {
     // end-effector box rows (end_effector_box_constraint.h): appended to the obstacle rows, nobs = npairs + 6
     int eebox;
     T eb_lo[3], eb_hi[3];
+    // inertial-alignment Gauss-Newton cost (inertial_alignment.cpp:151-163): e = S C' (a - g) / |g|
+    int iacost;
+    T ia_w, ia_S[6], ia_inv_g;
 };
 
 // Division in the interior-point row updates (eight per inequality row and pass): the fp32 kernels use the
@@ -147,6 +150,20 @@ template <typename T>
 struct KinTan {
     V3<T> r, v, w, a, al, th;
 };
+
+// e (2) and, if TANGENT, its derivative along this lane's direction
+template <typename T, bool TANGENT>
+__device__ __forceinline__ void inertial_alignment_error(const DevProblem<T>& P, const Kin<T>& K, const KinTan<T>& D, T* e, T* de) {
+    const V3<T> t = K.a - ld3(P.grav);
+    const V3<T> ce = K.C.tmul(t);
+    e[0] = dot(ld3(P.ia_S), ce) * P.ia_inv_g;
+    e[1] = dot(ld3(P.ia_S + 3), ce) * P.ia_inv_g;
+    if (TANGENT) {
+        const V3<T> dce = K.C.tmul(D.a - cross(D.th, t));
+        de[0] = dot(ld3(P.ia_S), dce) * P.ia_inv_g;
+        de[1] = dot(ld3(P.ia_S + 3), dce) * P.ia_inv_g;
+    }
+}
 
 // Forward kinematics with classical accelerations (what the reference obtains
 // from ocs2::PinocchioEndEffectorKinematicsCppAd,

@@ -30,11 +30,14 @@ struct Layout {
     int sSm;  // staged per-stage vectors [z | x | u | Jp | w] (with the staged side records)
     // instance-local copies of the desired positions [N+1, 3] and the body parameters [nb, 10]
     int TG, BD;
+    // inertial-alignment cost rows: values [N, 2] and Jacobians [N, 2, nx] (only when that cost is enabled)
+    int LIA, LJA;
 };
 // side records of a stage are staged in shared memory (cp.async, one stage ahead) up to this many rows
 #define UB_STAGE_ROWS_MAX 64
 struct LayoutDims {
     int N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, nb, tsize;
+    int nia = 0;   // rows of the inertial-alignment cost (0 or 2)
 };
 __host__ __device__ constexpr int ub_round4(int n) { return (n + 3) / 4 * 4; }
 __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
@@ -72,6 +75,8 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.UW = o;   o += ub_round4(N * nu);
     L.TG = o;   o += ub_round4((N + 1) * 3);
     L.BD = o;   o += ub_round4((d.nb > 0 ? d.nb : 1) * 10);
+    L.LIA = o;  o += ub_round4(N * d.nia);
+    L.LJA = o;  o += ub_round4(N * d.nia * nx);
     L.total = o;
     int s = 0;
     L.sM = s;   s += ub_round4(nz * ldm > fstride ? nz * ldm : fstride);
@@ -159,13 +164,15 @@ struct Solver {
     // end-effector box rows exist only in the run-time-dimension kernel (the specialised ones are not dispatched
     // for such problems)
     __device__ __forceinline__ bool EEBOX() const { if constexpr (D::kStatic) return false; else return P.eebox != 0; }
+    // the inertial-alignment cost likewise (run-time-dimension kernel only)
+    __device__ __forceinline__ bool IALIGN() const { if constexpr (D::kStatic) return false; else return P.iacost != 0; }
     __device__ __forceinline__ int NPAIRS() const { if constexpr (D::kStatic) return D::nobs; else return P.npairs; }
     // workspace / shared-memory offsets: immediates for the specialised kernels
 #define UB_OFF(name) \
     __device__ __forceinline__ int o##name() const { if constexpr (D::kStatic) { constexpr Layout l = D::template layout<T>(); return l.name; } else return L.name; }
     UB_OFF(Z) UB_OFF(DZ) UB_OFF(GAP) UB_OFF(LG) UB_OFF(LCT) UB_OFF(LR) UB_OFF(LJP) UB_OFF(LHO) UB_OFF(LJO) UB_OFF(DF)
     UB_OFF(RHOE) UB_OFF(YE) UB_OFF(RHOT) UB_OFF(YT) UB_OFF(TT) UB_OFF(LAM) UB_OFF(FAC) UB_OFF(WF) UB_OFF(XN) UB_OFF(UN)
-    UB_OFF(XW) UB_OFF(UW) UB_OFF(TG) UB_OFF(BD)
+    UB_OFF(XW) UB_OFF(UW) UB_OFF(TG) UB_OFF(BD) UB_OFF(LIA) UB_OFF(LJA)
 #undef UB_OFF
     __device__ __forceinline__ int LDM() const { return NZ() | 1; }
     __device__ __forceinline__ int LDF() const { return NU() | 1; }
@@ -482,6 +489,19 @@ struct Solver {
                     }
                 }
             }
+            if (IALIGN() && k < N) {
+                // e = S C_we' (a - g) / |g| and its Jacobian (inertial_alignment.cpp:151-163)
+                T e2[2], de2[2];
+                inertial_alignment_error<T, true>(P, Kn, Dt, e2, de2);
+                if (lane == 0) {
+                    ws[oLIA() + 2 * k] = e2[0];
+                    ws[oLIA() + 2 * k + 1] = e2[1];
+                }
+                if (lane < nx) {
+                    ws[oLJA() + (2 * k) * nx + lane] = de2[0];
+                    ws[oLJA() + (2 * k + 1) * nx + lane] = de2[1];
+                }
+            }
             if (NOBS() > 0) {
                 for (int i = 0; i < NPAIRS(); ++i) {
                     const int a = P.pa[i], bb = P.pb[i];
@@ -567,6 +587,11 @@ struct Solver {
             for (int i = 0; i < 3; ++i) {
                 const T e = Kn.r[i] - rd[i];
                 c += T(0.5) * P.Wd[i] * e * e;
+            }
+            if (IALIGN()) {
+                T e2[2];
+                inertial_alignment_error<T, false>(P, Kn, Dn, e2, nullptr);
+                c += T(0.5) * P.ia_w * (e2[0] * e2[0] + e2[1] * e2[1]);
             }
             cost += dt * c;
             const T* xn = Xt + (k + 1) * nx;
@@ -811,6 +836,16 @@ struct Solver {
                 sM[(nu + a) * ld + nu + b] += dt * acc;
             }
             __syncwarp();
+            if (IALIGN()) {   // Gauss-Newton Hessian w Je' Je of the inertial-alignment cost (dense over x)
+                const T* Ja = ws + oLJA() + 2 * k * nx;
+                const T wa = dt * P.ia_w;
+                for (int idx = lane; idx < nx * nx; idx += WARP) {
+                    const int a = idx / nx, b = idx % nx;
+                    if (b > a) continue;
+                    sM[(nu + a) * ld + nu + b] += wa * (Ja[a] * Ja[b] + Ja[nx + a] * Ja[nx + b]);
+                }
+                __syncwarp();
+            }
         }
         // equality rows: rho a a'
         const int ne = neq_of(k);
@@ -1100,6 +1135,17 @@ struct Solver {
                 const T part = lane < nq ? Jp[c * nq + lane] * zk[nu + lane] : T(0);
                 e3[c] = warp_sum(part) + ws[oLR() + 3 * k + c] - target[3 * k + c];
             }
+            // inertial-alignment residual at the QP iterate: e + Je dx
+            T ea[2] = {T(0), T(0)};
+            const T* Ja = ws + oLJA() + 2 * k * nx;
+            if (IALIGN()) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    T part = T(0);
+                    for (int j = lane; j < nx; j += WARP) part += Ja[r * nx + j] * zk[nu + j];
+                    ea[r] = warp_sum(part) + ws[oLIA() + 2 * k + r];
+                }
+            }
             for (int i = lane; i < nz; i += WARP) {
                 T g;
                 if (i < nq) g = dt * P.Rd[i] * (u[i] + zk[i]) + C.reg_input * zk[i];
@@ -1108,6 +1154,7 @@ struct Solver {
                     const int xi = i - nu;
                     g = dt * P.Qd[xi] * (x[xi] + zk[i] - P.xd[xi]);
                     if (xi < nq) g += dt * (C.Wd[0] * Jp[xi] * e3[0] + C.Wd[1] * Jp[nq + xi] * e3[1] + C.Wd[2] * Jp[2 * nq + xi] * e3[2]);
+                    if (IALIGN()) g += dt * P.ia_w * (Ja[xi] * ea[0] + Ja[nx + xi] * ea[1]);
                 }
                 vec[i] = g;
             }
@@ -1880,6 +1927,9 @@ struct Solver {
                         if (xi < nq)
                             for (int c = 0; c < 3; ++c)
                                 g += C.dt * C.Wd[c] * Jp[c * nq + xi] * (ws[oLR() + 3 * k + c] - target[3 * k + c]);
+                        if (IALIGN())
+                            for (int r = 0; r < 2; ++r)
+                                g += C.dt * P.ia_w * ws[oLJA() + (2 * k + r) * nx + xi] * ws[oLIA() + 2 * k + r];
                     }
                     desc += g * zk[i];
                 }

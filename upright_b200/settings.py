@@ -227,6 +227,16 @@ class ControllerSettings:
             cost_enabled=ia.get("cost_enabled", False),
             constraint_enabled=ia.get("constraint_enabled", False),
         )
+        if ia.get("cost_enabled") or ia.get("constraint_enabled"):   # wrappers.py:332-345
+            ias = self.inertial_alignment_settings
+            ias.use_angular_acceleration = ia.get("use_angular_acceleration", False)
+            ias.align_with_fixed_vector = ia.get("align_with_fixed_vector", False)
+            ias.cost_weight = float(ia.get("cost_weight", 1.0))
+            normal = np.array(ia.get("contact_plane_normal", [0, 0, 1]), dtype=float)
+            ias.contact_plane_normal = normal / np.linalg.norm(normal)
+            ias.contact_plane_span = geo.plane_span(ias.contact_plane_normal)
+            ias.com = np.array(ia.get("com", [0, 0, 0]), dtype=float)
+            ias.alpha = ia.get("alpha", 0)
 
         obs = config.get("obstacles", {"enabled": False})
         self.obstacle_settings = SimpleNamespace(
@@ -304,8 +314,13 @@ class ControllerSettings:
         if self.projectile_path_constraint_enabled:
             raise NotImplementedError("projectile_path_constraint is a 'next' row (SURVEY §8f-2)")
         ia = self.inertial_alignment_settings
-        if ia.cost_enabled or ia.constraint_enabled:
-            raise NotImplementedError("inertial_alignment cost / constraint is a 'next' row (SURVEY §8f-3)")
+        if ia.constraint_enabled:
+            raise NotImplementedError("the inertial_alignment constraint is a 'next' row (SURVEY §8f-3)")
+        # InertialAlignmentCostGaussNewton (controller_interface.cpp:296-305)
+        d.ia_cost_enabled = int(bool(ia.cost_enabled))
+        if d.ia_cost_enabled:
+            d.ia_cost_weight = float(ia.cost_weight)
+            d.ia_span[:] = np.asarray(ia.contact_plane_span, dtype=float).reshape(6)
         if self.use_operating_points:
             raise NotImplementedError("the operating-point initializer is not supported (DefaultInitializer only)")
         # EndEffectorBoxConstraint (end_effector_box_constraint.h; wrappers.py:240-250)
