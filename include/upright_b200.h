@@ -166,6 +166,16 @@ typedef struct ub_problem_desc {
     int32_t reserved1;
     double ia_cost_weight;
     double ia_span[6];
+    /* InertialAlignmentConstraint (inertial_alignment.h:68-110, src/inertial_alignment.cpp:7-53;
+     * controller_interface.cpp:306-315): five inequality rows of the "poly_ineq" family at the intermediate
+     * knots, a = C_we'(acc - g) [+ ddC_we com | = C_we' n], h = [a_n, alpha a_n -+ a_t0 -+ a_t1] >= 0 */
+    int32_t ia_constraint_enabled;
+    int32_t ia_use_angular_acceleration;
+    int32_t ia_align_with_fixed_vector;
+    int32_t reserved2;
+    double ia_alpha;
+    double ia_normal[3];
+    double ia_com[3];
 } ub_problem_desc_t;
 
 typedef struct ub_problem ub_problem_t;
@@ -224,7 +234,7 @@ int ub_solve_batch(ub_problem_t* problem, int32_t B, const void* x0, const void*
  * at M (x,u) pairs on the device.  Host double pointers.
  *   name in {"object_dynamics","contact_forces","obstacle_avoidance",
  *            "end_effector_box_constraint" (needs target),"end_effector_position","cost",
- *            "inertial_alignment_cost"}
+ *            "inertial_alignment_cost","inertial_alignment_constraint"}
  *   out [M, rows]; rows returned through *rows_out. */
 int ub_eval(ub_problem_t* problem, const char* name, int32_t M, const double* x,
             const double* u, const double* target /*[M,3] or NULL*/,

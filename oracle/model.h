@@ -189,6 +189,28 @@ void inertial_alignment_error(const ub_problem_desc_t& P, const Kinematics<S>& X
     e[1] = dot(vec3_from<S>(P.ia_span + 3), a_e) / S(gn);
 }
 
+// InertialAlignmentConstraint::constraintFunction (upright_control/src/inertial_alignment.cpp:7-53), literally
+template <typename S>
+void inertial_alignment_constraints(const ub_problem_desc_t& P, const Kinematics<S>& X, S* h) {
+    const Vec3<S> gravity = vec3_from<S>(P.gravity);
+    const Vec3<S> n = vec3_from<S>(P.ia_normal);
+    Vec3<S> a = X.C_we.transpose() * (X.a - gravity);
+    if (P.ia_use_angular_acceleration) {
+        const Mat3<S> Sw = skew3(X.w);
+        const Mat3<S> ddC = (skew3(X.al) + Sw * Sw) * X.C_we;
+        a = a + ddC * vec3_from<S>(P.ia_com);
+    } else if (P.ia_align_with_fixed_vector) {
+        a = X.C_we.transpose() * n;
+    }
+    const S an = dot(n, a), t0 = dot(vec3_from<S>(P.ia_span), a), t1 = dot(vec3_from<S>(P.ia_span + 3), a);
+    const S al(P.ia_alpha);
+    h[0] = an;
+    h[1] = al * an - t0 - t1;
+    h[2] = al * an - t0 + t1;
+    h[3] = al * an + t0 - t1;
+    h[4] = al * an + t0 + t1;
+}
+
 // Sphere-sphere distances minus the minimum distance, h >= 0.  Closed form of
 // ocs2::SelfCollisionConstraintCppAd + hpp-fcl for sphere pairs
 // (upright_control/src/controller_interface.cpp:450-481).

@@ -66,7 +66,8 @@ static Dims make_dims(const ub_problem_desc_t& P) {
     D.neq = bal ? 6 * P.nb : 0;
     D.nfric = (bal && P.nf == 3) ? 5 * P.nc : 0;
     D.npairs = P.obstacles_enabled ? P.n_pairs : 0;
-    D.nobs = D.npairs + (P.ee_box_enabled ? 6 : 0);  // end-effector box rows follow the sphere-pair rows
+    // end-effector box rows, then inertial-alignment rows, follow the sphere-pair rows
+    D.nobs = D.npairs + (P.ee_box_enabled ? 6 : 0) + (P.ia_constraint_enabled ? 5 : 0);
     D.nterm = 3 + 2 * P.nq;  // stationary_desired_position_constraint.h:39-41
     D.N = P.N;
     D.nz = D.nu + D.nx;
@@ -106,6 +107,8 @@ struct KnotLin {
     Mat Jobs;                   // d hobs / d q (nobs x nq)
     double ea[2] = {0, 0};      // inertial-alignment residual
     Mat Jea;                    // d ea / d x (2 x nx)
+    double hia[5] = {0, 0, 0, 0, 0};  // inertial-alignment constraint rows
+    Mat Jia;                    // d hia / d x (5 x nx)
 };
 
 static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const double* body_params, const double* x,
@@ -163,6 +166,15 @@ static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const doub
         for (int r = 0; r < 2; ++r) {
             L.ea[r] = e[r].v;
             for (int j = 0; j < nx; ++j) L.Jea(r, j) = e[r].d[j];
+        }
+    }
+    L.Jia = Mat(5, nx);
+    if (P.ia_constraint_enabled) {
+        Dual h[5];
+        inertial_alignment_constraints<Dual>(P, K, h);
+        for (int r = 0; r < 5; ++r) {
+            L.hia[r] = h[r].v;
+            for (int j = 0; j < nx; ++j) L.Jia(r, j) = h[r].d[j];
         }
     }
     L.hobs.assign(D.npairs, 0.0);
@@ -292,6 +304,14 @@ static Perf performance(const ub_problem_desc_t& P, const Dims& D, const Mat& A,
             for (int i = 0; i < D.npairs; ++i) {
                 pf.ineq_sse += dt * sq(std::min(0.0, h[i]));
                 pf.min_margin = std::min(pf.min_margin, h[i]);
+            }
+        }
+        if (P.ia_constraint_enabled && k >= 1) {   // inertial_alignment.cpp:7-53
+            double h5[5];
+            inertial_alignment_constraints<double>(P, K, h5);
+            for (int r = 0; r < 5; ++r) {
+                pf.ineq_sse += dt * sq(std::min(0.0, h5[r]));
+                pf.min_margin = std::min(pf.min_margin, h5[r]);
             }
         }
         if (P.ee_box_enabled && k >= 1)   // constraint/end_effector_box_constraint.h:46-58
@@ -449,6 +469,17 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
                         finish(r, soft_poly);
                         s.rows.push_back(r);
                     }
+            // inertial-alignment constraint rows, dense over x (inertial_alignment.cpp:7-53)
+            if (P.ia_constraint_enabled)
+                for (int i = 0; i < 5; ++i) {
+                    Row r;
+                    r.a.assign(s.nz, 0.0);
+                    for (int j = 0; j < nx; ++j) r.a[xo + j] = L.Jia(i, j);
+                    r.c = L.hia[i];
+                    r.lb = 0.0;
+                    finish(r, soft_poly);
+                    s.rows.push_back(r);
+                }
         }
         if (k == N) {
             // terminal equality [r_d - r; v; a] = 0 (stationary_desired_position_constraint.h:43-74)

@@ -154,8 +154,7 @@ def test_end_effector_box_and_next_rows():
     bad["end_effector_box_constraint"]["xyz_lower"] = [2.0, -1.0, -0.05]
     with pytest.raises(ValueError):
         settings.ControllerSettings(bad, x0=np.array(meta["x0"])).to_desc()
-    for key, patch in (("inertial_alignment", {"cost_enabled": False, "constraint_enabled": True, "alpha": 0.1}),
-                       ("projectile_path_constraint", {"enabled": True}),
+    for key, patch in (("projectile_path_constraint", {"enabled": True}),
                        ("operating_points", {"enabled": True})):
         c2 = copy.deepcopy(meta["controller_config"])
         c2[key] = dict(c2.get(key, {}), **patch)
@@ -173,6 +172,11 @@ def test_inertial_alignment_cost_settings():
                                  "align_with_fixed_vector": False, "cost_weight": 2.5, "contact_plane_normal": [0, 0, 2],
                                  "com": [0, 0, 0], "alpha": 0}
     desc = settings.ControllerSettings(cfg, x0=np.array(meta["x0"])).to_desc()
-    assert desc.ia_cost_enabled == 1 and desc.ia_cost_weight == 2.5
+    assert desc.ia_cost_enabled == 1 and desc.ia_cost_weight == 2.5 and desc.ia_constraint_enabled == 0
     S = np.array(list(desc.ia_span)).reshape(2, 3)
     assert np.allclose(S, geo.plane_span([0, 0, 1])) and np.allclose(S @ [0, 0, 1], 0) and np.allclose(S @ S.T, np.eye(2))
+    cfg["inertial_alignment"].update(cost_enabled=False, constraint_enabled=True, alpha=0.2, com=[0.0, 0.0, 0.1],
+                                     use_angular_acceleration=True)
+    d2 = settings.ControllerSettings(cfg, x0=np.array(meta["x0"])).to_desc()
+    assert (d2.ia_cost_enabled, d2.ia_constraint_enabled, d2.ia_use_angular_acceleration, d2.ia_align_with_fixed_vector) == (0, 1, 1, 0)
+    assert d2.ia_alpha == 0.2 and list(d2.ia_normal) == [0.0, 0.0, 1.0] and list(d2.ia_com) == [0.0, 0.0, 0.1]

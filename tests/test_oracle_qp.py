@@ -222,3 +222,55 @@ def test_inertial_alignment_cost_in_the_oracle():
     assert np.allclose(dH, desc.dt * 10.0 * Je.T @ Je, atol=1e-6) and np.linalg.matrix_rank(dH, tol=1e-9) <= 2
     aligned = oracle.solve_batch(ia, X[0], target)
     assert aligned["status"][0] == 0 and np.isfinite(aligned["X"]).all()
+
+
+@pytest.mark.parametrize("mode", ["plain", "angular", "fixed"])
+def test_inertial_alignment_constraint_rows_in_the_oracle(mode):
+    """InertialAlignmentConstraint (inertial_alignment.cpp:7-53): the five rows of the QP of the oracle equal the
+    literal formula and its central finite differences, for the three variants."""
+    import copy
+    import oracle
+    from upright_b200 import geometry as geo
+    desc, target, X, U = _setup("cfg2_thing_demo")
+    ia = copy.deepcopy(desc)
+    ia.ia_constraint_enabled = 1
+    ia.ia_alpha = 0.3
+    ia.ia_normal[:] = [0.0, 0.0, 1.0]
+    ia.ia_span[:] = geo.plane_span([0, 0, 1]).reshape(6)
+    ia.ia_com[:] = [0.02, -0.01, 0.15]
+    ia.ia_use_angular_acceleration = int(mode == "angular")
+    ia.ia_align_with_fixed_vector = int(mode == "fixed")
+    S, n, com = np.array(list(ia.ia_span)).reshape(2, 3), np.array([0, 0, 1.0]), np.array(list(ia.ia_com))
+    g = np.array(list(ia.gravity))
+
+    def rows(x):
+        k = oracle.fk(ia, x)
+        C, w, al = np.array(k["C"]).reshape(3, 3), np.array(k["w"]), np.array(k["alpha"])
+        a = C.T @ (np.array(k["a"]) - g)
+        sk = lambda v: np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])  # noqa: E731
+        if mode == "angular":
+            a = a + (sk(al) + sk(w) @ sk(w)) @ C @ com
+        elif mode == "fixed":
+            a = C.T @ n
+        an, at = n @ a, S @ a
+        return np.array([an, 0.3 * an - at[0] - at[1], 0.3 * an - at[0] + at[1], 0.3 * an + at[0] - at[1], 0.3 * an + at[0] + at[1]])
+
+    assert oracle.dims(ia)["n_ineq"] == oracle.dims(desc)["n_ineq"] + 5
+    rng = np.random.default_rng(8)
+    Xk = np.tile(X[0], (desc.N + 1, 1))
+    k = 4
+    Xk[k] += 0.1 * rng.standard_normal(desc.nx)
+    q0, q1 = oracle.qp_dump(desc, target, Xk, U)[k], oracle.qp_dump(ia, target, Xk, U)[k]
+    assert q1["A"].shape[0] == q0["A"].shape[0] + 5
+    A5, c5 = q1["A"][-5:], q1["c"][-5:]
+    assert np.allclose(c5, rows(Xk[k]), atol=1e-10) and np.abs(A5[:, : desc.nu]).max() == 0
+    J = np.zeros((5, desc.nx))
+    h = 1e-6
+    for j in range(desc.nx):
+        xp, xm = Xk[k].copy(), Xk[k].copy()
+        xp[j] += h
+        xm[j] -= h
+        J[:, j] = (rows(xp) - rows(xm)) / (2 * h)
+    assert np.allclose(A5[:, desc.nu:], J, atol=2e-6)
+    out = oracle.solve_batch(ia, X[0], target)
+    assert out["status"][0] in (0, 1) and np.isfinite(out["X"]).all()

@@ -94,6 +94,9 @@ class ProblemDesc(C.Structure):
         ("ee_box_lower", C.c_double * 3), ("ee_box_upper", C.c_double * 3),
         ("ia_cost_enabled", C.c_int32), ("reserved1", C.c_int32), ("ia_cost_weight", C.c_double),
         ("ia_span", C.c_double * 6),
+        ("ia_constraint_enabled", C.c_int32), ("ia_use_angular_acceleration", C.c_int32),
+        ("ia_align_with_fixed_vector", C.c_int32), ("reserved2", C.c_int32), ("ia_alpha", C.c_double),
+        ("ia_normal", C.c_double * 3), ("ia_com", C.c_double * 3),
     ]
 
     # convenience

@@ -161,7 +161,17 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
     P.nfric = (bal && d.nf == 3) ? 5 * d.nc : 0;
     P.npairs = d.obstacles_enabled ? d.n_pairs : 0;
     P.eebox = d.ee_box_enabled ? 1 : 0;
-    P.nobs = P.npairs + (P.eebox ? 6 : 0);   // end-effector box rows ride behind the sphere-pair rows
+    P.iacon = d.ia_constraint_enabled ? 1 : 0;
+    // end-effector box rows, then inertial-alignment rows, ride behind the sphere-pair rows
+    P.nobs = P.npairs + (P.eebox ? 6 : 0) + (P.iacon ? 5 : 0);
+    P.obsw = P.iacon ? 3 * d.nq : d.nq;
+    P.ia_use_ang = d.ia_use_angular_acceleration ? 1 : 0;
+    P.ia_fixed = d.ia_align_with_fixed_vector ? 1 : 0;
+    P.ia_alpha = T(d.ia_alpha);
+    for (int i = 0; i < 3; ++i) {
+        P.ia_n[i] = T(d.ia_normal[i]);
+        P.ia_com[i] = T(d.ia_com[i]);
+    }
     P.nterm = 3 + 2 * d.nq;
     P.N = d.N;
     P.nsph = d.obstacles_enabled ? d.n_spheres : 0;
@@ -256,7 +266,7 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
 template <typename T>
 ub::Layout make_layout(const ub::DevProblem<T>& P) {
     return ub::compute_layout(ub::LayoutDims{P.N, P.nq, P.nx, P.nu, P.neq, P.nfc, P.nterm, P.nrow, P.nobs, P.nb, int(sizeof(T)),
-                                             P.iacost ? 2 : 0});
+                                             P.iacost ? 2 : 0, P.obsw});
 }
 
 }  // namespace
@@ -363,7 +373,7 @@ int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
     // kernels specialised on the BASELINE dimensions (nq, nf, nc, nb); anything else runs the generic one
     const bool generic_only = std::getenv("UB_FORCE_GENERIC") != nullptr;
     ub::LaunchFn<T> fn = Pick<T>::generic();
-    if (!generic_only && H.balancing && H.N == 20 && !H.iacost) {
+    if (!generic_only && H.balancing && H.N == 20 && !H.iacost && !H.iacon) {
         const bool no_obs = H.nobs == 0;
         if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::thing_1obj();
         if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12 && !H.eebox) fn = Pick<T>::thing_obs12();
@@ -813,7 +823,7 @@ float ub_last_solve_ms(const ub_problem_t* p) {
 // thread per sample.
 namespace {
 
-enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4, EV_EEBOX = 5, EV_IACOST = 6 };
+enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4, EV_EEBOX = 5, EV_IACOST = 6, EV_IACON = 7 };
 
 __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int what, int M, int rows,
                             const double* __restrict__ x, const double* __restrict__ u,
@@ -874,6 +884,8 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
             o[c] = target[3 * m + c] + P.eb_hi[c] - K.r[c];
             o[3 + c] = K.r[c] - target[3 * m + c] - P.eb_lo[c];
         }
+    } else if (what == EV_IACON) {   // getStateInputInequalityConstraintValue("inertial_alignment_constraint")
+        ub::inertial_alignment_rows<double, false>(P, K, D, o, nullptr);
     } else if (what == EV_IACOST) {   // getCostValue("inertial_alignment_cost"): 1/2 w e'e
         double e2[2] = {0, 0};
         if (P.iacost) ub::inertial_alignment_error<double, false>(P, K, D, e2, nullptr);
@@ -923,6 +935,7 @@ extern "C" int ub_eval(ub_problem_t* p, const char* name, int32_t M, const doubl
     else if (n == "end_effector_position") { what = EV_EEPOS; rows = 3; }
     else if (n == "cost") { what = EV_COST; rows = 1; }
     else if (n == "inertial_alignment_cost") { what = EV_IACOST; rows = 1; }
+    else if (n == "inertial_alignment_constraint") { what = EV_IACON; rows = P.iacon ? 5 : 0; }
     else return fail(UB_E_INVALID, "unknown probe name " + n);
     if (rows_out) *rows_out = rows;
     if (rows == 0) return UB_OK;

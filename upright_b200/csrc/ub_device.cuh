@@ -43,6 +43,9 @@ struct DevProblem {
     // inertial-alignment Gauss-Newton cost (inertial_alignment.cpp:151-163): e = S C' (a - g) / |g|
     int iacost;
     T ia_w, ia_S[6], ia_inv_g;
+    // inertial-alignment constraint (inertial_alignment.cpp:7-53): five rows behind the obstacle / box rows
+    int iacon, ia_use_ang, ia_fixed, obsw;
+    T ia_alpha, ia_n[3], ia_com[3];
 };
 
 // Division in the interior-point row updates (eight per inequality row and pass): the fp32 kernels use the
@@ -162,6 +165,43 @@ __device__ __forceinline__ void inertial_alignment_error(const DevProblem<T>& P,
         const V3<T> dce = K.C.tmul(D.a - cross(D.th, t));
         de[0] = dot(ld3(P.ia_S), dce) * P.ia_inv_g;
         de[1] = dot(ld3(P.ia_S + 3), dce) * P.ia_inv_g;
+    }
+}
+
+// InertialAlignmentConstraint::constraintFunction (inertial_alignment.cpp:7-53), transcribed literally:
+//   a = C' (acc - g);  use_angular_acceleration: a += ddC_we com;  align_with_fixed_vector: a = C' n
+//   h = [a_n, alpha a_n -+ a_t0 -+ a_t1]   with a_n = n . a, a_t = S a
+template <typename T, bool TANGENT>
+__device__ __forceinline__ void inertial_alignment_rows(const DevProblem<T>& P, const Kin<T>& K, const KinTan<T>& D, T* h, T* dh) {
+    const V3<T> n = ld3(P.ia_n), s0 = ld3(P.ia_S), s1 = ld3(P.ia_S + 3);
+    const V3<T> t = K.a - ld3(P.grav);
+    V3<T> a = K.C.tmul(t), da;
+    if (TANGENT) da = K.C.tmul(D.a - cross(D.th, t));
+    if (P.ia_use_ang) {
+        const V3<T> cw = K.C.mul(ld3(P.ia_com));
+        const V3<T> wc = cross(K.w, cw);
+        a = a + cross(K.al, cw) + cross(K.w, wc);   // (S(alpha) + S(w) S(w)) C com
+        if (TANGENT) {
+            const V3<T> dcw = cross(D.th, cw);
+            da = da + cross(D.al, cw) + cross(K.al, dcw) + cross(D.w, wc) + cross(K.w, cross(D.w, cw) + cross(K.w, dcw));
+        }
+    } else if (P.ia_fixed) {
+        a = K.C.tmul(n);
+        if (TANGENT) da = K.C.tmul(T(-1) * cross(D.th, n));
+    }
+    const T an = dot(n, a), t0 = dot(s0, a), t1 = dot(s1, a), al = P.ia_alpha;
+    h[0] = an;
+    h[1] = al * an - t0 - t1;
+    h[2] = al * an - t0 + t1;
+    h[3] = al * an + t0 - t1;
+    h[4] = al * an + t0 + t1;
+    if (TANGENT) {
+        const T dn = dot(n, da), d0 = dot(s0, da), d1 = dot(s1, da);
+        dh[0] = dn;
+        dh[1] = al * dn - d0 - d1;
+        dh[2] = al * dn - d0 + d1;
+        dh[3] = al * dn + d0 - d1;
+        dh[4] = al * dn + d0 + d1;
     }
 }
 

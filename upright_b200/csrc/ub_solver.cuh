@@ -38,6 +38,7 @@ struct Layout {
 struct LayoutDims {
     int N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, nb, tsize;
     int nia = 0;   // rows of the inertial-alignment cost (0 or 2)
+    int obsw = 0;  // width of the obstacle-family rows (0 -> nq)
 };
 __host__ __device__ constexpr int ub_round4(int n) { return (n + 3) / 4 * 4; }
 __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
@@ -53,7 +54,7 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.LR = o;   o += ub_round4((N + 1) * 3);
     L.LJP = o;  o += ub_round4((N + 1) * 3 * nq);
     L.LHO = o;  o += ub_round4((N + 1) * d.nobs);
-    L.LJO = o;  o += ub_round4((N + 1) * d.nobs * nq);
+    L.LJO = o;  o += ub_round4((N + 1) * d.nobs * (d.obsw > 0 ? d.obsw : nq));
     L.DF = o;   o += ub_round4(d.neq * d.nfc);
     L.RHOE = o; o += ub_round4(N * d.neq);
     L.YE = o;   o += ub_round4(N * d.neq);
@@ -164,6 +165,10 @@ struct Solver {
     // end-effector box rows exist only in the run-time-dimension kernel (the specialised ones are not dispatched
     // for such problems)
     __device__ __forceinline__ bool EEBOX() const { if constexpr (D::kStatic) return false; else return P.eebox != 0; }
+    // width of the dense rows of the obstacle family: the configuration (nq) for distances and the end-effector
+    // box, the whole state when inertial-alignment constraint rows (which see v and a) ride along
+    __device__ __forceinline__ int OBSW() const { if constexpr (D::kStatic) return D::nq; else return P.obsw; }
+    __device__ __forceinline__ bool IACON() const { if constexpr (D::kStatic) return false; else return P.iacon != 0; }
     // the inertial-alignment cost likewise (run-time-dimension kernel only)
     __device__ __forceinline__ bool IALIGN() const { if constexpr (D::kStatic) return false; else return P.iacost != 0; }
     __device__ __forceinline__ int NPAIRS() const { if constexpr (D::kStatic) return D::nobs; else return P.npairs; }
@@ -270,9 +275,10 @@ struct Solver {
             return a.x * (f[0] + df[0]) + a.y * (f[1] + df[1]) + a.z * (f[2] + df[2]);
         }
         const int i = r - NBOXU() - NX() - NFRIC();
-        const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
+        const int ow = OBSW();
+        const T* J = ws + oLJO() + (k * NOBS() + i) * ow;
         T v = ws[oLHO() + k * NOBS() + i];
-        for (int j = 0; j < nq; ++j) v += J[j] * zk[nu + j];
+        for (int j = 0; j < ow; ++j) v += J[j] * zk[nu + j];
         return v;
     }
     // a_r . d  for a stage direction d = [du; dx]
@@ -287,9 +293,10 @@ struct Solver {
             return a.x * df[0] + a.y * df[1] + a.z * df[2];
         }
         const int i = r - NBOXU() - NX() - NFRIC();
-        const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
+        const int ow = OBSW();
+        const T* J = ws + oLJO() + (k * NOBS() + i) * ow;
         T v = 0;
-        for (int j = 0; j < nq; ++j) v += J[j] * d[nu + j];
+        for (int j = 0; j < ow; ++j) v += J[j] * d[nu + j];
         return v;
     }
     // vec += w * a_r   (vec indexed like the stage vector); called by ONE lane per row,
@@ -308,8 +315,8 @@ struct Solver {
             atomicAdd(vec + nq + 3 * c + 2, w * a.z);
         } else {
             const int i = r - NBOXU() - NX() - NFRIC();
-            const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
-            for (int j = 0; j < nq; ++j) atomicAdd(vec + nu + j, w * J[j]);
+            const T* J = ws + oLJO() + (k * NOBS() + i) * OBSW();
+            for (int j = 0; j < OBSW(); ++j) atomicAdd(vec + nu + j, w * J[j]);
         }
     }
     __device__ __forceinline__ int nz_of(int k) const { return k < NN() ? NZ() : NX(); }
@@ -510,7 +517,7 @@ struct Solver {
                     const V3<T> dd(dsph[3 * a] - dsph[3 * bb], dsph[3 * a + 1] - dsph[3 * bb + 1],
                                    dsph[3 * a + 2] - dsph[3 * bb + 2]);
                     if (lane == 0) ws[oLHO() + k * NOBS() + i] = dist - (P.srad[a] + P.srad[bb] + C.dmin);
-                    if (lane < nq) ws[oLJO() + (k * NOBS() + i) * nq + lane] = dot(d, dd) / dist;
+                    if (lane < OBSW()) ws[oLJO() + (k * NOBS() + i) * OBSW() + lane] = lane < nq ? dot(d, dd) / dist : T(0);
                 }
                 if (EEBOX()) {
                     // rows npairs..+2: r_d + upper - r >= 0; rows npairs+3..+5: r - r_d - lower >= 0
@@ -522,10 +529,21 @@ struct Solver {
                             ws[oLHO() + k * NOBS() + iu] = tg[c] + P.eb_hi[c] - Kn.r[c];
                             ws[oLHO() + k * NOBS() + il] = Kn.r[c] - tg[c] - P.eb_lo[c];
                         }
-                        if (lane < nq) {
-                            ws[oLJO() + (k * NOBS() + iu) * nq + lane] = -Dt.r[c];
-                            ws[oLJO() + (k * NOBS() + il) * nq + lane] = Dt.r[c];
+                        if (lane < OBSW()) {
+                            ws[oLJO() + (k * NOBS() + iu) * OBSW() + lane] = lane < nq ? -Dt.r[c] : T(0);
+                            ws[oLJO() + (k * NOBS() + il) * OBSW() + lane] = lane < nq ? Dt.r[c] : T(0);
                         }
+                    }
+                }
+                if (IACON()) {
+                    // five inertial-alignment rows (inertial_alignment.cpp:7-53) behind the box rows, dense over x
+                    T h5[5], dh5[5];
+                    inertial_alignment_rows<T, true>(P, Kn, Dt, h5, dh5);
+                    const int i0 = NPAIRS() + (EEBOX() ? 6 : 0);
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) {
+                        if (lane == 0) ws[oLHO() + k * NOBS() + i0 + r] = h5[r];
+                        if (lane < nx) ws[oLJO() + (k * NOBS() + i0 + r) * OBSW() + lane] = dh5[r];
                     }
                 }
             }
@@ -647,6 +665,15 @@ struct Solver {
                         ineq += dt * (mu_ * mu_ + ml * ml);
                         min_margin = min(min_margin, min(hu, hl));
                     }
+                if (IACON()) {
+                    T h5[5];
+                    inertial_alignment_rows<T, false>(P, Kn, Dn, h5, nullptr);
+                    for (int r = 0; r < 5; ++r) {
+                        const T m = min(T(0), h5[r]);
+                        ineq += dt * m * m;
+                        min_margin = min(min_margin, h5[r]);
+                    }
+                }
             }
         }
         Perf<T> pf;
@@ -932,12 +959,13 @@ struct Solver {
                 wrow[i] = fdiv(q.v[2], q.v[0] + eps * q.v[2]);
             }
             __syncwarp();
-            for (int idx = lane; idx < nq * nq; idx += WARP) {
-                const int a = idx / nq, b = idx % nq;
+            const int ow = OBSW();
+            for (int idx = lane; idx < ow * ow; idx += WARP) {
+                const int a = idx / ow, b = idx % ow;
                 if (b > a) continue;
                 T acc = 0;
                 for (int i = 0; i < NOBS(); ++i) {
-                    const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
+                    const T* J = ws + oLJO() + (k * NOBS() + i) * ow;
                     acc += wrow[i] * J[a] * J[b];
                 }
                 sM[(nu + a) * ld + nu + b] += acc;
@@ -1255,9 +1283,9 @@ struct Solver {
             T* crow = sV + 4 * nz;
             for (int i = lane; i < NOBS(); i += WARP) {
                 const int r = nbx + NFRIC() + i;
-                const T* J = ws + oLJO() + (k * NOBS() + i) * nq;
+                const T* J = ws + oLJO() + (k * NOBS() + i) * OBSW();
                 T val = ws[oLHO() + k * NOBS() + i];
-                for (int j = 0; j < nq; ++j) val += J[j] * zk[nu + j];
+                for (int j = 0; j < OBSW(); ++j) val += J[j] * zk[nu + j];
                 const Quad q = recs(k)[2 * r];
                 T corr = T(0);
                 if (corrector) {
@@ -1267,9 +1295,9 @@ struct Solver {
                 crow[i] = side_coef(q.v[0], q.v[2], val, eps, mu_target, corr);
             }
             __syncwarp();
-            if (lane < nq) {
+            if (lane < OBSW()) {
                 T acc = 0;
-                for (int i = 0; i < NOBS(); ++i) acc += crow[i] * ws[oLJO() + (k * NOBS() + i) * nq + lane];
+                for (int i = 0; i < NOBS(); ++i) acc += crow[i] * ws[oLJO() + (k * NOBS() + i) * OBSW() + lane];
                 vec[nu + lane] += acc;
             }
             __syncwarp();
@@ -1472,9 +1500,9 @@ struct Solver {
                     crow[i] = fdiv(dd.v[0] * dd.v[2] - target_mu, q.v[0] + eps * q.v[2]);
                 }
                 __syncwarp();
-                if (lane < nq) {
+                if (lane < OBSW()) {
                     T acc = 0;
-                    for (int i = 0; i < NOBS(); ++i) acc += crow[i] * ws[oLJO() + (k * NOBS() + i) * nq + lane];
+                    for (int i = 0; i < NOBS(); ++i) acc += crow[i] * ws[oLJO() + (k * NOBS() + i) * OBSW() + lane];
                     vec[nu + lane] += acc;
                 }
                 __syncwarp();

@@ -314,13 +314,17 @@ class ControllerSettings:
         if self.projectile_path_constraint_enabled:
             raise NotImplementedError("projectile_path_constraint is a 'next' row (SURVEY §8f-2)")
         ia = self.inertial_alignment_settings
-        if ia.constraint_enabled:
-            raise NotImplementedError("the inertial_alignment constraint is a 'next' row (SURVEY §8f-3)")
-        # InertialAlignmentCostGaussNewton (controller_interface.cpp:296-305)
+        # InertialAlignmentCostGaussNewton / InertialAlignmentConstraint (controller_interface.cpp:296-315)
         d.ia_cost_enabled = int(bool(ia.cost_enabled))
-        if d.ia_cost_enabled:
+        d.ia_constraint_enabled = int(bool(ia.constraint_enabled))
+        if d.ia_cost_enabled or d.ia_constraint_enabled:
             d.ia_cost_weight = float(ia.cost_weight)
             d.ia_span[:] = np.asarray(ia.contact_plane_span, dtype=float).reshape(6)
+            d.ia_normal[:] = ia.contact_plane_normal
+            d.ia_com[:] = ia.com
+            d.ia_alpha = float(ia.alpha)
+            d.ia_use_angular_acceleration = int(bool(ia.use_angular_acceleration))
+            d.ia_align_with_fixed_vector = int(bool(ia.align_with_fixed_vector))
         if self.use_operating_points:
             raise NotImplementedError("the operating-point initializer is not supported (DefaultInitializer only)")
         # EndEffectorBoxConstraint (end_effector_box_constraint.h; wrappers.py:240-250)
