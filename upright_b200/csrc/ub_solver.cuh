@@ -211,8 +211,10 @@ struct Solver {
     T* sTT;
     T* sSm;
     int nan_reason = 0;  // where a solve first went non-finite: 1 factorisation, 2 step, 4 complementarity, 5 step size, 3 iterate
-    long long t_lin = 0, t_fac = 0, t_swp = 0, t_side = 0, t_ls = 0, t_res = 0;
-    long long t_f1 = 0, t_f2 = 0, t_f3 = 0, t_f4 = 0, t_g = 0;  // finer: build / dynamics / cholesky / store ; gradient  // phase cycle counters (profile mode)
+    // phase cycle counters (profile mode, option stop_after = 9): linearise, factor pass, forward predictor, corrector
+    // passes, line search; and inside the factor pass: gradient, matrix build, dynamics terms, factorisation
+    long long t_lin = 0, t_fac = 0, t_swp = 0, t_side = 0, t_ls = 0;
+    long long t_g = 0, t_f1 = 0, t_f2 = 0, t_f3 = 0;
 
     __device__ Solver(const DevProblem<T>& P_, const DevProblem<T>& C_, const Layout& L_, int lane_)
         : P(P_), C(C_), L(L_), lane(lane_) {}
@@ -299,27 +301,6 @@ struct Solver {
         for (int j = 0; j < ow; ++j) v += J[j] * d[nu + j];
         return v;
     }
-    // vec += w * a_r   (vec indexed like the stage vector); called by ONE lane per row,
-    // rows may collide on entries -> atomics on shared memory
-    __device__ void row_axpy(int k, int r, int fam, T w, T* vec) const {
-        const int nq = NQ(), nu = NU();
-        if (fam == 0) {
-            atomicAdd(vec + r, w);
-        } else if (fam == 1) {
-            atomicAdd(vec + nu + r - NBOXU(), w);
-        } else if (fam == 2) {
-            const int i = r - NBOXU() - NX(), c = i / 5;
-            const V3<T> a = fric_coeff(c, i % 5);
-            atomicAdd(vec + nq + 3 * c, w * a.x);
-            atomicAdd(vec + nq + 3 * c + 1, w * a.y);
-            atomicAdd(vec + nq + 3 * c + 2, w * a.z);
-        } else {
-            const int i = r - NBOXU() - NX() - NFRIC();
-            const T* J = ws + oLJO() + (k * NOBS() + i) * OBSW();
-            for (int j = 0; j < OBSW(); ++j) atomicAdd(vec + nu + j, w * J[j]);
-        }
-    }
-    __device__ __forceinline__ int nz_of(int k) const { return k < NN() ? NZ() : NX(); }
     // Slack/multiplier record of one inequality row: {t_lo, t_hi, lam_lo, lam_hi} and the step
     // {dt_lo, dt_hi, dlam_lo, dlam_hi}, 8 consecutive values (two 16-byte quads) per row so that a warp
     // reads the rows of a stage with fully coalesced vector loads.
@@ -1859,7 +1840,6 @@ struct Solver {
                 *finite = false;
                 if (nan_reason == 0) nan_reason = !(mu < tinf<T>()) ? 4 : (!(alpha <= T(1)) ? 5 : 2);
             }
-            t_res += 0;
             if (!*finite) break;
         }
         *decr = last_step;
@@ -1895,7 +1875,7 @@ struct Solver {
     // --------------------------------------------------------------- solve
     __device__ void run(const BatchArgs<T>& A, int b) {
         const int nq = NQ(), nx = NX(), nu = NU(), N = NN(), nz = NZ();
-        t_lin = t_fac = t_swp = t_side = t_ls = t_res = t_f1 = t_f2 = t_f3 = t_f4 = t_g = 0;
+        t_lin = t_fac = t_swp = t_side = t_ls = t_f1 = t_f2 = t_f3 = t_g = 0;
         nan_reason = 0;
         // initial guess: DefaultInitializer = zero input, state held
         // (controller_interface.cpp:385-386); x_0 is always the observation
