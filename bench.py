@@ -198,6 +198,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL's own log lines (e.g. "NCCL version ...") go to stderr so that stdout carries the JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = load_library()
     mpc = BatchedMPC(desc, args.precision)
