@@ -29,6 +29,7 @@ extern "C" {
 #define UB_MAX_CONTACTS 32
 #define UB_MAX_SPHERES 16
 #define UB_MAX_PAIRS 32
+#define UB_MAX_DYNAMIC_OBSTACLES 4
 #define UB_MAX_NX (3 * UB_MAX_JOINTS)
 #define UB_BODY_PARAMS 10 /* m, m*com(3), vech(I)(6): rigid_body.h:36-54 */
 #define UB_STATS 8
@@ -75,7 +76,8 @@ typedef struct ub_contact {
 } ub_contact_t;
 
 /* Collision sphere rigidly attached to link `link` (0..nq-1), to the tool
- * frame (link == nq) or to the world (link == -1).  All collision geometry of
+ * frame (link == nq), to the world (link == -1), or riding on dynamic obstacle j
+ * (link == -2 - j; its centre is the position block of that obstacle's state).  All collision geometry of
  * the reference is spheres (upright_assets/thing/xacro/collision_links.urdf.xacro:31-184,
  * obstacles/simple.urdf.xacro:40-102). */
 typedef struct ub_sphere {
@@ -176,6 +178,13 @@ typedef struct ub_problem_desc {
     double ia_alpha;
     double ia_normal[3];
     double ia_com[3];
+
+    /* Dynamic obstacles (constraint/obstacle_constraint.h:8-43, controller_interface.cpp:54-82,194-210;
+     * dynamics/system_dynamics.h:28-38): each appends [p, v, a] (9 values) to the state, x = [x_robot, x_obs...],
+     * with the uncontrolled constant-acceleration model p' = v, v' = a, a' = 0.  State dimension as seen through
+     * the ABI = 3 nq + 9 n_dynamic_obstacles (ub_problem_dims out[0]); x0 and X carry that many columns. */
+    int32_t n_dynamic_obstacles;
+    int32_t reserved3;
 } ub_problem_desc_t;
 
 typedef struct ub_problem ub_problem_t;

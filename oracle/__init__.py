@@ -90,10 +90,12 @@ def linearize(desc, x, u, body_params=None):
     nobs = desc.n_pairs if desc.obstacles_enabled else 0
     o = dict(g=np.zeros(d["n_eq"]), C=np.zeros((d["n_eq"], d["nx"])), Df=np.zeros((d["n_eq"], nfc)), r=np.zeros(3),
              Jp=np.zeros((3, nq)), hfric=np.zeros(nfric), Ffric=np.zeros((nfric, nfc)), hobs=np.zeros(nobs),
-             Jobs=np.zeros((nobs, nq)))
+             Jobs=np.zeros((nobs, d["nx"])))   # dense over q (+ the position block of a dynamic obstacle)
     lib().oracle_linearize(C.byref(desc), _p(_f64(x)), _p(_f64(u)), _p(_f64(body_params)), _p(o["g"]), _p(o["C"]),
                            _p(o["Df"]), _p(o["r"]), _p(o["Jp"]), _p(o["hfric"]), _p(o["Ffric"]), _p(o["hobs"]),
                            _p(o["Jobs"]))
+    o["Jobs_full"] = o["Jobs"]
+    o["Jobs"] = o["Jobs"][:, :nq]
     return o
 
 

@@ -40,8 +40,15 @@ Kinematics<S> forward_kinematics(const ub_problem_desc_t& P, const S* x) {
         for (int s = 0; s < P.n_spheres; ++s)
             if (P.spheres[s].link == link) K.sphere[s] = p + R * vec3_from<S>(P.spheres[s].offset);
     };
-    for (int s = 0; s < P.n_spheres; ++s)
-        if (P.spheres[s].link < 0) K.sphere[s] = vec3_from<S>(P.spheres[s].offset);
+    for (int s = 0; s < P.n_spheres; ++s) {
+        if (P.spheres[s].link == -1) K.sphere[s] = vec3_from<S>(P.spheres[s].offset);
+        // sphere riding on dynamic obstacle j (link == -2 - j): centre = position block of that obstacle's state,
+        // x = [x_robot (3 nq), x_obs_0 (9), ...] (dimensions.h:36-41, obstacle_constraint.h:8-27)
+        if (P.spheres[s].link <= -2) {
+            const S* po = x + 3 * P.nq + 9 * (-2 - P.spheres[s].link);
+            K.sphere[s] = Vec3<S>(po[0], po[1], po[2]);
+        }
+    }
 
     auto offset_frame = [&](const double* Rt, const double* pt) {
         // move the frame origin by a body-fixed offset and re-orient it

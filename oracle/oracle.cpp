@@ -53,13 +53,17 @@ struct Mat {
 };
 
 struct Dims {
-    int nq, nx, nu, nfc, neq, nfric, nobs, npairs, nterm, N, nz;
+    int nq, nx, nxr, nu, nfc, neq, nfric, nobs, npairs, nterm, N, nz;   // nx = nxr (robot) + 9 per dynamic obstacle
 };
 
 static Dims make_dims(const ub_problem_desc_t& P) {
     Dims D;
     D.nq = P.nq;
-    D.nx = 3 * P.nq;
+    D.nxr = 3 * P.nq;
+    // Dynamic obstacles are GENUINE states of the oracle's QP (as in the reference: dimensions.h:36-41,
+    // system_dynamics.h:28-38,86-104): uncontrolled constant-acceleration blocks appended to A with zero rows in B.
+    // The CUDA kernels eliminate them analytically; agreement of the two formulations is part of the parity tests.
+    D.nx = D.nxr + (P.obstacles_enabled ? 9 * P.n_dynamic_obstacles : 0);
     const bool bal = P.balancing_enabled && P.nb > 0;
     D.nfc = bal ? P.nf * P.nc : 0;
     D.nu = P.nq + D.nfc;
@@ -91,6 +95,14 @@ static void discrete_dynamics(const ub_problem_desc_t& P, const Dims& D, Mat& A,
         B(nq + i, i) = 0.5 * dt * dt;
         B(2 * nq + i, i) = dt;
     }
+    // ObstacleDynamics::flowmap (system_dynamics.h:28-38): p' = v, v' = a, a' = 0, exact over dt
+    for (int o = D.nxr; o < D.nx; o += 9)
+        for (int c = 0; c < 3; ++c) {
+            A(o + c, o + c) = A(o + 3 + c, o + 3 + c) = A(o + 6 + c, o + 6 + c) = 1.0;
+            A(o + c, o + 3 + c) = dt;
+            A(o + c, o + 6 + c) = 0.5 * dt * dt;
+            A(o + 3 + c, o + 6 + c) = dt;
+        }
 }
 
 // ---------------------------------------------------------------------------
@@ -113,9 +125,9 @@ struct KnotLin {
 
 static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const double* body_params, const double* x,
                            const double* u, KnotLin& L) {
-    const int nq = D.nq, nx = D.nx;
+    const int nq = D.nq, nx = D.nx, nxr = D.nxr;
     std::vector<Dual> xd(nx);
-    for (int i = 0; i < nx; ++i) xd[i] = Dual::variable(x[i], i);
+    for (int i = 0; i < nx; ++i) xd[i] = i < nxr ? Dual::variable(x[i], i) : Dual(x[i]);  // AD over the robot state
     const Kinematics<Dual> K = forward_kinematics<Dual>(P, xd.data());
     L.Jp = Mat(3, nq);
     for (int i = 0; i < 3; ++i) {
@@ -131,7 +143,7 @@ static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const doub
         object_dynamics_constraints<Dual>(P, body_params, K, f.data(), g.data());
         for (int i = 0; i < D.neq; ++i) {
             L.g[i] = g[i].v;
-            for (int j = 0; j < nx; ++j) L.C(i, j) = g[i].d[j];
+            for (int j = 0; j < nxr; ++j) L.C(i, j) = g[i].d[j];
         }
         // g is affine in the forces: column j of Df = g(f + e_j) - g(f)
         const Kinematics<double> Kd = forward_kinematics<double>(P, x);
@@ -165,7 +177,7 @@ static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const doub
         inertial_alignment_error<Dual>(P, K, e);
         for (int r = 0; r < 2; ++r) {
             L.ea[r] = e[r].v;
-            for (int j = 0; j < nx; ++j) L.Jea(r, j) = e[r].d[j];
+            for (int j = 0; j < nxr; ++j) L.Jea(r, j) = e[r].d[j];
         }
     }
     L.Jia = Mat(5, nx);
@@ -174,17 +186,31 @@ static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const doub
         inertial_alignment_constraints<Dual>(P, K, h);
         for (int r = 0; r < 5; ++r) {
             L.hia[r] = h[r].v;
-            for (int j = 0; j < nx; ++j) L.Jia(r, j) = h[r].d[j];
+            for (int j = 0; j < nxr; ++j) L.Jia(r, j) = h[r].d[j];
         }
     }
     L.hobs.assign(D.npairs, 0.0);
-    L.Jobs = Mat(D.npairs, nq);
+    L.Jobs = Mat(D.npairs, nx);   // dense over q, plus the position block of a dynamic obstacle in the pair
     if (D.npairs > 0) {
         std::vector<Dual> h(D.npairs);
         obstacle_constraints<Dual>(P, K, h.data());
         for (int i = 0; i < D.npairs; ++i) {
             L.hobs[i] = h[i].v;
             for (int j = 0; j < nq; ++j) L.Jobs(i, j) = h[i].d[j];
+            // d |c_a - c_b| / d c_a = +n, / d c_b = -n for an obstacle-borne centre (analytic: AD runs over x_robot)
+            const int pa = P.pairs[i].a, pb = P.pairs[i].b;
+            double n[3], len = 0;
+            for (int c = 0; c < 3; ++c) {
+                n[c] = K.sphere[pa][c].v - K.sphere[pb][c].v;
+                len += n[c] * n[c];
+            }
+            len = std::sqrt(len);
+            for (int side = 0; side < 2; ++side) {
+                const int s = side == 0 ? pa : pb;
+                if (P.spheres[s].link > -2) continue;
+                const int o = nxr + 9 * (-2 - P.spheres[s].link);
+                for (int c = 0; c < 3; ++c) L.Jobs(i, o + c) += (side == 0 ? 1.0 : -1.0) * n[c] / len;
+            }
         }
     }
 }
@@ -247,13 +273,13 @@ static Perf performance(const ub_problem_desc_t& P, const Dims& D, const Mat& A,
                 pf.eq_sse += e * e;
                 pf.max_eq = std::max(pf.max_eq, std::fabs(e));
             }
-            for (int i = nq; i < nx; ++i) {
+            for (int i = nq; i < D.nxr; ++i) {
                 pf.eq_sse += sq(x[i]);
                 pf.max_eq = std::max(pf.max_eq, std::fabs(x[i]));
             }
         }
         if (k >= 1)
-            for (int i = 0; i < nx; ++i) {
+            for (int i = 0; i < D.nxr; ++i) {
                 const double lo = x[i] - P.state_lb[i], hi = P.state_ub[i] - x[i];
                 pf.ineq_sse += dt * (sq(std::min(0.0, lo)) + sq(std::min(0.0, hi)));
                 pf.min_margin = std::min(pf.min_margin, std::min(lo, hi));
@@ -261,7 +287,7 @@ static Perf performance(const ub_problem_desc_t& P, const Dims& D, const Mat& A,
         if (k == N) break;
         const double* u = U + size_t(k) * nu;
         double c = 0;
-        for (int i = 0; i < nx; ++i) c += 0.5 * P.state_weight[i] * sq(x[i] - P.xd[i]);
+        for (int i = 0; i < D.nxr; ++i) c += 0.5 * P.state_weight[i] * sq(x[i] - P.xd[i]);  // no weight on obstacle states
         for (int i = 0; i < nq; ++i) c += 0.5 * P.input_weight[i] * sq(u[i]);
         for (int i = 0; i < D.nfc; ++i) c += 0.5 * P.force_weight * sq(u[nq + i]);
         for (int i = 0; i < 3; ++i) c += 0.5 * P.ee_weight[i] * sq(K.r[i] - rd[i]);
@@ -373,7 +399,7 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
                 s.H(nq + i, nq + i) = dt * P.force_weight + P.reg_input;
                 s.g[nq + i] = dt * P.force_weight * u[nq + i];
             }
-            for (int i = 0; i < nx; ++i) {
+            for (int i = 0; i < D.nxr; ++i) {   // obstacle states carry no weight (controller_interface.cpp:410-414)
                 s.H(xo + i, xo + i) = dt * P.state_weight[i];
                 s.g[xo + i] = dt * P.state_weight[i] * (x[i] - P.xd[i]);
             }
@@ -435,7 +461,7 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
         }
         // state box, nodes 1..N (x_0 is fixed) (controller_interface.cpp:157-163)
         if (k >= 1)
-            for (int i = 0; i < nx; ++i) {
+            for (int i = 0; i < D.nxr; ++i) {   // bounds on the robot state only (controller_interface.cpp:157-163)
                 Row r;
                 r.idx = xo + i;
                 r.lb = P.state_lb[i] - x[i];
@@ -448,7 +474,7 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
             for (int i = 0; i < D.npairs; ++i) {
                 Row r;
                 r.a.assign(s.nz, 0.0);
-                for (int j = 0; j < nq; ++j) r.a[xo + j] = L.Jobs(i, j);
+                for (int j = 0; j < nx; ++j) r.a[xo + j] = L.Jobs(i, j);
                 r.c = L.hobs[i];
                 r.lb = 0.0;
                 finish(r, soft_poly);
@@ -492,7 +518,7 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
                 finish(r, soft_poly);
                 s.rows.push_back(r);
             }
-            for (int i = nq; i < nx; ++i) {
+            for (int i = nq; i < D.nxr; ++i) {
                 Row r;
                 r.a.assign(s.nz, 0.0);
                 r.a[xo + i] = 1.0;

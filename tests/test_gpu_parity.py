@@ -465,3 +465,61 @@ def test_inertial_alignment_constraint_parity(mode):
     ok = o32["status"] == ref["status"]
     ex = (np.abs(o32["X"] - ref["X"]) / rx).reshape(8, -1).max(axis=1)
     assert ok.mean() >= 0.75 and ex[ok].max() <= 1e-2
+
+
+def _dyn_obstacle_desc(moving):
+    """cfg4 with its first world sphere riding on a dynamic obstacle (+9 states)."""
+    import copy
+    desc, meta = problem_io.load_fixture("cfg4_thing_obstacles2")
+    d = copy.deepcopy(desc)
+    slot = [i for i in range(d.n_spheres) if d.spheres[i].link == -1][0]
+    d.spheres[slot].link = -2
+    d.n_dynamic_obstacles = 1
+    p0 = np.array(list(d.spheres[slot].offset))
+    return desc, d, meta, slot, p0
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_dynamic_obstacle_kernels_match_full_state_oracle(prec):
+    """Dynamic obstacles (obstacle_constraint.h:8-43): the kernels eliminate the uncontrolled obstacle states
+    analytically, the oracle carries them as genuine QP states (as the reference does) — same trajectories."""
+    desc, dyn, meta, slot, p0 = _dyn_obstacle_desc(True)
+    b = batch_for("cfg4_thing_obstacles2", 8, 5)
+    mpc = BatchedMPC(dyn, prec)
+    assert mpc.nx == 36 and mpc.nx_robot == 27
+    r_ee = mpc.eval("end_effector_position", np.hstack((b["x0"], np.zeros((8, 9)))), np.zeros((8, mpc.nu)))
+    # the obstacle starts 2 m behind the static sphere's place and heads for a point 0.7 m beside the tray
+    dirn = (p0 - r_ee) / np.linalg.norm(p0 - r_ee, axis=1, keepdims=True)
+    lateral = np.cross(dirn, [0.0, 0.0, 1.0])
+    lateral /= np.linalg.norm(lateral, axis=1, keepdims=True)
+    far = p0 + 2.0 * dirn
+    vel = (r_ee + 0.7 * lateral - far) / 3.0
+    xo = np.hstack((far, vel, np.zeros((8, 3))))
+    xo[0] = np.concatenate((p0, np.zeros(6)))                    # instance 0: obstacle at rest where the sphere was
+    x0 = np.hstack((b["x0"], xo))
+    # probe: distances use the obstacle position carried in x
+    h = mpc.eval("obstacle_avoidance", x0, np.zeros((8, mpc.nu)))
+    href = np.array([oracle.linearize(dyn, x0[i], np.zeros(mpc.nu))["hobs"] for i in range(8)])
+    assert np.allclose(h, href, atol=1e-10)
+    ref = oracle.solve_batch(dyn, x0, b["target"], b["body_params"])
+    out = mpc.solve(x0, b["target"], b["body_params"])
+    ok = ref["status"] == 0
+    assert ok.sum() >= 5
+    if prec == "f64":
+        assert (out["status"] == ref["status"]).all()
+        assert np.abs(out["X"][ok] - ref["X"][ok]).max() < 1e-7 and np.abs(out["U"][ok] - ref["U"][ok]).max() < 1e-6
+        # instance 0 = the static-sphere problem
+        static = BatchedMPC(desc, "f64").solve(b["x0"][:1], b["target"][:1], None if b["body_params"] is None else b["body_params"][:1])
+        assert np.abs(out["X"][0][:, :27] - static["X"][0]).max() < 1e-8
+    else:
+        good = ok & (out["status"] == 0)
+        assert good.sum() >= 4
+        rx, ru = ranges(desc)
+        ex = (np.abs(out["X"][good][:, :, :27] - ref["X"][good][:, :, :27]) / rx).reshape(good.sum(), -1).max(axis=1)
+        assert np.median(ex) <= 2e-3 and ex.max() <= 2e-2
+    # obstacle states of the solution = constant-acceleration prediction (full step) or the held guess (no step)
+    t = dyn.dt * np.arange(dyn.N + 1)[None, :, None]
+    pred = np.concatenate((xo[:, None, :3] + t * xo[:, None, 3:6] + 0.5 * t * t * xo[:, None, 6:],
+                           xo[:, None, 3:6] + t * xo[:, None, 6:], np.tile(xo[:, None, 6:], (1, dyn.N + 1, 1))), axis=2)
+    full = out["stats"][:, 3] == 1.0
+    assert full.sum() >= 4 and np.abs(out["X"][full][:, :, 27:] - pred[full]).max() < (1e-9 if prec == "f64" else 1e-4)

@@ -180,3 +180,21 @@ def test_inertial_alignment_cost_settings():
     d2 = settings.ControllerSettings(cfg, x0=np.array(meta["x0"])).to_desc()
     assert (d2.ia_cost_enabled, d2.ia_constraint_enabled, d2.ia_use_angular_acceleration, d2.ia_align_with_fixed_vector) == (0, 1, 1, 0)
     assert d2.ia_alpha == 0.2 and list(d2.ia_normal) == [0.0, 0.0, 1.0] and list(d2.ia_com) == [0.0, 0.0, 0.1]
+
+
+def test_dynamic_obstacle_settings():
+    """`obstacles.dynamic` (wrappers.py:363-384): +9 states per obstacle, a sphere riding on each, initial state at
+    rest at the first mode."""
+    import copy
+    d, meta = problem_io.load_fixture("cfg4_thing_obstacles2")
+    cfg = copy.deepcopy(meta["controller_config"])
+    cfg["obstacles"]["dynamic"] = [{"name": "ball", "radius": 0.1,
+                                    "modes": [{"time": 0, "position": [3.0, 0.5, 0.8], "velocity": [-1.0, 0, 0], "acceleration": [0, 0, -9.81]}]}]
+    cfg["obstacles"]["collision_pairs"] = list(cfg["obstacles"]["collision_pairs"]) + [["balanced_object_collision_link_0", "ball"]]
+    s = settings.ControllerSettings(cfg)
+    assert s.dims.o == 1 and s.dims.x() == 36 and s.initial_state.shape == (36,)
+    assert np.allclose(s.initial_state[27:], [3.0, 0.5, 0.8, 0, 0, 0, 0, 0, 0])
+    desc = s.to_desc()
+    assert desc.n_dynamic_obstacles == 1 and desc.n_pairs == d.n_pairs + 1
+    riding = [i for i in range(desc.n_spheres) if desc.spheres[i].link == -2]
+    assert len(riding) == 1 and desc.spheres[riding[0]].radius == 0.1

@@ -274,3 +274,54 @@ def test_inertial_alignment_constraint_rows_in_the_oracle(mode):
     assert np.allclose(A5[:, desc.nu:], J, atol=2e-6)
     out = oracle.solve_batch(ia, X[0], target)
     assert out["status"][0] in (0, 1) and np.isfinite(out["X"]).all()
+
+
+def _with_dynamic_obstacle(desc, sphere_slot, state9=None):
+    """Copy of `desc` in which the world sphere `sphere_slot` rides on dynamic obstacle 0."""
+    import copy
+    d = copy.deepcopy(desc)
+    assert d.spheres[sphere_slot].link == -1
+    d.spheres[sphere_slot].link = -2
+    d.n_dynamic_obstacles = 1
+    p = np.array(list(d.spheres[sphere_slot].offset))
+    return d, (np.concatenate((p, np.zeros(6))) if state9 is None else np.asarray(state9, dtype=float))
+
+
+def test_dynamic_obstacle_at_rest_equals_static_sphere():
+    """A dynamic obstacle (+9 states, obstacle_constraint.h:8-43, system_dynamics.h:28-38) that does not move must
+    give exactly the robot trajectory of the static world sphere it replaces; its states stay put."""
+    import oracle
+    desc, meta = problem_io.load_fixture("cfg4_thing_obstacles2")
+    slot = [i for i in range(desc.n_spheres) if desc.spheres[i].link == -1][0]
+    dyn, xo = _with_dynamic_obstacle(desc, slot)
+    assert oracle.dims(dyn)["nx"] == 27 + 9 and oracle.dims(dyn)["n_ineq"] == oracle.dims(desc)["n_ineq"]
+    x0 = np.array(meta["x0"], dtype=float)
+    target = np.tile(meta["r_ee0"] + np.array([0.1, 0.1, 0.05]), (desc.N + 1, 1))
+    ref = oracle.solve_batch(desc, x0, target)
+    out = oracle.solve_batch(dyn, np.concatenate((x0, xo)), target)
+    assert out["status"][0] == ref["status"][0] and out["X"].shape == (1, desc.N + 1, 36)
+    assert np.abs(out["X"][0][:, :27] - ref["X"][0]).max() < 1e-8 and np.abs(out["U"] - ref["U"]).max() < 1e-7
+    assert np.abs(out["X"][0][:, 27:] - xo).max() < 1e-12
+
+
+def test_moving_dynamic_obstacle_prediction_and_avoidance():
+    """The obstacle states of the solution follow the constant-acceleration model from the observation, and the
+    robot reacts to where the obstacle WILL be (rows linearised at the held guess + the known obstacle step)."""
+    import oracle
+    desc, meta = problem_io.load_fixture("cfg4_thing_obstacles2")
+    slot = [i for i in range(desc.n_spheres) if desc.spheres[i].link == -1][0]
+    p0 = np.array(list(desc.spheres[slot].offset))
+    x0 = np.array(meta["x0"], dtype=float)
+    target = np.tile(meta["r_ee0"] + np.array([0.1, 0.1, 0.05]), (desc.N + 1, 1))
+    r_ee = np.array(oracle.fk(desc, x0)["r"])
+    far = p0 + 3.0 * (p0 - r_ee) / np.linalg.norm(p0 - r_ee)          # starts 3 m further away ...
+    vel = (r_ee - far) / 2.0                                           # ... and reaches the tray in 2 s
+    dyn, xo = _with_dynamic_obstacle(desc, slot, np.concatenate((far, vel, [0.0, 0.0, -0.1])))
+    out = oracle.solve_batch(dyn, np.concatenate((x0, xo)), target)
+    assert out["status"][0] in (0, 1) and out["stats"][0][3] == 1.0       # full step accepted
+    t = desc.dt * np.arange(desc.N + 1)[:, None]
+    pred = np.hstack((xo[:3] + t * xo[3:6] + 0.5 * t * t * xo[6:], xo[3:6] + t * xo[6:], np.tile(xo[6:], (desc.N + 1, 1))))
+    assert np.abs(out["X"][0][:, 27:] - pred).max() < 1e-10
+    parked, xs = _with_dynamic_obstacle(desc, slot, np.concatenate((far, np.zeros(6))))
+    still = oracle.solve_batch(parked, np.concatenate((x0, xs)), target)
+    assert np.abs(out["X"][0][:, :27] - still["X"][0][:, :27]).max() > 1e-3   # the approaching obstacle changes the plan

@@ -14,6 +14,7 @@ UB_MAX_BODIES = 8
 UB_MAX_CONTACTS = 32
 UB_MAX_SPHERES = 16
 UB_MAX_PAIRS = 32
+UB_MAX_DYNAMIC_OBSTACLES = 4
 UB_MAX_NX = 27
 UB_BODY_PARAMS = 10
 UB_STATS = 8
@@ -97,6 +98,7 @@ class ProblemDesc(C.Structure):
         ("ia_constraint_enabled", C.c_int32), ("ia_use_angular_acceleration", C.c_int32),
         ("ia_align_with_fixed_vector", C.c_int32), ("reserved2", C.c_int32), ("ia_alpha", C.c_double),
         ("ia_normal", C.c_double * 3), ("ia_com", C.c_double * 3),
+        ("n_dynamic_obstacles", C.c_int32), ("reserved3", C.c_int32),
     ]
 
     # convenience

@@ -161,6 +161,8 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
     P.nfric = (bal && d.nf == 3) ? 5 * d.nc : 0;
     P.npairs = d.obstacles_enabled ? d.n_pairs : 0;
     P.eebox = d.ee_box_enabled ? 1 : 0;
+    P.ndyn = d.obstacles_enabled ? d.n_dynamic_obstacles : 0;
+    P.nxo = 9 * P.ndyn;
     P.iacon = d.ia_constraint_enabled ? 1 : 0;
     // end-effector box rows, then inertial-alignment rows, ride behind the sphere-pair rows
     P.nobs = P.npairs + (P.eebox ? 6 : 0) + (P.iacon ? 5 : 0);
@@ -266,7 +268,7 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
 template <typename T>
 ub::Layout make_layout(const ub::DevProblem<T>& P) {
     return ub::compute_layout(ub::LayoutDims{P.N, P.nq, P.nx, P.nu, P.neq, P.nfc, P.nterm, P.nrow, P.nobs, P.nb, int(sizeof(T)),
-                                             P.iacost ? 2 : 0, P.obsw});
+                                             P.iacost ? 2 : 0, P.obsw, P.nxo});
 }
 
 }  // namespace
@@ -373,7 +375,7 @@ int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
     // kernels specialised on the BASELINE dimensions (nq, nf, nc, nb); anything else runs the generic one
     const bool generic_only = std::getenv("UB_FORCE_GENERIC") != nullptr;
     ub::LaunchFn<T> fn = Pick<T>::generic();
-    if (!generic_only && H.balancing && H.N == 20 && !H.iacost && !H.iacon) {
+    if (!generic_only && H.balancing && H.N == 20 && !H.iacost && !H.iacon && H.ndyn == 0) {
         const bool no_obs = H.nobs == 0;
         if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::thing_1obj();
         if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12 && !H.eebox) fn = Pick<T>::thing_obs12();
@@ -409,6 +411,7 @@ int solve_device(ub_problem* p, int B, const void* x0, const void* target, const
     A.warm = (flags & UB_WARM_START) ? 1 : 0;
     A.stop_after = p->stop_after;
     A.gain_stages = gain_stages < 0 ? Pick<T>::host(p).N : gain_stages;
+    A.nxt = Pick<T>::host(p).nx + Pick<T>::host(p).nxo;
     UB_CUDA(cudaEventRecord(p->ev0, stream));
     int rc = launch_solve<T>(p, A, stream);
     if (rc != UB_OK) return rc;
@@ -422,8 +425,9 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
                double* K, int32_t* status, double* stats, uint32_t flags, cudaStream_t stream) {
     const ub::DevProblem<T>& P = Pick<T>::host(p);
     const ub::Layout& L = Pick<T>::layout(p);
-    const size_t n_x0 = size_t(B) * P.nx, n_tg = size_t(B) * (P.N + 1) * 3, n_bd = body ? size_t(B) * P.nb * UB_BODY_PARAMS : 0;
-    const size_t n_X = size_t(B) * (P.N + 1) * P.nx, n_U = size_t(B) * P.N * P.nu;
+    const size_t nxt = size_t(P.nx + P.nxo);   // robot state + dynamic-obstacle states
+    const size_t n_x0 = size_t(B) * nxt, n_tg = size_t(B) * (P.N + 1) * 3, n_bd = body ? size_t(B) * P.nb * UB_BODY_PARAMS : 0;
+    const size_t n_X = size_t(B) * (P.N + 1) * nxt, n_U = size_t(B) * P.N * P.nu;
     const size_t n_K = K ? size_t(B) * P.N * P.nu * P.nx : 0, n_st = size_t(B) * UB_STATS;
     const size_t n_ws = size_t(workspace_bytes<T>(p, B)) / sizeof(T);
     const size_t n_in = n_x0 + n_tg + n_bd, n_io = n_X + n_U;
@@ -506,8 +510,8 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
                 if (status[b] == UB_STATUS_NAN) idx.push_back(b);
             if (!idx.empty()) {
                 const int n = int(idx.size());
-                const size_t sx0 = P.nx, stg = size_t(P.N + 1) * 3, sbd = size_t(P.nb) * UB_BODY_PARAMS,
-                             sX = size_t(P.N + 1) * P.nx, sU = size_t(P.N) * P.nu, sK = size_t(P.N) * P.nu * P.nx;
+                const size_t sx0 = nxt, stg = size_t(P.N + 1) * 3, sbd = size_t(P.nb) * UB_BODY_PARAMS,
+                             sX = size_t(P.N + 1) * nxt, sU = size_t(P.N) * P.nu, sK = size_t(P.N) * P.nu * P.nx;
                 std::vector<double> rx0(n * sx0), rtg(n * stg), rbd(body ? n * sbd : 0), rX(n * sX), rU(n * sU),
                     rK(K ? n * sK : 0), rst(n * UB_STATS);
                 std::vector<int32_t> rstatus(n);
@@ -683,6 +687,11 @@ int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
     if (desc->nf != 1 && desc->nf != 3) return fail(UB_E_INVALID, "nf must be 1 or 3");
     if (desc->N < 1 || desc->N > 128) return fail(UB_E_INVALID, "N out of range");
     if (desc->n_spheres > UB_MAX_SPHERES || desc->n_pairs > UB_MAX_PAIRS) return fail(UB_E_INVALID, "too many spheres / pairs");
+    if (desc->n_dynamic_obstacles < 0 || desc->n_dynamic_obstacles > UB_MAX_DYNAMIC_OBSTACLES)
+        return fail(UB_E_INVALID, "too many dynamic obstacles");
+    for (int s = 0; s < desc->n_spheres; ++s)
+        if (desc->spheres[s].link < -1 - desc->n_dynamic_obstacles || desc->spheres[s].link > desc->nq)
+            return fail(UB_E_INVALID, "sphere attached to an unknown link / dynamic obstacle");
     if (desc->ee_box_enabled)
         for (int c = 0; c < 3; ++c)
             if (!(desc->ee_box_lower[c] < desc->ee_box_upper[c]))
@@ -726,7 +735,8 @@ void ub_problem_destroy(ub_problem_t* p) {
 
 int ub_problem_dims(const ub_problem_t* p, int32_t out[8]) {
     if (!p) return fail(UB_E_INVALID, "null problem");
-    out[0] = p->hf.nx; out[1] = p->hf.nu; out[2] = p->hf.neq; out[3] = p->hf.nfric + p->hf.nobs;
+    out[0] = p->hf.nx + p->hf.nxo;   // state dimension as the reference counts it (dimensions.h:36-41)
+    out[1] = p->hf.nu; out[2] = p->hf.neq; out[3] = p->hf.nfric + p->hf.nobs;
     out[4] = p->hf.nterm; out[5] = p->hf.N; out[6] = p->hf.nb; out[7] = p->hf.nc;
     return UB_OK;
 }
@@ -793,6 +803,7 @@ int ub_closed_loop(ub_problem_t* p, int32_t B, const double* x0, const double* t
                    int32_t M, const double* body_params, const ub_closed_loop_params_t* params, double* xs, double* us,
                    double* x_final, int32_t* n_replans, int32_t* status_counts, uint32_t flags, void* cuda_stream) {
     if (!p || !x0 || !target_times || !target_pos || !params) return fail(UB_E_INVALID, "null argument");
+    if (p->hf.ndyn > 0) return fail(UB_E_INVALID, "ub_closed_loop does not simulate dynamic obstacles");
     if (B <= 0 || M <= 0) return fail(UB_E_INVALID, "B and M must be positive");
     if (!(params->sim_dt > 0) || !(params->replan_period > 0) || params->n_steps <= 0)
         return fail(UB_E_INVALID, "sim_dt, replan_period and n_steps must be positive");
@@ -832,7 +843,7 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= M) return;
     const ub::DevProblem<double>& P = *Pg;
-    const double* xm = x + size_t(m) * P.nx;
+    const double* xm = x + size_t(m) * (P.nx + P.nxo);
     const double* um = u + size_t(m) * P.nu;
     const double* bp = body ? body + size_t(m) * P.nb * UB_BODY_PARAMS : &P.body[0][0];
     double* o = out + size_t(m) * rows;
@@ -840,6 +851,10 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
     ub::KinTan<double> D;
     double sph[3 * UB_MAX_SPHERES];
     ub::forward_kinematics<double, false>(P, xm, -1, K, D, P.npairs > 0 ? sph : nullptr, nullptr);
+    if (P.npairs > 0)
+        for (int s = 0; s < P.nsph; ++s)
+            if (P.slink[s] <= -2)   // sphere riding on a dynamic obstacle: centre = position block of its state
+                for (int c = 0; c < 3; ++c) sph[3 * s + c] = xm[P.nx + 9 * (-2 - P.slink[s]) + c];
     const int nq = P.nq;
     if (what == EV_EEPOS) {
         o[0] = K.r.x; o[1] = K.r.y; o[2] = K.r.z;
@@ -941,7 +956,7 @@ extern "C" int ub_eval(ub_problem_t* p, const char* name, int32_t M, const doubl
     if (rows == 0) return UB_OK;
     if (out_capacity < M * rows) return fail(UB_E_INVALID, "output buffer too small");
     UB_CUDA(cudaSetDevice(p->device));
-    const size_t nx_b = size_t(M) * P.nx * 8, nu_b = size_t(M) * P.nu * 8, tg_b = target ? size_t(M) * 24 : 0,
+    const size_t nx_b = size_t(M) * (P.nx + P.nxo) * 8, nu_b = size_t(M) * P.nu * 8, tg_b = target ? size_t(M) * 24 : 0,
                  bd_b = body_params ? size_t(M) * P.nb * UB_BODY_PARAMS * 8 : 0, out_b = size_t(M) * rows * 8;
     char* d = nullptr;
     UB_CUDA(cudaMalloc(&d, nx_b + nu_b + tg_b + bd_b + out_b));

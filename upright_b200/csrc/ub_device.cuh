@@ -46,6 +46,8 @@ struct DevProblem {
     // inertial-alignment constraint (inertial_alignment.cpp:7-53): five rows behind the obstacle / box rows
     int iacon, ia_use_ang, ia_fixed, obsw;
     T ia_alpha, ia_n[3], ia_com[3];
+    // dynamic obstacles: ndyn x [p, v, a] appended to the state (nxo = 9 ndyn); spheres with slink == -2 - j ride on j
+    int ndyn, nxo;
 };
 
 // Division in the interior-point row updates (eight per inequality row and pass): the fp32 kernels use the

@@ -32,6 +32,8 @@ struct Layout {
     int TG, BD;
     // inertial-alignment cost rows: values [N, 2] and Jacobians [N, 2, nx] (only when that cost is enabled)
     int LIA, LJA;
+    // dynamic-obstacle states: iterate [N+1, nxo] and Newton step (exact rollout - iterate) [N+1, nxo]
+    int XO, DXO;
 };
 // side records of a stage are staged in shared memory (cp.async, one stage ahead) up to this many rows
 #define UB_STAGE_ROWS_MAX 64
@@ -39,6 +41,7 @@ struct LayoutDims {
     int N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, nb, tsize;
     int nia = 0;   // rows of the inertial-alignment cost (0 or 2)
     int obsw = 0;  // width of the obstacle-family rows (0 -> nq)
+    int nxo = 0;   // dynamic-obstacle states (9 per obstacle)
 };
 __host__ __device__ constexpr int ub_round4(int n) { return (n + 3) / 4 * 4; }
 __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
@@ -78,6 +81,8 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.BD = o;   o += ub_round4((d.nb > 0 ? d.nb : 1) * 10);
     L.LIA = o;  o += ub_round4(N * d.nia);
     L.LJA = o;  o += ub_round4(N * d.nia * nx);
+    L.XO = o;   o += ub_round4((N + 1) * d.nxo);
+    L.DXO = o;  o += ub_round4((N + 1) * d.nxo);
     L.total = o;
     int s = 0;
     L.sM = s;   s += ub_round4(nz * ldm > fstride ? nz * ldm : fstride);
@@ -115,6 +120,7 @@ struct BatchArgs {
     // c * warps_per_cta + w in workspace slot of the same index (test aid: intermediate blocks are inspected).
     int* queue;
     int n_slots;      // workspace slots (= warps that may work); B in the static mode
+    int nxt;          // columns of x0 / X / Xin: robot state + dynamic-obstacle states
 };
 
 
@@ -169,6 +175,18 @@ struct Solver {
     // box, the whole state when inertial-alignment constraint rows (which see v and a) ride along
     __device__ __forceinline__ int OBSW() const { if constexpr (D::kStatic) return D::nq; else return P.obsw; }
     __device__ __forceinline__ bool IACON() const { if constexpr (D::kStatic) return false; else return P.iacon != 0; }
+    // dynamic obstacles (run-time-dimension kernel only): number of appended states
+    __device__ __forceinline__ int NXO() const { if constexpr (D::kStatic) return 0; else return P.nxo; }
+    // Sphere centres of the dynamic obstacles at knot k for the obstacle iterate XO + ao * DXO.  The obstacle states
+    // are uncontrolled (system_dynamics.h:28-38): their Newton step DXO = exact rollout - iterate is known before
+    // the QP, so they never enter it — their effect is the shift of the distance-row constants in linearize().
+    __device__ __forceinline__ void place_dynamic_spheres(int k, T ao, T* sph) const {
+        for (int s = 0; s < P.nsph; ++s)
+            if (P.slink[s] <= -2) {
+                const int o = (k * P.ndyn + (-2 - P.slink[s])) * 9;
+                for (int c = 0; c < 3; ++c) sph[3 * s + c] = ws[oXO() + o + c] + (ao != T(0) ? ao * ws[oDXO() + o + c] : T(0));
+            }
+    }
     // the inertial-alignment cost likewise (run-time-dimension kernel only)
     __device__ __forceinline__ bool IALIGN() const { if constexpr (D::kStatic) return false; else return P.iacost != 0; }
     __device__ __forceinline__ int NPAIRS() const { if constexpr (D::kStatic) return D::nobs; else return P.npairs; }
@@ -177,7 +195,7 @@ struct Solver {
     __device__ __forceinline__ int o##name() const { if constexpr (D::kStatic) { constexpr Layout l = D::template layout<T>(); return l.name; } else return L.name; }
     UB_OFF(Z) UB_OFF(DZ) UB_OFF(GAP) UB_OFF(LG) UB_OFF(LCT) UB_OFF(LR) UB_OFF(LJP) UB_OFF(LHO) UB_OFF(LJO) UB_OFF(DF)
     UB_OFF(RHOE) UB_OFF(YE) UB_OFF(RHOT) UB_OFF(YT) UB_OFF(TT) UB_OFF(LAM) UB_OFF(FAC) UB_OFF(WF) UB_OFF(XN) UB_OFF(UN)
-    UB_OFF(XW) UB_OFF(UW) UB_OFF(TG) UB_OFF(BD) UB_OFF(LIA) UB_OFF(LJA)
+    UB_OFF(XW) UB_OFF(UW) UB_OFF(TG) UB_OFF(BD) UB_OFF(LIA) UB_OFF(LJA) UB_OFF(XO) UB_OFF(DXO)
 #undef UB_OFF
     __device__ __forceinline__ int LDM() const { return NZ() | 1; }
     __device__ __forceinline__ int LDF() const { return NU() | 1; }
@@ -439,6 +457,7 @@ struct Solver {
             Kin<T> Kn;
             KinTan<T> Dt;
             forward_kinematics<T, true>(P, x, lane, Kn, Dt, NPAIRS() > 0 ? sph : nullptr, dsph);
+            if (NXO() > 0) place_dynamic_spheres(k, T(0), sph);
             if (lane == 0) {
                 ws[oLR() + 3 * k] = Kn.r.x;
                 ws[oLR() + 3 * k + 1] = Kn.r.y;
@@ -497,7 +516,18 @@ struct Solver {
                     const T dist = sqrt(dot(d, d));
                     const V3<T> dd(dsph[3 * a] - dsph[3 * bb], dsph[3 * a + 1] - dsph[3 * bb + 1],
                                    dsph[3 * a + 2] - dsph[3 * bb + 2]);
-                    if (lane == 0) ws[oLHO() + k * NOBS() + i] = dist - (P.srad[a] + P.srad[bb] + C.dmin);
+                    T shift = T(0);
+                    if (NXO() > 0) {
+                        // known Newton step of the obstacle positions: h + (dh/dc_a) dp_a + (dh/dc_b) dp_b, dh/dc = +-d/|d|
+                        for (int side = 0; side < 2; ++side) {
+                            const int s = side == 0 ? a : bb;
+                            if (P.slink[s] > -2) continue;
+                            const T* dp = ws + oDXO() + (k * P.ndyn + (-2 - P.slink[s])) * 9;
+                            const T proj = (d.x * dp[0] + d.y * dp[1] + d.z * dp[2]) / dist;
+                            shift += side == 0 ? proj : -proj;
+                        }
+                    }
+                    if (lane == 0) ws[oLHO() + k * NOBS() + i] = dist - (P.srad[a] + P.srad[bb] + C.dmin) + shift;
                     if (lane < OBSW()) ws[oLJO() + (k * NOBS() + i) * OBSW() + lane] = lane < nq ? dot(d, dd) / dist : T(0);
                 }
                 if (EEBOX()) {
@@ -544,7 +574,8 @@ struct Solver {
 
     // --------------------------------------------------- performance index
     // Lane k evaluates knot k (values only).  Mirrors orc::performance().
-    __device__ Perf<T> performance(const T* Xt, const T* Ut) const {
+    // `ao`: step along the (known) obstacle-state direction, 0 for the current iterate
+    __device__ Perf<T> performance(const T* Xt, const T* Ut, T ao = T(0)) const {
         const int nq = NQ(), nx = NX(), nu = NU(), N = NN();
         const T dt = C.dt;
         const T scale = rsqrt(T(6 * max(NB(), 1)));
@@ -555,6 +586,20 @@ struct Solver {
             Kin<T> Kn;
             KinTan<T> Dn;
             forward_kinematics<T, false>(P, x, -1, Kn, Dn, NPAIRS() > 0 ? sph : nullptr, nullptr);
+            if (NXO() > 0) {
+                place_dynamic_spheres(k, ao, sph);
+                if (k < N)   // dynamics defect of the obstacle states: (1 - ao) x the defect of the iterate
+                    for (int j = 0; j < P.ndyn; ++j) {
+                        const T* o0 = ws + oXO() + (k * P.ndyn + j) * 9;
+                        const T* o1 = ws + oXO() + ((k + 1) * P.ndyn + j) * 9;
+                        for (int c = 0; c < 3; ++c) {
+                            const T g0 = o0[c] + dt * o0[3 + c] + T(0.5) * dt * dt * o0[6 + c] - o1[c];
+                            const T g1 = o0[3 + c] + dt * o0[6 + c] - o1[3 + c];
+                            const T g2 = o0[6 + c] - o1[6 + c];
+                            dyn += dt * (T(1) - ao) * (T(1) - ao) * (g0 * g0 + g1 * g1 + g2 * g2);
+                        }
+                    }
+            }
             const T* rd = target + 3 * k;
             if (k == N) {
                 for (int i = 0; i < 3; ++i) {
@@ -1880,15 +1925,25 @@ struct Solver {
         // initial guess: DefaultInitializer = zero input, state held
         // (controller_interface.cpp:385-386); x_0 is always the observation
         {
-            const T* x0 = A.x0 + size_t(b) * nx;
+            const int nxt = A.nxt, nxo = NXO();
+            const T* x0 = A.x0 + size_t(b) * nxt;
+            T* XOw = ws + oXO();
             if (!A.warm) {
                 for (int idx = lane; idx < (N + 1) * nx; idx += WARP) X[idx] = x0[idx % nx];
                 for (int idx = lane; idx < N * nu; idx += WARP) U[idx] = T(0);
+                for (int idx = lane; idx < (N + 1) * nxo; idx += WARP) XOw[idx] = x0[nx + idx % nxo];   // state held
             } else {
-                const T* Xin = A.Xin + size_t(b) * (N + 1) * nx;
+                const T* Xin = A.Xin + size_t(b) * (N + 1) * nxt;
                 const T* Uin = A.Uin + size_t(b) * N * nu;
-                for (int idx = lane; idx < (N + 1) * nx; idx += WARP) X[idx] = idx < nx ? x0[idx] : Xin[idx];
+                for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
+                    const int k = idx / nx, i = idx % nx;
+                    X[idx] = k == 0 ? x0[i] : Xin[k * nxt + i];
+                }
                 for (int idx = lane; idx < N * nu; idx += WARP) U[idx] = Uin[idx];
+                for (int idx = lane; idx < (N + 1) * nxo; idx += WARP) {
+                    const int k = idx / nxo, i = idx % nxo;
+                    XOw[idx] = k == 0 ? x0[nx + i] : Xin[k * nxt + nx + i];
+                }
             }
             const T* tg = A.target + size_t(b) * (N + 1) * 3;
             T* tgl = ws + oTG();
@@ -1907,6 +1962,20 @@ struct Solver {
         for (int it = 0; it < max(1, C.sqp_iters); ++it) {
             ++sqp_done;
             long long c0 = clock64();
+            if (NXO() > 0) {
+                // Newton step of the obstacle states = exact constant-acceleration rollout of the observation - iterate
+                const T* o0 = ws + oXO();
+                for (int idx = lane; idx < (N + 1) * P.ndyn * 3; idx += WARP) {
+                    const int k = idx / (P.ndyn * 3), j = (idx / 3) % P.ndyn, c = idx % 3;
+                    const T t = C.dt * T(k);
+                    const T p0 = o0[j * 9 + c], v0 = o0[j * 9 + 3 + c], a0 = o0[j * 9 + 6 + c];
+                    const int o = (k * P.ndyn + j) * 9;
+                    ws[oDXO() + o + c] = p0 + t * v0 + T(0.5) * t * t * a0 - ws[oXO() + o + c];
+                    ws[oDXO() + o + 3 + c] = v0 + t * a0 - ws[oXO() + o + 3 + c];
+                    ws[oDXO() + o + 6 + c] = a0 - ws[oXO() + o + 6 + c];
+                }
+                __syncwarp();
+            }
             linearize();
             t_lin += clock64() - c0;
             if (A.stop_after == 1) break;
@@ -1959,7 +2028,7 @@ struct Solver {
                     Un[idx] = U[idx] + alpha * ws[oZ() + k * nz + i];
                 }
                 __syncwarp();
-                pn = performance(Xn, Un);
+                pn = performance(Xn, Un, alpha);
                 const T vn = pn.violation();
                 if (vn > C.g_max) accepted = false;
                 else if (vn < C.g_min) {
@@ -1988,6 +2057,7 @@ struct Solver {
                 dun += d * d;
                 U[idx] = Un[idx];
             }
+            for (int idx = lane; idx < (N + 1) * NXO(); idx += WARP) ws[oXO() + idx] += alpha * ws[oDXO() + idx];
             dxn = sqrt(warp_sum(dxn));
             dun = sqrt(warp_sum(dun));
             __syncwarp();
@@ -2000,13 +2070,15 @@ struct Solver {
         // solution out + NaN guard
         T bad = 0;
         {
-            T* Xo = A.X + size_t(b) * (N + 1) * nx;
+            const int nxt = A.nxt, nxo = NXO();
+            T* Xo = A.X + size_t(b) * (N + 1) * nxt;
             T* Uo = A.U + size_t(b) * N * nu;
             for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
                 const T v = X[idx];
                 bad += isfinite(v) ? T(0) : T(1);
-                Xo[idx] = v;
+                Xo[(idx / nx) * nxt + idx % nx] = v;
             }
+            for (int idx = lane; idx < (N + 1) * nxo; idx += WARP) Xo[(idx / nxo) * nxt + nx + idx % nxo] = ws[oXO() + idx];
             for (int idx = lane; idx < N * nu; idx += WARP) Uo[idx] = U[idx];
         }
         bad = warp_sum(bad);

@@ -41,6 +41,8 @@ class BatchedMPC:
         dims = (C.c_int32 * 8)()
         B.check(self.lib.ub_problem_dims(self.handle, dims))
         self.nx, self.nu, self.n_eq, self.n_ineq, self.n_term, self.N, self.nb, self.nc = list(dims)
+        # nx counts the dynamic-obstacle states too (9 each, behind the robot state); gains act on the robot state
+        self.nx_robot = 3 * desc.nq
         self._ws = None
 
     def __del__(self):
@@ -85,7 +87,7 @@ class BatchedMPC:
         if reuse:
             K, status, stats = out.get("K"), out["status"], out["stats"]
         else:
-            K = np.empty((Bn, self.N, self.nu, self.nx)) if want_gains else None
+            K = np.empty((Bn, self.N, self.nu, self.nx_robot)) if want_gains else None
             status = np.empty(Bn, dtype=np.int32)
             stats = np.empty((Bn, B.UB_STATS))
         flags = self.flags | (B.UB_WARM_START if warm else 0) | (B.UB_RESCUE_F64 if rescue else 0)
@@ -149,7 +151,7 @@ class BatchedMPC:
         prm = B.ClosedLoopParams(float(sim_dt), float(replan_period), int(n_steps), int(log_stride), int(bool(use_feedback)),
                                  int(bool(cold_start)), int(init_sqp_iteration), int(sqp_iteration), float(gains[0]),
                                  float(gains[1]), float(gains[2]))
-        nq = self.nx // 3
+        nq = self.desc.nq
         n_log = (int(n_steps) + int(log_stride) - 1) // int(log_stride) if log else 0
         xs = np.empty((Bn, n_log, self.nx)) if log else None
         us = np.empty((Bn, n_log, nq)) if log else None

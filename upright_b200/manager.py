@@ -195,7 +195,7 @@ class _RecedingHorizon:
 
     def gain(self, t):
         if self.K is None:
-            return np.zeros((self.B, self.engine.nu, self.engine.nx))
+            return np.zeros((self.B, self.engine.nu, getattr(self.engine, "nx_robot", self.engine.nx)))
         i, w = self._interp(t)
         j = min(i + 1, self.N - 1)
         return (1 - w) * self.K[:, i] + w * self.K[:, j]
@@ -206,7 +206,8 @@ class _RecedingHorizon:
         j = min(i + 1, self.N - 1)
         u_ff = (1 - w) * self.U[:, i] + w * self.U[:, j]
         if self.use_feedback and self.K is not None:
-            u = u_ff + np.einsum("bij,bj->bi", self.gain(t), x - x_nom)
+            nxr = self.K.shape[-1]   # gains act on the robot state (dynamic-obstacle states are uncontrolled)
+            u = u_ff + np.einsum("bij,bj->bi", self.gain(t), (x - x_nom)[:, :nxr])
         else:
             u = u_ff
         return x_nom, u
@@ -216,7 +217,7 @@ class _RecedingHorizon:
         i, w = self._interp(t)
         j = min(i + 1, self.N - 1)
         u_ff = (1 - w) * self.U[:, i] + w * self.U[:, j]
-        return u_ff - np.einsum("bij,bj->bi", self.gain(t), x_nom)
+        return u_ff - np.einsum("bij,bj->bi", self.gain(t), x_nom[:, : self.gain(t).shape[-1]])
 
 
 class ControllerManager:

@@ -256,14 +256,21 @@ class ControllerSettings:
                     path = _resolve_find(inc)
                     self.obstacle_settings.obstacle_urdf_path = str(path)
                     self.obstacle_settings.static_spheres.update(_read_obstacle_xacro(path))
-            if obs.get("dynamic"):
-                raise NotImplementedError(
-                    "dynamic obstacles (+9 states each) are a 'next' row (SURVEY §8f-2)")
+            # dynamic obstacles: +9 states each (wrappers.py:363-384)
+            for od in obs.get("dynamic") or []:
+                modes = [SimpleNamespace(time=float(m["time"]), position=np.array(m["position"], dtype=float),
+                                         velocity=np.array(m["velocity"], dtype=float),
+                                         acceleration=np.array(m["acceleration"], dtype=float)) for m in od["modes"]]
+                self.obstacle_settings.dynamic_obstacles.append(
+                    SimpleNamespace(name=od["name"], radius=float(od["radius"]), modes=modes))
+            self.dims.o = len(self.obstacle_settings.dynamic_obstacles)
 
         if x0 is None:
             x0_robot = pa(config["robot"]["x0"])
             assert x0_robot.shape == (rx,)
-            self.initial_state = x0_robot
+            # the obstacles start at rest at their first mode (wrappers.py:378-384)
+            x0_obs = [np.concatenate((o.modes[0].position, np.zeros(6))) for o in self.obstacle_settings.dynamic_obstacles]
+            self.initial_state = np.concatenate([x0_robot] + x0_obs)
         else:
             self.initial_state = np.array(x0, dtype=float)
         assert self.initial_state.shape == (self.dims.x(),)
@@ -377,6 +384,13 @@ class ControllerSettings:
             for name, (pos, rad) in self.obstacle_settings.static_spheres.items():
                 sidx[name] = len(spheres)
                 spheres.append(robot.Sphere(name, -1, pos, rad))
+            dyn = self.obstacle_settings.dynamic_obstacles
+            if len(dyn) > B.UB_MAX_DYNAMIC_OBSTACLES:
+                raise ValueError("too many dynamic obstacles")
+            for j, o in enumerate(dyn):   # sphere riding on obstacle j: link = -2 - j, centre = its position state
+                sidx[o.name] = len(spheres)
+                spheres.append(robot.Sphere(o.name, -2 - j, o.modes[0].position, o.radius))
+            d.n_dynamic_obstacles = len(dyn)
             used, pairs = {}, []
             for a, b in self.obstacle_settings.collision_link_pairs:
                 ia, ib = (sidx[n[:-2] if n.endswith("_0") else n] for n in (a, b))
