@@ -141,6 +141,17 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
+    # stdout carries the ONE JSON line: everything libraries print there meanwhile (NCCL's version banner ...) is
+    # sent to stderr by pointing file descriptor 1 at it until the line is emitted
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+
     from upright_b200 import workload
     desc, meta = workload.load(args.config)
     rank = int(os.environ.get("RANK", "0"))
@@ -186,7 +197,7 @@ def main():
                                            f"oracle-CPU (restated OCS2-equivalent, fp64), {cores} host threads"},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm
@@ -198,8 +209,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL's own log lines (e.g. "NCCL version ...") go to stderr so that stdout carries the JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = load_library()
     mpc = BatchedMPC(desc, args.precision)
@@ -339,7 +348,7 @@ def main():
         line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{cpu_n} instances of the same workload in {cpu_el:.1f} s, oracle-CPU "
                                           f"(restated OCS2-equivalent, fp64, dense Riccati), {cores} host threads"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
