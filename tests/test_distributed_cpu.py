@@ -62,3 +62,18 @@ def test_sharded_solve_even():
 
 def test_sharded_solve_uneven():
     _run(7)
+
+
+def test_pipelined_gather_views_are_consistent():
+    """Layout of the packed [X | U] buffers of PipelinedSolveGather (pure indexing, no device needed)."""
+    import torch
+    B, N, nx, nu, world = 3, 4, 5, 2, 2
+    nX, nU = (N + 1) * nx, N * nu
+    per = B * (nX + nU)
+    full = torch.arange(world * per, dtype=torch.float32)
+    v = full.view(world, per)
+    X = v[:, : B * nX].reshape(world, B, N + 1, nx)
+    U = v[:, B * nX:].reshape(world, B, N, nu)
+    # rank r, instance b: X rows start at r*per + b*nX, U rows at r*per + B*nX + b*nU
+    assert X[1, 2, 0, 0] == 1 * per + 2 * nX and U[1, 2, 0, 0] == 1 * per + B * nX + 2 * nU
+    assert X[0, 1, 3, 4] == 1 * nX + 3 * nx + 4 and U[0, 0, 3, 1] == B * nX + 3 * nu + 1

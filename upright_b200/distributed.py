@@ -52,3 +52,57 @@ def sharded_solve(solve_fn, x0, target, body_params=None, group=None):
     out = solve_fn(shard(x0, world, rank).contiguous(), shard(target, world, rank).contiguous(),
                    None if body_params is None else shard(body_params, world, rank).contiguous())
     return {k: all_gather_batch(out[k], total, group) for k in ("X", "U", "status")}
+
+
+class PipelinedSolveGather:
+    """Back-to-back sharded solves with the result exchange off the critical path.
+
+    Every rank solves its slice into one packed buffer `[X | U]` (so ONE all-gather moves a step's trajectories) and
+    the all-gather of step s runs on a side stream while the solve kernel of step s+1 already occupies the SMs; two
+    buffers alternate.  `finish()` joins the side stream (call it before reading results or stopping a timer)."""
+
+    def __init__(self, mpc, batch, group=None):
+        self.mpc, self.B, self.group = mpc, batch, group
+        self.world = dist.get_world_size(group)
+        dev, dt = torch.device("cuda", torch.cuda.current_device()), mpc.torch_dtype
+        self.nX, self.nU = (mpc.N + 1) * mpc.nx, mpc.N * mpc.nu
+        self.local = [torch.empty(batch * (self.nX + self.nU), dtype=dt, device=dev) for _ in range(2)]
+        self.full = [torch.empty(self.world * batch * (self.nX + self.nU), dtype=dt, device=dev) for _ in range(2)]
+        self.status = torch.empty(batch, dtype=torch.int32, device=dev)
+        self.stats = torch.empty((batch, 8), dtype=dt, device=dev)
+        self.comm = torch.cuda.Stream(device=dev)
+        self.solved = [torch.cuda.Event() for _ in range(2)]
+        self.gathered = [None, None]
+        self.step_index = 0
+
+    def views(self, i):
+        """(X [B, N+1, nx], U [B, N, nu]) views of local buffer i."""
+        buf, B = self.local[i], self.B
+        return (buf[: B * self.nX].view(B, self.mpc.N + 1, self.mpc.nx), buf[B * self.nX:].view(B, self.mpc.N, self.mpc.nu))
+
+    def gathered_views(self, i):
+        """Per-rank (X, U) views of gathered buffer i: X [world, B, N+1, nx], U [world, B, N, nu]."""
+        per = self.B * (self.nX + self.nU)
+        full = self.full[i].view(self.world, per)
+        return (full[:, : self.B * self.nX].reshape(self.world, self.B, self.mpc.N + 1, self.mpc.nx),
+                full[:, self.B * self.nX:].reshape(self.world, self.B, self.mpc.N, self.mpc.nu))
+
+    def step(self, x0, target, body=None):
+        i = self.step_index & 1
+        self.step_index += 1
+        cur = torch.cuda.current_stream()
+        if self.gathered[i] is not None:
+            cur.wait_event(self.gathered[i])          # the gather that last read this buffer has finished
+        X, U = self.views(i)
+        self.mpc.solve_device(x0, target, body, X=X, U=U, status=self.status, stats=self.stats)
+        self.solved[i].record(cur)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.solved[i])
+            dist.all_gather_into_tensor(self.full[i], self.local[i], group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+            self.gathered[i] = ev
+        return i
+
+    def finish(self):
+        torch.cuda.current_stream().wait_stream(self.comm)
