@@ -292,6 +292,8 @@ struct ub_problem {
     size_t dev_buf_bytes = 0;
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    void* cl_buf = nullptr;   // closed-loop arena
+    size_t cl_buf_bytes = 0;
 };
 
 namespace {
@@ -552,36 +554,50 @@ int closed_loop(ub_problem* p, int B, const double* x0, const double* target_tim
     const int stride = std::max(1, prm.log_stride);
     const int n_log = (xs || us) ? (prm.n_steps + stride - 1) / stride : 0;
     const int gain_stages = prm.use_feedback ? std::min(N, int(std::floor(prm.replan_period / P.dt + 1e-9)) + 2) : 0;
-    struct Dev {
-        std::vector<void*> ptrs;
-        ~Dev() {
-            for (void* q : ptrs) cudaFree(q);
-        }
+    struct Arena {
+        char* base = nullptr;
+        size_t used = 0;
         void* bytes(size_t n) {
-            void* q = nullptr;
-            if (cudaMalloc(&q, std::max<size_t>(n, 16)) != cudaSuccess) return nullptr;
-            ptrs.push_back(q);
-            return q;
+            const size_t at = used;
+            used += (std::max<size_t>(n, 16) + 255) & ~size_t(255);
+            return base ? static_cast<void*>(base + at) : reinterpret_cast<void*>(uintptr_t(256));
         }
     } dev;
     const size_t nX = size_t(B) * (N + 1) * nx, nU = size_t(B) * N * nu;
-    T* d_x = static_cast<T*>(dev.bytes((size_t(B) * nx) * sizeof(T)));
-    T* d_pos = static_cast<T*>(dev.bytes((size_t(B) * M * 3) * sizeof(T)));
-    double* d_times = static_cast<double*>(dev.bytes((M) * sizeof(double)));
-    T* d_body = body ? static_cast<T*>(dev.bytes((size_t(B) * P.nb * UB_BODY_PARAMS) * sizeof(T))) : nullptr;
-    T* d_target = static_cast<T*>(dev.bytes((size_t(B) * (N + 1) * 3) * sizeof(T)));
-    T* d_X[2] = {static_cast<T*>(dev.bytes((nX) * sizeof(T))), static_cast<T*>(dev.bytes((nX) * sizeof(T)))};
-    T* d_U[2] = {static_cast<T*>(dev.bytes((nU) * sizeof(T))), static_cast<T*>(dev.bytes((nU) * sizeof(T)))};
-    T* d_K = gain_stages ? static_cast<T*>(dev.bytes((size_t(B) * gain_stages * nu * nx) * sizeof(T))) : nullptr;
-    T* d_stats = static_cast<T*>(dev.bytes((size_t(B) * UB_STATS) * sizeof(T)));
-    int32_t* d_status = static_cast<int32_t*>(dev.bytes((B) * sizeof(int32_t)));
-    int32_t* d_counts = static_cast<int32_t*>(dev.bytes((size_t(B) * 4) * sizeof(int32_t)));
-    T* d_ws = static_cast<T*>(dev.bytes(size_t(workspace_bytes<T>(p, B)) + 64));
-    T* d_xs = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nx) * sizeof(T))) : nullptr;
-    T* d_us = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nq) * sizeof(T))) : nullptr;
-    if (!d_x || !d_pos || !d_times || (body && !d_body) || !d_target || !d_X[0] || !d_X[1] || !d_U[0] || !d_U[1] ||
-        (gain_stages && !d_K) || !d_stats || !d_status || !d_counts || !d_ws || (n_log && (!d_xs || !d_us)))
-        return fail(UB_E_ALLOC, "cudaMalloc failed for the closed-loop buffers");
+    T *d_x, *d_pos, *d_body, *d_target, *d_X[2], *d_U[2], *d_K, *d_stats, *d_ws, *d_xs, *d_us;
+    double* d_times;
+    int32_t *d_status, *d_counts;
+    // the arena is one cached allocation per problem (grown on demand, freed with the problem): repeated rollouts do
+    // not pay for cudaMalloc / cudaFree of the ~250 MB workspace.  The carve list runs twice: size, then place.
+    auto carve = [&]() {
+        d_x = static_cast<T*>(dev.bytes((size_t(B) * nx) * sizeof(T)));
+        d_pos = static_cast<T*>(dev.bytes((size_t(B) * M * 3) * sizeof(T)));
+        d_times = static_cast<double*>(dev.bytes((M) * sizeof(double)));
+        d_body = body ? static_cast<T*>(dev.bytes((size_t(B) * P.nb * UB_BODY_PARAMS) * sizeof(T))) : nullptr;
+        d_target = static_cast<T*>(dev.bytes((size_t(B) * (N + 1) * 3) * sizeof(T)));
+        d_X[0] = static_cast<T*>(dev.bytes((nX) * sizeof(T)));
+        d_X[1] = static_cast<T*>(dev.bytes((nX) * sizeof(T)));
+        d_U[0] = static_cast<T*>(dev.bytes((nU) * sizeof(T)));
+        d_U[1] = static_cast<T*>(dev.bytes((nU) * sizeof(T)));
+        d_K = gain_stages ? static_cast<T*>(dev.bytes((size_t(B) * gain_stages * nu * nx) * sizeof(T))) : nullptr;
+        d_stats = static_cast<T*>(dev.bytes((size_t(B) * UB_STATS) * sizeof(T)));
+        d_status = static_cast<int32_t*>(dev.bytes((B) * sizeof(int32_t)));
+        d_counts = static_cast<int32_t*>(dev.bytes((size_t(B) * 4) * sizeof(int32_t)));
+        d_ws = static_cast<T*>(dev.bytes(size_t(workspace_bytes<T>(p, B)) + 64));
+        d_xs = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nx) * sizeof(T))) : nullptr;
+        d_us = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nq) * sizeof(T))) : nullptr;
+    };
+    carve();
+    if (dev.used > p->cl_buf_bytes) {
+        if (p->cl_buf) cudaFree(p->cl_buf);
+        p->cl_buf = nullptr;
+        p->cl_buf_bytes = 0;
+        if (cudaMalloc(&p->cl_buf, dev.used) != cudaSuccess) return fail(UB_E_ALLOC, "cudaMalloc failed for the closed-loop buffers");
+        p->cl_buf_bytes = dev.used;
+    }
+    dev.base = static_cast<char*>(p->cl_buf);
+    dev.used = 0;
+    carve();
     while (reinterpret_cast<uintptr_t>(d_ws) % 16 != 0) ++d_ws;
     {
         std::vector<T> h(std::max(std::max(size_t(B) * nx, size_t(B) * M * 3), body ? size_t(B) * P.nb * UB_BODY_PARAMS : size_t(0)));
@@ -727,6 +743,7 @@ void ub_problem_destroy(ub_problem_t* p) {
     if (p->df) cudaFree(p->df);
     if (p->dd) cudaFree(p->dd);
     if (p->dev_buf) cudaFree(p->dev_buf);
+    if (p->cl_buf) cudaFree(p->cl_buf);
     if (p->pinned) cudaFreeHost(p->pinned);
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);

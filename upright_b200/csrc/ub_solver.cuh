@@ -1867,17 +1867,23 @@ struct Solver {
             mu = nsides > 0 ? warp_sum(musum) / T(nsides) : T(0);
             rdmax *= (T(1) - alpha);
             if (!C.soft_poly) {
+                // multiplier update of the hard equality rows and their infeasibility at the new iterate, one visit
+                T pv = T(0);
                 for (int k = 0; k <= N; ++k) {
                     if (neq_of(k) == 0) continue;
                     load_eq_rows(k);
                     const T* zk = Zk(k);
                     for (int i = lane; i < neq_of(k); i += WARP) {
                         const T rho = rho_eq(k)[i];
-                        if (rho > T(0)) y_eq(k)[i] += rho * eq_value(k, i, zk);
+                        if (rho > T(0)) {
+                            const T e = eq_value(k, i, zk);
+                            y_eq(k)[i] += rho * e;
+                            pv = max(pv, fabs(e));
+                        }
                     }
                     __syncwarp();
                 }
-                pinf = eq_infeasibility();
+                pinf = warp_max(pv);
             }
             last_alpha = alpha;
             last_step = warp_max(stepmax);
