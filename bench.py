@@ -344,7 +344,7 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "upright_b200.engine.BatchedMPC.solve -> ub_solve_batch (host double buffers in/out; inputs H2D from pinned staging, every solved instance written home by the kernel through mapped pinned memory, float<->double conversion on host threads)",
+                    "api": "upright_b200.engine.BatchedMPC.solve -> ub_solve_batch (host double buffers in/out; inputs H2D from pinned staging, every solved instance written home by the kernel through mapped pinned memory and converted float->double by host threads behind its completion flag while the kernel runs)",
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "roofline": roofline,
             "converged_fraction": float(np.mean(ok)), "mean_qp_iterations": mean_iters}

@@ -484,19 +484,53 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
     // buffer as soon as that instance is solved: the results cross PCIe while the rest of the batch is still being
     // solved and no device->host copy follows the kernel.  The warm-start inputs are read from the device copy.
     int32_t* h_status = reinterpret_cast<int32_t*>(h + stage_elems);
+    std::memset(h_status, 0xff, size_t(B) * sizeof(int32_t));   // -1 = not solved yet
     const auto t_in = now();
     int rc = solve_device<T>(p, B, d_x0, d_tg, d_bd, h + oX, h + oX + n_X, K ? h + oX + n_io : nullptr, h_status,
                              h + oX + n_io + n_K, d_ws, int64_t(n_ws * sizeof(T)), flags | UB_PTRS_DEVICE, stream, -1,
                              d_X, d_U);
     if (rc != UB_OK) return rc;
-    UB_CUDA(cudaStreamSynchronize(stream));
-    const auto t_sync = now();
+    // Streaming conversion: status[b] (pre-set to -1) is published by the kernel after the rows of instance b; host
+    // workers convert finished instances while the kernel solves the rest.  A worker that waits polls the stream, so
+    // a failed launch cannot hang the call.
+    const size_t sX = size_t(P.N + 1) * nxt, sU = size_t(P.N) * P.nu;
+    const T* hX = h + oX;
+    const T* hU = h + oX + n_X;
+    const T* hS = h + oX + n_io + n_K;
+    std::atomic<int> failed{0};
     {
-        std::vector<Segment<double, T>> outs = {{X, h + oX, n_X}, {U, h + oX + n_X, n_U}};
-        if (n_K) outs.push_back({K, h + oX + n_io, n_K});
-        if (stats) outs.push_back({stats, h + oX + n_io + n_K, n_st});
-        convert_segments(outs);
+        const int n_tasks = std::max(1, std::min(conversion_threads(), (B + 63) / 64));
+        const int device = p->device;
+        WorkerPool::get().parallel_for(n_tasks, [&](int task) {
+            cudaSetDevice(device);
+            // interleaved blocks of 16 instances: the kernel hands instances out in index order, so all workers
+            // stay close behind it
+            for (int blk = task; blk * 16 < B && !failed.load(std::memory_order_relaxed); blk += n_tasks) {
+                for (int b = blk * 16; b < std::min(B, blk * 16 + 16); ++b) {
+                    volatile const int32_t* flag = h_status + b;
+                    unsigned spins = 0;
+                    while (*flag < 0) {
+                        if ((++spins & 0xfff) == 0) {
+                            const cudaError_t q = cudaStreamQuery(stream);
+                            if (q != cudaErrorNotReady && *flag < 0) {   // stream drained (or failed) without this result
+                                failed.store(1);
+                                return;
+                            }
+                        }
+                    }
+                    std::atomic_thread_fence(std::memory_order_acquire);
+                    for (size_t i = 0; i < sX; ++i) X[size_t(b) * sX + i] = double(hX[size_t(b) * sX + i]);
+                    for (size_t i = 0; i < sU; ++i) U[size_t(b) * sU + i] = double(hU[size_t(b) * sU + i]);
+                    if (stats)
+                        for (int i = 0; i < UB_STATS; ++i) stats[size_t(b) * UB_STATS + i] = double(hS[size_t(b) * UB_STATS + i]);
+                }
+            }
+        });
     }
+    UB_CUDA(cudaStreamSynchronize(stream));
+    if (failed.load()) return fail(UB_E_CUDA, "the solve kernel ended without publishing every instance");
+    const auto t_sync = now();
+    if (n_K) convert_array(K, h + oX + n_io, n_K);
     std::memcpy(status, h_status, size_t(B) * sizeof(int32_t));
     if (timing) {
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };

@@ -2092,8 +2092,12 @@ struct Solver {
             status = UB_STATUS_NAN;
             if (nan_reason == 0) nan_reason = 3;
         }
+        // status[b] is the completion flag of the instance: the host path polls it in mapped pinned memory and
+        // converts the rows of finished instances while the kernel is still solving others, so every result of
+        // this warp is fenced system-wide before lane 0 publishes the status (last store below)
+        __threadfence_system();
+        __syncwarp();
         if (lane == 0) {
-            A.status[b] = status;
             if (A.stats) {
                 T* s = A.stats + size_t(b) * UB_STATS;
                 s[0] = T(qp_iters);
@@ -2113,7 +2117,9 @@ struct Solver {
                     s[6] = T(t_swp);
                     s[7] = T(t_side);
                 }
+                __threadfence_system();
             }
+            *reinterpret_cast<volatile int32_t*>(A.status + b) = status;
         }
     }
 };
