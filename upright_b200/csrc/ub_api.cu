@@ -311,6 +311,8 @@ struct Pick<float> {
     static ub::LaunchFn<float> ur10_1obj() { return ub::launch_ur10_1obj_f32; }
     static ub::LaunchFn<float> thing_arch() { return ub::launch_thing_arch_f32; }
     static ub::LaunchFn<float> thing_robust8() { return ub::launch_thing_robust8_f32; }
+    static ub::LaunchFn<float> thing_arch_team() { return ub::launch_thing_arch_team_f32; }
+    static ub::LaunchFn<float> thing_robust8_team() { return ub::launch_thing_robust8_team_f32; }
 };
 template <>
 struct Pick<double> {
@@ -323,21 +325,52 @@ struct Pick<double> {
     static ub::LaunchFn<double> ur10_1obj() { return ub::launch_ur10_1obj_f64; }
     static ub::LaunchFn<double> thing_arch() { return ub::launch_thing_arch_f64; }
     static ub::LaunchFn<double> thing_robust8() { return ub::launch_thing_robust8_f64; }
+    static ub::LaunchFn<double> thing_arch_team() { return ub::launch_thing_arch_team_f64; }
+    static ub::LaunchFn<double> thing_robust8_team() { return ub::launch_thing_robust8_team_f64; }
 };
+
+// Which kernel serves a problem: the instantiations specialised on the BASELINE dimensions (nq, nf, nc, nb), with a
+// team of UB_TEAM_WARPS warps per instance for the large stage matrices (cfg3, cfg5; UB_TEAM=0 keeps one warp), the
+// run-time-dimension kernel for everything else.
+template <typename T>
+ub::LaunchFn<T> select_kernel(const ub_problem* p, int* team_warps) {
+    const ub::DevProblem<T>& H = Pick<T>::host(p);
+    *team_warps = 1;
+    ub::LaunchFn<T> fn = Pick<T>::generic();
+    if (std::getenv("UB_FORCE_GENERIC") != nullptr) return fn;
+    if (!(H.balancing && H.N == 20 && !H.iacost && !H.iacon && H.ndyn == 0)) return fn;
+    const char* te = std::getenv("UB_TEAM");
+    const bool team = !(te && std::atoi(te) == 0);
+    const bool no_obs = H.nobs == 0;
+    if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::thing_1obj();
+    if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12 && !H.eebox) fn = Pick<T>::thing_obs12();
+    if (H.nq == 6 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::ur10_1obj();
+    if (H.nq == 9 && H.nf == 3 && H.nc == 16 && H.nb == 3 && no_obs) {
+        fn = team ? Pick<T>::thing_arch_team() : Pick<T>::thing_arch();
+        *team_warps = team ? UB_TEAM_WARPS : 1;
+    }
+    if (H.nq == 9 && H.nf == 1 && H.nc == 32 && H.nb == 8 && no_obs) {
+        fn = team ? Pick<T>::thing_robust8_team() : Pick<T>::thing_robust8();
+        *team_warps = team ? UB_TEAM_WARPS : 1;
+    }
+    return fn;
+}
 
 // Launch geometry: warps per CTA — two CTAs per SM (the 128-register kernels allow 16 warps per SM), each taking
 // half of the SM's shared memory minus the 1 KB the driver reserves per CTA; at most 8 warps.
 template <typename T>
-int warps_per_cta(const ub_problem* p) {
+int warps_per_cta(const ub_problem* p) {   // = instance teams per CTA
+    int tw = 1;
+    select_kernel<T>(p, &tw);
     const ub::Layout& L = Pick<T>::layout(p);
     const size_t pbytes = (sizeof(ub::DevProblem<T>) + 15) / 16 * 16;
     const size_t per_warp = size_t(L.s_total) * sizeof(T);
     const size_t cta_budget = size_t(p->max_smem_sm) / 2 - 1024;
     int wpc = cta_budget > pbytes ? int((cta_budget - pbytes) / per_warp) : 1;
+    if (wpc > 8 / tw) wpc = 8 / tw;
     if (wpc < 1) wpc = 1;
-    if (wpc > 8) wpc = 8;
     const char* env = std::getenv("UB_WARPS_PER_CTA");
-    if (env) wpc = std::max(1, std::min(8, std::atoi(env)));
+    if (env) wpc = std::max(1, std::min(8 / tw, std::atoi(env)));
     return wpc;
 }
 // Workspace slots of a batch of B: the persistent grid holds one slot per resident warp; the static test mode
@@ -374,17 +407,8 @@ int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
     A.n_slots = int(slots);
     const int grid = int((slots + wpc - 1) / wpc);
     const ub::DevProblem<T>& H = Pick<T>::host(p);
-    // kernels specialised on the BASELINE dimensions (nq, nf, nc, nb); anything else runs the generic one
-    const bool generic_only = std::getenv("UB_FORCE_GENERIC") != nullptr;
-    ub::LaunchFn<T> fn = Pick<T>::generic();
-    if (!generic_only && H.balancing && H.N == 20 && !H.iacost && !H.iacon && H.ndyn == 0) {
-        const bool no_obs = H.nobs == 0;
-        if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::thing_1obj();
-        if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12 && !H.eebox) fn = Pick<T>::thing_obs12();
-        if (H.nq == 6 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::ur10_1obj();
-        if (H.nq == 9 && H.nf == 3 && H.nc == 16 && H.nb == 3 && no_obs) fn = Pick<T>::thing_arch();
-        if (H.nq == 9 && H.nf == 1 && H.nc == 32 && H.nb == 8 && no_obs) fn = Pick<T>::thing_robust8();
-    }
+    int tw = 1;
+    ub::LaunchFn<T> fn = select_kernel<T>(p, &tw);
     UB_CUDA(fn(H, Pick<T>::dev(p), L, A, wpc, grid, smem, stream));
     ++g_launches;
     return UB_OK;

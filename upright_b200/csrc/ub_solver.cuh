@@ -28,6 +28,7 @@ struct Layout {
     // shared memory (units of T, per warp)
     int sM, sP, sPv, sSA, sV, s_total;
     int sSm;  // staged per-stage vectors [z | x | u | Jp | w] (with the staged side records)
+    int sRed; // team reduction / broadcast scratch (16 values)
     // instance-local copies of the desired positions [N+1, 3] and the body parameters [nb, 10]
     int TG, BD;
     // inertial-alignment cost rows: values [N, 2] and Jacobians [N, 2, nx] (only when that cost is enabled)
@@ -93,6 +94,8 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.sTT = s;  s += (d.nrow <= UB_STAGE_ROWS_MAX) ? ub_round4(d.nrow * 8) : 0;  // staged side records of one stage
     L.sSm = s;
     s += (d.nrow <= UB_STAGE_ROWS_MAX) ? ub_round4(nz) + ub_round4(nx) + 2 * ub_round4(nu) + ub_round4(3 * nq) : 0;
+    L.sRed = s;
+    s += 16;
     L.s_total = s;
     return L;
 }
@@ -157,8 +160,12 @@ struct RuntimeDims {
     __host__ __device__ static constexpr Layout layout() { return Layout{}; }
 };
 
-template <typename T, typename D>
+// TW = warps per instance ("team").  One warp serves the small stage matrices (nz <= 40: everything above is
+// written for it); the large ones (cfg3: 84 x 84, cfg5: 68 x 68) take a team of four warps per instance — same
+// shared-memory footprint, four times the lanes in every strided loop, named barriers instead of warp barriers.
+template <typename T, typename D, int TW = 1>
 struct Solver {
+    static constexpr int kTS = TW * WARP;   // threads per instance = stride of the lane-parallel loops
     const DevProblem<T>& P;   // shared-memory copy: arrays indexed per lane
     const DevProblem<T>& C;   // kernel-parameter copy (constant bank): scalars and uniformly indexed entries
     const Layout& L;
@@ -209,7 +216,7 @@ struct Solver {
     // entry (i, j) of a stored factor block [L; Y]: column-major (column length nz+1) for the blocked kernels
     // — written straight from the panel registers with coalesced stores, read conflict-free by every sweep —
     // row-major otherwise
-    static constexpr bool kBlocked = D::kStatic && D::nu <= 16 && D::nz < 2 * WARP;
+    static constexpr bool kBlocked = TW == 1 && D::kStatic && D::nu <= 16 && D::nz < 2 * WARP;
     __device__ __forceinline__ int fidx(int i, int j) const {
         if constexpr (kBlocked) return j * (D::nz + 1) + i;
         else return i * LDF() + j;
@@ -228,6 +235,29 @@ struct Solver {
     T* sV;
     T* sTT;
     T* sSm;
+    T* sRed;     // team reductions / broadcasts (TW > 1)
+    int bar_id;  // named barrier of this team (TW > 1)
+
+    // ---- team primitives: plain warp operations for TW = 1 ----
+    __device__ __forceinline__ void tsync() const {
+        if constexpr (TW == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(TW * WARP) : "memory");
+    }
+    template <typename Op>
+    __device__ __forceinline__ T treduce(T v, Op op) const {
+        if constexpr (TW > 1) {
+            tsync();                                  // the previous reduction has been read by everybody
+            if ((lane & (WARP - 1)) == 0) sRed[lane / WARP] = v;
+            tsync();
+            v = sRed[0];
+#pragma unroll
+            for (int w = 1; w < TW; ++w) v = op(v, sRed[w]);
+        }
+        return v;
+    }
+    __device__ __forceinline__ T tsum(T v) const { return treduce(warp_sum(v), [](T a, T b) { return a + b; }); }
+    __device__ __forceinline__ T tmax(T v) const { return treduce(warp_max(v), [](T a, T b) { return max(a, b); }); }
+    __device__ __forceinline__ T tmin(T v) const { return treduce(warp_min(v), [](T a, T b) { return min(a, b); }); }
     int nan_reason = 0;  // where a solve first went non-finite: 1 factorisation, 2 step, 4 complementarity, 5 step size, 3 iterate
     // phase cycle counters (profile mode, option stop_after = 9): linearise, factor pass, forward predictor, corrector
     // passes, line search; and inside the factor pass: gradient, matrix build, dynamics terms, factorisation
@@ -330,7 +360,7 @@ struct Solver {
     // Staging of the side records: the records of the stage a pass visits NEXT are copied into shared memory
     // with cp.async while the current stage computes; readers take them from `recs(k)` ([2r] = {t, lam},
     // [2r+1] = {dt, dlam}).  Writers always store to the workspace.
-    static constexpr bool kStageTT = D::kStatic && D::nrow <= UB_STAGE_ROWS_MAX;
+    static constexpr bool kStageTT = TW == 1 && D::kStatic && D::nrow <= UB_STAGE_ROWS_MAX;
     __device__ __forceinline__ const Quad* recs(int k) const {
         if constexpr (kStageTT) return reinterpret_cast<const Quad*>(sTT);
         else return reinterpret_cast<const Quad*>(ws + oTT()) + k * NROW() * 2;
@@ -342,7 +372,7 @@ struct Solver {
     template <int NYOUNGER>
     __device__ __forceinline__ void cp_wait() const {
         asm volatile("cp.async.wait_group %0;" ::"n"(NYOUNGER) : "memory");
-        __syncwarp();
+        tsync();
     }
     // issue (no commit) the copy of the records of stage k; k outside [0, N] issues nothing
     __device__ __forceinline__ void tt_issue(int k) const {
@@ -351,7 +381,7 @@ struct Solver {
             constexpr int CH = NROW_STATIC * 8 * int(sizeof(T)) / 16;
             const char* src = reinterpret_cast<const char*>(ws + oTT() + k * NROW() * 8);
             char* dst = reinterpret_cast<char*>(sTT);
-            for (int i = lane; i < CH; i += WARP) cp_async16(dst + 16 * i, src + 16 * i);
+            for (int i = lane; i < CH; i += kTS) cp_async16(dst + 16 * i, src + 16 * i);
         }
     }
     static constexpr int NROW_STATIC = D::nrow;
@@ -366,7 +396,7 @@ struct Solver {
     __device__ __forceinline__ const T* st_jp(int k) const { if constexpr (kStageTT) return sSm + kSmJ; else return ws + oLJP() + k * 3 * NQ(); }
     __device__ __forceinline__ const T* st_w(int k) const { if constexpr (kStageTT) return sSm + kSmW; else return ws + oWF() + k * NU(); }
     __device__ __forceinline__ void cp_async_elems(T* dst, const T* src, int n) const {
-        for (int i = lane; i < n; i += WARP) {
+        for (int i = lane; i < n; i += kTS) {
             if constexpr (sizeof(T) == 4)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst + i)), "l"(src + i) : "memory");
             else
@@ -411,9 +441,9 @@ struct Solver {
     __device__ void build_Df() {
         const T scale = rsqrt(T(6 * NB()));
         T* Df = ws + oDF();
-        for (int idx = lane; idx < NEQ() * NFC(); idx += WARP) Df[idx] = T(0);
-        __syncwarp();
-        for (int j = lane; j < NFC(); j += WARP) {
+        for (int idx = lane; idx < NEQ() * NFC(); idx += kTS) Df[idx] = T(0);
+        tsync();
+        for (int j = lane; j < NFC(); j += kTS) {
             const int c = j / NF(), comp = j % NF();
             V3<T> e;
             if (NF() == 1) e = ld3(P.cn[c]);
@@ -442,7 +472,7 @@ struct Solver {
                 Df[(6 * b2 + 5) * NFC() + j] = s * tq.z;
             }
         }
-        __syncwarp();
+        tsync();
     }
 
     // Linearise every knot around (X, U): lane j carries d/dx_j.
@@ -480,7 +510,7 @@ struct Solver {
 #pragma unroll
                         for (int i = 0; i < 6; ++i) R[i * NZ()] = dg6[i];
                     }
-                    for (int idx = lane; idx < 6 * nu; idx += WARP) {
+                    for (int idx = lane; idx < 6 * nu; idx += kTS) {
                         const int i = idx / nu, j = idx % nu;
                         ws[oLCT() + (k * NEQ() + 6 * b + i) * NZ() + j] = (j >= nq) ? ws[oDF() + (6 * b + i) * NFC() + (j - nq)] : T(0);
                     }
@@ -569,7 +599,7 @@ struct Solver {
                 gap[2 * nq + lane] = a + dt * j - xn[2 * nq + lane];
             }
         }
-        __syncwarp();
+        tsync();
     }
 
     // --------------------------------------------------- performance index
@@ -581,7 +611,7 @@ struct Solver {
         const T scale = rsqrt(T(6 * max(NB(), 1)));
         T cost = 0, dyn = 0, eq = 0, ineq = 0, max_eq = 0, min_margin = tinf<T>();
         T sph[3 * UB_MAX_SPHERES];
-        for (int k = lane; k <= N; k += WARP) {
+        for (int k = lane; k <= N; k += kTS) {
             const T* x = Xt + k * nx;
             Kin<T> Kn;
             KinTan<T> Dn;
@@ -703,12 +733,12 @@ struct Solver {
             }
         }
         Perf<T> pf;
-        pf.cost = warp_sum(cost);
-        pf.dyn = warp_sum(dyn);
-        pf.eq = warp_sum(eq);
-        pf.ineq = warp_sum(ineq);
-        pf.max_eq = warp_max(max_eq);
-        pf.min_margin = warp_min(min_margin);
+        pf.cost = tsum(cost);
+        pf.dyn = tsum(dyn);
+        pf.eq = tsum(eq);
+        pf.ineq = tsum(ineq);
+        pf.max_eq = tmax(max_eq);
+        pf.min_margin = tmin(min_margin);
         return pf;
     }
 
@@ -720,17 +750,17 @@ struct Solver {
         const int nq = NQ(), nx = NX(), nu = NU(), nz = NZ();
         if (k < NN()) {
             const T* __restrict__ R = ws + oLCT() + k * NEQ() * nz;
-            for (int idx = lane; idx < NEQ() * nz; idx += WARP) sSA[idx] = R[idx];
+            for (int idx = lane; idx < NEQ() * nz; idx += kTS) sSA[idx] = R[idx];
         } else {
             // terminal equality [r_d - r; v; a] = 0: three dense rows over q, the rest are unit rows
-            for (int idx = lane; idx < 3 * nz; idx += WARP) {
+            for (int idx = lane; idx < 3 * nz; idx += kTS) {
                 const int i = idx / nz, j = idx % nz;
                 T v = T(0);
                 if (j >= nu && j < nu + nq) v = -ws[oLJP() + (k * 3 + i) * nq + (j - nu)];
                 sSA[idx] = v;
             }
         }
-        __syncwarp();
+        tsync();
     }
     // constant (value at z = 0) of equality row i of stage k
     __device__ __forceinline__ T eq_const(int k, int i) const {
@@ -756,7 +786,7 @@ struct Solver {
             const int ne = neq_of(k);
             if (ne == 0) continue;
             load_eq_rows(k);
-            for (int i = lane; i < ne; i += WARP) {
+            for (int i = lane; i < ne; i += kTS) {
                 T rho = C.Z;
                 if (!C.soft_poly) {
                     T n2 = T(1);
@@ -769,7 +799,7 @@ struct Solver {
                 rho_eq(k)[i] = rho;
                 y_eq(k)[i] = T(0);
             }
-            __syncwarp();
+            tsync();
         }
     }
 
@@ -790,7 +820,7 @@ struct Solver {
             // P_ab(ii, jj) are loaded once and feed all ten block pairs (I >= J); zero entries of T3 drop out at
             // compile time (52 products per position).
 #pragma unroll 1
-            for (int e = lane; e < D::nq * D::nq; e += WARP) {
+            for (int e = lane; e < D::nq * D::nq; e += kTS) {
                 const int ii = e / D::nq, jj = e % D::nq;
                 T pab[3][3];
 #pragma unroll
@@ -820,12 +850,12 @@ struct Solver {
             }
             if constexpr (ASSIGN && D::nfc > 0) {
                 // force rows (all columns up to the diagonal) and force columns of the state rows
-                for (int idx = lane; idx < D::nfc * D::nu; idx += WARP) sM[(D::nq + idx / D::nu) * ld + idx % D::nu] = T(0);
-                for (int idx = lane; idx < D::nx * D::nfc; idx += WARP) sM[(D::nu + idx / D::nfc) * ld + D::nq + idx % D::nfc] = T(0);
+                for (int idx = lane; idx < D::nfc * D::nu; idx += kTS) sM[(D::nq + idx / D::nu) * ld + idx % D::nu] = T(0);
+                for (int idx = lane; idx < D::nx * D::nfc; idx += kTS) sM[(D::nu + idx / D::nfc) * ld + D::nq + idx % D::nfc] = T(0);
             }
         } else {
             const int nb4 = 4 * nq;
-            for (int idx = lane; idx < nb4 * nb4; idx += WARP) {
+            for (int idx = lane; idx < nb4 * nb4; idx += kTS) {
                 const int bi = idx / nb4, bj = idx % nb4;
                 if (bj > bi) continue;
                 const int I = bi / nq, ii = bi % nq, J = bj / nq, jj = bj % nq;
@@ -844,7 +874,7 @@ struct Solver {
                 sM[mi * ld + mj] += acc;
             }
         }
-        __syncwarp();
+        tsync();
     }
     // vec (stage layout) += [B A]' pv
     __device__ void add_dynamics_gradient(T* vec) const {
@@ -857,7 +887,7 @@ struct Solver {
             vec[nu + nq + lane] += dt * p0 + p1;
             vec[nu + 2 * nq + lane] += T(0.5) * dt * dt * p0 + dt * p1 + p2;
         }
-        __syncwarp();
+        tsync();
     }
 
     // Build the Newton matrix of stage k in sM (lower triangle): cost Hessian +
@@ -867,37 +897,37 @@ struct Solver {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ld = LDM();
         const T dt = C.dt;
         if (!initialised) {
-            for (int idx = lane; idx < nz * ld; idx += WARP) sM[idx] = T(0);
-            __syncwarp();
+            for (int idx = lane; idx < nz * ld; idx += kTS) sM[idx] = T(0);
+            tsync();
         }
         if (k < NN()) {
             // cost (quadratic_joint_state_input_cost.h:9-33, end_effector_cost.h:48-84), scaled by dt
-            for (int i = lane; i < nz; i += WARP) {
+            for (int i = lane; i < nz; i += kTS) {
                 T d;
                 if (i < nq) d = dt * P.Rd[i] + C.reg_input;
                 else if (i < nu) d = dt * C.fw + C.reg_input;
                 else d = dt * P.Qd[i - nu];
                 sM[i * ld + i] += d;
             }
-            __syncwarp();
+            tsync();
             const T* Jp = st_jp(k);
-            for (int idx = lane; idx < nq * nq; idx += WARP) {
+            for (int idx = lane; idx < nq * nq; idx += kTS) {
                 const int a = idx / nq, b = idx % nq;
                 if (b > a) continue;
                 T acc = 0;
                 for (int c = 0; c < 3; ++c) acc += C.Wd[c] * Jp[c * nq + a] * Jp[c * nq + b];
                 sM[(nu + a) * ld + nu + b] += dt * acc;
             }
-            __syncwarp();
+            tsync();
             if (IALIGN()) {   // Gauss-Newton Hessian w Je' Je of the inertial-alignment cost (dense over x)
                 const T* Ja = ws + oLJA() + 2 * k * nx;
                 const T wa = dt * P.ia_w;
-                for (int idx = lane; idx < nx * nx; idx += WARP) {
+                for (int idx = lane; idx < nx * nx; idx += kTS) {
                     const int a = idx / nx, b = idx % nx;
                     if (b > a) continue;
                     sM[(nu + a) * ld + nu + b] += wa * (Ja[a] * Ja[b] + Ja[nx + a] * Ja[nx + b]);
                 }
-                __syncwarp();
+                tsync();
             }
         }
         // equality rows: rho a a'
@@ -910,7 +940,7 @@ struct Solver {
             const int span = nz - j0;
             if (D::kStatic && D::neq <= 8 && k < NN()) {
                 constexpr int NE = D::kStatic ? (D::neq > 0 ? D::neq : 1) : 1;
-                for (int c = j0 + lane; c < nz; c += WARP) {
+                for (int c = j0 + lane; c < nz; c += kTS) {
                     T ac[NE];
 #pragma unroll
                     for (int r = 0; r < NE; ++r) ac[r] = rho[r] * sSA[r * nz + c];
@@ -922,7 +952,7 @@ struct Solver {
                     }
                 }
             } else {
-                for (int idx = lane; idx < span * span; idx += WARP) {
+                for (int idx = lane; idx < span * span; idx += kTS) {
                     const int i = j0 + idx / span, j = j0 + idx % span;
                     if (j > i) continue;
                     T acc = 0;
@@ -931,17 +961,17 @@ struct Solver {
                 }
             }
             if (k == NN()) {
-                __syncwarp();   // the dense-row loop above adds (zeros) to the same diagonal entries
-                for (int i = 3 + lane; i < ne; i += WARP) {
+                tsync();   // the dense-row loop above adds (zeros) to the same diagonal entries
+                for (int i = 3 + lane; i < ne; i += kTS) {
                     const int m = nu + nq + (i - 3);
                     sM[m * ld + m] += rho[i];
                 }
             }
-            __syncwarp();
+            tsync();
         }
         // inequality sides: w a a', w = lam / (t + eps lam)
         const int nbx = NBOXU() + NX();
-        for (int r = lane; r < nbx; r += WARP) {
+        for (int r = lane; r < nbx; r += kTS) {
             const int fam = r < NBOXU() ? 0 : 1;
             if (!row_valid(k, fam)) continue;
             const T eps = row_eps(fam);
@@ -950,11 +980,11 @@ struct Solver {
             const int m = fam == 0 ? r : nu + (r - NBOXU());
             sM[m * ld + m] += w;
         }
-        __syncwarp();
+        tsync();
         if (NFRIC() > 0 && k < NN()) {
             const T eps = row_eps(2);
             // one lane per contact: its five pyramid rows give a symmetric 3x3 block
-            for (int c = lane; c < NC(); c += WARP) {
+            for (int c = lane; c < NC(); c += kTS) {
                 T blk[6] = {0, 0, 0, 0, 0, 0};
                 for (int which = 0; which < 5; ++which) {
                     const Quad q = recs(k)[2 * (nbx + 5 * c + which)];
@@ -975,18 +1005,18 @@ struct Solver {
                 Mb[2 * ld + 1] += blk[4];
                 Mb[2 * ld + 2] += blk[5];
             }
-            __syncwarp();
+            tsync();
         }
         if (NOBS() > 0 && k >= 1 && k < NN()) {
             const T eps = row_eps(3);
             T* wrow = sV + 4 * nz;  // barrier weights of the obstacle rows
-            for (int i = lane; i < NOBS(); i += WARP) {
+            for (int i = lane; i < NOBS(); i += kTS) {
                 const Quad q = recs(k)[2 * (nbx + NFRIC() + i)];
                 wrow[i] = fdiv(q.v[2], q.v[0] + eps * q.v[2]);
             }
-            __syncwarp();
+            tsync();
             const int ow = OBSW();
-            for (int idx = lane; idx < ow * ow; idx += WARP) {
+            for (int idx = lane; idx < ow * ow; idx += kTS) {
                 const int a = idx / ow, b = idx % ow;
                 if (b > a) continue;
                 T acc = 0;
@@ -996,7 +1026,7 @@ struct Solver {
                 }
                 sM[(nu + a) * ld + nu + b] += acc;
             }
-            __syncwarp();
+            tsync();
         }
     }
 
@@ -1011,10 +1041,10 @@ struct Solver {
             if (d != d) ok = false;
             if (!(d > C.reg_input)) d = C.reg_input;   // see stage_factor_blocked
             const T inv = rsqrt(d);
-            for (int i = j + 1 + lane; i < n; i += WARP) sM[i * ld + j] *= inv;
-            __syncwarp();
+            for (int i = j + 1 + lane; i < n; i += kTS) sM[i * ld + j] *= inv;
+            tsync();
             if (lane == 0) sM[j * ld + j] = inv;
-            for (int l = j + 1 + lane; l < n; l += WARP) {
+            for (int l = j + 1 + lane; l < n; l += kTS) {
                 const T mlj = sM[l * ld + j];
                 T* __restrict__ dst = sM + l * ld + l;         // column l, rows l..n-1
                 const T* __restrict__ src = sM + l * ld + j;   // column j, rows l..n-1
@@ -1035,7 +1065,7 @@ struct Solver {
                     dst += ld;
                 }
             }
-            __syncwarp();
+            tsync();
         }
         return ok;
     }
@@ -1053,14 +1083,14 @@ struct Solver {
     template <int NU_, int NX_>
     __device__ bool stage_factor_blocked(T* vec, T* Fg) {
         constexpr int NZ_ = NU_ + NX_, AUG = NZ_;
-        constexpr int R = (NZ_ + 1 + WARP - 1) / WARP;
+        constexpr int R = (NZ_ + 1 + kTS - 1) / kTS;
         constexpr int TR = (NX_ + 7) / 8, TC = (NX_ + 1 + 3) / 4;
         static_assert(NU_ <= 16 && R <= 2 && 4 * TC > NX_, "blocked factorisation is for small stage matrices");
         const int ld = LDM();
         T row[R][NU_];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int i = lane + WARP * r;
+            const int i = lane + kTS * r;
             const T* src = (i == AUG) ? vec : sM + min(i, NZ_ - 1) * ld;
 #pragma unroll
             for (int c = 0; c < NU_; ++c) row[r][c] = src[c];
@@ -1078,7 +1108,7 @@ struct Solver {
             T lij[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int i = lane + WARP * r;
+                const int i = lane + kTS * r;
                 lij[r] = (i > j) ? row[r][j] * inv : T(0);
             }
 #pragma unroll
@@ -1089,14 +1119,14 @@ struct Solver {
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int i = lane + WARP * r;
+                const int i = lane + kTS * r;
                 row[r][j] = (i > j) ? lij[r] : (i == j ? inv : T(0));
             }
         }
-        __syncwarp();   // lanes beyond the last row read a clamped (real) row above
+        tsync();   // lanes beyond the last row read a clamped (real) row above
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const int i = lane + WARP * r;
+            const int i = lane + kTS * r;
             if (i < NZ_) {
 #pragma unroll
                 for (int c = 0; c < NU_; ++c) {
@@ -1108,7 +1138,7 @@ struct Solver {
                 for (int c = 0; c < NU_; ++c) vec[c] = row[r][c];  // w = L^{-1} m_u
             }
         }
-        __syncwarp();
+        tsync();
         // Schur complement tile of lane (a, b): rows a*TR.., columns b*TC.. of the state block; column NX_ = p
         const int a = lane >> 2, b = lane & 3;
         int ri[TR];
@@ -1147,7 +1177,7 @@ struct Solver {
                 if (i < NX_ && c < NX_) sP[i * NX_ + c] = acc[ii][cc];
                 else if (i < NX_ && c == NX_) sPv[i] = acc[ii][cc];
             }
-        __syncwarp();
+        tsync();
         return ok;
     }
 
@@ -1161,11 +1191,11 @@ struct Solver {
     // cost-to-go Hessian = trailing block of sM, expanded to the full symmetric matrix
     __device__ __forceinline__ void copy_cost_to_go() {
         const int nu = NU(), nx = NX(), ld = LDM();
-        for (int idx = lane; idx < nx * nx; idx += WARP) {
+        for (int idx = lane; idx < nx * nx; idx += kTS) {
             const int i = idx / nx, j = idx % nx;
             sP[idx] = (j <= i) ? sM[(nu + i) * ld + nu + j] : sM[(nu + j) * ld + nu + i];
         }
-        __syncwarp();
+        tsync();
     }
 
     // Stage gradient of the barrier/proximal Lagrangian at the current iterate:
@@ -1187,7 +1217,7 @@ struct Solver {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const T part = lane < nq ? Jp[c * nq + lane] * zk[nu + lane] : T(0);
-                e3[c] = warp_sum(part) + ws[oLR() + 3 * k + c] - target[3 * k + c];
+                e3[c] = tsum(part) + ws[oLR() + 3 * k + c] - target[3 * k + c];
             }
             // inertial-alignment residual at the QP iterate: e + Je dx
             T ea[2] = {T(0), T(0)};
@@ -1196,11 +1226,11 @@ struct Solver {
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     T part = T(0);
-                    for (int j = lane; j < nx; j += WARP) part += Ja[r * nx + j] * zk[nu + j];
-                    ea[r] = warp_sum(part) + ws[oLIA() + 2 * k + r];
+                    for (int j = lane; j < nx; j += kTS) part += Ja[r * nx + j] * zk[nu + j];
+                    ea[r] = tsum(part) + ws[oLIA() + 2 * k + r];
                 }
             }
-            for (int i = lane; i < nz; i += WARP) {
+            for (int i = lane; i < nz; i += kTS) {
                 T g;
                 if (i < nq) g = dt * P.Rd[i] * (u[i] + zk[i]) + C.reg_input * zk[i];
                 else if (i < nu) g = dt * C.fw * (u[i] + zk[i]) + C.reg_input * zk[i];
@@ -1213,11 +1243,11 @@ struct Solver {
                 vec[i] = g;
             }
         } else {
-            for (int i = lane; i < nz; i += WARP) vec[i] = T(0);
+            for (int i = lane; i < nz; i += kTS) vec[i] = T(0);
         }
-        __syncwarp();
+        tsync();
         // box rows: one entry each
-        for (int r = lane; r < NBOXU() + nx; r += WARP) {
+        for (int r = lane; r < NBOXU() + nx; r += kTS) {
             const int fam = r < NBOXU() ? 0 : 1;
             if (!row_valid(k, fam)) continue;
             const int m = fam == 0 ? r : nu + (r - NBOXU());
@@ -1242,7 +1272,7 @@ struct Solver {
             const T c1 = side_coef(q.v[1], q.v[3], ub - val, eps, mu_target, cm * dd.v[1] * dd.v[3]);
             vec[m] += c0 - c1;
         }
-        __syncwarp();
+        tsync();
         // equality rows
         const int ne = neq_of(k);
         if (ne > 0) {
@@ -1255,30 +1285,30 @@ struct Solver {
                 // few dense rows: every row value as a warp-wide dot product
                 for (int i = 0; i < nd; ++i) {
                     T part = T(0);
-                    for (int j = nq + lane; j < nz; j += WARP) part += sSA[i * nz + j] * zk[j];
-                    const T e = warp_sum(part) + eq_const(k, i);
+                    for (int j = nq + lane; j < nz; j += kTS) part += sSA[i * nz + j] * zk[j];
+                    const T e = tsum(part) + eq_const(k, i);
                     if (lane == 0) mrow[i] = rho[i] * e + y[i];
                 }
             } else {
-                for (int i = lane; i < ne; i += WARP) {
+                for (int i = lane; i < ne; i += kTS) {
                     const T m = rho[i] * eq_value(k, i, zk) + y[i];
                     if (i < nd) mrow[i] = m;
                     else vec[nu + nq + (i - 3)] += m;  // terminal unit rows (distinct entries)
                 }
             }
-            __syncwarp();
-            for (int j = lane; j < nz; j += WARP) {
+            tsync();
+            for (int j = lane; j < nz; j += kTS) {
                 T acc = 0;
                 for (int i = 0; i < nd; ++i) acc += mrow[i] * sSA[i * nz + j];
                 vec[j] += acc;
             }
-            __syncwarp();
+            tsync();
         }
         const int nbx = NBOXU() + nx;
         if (NFRIC() > 0 && k < NN()) {
             // one lane per contact: five pyramid rows -> three force entries
             const T eps = row_eps(2);
-            for (int c = lane; c < NC(); c += WARP) {
+            for (int c = lane; c < NC(); c += kTS) {
                 const T* f = st_u(k) + nq + 3 * c;
                 const T* df = zk + nq + 3 * c;
                 const T f0 = f[0] + df[0], f1 = f[1] + df[1], f2 = f[2] + df[2];
@@ -1302,12 +1332,12 @@ struct Solver {
                 vec[nq + 3 * c + 1] += g1;
                 vec[nq + 3 * c + 2] += g2;
             }
-            __syncwarp();
+            tsync();
         }
         if (NOBS() > 0 && k >= 1 && k < NN()) {
             const T eps = row_eps(3);
             T* crow = sV + 4 * nz;
-            for (int i = lane; i < NOBS(); i += WARP) {
+            for (int i = lane; i < NOBS(); i += kTS) {
                 const int r = nbx + NFRIC() + i;
                 const T* J = ws + oLJO() + (k * NOBS() + i) * OBSW();
                 T val = ws[oLHO() + k * NOBS() + i];
@@ -1320,13 +1350,13 @@ struct Solver {
                 }
                 crow[i] = side_coef(q.v[0], q.v[2], val, eps, mu_target, corr);
             }
-            __syncwarp();
+            tsync();
             if (lane < OBSW()) {
                 T acc = 0;
                 for (int i = 0; i < NOBS(); ++i) acc += crow[i] * ws[oLJO() + (k * NOBS() + i) * OBSW() + lane];
                 vec[nu + lane] += acc;
             }
-            __syncwarp();
+            tsync();
         }
     }
 
@@ -1343,7 +1373,7 @@ struct Solver {
         constexpr int V = 16 / sizeof(T);
         const T* src = ws + oFAC() + k * FSTRIDE();
         T* dst = sM + buf * FSTRIDE();
-        for (int i = lane; i < FSTRIDE() / V; i += WARP) cp_async16(dst + i * V, src + i * V);
+        for (int i = lane; i < FSTRIDE() / V; i += kTS) cp_async16(dst + i * V, src + i * V);
     }
     // equality rows of stage k (k < N) straight into sSA
     static constexpr bool kStageEQ = kStageTT && D::neq > 0 && (D::neq * D::nz) % 4 == 0;
@@ -1352,7 +1382,7 @@ struct Solver {
             if (k < 0 || k >= NN()) return;
             constexpr int V = 16 / sizeof(T);
             const T* src = ws + oLCT() + k * NEQ() * NZ();
-            for (int i = lane; i < NEQ() * NZ() / V; i += WARP) cp_async16(sSA + i * V, src + i * V);
+            for (int i = lane; i < NEQ() * NZ() / V; i += kTS) cp_async16(sSA + i * V, src + i * V);
         }
     }
     // 16-byte vectorised copy global -> shared (both 16-byte aligned; n in elements)
@@ -1361,8 +1391,8 @@ struct Solver {
         const int nv = n / V;
         const int4* s4 = reinterpret_cast<const int4*>(src);
         int4* d4 = reinterpret_cast<int4*>(dst);
-        for (int i = lane; i < nv; i += WARP) d4[i] = s4[i];
-        for (int i = nv * V + lane; i < n; i += WARP) dst[i] = src[i];
+        for (int i = lane; i < nv; i += kTS) d4[i] = s4[i];
+        for (int i = nv * V + lane; i < n; i += kTS) dst[i] = src[i];
     }
 
     // ---------------------------------------------------------------- fused IPM passes
@@ -1373,8 +1403,8 @@ struct Solver {
         const int nu = NU(), nx = NX(), nz = NZ(), ld = LDM(), ldf = LDF();
         T* vec = sV;
         bool ok = true;
-        for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
-        __syncwarp();
+        for (int i = lane; i < nx; i += kTS) sPv[i] = T(0);
+        tsync();
         if constexpr (kStageTT) {
             tt_issue(NN());
             sm_issue(NN(), false, true);
@@ -1385,18 +1415,18 @@ struct Solver {
             if constexpr (kStageTT) cp_wait<0>();           // side records (and equality rows) of stage k are staged
             stage_gradient(k, false, T(0), vec, kStageEQ && k < NN());  // equality rows of stage k in sSA afterwards
             T* GPk = ws + oLAM() + k * nz;
-            for (int i = lane; i < nz; i += WARP) GPk[i] = vec[i];
+            for (int i = lane; i < nz; i += kTS) GPk[i] = vec[i];
 #ifdef UB_DEBUG_NAN
             {
                 T bad = 0, badr = 0;
-                for (int i = lane; i < nz; i += WARP) bad += (vec[i] == vec[i]) ? T(0) : T(1);
-                for (int r = lane; r < NROW(); r += WARP) {
+                for (int i = lane; i < nz; i += kTS) bad += (vec[i] == vec[i]) ? T(0) : T(1);
+                for (int r = lane; r < NROW(); r += kTS) {
                     const Quad q = recs(k)[2 * r];
                     for (int c = 0; c < 4; ++c) badr += (q.v[c] == q.v[c] && fabs(q.v[c]) < T(1e30)) ? T(0) : T(1);
                     if (row_valid(k, row_family(r)) && (!(q.v[0] > T(0)) || !(q.v[2] > T(0)))) badr += T(100);
                 }
-                bad = warp_sum(bad);
-                badr = warp_sum(badr);
+                bad = tsum(bad);
+                badr = tsum(badr);
                 if (nan_reason == 0 && badr > T(0)) nan_reason = 20000 + 100 * k + int(badr > T(99));
                 if (nan_reason == 0 && bad > T(0)) nan_reason = 10000 + 100 * k;
             }
@@ -1425,27 +1455,27 @@ struct Solver {
                     // factor, forward substitution (w in vec[0, nu)), p -> sPv, P -> sP, factor block -> workspace
                     ok &= stage_factor_blocked<D::nu, D::nx>(vec, F);
                     t_f3 += clock64() - f3;
-                    for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
+                    for (int j = lane; j < nu; j += kTS) Wk[j] = vec[j];
                 } else {
                     ok &= stage_cholesky();
                     t_f3 += clock64() - f3;
                     for (int j = 0; j < nu; ++j) {  // forward substitution, column oriented
                         const T wj = vec[j] * sM[j * ld + j];
-                        __syncwarp();
+                        tsync();
                         if (lane == 0) vec[j] = wj;
-                        for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= sM[i * ld + j] * wj;
-                        __syncwarp();
+                        for (int i = j + 1 + lane; i < nu; i += kTS) vec[i] -= sM[i * ld + j] * wj;
+                        tsync();
                     }
-                    for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
+                    for (int j = lane; j < nu; j += kTS) Wk[j] = vec[j];
                     // p = m_x - Y' w
-                    for (int i = lane; i < nx; i += WARP) {
+                    for (int i = lane; i < nx; i += kTS) {
                         T acc = vec[nu + i];
                         const T* Mr = sM + (nu + i) * ld;
                         for (int j = 0; j < nu; ++j) acc -= Mr[j] * vec[j];
                         sPv[i] = acc;
                     }
                     // factor block [L; Y] -> workspace for the forward / corrector passes
-                    for (int idx = lane; idx < nz * nu; idx += WARP) {
+                    for (int idx = lane; idx < nz * nu; idx += kTS) {
                         const int i = idx / nu, j = idx % nu;
                         T v = T(0);
                         if (j <= i) v = sM[i * ld + j];
@@ -1453,10 +1483,10 @@ struct Solver {
                     }
                 }
             } else {
-                for (int i = lane; i < nx; i += WARP) sPv[i] = vec[nu + i];
+                for (int i = lane; i < nx; i += kTS) sPv[i] = vec[nu + i];
                 copy_cost_to_go();
             }
-            __syncwarp();
+            tsync();
         }
         return ok;
     }
@@ -1466,8 +1496,8 @@ struct Solver {
     __device__ void pass_backward_corrector(T target_mu) {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ(), ldf = LDF();
         T* vec = sV;
-        for (int i = lane; i < nx; i += WARP) sPv[i] = T(0);
-        __syncwarp();
+        for (int i = lane; i < nx; i += kTS) sPv[i] = T(0);
+        tsync();
         const int nbx = NBOXU() + nx;
         // cp.async group schedule: TT(k) is committed before FAC(k); every wait leaves exactly one younger group
         // in flight (none at the terminal stage)
@@ -1482,10 +1512,10 @@ struct Solver {
                 else cp_wait<1>();
             }
             const T* GPk = st_gp(k);
-            for (int i = lane; i < nz; i += WARP) vec[i] = GPk[i];
-            __syncwarp();
+            for (int i = lane; i < nz; i += kTS) vec[i] = GPk[i];
+            tsync();
             // (corr - target) / (t + eps lam) per side
-            for (int r = lane; r < nbx; r += WARP) {
+            for (int r = lane; r < nbx; r += kTS) {
                 const int fam = r < NBOXU() ? 0 : 1;
                 if (!row_valid(k, fam)) continue;
                 const int m = fam == 0 ? r : nu + (r - NBOXU());
@@ -1495,10 +1525,10 @@ struct Solver {
                 vec[m] += fdiv(dd.v[0] * dd.v[2] - target_mu, q.v[0] + eps * q.v[2]) -
                           fdiv(dd.v[1] * dd.v[3] - target_mu, q.v[1] + eps * q.v[3]);
             }
-            __syncwarp();
+            tsync();
             if (NFRIC() > 0 && k < NN()) {
                 const T eps = row_eps(2);
-                for (int c = lane; c < NC(); c += WARP) {
+                for (int c = lane; c < NC(); c += kTS) {
                     T g0 = 0, g1 = 0, g2 = 0;
                     for (int which = 0; which < 5; ++which) {
                         const int r = nbx + 5 * c + which;
@@ -1514,38 +1544,38 @@ struct Solver {
                     vec[nq + 3 * c + 1] += g1;
                     vec[nq + 3 * c + 2] += g2;
                 }
-                __syncwarp();
+                tsync();
             }
             if (NOBS() > 0 && k >= 1 && k < NN()) {
                 const T eps = row_eps(3);
                 T* crow = sV + 4 * nz;
-                for (int i = lane; i < NOBS(); i += WARP) {
+                for (int i = lane; i < NOBS(); i += kTS) {
                     const int r = nbx + NFRIC() + i;
                     const Quad q = recs(k)[2 * r];
                     const Quad dd = recs(k)[2 * r + 1];
                     crow[i] = fdiv(dd.v[0] * dd.v[2] - target_mu, q.v[0] + eps * q.v[2]);
                 }
-                __syncwarp();
+                tsync();
                 if (lane < OBSW()) {
                     T acc = 0;
                     for (int i = 0; i < NOBS(); ++i) acc += crow[i] * ws[oLJO() + (k * NOBS() + i) * OBSW() + lane];
                     vec[nu + lane] += acc;
                 }
-                __syncwarp();
+                tsync();
             }
             if constexpr (kFacDouble) {
-                __syncwarp();
+                tsync();
                 tt_issue(k - 1);
                 sm_issue(k - 1, true, false);
                 cp_commit();
             }
             if (k == NN()) {
-                for (int i = lane; i < nx; i += WARP) sPv[i] = vec[nu + i];
+                for (int i = lane; i < nx; i += kTS) sPv[i] = vec[nu + i];
                 if constexpr (kFacDouble) {
                     fac_issue(k - 1, (k - 1) & 1);
                     cp_commit();
                 }
-                __syncwarp();
+                tsync();
                 continue;
             }
             add_dynamics_gradient(vec);
@@ -1557,24 +1587,24 @@ struct Solver {
                 F = sM + (k & 1) * FSTRIDE();
             } else {
                 copy_block(sM, ws + oFAC() + k * FSTRIDE(), nz * ldf);
-                __syncwarp();
+                tsync();
             }
             T* Wk = ws + oWF() + k * nu;
             for (int j = 0; j < nu; ++j) {
                 const T wj = vec[j] * F[fidx(j, j)];
-                __syncwarp();
+                tsync();
                 if (lane == 0) vec[j] = wj;
-                for (int i = j + 1 + lane; i < nu; i += WARP) vec[i] -= F[fidx(i, j)] * wj;
-                __syncwarp();
+                for (int i = j + 1 + lane; i < nu; i += kTS) vec[i] -= F[fidx(i, j)] * wj;
+                tsync();
             }
-            for (int j = lane; j < nu; j += WARP) Wk[j] = vec[j];
+            for (int j = lane; j < nu; j += kTS) Wk[j] = vec[j];
         
-            for (int i = lane; i < nx; i += WARP) {
+            for (int i = lane; i < nx; i += kTS) {
                 T acc = vec[nu + i];
                 for (int j = 0; j < nu; ++j) acc -= F[fidx(nu + i, j)] * vec[j];
                 sPv[i] = acc;
             }
-            __syncwarp();
+            tsync();
         }
         if constexpr (kFacDouble) cp_wait<0>();
     }
@@ -1584,7 +1614,7 @@ struct Solver {
     __device__ __forceinline__ void stage_side_steps(int k, const T* d, bool corrector, T target_mu, T& amax) {
         const T* zk = st_z(k);
         const T cm = corrector ? T(1) : T(0);
-        for (int r = lane; r < NROW(); r += WARP) {
+        for (int r = lane; r < NROW(); r += kTS) {
             const int fam = row_family(r);
             if (!row_valid(k, fam)) continue;
             T lb, ub;
@@ -1622,8 +1652,8 @@ struct Solver {
         T* du = dst;
         T* dx = dst + nu;
         T amax = T(1);
-        for (int i = lane; i < nz; i += WARP) dst[i] = T(0);
-        __syncwarp();
+        for (int i = lane; i < nz; i += kTS) dst[i] = T(0);
+        tsync();
         // cp.async group schedule: FAC(k) is committed before TT(k); every wait leaves exactly one younger group
         // in flight (none for the records of the terminal stage)
         if constexpr (kFacDouble) {
@@ -1642,9 +1672,9 @@ struct Solver {
                 if constexpr (kFacDouble) {
                     cp_wait<1>();
                     if constexpr (kStageTT) {   // w_k leaves its (single) staging slot before w_{k+1} is requested
-                        static_assert(D::nu <= WARP, "one register per lane holds the staged w");
+                        static_assert(D::nu <= kTS, "one register per lane holds the staged w");
                         if (lane < nu) wreg = st_w(k)[lane];
-                        __syncwarp();
+                        tsync();
                     }
                     fac_issue(k + 1, (k + 1) & 1);
                     w_issue(k + 1);
@@ -1652,36 +1682,36 @@ struct Solver {
                     F = sM + (k & 1) * FSTRIDE();
                 } else {
                     copy_block(sM, ws + oFAC() + k * FSTRIDE(), nz * ldf);
-                    __syncwarp();
+                    tsync();
                 }
                 // s = w + Y dx
-                for (int j = lane; j < nu; j += WARP) {
+                for (int j = lane; j < nu; j += kTS) {
                     T acc = kStageTT ? wreg : Wk[j];
                     for (int i = 0; i < nx; ++i) acc += F[fidx(nu + i, j)] * dx[i];
                     du[j] = acc;
                 }
-                __syncwarp();
+                tsync();
                 for (int j = nu - 1; j >= 0; --j) {
                     const T uj = -du[j] * F[fidx(j, j)];
-                    __syncwarp();
-                    for (int i = lane; i < j; i += WARP) du[i] += F[fidx(j, i)] * uj;
+                    tsync();
+                    for (int i = lane; i < j; i += kTS) du[i] += F[fidx(j, i)] * uj;
                     if (lane == 0) du[j] = uj;
-                    __syncwarp();
+                    tsync();
                 }
             
             } else {
-                for (int j = lane; j < nu; j += WARP) du[j] = T(0);
-                __syncwarp();
+                for (int j = lane; j < nu; j += kTS) du[j] = T(0);
+                tsync();
             }
             T* Dk = DZk(k);
-            for (int i = lane; i < nz; i += WARP) Dk[i] = dst[i];
+            for (int i = lane; i < nz; i += kTS) Dk[i] = dst[i];
             if constexpr (kFacDouble) {
                 if (k == NN()) cp_wait<0>();
                 else cp_wait<1>();
             }
             stage_side_steps(k, dst, corrector, target_mu, amax);
             if constexpr (kFacDouble) {
-                __syncwarp();
+                tsync();
                 tt_issue(k + 1);
                 sm_issue(k + 1, false, false);
                 cp_commit();
@@ -1694,13 +1724,13 @@ struct Solver {
                     dxn[nq + lane] = v + dt * a + T(0.5) * dt * dt * j;
                     dxn[2 * nq + lane] = a + dt * j;
                 }
-                __syncwarp();
-                for (int i = lane; i < nx; i += WARP) dx[i] = dxn[i];
-                __syncwarp();
+                tsync();
+                for (int i = lane; i < nx; i += kTS) dx[i] = dxn[i];
+                tsync();
             }
         }
         if constexpr (kFacDouble) cp_wait<0>();
-        return warp_min(amax);
+        return tmin(amax);
     }
 
     // Interior-point QP solve around the current (X, U).  Leaves the step in Z
@@ -1711,8 +1741,8 @@ struct Solver {
         *converged = false;
         *finite = true;
         // dynamics-feasible start: du = 0, dx_0 = 0, dx_{k+1} = A dx_k + gap_k
-        for (int idx = lane; idx < (N + 1) * nz; idx += WARP) ws[oZ() + idx] = T(0);
-        __syncwarp();
+        for (int idx = lane; idx < (N + 1) * nz; idx += kTS) ws[oZ() + idx] = T(0);
+        tsync();
         if (lane < nq) {
             const T dt = C.dt;
             T q = 0, v = 0, a = 0;
@@ -1728,13 +1758,13 @@ struct Solver {
                 zn[nu + 2 * nq + lane] = a;
             }
         }
-        __syncwarp();
+        tsync();
         init_eq_weights();
         // slack / multiplier initialisation
         int nsides_l = 0;
         for (int k = 0; k <= N; ++k) {
             const T* zk = Zk(k);
-            for (int r = lane; r < NROW(); r += WARP) {
+            for (int r = lane; r < NROW(); r += kTS) {
                 const int fam = row_family(r);
                 Quad q, dd;
                 q.v[0] = q.v[1] = T(1);
@@ -1756,8 +1786,8 @@ struct Solver {
                 *side_dd(k, r) = dd;
             }
         }
-        const int nsides = __reduce_add_sync(FULL, nsides_l);
-        __syncwarp();
+        const int nsides = int(tsum(T(nsides_l)) + T(0.5));
+        tsync();
         T last_alpha = T(0), last_step = tinf<T>();
         int iters = 0;
         // initial residual summary (afterwards mu comes from the update pass and the slack residual
@@ -1765,7 +1795,7 @@ struct Solver {
         T mu = 0, rdmax = 0;
         for (int k = 0; k <= N; ++k) {
             const T* zk = Zk(k);
-            for (int r = lane; r < NROW(); r += WARP) {
+            for (int r = lane; r < NROW(); r += kTS) {
                 const int fam = row_family(r);
                 if (!row_valid(k, fam)) continue;
                 T lb, ub;
@@ -1780,8 +1810,8 @@ struct Solver {
                 }
             }
         }
-        mu = nsides > 0 ? warp_sum(mu) / T(nsides) : T(0);
-        rdmax = warp_max(rdmax);
+        mu = nsides > 0 ? tsum(mu) / T(nsides) : T(0);
+        rdmax = tmax(rdmax);
         T pinf = T(0);
         auto eq_infeasibility = [&]() {
             T pv = T(0);
@@ -1790,11 +1820,11 @@ struct Solver {
                     if (neq_of(k) == 0) continue;
                     load_eq_rows(k);
                     const T* zk = Zk(k);
-                    for (int i = lane; i < neq_of(k); i += WARP)
+                    for (int i = lane; i < neq_of(k); i += kTS)
                         if (rho_eq(k)[i] > T(0)) pv = max(pv, fabs(eq_value(k, i, zk)));
-                    __syncwarp();
+                    tsync();
                 }
-            return warp_max(pv);
+            return tmax(pv);
         };
         pinf = eq_infeasibility();
         for (int it = 0; it < C.qp_iter_max; ++it) {
@@ -1821,7 +1851,7 @@ struct Solver {
                     // mean complementarity after the affine step -> centring target (Mehrotra)
                     const T a_aff = a_fwd;
                     T acc = 0;
-                    for (int idx = lane; idx < (N + 1) * NROW(); idx += WARP) {
+                    for (int idx = lane; idx < (N + 1) * NROW(); idx += kTS) {
                         const int k = idx / NROW(), r = idx % NROW();
                         const int fam = row_family(r);
                         if (!row_valid(k, fam)) continue;
@@ -1830,7 +1860,7 @@ struct Solver {
                         acc += (q.v[0] + a_aff * dd.v[0]) * (q.v[2] + a_aff * dd.v[2]);
                         if (fam < 2) acc += (q.v[1] + a_aff * dd.v[1]) * (q.v[3] + a_aff * dd.v[3]);
                     }
-                    const T mu_aff = warp_sum(acc) / T(nsides);
+                    const T mu_aff = tsum(acc) / T(nsides);
                     const T ratio = mu_aff / mu;
                     target_mu = max(ratio * ratio * ratio * mu, C.mu_target);
                     long long c3 = clock64();
@@ -1844,12 +1874,12 @@ struct Solver {
             t_side += clock64() - c2;
             // update z, t, lambda; new mean complementarity
             T stepmax = 0, musum = 0;
-            for (int idx = lane; idx < (N + 1) * nz; idx += WARP) {
+            for (int idx = lane; idx < (N + 1) * nz; idx += kTS) {
                 const T d = ws[oDZ() + idx];
                 ws[oZ() + idx] += alpha * d;
                 stepmax = max(stepmax, fabs(alpha * d));
             }
-            for (int idx = lane; idx < (N + 1) * NROW(); idx += WARP) {
+            for (int idx = lane; idx < (N + 1) * NROW(); idx += kTS) {
                 const int k = idx / NROW(), r = idx % NROW();
                 const int fam = row_family(r);
                 Quad* rec = reinterpret_cast<Quad*>(ws + oTT()) + 2 * idx;
@@ -1863,8 +1893,8 @@ struct Solver {
                     if (fam < 2) musum += q.v[1] * q.v[3];
                 }
             }
-            __syncwarp();
-            mu = nsides > 0 ? warp_sum(musum) / T(nsides) : T(0);
+            tsync();
+            mu = nsides > 0 ? tsum(musum) / T(nsides) : T(0);
             rdmax *= (T(1) - alpha);
             if (!C.soft_poly) {
                 // multiplier update of the hard equality rows and their infeasibility at the new iterate, one visit
@@ -1873,7 +1903,7 @@ struct Solver {
                     if (neq_of(k) == 0) continue;
                     load_eq_rows(k);
                     const T* zk = Zk(k);
-                    for (int i = lane; i < neq_of(k); i += WARP) {
+                    for (int i = lane; i < neq_of(k); i += kTS) {
                         const T rho = rho_eq(k)[i];
                         if (rho > T(0)) {
                             const T e = eq_value(k, i, zk);
@@ -1881,12 +1911,12 @@ struct Solver {
                             pv = max(pv, fabs(e));
                         }
                     }
-                    __syncwarp();
+                    tsync();
                 }
-                pinf = warp_max(pv);
+                pinf = tmax(pv);
             }
             last_alpha = alpha;
-            last_step = warp_max(stepmax);
+            last_step = tmax(stepmax);
             if (!(last_step < tinf<T>())) {
                 *finite = false;
                 if (nan_reason == 0) nan_reason = !(mu < tinf<T>()) ? 4 : (!(alpha <= T(1)) ? 5 : 2);
@@ -1904,21 +1934,21 @@ struct Solver {
         T* col = sV;
         for (int k = 0; k < stages; ++k) {
             const T* Fg = ws + oFAC() + k * FSTRIDE();
-            for (int idx = lane; idx < FSTRIDE(); idx += WARP) F[idx] = Fg[idx];
-            __syncwarp();
+            for (int idx = lane; idx < FSTRIDE(); idx += kTS) F[idx] = Fg[idx];
+            tsync();
             for (int xcol = 0; xcol < nx; ++xcol) {
-                for (int j = lane; j < nu; j += WARP) col[j] = F[fidx(nu + xcol, j)];
-                __syncwarp();
+                for (int j = lane; j < nu; j += kTS) col[j] = F[fidx(nu + xcol, j)];
+                tsync();
                 for (int j = nu - 1; j >= 0; --j) {
                     const T uj = -col[j] * F[fidx(j, j)];
-                    __syncwarp();
-                    for (int i = lane; i < j; i += WARP) col[i] += F[fidx(j, i)] * uj;
+                    tsync();
+                    for (int i = lane; i < j; i += kTS) col[i] += F[fidx(j, i)] * uj;
                     if (lane == 0) col[j] = uj;
-                    __syncwarp();
+                    tsync();
                 }
             
-                for (int j = lane; j < nu; j += WARP) Kout[(k * nu + j) * nx + xcol] = col[j];
-                __syncwarp();
+                for (int j = lane; j < nu; j += kTS) Kout[(k * nu + j) * nx + xcol] = col[j];
+                tsync();
             }
         }
     }
@@ -1935,30 +1965,30 @@ struct Solver {
             const T* x0 = A.x0 + size_t(b) * nxt;
             T* XOw = ws + oXO();
             if (!A.warm) {
-                for (int idx = lane; idx < (N + 1) * nx; idx += WARP) X[idx] = x0[idx % nx];
-                for (int idx = lane; idx < N * nu; idx += WARP) U[idx] = T(0);
-                for (int idx = lane; idx < (N + 1) * nxo; idx += WARP) XOw[idx] = x0[nx + idx % nxo];   // state held
+                for (int idx = lane; idx < (N + 1) * nx; idx += kTS) X[idx] = x0[idx % nx];
+                for (int idx = lane; idx < N * nu; idx += kTS) U[idx] = T(0);
+                for (int idx = lane; idx < (N + 1) * nxo; idx += kTS) XOw[idx] = x0[nx + idx % nxo];   // state held
             } else {
                 const T* Xin = A.Xin + size_t(b) * (N + 1) * nxt;
                 const T* Uin = A.Uin + size_t(b) * N * nu;
-                for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
+                for (int idx = lane; idx < (N + 1) * nx; idx += kTS) {
                     const int k = idx / nx, i = idx % nx;
                     X[idx] = k == 0 ? x0[i] : Xin[k * nxt + i];
                 }
-                for (int idx = lane; idx < N * nu; idx += WARP) U[idx] = Uin[idx];
-                for (int idx = lane; idx < (N + 1) * nxo; idx += WARP) {
+                for (int idx = lane; idx < N * nu; idx += kTS) U[idx] = Uin[idx];
+                for (int idx = lane; idx < (N + 1) * nxo; idx += kTS) {
                     const int k = idx / nxo, i = idx % nxo;
                     XOw[idx] = k == 0 ? x0[nx + i] : Xin[k * nxt + nx + i];
                 }
             }
             const T* tg = A.target + size_t(b) * (N + 1) * 3;
             T* tgl = ws + oTG();
-            for (int idx = lane; idx < (N + 1) * 3; idx += WARP) tgl[idx] = tg[idx];
+            for (int idx = lane; idx < (N + 1) * 3; idx += kTS) tgl[idx] = tg[idx];
             const T* bd = A.body ? A.body + size_t(b) * NB() * UB_BODY_PARAMS : &P.body[0][0];
             T* bdl = ws + oBD();
-            for (int idx = lane; idx < NB() * UB_BODY_PARAMS; idx += WARP) bdl[idx] = bd[idx];
+            for (int idx = lane; idx < NB() * UB_BODY_PARAMS; idx += kTS) bdl[idx] = bd[idx];
         }
-        __syncwarp();
+        tsync();
         if (NEQ() > 0) build_Df();
         Perf<T> base = performance(X, U);
         int status = UB_STATUS_CONVERGED, qp_iters = 0, sqp_done = 0;
@@ -1971,7 +2001,7 @@ struct Solver {
             if (NXO() > 0) {
                 // Newton step of the obstacle states = exact constant-acceleration rollout of the observation - iterate
                 const T* o0 = ws + oXO();
-                for (int idx = lane; idx < (N + 1) * P.ndyn * 3; idx += WARP) {
+                for (int idx = lane; idx < (N + 1) * P.ndyn * 3; idx += kTS) {
                     const int k = idx / (P.ndyn * 3), j = (idx / 3) % P.ndyn, c = idx % 3;
                     const T t = C.dt * T(k);
                     const T p0 = o0[j * 9 + c], v0 = o0[j * 9 + 3 + c], a0 = o0[j * 9 + 6 + c];
@@ -1980,7 +2010,7 @@ struct Solver {
                     ws[oDXO() + o + 3 + c] = v0 + t * a0 - ws[oXO() + o + 3 + c];
                     ws[oDXO() + o + 6 + c] = a0 - ws[oXO() + o + 6 + c];
                 }
-                __syncwarp();
+                tsync();
             }
             linearize();
             t_lin += clock64() - c0;
@@ -2000,7 +2030,7 @@ struct Solver {
                 const T* x = X + k * nx;
                 const T* u = U + k * nu;
                 const T* Jp = ws + oLJP() + k * 3 * nq;
-                for (int i = lane; i < nz; i += WARP) {
+                for (int i = lane; i < nz; i += kTS) {
                     T g;
                     if (i < nq) g = C.dt * P.Rd[i] * u[i];
                     else if (i < nu) g = C.dt * C.fw * u[i];
@@ -2017,7 +2047,7 @@ struct Solver {
                     desc += g * zk[i];
                 }
             }
-            desc = warp_sum(desc);
+            desc = tsum(desc);
             const long long c_ls = clock64();
             // filter line search (ocs2 FilterLinesearch [EXT])
             const T vb = base.violation();
@@ -2025,15 +2055,15 @@ struct Solver {
             Perf<T> pn = base;
             alpha = T(1);
             while (alpha >= C.alpha_min) {
-                for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
+                for (int idx = lane; idx < (N + 1) * nx; idx += kTS) {
                     const int k = idx / nx, i = idx % nx;
                     Xn[idx] = X[idx] + alpha * ws[oZ() + k * nz + nu + i];
                 }
-                for (int idx = lane; idx < N * nu; idx += WARP) {
+                for (int idx = lane; idx < N * nu; idx += kTS) {
                     const int k = idx / nu, i = idx % nu;
                     Un[idx] = U[idx] + alpha * ws[oZ() + k * nz + i];
                 }
-                __syncwarp();
+                tsync();
                 pn = performance(Xn, Un, alpha);
                 const T vn = pn.violation();
                 if (vn > C.g_max) accepted = false;
@@ -2053,20 +2083,20 @@ struct Solver {
                 break;
             }
             T dxn = 0, dun = 0;
-            for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
+            for (int idx = lane; idx < (N + 1) * nx; idx += kTS) {
                 const T d = Xn[idx] - X[idx];
                 dxn += d * d;
                 X[idx] = Xn[idx];
             }
-            for (int idx = lane; idx < N * nu; idx += WARP) {
+            for (int idx = lane; idx < N * nu; idx += kTS) {
                 const T d = Un[idx] - U[idx];
                 dun += d * d;
                 U[idx] = Un[idx];
             }
-            for (int idx = lane; idx < (N + 1) * NXO(); idx += WARP) ws[oXO() + idx] += alpha * ws[oDXO() + idx];
-            dxn = sqrt(warp_sum(dxn));
-            dun = sqrt(warp_sum(dun));
-            __syncwarp();
+            for (int idx = lane; idx < (N + 1) * NXO(); idx += kTS) ws[oXO() + idx] += alpha * ws[oDXO() + idx];
+            dxn = sqrt(tsum(dxn));
+            dun = sqrt(tsum(dun));
+            tsync();
             const T dcost = fabs(pn.cost - base.cost);
             base = pn;
             if ((dxn < C.delta_tol && dun < C.delta_tol) || (dcost < C.cost_tol && base.violation() < C.g_min)) break;
@@ -2079,15 +2109,15 @@ struct Solver {
             const int nxt = A.nxt, nxo = NXO();
             T* Xo = A.X + size_t(b) * (N + 1) * nxt;
             T* Uo = A.U + size_t(b) * N * nu;
-            for (int idx = lane; idx < (N + 1) * nx; idx += WARP) {
+            for (int idx = lane; idx < (N + 1) * nx; idx += kTS) {
                 const T v = X[idx];
                 bad += isfinite(v) ? T(0) : T(1);
                 Xo[(idx / nx) * nxt + idx % nx] = v;
             }
-            for (int idx = lane; idx < (N + 1) * nxo; idx += WARP) Xo[(idx / nxo) * nxt + nx + idx % nxo] = ws[oXO() + idx];
-            for (int idx = lane; idx < N * nu; idx += WARP) Uo[idx] = U[idx];
+            for (int idx = lane; idx < (N + 1) * nxo; idx += kTS) Xo[(idx / nxo) * nxt + nx + idx % nxo] = ws[oXO() + idx];
+            for (int idx = lane; idx < N * nu; idx += kTS) Uo[idx] = U[idx];
         }
-        bad = warp_sum(bad);
+        bad = tsum(bad);
         if (bad > T(0)) {
             status = UB_STATUS_NAN;
             if (nan_reason == 0) nan_reason = 3;
@@ -2096,7 +2126,7 @@ struct Solver {
         // converts the rows of finished instances while the kernel is still solving others, so every result of
         // this warp is fenced system-wide before lane 0 publishes the status (last store below)
         __threadfence_system();
-        __syncwarp();
+        tsync();
         if (lane == 0) {
             if (A.stats) {
                 T* s = A.stats + size_t(b) * UB_STATS;
@@ -2124,9 +2154,9 @@ struct Solver {
     }
 };
 
-template <typename T, typename D>
+template <typename T, typename D, int TW = 1>
 __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const __grid_constant__ DevProblem<T> Pc, const DevProblem<T>* __restrict__ Pg,
-                                                          Layout L, BatchArgs<T> A, int warps_per_cta) {
+                                                          Layout L, BatchArgs<T> A, int teams_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // CTA-shared copy of the problem constants
     DevProblem<T>* Ps = reinterpret_cast<DevProblem<T>*>(smem_raw);
@@ -2137,21 +2167,22 @@ __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const __grid_consta
         for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const int warp = int(threadIdx.x) / WARP, lane = threadIdx.x % WARP;
-    const int slot = blockIdx.x * warps_per_cta + warp;
-    if (slot >= A.n_slots) return;
+    constexpr int kTeam = TW * WARP;
+    const int team = int(threadIdx.x) / kTeam, lane = threadIdx.x % kTeam;   // "lane" = thread of the instance team
+    const int slot = blockIdx.x * teams_per_cta + team;
+    if (slot >= A.n_slots) return;   // whole teams leave together (their named barrier is theirs alone)
     constexpr size_t off = (sizeof(DevProblem<T>) + 15) / 16 * 16;
     Layout Lk = L;
     if constexpr (D::kStatic) Lk = D::template layout<T>();  // compile-time offsets (host passes the same numbers)
-    // The per-warp shared-memory offset and the per-instance workspace offset pass through an opaque move: the
+    // The per-team shared-memory offset and the per-slot workspace offset pass through an opaque move: the
     // compiler then keeps them in a register instead of re-deriving them from threadIdx / blockIdx at every use
     // (measured: that rematerialisation was ~8 % of all executed instructions).
-    uint32_t sm_off = uint32_t(off + size_t(warp) * Lk.s_total * sizeof(T));
+    uint32_t sm_off = uint32_t(off + size_t(team) * Lk.s_total * sizeof(T));
     asm volatile("mov.u32 %0, %0;" : "+r"(sm_off));
     unsigned long long ws_off = (unsigned long long)(slot) * (unsigned long long)(Lk.total);
     asm volatile("mov.u64 %0, %0;" : "+l"(ws_off));
     T* sm = reinterpret_cast<T*>(smem_raw + sm_off);
-    Solver<T, D> S(*Ps, Pc, L, lane);
+    Solver<T, D, TW> S(*Ps, Pc, L, lane);
     S.ws = A.ws + ws_off;
     S.X = S.ws + Lk.XW;
     S.U = S.ws + Lk.UW;
@@ -2164,6 +2195,8 @@ __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const __grid_consta
     S.sV = sm + Lk.sV;
     S.sTT = sm + Lk.sTT;
     S.sSm = sm + Lk.sSm;
+    S.sRed = sm + Lk.sRed;
+    S.bar_id = 1 + team;             // barrier 0 is __syncthreads
     if (A.queue == nullptr) {   // static mode (test aid)
         S.run(A, slot);
         return;
@@ -2171,10 +2204,17 @@ __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const __grid_consta
     for (;;) {
         int b = 0;
         if (lane == 0) b = atomicAdd(A.queue, 1);
-        b = __shfl_sync(FULL, b, 0);
+        if constexpr (TW == 1) {
+            b = __shfl_sync(FULL, b, 0);
+        } else {   // broadcast through the team scratch
+            S.tsync();
+            if (lane == 0) *reinterpret_cast<volatile int*>(S.sRed + TW) = b;
+            S.tsync();
+            b = *reinterpret_cast<volatile int*>(S.sRed + TW);
+        }
         if (b >= A.B) break;
         S.run(A, b);
-        __syncwarp();
+        S.tsync();
     }
 }
 

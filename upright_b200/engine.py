@@ -16,7 +16,7 @@ from . import bindings as B
 
 LAYOUT_FIELDS = ("Z", "DZ", "GAP", "LG", "LCT", "LR", "LJP", "LHO", "LJO", "DF", "RHOE", "YE", "RHOT", "YT", "TT",
                  "LAM", "XW", "UW", "sTT", "FAC", "WF", "XN", "UN", "total", "sM", "sP", "sPv", "sSA", "sV",
-                 "s_total", "sSm", "TG", "BD", "LIA", "LJA")
+                 "s_total", "sSm", "sRed", "TG", "BD", "LIA", "LJA", "XO", "DXO")
 
 
 def _ptr(a):
