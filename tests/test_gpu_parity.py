@@ -523,3 +523,17 @@ def test_dynamic_obstacle_kernels_match_full_state_oracle(prec):
                            xo[:, None, 3:6] + t * xo[:, None, 6:], np.tile(xo[:, None, 6:], (1, dyn.N + 1, 1))), axis=2)
     full = out["stats"][:, 3] == 1.0
     assert full.sum() >= 4 and np.abs(out["X"][full][:, :, 27:] - pred[full]).max() < (1e-9 if prec == "f64" else 1e-4)
+
+
+@pytest.mark.parametrize("name", ["cfg3_thing_box_arch", "cfg5_thing_robust8", "cfg2_thing_demo"])
+def test_run_time_dimension_kernels_match_oracle(name, monkeypatch):
+    """UB_FORCE_GENERIC: the run-time-dimension kernels (a team of four warps per instance above 64 stage
+    variables, one warp below) solve the BASELINE configurations like the specialised ones."""
+    mpc, desc, meta = engine(name, "f64")
+    b = batch_for(name, 4, 31)
+    ref = oracle.solve_batch(desc, b["x0"], b["target"], b["body_params"])
+    monkeypatch.setenv("UB_FORCE_GENERIC", "1")
+    out = mpc.solve(b["x0"], b["target"], b["body_params"])
+    monkeypatch.delenv("UB_FORCE_GENERIC")
+    assert (out["status"] == ref["status"]).all()
+    assert np.abs(out["X"] - ref["X"]).max() < 1e-7 and np.abs(out["U"] - ref["U"]).max() < 1e-6

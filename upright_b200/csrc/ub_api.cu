@@ -306,6 +306,7 @@ struct Pick<float> {
     static const ub::DevProblem<float>& host(const ub_problem* p) { return p->hf; }
     static const ub::Layout& layout(const ub_problem* p) { return p->Lf; }
     static ub::LaunchFn<float> generic() { return ub::launch_generic_f32; }
+    static ub::LaunchFn<float> generic_team() { return ub::launch_generic_team_f32; }
     static ub::LaunchFn<float> thing_1obj() { return ub::launch_thing_1obj_f32; }
     static ub::LaunchFn<float> thing_obs12() { return ub::launch_thing_obs12_f32; }
     static ub::LaunchFn<float> ur10_1obj() { return ub::launch_ur10_1obj_f32; }
@@ -320,6 +321,7 @@ struct Pick<double> {
     static const ub::DevProblem<double>& host(const ub_problem* p) { return p->hd; }
     static const ub::Layout& layout(const ub_problem* p) { return p->Ld; }
     static ub::LaunchFn<double> generic() { return ub::launch_generic_f64; }
+    static ub::LaunchFn<double> generic_team() { return ub::launch_generic_team_f64; }
     static ub::LaunchFn<double> thing_1obj() { return ub::launch_thing_1obj_f64; }
     static ub::LaunchFn<double> thing_obs12() { return ub::launch_thing_obs12_f64; }
     static ub::LaunchFn<double> ur10_1obj() { return ub::launch_ur10_1obj_f64; }
@@ -336,15 +338,24 @@ template <typename T>
 ub::LaunchFn<T> select_kernel(const ub_problem* p, int* team_warps) {
     const ub::DevProblem<T>& H = Pick<T>::host(p);
     *team_warps = 1;
-    ub::LaunchFn<T> fn = Pick<T>::generic();
-    if (std::getenv("UB_FORCE_GENERIC") != nullptr) return fn;
-    if (!(H.balancing && H.N == 20 && !H.iacost && !H.iacon && H.ndyn == 0)) return fn;
     const char* te = std::getenv("UB_TEAM");
     const bool team = !(te && std::atoi(te) == 0);
+    // run-time dimensions: one warp per instance up to 64 stage variables, a team beyond
+    ub::LaunchFn<T> fn = Pick<T>::generic();
+    if (team && H.nz > 64) {
+        fn = Pick<T>::generic_team();
+        *team_warps = UB_TEAM_WARPS;
+    }
+    if (std::getenv("UB_FORCE_GENERIC") != nullptr) return fn;
+    if (!(H.balancing && H.N == 20 && !H.iacost && !H.iacon && H.ndyn == 0)) return fn;
     const bool no_obs = H.nobs == 0;
-    if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::thing_1obj();
-    if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12 && !H.eebox) fn = Pick<T>::thing_obs12();
-    if (H.nq == 6 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::ur10_1obj();
+    auto one_warp = [&](ub::LaunchFn<T> f) {
+        fn = f;
+        *team_warps = 1;
+    };
+    if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) one_warp(Pick<T>::thing_1obj());
+    if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12 && !H.eebox) one_warp(Pick<T>::thing_obs12());
+    if (H.nq == 6 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) one_warp(Pick<T>::ur10_1obj());
     if (H.nq == 9 && H.nf == 3 && H.nc == 16 && H.nb == 3 && no_obs) {
         fn = team ? Pick<T>::thing_arch_team() : Pick<T>::thing_arch();
         *team_warps = team ? UB_TEAM_WARPS : 1;

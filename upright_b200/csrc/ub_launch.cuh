@@ -42,5 +42,6 @@ UB_DECLARE_LAUNCHER(thing_robust8) // cfg5: nq 9, nf 1, nc 32, nb 8
 #define UB_TEAM_WARPS 4
 UB_DECLARE_LAUNCHER(thing_arch_team)
 UB_DECLARE_LAUNCHER(thing_robust8_team)
+UB_DECLARE_LAUNCHER(generic_team)   // run-time dimensions, large stage matrices
 
 }  // namespace ub
