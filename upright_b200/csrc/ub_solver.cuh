@@ -1044,6 +1044,16 @@ struct Solver {
             for (int i = j + 1 + lane; i < n; i += kTS) sM[i * ld + j] *= inv;
             tsync();
             if (lane == 0) sM[j * ld + j] = inv;
+            if constexpr (TW > 1) {
+                // team: 2-D cyclic decomposition of the trailing lower triangle (rows over lane / 16, columns over
+                // lane % 16) — balanced, where one column per lane would leave most of the 128 lanes idle
+                constexpr int CB = 16, RA = kTS / CB;
+                const int cb = lane % CB, ra = lane / CB;
+                for (int i = j + 1 + ra; i < n; i += RA) {
+                    const T mij = sM[i * ld + j];
+                    for (int l = j + 1 + cb; l <= i; l += CB) sM[i * ld + l] -= mij * sM[l * ld + j];
+                }
+            } else
             for (int l = j + 1 + lane; l < n; l += kTS) {
                 const T mlj = sM[l * ld + j];
                 T* __restrict__ dst = sM + l * ld + l;         // column l, rows l..n-1
