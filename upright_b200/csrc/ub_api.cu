@@ -46,7 +46,11 @@ int fail(int code, const std::string& msg) {
 int conversion_threads() {
     static const int n = [] {
         const char* env = std::getenv("UB_HOST_THREADS");
-        int v = env ? std::atoi(env) : int(std::thread::hardware_concurrency());
+        int v = int(std::thread::hardware_concurrency());
+        // one process per GPU under torchrun: the ranks of a node share its cores
+        const char* lws = std::getenv("LOCAL_WORLD_SIZE");
+        if (lws && std::atoi(lws) > 1) v = std::max(1, v / std::atoi(lws));
+        if (env) v = std::atoi(env);
         return std::max(1, std::min(v, 16));
     }();
     return n;
@@ -545,7 +549,8 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
                     volatile const int32_t* flag = h_status + b;
                     unsigned spins = 0;
                     while (*flag < 0) {
-                        if ((++spins & 0xfff) == 0) {
+                        if ((++spins & 0x3f) == 0) std::this_thread::yield();
+                        if ((spins & 0xfff) == 0) {
                             const cudaError_t q = cudaStreamQuery(stream);
                             if (q != cudaErrorNotReady && *flag < 0) {   // stream drained (or failed) without this result
                                 failed.store(1);
