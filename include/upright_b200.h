@@ -30,6 +30,7 @@ extern "C" {
 #define UB_MAX_SPHERES 16
 #define UB_MAX_PAIRS 32
 #define UB_MAX_DYNAMIC_OBSTACLES 4
+#define UB_MAX_PROJECTILE_LINKS 8
 #define UB_MAX_NX (3 * UB_MAX_JOINTS)
 #define UB_BODY_PARAMS 10 /* m, m*com(3), vech(I)(6): rigid_body.h:36-54 */
 #define UB_STATS 8
@@ -185,6 +186,23 @@ typedef struct ub_problem_desc {
      * the ABI = 3 nq + 9 n_dynamic_obstacles (ub_problem_dims out[0]); x0 and X carry that many columns. */
     int32_t n_dynamic_obstacles;
     int32_t reserved3;
+
+    /* ProjectilePathConstraint (constraint/projectile_path_constraint.h:46-156; added to the problem at
+     * controller_interface.cpp:272-294, settings wrappers.py:252-265): one inequality row per listed collision
+     * link at the intermediate knots, "poly_ineq" family, behind the inertial-alignment rows:
+     *     h_i = (scale / d_i) s (|c_i(x) - r_closest| - d_i) >= 0
+     * c_i = origin of the link's collision frame (= centre of collision sphere projectile_spheres[i]),
+     * r_closest = point of the LAST dynamic obstacle's ballistic path p + t v + t^2 a / 2 nearest to c_i over t >= 0
+     * (cubic stationarity condition, <= 10 Newton steps from t = 0, step tolerance 1e-4; :11-44), Jacobian with t
+     * held fixed (:120-146).  s = last element of the first target state (wrappers.py:36-42; raised to 1 by
+     * mrt_node.cpp:241-252 while the projectile is in flight): rows are identically zero while s = 0 and
+     * r_closest = p (t = 0) unless s > 0.5.  Change it between solves with ub_set_option("projectile_active"). */
+    int32_t projectile_enabled;
+    int32_t n_projectile_links;
+    int32_t projectile_spheres[UB_MAX_PROJECTILE_LINKS];
+    double projectile_distances[UB_MAX_PROJECTILE_LINKS];
+    double projectile_scale;
+    double projectile_active;
 } ub_problem_desc_t;
 
 typedef struct ub_problem ub_problem_t;
@@ -243,7 +261,7 @@ int ub_solve_batch(ub_problem_t* problem, int32_t B, const void* x0, const void*
  * at M (x,u) pairs on the device.  Host double pointers.
  *   name in {"object_dynamics","contact_forces","obstacle_avoidance",
  *            "end_effector_box_constraint" (needs target),"end_effector_position","cost",
- *            "inertial_alignment_cost","inertial_alignment_constraint"}
+ *            "inertial_alignment_cost","inertial_alignment_constraint","projectile_constraint"}
  *   out [M, rows]; rows returned through *rows_out. */
 int ub_eval(ub_problem_t* problem, const char* name, int32_t M, const double* x,
             const double* u, const double* target /*[M,3] or NULL*/,
@@ -281,8 +299,9 @@ int ub_closed_loop(ub_problem_t* problem, int32_t B, const double* x0, const dou
                    int32_t* n_replans, int32_t* status_counts, uint32_t flags, void* cuda_stream);
 
 /* Runtime options: "sqp_iteration" (init_sqp_iteration vs sqp_iteration,
- * controller.yaml:56-57) and the test aid "stop_after" (0 full solve, 1 stop
- * after the first linearisation, 2 after the first QP). */
+ * controller.yaml:56-57), "projectile_active" (the target-state flag s of the
+ * projectile path constraint, 0 or 1) and the test aid "stop_after" (0 full
+ * solve, 1 stop after the first linearisation, 2 after the first QP). */
 int ub_set_option(ub_problem_t* problem, const char* key, int value);
 
 /* Per-instance workspace layout (offsets in elements) for tests that inspect

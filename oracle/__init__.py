@@ -99,6 +99,15 @@ def linearize(desc, x, u, body_params=None):
     return o
 
 
+def projectile(desc, x):
+    """Projectile-path rows of one knot: values h, Jacobian J over the full state, times of closest approach."""
+    d = dims(desc)
+    n = desc.n_projectile_links
+    o = dict(h=np.zeros(n), J=np.zeros((n, d["nx"])), tclose=np.zeros(n))
+    got = lib().oracle_projectile(C.byref(desc), _p(_f64(x)), _p(o["h"]), _p(o["J"]), _p(o["tclose"]))
+    return {k: v[:got] for k, v in o.items()}
+
+
 def performance(desc, target, X, U, body_params=None):
     out = np.zeros(7)
     lib().oracle_performance(C.byref(desc), _p(_f64(target)), _p(_f64(body_params)), _p(_f64(X)), _p(_f64(U)), _p(out))

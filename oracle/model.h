@@ -230,4 +230,50 @@ void obstacle_constraints(const ub_problem_desc_t& P, const Kinematics<S>& X, S*
     }
 }
 
+// cubic_newtons + projectile_closest_time (constraint/projectile_path_constraint.h:11-44), literally: Newton on
+// a t^3 + b t^2 + c t + d from t = 0, at most 10 steps, stop once a step is below 1e-4.
+inline double projectile_closest_time(const double* r, const double* r0, const double* v0, const double* g) {
+    double gg = 0, vg = 0, vv = 0, dg = 0, dv = 0;
+    for (int i = 0; i < 3; ++i) {
+        const double dr = r[i] - r0[i];
+        gg += g[i] * g[i];
+        vg += v0[i] * g[i];
+        vv += v0[i] * v0[i];
+        dg += dr * g[i];
+        dv += dr * v0[i];
+    }
+    const double a = gg, b = 3 * vg, c = 2 * (vv - dg), d = -2 * dv;
+    double t = 0.0;
+    for (int it = 0; it < 10; ++it) {
+        const double f = a * t * t * t + b * t * t + c * t + d;
+        const double df = 3 * a * t * t + 2 * b * t + c;
+        const double update = f / df;
+        t -= update;
+        if (std::fabs(update) < 1e-4) break;
+    }
+    return t;
+}
+
+// ProjectilePathConstraint::getValue / getLinearApproximation (projectile_path_constraint.h:77-146).  x_obs = the
+// LAST nine states (state.tail(9)); the time of closest approach is evaluated on values and held fixed in the
+// derivative, as the reference does; `tclose[i]` returns it for the obstacle-state Jacobian [I, t I, t^2/2 I].
+template <typename S>
+void projectile_constraints(const ub_problem_desc_t& P, const Kinematics<S>& X, const double* x_obs, S* h,
+                            double* tclose) {
+    const double s = P.projectile_active;
+    for (int i = 0; i < P.n_projectile_links; ++i) {
+        const Vec3<S>& c = X.sphere[P.projectile_spheres[i]];
+        const double cv[3] = {value(c[0]), value(c[1]), value(c[2])};
+        double t = 0.0;
+        if (s > 0.5) t = std::max(0.0, projectile_closest_time(cv, x_obs, x_obs + 3, x_obs + 6));
+        const Vec3<S> closest(S(x_obs[0] + t * x_obs[3] + 0.5 * t * t * x_obs[6]),
+                              S(x_obs[1] + t * x_obs[4] + 0.5 * t * t * x_obs[7]),
+                              S(x_obs[2] + t * x_obs[5] + 0.5 * t * t * x_obs[8]));
+        const Vec3<S> delta = c - closest;
+        const double w = P.projectile_scale / P.projectile_distances[i];
+        h[i] = S(w * s) * (sqrt(dot(delta, delta)) - S(P.projectile_distances[i]));
+        if (tclose) tclose[i] = t;
+    }
+}
+
 }  // namespace orc

@@ -53,7 +53,7 @@ struct Mat {
 };
 
 struct Dims {
-    int nq, nx, nxr, nu, nfc, neq, nfric, nobs, npairs, nterm, N, nz;   // nx = nxr (robot) + 9 per dynamic obstacle
+    int nq, nx, nxr, nu, nfc, neq, nfric, nobs, npairs, nproj, nterm, N, nz;   // nx = nxr (robot) + 9 per dynamic obstacle
 };
 
 static Dims make_dims(const ub_problem_desc_t& P) {
@@ -71,7 +71,9 @@ static Dims make_dims(const ub_problem_desc_t& P) {
     D.nfric = (bal && P.nf == 3) ? 5 * P.nc : 0;
     D.npairs = P.obstacles_enabled ? P.n_pairs : 0;
     // end-effector box rows, then inertial-alignment rows, follow the sphere-pair rows
-    D.nobs = D.npairs + (P.ee_box_enabled ? 6 : 0) + (P.ia_constraint_enabled ? 5 : 0);
+    // projectile-path rows (one per listed link) close the family; they need the obstacle state x.tail(9)
+    D.nproj = (P.projectile_enabled && D.nx > D.nxr) ? P.n_projectile_links : 0;
+    D.nobs = D.npairs + (P.ee_box_enabled ? 6 : 0) + (P.ia_constraint_enabled ? 5 : 0) + D.nproj;
     D.nterm = 3 + 2 * P.nq;  // stationary_desired_position_constraint.h:39-41
     D.N = P.N;
     D.nz = D.nu + D.nx;
@@ -121,6 +123,8 @@ struct KnotLin {
     Mat Jea;                    // d ea / d x (2 x nx)
     double hia[5] = {0, 0, 0, 0, 0};  // inertial-alignment constraint rows
     Mat Jia;                    // d hia / d x (5 x nx)
+    std::vector<double> hproj;  // projectile-path rows, nproj
+    Mat Jproj;                  // d hproj / d x (nproj x nx): robot q block and the last obstacle's nine states
 };
 
 static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const double* body_params, const double* x,
@@ -187,6 +191,31 @@ static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const doub
         for (int r = 0; r < 5; ++r) {
             L.hia[r] = h[r].v;
             for (int j = 0; j < nxr; ++j) L.Jia(r, j) = h[r].d[j];
+        }
+    }
+    L.hproj.assign(D.nproj, 0.0);
+    L.Jproj = Mat(D.nproj, nx);
+    if (D.nproj > 0) {   // projectile_path_constraint.h:108-146
+        std::vector<Dual> h(D.nproj);
+        std::vector<double> tc(D.nproj);
+        const double* xo = x + nx - 9;
+        projectile_constraints<Dual>(P, K, xo, h.data(), tc.data());
+        for (int i = 0; i < D.nproj; ++i) {
+            L.hproj[i] = h[i].v;
+            for (int j = 0; j < nq; ++j) L.Jproj(i, j) = h[i].d[j];
+            // - w s n' [I, t I, t^2/2 I] over the obstacle state, n = delta / |delta|
+            const double t = tc[i], w = P.projectile_scale / P.projectile_distances[i] * P.projectile_active;
+            double n[3], len = 0;
+            for (int c = 0; c < 3; ++c) {
+                n[c] = K.sphere[P.projectile_spheres[i]][c].v - (xo[c] + t * xo[3 + c] + 0.5 * t * t * xo[6 + c]);
+                len += n[c] * n[c];
+            }
+            len = std::sqrt(len);
+            for (int c = 0; c < 3; ++c) {
+                L.Jproj(i, nx - 9 + c) = -w * n[c] / len;
+                L.Jproj(i, nx - 6 + c) = -w * t * n[c] / len;
+                L.Jproj(i, nx - 3 + c) = -w * 0.5 * t * t * n[c] / len;
+            }
         }
     }
     L.hobs.assign(D.npairs, 0.0);
@@ -346,6 +375,14 @@ static Perf performance(const ub_problem_desc_t& P, const Dims& D, const Mat& A,
                 pf.ineq_sse += dt * (sq(std::min(0.0, hu)) + sq(std::min(0.0, hl)));
                 pf.min_margin = std::min(pf.min_margin, std::min(hu, hl));
             }
+        if (D.nproj > 0 && k >= 1) {   // projectile_path_constraint.h:77-106
+            double hp[UB_MAX_PROJECTILE_LINKS];
+            projectile_constraints<double>(P, K, x + nx - 9, hp, nullptr);
+            for (int i = 0; i < D.nproj; ++i) {
+                pf.ineq_sse += dt * sq(std::min(0.0, hp[i]));
+                pf.min_margin = std::min(pf.min_margin, hp[i]);
+            }
+        }
     }
     return pf;
 }
@@ -506,6 +543,16 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
                     finish(r, soft_poly);
                     s.rows.push_back(r);
                 }
+            // projectile-path rows (projectile_path_constraint.h:108-146)
+            for (int i = 0; i < D.nproj; ++i) {
+                Row r;
+                r.a.assign(s.nz, 0.0);
+                for (int j = 0; j < nx; ++j) r.a[xo + j] = L.Jproj(i, j);
+                r.c = L.hproj[i];
+                r.lb = 0.0;
+                finish(r, soft_poly);
+                s.rows.push_back(r);
+            }
         }
         if (k == N) {
             // terminal equality [r_d - r; v; a] = 0 (stationary_desired_position_constraint.h:43-74)
@@ -1368,6 +1415,23 @@ int oracle_linearize(const ub_problem_desc_t* P, const double* x, const double* 
     cp(hfric, L.hfric); cp(Ffric, L.Ffric.d); cp(hobs, L.hobs); cp(Jobs, L.Jobs.d);
     if (r) std::memcpy(r, L.r, sizeof(L.r));
     return 0;
+}
+
+// Projectile-path rows of one knot: h[nproj], J[nproj*nx], tclose[nproj] (any may be NULL); returns nproj
+int oracle_projectile(const ub_problem_desc_t* P, const double* x, double* h, double* J, double* tclose) {
+    const orc::Dims D = orc::make_dims(*P);
+    if (D.nproj == 0) return 0;
+    std::vector<double> u(D.nu, 0.0);
+    orc::KnotLin L;
+    orc::linearize_knot(*P, D, &P->body_params[0][0], x, u.data(), L);
+    if (h) std::memcpy(h, L.hproj.data(), sizeof(double) * D.nproj);
+    if (J) std::memcpy(J, L.Jproj.d.data(), sizeof(double) * L.Jproj.d.size());
+    if (tclose) {
+        const orc::Kinematics<double> K = orc::forward_kinematics<double>(*P, x);
+        std::vector<double> hv(D.nproj);
+        orc::projectile_constraints<double>(*P, K, x + D.nx - 9, hv.data(), tclose);
+    }
+    return D.nproj;
 }
 
 // Performance index of a trajectory: out = {cost, dyn_sse, eq_sse, ineq_sse, violation, max_eq, min_margin}

@@ -525,6 +525,57 @@ def test_dynamic_obstacle_kernels_match_full_state_oracle(prec):
     assert full.sum() >= 4 and np.abs(out["X"][full][:, :, 27:] - pred[full]).max() < (1e-9 if prec == "f64" else 1e-4)
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_projectile_path_constraint_matches_oracle(prec):
+    """ProjectilePathConstraint (projectile_path_constraint.h:46-156): probe values, warm- and cold-started solves
+    with the flag s raised, and the flag lowered through ub_set_option, against the oracle (which carries the
+    projectile as genuine states with the row's obstacle block - w s n' [I, t I, t^2/2 I])."""
+    from _util import ballistic_prediction, projectile_problem, projectile_throws
+    d, meta, tray = projectile_problem()
+    d0, _, _ = projectile_problem(active=0.0)
+    mpc = BatchedMPC(d, prec)
+    assert mpc.nx == 36 and mpc.nx_robot == 27
+    x0r = np.array(meta["x0"], dtype=float)
+    throws = projectile_throws(oracle.fk(d, np.concatenate((x0r, np.zeros(9))))["spheres"][tray])
+    Bn = len(throws)
+    x0 = np.hstack((np.tile(x0r, (Bn, 1)), throws))
+    target = np.tile(meta["r_ee0"] + np.array([0.1, 0.1, 0.05]), (Bn, d.N + 1, 1))
+    h = mpc.eval("projectile_constraint", x0, np.zeros((Bn, mpc.nu)))
+    href = np.array([oracle.projectile(d, x0[i])["h"] for i in range(Bn)])
+    assert h.shape == (Bn, 2) and np.allclose(h, href, atol=1e-9)
+    Xw = np.stack([np.hstack((np.tile(x0r, (d.N + 1, 1)), ballistic_prediction(xo, d.N, d.dt))) for xo in throws])
+    Uw = np.zeros((Bn, d.N, mpc.nu))
+    rx, ru = ranges(d)
+
+    def check(out, ref):
+        assert (ref["status"] == 0).all()
+        if prec == "f64":
+            assert (out["status"] == ref["status"]).all()
+            assert np.abs(out["X"] - ref["X"]).max() < 1e-7 and np.abs(out["U"] - ref["U"]).max() < 1e-6
+        else:
+            assert (out["status"] == 0).sum() >= Bn - 1
+            good = out["status"] == 0
+            ex = (np.abs(out["X"][good][:, :, :27] - ref["X"][good][:, :, :27]) / rx).reshape(good.sum(), -1).max(axis=1)
+            eu = (np.abs(out["U"][good] - ref["U"][good]) / ru).reshape(good.sum(), -1).max(axis=1)
+            assert np.median(ex) <= 2e-3 and ex.max() <= 2e-2 and np.median(eu) <= 2e-3 and eu.max() <= 2e-2
+
+    ref = oracle.solve_batch(d, x0, target, X=Xw.copy(), U=Uw.copy(), warm=True)
+    out = mpc.solve(x0, target, None, X=Xw.copy(), U=Uw.copy(), warm=True)
+    check(out, ref)
+    # the rows did something: the tray gives way where the flag-down plan does not
+    ref0 = oracle.solve_batch(d0, x0, target, X=Xw.copy(), U=Uw.copy(), warm=True)
+    assert np.abs(ref["X"][:, :, :27] - ref0["X"][:, :, :27]).max() > 1e-2
+    if prec == "f64":   # cold start: obstacle states held over the horizon, rows linearised far from the prediction
+        check(mpc.solve(x0, target), oracle.solve_batch(d, x0, target))
+    mpc.set_option("projectile_active", 0)
+    try:
+        assert np.abs(mpc.eval("projectile_constraint", x0, np.zeros((Bn, mpc.nu)))).max() == 0
+        check(mpc.solve(x0, target, None, X=Xw.copy(), U=Uw.copy(), warm=True), ref0)
+    finally:
+        mpc.set_option("projectile_active", 1)
+    check(mpc.solve(x0, target, None, X=Xw.copy(), U=Uw.copy(), warm=True), ref)
+
+
 @pytest.mark.parametrize("name", ["cfg3_thing_box_arch", "cfg5_thing_robust8", "cfg2_thing_demo"])
 def test_run_time_dimension_kernels_match_oracle(name, monkeypatch):
     """UB_FORCE_GENERIC: the run-time-dimension kernels (a team of four warps per instance above 64 stage

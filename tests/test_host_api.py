@@ -154,8 +154,7 @@ def test_end_effector_box_and_next_rows():
     bad["end_effector_box_constraint"]["xyz_lower"] = [2.0, -1.0, -0.05]
     with pytest.raises(ValueError):
         settings.ControllerSettings(bad, x0=np.array(meta["x0"])).to_desc()
-    for key, patch in (("projectile_path_constraint", {"enabled": True}),
-                       ("operating_points", {"enabled": True})):
+    for key, patch in (("operating_points", {"enabled": True}),):
         c2 = copy.deepcopy(meta["controller_config"])
         c2[key] = dict(c2.get(key, {}), **patch)
         with pytest.raises(NotImplementedError):
@@ -198,3 +197,32 @@ def test_dynamic_obstacle_settings():
     assert desc.n_dynamic_obstacles == 1 and desc.n_pairs == d.n_pairs + 1
     riding = [i for i in range(desc.n_spheres) if desc.spheres[i].link == -2]
     assert len(riding) == 1 and desc.spheres[riding[0]].radius == 0.1
+
+
+def test_projectile_path_constraint_settings():
+    """`projectile_path_constraint` (wrappers.py:252-265; ral23/experiments/projectile/_base.yaml:81-86): the listed
+    collision links become rows measured from their collision spheres to the last dynamic obstacle; the sanity
+    checks of the reference (projectile_path_constraint.h:57-62) are kept."""
+    import copy
+    d, meta = problem_io.load_fixture("cfg4_thing_obstacles2")
+    cfg = copy.deepcopy(meta["controller_config"])
+    cfg["obstacles"]["dynamic"] = [{"name": "projectile1", "radius": 0.2,
+                                    "modes": [{"time": 0, "position": [0, -10, 0], "velocity": [0, 0, 0], "acceleration": [0, 0, -9.81]}]}]
+    cfg["projectile_path_constraint"] = {"enabled": True, "distances": [0.35, 0.2], "scale": 0.2,
+                                         "collision_links": ["balanced_object_collision_link", "wrist3_collision_link"]}
+    s = settings.ControllerSettings(cfg)
+    desc = s.to_desc()
+    assert desc.projectile_enabled == 1 and desc.n_projectile_links == 2 and desc.n_dynamic_obstacles == 1
+    assert list(desc.projectile_distances)[:2] == [0.35, 0.2] and desc.projectile_scale == 0.2 and desc.projectile_active == 0.0
+    slots = list(desc.projectile_spheres)[:2]
+    assert all(0 <= k < desc.n_spheres and desc.spheres[k].link >= 0 for k in slots) and slots[0] != slots[1]
+    assert desc.spheres[slots[0]].link == desc.nq   # the balanced object's sphere rides on the tool frame
+    assert desc.n_pairs == d.n_pairs                # the projectile has no distance rows of its own (dynamic.yaml:31-36)
+    bad = copy.deepcopy(cfg)
+    bad["projectile_path_constraint"]["distances"] = [0.35]
+    with pytest.raises(RuntimeError):
+        settings.ControllerSettings(bad).to_desc()
+    bad = copy.deepcopy(cfg)
+    bad["obstacles"]["dynamic"] = []
+    with pytest.raises(ValueError):
+        settings.ControllerSettings(bad).to_desc()

@@ -325,3 +325,95 @@ def test_moving_dynamic_obstacle_prediction_and_avoidance():
     parked, xs = _with_dynamic_obstacle(desc, slot, np.concatenate((far, np.zeros(6))))
     still = oracle.solve_batch(parked, np.concatenate((x0, xs)), target)
     assert np.abs(out["X"][0][:, :27] - still["X"][0][:, :27]).max() > 1e-3   # the approaching obstacle changes the plan
+
+
+def _cubic_newton_literal(r, xo):
+    """projectile_path_constraint.h:11-44, line by line."""
+    r0, v0, g = xo[:3], xo[3:6], xo[6:]
+    dr = r - r0
+    a, b, c, d = g @ g, 3 * v0 @ g, 2 * (v0 @ v0 - dr @ g), -2 * dr @ v0
+    x = 0.0
+    for _ in range(10):
+        f = a * x * x * x + b * x * x + c * x + d
+        dfdx = 3 * a * x * x + 2 * b * x + c
+        update = f / dfdx
+        x = x - update
+        if abs(update) < 1e-4:
+            return x
+    return x
+
+
+def test_projectile_path_rows():
+    """ProjectilePathConstraint (projectile_path_constraint.h:46-156): value against a brute-force closest approach,
+    Jacobian (time of closest approach held fixed = envelope derivative) against finite differences over robot and
+    obstacle states, the flag s, and the literal Newton iteration where it does NOT converge (ball thrown upwards)."""
+    import oracle
+    from _util import projectile_problem, projectile_throws
+    d, meta, tray = projectile_problem()
+    base, _ = problem_io.load_fixture("cfg4_thing_obstacles2")
+    assert oracle.dims(d)["nx"] == 36 and oracle.dims(d)["n_ineq"] == oracle.dims(base)["n_ineq"] + 2
+    x0 = np.array(meta["x0"], dtype=float)
+    spheres = oracle.fk(d, np.concatenate((x0, np.zeros(9))))["spheres"]
+    slots = [d.projectile_spheres[i] for i in range(2)]
+    dist = [d.projectile_distances[i] for i in range(2)]
+    tt = np.linspace(0, 3, 300001)
+    for xo in projectile_throws(spheres[tray]):
+        x = np.concatenate((x0, xo))
+        pr = oracle.projectile(d, x)
+        path = xo[None, :3] + tt[:, None] * xo[None, 3:6] + 0.5 * tt[:, None] ** 2 * xo[None, 6:]
+        for i in range(2):
+            dmin = np.linalg.norm(spheres[slots[i]][None] - path, axis=1).min()
+            assert abs(pr["h"][i] - 0.2 / dist[i] * (dmin - dist[i])) < 1e-7
+            assert abs(pr["tclose"][i] - max(0.0, _cubic_newton_literal(spheres[slots[i]], xo))) < 1e-12
+        J = np.zeros_like(pr["J"])
+        h = 1e-6
+        for j in range(len(x)):
+            xp, xm = x.copy(), x.copy()
+            xp[j] += h
+            xm[j] -= h
+            J[:, j] = (oracle.projectile(d, xp)["h"] - oracle.projectile(d, xm)["h"]) / (2 * h)
+        assert np.abs(pr["J"] - J).max() < 1e-6 and np.abs(pr["J"][:, 9:27]).max() == 0   # positions only
+    # ball that has passed: closest approach clamps to t = 0 (":123 don't care about the past")
+    xo = np.concatenate((spheres[tray] + [0.0, 1.0, 0.0], [0.0, 3.0, -1.0], [0.0, 0.0, -9.81]))
+    pr = oracle.projectile(d, np.concatenate((x0, xo)))
+    assert pr["tclose"][0] == 0.0 and abs(pr["h"][0] - 0.2 / 0.35 * (1.0 - 0.35)) < 1e-12
+    # upward throw of the reference's own simulation (obstacles/dynamic.yaml:48-52): Newton leaves t = 0 towards a
+    # far root and runs out of iterations — reproduced, not repaired
+    xo = np.concatenate((spheres[tray] + [0.0, -2.0, 0.3], [0.0, 2.67, 3.68], [0.0, 0.0, -9.81]))
+    pr = oracle.projectile(d, np.concatenate((x0, xo)))
+    lit = _cubic_newton_literal(spheres[tray], xo)
+    assert abs(pr["tclose"][0] - lit) < 1e-9 * max(1.0, abs(lit))
+    # s = 0: rows vanish identically (value and Jacobian); s <= 0.5 never looks ahead
+    d0, _, _ = projectile_problem(active=0.0)
+    pr0 = oracle.projectile(d0, np.concatenate((x0, projectile_throws(spheres[tray])[0])))
+    assert np.all(pr0["h"] == 0) and np.all(pr0["J"] == 0) and np.all(pr0["tclose"] == 0)
+
+
+def test_projectile_constraint_shapes_the_plan():
+    """With the flag raised the plan gives way to the ball's predicted path (soft rows: the violation shrinks), with
+    the flag down it is the plan of the problem without the rows."""
+    import oracle
+    from _util import ballistic_prediction, projectile_problem, projectile_throws
+    d, meta, tray = projectile_problem()
+    d0, _, _ = projectile_problem(active=0.0)
+    x0 = np.array(meta["x0"], dtype=float)
+    spheres = oracle.fk(d, np.concatenate((x0, np.zeros(9))))["spheres"]
+    target = np.tile(meta["r_ee0"] + np.array([0.1, 0.1, 0.05]), (d.N + 1, 1))
+    xo = projectile_throws(spheres[tray])[0]
+    x = np.concatenate((x0, xo))
+    Xw = np.hstack((np.tile(x0, (d.N + 1, 1)), ballistic_prediction(xo, d.N, d.dt)))[None]
+    Uw = np.zeros((1, d.N, 13))
+    on = oracle.solve_batch(d, x, target, X=Xw.copy(), U=Uw.copy(), warm=True)
+    off = oracle.solve_batch(d0, x, target, X=Xw.copy(), U=Uw.copy(), warm=True)
+    assert on["status"][0] == 0 and off["status"][0] == 0
+    # obstacle states of an accepted full step = the ballistic prediction
+    assert on["stats"][0, 3] == 1.0 and np.abs(on["X"][0][:, 27:] - Xw[0][:, 27:]).max() < 1e-9
+    rows = lambda X: np.array([oracle.projectile(d, X[k])["h"] for k in range(1, d.N)])  # noqa: E731
+    h_on, h_off = rows(on["X"][0]), rows(off["X"][0])
+    assert h_off.min() < -0.05 and (np.minimum(h_on, 0) ** 2).sum() < 0.97 * (np.minimum(h_off, 0) ** 2).sum()
+    # flag down = the problem without the rows (same robot trajectory as the plain dynamic-obstacle problem)
+    import copy
+    plain = copy.deepcopy(d0)
+    plain.projectile_enabled = 0
+    ref = oracle.solve_batch(plain, x, target, X=Xw.copy(), U=Uw.copy(), warm=True)
+    assert np.abs(ref["X"] - off["X"]).max() < 1e-6 and np.abs(ref["U"] - off["U"]).max() < 1e-5

@@ -15,6 +15,7 @@ UB_MAX_CONTACTS = 32
 UB_MAX_SPHERES = 16
 UB_MAX_PAIRS = 32
 UB_MAX_DYNAMIC_OBSTACLES = 4
+UB_MAX_PROJECTILE_LINKS = 8
 UB_MAX_NX = 27
 UB_BODY_PARAMS = 10
 UB_STATS = 8
@@ -99,6 +100,10 @@ class ProblemDesc(C.Structure):
         ("ia_align_with_fixed_vector", C.c_int32), ("reserved2", C.c_int32), ("ia_alpha", C.c_double),
         ("ia_normal", C.c_double * 3), ("ia_com", C.c_double * 3),
         ("n_dynamic_obstacles", C.c_int32), ("reserved3", C.c_int32),
+        ("projectile_enabled", C.c_int32), ("n_projectile_links", C.c_int32),
+        ("projectile_spheres", C.c_int32 * UB_MAX_PROJECTILE_LINKS),
+        ("projectile_distances", C.c_double * UB_MAX_PROJECTILE_LINKS),
+        ("projectile_scale", C.c_double), ("projectile_active", C.c_double),
     ]
 
     # convenience
@@ -128,7 +133,9 @@ _lib = None
 
 
 def library_path() -> Path:
-    return Path(__file__).resolve().parent / LIB_NAME
+    """The in-tree library; UB_LIBRARY names another build of it (diagnostic builds such as -DUB_DEBUG_NAN)."""
+    override = os.environ.get("UB_LIBRARY")
+    return Path(override).resolve() if override else Path(__file__).resolve().parent / LIB_NAME
 
 
 def load_library():

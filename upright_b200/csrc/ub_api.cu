@@ -169,7 +169,14 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
     P.nxo = 9 * P.ndyn;
     P.iacon = d.ia_constraint_enabled ? 1 : 0;
     // end-effector box rows, then inertial-alignment rows, ride behind the sphere-pair rows
-    P.nobs = P.npairs + (P.eebox ? 6 : 0) + (P.iacon ? 5 : 0);
+    P.nproj = (d.projectile_enabled && P.ndyn > 0) ? d.n_projectile_links : 0;
+    P.nobs = P.npairs + (P.eebox ? 6 : 0) + (P.iacon ? 5 : 0) + P.nproj;
+    for (int i = 0; i < P.nproj; ++i) {
+        P.proj_sph[i] = d.projectile_spheres[i];
+        P.proj_d[i] = T(d.projectile_distances[i]);
+    }
+    P.proj_scale = T(d.projectile_scale);
+    P.proj_s = T(d.projectile_active);
     P.obsw = P.iacon ? 3 * d.nq : d.nq;
     P.ia_use_ang = d.ia_use_angular_acceleration ? 1 : 0;
     P.ia_fixed = d.ia_align_with_fixed_vector ? 1 : 0;
@@ -782,6 +789,19 @@ int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
     for (int s = 0; s < desc->n_spheres; ++s)
         if (desc->spheres[s].link < -1 - desc->n_dynamic_obstacles || desc->spheres[s].link > desc->nq)
             return fail(UB_E_INVALID, "sphere attached to an unknown link / dynamic obstacle");
+    if (desc->projectile_enabled) {
+        if (!desc->obstacles_enabled || desc->n_dynamic_obstacles < 1)
+            return fail(UB_E_INVALID, "projectile path constraint needs a dynamic obstacle (the projectile)");
+        if (desc->n_projectile_links < 0 || desc->n_projectile_links > UB_MAX_PROJECTILE_LINKS)
+            return fail(UB_E_INVALID, "too many projectile collision links");
+        for (int i = 0; i < desc->n_projectile_links; ++i) {
+            const int s = desc->projectile_spheres[i];
+            if (s < 0 || s >= desc->n_spheres || desc->spheres[s].link < 0)
+                return fail(UB_E_INVALID, "projectile collision link must name a robot collision sphere");
+            if (!(desc->projectile_distances[i] > 0)) return fail(UB_E_INVALID, "projectile distances must be positive");
+        }
+        if (desc->projectile_scale < 0) return fail(UB_E_INVALID, "projectile scale must be non-negative");
+    }
     if (desc->ee_box_enabled)
         for (int c = 0; c < 3; ++c)
             if (!(desc->ee_box_lower[c] < desc->ee_box_upper[c]))
@@ -850,6 +870,16 @@ int ub_set_option(ub_problem_t* p, const char* key, int value) {
         if (value < 1) return fail(UB_E_INVALID, "sqp_iteration must be >= 1");
         if (p->hf.sqp_iters == value) return UB_OK;
         p->desc.sqp_iteration = p->hf.sqp_iters = p->hd.sqp_iters = value;
+        UB_CUDA(cudaMemcpy(p->df, &p->hf, sizeof(p->hf), cudaMemcpyHostToDevice));
+        UB_CUDA(cudaMemcpy(p->dd, &p->hd, sizeof(p->hd), cudaMemcpyHostToDevice));
+        return UB_OK;
+    }
+    if (std::strcmp(key, "projectile_active") == 0) {   // the flag s of the first target state (mrt_node.cpp:241-263)
+        const double sv = value ? 1.0 : 0.0;
+        if (p->desc.projectile_active == sv) return UB_OK;
+        p->desc.projectile_active = sv;
+        p->hf.proj_s = float(sv);
+        p->hd.proj_s = sv;
         UB_CUDA(cudaMemcpy(p->df, &p->hf, sizeof(p->hf), cudaMemcpyHostToDevice));
         UB_CUDA(cudaMemcpy(p->dd, &p->hd, sizeof(p->hd), cudaMemcpyHostToDevice));
         return UB_OK;
@@ -925,7 +955,7 @@ float ub_last_solve_ms(const ub_problem_t* p) {
 // thread per sample.
 namespace {
 
-enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4, EV_EEBOX = 5, EV_IACOST = 6, EV_IACON = 7 };
+enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4, EV_EEBOX = 5, EV_IACOST = 6, EV_IACON = 7, EV_PROJ = 8 };
 
 __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int what, int M, int rows,
                             const double* __restrict__ x, const double* __restrict__ u,
@@ -941,7 +971,7 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
     ub::Kin<double> K;
     ub::KinTan<double> D;
     double sph[3 * UB_MAX_SPHERES];
-    ub::forward_kinematics<double, false>(P, xm, -1, K, D, P.npairs > 0 ? sph : nullptr, nullptr);
+    ub::forward_kinematics<double, false>(P, xm, -1, K, D, (P.npairs > 0 || P.nproj > 0) ? sph : nullptr, nullptr);
     if (P.npairs > 0)
         for (int s = 0; s < P.nsph; ++s)
             if (P.slink[s] <= -2)   // sphere riding on a dynamic obstacle: centre = position block of its state
@@ -992,6 +1022,12 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
         }
     } else if (what == EV_IACON) {   // getStateInputInequalityConstraintValue("inertial_alignment_constraint")
         ub::inertial_alignment_rows<double, false>(P, K, D, o, nullptr);
+    } else if (what == EV_PROJ) {   // getStateInputInequalityConstraintValue("projectile_constraint")
+        for (int i = 0; i < P.nproj; ++i) {
+            ub::V3<double> n;
+            double tc;
+            o[i] = ub::projectile_row(P, i, ub::ld3(sph + 3 * P.proj_sph[i]), xm + P.nx + P.nxo - 9, &n, &tc);
+        }
     } else if (what == EV_IACOST) {   // getCostValue("inertial_alignment_cost"): 1/2 w e'e
         double e2[2] = {0, 0};
         if (P.iacost) ub::inertial_alignment_error<double, false>(P, K, D, e2, nullptr);
@@ -1042,6 +1078,7 @@ extern "C" int ub_eval(ub_problem_t* p, const char* name, int32_t M, const doubl
     else if (n == "cost") { what = EV_COST; rows = 1; }
     else if (n == "inertial_alignment_cost") { what = EV_IACOST; rows = 1; }
     else if (n == "inertial_alignment_constraint") { what = EV_IACON; rows = P.iacon ? 5 : 0; }
+    else if (n == "projectile_constraint") { what = EV_PROJ; rows = P.nproj; }
     else return fail(UB_E_INVALID, "unknown probe name " + n);
     if (rows_out) *rows_out = rows;
     if (rows == 0) return UB_OK;

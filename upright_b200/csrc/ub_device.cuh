@@ -48,6 +48,10 @@ struct DevProblem {
     T ia_alpha, ia_n[3], ia_com[3];
     // dynamic obstacles: ndyn x [p, v, a] appended to the state (nxo = 9 ndyn); spheres with slink == -2 - j ride on j
     int ndyn, nxo;
+    // projectile-path rows (projectile_path_constraint.h:46-156): one per listed collision sphere, behind the
+    // inertial-alignment rows; proj_s = the target-state flag s
+    int nproj, proj_sph[UB_MAX_PROJECTILE_LINKS];
+    T proj_d[UB_MAX_PROJECTILE_LINKS], proj_scale, proj_s;
 };
 
 // Division in the interior-point row updates (eight per inequality row and pass): the fp32 kernels use the
@@ -78,6 +82,37 @@ __device__ __forceinline__ V3<T> cross(const V3<T>& a, const V3<T>& b) {
 }
 template <typename T>
 __device__ __forceinline__ V3<T> ld3(const T* p) { return V3<T>(p[0], p[1], p[2]); }
+
+// cubic_newtons + projectile_closest_time (constraint/projectile_path_constraint.h:11-44): time at which the
+// ballistic path r0 + t v0 + t^2 g / 2 is nearest to r; Newton from t = 0, at most 10 steps, step tolerance 1e-4
+template <typename T>
+__device__ inline T projectile_closest_time(const V3<T>& r, const V3<T>& r0, const V3<T>& v0, const V3<T>& g) {
+    const V3<T> dr = r - r0;
+    const T a = dot(g, g), b = T(3) * dot(v0, g), c = T(2) * (dot(v0, v0) - dot(dr, g)), d = T(-2) * dot(dr, v0);
+    T t = T(0);
+    for (int it = 0; it < 10; ++it) {
+        const T f = ((a * t + b) * t + c) * t + d;
+        const T df = (T(3) * a * t + T(2) * b) * t + c;
+        const T update = f / df;
+        t -= update;
+        if (fabs(update) < T(1e-4)) break;
+    }
+    return t;
+}
+// Row i of ProjectilePathConstraint (projectile_path_constraint.h:77-146) for the collision-sphere centre c and the
+// projectile state xo = [p, v, a]: value (scale / d_i) s (|c - r_closest| - d_i); *n = unit vector from the closest
+// point of the path to c, *tc = time of closest approach (clamped at 0; 0 while s <= 0.5)
+template <typename T>
+__device__ inline T projectile_row(const DevProblem<T>& P, int i, const V3<T>& c, const T* xo, V3<T>* n, T* tc) {
+    const V3<T> p0 = ld3(xo), v0 = ld3(xo + 3), a0 = ld3(xo + 6);
+    T t = T(0);
+    if (P.proj_s > T(0.5)) t = max(T(0), projectile_closest_time(c, p0, v0, a0));
+    const V3<T> delta = c - (p0 + t * v0 + (T(0.5) * t * t) * a0);
+    const T dist = sqrt(dot(delta, delta));
+    *n = (T(1) / dist) * delta;
+    *tc = t;
+    return P.proj_scale / P.proj_d[i] * P.proj_s * (dist - P.proj_d[i]);
+}
 
 template <typename T>
 struct M3 {

@@ -182,6 +182,9 @@ struct Solver {
     // box, the whole state when inertial-alignment constraint rows (which see v and a) ride along
     __device__ __forceinline__ int OBSW() const { if constexpr (D::kStatic) return D::nq; else return P.obsw; }
     __device__ __forceinline__ bool IACON() const { if constexpr (D::kStatic) return false; else return P.iacon != 0; }
+    // projectile-path rows (run-time-dimension kernel only), last of the obstacle family
+    __device__ __forceinline__ int NPROJ() const { if constexpr (D::kStatic) return 0; else return P.nproj; }
+    __device__ __forceinline__ bool SPHERES() const { return NPAIRS() > 0 || NPROJ() > 0; }
     // dynamic obstacles (run-time-dimension kernel only): number of appended states
     __device__ __forceinline__ int NXO() const { if constexpr (D::kStatic) return 0; else return P.nxo; }
     // Sphere centres of the dynamic obstacles at knot k for the obstacle iterate XO + ao * DXO.  The obstacle states
@@ -486,7 +489,7 @@ struct Solver {
             const T* x = X + k * nx;
             Kin<T> Kn;
             KinTan<T> Dt;
-            forward_kinematics<T, true>(P, x, lane, Kn, Dt, NPAIRS() > 0 ? sph : nullptr, dsph);
+            forward_kinematics<T, true>(P, x, lane, Kn, Dt, SPHERES() ? sph : nullptr, dsph);
             if (NXO() > 0) place_dynamic_spheres(k, T(0), sph);
             if (lane == 0) {
                 ws[oLR() + 3 * k] = Kn.r.x;
@@ -587,6 +590,26 @@ struct Solver {
                         if (lane < nx) ws[oLJO() + (k * NOBS() + i0 + r) * OBSW() + lane] = dh5[r];
                     }
                 }
+                if (NPROJ() > 0) {
+                    // projectile-path rows (projectile_path_constraint.h:108-146) close the family: dense over q with
+                    // the time of closest approach held fixed; the obstacle-state block - w s n' [I, t I, t^2/2 I]
+                    // meets the known Newton step of the (last) obstacle and lands in the constant
+                    const int i0 = NPAIRS() + (EEBOX() ? 6 : 0) + (IACON() ? 5 : 0);
+                    const int o = (k * P.ndyn + P.ndyn - 1) * 9;
+                    const T* xo = ws + oXO() + o;
+                    const T* dxo = ws + oDXO() + o;
+                    for (int i = 0; i < NPROJ(); ++i) {
+                        const int a = P.proj_sph[i];
+                        V3<T> n;
+                        T tc;
+                        const T h = projectile_row(P, i, ld3(sph + 3 * a), xo, &n, &tc);
+                        const T w = C.proj_scale / P.proj_d[i] * C.proj_s;
+                        const V3<T> dstep = ld3(dxo) + tc * ld3(dxo + 3) + (T(0.5) * tc * tc) * ld3(dxo + 6);
+                        if (lane == 0) ws[oLHO() + k * NOBS() + i0 + i] = h - w * dot(n, dstep);
+                        if (lane < OBSW())
+                            ws[oLJO() + (k * NOBS() + i0 + i) * OBSW() + lane] = lane < nq ? w * dot(n, ld3(dsph + 3 * a)) : T(0);
+                    }
+                }
             }
             // dynamics gap b_k = A x_k + B u_k - x_{k+1}  (exact triple integrator, system_dynamics.h:15-26)
             if (k < N && lane < nq) {
@@ -615,7 +638,7 @@ struct Solver {
             const T* x = Xt + k * nx;
             Kin<T> Kn;
             KinTan<T> Dn;
-            forward_kinematics<T, false>(P, x, -1, Kn, Dn, NPAIRS() > 0 ? sph : nullptr, nullptr);
+            forward_kinematics<T, false>(P, x, -1, Kn, Dn, SPHERES() ? sph : nullptr, nullptr);
             if (NXO() > 0) {
                 place_dynamic_spheres(k, ao, sph);
                 if (k < N)   // dynamics defect of the obstacle states: (1 - ao) x the defect of the iterate
@@ -728,6 +751,19 @@ struct Solver {
                         const T m = min(T(0), h5[r]);
                         ineq += dt * m * m;
                         min_margin = min(min_margin, h5[r]);
+                    }
+                }
+                if (NPROJ() > 0) {
+                    const int o = (k * P.ndyn + P.ndyn - 1) * 9;
+                    T xo[9];
+                    for (int c = 0; c < 9; ++c) xo[c] = ws[oXO() + o + c] + (ao != T(0) ? ao * ws[oDXO() + o + c] : T(0));
+                    for (int i = 0; i < NPROJ(); ++i) {
+                        V3<T> n;
+                        T tc;
+                        const T h = projectile_row(P, i, ld3(sph + 3 * P.proj_sph[i]), xo, &n, &tc);
+                        const T m = min(T(0), h);
+                        ineq += dt * m * m;
+                        min_margin = min(min_margin, h);
                     }
                 }
             }

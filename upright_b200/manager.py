@@ -174,6 +174,10 @@ class _RecedingHorizon:
                     U[:, k] = (1 - w) * Uext[:, i] + w * Uext[:, i + 1]
         iters = self.settings.sqp.init_sqp_iteration if self.first else self.settings.sqp.sqp_iteration
         self.engine.set_option("sqp_iteration", int(iters))
+        if getattr(self.settings, "projectile_path_constraint_enabled", False):
+            # the flag s = last element of the FIRST target state (projectile_path_constraint.h:78-80), raised by the
+            # caller while the projectile is in flight (mrt_node.cpp:241-263); one flag for the whole batch
+            self.engine.set_option("projectile_active", int(self.targets[0].xs[0][7] > 0.5))
         out = self.engine.solve(self.x_obs, self._knot_targets(t), self.body_params, X=X, U=U, warm=warm,
                                 want_gains=self.use_feedback, rescue=True)
         self.X, self.U = out["X"], out["U"]

@@ -196,6 +196,13 @@ class ControllerSettings:
         self.xyz_upper = pa(ebc.get("xyz_upper", [1, 1, 1]))
         ppc = config.get("projectile_path_constraint", {"enabled": False})
         self.projectile_path_constraint_enabled = ppc["enabled"]
+        # wrappers.py:252-265
+        self.projectile_path_distances = np.array(ppc.get("distances", []), dtype=float)
+        self.projectile_path_scale = float(ppc.get("scale", 1.0))
+        self.projectile_path_collision_links = list(ppc.get("collision_links", []))
+        if self.projectile_path_constraint_enabled:
+            assert (self.projectile_path_distances >= 0).all()
+            assert self.projectile_path_scale >= 0
 
         self.locked_joints = {
             k: pn(v) for k, v in config["robot"].get("locked_joints", {}).items()
@@ -318,8 +325,6 @@ class ControllerSettings:
         d.gravity[:] = self.gravity
 
         # features of the reference that are 'next' rows are rejected loudly, never ignored
-        if self.projectile_path_constraint_enabled:
-            raise NotImplementedError("projectile_path_constraint is a 'next' row (SURVEY §8f-2)")
         ia = self.inertial_alignment_settings
         # InertialAlignmentCostGaussNewton / InertialAlignmentConstraint (controller_interface.cpp:296-315)
         d.ia_cost_enabled = int(bool(ia.cost_enabled))
@@ -378,6 +383,8 @@ class ControllerSettings:
                 dc.normal[:] = c.normal
                 dc.span[:] = np.asarray(c.span).ravel()
 
+        if self.projectile_path_constraint_enabled and not d.obstacles_enabled:
+            raise ValueError("projectile_path_constraint needs obstacles.enabled (the projectile is a dynamic obstacle)")
         if d.obstacles_enabled:
             spheres = list(self.chain.spheres)
             sidx = {s.name: i for i, s in enumerate(spheres)}
@@ -397,6 +404,23 @@ class ControllerSettings:
                 for k in (ia, ib):
                     used.setdefault(k, len(used))
                 pairs.append((used[ia], used[ib]))
+            # ProjectilePathConstraint (controller_interface.cpp:272-294): one row per listed collision link, measured
+            # from the origin of the link's frame = the centre of its collision sphere, to the LAST dynamic obstacle
+            if self.projectile_path_constraint_enabled:
+                links = self.projectile_path_collision_links
+                if len(links) != len(self.projectile_path_distances):
+                    raise RuntimeError("Number of distances and EEs must be equal!")   # projectile_path_constraint.h:57-62
+                if not dyn:
+                    raise ValueError("projectile_path_constraint needs a dynamic obstacle (the projectile)")
+                if len(links) > B.UB_MAX_PROJECTILE_LINKS:
+                    raise ValueError("too many projectile collision links")
+                d.projectile_enabled, d.n_projectile_links = 1, len(links)
+                d.projectile_scale = self.projectile_path_scale
+                d.projectile_active = float(getattr(self, "projectile_active", 0.0))
+                for i, n in enumerate(links):
+                    k = sidx[n[:-2] if n.endswith("_0") else n]
+                    d.projectile_spheres[i] = used.setdefault(k, len(used))
+                    d.projectile_distances[i] = float(self.projectile_path_distances[i])
             if len(used) > B.UB_MAX_SPHERES or len(pairs) > B.UB_MAX_PAIRS:
                 raise ValueError("too many collision spheres / pairs")
             for k, slot in used.items():
