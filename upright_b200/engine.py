@@ -171,7 +171,7 @@ class BatchedMPC:
         x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
         u = np.ascontiguousarray(np.atleast_2d(u), dtype=np.float64)
         M = x.shape[0]
-        cap = M * max(self.n_eq, 5 * self.nc, self.desc.n_pairs, 6, 1)
+        cap = M * max(self.n_eq, 5 * self.nc, self.desc.n_pairs, self.desc.n_projectile_links, 6, 1)
         out = np.zeros(cap)
         rows = C.c_int32()
         tg = None if target is None else np.ascontiguousarray(target, dtype=np.float64).reshape(M, 3)

@@ -102,6 +102,8 @@ class ControllerInterface:
         return float(self._engine.eval("cost", x, u, target=tgt[None])[0, 0])
 
     def getCostValue(self, name, t, x, u):
+        if name == "inertial_alignment_cost":   # controller_interface.cpp:296-305
+            return float(self._engine.eval(name, x, u)[0, 0])
         if name not in ("state_input_cost", "end_effector_cost"):
             raise RuntimeError(f"unknown cost {name}")
         total = self.cost(t, x, u)
@@ -114,9 +116,14 @@ class ControllerInterface:
         return self._engine.eval("object_dynamics", x, u)[0]
 
     def getStateInputInequalityConstraintValue(self, name, t, x, u):
-        if name not in ("contact_forces", "obstacle_avoidance"):
+        # names as registered at controller_interface.cpp:221,266,291,312,347
+        if name not in ("contact_forces", "obstacle_avoidance", "end_effector_box_constraint",
+                        "inertial_alignment_constraint", "projectile_constraint"):
             raise RuntimeError(f"unknown inequality constraint {name}")
-        return self._engine.eval(name, x, u)[0]
+        tgt = None
+        if name == "end_effector_box_constraint":
+            tgt = self._core.targets[0].get_desired_state(t)[:3][None]
+        return self._engine.eval(name, x, u, target=tgt)[0]
 
 
 class _RecedingHorizon:
