@@ -576,6 +576,41 @@ def test_projectile_path_constraint_matches_oracle(prec):
     check(mpc.solve(x0, target, None, X=Xw.copy(), U=Uw.copy(), warm=True), ref)
 
 
+def test_operating_point_initializer_matches_oracle():
+    """use_operating_points (controller_interface.cpp:380-387): the first solve starts from the operating trajectory
+    instead of the held state — same result as the oracle started from that iterate, and not the cold-start one."""
+    from upright_b200 import settings
+    from upright_b200.manager import _RecedingHorizon
+    from upright_b200.settings import TargetTrajectories
+    from upright_b200.trajectory import StateInputTrajectory
+    desc, meta = problem_io.load_fixture("cfg2_thing_demo")
+    x0 = np.array(meta["x0"], dtype=float)
+    # operating trajectory: the arm eases 0.2 rad on joints 3..8 over 2 s with consistent velocities
+    ts = np.linspace(0.0, 2.0, 11)
+    prof, dprof = 0.5 * (1 - np.cos(np.pi * ts / 2.0)), 0.25 * np.pi * np.sin(np.pi * ts / 2.0)
+    xs = np.tile(x0, (len(ts), 1))
+    xs[:, 3:9] += 0.2 * prof[:, None]
+    xs[:, 12:18] = 0.2 * dprof[:, None]
+    us = np.zeros((len(ts), desc.nu))
+    us[:, 9:] = 0.827 * 9.81 / 4                       # the forces that carry the object at rest
+    st = settings.ControllerSettings(meta["controller_config"], x0=x0, operating_trajectory=StateInputTrajectory(ts, xs, us))
+    st.use_operating_points = True
+    mpc = BatchedMPC(st.to_desc(), "f64")
+    rh = _RecedingHorizon(mpc, st, 2)
+    r0 = mpc.eval("end_effector_position", x0, np.zeros(desc.nu))[0]
+    goal = TargetTrajectories([0.0], [np.r_[r0 + [0.2, 0.1, 0.1], 0, 0, 0, 1, 0]], [np.zeros(desc.nu)])
+    rh.reset([goal])
+    rh.observe(0.0, np.tile(x0, (2, 1)))
+    rh.advance()
+    Xg, Ug = rh.operating_guess(0.0)
+    target = np.tile(r0 + [0.2, 0.1, 0.1], (2, desc.N + 1, 1))
+    ref = oracle.solve_batch(st.to_desc(), np.tile(x0, (2, 1)), target, X=Xg.copy(), U=Ug.copy(), warm=True)
+    assert (rh.status == ref["status"]).all()
+    assert np.abs(rh.X - ref["X"]).max() < 1e-7 and np.abs(rh.U - ref["U"]).max() < 1e-6
+    cold = oracle.solve_batch(st.to_desc(), np.tile(x0, (2, 1)), target)
+    assert np.abs(cold["X"] - ref["X"]).max() > 1e-3
+
+
 @pytest.mark.parametrize("name", ["cfg3_thing_box_arch", "cfg5_thing_robust8", "cfg2_thing_demo"])
 def test_run_time_dimension_kernels_match_oracle(name, monkeypatch):
     """UB_FORCE_GENERIC: the run-time-dimension kernels (a team of four warps per instance above 64 stage

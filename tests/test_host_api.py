@@ -154,11 +154,6 @@ def test_end_effector_box_and_next_rows():
     bad["end_effector_box_constraint"]["xyz_lower"] = [2.0, -1.0, -0.05]
     with pytest.raises(ValueError):
         settings.ControllerSettings(bad, x0=np.array(meta["x0"])).to_desc()
-    for key, patch in (("operating_points", {"enabled": True}),):
-        c2 = copy.deepcopy(meta["controller_config"])
-        c2[key] = dict(c2.get(key, {}), **patch)
-        with pytest.raises(NotImplementedError):
-            settings.ControllerSettings(c2, x0=np.array(meta["x0"])).to_desc()
 
 
 def test_inertial_alignment_cost_settings():
@@ -226,3 +221,67 @@ def test_projectile_path_constraint_settings():
     bad["obstacles"]["dynamic"] = []
     with pytest.raises(ValueError):
         settings.ControllerSettings(bad).to_desc()
+
+
+def test_operating_point_initializer(tmp_path):
+    """ocs2::OperatingPoints (controller_interface.cpp:380-387, wrappers.py:289-296): the trajectory file is loaded
+    by the settings; with `use_operating_points` set the first solve starts from it (u_k = inputs(t_k),
+    x_{k+1} = states(t_{k+1}), x_0 observed) and, on later solves, so do the knots beyond the previous horizon."""
+    import copy
+    from types import SimpleNamespace
+
+    from upright_b200.manager import _RecedingHorizon
+    from upright_b200.trajectory import StateInputTrajectory
+
+    d, meta = problem_io.load_fixture("cfg2_thing_demo")
+    ts = np.array([0.0, 1.0, 3.0])
+    xs = np.stack([np.full(27, v) for v in (0.0, 1.0, 2.0)])
+    us = np.stack([np.full(13, v) for v in (0.0, -1.0, -1.0)])
+    path = tmp_path / "operating.npz"
+    StateInputTrajectory(ts, xs, us).save(path)
+    st = settings.ControllerSettings(copy.deepcopy(meta["controller_config"]), x0=np.array(meta["x0"]),
+                                     operating_trajectory=StateInputTrajectory.load(path))
+    assert st.use_operating_points is False and len(st.operating_times) == 3    # loaded, not switched on (as upstream)
+    st.to_desc()
+    st.use_operating_points = True
+    st.to_desc()
+    bad = settings.ControllerSettings(copy.deepcopy(meta["controller_config"]), x0=np.array(meta["x0"]))
+    bad.use_operating_points = True
+    with pytest.raises(ValueError):
+        bad.to_desc()
+
+    N, nx, nu = 20, 27, 13
+
+    class Stub:
+        def __init__(self):
+            self.N, self.nx, self.nu = N, nx, nu
+            self.calls = []
+
+        def set_option(self, *a):
+            pass
+
+        def solve(self, x0, target, body, X=None, U=None, warm=False, want_gains=False, **kw):
+            self.calls.append(dict(warm=warm, X=None if X is None else X.copy(), U=None if U is None else U.copy()))
+            B = x0.shape[0]
+            return dict(X=np.full((B, N + 1, nx), 7.0), U=np.full((B, N, nu), 7.0), status=np.zeros(B, np.int32),
+                        stats=np.zeros((B, 8)), K=None)
+
+    eng = Stub()
+    rh = _RecedingHorizon(eng, st, 2)
+    rh.reset([TargetTrajectories([0.0], [np.r_[1, 2, 3, 0, 0, 0, 1, 0]], [np.zeros(nu)])])
+    x_obs = np.full((2, nx), 0.25)
+    rh.observe(0.5, x_obs)
+    rh.advance()
+    c = eng.calls[0]
+    assert c["warm"] is True                                     # the guess goes in as the starting iterate
+    tk = 0.5 + 0.1 * np.arange(N + 1)
+    want_x = np.where(tk <= 1.0, tk, 1.0 + (tk - 1.0) / 2.0)
+    assert np.allclose(c["X"][:, 0], 0.25) and np.allclose(c["X"][0, 1:, 5], want_x[1:]) and np.allclose(c["X"][1], c["X"][0])
+    assert np.allclose(c["U"][0, :, 3], -np.minimum(tk[:-1], 1.0))
+    # next solve 0.3 s later: covered knots from the previous solution (7), the three beyond it from the initializer
+    rh.observe(0.8, x_obs)
+    rh.advance()
+    c = eng.calls[1]
+    tn = 0.8 + 0.1 * np.arange(N + 1)
+    assert np.allclose(c["X"][0, :18, 5], 7.0) and np.allclose(c["X"][0, 18:, 5], 1.0 + (tn[18:] - 1.0) / 2.0)
+    assert np.allclose(c["U"][0, :17, 3], 7.0) and np.allclose(c["U"][0, 17:, 3], -1.0)

@@ -162,10 +162,28 @@ class _RecedingHorizon:
             tg[b] = tt.positions_at(times)
         return tg
 
+    def operating_guess(self, t):
+        """Initial guess from the operating trajectory (ocs2::OperatingPoints [EXT], chosen at
+        controller_interface.cpp:380-387): u_k = inputs(t_k), x_{k+1} = states(t_{k+1}), linear interpolation clamped
+        at both ends; x_0 is the observation."""
+        from .trajectory import interp_rows
+        s = self.settings
+        times = t + self.dt * np.arange(self.N + 1)
+        ts, xs, us = np.asarray(s.operating_times), np.asarray(s.operating_states), np.asarray(s.operating_inputs)
+        X1 = np.stack([interp_rows(ts, xs, tk) for tk in times])
+        U1 = np.stack([interp_rows(ts, us, tk) for tk in times[:-1]])
+        X = np.tile(X1, (self.B, 1, 1))
+        X[:, 0] = self.x_obs
+        return X, np.tile(U1, (self.B, 1, 1))
+
     def advance(self):
         t = self.t_obs
         warm = (self.X is not None) and not self.settings.mpc.cold_start
         X = U = None
+        operating = bool(getattr(self.settings, "use_operating_points", False))
+        if operating and not warm:
+            # the initializer covers the whole horizon; handed to the solver as its starting iterate
+            X, U = self.operating_guess(t)
         if warm:
             # previous primal solution interpolated at the new grid, tail held
             told = self.t0 + self.dt * np.arange(self.N + 1)
@@ -179,13 +197,17 @@ class _RecedingHorizon:
                 X[:, k] = (1 - w) * self.X[:, i] + w * self.X[:, i + 1]
                 if k < self.N:
                     U[:, k] = (1 - w) * Uext[:, i] + w * Uext[:, i + 1]
+            if operating:   # knots beyond the previous horizon come from the initializer, not from holding the tail
+                Xo, Uo = self.operating_guess(t)
+                X[:, tnew > told[-1] + 1e-12] = Xo[:, tnew > told[-1] + 1e-12]
+                U[:, tnew[:-1] > told[-1] - 1e-12] = Uo[:, tnew[:-1] > told[-1] - 1e-12]   # intervals not covered
         iters = self.settings.sqp.init_sqp_iteration if self.first else self.settings.sqp.sqp_iteration
         self.engine.set_option("sqp_iteration", int(iters))
         if getattr(self.settings, "projectile_path_constraint_enabled", False):
             # the flag s = last element of the FIRST target state (projectile_path_constraint.h:78-80), raised by the
             # caller while the projectile is in flight (mrt_node.cpp:241-263); one flag for the whole batch
             self.engine.set_option("projectile_active", int(self.targets[0].xs[0][7] > 0.5))
-        out = self.engine.solve(self.x_obs, self._knot_targets(t), self.body_params, X=X, U=U, warm=warm,
+        out = self.engine.solve(self.x_obs, self._knot_targets(t), self.body_params, X=X, U=U, warm=X is not None,
                                 want_gains=self.use_feedback, rescue=True)
         self.X, self.U = out["X"], out["U"]
         self.K = out.get("K")

@@ -212,7 +212,20 @@ class ControllerSettings:
         # The un-vendored URDF is replaced by the in-repo chain fixture.
         self.robot_urdf_path = "<upright_b200.robot fixture>"
         self.lib_folder = "/tmp/ocs2"
-        self.use_operating_points = bool(config.get("operating_points", {}).get("enabled", False))
+        # Operating points (wrappers.py:289-296; controller_settings.h:90-97; initializer chosen at
+        # controller_interface.cpp:380-387).  As in the reference, loading the trajectory does not switch the
+        # initializer on: `use_operating_points` stays False until the caller sets it.
+        self.use_operating_points = False
+        self.operating_times, self.operating_states, self.operating_inputs = [], [], []
+        op = config.get("operating_points", {"enabled": False})
+        if op.get("enabled", False) or operating_trajectory is not None:
+            if operating_trajectory is None:
+                from .trajectory import StateInputTrajectory
+                operating_trajectory = StateInputTrajectory.load(cfgmod.resolve_package_path(op))
+            for i in range(len(operating_trajectory)):
+                self.operating_times.append(float(operating_trajectory.ts[i]))
+                self.operating_states.append(np.array(operating_trajectory.xs[i], dtype=float))
+                self.operating_inputs.append(np.array(operating_trajectory.us[i], dtype=float))
 
         bal = config["balancing"]
         self.balancing_settings = SimpleNamespace(
@@ -337,8 +350,12 @@ class ControllerSettings:
             d.ia_alpha = float(ia.alpha)
             d.ia_use_angular_acceleration = int(bool(ia.use_angular_acceleration))
             d.ia_align_with_fixed_vector = int(bool(ia.align_with_fixed_vector))
-        if self.use_operating_points:
-            raise NotImplementedError("the operating-point initializer is not supported (DefaultInitializer only)")
+        if self.use_operating_points:   # host-side initial guess (manager.py); the device needs nothing
+            if not self.operating_times:
+                raise ValueError("use_operating_points is set but no operating trajectory was loaded")
+            if any(x.shape != (self.dims.x(),) for x in self.operating_states) or \
+                    any(u.shape != (self.dims.u(),) for u in self.operating_inputs):
+                raise ValueError("operating states / inputs must have the problem's state / input dimension")
         # EndEffectorBoxConstraint (end_effector_box_constraint.h; wrappers.py:240-250)
         d.ee_box_enabled = int(bool(self.end_effector_box_constraint_enabled))
         if d.ee_box_enabled:
