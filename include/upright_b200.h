@@ -211,8 +211,8 @@ typedef struct ub_problem ub_problem_t;
 #define UB_PTRS_DEVICE 0x1u /* all batch pointers are device pointers (f32)  */
 #define UB_WARM_START 0x2u  /* X/U hold the previous solution on entry       */
 #define UB_COMPUTE_F64 0x4u /* validation build: run the kernels in fp64     */
-#define UB_RESCUE_F64 0x8u  /* host mode: instances the fp32 kernels end with UB_STATUS_NAN are solved again
-                               (cold start) by the fp64 kernels inside the same call */
+#define UB_RESCUE_F64 0x8u  /* host mode: instances the fp32 kernels end with UB_STATUS_NAN are solved again by
+                               the fp64 kernels inside the same call (from the same starting iterate) */
 
 const char* ub_last_error(void);
 int ub_version(void);

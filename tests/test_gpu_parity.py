@@ -345,6 +345,31 @@ def test_fp64_rescue_of_fp32_breakdowns():
         assert np.abs(resc["X"][idx] - ref["X"]).max() < 1e-7 and (resc["status"][idx] == ref["status"]).all()
 
 
+def test_fp64_rescue_keeps_the_warm_start():
+    """A warm-started call that breaks down in fp32 is re-solved in fp64 from the SAME starting iterate (its fp32 copy
+    on the device), not from a cold start.  Case: the projectile problem with cfg4's 20 g object and soft
+    object-dynamics rows — the documented fp32 conditioning limit."""
+    from _util import ballistic_prediction, projectile_problem, projectile_throws
+    d, meta, tray = projectile_problem(light_object=True)
+    x0r = np.array(meta["x0"], dtype=float)
+    throws = projectile_throws(oracle.fk(d, np.concatenate((x0r, np.zeros(9))))["spheres"][tray])
+    Bn = len(throws)
+    x0 = np.hstack((np.tile(x0r, (Bn, 1)), throws))
+    target = np.tile(meta["r_ee0"] + np.array([0.1, 0.1, 0.05]), (Bn, d.N + 1, 1))
+    Xw = np.stack([np.hstack((np.tile(x0r, (d.N + 1, 1)), ballistic_prediction(xo, d.N, d.dt))) for xo in throws])
+    Uw = np.zeros((Bn, d.N, 13))
+    mpc = BatchedMPC(d, "f32")
+    plain = mpc.solve(x0, target, None, X=Xw.copy(), U=Uw.copy(), warm=True)
+    nan = plain["status"] == 3
+    assert nan.any()
+    resc = mpc.solve(x0, target, None, X=Xw.copy(), U=Uw.copy(), warm=True, rescue=True)
+    ref = oracle.solve_batch(d, x0, target, X=Xw.copy(), U=Uw.copy(), warm=True)
+    cold = oracle.solve_batch(d, x0, target)
+    assert (resc["status"][nan] == ref["status"][nan]).all()
+    assert np.abs(resc["X"][nan] - ref["X"][nan]).max() < 1e-4 and np.abs(resc["U"][nan] - ref["U"][nan]).max() < 1e-3
+    assert np.abs(cold["X"][nan] - ref["X"][nan]).max() > 1e-2
+
+
 def test_end_effector_box_constraint_parity():
     """EndEffectorBoxConstraint rows (end_effector_box_constraint.h:46-76): probe values, fp64 kernels against
     the oracle to 1e-7, fp32 within the stated tolerance, and the rows are active."""
@@ -574,6 +599,18 @@ def test_projectile_path_constraint_matches_oracle(prec):
     finally:
         mpc.set_option("projectile_active", 1)
     check(mpc.solve(x0, target, None, X=Xw.copy(), U=Uw.copy(), warm=True), ref)
+
+
+def test_host_rollout_with_projectile_matches_oracle_engine():
+    """The closed loop with the simulated projectile and the in-flight gate (rollout_host, mpc_sim.py:118-160 with
+    mrt_node.cpp:241-263) on the fp64 kernels against the same loop on the CPU oracle: 14 warm-started replans
+    with the flag going up and down reproduce the oracle's closed loop."""
+    from _util import OracleEngine, projectile_rollout
+    ref, desc, _ = projectile_rollout(OracleEngine, True)
+    out, _, info = projectile_rollout(lambda d: BatchedMPC(d, "f64"), True)
+    assert out["n_replans"] == ref["n_replans"] == 14 and (out["flags"] == ref["flags"]).all()
+    assert np.abs(out["xs"] - ref["xs"]).max() < 1e-6 and np.abs(out["us"] - ref["us"]).max() < 1e-4
+    assert np.abs(out["x_final"] - ref["x_final"]).max() < 1e-6
 
 
 def test_operating_point_initializer_matches_oracle():

@@ -285,3 +285,51 @@ def test_operating_point_initializer(tmp_path):
     tn = 0.8 + 0.1 * np.arange(N + 1)
     assert np.allclose(c["X"][0, :18, 5], 7.0) and np.allclose(c["X"][0, 18:, 5], 1.0 + (tn[18:] - 1.0) / 2.0)
     assert np.allclose(c["U"][0, :17, 3], 7.0) and np.allclose(c["U"][0, 17:, 3], -1.0)
+
+
+def test_ballistic_obstacles_and_projectile_gate():
+    """plant.BallisticObstacles = the uncontrolled obstacle of upright_sim (simulation.py:300-435): free flight under
+    the mode's acceleration, reset to the next mode when its time has come, `relative` placement; plant.ProjectileGate
+    = mrt_node.cpp:241-263."""
+    from upright_b200.plant import BallisticObstacles, ProjectileGate
+    cfg = [{"controlled": False, "radius": 0.1, "relative": True,
+            "modes": [{"time": 0, "position": [0.0, -2.0, 0.3], "velocity": [0, 2.67, 3.68], "acceleration": [0, 0, -9.81]},
+                      {"time": 0.5, "position": [1.414, -1.414, 0], "velocity": [-1.89, 1.89, 3.68], "acceleration": [0, 0, -9.81]}]}]
+    off = np.array([[1.0, 2.0, 0.7], [0.0, 0.0, 0.5]])
+    ob = BallisticObstacles(cfg, 2, offsets=off)
+    assert len(ob) == 1 and ob.state().shape == (2, 9)
+    assert np.allclose(ob.state()[:, :3], off + [0.0, -2.0, 0.3]) and np.allclose(ob.state()[:, 6:], [0, 0, -9.81])
+    h, resets = 0.01, []
+    for s in range(60):
+        resets.append(ob.step(s * h, h))
+    # entered the second mode at the step starting at t = 0.5, then flew 10 steps from its initial values
+    assert resets.index(True) == 50 and sum(resets) == 1
+    t = 10 * h
+    assert np.allclose(ob.state()[:, :3], off + [1.414, -1.414, 0] + t * np.array([-1.89, 1.89, 3.68]) + 0.5 * t * t * np.array([0, 0, -9.81]))
+    assert np.allclose(ob.state()[:, 3:6], np.array([-1.89, 1.89, 3.68]) + t * np.array([0, 0, -9.81]))
+    with pytest.raises(NotImplementedError):
+        BallisticObstacles([dict(cfg[0], controlled=True)], 1)
+    g = ProjectileGate()
+    zs = [0.5, 0.9, 1.01, 1.5, 0.8, 0.21, 0.19, 1.5]
+    assert [g.update(z) for z in zs] == [0, 0, 1, 1, 1, 1, 0, 0] and g.observing   # no second flight
+
+
+def test_host_rollout_with_projectile_on_oracle_engine():
+    """BatchedControllerManager.rollout_host — the mpc_sim.py loop with the simulated projectile feeding the obstacle
+    columns and the in-flight gate raising the flag s — driven here by the CPU oracle standing in for the engine:
+    the tray keeps a larger distance from the ball than with the constraint disabled."""
+    import oracle
+    from _util import OracleEngine, projectile_rollout
+    dist = {}
+    for enabled in (True, False):
+        out, desc, info = projectile_rollout(OracleEngine, enabled)
+        eng = info["engine"]
+        assert out["xs"].shape == (1, 70, 36) and out["n_replans"] == 14 and np.isfinite(out["xs"]).all()
+        # the obstacle columns are the simulated flight, the flag follows the height of the ball
+        assert np.allclose(out["xs"][0, :, 27:30], info["flight"])
+        z = out["xs"][0, :, 29]
+        assert out["flags"][0] == 1.0 and out["flags"][-1] == 0.0 and (out["flags"][z > 1.0] == 1.0).all()
+        assert eng.flags[0] == 1.0 and eng.flags[-1] == 0.0
+        cen = np.array([oracle.fk(desc, out["xs"][0, k])["spheres"][info["tray"]] for k in range(70)])
+        dist[enabled] = np.linalg.norm(cen - out["xs"][0, :, 27:30], axis=1).min()
+    assert dist[True] > dist[False] + 0.02, dist   # measured: 0.42 m against 0.20 m

@@ -587,7 +587,8 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
     if constexpr (sizeof(T) == 4) {
         if (flags & UB_RESCUE_F64) {
             // fp32 breakdown (a factorisation that lost positive definiteness to roundoff): the few instances
-            // concerned go through the fp64 kernels, cold-started, and replace their rows
+            // concerned go through the fp64 kernels and replace their rows.  A warm-started call re-solves them from
+            // the same starting iterate: its fp32 copy is still on the device (the results went to pinned memory).
             std::vector<int> idx;
             for (int b = 0; b < B; ++b)
                 if (status[b] == UB_STATUS_NAN) idx.push_back(b);
@@ -598,12 +599,20 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
                 std::vector<double> rx0(n * sx0), rtg(n * stg), rbd(body ? n * sbd : 0), rX(n * sX), rU(n * sU),
                     rK(K ? n * sK : 0), rst(n * UB_STATS);
                 std::vector<int32_t> rstatus(n);
+                const bool warm = (flags & UB_WARM_START) != 0;
+                std::vector<T> row(warm ? sX + sU : 0);
                 for (int i = 0; i < n; ++i) {
                     std::memcpy(&rx0[i * sx0], x0 + idx[i] * sx0, sx0 * sizeof(double));
                     std::memcpy(&rtg[i * stg], target + idx[i] * stg, stg * sizeof(double));
                     if (body) std::memcpy(&rbd[i * sbd], body + idx[i] * sbd, sbd * sizeof(double));
+                    if (warm) {   // before the nested call below reuses (or reallocates) the device buffer
+                        UB_CUDA(cudaMemcpy(row.data(), d_X + idx[i] * sX, sX * sizeof(T), cudaMemcpyDeviceToHost));
+                        UB_CUDA(cudaMemcpy(row.data() + sX, d_U + idx[i] * sU, sU * sizeof(T), cudaMemcpyDeviceToHost));
+                        for (size_t j = 0; j < sX; ++j) rX[i * sX + j] = double(row[j]);
+                        for (size_t j = 0; j < sU; ++j) rU[i * sU + j] = double(row[sX + j]);
+                    }
                 }
-                const uint32_t f2 = (flags & ~(UB_RESCUE_F64 | UB_WARM_START | UB_PTRS_DEVICE)) | UB_COMPUTE_F64;
+                const uint32_t f2 = (flags & ~(UB_RESCUE_F64 | UB_PTRS_DEVICE)) | UB_COMPUTE_F64;
                 const int rc2 = solve_host<double>(p, n, rx0.data(), rtg.data(), body ? rbd.data() : nullptr, rX.data(), rU.data(),
                                                    K ? rK.data() : nullptr, rstatus.data(), rst.data(), f2, stream);
                 if (rc2 != UB_OK) return rc2;

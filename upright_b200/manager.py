@@ -350,6 +350,9 @@ class BatchedControllerManager:
         """Closed loop for `duration` seconds entirely on the device (`ub_closed_loop`): the loop of
         `mpc_sim.py:118-160` — `step(t, x)`, `u_cmd = Kx (xd - x) + u`, integrate — for all B robots, with the
         model's triple integrator as the plant.  The waypoint times must be shared by all targets."""
+        if self.desc.n_dynamic_obstacles > 0:
+            raise ValueError("problems with dynamic obstacles roll out through rollout_host (the obstacle plant and "
+                             "its mode schedule belong to the simulation)")
         tr = self.settings.tracking
         tt = self.core.targets[0].ts
         for tg in self.core.targets:
@@ -364,3 +367,47 @@ class BatchedControllerManager:
             use_feedback=bool(self.settings.sqp.use_feedback_policy), cold_start=bool(self.settings.mpc.cold_start),
             init_sqp_iteration=self.settings.sqp.init_sqp_iteration, sqp_iteration=self.settings.sqp.sqp_iteration,
             gains=(getattr(tr, "kp", 0.0), getattr(tr, "kv", 0.0), getattr(tr, "ka", 0.0)), log_stride=log_stride, log=log)
+
+    def rollout_host(self, x0, duration, sim_timestep, obstacles=None, gate=None, log_stride=1):
+        """The loop of `mpc_sim.py:118-160` on the host, one `step(t, x)` per simulation step for all B robots, for
+        the problems the device loop does not take: dynamic obstacles.  `x0` is the robot state [B, 3 nq];
+        `obstacles` a `plant.BallisticObstacles` (its state fills the obstacle columns of x every step, as
+        `env.dynamic_obstacle_state()` does at mpc_sim.py:120-121), `gate` a `plant.ProjectileGate` driven by the
+        height of the LAST obstacle of instance 0 (one flag s for the batch: it is a problem option).  The robot
+        plant is the model's exact triple integrator, as in `ub_closed_loop`."""
+        nq = self.settings.dims.robot.q
+        nxr = 3 * nq
+        tr = self.settings.tracking
+        kp, kv, ka = (getattr(tr, k, 0.0) for k in ("kp", "kv", "ka"))
+        xr = np.array(x0, dtype=float).reshape(self.B, nxr)
+        n_obs = self.desc.n_dynamic_obstacles
+        if n_obs and (obstacles is None or len(obstacles) != n_obs):
+            raise ValueError(f"the problem carries {n_obs} dynamic obstacle(s): pass a matching obstacle plant")
+        nominal = obstacles.state() if n_obs else np.zeros((self.B, 0))
+        n_steps = int(round(duration / sim_timestep))
+        xs, us, flags = [], [], []
+        h = sim_timestep
+        for step in range(n_steps):
+            t = h * step
+            xo = obstacles.state() if n_obs else nominal
+            if gate is not None:
+                s = gate.update(float(xo[0, -7]))          # z of the last obstacle
+                for tg in self.core.targets:
+                    tg.xs[0][7] = s
+                if not gate.observing:
+                    xo = nominal                           # mrt_node.cpp:265-270: state updated once past pre-flight
+                flags.append(s)
+            x = np.hstack((xr, xo))
+            xd, u = self.step(t, x)
+            e = (xd - x)[:, :nxr]
+            ucmd = kp * e[:, :nq] + kv * e[:, nq:2 * nq] + ka * e[:, 2 * nq:] + u[:, :nq]
+            if step % log_stride == 0:
+                xs.append(x.copy())
+                us.append(ucmd.copy())
+            q, v, a = xr[:, :nq], xr[:, nq:2 * nq], xr[:, 2 * nq:]
+            xr = np.hstack((q + h * v + 0.5 * h * h * a + h**3 / 6 * ucmd, v + h * a + 0.5 * h * h * ucmd, a + h * ucmd))
+            if n_obs:
+                obstacles.step(t, h)
+        xo = obstacles.state() if n_obs else nominal
+        return dict(xs=np.stack(xs, 1), us=np.stack(us, 1), x_final=np.hstack((xr, xo)),
+                    n_replans=len(self.replanning_times), flags=np.array(flags))
