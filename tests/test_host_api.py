@@ -333,3 +333,19 @@ def test_host_rollout_with_projectile_on_oracle_engine():
         cen = np.array([oracle.fk(desc, out["xs"][0, k])["spheres"][info["tray"]] for k in range(70)])
         dist[enabled] = np.linalg.norm(cen - out["xs"][0, :, 27:30], axis=1).min()
     assert dist[True] > dist[False] + 0.02, dist   # measured: 0.42 m against 0.20 m
+
+
+def test_fp32_conditioning_estimate():
+    """The estimate that makes BatchedMPC warn: fine for the shipped configurations, beyond fp32 for cfg4's 20 g
+    object once its object-dynamics rows are softened (measured on the B200: NaN status for every instance)."""
+    import copy
+    from upright_b200.problem_io import fp32_conditioning_estimate
+    demo, _ = problem_io.load_fixture("cfg2_thing_demo")
+    obst, _ = problem_io.load_fixture("cfg4_thing_obstacles2")
+    assert 1e4 < fp32_conditioning_estimate(demo) < 1e7
+    assert fp32_conditioning_estimate(obst) == 1.0            # slacks off: normalised hard rows
+    soft = copy.deepcopy(obst)
+    soft.slacks.enabled = 1
+    assert fp32_conditioning_estimate(soft) > 1e8
+    heavy = np.tile(np.array(list(demo.body_params[0])), (3, 1, 1))
+    assert fp32_conditioning_estimate(soft, heavy) == pytest.approx(fp32_conditioning_estimate(demo))

@@ -821,7 +821,12 @@ int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(UB_E_NO_DEVICE, "no CUDA device: upright_b200 has no CPU fallback");
-    ub_problem* p = new ub_problem();
+    // owned until every allocation below has succeeded: an early return must not leak device memory
+    struct Guard {
+        ub_problem* p;
+        ~Guard() { if (p) ub_problem_destroy(p); }
+    } guard{new ub_problem()};
+    ub_problem* p = guard.p;
     p->desc = *desc;
     convert_problem(*desc, p->hf);
     convert_problem(*desc, p->hd);
@@ -837,6 +842,7 @@ int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
     UB_CUDA(cudaMemcpy(p->dd, &p->hd, sizeof(p->hd), cudaMemcpyHostToDevice));
     UB_CUDA(cudaEventCreate(&p->ev0));
     UB_CUDA(cudaEventCreate(&p->ev1));
+    guard.p = nullptr;
     *out = p;
     return UB_OK;
 }

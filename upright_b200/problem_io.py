@@ -76,3 +76,22 @@ FIXTURES = {
     "cfg4_thing_obstacles2": "upright_b200_cfg/config/thing_obstacles2.yaml",
     "cfg5_thing_robust8": "upright_b200_cfg/config/thing_robust8.yaml",
 }
+
+
+def fp32_conditioning_estimate(desc, body_params=None):
+    """Rough ratio between the largest and smallest curvature the force block of a stage matrix sees when the
+    object-dynamics rows are SOFT: the rows are divided by the body mass (contact_constraints.h:84-100) and by
+    sqrt(6 nb) (balancing_constraints.cpp:144-151) and penalised with Z directly, against a force weight of
+    dt * force_weight (floored by the input regularisation).  Above ~1e7 (1 / fp32 epsilon) the fp32 factorisation
+    of the kernels cannot be trusted: use the fp64 kernels or UB_RESCUE_F64.  1.0 when the
+    rows are hard (normalised proximal weights) or balancing is off."""
+    import numpy as np
+    if not (desc.balancing_enabled and desc.nb > 0 and desc.slacks.enabled and desc.slacks.poly_ineq):
+        return 1.0
+    if body_params is None:
+        masses = np.array([desc.body_params[b][0] for b in range(desc.nb)])
+    else:
+        masses = np.asarray(body_params, dtype=float).reshape(-1, desc.nb, 10)[:, :, 0].ravel()
+    Z = desc.slacks.upper_L2_penalty if desc.slacks.upper_L2_penalty > 0 else 100.0
+    floor = max(desc.dt * desc.force_weight, desc.reg_input, 1e-300)
+    return float(Z / (6.0 * desc.nb * masses.min() ** 2) / floor)
