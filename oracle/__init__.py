@@ -144,3 +144,14 @@ def qp_step(desc, target, X, U, body_params=None):
     lib().oracle_qp_step(C.byref(desc), _p(_f64(target)), _p(_f64(body_params)), _p(_f64(X)), _p(_f64(U)), _p(dX),
                          _p(dU), _p(info))
     return dX, dU, dict(iters=int(info[0]), converged=bool(info[1]), decrement=info[2], hard_infeas=info[3])
+
+
+def qp_step_precision(desc, target, X, U, mode, body_params=None):
+    """QP step of the first SQP iteration in a chosen arithmetic (precision study, tools/precision_lab.py):
+    mode 0 = fp64, 1 = fp32 throughout (the kernels' arithmetic), 2 = fp32 Newton matrices / factors / direction with
+    the iterate, slack records and residuals in fp64."""
+    d = dims(desc)
+    dX, dU, info = np.zeros((desc.N + 1, d["nx"])), np.zeros((desc.N, d["nu"])), np.zeros(5)
+    lib().oracle_qp_step_precision(C.byref(desc), _p(_f64(target)), _p(_f64(body_params)), _p(_f64(X)), _p(_f64(U)),
+                                   C.c_int32(int(mode)), _p(dX), _p(dU), _p(info))
+    return dict(dX=dX, dU=dU, iters=int(info[0]), converged=bool(info[1]), failed=int(info[2]), mu=info[3], rd=info[4])

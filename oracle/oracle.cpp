@@ -1343,6 +1343,377 @@ static void solve_one(const ub_problem_desc_t& P, const double* x0, const double
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Precision study (test infrastructure, tools/precision_lab.py): the interior-point iteration of solve_qp_ipm with
+// the Newton matrices, their Riccati factorisation and the direction in type F, and the iterate, the slack records
+// and every residual in type R.  <double, double> reproduces solve_qp_ipm; <float, float> is the arithmetic of the
+// fp32 kernels (same method, dense recursion instead of their blocked one); <float, double> is the
+// mixed-precision refinement proposed in DESIGN.md section 9.
+template <typename R>
+struct RowT {
+    int idx = -1;
+    std::vector<R> a;
+    R c = 0, lb = 0, ub = 0, rho = 0, lambda = 0;
+    bool hard = false, eq = false, on[2] = {false, false};
+    R t[2] = {0, 0}, lam[2] = {0, 0}, dt[2] = {0, 0}, dl[2] = {0, 0};
+};
+template <typename R>
+struct StageT {
+    int nz = 0, nu = 0;
+    std::vector<R> H, g, b;
+    std::vector<RowT<R>> rows;
+};
+template <typename R>
+static inline R row_value_t(const RowT<R>& r, const R* z) {
+    if (r.idx >= 0) return r.c + z[r.idx];
+    R v = r.c;
+    for (size_t j = 0; j < r.a.size(); ++j) v += r.a[j] * z[j];
+    return v;
+}
+template <typename R, typename V>
+static inline R row_dot_t(const RowT<R>& r, const V* d) {
+    if (r.idx >= 0) return R(d[r.idx]);
+    R v = 0;
+    for (size_t j = 0; j < r.a.size(); ++j) v += r.a[j] * R(d[j]);
+    return v;
+}
+
+template <typename F>
+struct RiccatiT {
+    // The recursion in the form the kernels use (ub_solver.cuh: stage_factor_blocked / partial_cholesky): partial
+    // Cholesky of the first nu columns of the stage matrix M_k + [B A]' P_{k+1} [B A]; the trailing block it leaves
+    // is the Schur complement P_k (symmetric by construction), pivots floored at reg_input.
+    int nx = 0, nu = 0, N = 0;
+    F pivot_floor = 0;
+    std::vector<F> A, B;                 // nx x nx, nx x nu
+    std::vector<std::vector<F>> L;       // per stage: nz x nu, column j = column j of the factor (rows j..nz-1)
+    std::vector<F> P;                    // running cost-to-go Hessian, nx x nx
+    bool factor(const std::vector<std::vector<F>>& M) {
+        const int nz = nu + nx;
+        L.assign(N, {});
+        P = M[N];
+        std::vector<F> T(size_t(nx) * nz);
+        for (int i = 0; i < nx; ++i) {
+            for (int j = 0; j < nu; ++j) T[i * nz + j] = B[i * nu + j];
+            for (int j = 0; j < nx; ++j) T[i * nz + nu + j] = A[i * nx + j];
+        }
+        for (int k = N - 1; k >= 0; --k) {
+            std::vector<F> Mk = M[k];
+            std::vector<F> PT(size_t(nx) * nz, F(0));
+            for (int i = 0; i < nx; ++i)
+                for (int l = 0; l < nx; ++l) {
+                    const F pv = P[i * nx + l];
+                    if (pv == F(0)) continue;
+                    for (int j = 0; j < nz; ++j) PT[i * nz + j] += pv * T[l * nz + j];
+                }
+            for (int l = 0; l < nx; ++l)
+                for (int i = 0; i < nz; ++i) {
+                    const F tv = T[l * nz + i];
+                    if (tv == F(0)) continue;
+                    for (int j = 0; j <= i; ++j) Mk[i * nz + j] += tv * PT[l * nz + j];   // lower triangle
+                }
+            L[k].assign(size_t(nz) * nu, F(0));
+            for (int j = 0; j < nu; ++j) {
+                F d = Mk[j * nz + j];
+                if (d != d) return false;
+                if (!(d > pivot_floor)) {
+                    if (!(pivot_floor > F(0))) return false;
+                    d = pivot_floor;
+                }
+                const F inv = F(1) / std::sqrt(d);
+                L[k][j * nu + j] = std::sqrt(d);
+                for (int i = j + 1; i < nz; ++i) L[k][i * nu + j] = Mk[i * nz + j] * inv;
+                for (int i = j + 1; i < nz; ++i) {
+                    const F lij = L[k][i * nu + j];
+                    for (int l = j + 1; l <= i; ++l) Mk[i * nz + l] -= lij * L[k][l * nu + j];
+                }
+            }
+            for (int i = 0; i < nx; ++i)
+                for (int j = 0; j <= i; ++j) P[i * nx + j] = P[j * nx + i] = Mk[(nu + i) * nz + nu + j];
+        }
+        return true;
+    }
+    void solve(const std::vector<std::vector<F>>& grad, std::vector<std::vector<F>>& dir) const {
+        std::vector<std::vector<F>> w(N);
+        std::vector<F> p = grad[N];
+        for (int k = N - 1; k >= 0; --k) {
+            std::vector<F> m = grad[k];
+            for (int l = 0; l < nx; ++l) {
+                for (int j = 0; j < nu; ++j) m[j] += B[l * nu + j] * p[l];
+                for (int j = 0; j < nx; ++j) m[nu + j] += A[l * nx + j] * p[l];
+            }
+            w[k].assign(nu, F(0));
+            for (int i = 0; i < nu; ++i) {          // L_uu w = m_u
+                F s = m[i];
+                for (int j = 0; j < i; ++j) s -= L[k][i * nu + j] * w[k][j];
+                w[k][i] = s / L[k][i * nu + i];
+            }
+            for (int i = 0; i < nx; ++i) {          // p = m_x - L_xu w
+                F s = m[nu + i];
+                for (int j = 0; j < nu; ++j) s -= L[k][(nu + i) * nu + j] * w[k][j];
+                p[i] = s;
+            }
+        }
+        dir.assign(N + 1, {});
+        std::vector<F> dx(nx, F(0)), dxn(nx);
+        for (int k = 0; k < N; ++k) {
+            dir[k].assign(nu + nx, F(0));
+            std::vector<F> rhs(nu);
+            for (int j = 0; j < nu; ++j) {          // s = w + L_xu' dx
+                F s = w[k][j];
+                for (int i = 0; i < nx; ++i) s += L[k][(nu + i) * nu + j] * dx[i];
+                rhs[j] = s;
+            }
+            for (int j = nu - 1; j >= 0; --j) {     // du = - L_uu^-T s
+                F s = -rhs[j];
+                for (int i = j + 1; i < nu; ++i) s -= L[k][i * nu + j] * dir[k][i];
+                dir[k][j] = s / L[k][j * nu + j];
+            }
+            for (int i = 0; i < nx; ++i) dir[k][nu + i] = dx[i];
+            for (int i = 0; i < nx; ++i) {
+                F v = 0;
+                for (int j = 0; j < nx; ++j) v += A[i * nx + j] * dx[j];
+                for (int j = 0; j < nu; ++j) v += B[i * nu + j] * dir[k][j];
+                dxn[i] = v;
+            }
+            dx = dxn;
+        }
+        dir[N] = dx;
+    }
+};
+
+// info: {iterations, converged, factorisation failed (iteration index + 1, else 0), last mu, last max slack residual}
+template <typename F, typename R>
+static void solve_qp_ipm_precision(const ub_problem_desc_t& P, const Workspace& W, std::vector<std::vector<double>>& zout,
+                                   double* info, int extra = 0) {
+    int extra_left = extra;
+    const Dims& D = W.D;
+    const int nx = D.nx, nu = D.nu, N = D.N;
+    std::vector<StageT<R>> st(N + 1);
+    for (int k = 0; k <= N; ++k) {
+        const Stage& s = W.st[k];
+        StageT<R>& q = st[k];
+        q.nz = s.nz;
+        q.nu = s.nu;
+        q.H.assign(s.H.d.begin(), s.H.d.end());
+        q.g.assign(s.g.begin(), s.g.end());
+        q.b.assign(s.b.begin(), s.b.end());
+        for (const Row& r : s.rows) {
+            RowT<R> t;
+            t.idx = r.idx;
+            t.a.assign(r.a.begin(), r.a.end());
+            t.c = R(r.c);
+            t.eq = !(r.lb < r.ub);
+            t.lb = R(std::isfinite(r.lb) ? r.lb : 0.0);
+            t.ub = R(std::isfinite(r.ub) ? r.ub : 0.0);
+            t.on[0] = !t.eq && std::isfinite(r.lb);
+            t.on[1] = !t.eq && std::isfinite(r.ub);
+            t.rho = R(r.rho);
+            t.lambda = R(r.lambda);
+            t.hard = r.hard;
+            q.rows.push_back(t);
+        }
+    }
+    RiccatiT<F> ric;
+    ric.nx = nx; ric.nu = nu; ric.N = N;
+    ric.pivot_floor = F(P.reg_input);
+    ric.A.assign(W.A.d.begin(), W.A.d.end());
+    ric.B.assign(W.B.d.begin(), W.B.d.end());
+    std::vector<std::vector<R>> z(N + 1);
+    for (int k = 0; k <= N; ++k) z[k].assign(st[k].nz, R(0));
+    for (int k = 0; k < N; ++k)
+        for (int i = 0; i < nx; ++i) {
+            R v = st[k].b[i];
+            for (int j = 0; j < nx; ++j) v += R(W.A(i, j)) * z[k][nu + j];
+            z[k + 1][st[k + 1].nu + i] = v;
+        }
+    const R sgn[2] = {R(1), R(-1)};
+    auto side_d = [](const RowT<R>& r, int s, R val) { return s == 0 ? val - r.lb : r.ub - val; };
+    auto side_eps = [](const RowT<R>& r) { return r.hard ? R(1.0e-6) : R(1) / r.rho; };
+    long nsides = 0;
+    for (int k = 0; k <= N; ++k)
+        for (RowT<R>& r : st[k].rows) {
+            const R val = row_value_t(r, z[k].data());
+            for (int s = 0; s < 2; ++s) {
+                if (!r.on[s]) continue;
+                r.t[s] = std::max(side_d(r, s, val), R(P.qp_thr0));
+                r.lam[s] = R(P.qp_mu0) / r.t[s];
+                ++nsides;
+            }
+        }
+    std::vector<std::vector<F>> M(N + 1), grad(N + 1), dz;
+    std::vector<std::vector<R>> rg(N + 1);
+    R last_alpha = 0, last_step = std::numeric_limits<R>::infinity(), mu = 0, rd_max = 0;
+    int iters = 0, failed = 0;
+    bool converged = false;
+    for (int it = 0; it < P.qp_iter_max; ++it) {
+        mu = 0;
+        rd_max = 0;
+        R pinf = 0;
+        for (int k = 0; k <= N; ++k) {
+            StageT<R>& s = st[k];
+            const int nz = s.nz;
+            M[k].assign(s.H.begin(), s.H.end());
+            rg[k].assign(nz, R(0));
+            for (int i = 0; i < nz; ++i) {
+                R v = s.g[i];
+                for (int j = 0; j < nz; ++j) v += s.H[i * nz + j] * z[k][j];
+                rg[k][i] = v;
+            }
+            auto add_outer = [&](const RowT<R>& r, R w) {
+                if (r.idx >= 0) {
+                    M[k][r.idx * nz + r.idx] += F(w);
+                    return;
+                }
+                for (int i = 0; i < nz; ++i) {
+                    if (r.a[i] == R(0)) continue;
+                    const F wi = F(w) * F(r.a[i]);
+                    for (int j = 0; j < nz; ++j) M[k][i * nz + j] += wi * F(r.a[j]);
+                }
+            };
+            auto add_vec = [&](const RowT<R>& r, R w) {
+                if (r.idx >= 0) {
+                    rg[k][r.idx] += w;
+                    return;
+                }
+                for (int j = 0; j < nz; ++j) rg[k][j] += w * r.a[j];
+            };
+            for (RowT<R>& r : s.rows) {
+                const R val = row_value_t(r, z[k].data());
+                if (r.eq) {
+                    const R e = val - r.lb;
+                    if (r.rho <= R(0)) continue;
+                    add_outer(r, r.rho);
+                    add_vec(r, r.rho * e + r.lambda);
+                    if (r.hard) pinf = std::max(pinf, R(std::fabs(e)));
+                    continue;
+                }
+                const R eps = side_eps(r);
+                for (int sd = 0; sd < 2; ++sd) {
+                    if (!r.on[sd]) continue;
+                    const R rd = side_d(r, sd, val) + eps * r.lam[sd] - r.t[sd];
+                    rd_max = std::max(rd_max, R(std::fabs(rd)));
+                    mu += r.t[sd] * r.lam[sd];
+                    add_outer(r, r.lam[sd] / (r.t[sd] + eps * r.lam[sd]));
+                    add_vec(r, -sgn[sd] * r.lam[sd]);
+                }
+            }
+        }
+        mu = nsides > 0 ? mu / R(nsides) : R(0);
+        if (it > 0 && mu <= R(2.0 * P.qp_mu_target) && rd_max <= R(P.qp_tol) && last_alpha >= R(0.5) &&
+            (pinf <= R(P.qp_tol) || last_step <= R(P.qp_tol))) {
+            converged = true;
+            // `extra` further Newton iterations on the exact residual: what an inexact (fp32) direction leaves of the
+            // stationarity residual contracts by the accuracy of the factorisation per iteration
+            if (extra_left-- <= 0) break;
+        }
+        iters = it + 1;
+        if (!ric.factor(M)) {
+            failed = it + 1;
+            break;
+        }
+        auto solve_with = [&](bool corrector, R target) {
+            for (int k = 0; k <= N; ++k) {
+                StageT<R>& s = st[k];
+                std::vector<R> gk = rg[k];
+                for (RowT<R>& r : s.rows) {
+                    if (r.eq) continue;
+                    const R val = row_value_t(r, z[k].data());
+                    const R eps = side_eps(r);
+                    for (int sd = 0; sd < 2; ++sd) {
+                        if (!r.on[sd]) continue;
+                        const R rd = side_d(r, sd, val) + eps * r.lam[sd] - r.t[sd];
+                        R rc = r.t[sd] * r.lam[sd] - target;
+                        if (corrector) rc += r.dt[sd] * r.dl[sd];
+                        const R w = sgn[sd] * (rc + r.lam[sd] * rd) / (r.t[sd] + eps * r.lam[sd]);
+                        if (r.idx >= 0) gk[r.idx] += w;
+                        else for (int j = 0; j < s.nz; ++j) gk[j] += w * r.a[j];
+                    }
+                }
+                grad[k].assign(gk.begin(), gk.end());
+            }
+            ric.solve(grad, dz);
+            for (int k = 0; k <= N; ++k)
+                for (RowT<R>& r : st[k].rows) {
+                    if (r.eq) continue;
+                    const R val = row_value_t(r, z[k].data());
+                    const R eps = side_eps(r);
+                    const R adz = row_dot_t(r, dz[k].data());
+                    for (int sd = 0; sd < 2; ++sd) {
+                        if (!r.on[sd]) continue;
+                        const R rd = side_d(r, sd, val) + eps * r.lam[sd] - r.t[sd];
+                        R rc = r.t[sd] * r.lam[sd] - target;
+                        if (corrector) rc += r.dt[sd] * r.dl[sd];
+                        const R den = r.t[sd] + eps * r.lam[sd];
+                        const R dl = -(rc + r.lam[sd] * rd) / den - (r.lam[sd] / den) * sgn[sd] * adz;
+                        r.dl[sd] = dl;
+                        r.dt[sd] = sgn[sd] * adz + eps * dl + rd;
+                    }
+                }
+        };
+        auto max_step = [&]() {
+            R a = 1;
+            for (int k = 0; k <= N; ++k)
+                for (const RowT<R>& r : st[k].rows) {
+                    if (r.eq) continue;
+                    for (int sd = 0; sd < 2; ++sd) {
+                        if (!r.on[sd]) continue;
+                        if (r.dt[sd] < R(0)) a = std::min(a, -r.t[sd] / r.dt[sd]);
+                        if (r.dl[sd] < R(0)) a = std::min(a, -r.lam[sd] / r.dl[sd]);
+                    }
+                }
+            return a;
+        };
+        for (int k = 0; k <= N; ++k)
+            for (RowT<R>& r : st[k].rows) r.dt[0] = r.dt[1] = r.dl[0] = r.dl[1] = R(0);
+        if (nsides > 0) {
+            solve_with(false, R(0));
+            const R a_aff = max_step();
+            R mu_aff = 0;
+            for (int k = 0; k <= N; ++k)
+                for (const RowT<R>& r : st[k].rows) {
+                    if (r.eq) continue;
+                    for (int sd = 0; sd < 2; ++sd)
+                        if (r.on[sd]) mu_aff += (r.t[sd] + a_aff * r.dt[sd]) * (r.lam[sd] + a_aff * r.dl[sd]);
+                }
+            mu_aff /= R(nsides);
+            const R ratio = mu_aff / mu;
+            solve_with(true, std::max(ratio * ratio * ratio * mu, R(P.qp_mu_target)));
+        } else {
+            solve_with(false, R(0));
+        }
+        const R alpha = nsides > 0 ? std::min(R(1), R(0.995) * max_step()) : R(1);
+        last_step = 0;
+        for (int k = 0; k <= N; ++k) {
+            for (int i = 0; i < st[k].nz; ++i) {
+                const R step = alpha * R(dz[k][i]);
+                z[k][i] += step;
+                last_step = std::max(last_step, R(std::fabs(step)));
+            }
+            for (RowT<R>& r : st[k].rows) {
+                if (r.eq) {
+                    if (r.hard && r.rho > R(0)) r.lambda += r.rho * (row_value_t(r, z[k].data()) - r.lb);
+                    continue;
+                }
+                for (int sd = 0; sd < 2; ++sd) {
+                    if (!r.on[sd]) continue;
+                    r.t[sd] += alpha * r.dt[sd];
+                    r.lam[sd] += alpha * r.dl[sd];
+                }
+            }
+        }
+        last_alpha = alpha;
+        if (!(last_step < std::numeric_limits<R>::infinity())) {   // non-finite step
+            failed = it + 1;
+            break;
+        }
+    }
+    zout.assign(N + 1, {});
+    for (int k = 0; k <= N; ++k) zout[k].assign(z[k].begin(), z[k].end());
+    info[0] = iters; info[1] = converged; info[2] = failed; info[3] = double(mu); info[4] = double(rd_max);
+}
+
 }  // namespace orc
 
 // ---------------------------------------------------------------------------
@@ -1494,6 +1865,31 @@ int oracle_qp_step(const ub_problem_desc_t* P, const double* target, const doubl
         info[0] = qr.iters; info[1] = qr.converged; info[2] = qr.decrement; info[3] = qr.hard_infeas;
     }
     return qr.iters;
+}
+
+
+// Precision study entry (tools/precision_lab.py): QP step of the first SQP iteration around (X, U) with
+// mode 0 = <double, double>, 1 = <float, float> (the fp32 kernels' arithmetic), 2 = <float factors, double iterate>.
+// dX [N+1, nx], dU [N, nu]; info[5] as solve_qp_ipm_precision.
+int oracle_qp_step_precision(const ub_problem_desc_t* P, const double* target, const double* body_params,
+                             const double* X, const double* U, int32_t mode, double* dX, double* dU, double* info) {
+    orc::Workspace W;
+    W.D = orc::make_dims(*P);
+    orc::discrete_dynamics(*P, W.D, W.A, W.B);
+    orc::build_qp(*P, W, body_params ? body_params : &P->body_params[0][0], target, X, U);
+    std::vector<std::vector<double>> z;
+    const int extra = mode / 10;   // tens digit: Newton iterations run after the convergence test has passed
+    mode %= 10;
+    if (mode == 0) orc::solve_qp_ipm_precision<double, double>(*P, W, z, info, extra);
+    else if (mode == 1) orc::solve_qp_ipm_precision<float, float>(*P, W, z, info, extra);
+    else orc::solve_qp_ipm_precision<float, double>(*P, W, z, info, extra);
+    for (int k = 0; k <= W.D.N; ++k) {
+        const int xo = W.st[k].nu;
+        for (int i = 0; i < W.D.nx; ++i) dX[size_t(k) * W.D.nx + i] = z[k][xo + i];
+        if (k < W.D.N)
+            for (int i = 0; i < W.D.nu; ++i) dU[size_t(k) * W.D.nu + i] = z[k][i];
+    }
+    return 0;
 }
 
 }  // extern "C"

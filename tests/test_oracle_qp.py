@@ -417,3 +417,24 @@ def test_projectile_constraint_shapes_the_plan():
     plain.projectile_enabled = 0
     ref = oracle.solve_batch(plain, x, target, X=Xw.copy(), U=Uw.copy(), warm=True)
     assert np.abs(ref["X"] - off["X"]).max() < 1e-6 and np.abs(ref["U"] - off["U"]).max() < 1e-5
+
+
+def test_precision_study_modes():
+    """oracle.qp_step_precision (tools/precision_lab.py): the fp64 mode is the oracle's interior-point step computed
+    with the kernels' form of the Riccati recursion (partial Cholesky + Schur complement) instead of the dense gain
+    recursion — same step; the fp32 mode stays within the kernels' stated tolerance; fp32 factors with an fp64
+    iterate come closer."""
+    import oracle
+    desc, meta = problem_io.load_fixture("cfg2_thing_demo")
+    x0 = np.array(meta["x0"], dtype=float)
+    target = np.tile(oracle.fk(desc, x0)["r"] + [0.2, 0.1, 0.1], (desc.N + 1, 1))
+    X, U = np.tile(x0, (desc.N + 1, 1)), np.zeros((desc.N, desc.nu))
+    dX, dU, info = oracle.qp_step(desc, target, X, U)
+    r64, r32, rmx = (oracle.qp_step_precision(desc, target, X, U, m) for m in (0, 1, 2))
+    assert r64["converged"] and r64["iters"] == info["iters"]
+    assert np.abs(r64["dX"] - dX).max() < 1e-9 and np.abs(r64["dU"] - dU).max() < 1e-8
+    rx = np.array(desc.state_ub[:27]) - np.array(desc.state_lb[:27])
+    e32 = (np.abs(r32["dX"] - dX) / rx).max()
+    emx = (np.abs(rmx["dX"] - dX) / rx).max()
+    assert r32["converged"] and rmx["converged"] and r32["failed"] == 0
+    assert e32 < 1e-2 and emx < 1e-4 and emx <= e32
