@@ -1486,7 +1486,7 @@ struct RiccatiT {
 // info: {iterations, converged, factorisation failed (iteration index + 1, else 0), last mu, last max slack residual}
 template <typename F, typename R>
 static void solve_qp_ipm_precision(const ub_problem_desc_t& P, const Workspace& W, std::vector<std::vector<double>>& zout,
-                                   double* info, int extra = 0) {
+                                   double* info, int extra = 0, double mu_factor = 2.0) {
     int extra_left = extra;
     const Dims& D = W.D;
     const int nx = D.nx, nu = D.nu, N = D.N;
@@ -1601,7 +1601,7 @@ static void solve_qp_ipm_precision(const ub_problem_desc_t& P, const Workspace& 
             }
         }
         mu = nsides > 0 ? mu / R(nsides) : R(0);
-        if (it > 0 && mu <= R(2.0 * P.qp_mu_target) && rd_max <= R(P.qp_tol) && last_alpha >= R(0.5) &&
+        if (it > 0 && mu <= R(mu_factor * P.qp_mu_target) && rd_max <= R(P.qp_tol) && last_alpha >= R(0.5) &&
             (pinf <= R(P.qp_tol) || last_step <= R(P.qp_tol))) {
             converged = true;
             // `extra` further Newton iterations on the exact residual: what an inexact (fp32) direction leaves of the
@@ -1878,11 +1878,15 @@ int oracle_qp_step_precision(const ub_problem_desc_t* P, const double* target, c
     orc::discrete_dynamics(*P, W.D, W.A, W.B);
     orc::build_qp(*P, W, body_params ? body_params : &P->body_params[0][0], target, X, U);
     std::vector<std::vector<double>> z;
-    const int extra = mode / 10;   // tens digit: Newton iterations run after the convergence test has passed
+    // hundreds digit: acceptance threshold on the complementarity, mu <= f * mu_target with f = 2 (the specification),
+    // 1.2 or 1.05; tens digit: Newton iterations run after the convergence test has passed
+    const double factors[3] = {2.0, 1.2, 1.05};
+    const double f = factors[std::min(2, mode / 100)];
+    const int extra = (mode / 10) % 10;
     mode %= 10;
-    if (mode == 0) orc::solve_qp_ipm_precision<double, double>(*P, W, z, info, extra);
-    else if (mode == 1) orc::solve_qp_ipm_precision<float, float>(*P, W, z, info, extra);
-    else orc::solve_qp_ipm_precision<float, double>(*P, W, z, info, extra);
+    if (mode == 0) orc::solve_qp_ipm_precision<double, double>(*P, W, z, info, extra, f);
+    else if (mode == 1) orc::solve_qp_ipm_precision<float, float>(*P, W, z, info, extra, f);
+    else orc::solve_qp_ipm_precision<float, double>(*P, W, z, info, extra, f);
     for (int k = 0; k <= W.D.N; ++k) {
         const int xo = W.st[k].nu;
         for (int i = 0; i < W.D.nx; ++i) dX[size_t(k) * W.D.nx + i] = z[k][xo + i];

@@ -47,7 +47,9 @@ for name, desc, meta in cases():
     b = workload.sample_batch(fixture, desc, meta, B, 1234, ee, margin_fn=mg)
     rx, ru = ranges(desc)
     MODES = ((0, 'fp64'), (1, 'fp32'), (2, 'fp32 factors + fp64 it.'), (10, 'fp64, +1 iteration'), (11, 'fp32, +1 iteration'),
-             (12, 'mixed, +1 iteration'), (20, 'fp64, +2 iterations'), (22, 'mixed, +2 iterations'))   # compared with fp64 at the same count
+             (12, 'mixed, +1 iteration'), (20, 'fp64, +2 iterations'), (22, 'mixed, +2 iterations'),
+             (100, 'fp64, mu <= 1.2 target'), (101, 'fp32, mu <= 1.2 target'), (200, 'fp64, mu <= 1.05 target'),
+             (201, 'fp32, mu <= 1.05 target'), (202, 'mixed, mu <= 1.05 target'))   # compared with fp64 of the same variant
     res = {m: [] for m, _ in MODES}
     for i in range(B):
         X = np.tile(b["x0"][i], (desc.N + 1, 1))
