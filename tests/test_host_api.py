@@ -397,3 +397,75 @@ def test_closed_loop_solves_the_waiters_problem_on_oracle_engine():
     xs_free = closed_loop(free)
     assert np.linalg.norm(oracle.fk(desc, xs_free[-1])["r"] - goal) < 5e-3
     assert missing_force(xs_free) > 0.1 * at_rest                       # measured 1.07
+
+
+def _oracle_closed_loop(cfg, x0, goal, duration, replan=0.05):
+    """mpc_sim.py loop on the CPU oracle (see test_closed_loop_solves_the_waiters_problem_on_oracle_engine)."""
+    from _util import OracleEngine
+    from upright_b200.manager import BatchedControllerManager, _RecedingHorizon
+    st = settings.ControllerSettings(cfg, x0=x0[0])
+    d = st.to_desc()
+    mgr = object.__new__(BatchedControllerManager)
+    mgr.settings, mgr.desc, mgr.engine, mgr.B = st, d, OracleEngine(d), 1
+    mgr.core = _RecedingHorizon(mgr.engine, st, 1)
+    mgr.core.reset([TargetTrajectories([0.0], [np.r_[goal, 0, 0, 0, 1, 0]], [np.zeros(st.dims.u())])])
+    mgr.core.body_params = None
+    mgr.timestep, mgr.last_planning_time = replan, -np.inf
+    mgr.replanning_times, mgr.replanning_durations = [], []
+    return mgr.rollout_host(x0, duration, 0.01)["xs"][0]
+
+
+def test_closed_loop_keeps_friction_cones_on_oracle_engine():
+    """cfg3 (three stacked bodies, 16 friction contacts): along 4 s of closed loop there are contact forces inside
+    the friction pyramids that carry all three bodies at every simulated state (a linear programme on the
+    object-dynamics rows and the pyramid rows); planned without the balancing constraints there are none."""
+    import copy
+
+    import oracle
+    from scipy.optimize import linprog
+    desc, meta = problem_io.load_fixture("cfg3_thing_box_arch")
+    x0 = np.array(meta["x0"], dtype=float)[None]
+    goal = np.array(meta["r_ee0"]) + [-0.25, 0.5, 0.25]
+    nfc = desc.nf * desc.nc
+
+    def cone_gap(xs):
+        worst = 0.0
+        for x in xs[::20]:
+            lin = oracle.linearize(desc, x, np.zeros(desc.nq + nfc))
+            Df, g, F = lin["Df"], lin["g"], lin["Ffric"]
+            ne, one = Df.shape[0], np.ones((Df.shape[0], 1))
+            res = linprog(np.r_[np.zeros(nfc), 1.0],                       # min t: |Df f + g| <= t, F f >= 0
+                          A_ub=np.block([[Df, -one], [-Df, -one], [-F, np.zeros((F.shape[0], 1))]]),
+                          b_ub=np.r_[-g, g, np.zeros(F.shape[0])], bounds=[(-100, 100)] * nfc + [(0, None)])
+            assert res.status == 0
+            worst = max(worst, res.x[-1])
+        return worst
+
+    xs = _oracle_closed_loop(meta["controller_config"], x0, goal, 4.0)
+    assert np.linalg.norm(oracle.fk(desc, xs[-1])["r"] - goal) < 1e-2
+    assert cone_gap(xs) < 1e-3                                             # measured 0
+    free = copy.deepcopy(meta["controller_config"])
+    free["balancing"]["enabled"] = False
+    assert cone_gap(_oracle_closed_loop(free, x0, goal, 4.0)) > 0.05       # measured 0.11
+
+
+def test_closed_loop_avoids_obstacles_on_oracle_engine():
+    """cfg4 (hard sphere-distance rows): sent to a point behind an obstacle the closed loop keeps every collision
+    pair at its minimum distance and stops in front of it (a 2 s horizon does not plan around), where the same loop
+    with obstacles disabled drives through."""
+    import copy
+
+    import oracle
+    desc, meta = problem_io.load_fixture("cfg4_thing_obstacles2")
+    x0 = np.array(meta["x0"], dtype=float)[None]
+    goal = np.array(meta["r_ee0"]) + [1.9, -0.25, 0.0]
+    margin = lambda xs: min(oracle.linearize(desc, x, np.zeros(desc.nu))["hobs"].min() for x in xs[::5])  # noqa: E731
+    xs = _oracle_closed_loop(meta["controller_config"], x0, goal, 6.0)
+    d0 = np.linalg.norm(oracle.fk(desc, xs[0])["r"] - goal)
+    assert margin(xs) > -1e-3                                              # measured +0.011
+    assert np.linalg.norm(oracle.fk(desc, xs[-1])["r"] - goal) < 0.6 * d0  # it does approach
+    free = copy.deepcopy(meta["controller_config"])
+    free["obstacles"]["enabled"] = False
+    xs_free = _oracle_closed_loop(free, x0, goal, 6.0)
+    assert margin(xs_free) < -0.2                                          # measured -0.48
+    assert np.linalg.norm(oracle.fk(desc, xs_free[-1])["r"] - goal) < 1e-2
