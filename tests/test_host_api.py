@@ -457,3 +457,41 @@ def test_closed_loop_avoids_obstacles_on_oracle_engine():
     xs_free = _oracle_closed_loop(free, x0, goal, 6.0)
     assert margin(xs_free) < -0.2                                          # measured -0.48
     assert np.linalg.norm(oracle.fk(desc, xs_free[-1])["r"] - goal) < 1e-2
+
+
+def test_closed_loop_inertial_alignment_on_oracle_engine():
+    """Inertial alignment as the alternative to the balancing constraints (inertial_alignment.h:68-204): with the
+    five constraint rows the tray normal stays inside the alpha-pyramid around C_we'(a - g) along the whole closed
+    loop, with the Gauss-Newton cost alone it leans that way, with neither the rows are violated grossly."""
+    import copy
+
+    import oracle
+    desc, meta = problem_io.load_fixture("cfg2_thing_demo")
+    x0 = np.array(meta["x0"], dtype=float)[None]
+    goal = np.array(meta["r_ee0"]) + [-0.25, 0.5, 0.25]
+
+    def cfg(constraint, cost):
+        c = copy.deepcopy(meta["controller_config"])
+        c["balancing"]["enabled"] = False
+        c["inertial_alignment"] = {"cost_enabled": cost, "constraint_enabled": constraint, "use_angular_acceleration": False,
+                                   "align_with_fixed_vector": False, "cost_weight": 10, "contact_plane_normal": [0, 0, 1],
+                                   "com": [0, 0, 0], "alpha": 0.05}
+        return c
+
+    probe = settings.ControllerSettings(cfg(True, False), x0=x0[0]).to_desc()
+
+    def worst_row(xs):
+        w = np.inf
+        for x in xs[::5]:   # the five rows at state x = the constants of the QP rows of a trajectory resting at x
+            q = oracle.qp_dump(probe, np.tile(goal, (probe.N + 1, 1)), np.tile(x, (probe.N + 1, 1)), np.zeros((probe.N, 9)))[3]
+            w = min(w, q["c"][-5:].min())
+        return w
+
+    res = {}
+    for label, c in (("constraint", cfg(True, False)), ("cost", cfg(False, True)), ("neither", cfg(False, False))):
+        xs = _oracle_closed_loop(c, x0, goal, 5.0)
+        assert np.linalg.norm(oracle.fk(probe, xs[-1])["r"] - goal) < 5e-3
+        res[label] = worst_row(xs)
+    assert res["constraint"] > -0.02                     # measured -0.004 (soft rows)
+    assert res["neither"] < -1.0                         # measured -3.0
+    assert res["neither"] < res["cost"] < res["constraint"]   # measured -0.59
