@@ -19,7 +19,7 @@ _lib = None
 
 def build(force=False):
     so = _DIR / "liboracle.so"
-    srcs = [_DIR / n for n in ("oracle.cpp", "model.h", "smallmath.h")] + [_DIR.parent / "include" / "upright_b200.h"]
+    srcs = [_DIR / n for n in ("oracle.cpp", "model.h", "smallmath.h", "reduced_lab.h")] + [_DIR.parent / "include" / "upright_b200.h"]
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.check_call(["make", "-C", str(_DIR), "-s", "liboracle.so"])
     return so

@@ -33,6 +33,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <stdexcept>
 #include <thread>
 #include <vector>
 
@@ -418,6 +419,27 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
         const double* u = (k < N) ? U + size_t(k) * nu : zero_u.data();
         KnotLin& L = W.lin[k];
         linearize_knot(P, D, body_params, x, u, L);
+        if (const char* ne = std::getenv("ORACLE_LIN_NOISE")) {
+            // precision study only (tools/precision_lab2.py): perturb every block of the linearisation by noise x its
+            // largest magnitude — the size of the error an fp32 forward-kinematics pass leaves in it
+            const double noise = std::atof(ne);
+            static thread_local unsigned long long hs = 88172645463325252ull;
+            auto jiggle = [&](double* v, size_t n) {
+                double mx = 0;
+                for (size_t i = 0; i < n; ++i) mx = std::max(mx, std::fabs(v[i]));
+                for (size_t i = 0; i < n; ++i) {
+                    if (v[i] == 0.0) continue;
+                    hs ^= hs << 13; hs ^= hs >> 7; hs ^= hs << 17;
+                    v[i] += 2.0 * noise * mx * (double(hs >> 11) / double(1ull << 53) - 0.5);
+                }
+            };
+            jiggle(L.Jp.d.data(), L.Jp.d.size());
+            jiggle(L.r, 3);
+            jiggle(L.C.d.data(), L.C.d.size());
+            jiggle(L.g.data(), L.g.size());
+            jiggle(L.Jobs.d.data(), L.Jobs.d.size());
+            jiggle(L.hobs.data(), L.hobs.size());
+        }
         Stage& s = W.st[k];
         s.nu = (k < N) ? nu : 0;
         s.nz = s.nu + nx;
@@ -1714,6 +1736,8 @@ static void solve_qp_ipm_precision(const ub_problem_desc_t& P, const Workspace& 
     info[0] = iters; info[1] = converged; info[2] = failed; info[3] = double(mu); info[4] = double(rd_max);
 }
 
+#include "reduced_lab.h"
+
 }  // namespace orc
 
 // ---------------------------------------------------------------------------
@@ -1886,7 +1910,13 @@ int oracle_qp_step_precision(const ub_problem_desc_t* P, const double* target, c
     mode %= 10;
     if (mode == 0) orc::solve_qp_ipm_precision<double, double>(*P, W, z, info, extra, f);
     else if (mode == 1) orc::solve_qp_ipm_precision<float, float>(*P, W, z, info, extra, f);
-    else orc::solve_qp_ipm_precision<float, double>(*P, W, z, info, extra, f);
+    else if (mode == 2) orc::solve_qp_ipm_precision<float, double>(*P, W, z, info, extra, f);
+    // reduced stage (forces eliminated in range-space form, Riccati on [jerk; state]): oracle/reduced_lab.h
+    else if (mode == 3) orc::solve_qp_ipm_reduced<double, double, double, double>(*P, W, z, info, extra, f);
+    else if (mode == 4) orc::solve_qp_ipm_reduced<float, double, double, float>(*P, W, z, info, extra, f);
+    else if (mode == 5) orc::solve_qp_ipm_reduced<float, double, double, double>(*P, W, z, info, extra, f);
+    else if (mode == 6) orc::solve_qp_ipm_reduced<float, double, float, float>(*P, W, z, info, extra, f);
+    else orc::solve_qp_ipm_reduced<float, float, float, float>(*P, W, z, info, extra, f);
     for (int k = 0; k <= W.D.N; ++k) {
         const int xo = W.st[k].nu;
         for (int i = 0; i < W.D.nx; ++i) dX[size_t(k) * W.D.nx + i] = z[k][xo + i];
