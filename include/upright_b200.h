@@ -304,9 +304,10 @@ int ub_closed_loop(ub_problem_t* problem, int32_t B, const double* x0, const dou
  * solve, 1 stop after the first linearisation, 2 after the first QP). */
 int ub_set_option(ub_problem_t* problem, const char* key, int value);
 
-/* Per-instance workspace layout (offsets in elements) for tests that inspect
- * intermediate blocks; see upright_b200/engine.py LAYOUT_FIELDS. */
-int ub_workspace_layout(const ub_problem_t* problem, uint32_t flags, int32_t out[40]);
+/* Per-instance workspace layout for tests that inspect intermediate blocks: offsets in units of the kernels'
+ * matrix type (float; double with UB_COMPUTE_F64); blocks holding doubles take `rw` units per element.
+ * Field order: upright_b200/engine.py LAYOUT_FIELDS. */
+int ub_workspace_layout(const ub_problem_t* problem, uint32_t flags, int32_t out[80]);
 
 /* Device time of the last ub_solve_batch on this problem (CUDA events), ms.
  * Replaces getLastSolveTime() (controller_python_interface.h:27-29). */

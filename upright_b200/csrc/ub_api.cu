@@ -69,18 +69,22 @@ class WorkerPool {
             return;
         }
         std::unique_lock<std::mutex> call_lock(call_mutex_);   // one parallel region at a time
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            fn_ = &fn;
-            n_tasks_ = n_tasks;
-            next_.store(0);
-            pending_ = n_tasks;
-            ++epoch_;
-        }
+        std::unique_lock<std::mutex> lk(m_);
+        // A region is published only while nobody is inside run_tasks, and it ends only when everybody has left
+        // it again: a worker can therefore never claim a task index with the counters of another region.
+        done_cv_.wait(lk, [&] { return active_ == 0; });
+        fn_ = &fn;
+        n_tasks_ = n_tasks;
+        next_.store(0);
+        pending_ = n_tasks;
+        ++epoch_;
+        ++active_;   // the calling thread works too
+        lk.unlock();
         cv_.notify_all();
         run_tasks();
-        std::unique_lock<std::mutex> lk(m_);
-        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        lk.lock();
+        --active_;
+        done_cv_.wait(lk, [&] { return pending_ == 0 && active_ == 0; });
         fn_ = nullptr;
     }
 
@@ -113,8 +117,12 @@ class WorkerPool {
                 cv_.wait(lk, [&] { return stop_ || epoch_ != seen; });
                 if (stop_) return;
                 seen = epoch_;
+                if (fn_ == nullptr) continue;   // woke up after the region had already finished
+                ++active_;                      // entering is atomic with reading the region
             }
             run_tasks();
+            std::lock_guard<std::mutex> lk(m_);
+            if (--active_ == 0) done_cv_.notify_all();
         }
     }
     std::vector<std::thread> workers_;
@@ -122,7 +130,7 @@ class WorkerPool {
     std::condition_variable cv_, done_cv_;
     const std::function<void(int)>* fn_ = nullptr;
     std::atomic<int> next_{0};
-    int n_tasks_ = 0, pending_ = 0;
+    int n_tasks_ = 0, pending_ = 0, active_ = 0;
     unsigned long long epoch_ = 0;
     bool stop_ = false;
 };
@@ -269,6 +277,22 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
         P.eb_lo[c] = T(d.ee_box_lower[c]);
         P.eb_hi[c] = T(d.ee_box_upper[c]);
     }
+    // force block of the reduced stage: bodies that share a contact (body1 >= 0) are eliminated together
+    {
+        bool coupled = false;
+        for (int c = 0; c < P.nc; ++c) coupled = coupled || d.contacts[c].body1 >= 0;
+        P.ngrp = P.nb == 0 ? 0 : (coupled ? 1 : P.nb);
+        P.ng = P.nb == 0 ? 0 : (coupled ? 6 * P.nb : 6);
+        int n = 0;
+        for (int b = 0; b < P.nb; ++b) {
+            P.bc_start[b] = n;
+            for (int c = 0; c < P.nc; ++c) {
+                if (d.contacts[c].body2 == b) P.bc_list[n++] = 2 * c;
+                if (d.contacts[c].body1 == b) P.bc_list[n++] = 2 * c + 1;
+            }
+        }
+        for (int b = P.nb; b <= UB_MAX_BODIES; ++b) P.bc_start[b] = n;
+    }
     P.iacost = d.ia_cost_enabled ? 1 : 0;
     P.ia_w = T(d.ia_cost_weight);
     for (int i = 0; i < 6; ++i) P.ia_S[i] = T(d.ia_span[i]);
@@ -278,8 +302,8 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
 
 template <typename T>
 ub::Layout make_layout(const ub::DevProblem<T>& P) {
-    return ub::compute_layout(ub::LayoutDims{P.N, P.nq, P.nx, P.nu, P.neq, P.nfc, P.nterm, P.nrow, P.nobs, P.nb, int(sizeof(T)),
-                                             P.iacost ? 2 : 0, P.obsw, P.nxo});
+    return ub::compute_layout(ub::LayoutDims{P.N, P.nq, P.nx, P.nu, P.neq, P.nfc, P.nterm, P.nrow, P.nobs, P.nb, P.nc, P.nf,
+                                             int(sizeof(double) / sizeof(T)), P.ngrp, P.ng, P.iacost ? 2 : 0, P.obsw, P.nxo});
 }
 
 }  // namespace
@@ -311,88 +335,68 @@ namespace {
 
 template <typename T>
 struct Pick;
+#define UB_PICK_LAUNCHERS(T, SFX)                                                              \
+    static ub::LaunchFn<T> generic9() { return ub::launch_generic9_##SFX; }                    \
+    static ub::LaunchFn<T> generic6() { return ub::launch_generic6_##SFX; }                    \
+    static ub::LaunchFn<T> thing_1obj() { return ub::launch_thing_1obj_##SFX; }                \
+    static ub::LaunchFn<T> thing_obs12() { return ub::launch_thing_obs12_##SFX; }              \
+    static ub::LaunchFn<T> ur10_1obj() { return ub::launch_ur10_1obj_##SFX; }                  \
+    static ub::LaunchFn<T> thing_arch() { return ub::launch_thing_arch_##SFX; }                \
+    static ub::LaunchFn<T> thing_robust8() { return ub::launch_thing_robust8_##SFX; }
 template <>
 struct Pick<float> {
     static const ub::DevProblem<float>* dev(const ub_problem* p) { return p->df; }
     static const ub::DevProblem<float>& host(const ub_problem* p) { return p->hf; }
     static const ub::Layout& layout(const ub_problem* p) { return p->Lf; }
-    static ub::LaunchFn<float> generic() { return ub::launch_generic_f32; }
-    static ub::LaunchFn<float> generic_team() { return ub::launch_generic_team_f32; }
-    static ub::LaunchFn<float> thing_1obj() { return ub::launch_thing_1obj_f32; }
-    static ub::LaunchFn<float> thing_obs12() { return ub::launch_thing_obs12_f32; }
-    static ub::LaunchFn<float> ur10_1obj() { return ub::launch_ur10_1obj_f32; }
-    static ub::LaunchFn<float> thing_arch() { return ub::launch_thing_arch_f32; }
-    static ub::LaunchFn<float> thing_robust8() { return ub::launch_thing_robust8_f32; }
-    static ub::LaunchFn<float> thing_arch_team() { return ub::launch_thing_arch_team_f32; }
-    static ub::LaunchFn<float> thing_robust8_team() { return ub::launch_thing_robust8_team_f32; }
+    UB_PICK_LAUNCHERS(float, f32)
 };
 template <>
 struct Pick<double> {
     static const ub::DevProblem<double>* dev(const ub_problem* p) { return p->dd; }
     static const ub::DevProblem<double>& host(const ub_problem* p) { return p->hd; }
     static const ub::Layout& layout(const ub_problem* p) { return p->Ld; }
-    static ub::LaunchFn<double> generic() { return ub::launch_generic_f64; }
-    static ub::LaunchFn<double> generic_team() { return ub::launch_generic_team_f64; }
-    static ub::LaunchFn<double> thing_1obj() { return ub::launch_thing_1obj_f64; }
-    static ub::LaunchFn<double> thing_obs12() { return ub::launch_thing_obs12_f64; }
-    static ub::LaunchFn<double> ur10_1obj() { return ub::launch_ur10_1obj_f64; }
-    static ub::LaunchFn<double> thing_arch() { return ub::launch_thing_arch_f64; }
-    static ub::LaunchFn<double> thing_robust8() { return ub::launch_thing_robust8_f64; }
-    static ub::LaunchFn<double> thing_arch_team() { return ub::launch_thing_arch_team_f64; }
-    static ub::LaunchFn<double> thing_robust8_team() { return ub::launch_thing_robust8_team_f64; }
+    UB_PICK_LAUNCHERS(double, f64)
 };
 
-// Which kernel serves a problem: the instantiations specialised on the BASELINE dimensions (nq, nf, nc, nb), with a
-// team of UB_TEAM_WARPS warps per instance for the large stage matrices (cfg3, cfg5; UB_TEAM=0 keeps one warp), the
-// run-time-dimension kernel for everything else.
+// Which kernel serves a problem: the instantiations specialised on the BASELINE dimensions (nq, nf, nc, nb, pairs),
+// the run-time-dimension kernel of the robot (nq = 9 Thing, 6 fixed-base UR10) for everything else.  One warp per
+// instance in every case: the Riccati recursion runs on [jerk; state] only (ub_solver.cuh).
 template <typename T>
-ub::LaunchFn<T> select_kernel(const ub_problem* p, int* team_warps) {
+ub::LaunchFn<T> select_kernel(const ub_problem* p) {
     const ub::DevProblem<T>& H = Pick<T>::host(p);
-    *team_warps = 1;
-    const char* te = std::getenv("UB_TEAM");
-    const bool team = !(te && std::atoi(te) == 0);
-    // run-time dimensions: one warp per instance up to 64 stage variables, a team beyond
-    ub::LaunchFn<T> fn = Pick<T>::generic();
-    if (team && H.nz > 64) {
-        fn = Pick<T>::generic_team();
-        *team_warps = UB_TEAM_WARPS;
-    }
+    ub::LaunchFn<T> fn = H.nq == 9 ? Pick<T>::generic9() : Pick<T>::generic6();
     if (std::getenv("UB_FORCE_GENERIC") != nullptr) return fn;
-    if (!(H.balancing && H.N == 20 && !H.iacost && !H.iacon && H.ndyn == 0)) return fn;
-    const bool no_obs = H.nobs == 0;
-    auto one_warp = [&](ub::LaunchFn<T> f) {
-        fn = f;
-        *team_warps = 1;
-    };
-    if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) one_warp(Pick<T>::thing_1obj());
-    if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12 && !H.eebox) one_warp(Pick<T>::thing_obs12());
-    if (H.nq == 6 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) one_warp(Pick<T>::ur10_1obj());
-    if (H.nq == 9 && H.nf == 3 && H.nc == 16 && H.nb == 3 && no_obs) {
-        fn = team ? Pick<T>::thing_arch_team() : Pick<T>::thing_arch();
-        *team_warps = team ? UB_TEAM_WARPS : 1;
-    }
-    if (H.nq == 9 && H.nf == 1 && H.nc == 32 && H.nb == 8 && no_obs) {
-        fn = team ? Pick<T>::thing_robust8_team() : Pick<T>::thing_robust8();
-        *team_warps = team ? UB_TEAM_WARPS : 1;
-    }
+    if (!(H.balancing && H.N == 20 && !H.iacost && !H.iacon && H.ndyn == 0 && !H.eebox && H.nproj == 0)) return fn;
+    const bool no_obs = H.nobs == 0, per_body = H.ngrp == H.nb;
+    if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::thing_1obj();
+    if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12) fn = Pick<T>::thing_obs12();
+    if (H.nq == 6 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::ur10_1obj();
+    if (H.nq == 9 && H.nf == 3 && H.nc == 16 && H.nb == 3 && no_obs && !per_body) fn = Pick<T>::thing_arch();
+    if (H.nq == 9 && H.nf == 1 && H.nc == 32 && H.nb == 8 && no_obs && per_body) fn = Pick<T>::thing_robust8();
     return fn;
+}
+
+// shared memory of one CTA: the problem constants (F copy, and the double copy the product kernels use for
+// residuals and the linearisation) + one block per warp
+template <typename T>
+size_t problem_smem_bytes() {
+    const size_t f = (sizeof(ub::DevProblem<T>) + 15) / 16 * 16;
+    return sizeof(T) == 8 ? f : f + (sizeof(ub::DevProblem<double>) + 15) / 16 * 16;
 }
 
 // Launch geometry: warps per CTA — two CTAs per SM (the 128-register kernels allow 16 warps per SM), each taking
 // half of the SM's shared memory minus the 1 KB the driver reserves per CTA; at most 8 warps.
 template <typename T>
-int warps_per_cta(const ub_problem* p) {   // = instance teams per CTA
-    int tw = 1;
-    select_kernel<T>(p, &tw);
+int warps_per_cta(const ub_problem* p) {   // = instances per CTA
     const ub::Layout& L = Pick<T>::layout(p);
-    const size_t pbytes = (sizeof(ub::DevProblem<T>) + 15) / 16 * 16;
+    const size_t pbytes = problem_smem_bytes<T>();
     const size_t per_warp = size_t(L.s_total) * sizeof(T);
     const size_t cta_budget = size_t(p->max_smem_sm) / 2 - 1024;
     int wpc = cta_budget > pbytes ? int((cta_budget - pbytes) / per_warp) : 1;
-    if (wpc > 8 / tw) wpc = 8 / tw;
+    if (wpc > 8) wpc = 8;
     if (wpc < 1) wpc = 1;
     const char* env = std::getenv("UB_WARPS_PER_CTA");
-    if (env) wpc = std::max(1, std::min(8 / tw, std::atoi(env)));
+    if (env) wpc = std::max(1, std::min(8, std::atoi(env)));
     return wpc;
 }
 // Workspace slots of a batch of B: the persistent grid holds one slot per resident warp; the static test mode
@@ -411,7 +415,7 @@ int64_t workspace_bytes(const ub_problem* p, int B) {
 template <typename T>
 int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
     const ub::Layout& L = Pick<T>::layout(p);
-    const size_t pbytes = (sizeof(ub::DevProblem<T>) + 15) / 16 * 16;
+    const size_t pbytes = problem_smem_bytes<T>();
     const size_t per_warp = size_t(L.s_total) * sizeof(T);
     const int wpc = warps_per_cta<T>(p);
     const size_t smem = pbytes + per_warp * wpc;
@@ -429,9 +433,8 @@ int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
     A.n_slots = int(slots);
     const int grid = int((slots + wpc - 1) / wpc);
     const ub::DevProblem<T>& H = Pick<T>::host(p);
-    int tw = 1;
-    ub::LaunchFn<T> fn = select_kernel<T>(p, &tw);
-    UB_CUDA(fn(H, Pick<T>::dev(p), L, A, wpc, grid, smem, stream));
+    ub::LaunchFn<T> fn = select_kernel<T>(p);
+    UB_CUDA(fn(H, Pick<T>::dev(p), p->dd, L, A, wpc, grid, smem, stream));
     ++g_launches;
     return UB_OK;
 }
@@ -787,7 +790,8 @@ int64_t ub_launch_count(void) { return g_launches.load(); }
 
 int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
     if (!desc || !out) return fail(UB_E_INVALID, "null argument");
-    if (desc->nq < 1 || desc->nq > UB_MAX_JOINTS) return fail(UB_E_INVALID, "nq out of range");
+    if (desc->nq != 6 && desc->nq != 9)
+        return fail(UB_E_INVALID, "nq must be 6 (fixed-base UR10) or 9 (Thing): the kernels are instantiated for the reference's two robots");
     if (desc->nb < 0 || desc->nb > UB_MAX_BODIES || desc->nc < 0 || desc->nc > UB_MAX_CONTACTS)
         return fail(UB_E_INVALID, "too many bodies / contacts");
     if (desc->nf != 1 && desc->nf != 3) return fail(UB_E_INVALID, "nf must be 1 or 3");
@@ -795,9 +799,17 @@ int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
     if (desc->n_spheres > UB_MAX_SPHERES || desc->n_pairs > UB_MAX_PAIRS) return fail(UB_E_INVALID, "too many spheres / pairs");
     if (desc->n_dynamic_obstacles < 0 || desc->n_dynamic_obstacles > UB_MAX_DYNAMIC_OBSTACLES)
         return fail(UB_E_INVALID, "too many dynamic obstacles");
+    if (desc->n_spheres < 0 || desc->n_pairs < 0) return fail(UB_E_INVALID, "negative sphere / pair count");
     for (int s = 0; s < desc->n_spheres; ++s)
         if (desc->spheres[s].link < -1 - desc->n_dynamic_obstacles || desc->spheres[s].link > desc->nq)
             return fail(UB_E_INVALID, "sphere attached to an unknown link / dynamic obstacle");
+    for (int i = 0; i < desc->n_pairs; ++i)
+        if (desc->pairs[i].a < 0 || desc->pairs[i].a >= desc->n_spheres || desc->pairs[i].b < 0 || desc->pairs[i].b >= desc->n_spheres)
+            return fail(UB_E_INVALID, "collision pair names an unknown sphere");
+    for (int c = 0; c < desc->nc; ++c)
+        if (desc->contacts[c].body2 < 0 || desc->contacts[c].body2 >= desc->nb || desc->contacts[c].body1 < -1 ||
+            desc->contacts[c].body1 >= desc->nb)
+            return fail(UB_E_INVALID, "contact names an unknown body (body2 in [0, nb), body1 in [-1, nb))");
     if (desc->projectile_enabled) {
         if (!desc->obstacles_enabled || desc->n_dynamic_obstacles < 1)
             return fail(UB_E_INVALID, "projectile path constraint needs a dynamic obstacle (the projectile)");
@@ -874,7 +886,7 @@ int64_t ub_workspace_bytes(const ub_problem_t* p, int32_t B, uint32_t flags) {
 
 // Debug/testing aids (not part of the reference surface): option "stop_after"
 // (0 full solve, 1 after the first linearisation, 2 after the first QP) and the
-// per-problem workspace layout in elements: out[0..23] = Layout offsets, out[23] = total.
+// per-problem workspace layout in units of the kernel's F type (ub::Layout, field order of engine.LAYOUT_FIELDS).
 int ub_set_option(ub_problem_t* p, const char* key, int value) {
     if (!p || !key) return fail(UB_E_INVALID, "null argument");
     if (std::strcmp(key, "stop_after") == 0) {
@@ -901,11 +913,11 @@ int ub_set_option(ub_problem_t* p, const char* key, int value) {
     }
     return fail(UB_E_INVALID, std::string("unknown option ") + key);
 }
-int ub_workspace_layout(const ub_problem_t* p, uint32_t flags, int32_t out[40]) {
+int ub_workspace_layout(const ub_problem_t* p, uint32_t flags, int32_t out[80]) {
     if (!p) return fail(UB_E_INVALID, "null problem");
     const ub::Layout& L = (flags & UB_COMPUTE_F64) ? p->Ld : p->Lf;
-    static_assert(sizeof(ub::Layout) <= 40 * sizeof(int32_t), "layout export too small");
-    std::memset(out, 0, 40 * sizeof(int32_t));
+    static_assert(sizeof(ub::Layout) <= 80 * sizeof(int32_t), "layout export too small");
+    std::memset(out, 0, 80 * sizeof(int32_t));
     std::memcpy(out, &L, sizeof(L));
     return UB_OK;
 }
@@ -997,7 +1009,7 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
     } else if (what == EV_OBJDYN) {
         const double scale = rsqrt(double(6 * P.nb));
         for (int b = 0; b < P.nb; ++b) {
-            const ub::BodyP<double> Bd = ub::load_body(bp + b * UB_BODY_PARAMS);
+            const ub::BodyP<double> Bd = ub::load_body<double>(bp + b * UB_BODY_PARAMS);
             ub::object_dynamics_state_part<double, false>(P, Bd, K, D, scale, o + 6 * b, nullptr);
         }
         // wrench part: compute_object_wrenches (contact_constraints.h:106-157)
@@ -1007,13 +1019,13 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
             else f = ub::V3<double>(um[nq + 3 * c], um[nq + 3 * c + 1], um[nq + 3 * c + 2]);
             const int b1 = P.cb1[c], b2 = P.cb2[c];
             if (b1 >= 0) {
-                const ub::BodyP<double> Bd = ub::load_body(bp + b1 * UB_BODY_PARAMS);
+                const ub::BodyP<double> Bd = ub::load_body<double>(bp + b1 * UB_BODY_PARAMS);
                 const ub::V3<double> tq = ub::cross(ub::ld3(P.cr1[c]) - Bd.com, f);
                 const double s = scale / Bd.m;
                 o[6 * b1] -= s * f.x; o[6 * b1 + 1] -= s * f.y; o[6 * b1 + 2] -= s * f.z;
                 o[6 * b1 + 3] -= s * tq.x; o[6 * b1 + 4] -= s * tq.y; o[6 * b1 + 5] -= s * tq.z;
             }
-            const ub::BodyP<double> Bd = ub::load_body(bp + b2 * UB_BODY_PARAMS);
+            const ub::BodyP<double> Bd = ub::load_body<double>(bp + b2 * UB_BODY_PARAMS);
             const ub::V3<double> tq = ub::cross(ub::ld3(P.cr2[c]) - Bd.com, f);
             const double s = scale / Bd.m;
             o[6 * b2] += s * f.x; o[6 * b2 + 1] += s * f.y; o[6 * b2 + 2] += s * f.z;

@@ -52,6 +52,11 @@ struct DevProblem {
     // inertial-alignment rows; proj_s = the target-state flag s
     int nproj, proj_sph[UB_MAX_PROJECTILE_LINKS];
     T proj_d[UB_MAX_PROJECTILE_LINKS], proj_scale, proj_s;
+    // force block of the reduced stage (ub_solver.cuh): equality rows fall into ngrp groups of ng rows — one group
+    // of 6 per body when every contact is with the tray (body1 == -1), ONE group of 6 nb when bodies share contacts;
+    // bc_list[bc_start[b] .. bc_start[b+1]) = the contacts of body b as 2 * contact + side (0: it is body2, 1: body1)
+    int ngrp, ng;
+    int bc_start[UB_MAX_BODIES + 1], bc_list[2 * UB_MAX_CONTACTS];
 };
 
 // Division in the interior-point row updates (eight per inequality row and pass): the fp32 kernels use the
@@ -249,8 +254,8 @@ __device__ __forceinline__ void inertial_alignment_rows(const DevProblem<T>& P, 
 // If TANGENT, also propagates d/dx_dir (dir = this lane's direction; dir >= nx
 // propagates zeros).  Sphere centres (and tangents) are written to sph / dsph
 // (3 values per sphere, registers of this lane) when non-null.
-template <typename T, bool TANGENT>
-__device__ void forward_kinematics(const DevProblem<T>& P, const T* __restrict__ x, int dir, Kin<T>& K, KinTan<T>& D,
+template <typename T, bool TANGENT, typename XT = T>
+__device__ void forward_kinematics(const DevProblem<T>& P, const XT* __restrict__ x, int dir, Kin<T>& K, KinTan<T>& D,
                                    T* sph, T* dsph) {
     const int nq = P.nq;
     M3<T> R;
@@ -302,7 +307,7 @@ __device__ void forward_kinematics(const DevProblem<T>& P, const T* __restrict__
         offset_frame(P.jR[i], P.jp[i]);
         const V3<T> ul = ld3(P.jaxis[i]);
         const V3<T> z = R.mul(ul);
-        const T qi = x[i], qd = x[nq + i], qdd = x[2 * nq + i];
+        const T qi = T(x[i]), qd = T(x[nq + i]), qdd = T(x[2 * nq + i]);   // the iterate may be stored narrower than T
         const T dq = (TANGENT && dir == i) ? T(1) : T(0);
         const T dqd = (TANGENT && dir == nq + i) ? T(1) : T(0);
         const T dqdd = (TANGENT && dir == 2 * nq + i) ? T(1) : T(0);
@@ -367,14 +372,14 @@ struct BodyP {
                      I[2] * v.x + I[4] * v.y + I[5] * v.z);
     }
 };
-template <typename T>
-__device__ __forceinline__ BodyP<T> load_body(const T* p) {
+template <typename T, typename S>
+__device__ __forceinline__ BodyP<T> load_body(const S* p) {   // S: storage type of the parameters
     BodyP<T> b;
-    b.m = p[0];
-    const T inv = T(1) / p[0];
-    b.com = V3<T>(p[1] * inv, p[2] * inv, p[3] * inv);
+    b.m = T(p[0]);
+    const T inv = T(1) / T(p[0]);
+    b.com = V3<T>(T(p[1]) * inv, T(p[2]) * inv, T(p[3]) * inv);
 #pragma unroll
-    for (int i = 0; i < 6; ++i) b.I[i] = p[4 + i];
+    for (int i = 0; i < 6; ++i) b.I[i] = T(p[4 + i]);
     return b;
 }
 

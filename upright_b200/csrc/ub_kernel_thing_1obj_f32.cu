@@ -1,5 +1,5 @@
-// solve kernel instantiation: thing_1obj (StaticDims<9, 1, 4, 1>), float
+// solve kernel instantiation: thing_1obj (UB_DIMS_THING_1OBJ), F = float
 #include "ub_launch.cuh"
 namespace ub {
-UB_DEFINE_LAUNCHER(thing_1obj, float, f32, StaticDims<9, 1, 4, 1>)
+UB_DEFINE_LAUNCHER(thing_1obj, float, f32, UB_DIMS_THING_1OBJ)
 }

@@ -1,5 +1,5 @@
-// solve kernel instantiation: thing_1obj (StaticDims<9, 1, 4, 1>), double
+// solve kernel instantiation: thing_1obj (UB_DIMS_THING_1OBJ), F = double
 #include "ub_launch.cuh"
 namespace ub {
-UB_DEFINE_LAUNCHER(thing_1obj, double, f64, StaticDims<9, 1, 4, 1>)
+UB_DEFINE_LAUNCHER(thing_1obj, double, f64, UB_DIMS_THING_1OBJ)
 }

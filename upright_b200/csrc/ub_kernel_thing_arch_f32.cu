@@ -1,5 +1,5 @@
-// solve kernel instantiation: thing_arch (StaticDims<9, 3, 16, 3>), float
+// solve kernel instantiation: thing_arch (UB_DIMS_THING_ARCH), F = float
 #include "ub_launch.cuh"
 namespace ub {
-UB_DEFINE_LAUNCHER(thing_arch, float, f32, StaticDims<9, 3, 16, 3>)
+UB_DEFINE_LAUNCHER(thing_arch, float, f32, UB_DIMS_THING_ARCH)
 }

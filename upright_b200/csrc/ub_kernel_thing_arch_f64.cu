@@ -1,5 +1,5 @@
-// solve kernel instantiation: thing_arch (StaticDims<9, 3, 16, 3>), double
+// solve kernel instantiation: thing_arch (UB_DIMS_THING_ARCH), F = double
 #include "ub_launch.cuh"
 namespace ub {
-UB_DEFINE_LAUNCHER(thing_arch, double, f64, StaticDims<9, 3, 16, 3>)
+UB_DEFINE_LAUNCHER(thing_arch, double, f64, UB_DIMS_THING_ARCH)
 }

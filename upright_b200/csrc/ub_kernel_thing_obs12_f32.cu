@@ -1,5 +1,5 @@
-// solve kernel instantiation: thing_obs12 (StaticDims<9, 1, 4, 1, 12>), float
+// solve kernel instantiation: thing_obs12 (UB_DIMS_THING_OBS12), F = float
 #include "ub_launch.cuh"
 namespace ub {
-UB_DEFINE_LAUNCHER(thing_obs12, float, f32, StaticDims<9, 1, 4, 1, 12>)
+UB_DEFINE_LAUNCHER(thing_obs12, float, f32, UB_DIMS_THING_OBS12)
 }

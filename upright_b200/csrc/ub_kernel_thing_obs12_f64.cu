@@ -1,5 +1,5 @@
-// solve kernel instantiation: thing_obs12 (StaticDims<9, 1, 4, 1, 12>), double
+// solve kernel instantiation: thing_obs12 (UB_DIMS_THING_OBS12), F = double
 #include "ub_launch.cuh"
 namespace ub {
-UB_DEFINE_LAUNCHER(thing_obs12, double, f64, StaticDims<9, 1, 4, 1, 12>)
+UB_DEFINE_LAUNCHER(thing_obs12, double, f64, UB_DIMS_THING_OBS12)
 }

@@ -1,5 +1,5 @@
-// solve kernel instantiation: thing_robust8 (StaticDims<9, 1, 32, 8>), float
+// solve kernel instantiation: thing_robust8 (UB_DIMS_THING_ROBUST8), F = float
 #include "ub_launch.cuh"
 namespace ub {
-UB_DEFINE_LAUNCHER(thing_robust8, float, f32, StaticDims<9, 1, 32, 8>)
+UB_DEFINE_LAUNCHER(thing_robust8, float, f32, UB_DIMS_THING_ROBUST8)
 }

@@ -1,5 +1,5 @@
-// solve kernel instantiation: ur10_1obj (StaticDims<6, 1, 4, 1>), double
+// solve kernel instantiation: ur10_1obj (UB_DIMS_UR10_1OBJ), F = double
 #include "ub_launch.cuh"
 namespace ub {
-UB_DEFINE_LAUNCHER(ur10_1obj, double, f64, StaticDims<6, 1, 4, 1>)
+UB_DEFINE_LAUNCHER(ur10_1obj, double, f64, UB_DIMS_UR10_1OBJ)
 }

@@ -14,9 +14,12 @@ import numpy as np
 
 from . import bindings as B
 
-LAYOUT_FIELDS = ("Z", "DZ", "GAP", "LG", "LCT", "LR", "LJP", "LHO", "LJO", "DF", "RHOE", "YE", "RHOT", "YT", "TT",
-                 "LAM", "XW", "UW", "sTT", "FAC", "WF", "XN", "UN", "total", "sM", "sP", "sPv", "sSA", "sV",
-                 "s_total", "sSm", "sRed", "TG", "BD", "LIA", "LJA", "XO", "DXO")
+LAYOUT_FIELDS = ("Z", "DZ", "GAP", "LG", "LC", "LR", "LJP", "LHO", "LJO", "DF", "DFC", "RHOE", "YE", "RHOT", "YT", "TL", "DD",
+                 "GP", "VE", "FAC", "WF", "FBD", "FBL", "GS", "GL", "QF", "XN", "UN", "XW", "UW", "TG", "BD", "LIA", "LJA",
+                 "XO", "DXO", "total", "sM", "sP", "sPv", "sC", "sS", "sD", "sFq", "sFv", "sFg", "sFl", "sVec", "sDst",
+                 "sDxn", "sRv", "sScr", "sTL", "sDD", "sSmZ", "sSmX", "sSmU", "sSmJ", "sSmW", "s_total", "rw")
+# workspace blocks that hold doubles whatever the kernels' matrix type (ub_solver.cuh: compute_layout)
+LAYOUT_DOUBLE_BLOCKS = ("Z", "GAP", "LG", "LR", "RHOE", "YE", "RHOT", "YT", "TL", "GP", "VE", "FBD", "FBL", "GL", "QF")
 
 
 def _ptr(a):
@@ -192,7 +195,7 @@ class BatchedMPC:
         B.check(self.lib.ub_set_option(self.handle, key.encode(), int(value)))
 
     def layout(self):
-        out = (C.c_int32 * 40)()
+        out = (C.c_int32 * 80)()
         B.check(self.lib.ub_workspace_layout(self.handle, self.flags, out))
         return dict(zip(LAYOUT_FIELDS, list(out)))
 
@@ -201,3 +204,13 @@ class BatchedMPC:
         L = self.layout()
         ws = self._ws.view(self.torch_dtype)
         return ws[: Bn * L["total"]].view(Bn, L["total"]), L
+
+    def workspace_block(self, Bn, name, count):
+        """`count` elements of block `name` for each of the Bn static slots of the last device solve, as float64
+        numpy [Bn, count]; blocks in LAYOUT_DOUBLE_BLOCKS hold doubles even under the fp32 kernels."""
+        import torch
+        ws, L = self.workspace_view(Bn)
+        if name in LAYOUT_DOUBLE_BLOCKS and self.precision == "f32":
+            raw = ws[:, L[name]: L[name] + 2 * count].contiguous()
+            return raw.view(torch.float64).cpu().numpy()
+        return ws[:, L[name]: L[name] + count].double().cpu().numpy()
