@@ -83,10 +83,14 @@ typedef struct ub_contact {
  * obstacles/simple.urdf.xacro:40-102). */
 typedef struct ub_sphere {
     int32_t link;
-    int32_t reserved;
+    int32_t shape;  /* UB_SHAPE_SPHERE, or UB_SHAPE_HALFSPACE: the `ground` object the reference adds to every collision
+                       model (add_ground_plane, controller_interface.cpp:93-101,189: hpp::fcl::Halfspace(UnitZ, 0)) —
+                       link = -1, offset = unit normal n, radius = plane offset d; the solid is {p : n.p <= d} and the
+                       row of a pair (sphere a, half-space) is n.c_a - d - r_a - minimum_distance >= 0 */
     double radius;
     double offset[3];
 } ub_sphere_t;
+enum { UB_SHAPE_SPHERE = 0, UB_SHAPE_HALFSPACE = 1 };
 
 typedef struct ub_pair {
     int32_t a;

@@ -221,10 +221,18 @@ void inertial_alignment_constraints(const ub_problem_desc_t& P, const Kinematics
 // Sphere-sphere distances minus the minimum distance, h >= 0.  Closed form of
 // ocs2::SelfCollisionConstraintCppAd + hpp-fcl for sphere pairs
 // (upright_control/src/controller_interface.cpp:450-481).
+// The `ground` object of the reference is a half-space (add_ground_plane, controller_interface.cpp:93-101:
+// hpp::fcl::Halfspace(UnitZ, 0), solid {p : n.p <= d}): sphere against it -> n.c - d - r.
 template <typename S>
 void obstacle_constraints(const ub_problem_desc_t& P, const Kinematics<S>& X, S* h) {
     for (int i = 0; i < P.n_pairs; ++i) {
         const int a = P.pairs[i].a, b = P.pairs[i].b;
+        if (P.spheres[a].shape == UB_SHAPE_HALFSPACE || P.spheres[b].shape == UB_SHAPE_HALFSPACE) {
+            const int hs = P.spheres[b].shape == UB_SHAPE_HALFSPACE ? b : a, s = hs == b ? a : b;
+            const Vec3<S> n = vec3_from<S>(P.spheres[hs].offset);
+            h[i] = dot(n, X.sphere[s]) - S(P.spheres[hs].radius + P.spheres[s].radius + P.minimum_distance);
+            continue;
+        }
         const Vec3<S> d = X.sphere[a] - X.sphere[b];
         h[i] = sqrt(dot(d, d)) - S(P.spheres[a].radius + P.spheres[b].radius + P.minimum_distance);
     }

@@ -235,6 +235,12 @@ static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const doub
                 len += n[c] * n[c];
             }
             len = std::sqrt(len);
+            if (P.spheres[pa].shape == UB_SHAPE_HALFSPACE || P.spheres[pb].shape == UB_SHAPE_HALFSPACE) {
+                // sphere against the half-space: d h / d c = +n (the half-space itself never rides on an obstacle)
+                const int hs = P.spheres[pb].shape == UB_SHAPE_HALFSPACE ? pb : pa;
+                for (int c = 0; c < 3; ++c) n[c] = (hs == pb ? 1.0 : -1.0) * P.spheres[hs].offset[c];
+                len = 1.0;
+            }
             for (int side = 0; side < 2; ++side) {
                 const int s = side == 0 ? pa : pb;
                 if (P.spheres[s].link > -2) continue;

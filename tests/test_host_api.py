@@ -1,11 +1,13 @@
 """Host-side logic that needs no GPU: settings parsing from the reference's own
 YAML (when present) against the committed fixtures, target trajectories,
 workload generator, receding-horizon bookkeeping with a stub engine."""
+import copy
 from pathlib import Path
 
 import numpy as np
 import pytest
 
+from upright_b200 import bindings as B
 from upright_b200 import config, problem_io, settings, workload
 from upright_b200.settings import TargetTrajectories
 
@@ -192,6 +194,30 @@ def test_dynamic_obstacle_settings():
     assert desc.n_dynamic_obstacles == 1 and desc.n_pairs == d.n_pairs + 1
     riding = [i for i in range(desc.n_spheres) if desc.spheres[i].link == -2]
     assert len(riding) == 1 and desc.spheres[riding[0]].radius == 0.1
+
+
+@pytest.mark.skipif(not REF.exists(), reason="reference tree only in the build container")
+@pytest.mark.parametrize("path", ["upright_cmd/config/ral23/experiments/sudden_obstacle/sudden_t1.0.yaml",
+                                  "upright_cmd/config/ral23/experiments/projectile/projectile_head_on.yaml"])
+def test_reference_obstacle_configs_load_unchanged(path):
+    """The ral23 obstacle experiment families pair a wrist sphere against `ground` — the half-space the reference adds
+    to every collision model (add_ground_plane, controller_interface.cpp:93-101,189).  The configurations load as
+    shipped and the pair becomes a sphere / half-space row."""
+    cfg = config.load_config(REF / path)["controller"]
+    s = settings.ControllerSettings(cfg)
+    desc = s.to_desc()
+    assert desc.obstacles_enabled == 1 and desc.n_dynamic_obstacles == 1
+    hs = [i for i in range(desc.n_spheres) if desc.spheres[i].shape == B.UB_SHAPE_HALFSPACE]
+    assert len(hs) == 1 and desc.spheres[hs[0]].link == -1 and desc.spheres[hs[0]].radius == 0.0
+    assert list(desc.spheres[hs[0]].offset) == [0.0, 0.0, 1.0]
+    ground_pairs = [(desc.pairs[i].a, desc.pairs[i].b) for i in range(desc.n_pairs) if hs[0] in (desc.pairs[i].a, desc.pairs[i].b)]
+    assert len(ground_pairs) == 1 and ground_pairs[0][1] == hs[0]          # the sphere first, the half-space second
+    assert desc.spheres[ground_pairs[0][0]].link >= 0                        # a robot (wrist) sphere
+    assert desc.n_pairs == len(cfg["obstacles"]["collision_pairs"])
+    with pytest.raises(ValueError, match="unknown collision object"):
+        bad = copy.deepcopy(cfg)
+        bad["obstacles"]["collision_pairs"] = list(bad["obstacles"]["collision_pairs"]) + [["wrist3_collision_link_0", "no_such_thing"]]
+        settings.ControllerSettings(bad).to_desc()
 
 
 def test_projectile_path_constraint_settings():

@@ -145,3 +145,34 @@ def test_object_dynamics_against_direct_numpy(oracle_lib):
         Tq += np.cross(np.array(list(c.r_co_o2)) - com, -f)
     exp = np.concatenate([(gi - F) / m, (tau - Tq) / m]) / np.sqrt(6.0)
     assert np.allclose(oracle_lib.linearize(desc, x, u)["g"], exp, atol=1e-12)
+
+
+def test_ground_half_space_row_in_the_oracle(oracle_lib):
+    import copy
+    from upright_b200 import bindings as B
+    oracle = oracle_lib
+    """Sphere against the half-space z <= 0: value c_z - r - minimum_distance, Jacobian = z-row of the sphere's
+    position Jacobian (central differences), and the row keeps the wrist above the floor in a solve."""
+    d0, meta = problem_io.load_fixture("cfg4_thing_obstacles2")
+    d = copy.deepcopy(d0)
+    robot_slots = [i for i in range(d.n_spheres) if d.spheres[i].link >= 0]
+    g = d.n_spheres
+    d.spheres[g].link, d.spheres[g].shape, d.spheres[g].radius = -1, B.UB_SHAPE_HALFSPACE, 0.0
+    d.spheres[g].offset[:] = [0.0, 0.0, 1.0]
+    d.n_spheres += 1
+    a = robot_slots[0]
+    d.pairs[d.n_pairs].a, d.pairs[d.n_pairs].b = a, g
+    d.n_pairs += 1
+    x = np.array(meta["x0"], dtype=float)
+    x[:9] += 0.1 * np.random.default_rng(0).standard_normal(9)
+    nu = oracle.dims(d)["nu"]
+    lin = oracle.linearize(d, x, np.zeros(nu))
+    c = oracle.fk(d, x)["spheres"][a]
+    assert lin["hobs"][-1] == pytest.approx(c[2] - d.spheres[a].radius - d.minimum_distance, abs=1e-12)
+    J = np.zeros(9)
+    for j in range(9):
+        e = np.zeros(27)
+        e[j] = 1e-6
+        J[j] = (oracle.linearize(d, x + e, np.zeros(nu))["hobs"][-1] - oracle.linearize(d, x - e, np.zeros(nu))["hobs"][-1]) / 2e-6
+    assert np.allclose(lin["Jobs"][-1], J, atol=1e-7)
+    assert np.allclose(lin["hobs"][:-1], oracle.linearize(d0, x, np.zeros(nu))["hobs"], atol=1e-14)   # other rows untouched

@@ -24,6 +24,7 @@ UB_PTRS_DEVICE = 0x1
 UB_WARM_START = 0x2
 UB_COMPUTE_F64 = 0x4
 UB_RESCUE_F64 = 0x8
+UB_SHAPE_SPHERE, UB_SHAPE_HALFSPACE = 0, 1
 
 STATUS_NAMES = {0: "converged", 1: "qp_maxiter", 2: "linesearch_failed", 3: "nan"}
 
@@ -40,7 +41,7 @@ class Contact(C.Structure):
 
 
 class Sphere(C.Structure):
-    _fields_ = [("link", C.c_int32), ("reserved", C.c_int32), ("radius", C.c_double),
+    _fields_ = [("link", C.c_int32), ("shape", C.c_int32), ("radius", C.c_double),
                 ("offset", C.c_double * 3)]
 
 

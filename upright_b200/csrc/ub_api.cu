@@ -265,6 +265,7 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
     }
     for (int s = 0; s < d.n_spheres; ++s) {
         P.slink[s] = d.spheres[s].link;
+        P.sshape[s] = d.spheres[s].shape;
         P.srad[s] = T(d.spheres[s].radius);
         for (int j = 0; j < 3; ++j) P.soff[s][j] = T(d.spheres[s].offset[j]);
     }
@@ -803,6 +804,19 @@ int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
     for (int s = 0; s < desc->n_spheres; ++s)
         if (desc->spheres[s].link < -1 - desc->n_dynamic_obstacles || desc->spheres[s].link > desc->nq)
             return fail(UB_E_INVALID, "sphere attached to an unknown link / dynamic obstacle");
+    for (int s = 0; s < desc->n_spheres; ++s) {
+        const int sh = desc->spheres[s].shape;
+        if (sh != UB_SHAPE_SPHERE && sh != UB_SHAPE_HALFSPACE) return fail(UB_E_INVALID, "unknown collision shape");
+        if (sh == UB_SHAPE_HALFSPACE && desc->spheres[s].link != -1) return fail(UB_E_INVALID, "a half-space is fixed to the world (link -1)");
+    }
+    for (int i = 0; i < desc->n_pairs; ++i)
+        if (desc->pairs[i].a >= 0 && desc->pairs[i].a < desc->n_spheres && desc->pairs[i].b >= 0 && desc->pairs[i].b < desc->n_spheres &&
+            desc->spheres[desc->pairs[i].a].shape == UB_SHAPE_HALFSPACE && desc->spheres[desc->pairs[i].b].shape == UB_SHAPE_HALFSPACE)
+            return fail(UB_E_INVALID, "a collision pair of two half-spaces");
+    for (int i = 0; i < desc->n_projectile_links && desc->projectile_enabled; ++i)
+        if (desc->projectile_spheres[i] >= 0 && desc->projectile_spheres[i] < desc->n_spheres &&
+            desc->spheres[desc->projectile_spheres[i]].shape != UB_SHAPE_SPHERE)
+            return fail(UB_E_INVALID, "projectile collision link must be a sphere");
     for (int i = 0; i < desc->n_pairs; ++i)
         if (desc->pairs[i].a < 0 || desc->pairs[i].a >= desc->n_spheres || desc->pairs[i].b < 0 || desc->pairs[i].b >= desc->n_spheres)
             return fail(UB_E_INVALID, "collision pair names an unknown sphere");
@@ -1061,9 +1075,8 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
         o[0] = 0.5 * P.ia_w * (e2[0] * e2[0] + e2[1] * e2[1]);
     } else if (what == EV_OBST) {
         for (int i = 0; i < P.npairs; ++i) {
-            const int a = P.pa[i], b = P.pb[i];
-            const ub::V3<double> d(sph[3 * a] - sph[3 * b], sph[3 * a + 1] - sph[3 * b + 1], sph[3 * a + 2] - sph[3 * b + 2]);
-            o[i] = sqrt(ub::dot(d, d)) - (P.srad[a] + P.srad[b] + P.dmin);
+            ub::V3<double> dir;
+            o[i] = ub::pair_separation(P, P.pa[i], P.pb[i], sph, &dir) - P.dmin;
         }
     } else {  // intermediate cost (not scaled by dt), as ocs2 PythonInterface::cost
         double c = 0;

@@ -33,7 +33,7 @@ struct DevProblem {
     int cb1[UB_MAX_CONTACTS], cb2[UB_MAX_CONTACTS];
     T cmu[UB_MAX_CONTACTS], cr1[UB_MAX_CONTACTS][3], cr2[UB_MAX_CONTACTS][3], cn[UB_MAX_CONTACTS][3],
         cspan[UB_MAX_CONTACTS][6];
-    int slink[UB_MAX_SPHERES];
+    int slink[UB_MAX_SPHERES], sshape[UB_MAX_SPHERES];
     T srad[UB_MAX_SPHERES], soff[UB_MAX_SPHERES][3];
     int pa[UB_MAX_PAIRS], pb[UB_MAX_PAIRS];
     T dmin;
@@ -87,6 +87,23 @@ __device__ __forceinline__ V3<T> cross(const V3<T>& a, const V3<T>& b) {
 }
 template <typename T>
 __device__ __forceinline__ V3<T> ld3(const T* p) { return V3<T>(p[0], p[1], p[2]); }
+
+// Separation of collision pair (a, b) given the centres `sph` (3 per object), without the minimum distance:
+// sphere-sphere |c_a - c_b| - r_a - r_b, or sphere against the half-space {p : n.p <= d} (the reference's `ground`,
+// controller_interface.cpp:93-101): n.c_a - d - r_a.  *dir: d h / d c_a (= -d h / d c_b between spheres).
+template <typename T, typename PT>
+__device__ __forceinline__ T pair_separation(const DevProblem<PT>& P, int a, int b, const T* sph, V3<T>* dir) {
+    if (P.sshape[b] == UB_SHAPE_HALFSPACE || P.sshape[a] == UB_SHAPE_HALFSPACE) {
+        const int h = P.sshape[b] == UB_SHAPE_HALFSPACE ? b : a, s = h == b ? a : b;
+        const V3<T> n(T(P.soff[h][0]), T(P.soff[h][1]), T(P.soff[h][2]));
+        *dir = h == b ? n : T(-1) * n;
+        return n.x * sph[3 * s] + n.y * sph[3 * s + 1] + n.z * sph[3 * s + 2] - T(P.srad[h]) - T(P.srad[s]);
+    }
+    const V3<T> d(sph[3 * a] - sph[3 * b], sph[3 * a + 1] - sph[3 * b + 1], sph[3 * a + 2] - sph[3 * b + 2]);
+    const T dist = sqrt(dot(d, d));
+    *dir = (T(1) / dist) * d;
+    return dist - T(P.srad[a]) - T(P.srad[b]);
+}
 
 // cubic_newtons + projectile_closest_time (constraint/projectile_path_constraint.h:11-44): time at which the
 // ballistic path r0 + t v0 + t^2 g / 2 is nearest to r; Newton from t = 0, at most 10 steps, step tolerance 1e-4

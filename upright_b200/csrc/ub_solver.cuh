@@ -601,23 +601,23 @@ struct Solver {
             if (NOBS() > 0) {
                 for (int i = 0; i < NPAIRS(); ++i) {
                     const int a = P.pa[i], bb = P.pb[i];
-                    const V3<R> d(sph[3 * a] - sph[3 * bb], sph[3 * a + 1] - sph[3 * bb + 1], sph[3 * a + 2] - sph[3 * bb + 2]);
-                    const R dist = sqrt(dot(d, d));
+                    V3<R> dir;   // d h / d c_a = - d h / d c_b
+                    const R sep = pair_separation(PR, a, bb, sph, &dir);
                     const V3<R> dd(dsph[3 * a] - dsph[3 * bb], dsph[3 * a + 1] - dsph[3 * bb + 1],
                                    dsph[3 * a + 2] - dsph[3 * bb + 2]);
                     R shift = R(0);
                     if (NXO() > 0) {
-                        // known Newton step of the obstacle positions: h + (dh/dc_a) dp_a + (dh/dc_b) dp_b, dh/dc = +-d/|d|
+                        // known Newton step of the obstacle positions: h + (dh/dc_a) dp_a + (dh/dc_b) dp_b
                         for (int side = 0; side < 2; ++side) {
                             const int s = side == 0 ? a : bb;
                             if (P.slink[s] > -2) continue;
                             const F* dp = ws + oDXO() + (k * P.ndyn + (-2 - P.slink[s])) * 9;
-                            const R proj = (d.x * R(dp[0]) + d.y * R(dp[1]) + d.z * R(dp[2])) / dist;
+                            const R proj = dir.x * R(dp[0]) + dir.y * R(dp[1]) + dir.z * R(dp[2]);
                             shift += side == 0 ? proj : -proj;
                         }
                     }
-                    if (lane == 0) ws[oLHO() + k * NOBS() + i] = F(dist - (PR.srad[a] + PR.srad[bb] + PR.dmin) + shift);
-                    if (lane < OBSW()) ws[oLJO() + (k * NOBS() + i) * OBSW() + lane] = lane < nq ? F(dot(d, dd) / dist) : F(0);
+                    if (lane == 0) ws[oLHO() + k * NOBS() + i] = F(sep - PR.dmin + shift);
+                    if (lane < OBSW()) ws[oLJO() + (k * NOBS() + i) * OBSW() + lane] = lane < nq ? F(dot(dir, dd)) : F(0);
                 }
                 if (EEBOX()) {
                     // rows npairs..+2: r_d + upper - r >= 0; rows npairs+3..+5: r - r_d - lower >= 0
@@ -794,9 +794,8 @@ struct Solver {
             if (k >= 1)
             {
                 for (int i = 0; i < NPAIRS(); ++i) {
-                    const int a = P.pa[i], bb = P.pb[i];
-                    const V3<F> d(sph[3 * a] - sph[3 * bb], sph[3 * a + 1] - sph[3 * bb + 1], sph[3 * a + 2] - sph[3 * bb + 2]);
-                    const F h = sqrt(dot(d, d)) - (P.srad[a] + P.srad[bb] + C.dmin);
+                    V3<F> dir;
+                    const F h = pair_separation(P, P.pa[i], P.pb[i], sph, &dir) - C.dmin;
                     const F m = min(F(0), h);
                     ineq += dt * m * m;
                     min_margin = min(min_margin, h);

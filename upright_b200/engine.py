@@ -47,14 +47,6 @@ class BatchedMPC:
         # nx counts the dynamic-obstacle states too (9 each, behind the robot state); gains act on the robot state
         self.nx_robot = 3 * desc.nq
         self._ws = None
-        if precision == "f32":
-            from .problem_io import fp32_conditioning_estimate
-            kappa = fp32_conditioning_estimate(desc)
-            if kappa > 1e7:
-                import warnings
-                warnings.warn(f"soft object-dynamics rows with a {min(desc.body_params[b][0] for b in range(desc.nb)):.3g} kg "
-                              f"body: stage matrices conditioned ~{kappa:.1e}, beyond fp32 — solve with rescue=True "
-                              "(UB_RESCUE_F64) or precision='f64'", RuntimeWarning, stacklevel=2)
 
     def __del__(self):
         try:

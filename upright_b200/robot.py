@@ -67,6 +67,7 @@ class Sphere:
     link: int  # 0..nq-1 link after that joint, nq = tool frame, -1 = world
     offset: np.ndarray
     radius: float
+    shape: int = 0  # 0 sphere; 1 half-space (offset = unit normal, radius = plane offset): the reference's `ground`
 
 
 @dataclass

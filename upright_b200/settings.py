@@ -408,6 +408,10 @@ class ControllerSettings:
             for name, (pos, rad) in self.obstacle_settings.static_spheres.items():
                 sidx[name] = len(spheres)
                 spheres.append(robot.Sphere(name, -1, pos, rad))
+            # the `ground` half-space z <= 0 is part of every collision model (add_ground_plane,
+            # controller_interface.cpp:93-101,189); obstacles/dynamic.yaml:28-29 and sudden.yaml:29-30 pair against it
+            sidx["ground"] = len(spheres)
+            spheres.append(robot.Sphere("ground", -1, np.array([0.0, 0.0, 1.0]), 0.0, shape=B.UB_SHAPE_HALFSPACE))
             dyn = self.obstacle_settings.dynamic_obstacles
             if len(dyn) > B.UB_MAX_DYNAMIC_OBSTACLES:
                 raise ValueError("too many dynamic obstacles")
@@ -416,8 +420,16 @@ class ControllerSettings:
                 spheres.append(robot.Sphere(o.name, -2 - j, o.modes[0].position, o.radius))
             d.n_dynamic_obstacles = len(dyn)
             used, pairs = {}, []
+            def lookup(n):
+                key = n[:-2] if n.endswith("_0") else n
+                if key not in sidx:
+                    raise ValueError(f"collision pair names an unknown collision object {n!r} (known: {sorted(sidx)})")
+                return sidx[key]
+
             for a, b in self.obstacle_settings.collision_link_pairs:
-                ia, ib = (sidx[n[:-2] if n.endswith("_0") else n] for n in (a, b))
+                ia, ib = lookup(a), lookup(b)
+                if spheres[ia].shape and not spheres[ib].shape:
+                    ia, ib = ib, ia   # the sphere first, the half-space second
                 for k in (ia, ib):
                     used.setdefault(k, len(used))
                 pairs.append((used[ia], used[ib]))
@@ -435,7 +447,7 @@ class ControllerSettings:
                 d.projectile_scale = self.projectile_path_scale
                 d.projectile_active = float(getattr(self, "projectile_active", 0.0))
                 for i, n in enumerate(links):
-                    k = sidx[n[:-2] if n.endswith("_0") else n]
+                    k = lookup(n)
                     d.projectile_spheres[i] = used.setdefault(k, len(used))
                     d.projectile_distances[i] = float(self.projectile_path_distances[i])
             if len(used) > B.UB_MAX_SPHERES or len(pairs) > B.UB_MAX_PAIRS:
@@ -443,6 +455,7 @@ class ControllerSettings:
             for k, slot in used.items():
                 s = spheres[k]
                 d.spheres[slot].link = s.link
+                d.spheres[slot].shape = s.shape
                 d.spheres[slot].radius = s.radius
                 d.spheres[slot].offset[:] = s.offset
             for i, (a, b) in enumerate(pairs):
