@@ -112,12 +112,12 @@ class ClockSampler:
                 "samples": len(sm), "window": window}
 
 
-def oracle_rate(desc, batch, threads, min_seconds=10.0, max_instances=None):
+def oracle_rate(desc, batch, threads, min_seconds=10.0, max_instances=None, chunk=None):
     """Time the CPU oracle (restated OCS2-equivalent, fp64) on a bounded sample."""
     import oracle
     n = min(len(batch["x0"]), max_instances or len(batch["x0"]))
     done, t0 = 0, time.perf_counter()
-    chunk = max(threads * 4, 32)
+    chunk = chunk or max(threads * 4, 32)
     while True:
         idx = np.arange(done, done + chunk) % n
         bp = None if batch["body_params"] is None else batch["body_params"][idx]
@@ -126,6 +126,78 @@ def oracle_rate(desc, batch, threads, min_seconds=10.0, max_instances=None):
         el = time.perf_counter() - t0
         if el >= min_seconds:
             return done / el, done, el
+
+
+PER_GPU_BATCH = {   # BASELINE.json batch of a configuration on ONE GPU (cfg4: 16384 / 8, cfg5: 8192 / 8)
+    "cfg1_ur10_demo": 4096, "cfg2_thing_demo": 4096, "cfg3_thing_box_arch": 4096, "cfg4_thing_obstacles2": 2048,
+    "cfg5_thing_robust8": 1024,
+}
+
+
+def config_block(name, prec, world, dev, peak_tflops, seed=4321):
+    """One BASELINE configuration at its per-GPU batch: kernel time (CUDA events, mean of 3 launches after a warm-up),
+    iteration statistics, status counts and the arithmetic roofline fraction.  With world > 1 every rank solves its own
+    shard (cfg4: 8 x 2048 = 16384, cfg5: 8 x 1024 = 8192 — BASELINE's split) and the packed results are all-gathered;
+    the time is the max over ranks, the rate the global batch over it."""
+    import torch
+    import torch.distributed as dist
+    from upright_b200 import workload
+    from upright_b200.engine import BatchedMPC
+    desc, meta = workload.load(name)
+    mpc = BatchedMPC(desc, prec)
+    dt = mpc.torch_dtype
+    B = PER_GPU_BATCH[name]
+    rank = dist.get_rank() if world > 1 else 0
+    ee = lambda x: mpc.eval("end_effector_position", x, np.zeros((x.shape[0], mpc.nu)))  # noqa: E731
+    mg = (lambda x: mpc.eval("obstacle_avoidance", x, np.zeros((x.shape[0], mpc.nu)))) if desc.obstacles_enabled else None
+    b = workload.sample_batch(name, desc, meta, B, seed + 1000 * rank, ee, margin_fn=mg)
+    t = lambda a: None if a is None else torch.tensor(a, dtype=dt, device=dev)  # noqa: E731
+    x0, tg, bp = t(b["x0"]), t(b["target"]), t(b["body_params"])
+    nX, nU = (mpc.N + 1) * mpc.nx, mpc.N * mpc.nu
+    packed = torch.empty(B * (nX + nU), dtype=dt, device=dev)
+    X, U = packed[: B * nX].view(B, mpc.N + 1, mpc.nx), packed[B * nX:].view(B, mpc.N, mpc.nu)
+    full = torch.empty(world * B * (nX + nU), dtype=dt, device=dev) if world > 1 else None
+    status = torch.empty(B, dtype=torch.int32, device=dev)
+    stats = torch.empty((B, 8), dtype=dt, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms, kms = [], []
+    for it in range(4):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record()
+        mpc.solve_device(x0, tg, bp, X=X, U=U, status=status, stats=stats)
+        if world > 1:
+            dist.all_gather_into_tensor(full, packed)
+        ev1.record()
+        torch.cuda.synchronize()
+        if it > 0:
+            ms.append(ev0.elapsed_time(ev1))
+            kms.append(mpc.last_solve_ms())
+    tm = torch.tensor([float(np.mean(ms))], dtype=torch.float64, device=dev)
+    counts = torch.bincount(status.long().clamp(0, 3), minlength=4).double()
+    it_sum = torch.stack((stats[:, 0].double().sum(), stats[:, 0].double().max()))
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        it_max = it_sum[1:].clone()
+        dist.all_reduce(it_sum[:1], op=dist.ReduceOp.SUM)
+        dist.all_reduce(it_max, op=dist.ReduceOp.MAX)
+        it_sum[1] = it_max[0]
+    mean_it = float(it_sum[0].item()) / (B * world)
+    step_ms = float(tm.item())
+    flops = workload.algorithmic_flops_per_solve(desc, mean_it, desc.sqp_iteration) * B * world
+    tf = flops / (step_ms * 1e-3) / 1e12
+    traffic, src = measured_traffic(name, B)
+    out = {"per_gpu_batch": B, "global_batch": B * world, "solves_per_s": B * world / (step_ms * 1e-3), "ms_per_batch": step_ms,
+           "kernel_ms": float(np.mean(kms)), "mean_ipm_iterations": mean_it, "max_ipm_iterations": float(it_sum[1].item()),
+           "status_counts": {"converged": int(counts[0].item()), "qp_maxiter": int(counts[1].item()),
+                             "linesearch_failed": int(counts[2].item()), "nan": int(counts[3].item())},
+           "algorithmic_tflops": tf, "fp32_frac": tf / (peak_tflops * world) if peak_tflops else None,
+           "dram_bytes_per_launch": traffic, "dram_bytes_source": src,
+           "nx": mpc.nx, "nu": mpc.nu, "dtype": prec}
+    del mpc
+    return out
 
 
 def main():
@@ -138,6 +210,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="instances per GPU per step")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-batch", type=int, default=None, help="reference arm: instances per step (default: the batch)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-configuration block")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU result exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -157,15 +232,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    B = args.batch or workload.BASELINE_BATCH.get(args.config, 4096)
-    if args.config != "cfg2_thing_demo" and args.batch is None:
-        B = max(1, B // max(world, 1)) if B > 4096 else B
+    B = args.batch or PER_GPU_BATCH.get(args.config, 4096)
     cores = os.cpu_count() or 1
     config = {"workload": f"{args.config}: {meta['source']}, batch={B}/GPU cold start, sqp_iteration={desc.sqp_iteration}, "
                           f"N={desc.N} knots, nx={desc.nx}, nu={desc.nu}",
               "global_batch": B * world, "per_gpu_batch": B, "seed": 1234,
               "parallelism": f"dp{world} (independent instances sharded; one NCCL all-gather of the packed [X|U] results per step, on a side stream under the next step's solve)" if world > 1 else "dp1",
-              "l2": "no explicit flush: the per-step working set (246 MB of workspace slots, rewritten every interior-point iteration) exceeds the 126 MB L2; inputs differ every step"}
+              "l2": "no explicit flush: the per-step working set (workspace slots of every resident warp, rewritten every interior-point iteration) exceeds the 126 MB L2; inputs differ every step"}
 
     # ------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -177,17 +250,24 @@ def main():
         def ee_fn(x):
             return np.array([oracle.fk(desc, xi)["r"] for xi in x])
 
-        sample_n = 128
-        sets = [workload.sample_batch(args.config, desc, meta, sample_n, 1234 + s, ee_fn) for s in range(args.warmup + args.steps)]
+        sample_n = args.ref_batch or B
+        # the same per-step batch as our arm (one distinct seeded set per step would cost minutes of set-up on the
+        # host for nothing: the oracle's time does not depend on it), rotated by step
+        base = workload.sample_batch(args.config, desc, meta, sample_n, 1234, ee_fn)
+
+        def one(s):
+            idx = (np.arange(sample_n) + 17 * s) % sample_n
+            bp = None if base["body_params"] is None else base["body_params"][idx]
+            oracle.solve_batch(desc, base["x0"][idx], base["target"][idx], bp, nthreads=cores)
+
         for s in range(args.warmup):
-            b = sets[s]
-            oracle.solve_batch(desc, b["x0"], b["target"], b["body_params"], nthreads=cores)
+            one(s)
         t0 = time.perf_counter()
         for s in range(args.warmup, args.warmup + args.steps):
-            b = sets[s]
-            oracle.solve_batch(desc, b["x0"], b["target"], b["body_params"], nthreads=cores)
+            one(s)
         el = time.perf_counter() - t0
         value = sample_n * args.steps / el
+        config["reference_per_step_batch"] = sample_n
         line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -201,9 +281,10 @@ def main():
         return 0
 
     # ------------------------------------------------------------------ our arm
+    import ctypes
     import torch
     import torch.distributed as dist
-    from upright_b200.bindings import load_library
+    from upright_b200.bindings import check, load_library
     from upright_b200.engine import BatchedMPC
 
     torch.cuda.set_device(local_rank)
@@ -227,10 +308,17 @@ def main():
     U = torch.empty((B, mpc.N, mpc.nu), dtype=dt, device=dev)
     status = torch.empty(B, dtype=torch.int32, device=dev)
     stats = torch.empty((B, 8), dtype=dt, device=dev)
-    pipe = None
+    pipe, gather_kind = None, None
     if world > 1:
-        from upright_b200.distributed import PipelinedSolveGather
-        pipe = PipelinedSolveGather(mpc, B)   # packed [X | U] results, ONE all-gather per step on a side stream
+        from upright_b200.distributed import FusedSolveGather, PipelinedSolveGather
+        if args.gather == "fused":
+            try:   # the solve kernel's epilogue stores every instance into the peers' gathered buffers (NVLink P2P)
+                pipe, gather_kind = FusedSolveGather(mpc, B), "fused into the solve kernel (P2P stores from its epilogue, no collective kernel)"
+            except Exception as e:  # noqa: BLE001 — e.g. no peer access: fall back to the NCCL collective, and say so
+                print(f"[bench] fused gather unavailable ({e}); using the NCCL all-gather", file=sys.stderr)
+        if pipe is None:
+            pipe = PipelinedSolveGather(mpc, B)   # packed [X | U] results, ONE all-gather per step on a side stream
+            gather_kind = "ncclAllGather of the packed [X|U] results on a side stream under the next step's solve"
 
     def step(s):
         d = dsets[s]
@@ -252,7 +340,7 @@ def main():
         dist.barrier()
     launches0 = lib.ub_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kern_ms, iters, ok = [], [], []
+    iters, ok = [], []
     torch.cuda.synchronize()
     t_begin = sampler.mark()
     ev0.record()
@@ -268,11 +356,10 @@ def main():
     launches = lib.ub_launch_count() - launches0
     t_end = sampler.mark()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
-    # per-launch kernel duration + iteration statistics (outside the timed region)
-    for s in range(args.warmup, min(nsets, args.warmup + 5)):
+    # iteration statistics of a few steps (outside the timed region)
+    for s in range(args.warmup, min(nsets, args.warmup + 3)):
         step(s)
         torch.cuda.synchronize()
-        kern_ms.append(mpc.last_solve_ms())
         st, ss = (pipe.stats, pipe.status) if pipe is not None else (stats, status)
         iters.append(float(st[:, 0].double().mean().item()))
         ok.append(float((ss == 0).double().mean().item()))
@@ -318,44 +405,72 @@ def main():
                        "status_counts": out["status_counts"].sum(axis=0).tolist(),
                        "api": "BatchedMPC.closed_loop -> ub_closed_loop (host x0 in, final state out, everything else on the device)"}
 
+    # measured FP32 multiply-add peak of this GPU (register-resident FMA loop, ub_measure_fma_peak)
+    pk = ctypes.c_double()
+    check(lib.ub_measure_fma_peak(ctypes.byref(pk)))
+    fp32_peak = float(pk.value)
+
+    # every BASELINE configuration at its per-GPU batch (cfg4 / cfg5: BASELINE's 8-GPU split when world = 8)
+    configs = None
+    if not args.no_configs:
+        configs = {}
+        for name in PER_GPU_BATCH:
+            try:
+                configs[name.split("_")[0]] = config_block(name, args.precision, world, dev, fp32_peak)
+            except Exception as e:  # noqa: BLE001 — a failing extra must not cost the headline line
+                configs[name.split("_")[0]] = {"error": str(e)[:300]}
+
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
 
+    if gather_kind:
+        config["parallelism"] = f"dp{world} (independent instances sharded, no exchange during the solve; result gather: {gather_kind})"
     peaks, peak_kind = measured_peaks()
-    kms = float(np.mean(kern_ms))
+    kms = ms_total / args.steps          # the solve kernel (+ a 4-byte memset of its work queue) is the whole step
     abytes = workload.algorithmic_bytes_per_solve(desc) * B
     achieved_gbs = abytes / (kms * 1e-3) / 1e9
     mean_iters = float(np.mean(iters))
     flops = workload.algorithmic_flops_per_solve(desc, mean_iters, desc.sqp_iteration) * B
-    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal CUDA-core FMA peak, TFLOP/s
+    tflops = flops / (kms * 1e-3) / 1e12
     traffic, traffic_src = measured_traffic(args.config, B)
-    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
-                "kernel": "ub::solve_batch_kernel", "kernel_ms": kms, "algorithmic_bytes_per_launch": abytes,
-                "note": "compulsory I/O is ~3.7 KB/solve: the kernel is on-chip (FP32 pipe / shared memory) bound by "
-                        "construction (SURVEY.md §8d); fp32 figures below use the algorithmic flop count",
-                "fp32": {"achieved_tflops": flops / (kms * 1e-3) / 1e12, "peak_tflops": fp32_peak,
-                         "frac": flops / (kms * 1e-3) / 1e12 / fp32_peak, "peak_source": "nominal 148 SM x 128 FMA/clk x 1.965 GHz",
-                         "mean_ipm_iterations": mean_iters, "algorithmic_flops_per_launch": flops}}
-    cpu_rate, cpu_n, cpu_el = oracle_rate(desc, sets[0], cores, min_seconds=args.cpu_seconds) if world == 1 else (None, 0, 0)
+    roofline = {"bound": "fp32-issue", "achieved": tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tflops / fp32_peak,
+                "traffic": traffic, "traffic_ratio": (traffic / abytes) if traffic else None, "traffic_source": traffic_src,
+                "peak_source": "measured in this run: ub_measure_fma_peak (16 independent FMA chains per thread on every SM)",
+                "kernel": "ub::solve_batch_kernel", "kernel_ms": kms, "algorithmic_flops_per_launch": flops,
+                "mean_ipm_iterations": mean_iters,
+                "note": "many small dependent factorisations: the binding resources are FP32/FP64 issue and shared-memory "
+                        "latency (SURVEY.md §8d); the algorithmic flop count is SURVEY.md §8(d)'s dense-Riccati convention, "
+                        "the kernels execute fewer (forces eliminated, A and B structured)",
+                "hbm": {"achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
+                        "algorithmic_bytes_per_launch": abytes, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                        "note": "compulsory I/O is ~3.7 KB per solve: HBM is not the roof by construction"}}
+    cpu_seconds = args.cpu_seconds if world == 1 else min(args.cpu_seconds, 5.0)
+    cpu_rate, cpu_n, cpu_el = oracle_rate(desc, sets[0], cores, min_seconds=cpu_seconds)
+    cpu1_rate, cpu1_n, cpu1_el = oracle_rate(desc, sets[0], 1, min_seconds=min(3.0, cpu_seconds), chunk=8)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic", "config": config, "clocks": clocks,
+            "arithmetic": "f32: Riccati recursion (matrices, factors, directions) in fp32; iterate, slack / multiplier records, "
+                          "residuals, linearisation and the force block in fp64" if args.precision == "f32" else "fp64 throughout",
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "upright_b200.engine.BatchedMPC.solve -> ub_solve_batch (host double buffers in/out; inputs H2D from pinned staging, every solved instance written home by the kernel through mapped pinned memory and converted float->double by host threads behind its completion flag while the kernel runs)",
                     "steps": e2e_steps},
             "gpu_launches": int(launches), "roofline": roofline,
             "converged_fraction": float(np.mean(ok)), "mean_qp_iterations": mean_iters}
+    if configs is not None:
+        line["configs"] = configs
     if closed_loop is not None:
         line["closed_loop"] = closed_loop
-    if cpu_rate is not None:
-        line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{cpu_n} instances of the same workload in {cpu_el:.1f} s, oracle-CPU "
-                                          f"(restated OCS2-equivalent, fp64, dense Riccati), {cores} host threads"}
+    line["cpu_baseline"] = {"value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{cpu_n} instances of the same workload in {cpu_el:.1f} s, oracle-CPU "
+                                      f"(restated OCS2-equivalent, fp64, dense Riccati), {cores} host threads",
+                            "single_core": {"value": cpu1_rate, "sample": f"{cpu1_n} instances in {cpu1_el:.1f} s, 1 thread"}}
     emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 

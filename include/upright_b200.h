@@ -33,6 +33,7 @@ extern "C" {
 #define UB_MAX_PROJECTILE_LINKS 8
 #define UB_MAX_NX (3 * UB_MAX_JOINTS)
 #define UB_BODY_PARAMS 10 /* m, m*com(3), vech(I)(6): rigid_body.h:36-54 */
+#define UB_MAX_GATHER 8   /* peer GPUs whose gathered buffers a solve writes into (ub_set_gather_targets) */
 #define UB_STATS 8
 
 enum {
@@ -243,7 +244,8 @@ int64_t ub_workspace_bytes(const ub_problem_t* problem, int32_t B, uint32_t flag
  *                            (interpolate_end_effector_pose, reference_trajectory.h:18-47)
  *   body_params [B, nb, 10]  per-instance inertial parameters or NULL (shared)
  *   X  [B, N+1, nx], U [B, N, nu]  solution (in/out when UB_WARM_START)
- *   K  [B, N, nu, nx] Riccati feedback gains or NULL
+ *   K  [B, N, nu, 3 nq] Riccati feedback gains or NULL (over the ROBOT state: the dynamic-obstacle states that
+ *      ub_problem_dims counts in nx are uncontrolled and carry no gain columns)
  *   status [B] int32, stats [B, UB_STATS] or NULL
  *      stats = {qp_iters, cost, violation, step alpha, qp_residual,
  *               max |object-dynamics eq|, min ineq margin, reserved}
@@ -265,7 +267,9 @@ int ub_solve_batch(ub_problem_t* problem, int32_t B, const void* x0, const void*
  * at M (x,u) pairs on the device.  Host double pointers.
  *   name in {"object_dynamics","contact_forces","obstacle_avoidance",
  *            "end_effector_box_constraint" (needs target),"end_effector_position","cost",
- *            "inertial_alignment_cost","inertial_alignment_constraint","projectile_constraint"}
+ *            "inertial_alignment_cost","inertial_alignment_constraint","projectile_constraint",
+ *            "end_effector_jacobian" (3 x nq, row-major), "object_dynamics_jacobian" (neq x (nx + nu): [dg/dx | dg/du],
+ *            what BalancingConstraintWrapper::getLinearApproximation exposes, balancing_constraint_wrapper.h:45-60)}
  *   out [M, rows]; rows returned through *rows_out. */
 int ub_eval(ub_problem_t* problem, const char* name, int32_t M, const double* x,
             const double* u, const double* target /*[M,3] or NULL*/,
@@ -295,12 +299,41 @@ typedef struct ub_closed_loop_params {
  * (pybindings.cpp:378-381), and the model's own triple integrator as the plant.  Everything stays on the
  * device between the first upload and the final download.  Host double pointers.
  *   x0 [B, nx]; target_times [M] increasing; target_pos [B, M, 3]; body_params [B, nb, 10] or NULL
+ *   (nx as ub_problem_dims reports it: 3 nq + 9 per dynamic obstacle; the obstacle columns of x0 are their states at
+ *   the start, and they evolve by ub_closed_loop_set_obstacles)
  *   xs [B, n_log, nx], us [B, n_log, nq] (n_log = ceil(n_steps / log_stride)) or both NULL
  *   x_final [B, nx] or NULL; *n_replans or NULL; status_counts [B, 4] (solves per UB_STATUS_*) or NULL */
 int ub_closed_loop(ub_problem_t* problem, int32_t B, const double* x0, const double* target_times,
                    const double* target_pos, int32_t M, const double* body_params,
                    const ub_closed_loop_params_t* params, double* xs, double* us, double* x_final,
                    int32_t* n_replans, int32_t* status_counts, uint32_t flags, void* cuda_stream);
+
+/* Simulated dynamic obstacles of ub_closed_loop (the uncontrolled obstacles of the reference's simulation,
+ * upright_sim/src/upright_sim/simulation.py:300-435, configured under `simulation.dynamic_obstacles.obstacles`, e.g.
+ * upright_cmd/config/obstacles/dynamic.yaml:38-75): free flight under the current mode's acceleration; at the first
+ * simulation step whose start time has reached the next mode's `time` the state is reset to that mode's position
+ * (+ the instance's offset, for `relative` obstacles) and velocity.  The obstacle columns of the plant state are what
+ * the controller observes at every replan (mpc_sim.py:120-121).  One entry per dynamic obstacle of the problem, in
+ * order; modes [n_obstacles][UB_MAX_OBSTACLE_MODES]; offsets [B, n_obstacles, 3] or NULL.  Without a plant the
+ * obstacle states of x0 fly freely under their own acceleration.  n_obstacles = 0 removes the plant. */
+#define UB_MAX_OBSTACLE_MODES 8
+typedef struct ub_obstacle_mode {
+    double time;
+    double position[3], velocity[3], acceleration[3];
+} ub_obstacle_mode_t;
+int ub_closed_loop_set_obstacles(ub_problem_t* problem, int32_t n_obstacles, const int32_t* n_modes,
+                                 const ub_obstacle_mode_t* modes, int32_t B, const double* offsets);
+
+/* Multi-GPU gather fused into the solve (no counterpart in the reference, which is single-process):
+ * after this call every device-mode ub_solve_batch stores the trajectories of instance b not only to its X / U
+ * arguments but also to row `row_offset + b` of each of the `n` (<= UB_MAX_GATHER) peer buffers
+ *     X_bases[p] : [rows, N+1, nx],   U_bases[p] : [rows, N, nu]      (same element type as X / U)
+ * which are device pointers of OTHER GPUs mapped into this process (CUDA IPC; peer access enabled) — the solve
+ * kernel's epilogue writes them over NVLink while the rest of the batch is still being solved, so the all-gather
+ * of the results needs no collective kernel and no copy.  n = 0 switches it off.  The caller synchronises the
+ * ranks (one barrier) before any rank reads its gathered buffer. */
+int ub_set_gather_targets(ub_problem_t* problem, int32_t n, void* const* X_bases, void* const* U_bases,
+                          int64_t row_offset);
 
 /* Runtime options: "sqp_iteration" (init_sqp_iteration vs sqp_iteration,
  * controller.yaml:56-57), "projectile_active" (the target-state flag s of the
@@ -316,6 +349,10 @@ int ub_workspace_layout(const ub_problem_t* problem, uint32_t flags, int32_t out
 /* Device time of the last ub_solve_batch on this problem (CUDA events), ms.
  * Replaces getLastSolveTime() (controller_python_interface.h:27-29). */
 float ub_last_solve_ms(const ub_problem_t* problem);
+
+/* Measured FP32 multiply-add throughput of the current device in TFLOP/s (a register-resident FMA loop on every SM):
+ * the denominator of the arithmetic roofline bench.py reports for the solve kernel. */
+int ub_measure_fma_peak(double* tflops);
 
 /* Number of kernel launches issued by this library since load. */
 int64_t ub_launch_count(void);

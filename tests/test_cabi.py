@@ -34,14 +34,14 @@ def test_struct_sizes_match_header(lib):
     """ctypes mirror and C struct agree (compiled probe with gcc)."""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "upright_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu", sizeof(ub_problem_desc_t), sizeof(ub_joint_t), sizeof(ub_contact_t), sizeof(ub_sphere_t), sizeof(ub_closed_loop_params_t));return 0;}'
+    src = '#include <stdio.h>\n#include "upright_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu", sizeof(ub_problem_desc_t), sizeof(ub_joint_t), sizeof(ub_contact_t), sizeof(ub_sphere_t), sizeof(ub_closed_loop_params_t), sizeof(ub_obstacle_mode_t));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         p = Path(d) / "probe.c"
         p.write_text(src)
         subprocess.check_call(["gcc", "-I", str(ROOT / "include"), str(p), "-o", str(Path(d) / "probe")])
         sizes = list(map(int, subprocess.check_output([str(Path(d) / "probe")]).split()))
     from upright_b200 import bindings as B
-    assert sizes == [C.sizeof(B.ProblemDesc), C.sizeof(B.Joint), C.sizeof(B.Contact), C.sizeof(B.Sphere), C.sizeof(B.ClosedLoopParams)]
+    assert sizes == [C.sizeof(B.ProblemDesc), C.sizeof(B.Joint), C.sizeof(B.Contact), C.sizeof(B.Sphere), C.sizeof(B.ClosedLoopParams), C.sizeof(B.ObstacleMode)]
 
 
 def test_sass_is_sm100a(lib):

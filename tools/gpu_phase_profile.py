@@ -28,3 +28,13 @@ print("profile-mode ms", mpc.last_solve_ms(), "mean iters", st[:, 0].mean(), "ma
 for i in range(1, 8):
     print(f"  {names[i]:14s} mean {st[:, i].mean() / 1e6:8.3f} Mcyc  ({100 * st[:, i].mean() / tot.mean():5.1f} %)  per-iter {st[:, i].mean() / st[:, 0].mean() / 1e3:8.1f} kcyc")
 print("  total per warp %.2f Mcyc" % (tot.mean() / 1e6))
+
+mpc.set_option("stop_after", 8)
+out = mpc.solve_device(x0, tg, bp)
+torch.cuda.synchronize()
+st = out["stats"].double().cpu().numpy()
+tot = st[:, 3].mean()
+print("whole-solve profile (Mcyc per warp): total %.2f | linearise %.2f (%.0f %%) | interior point %.2f (%.0f %%) | line search %.2f (%.0f %%) | "
+      "init (Df + base performance) %.2f (%.0f %%)" % (tot / 1e6, st[:, 1].mean() / 1e6, 100 * st[:, 1].mean() / tot, st[:, 4].mean() / 1e6,
+                                                     100 * st[:, 4].mean() / tot, st[:, 2].mean() / 1e6, 100 * st[:, 2].mean() / tot,
+                                                     st[:, 5].mean() / 1e6, 100 * st[:, 5].mean() / tot))

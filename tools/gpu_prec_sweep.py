@@ -27,4 +27,5 @@ for name, B in [("cfg1_ur10_demo", 4096), ("cfg2_thing_demo", 4096), ("cfg3_thin
         it = out["stats"][:, 0].double()
         st = out["status"]
         print(f"{name:24s} {prec} B={B:5d} ms {min(ts[1:]):8.3f} solves/s {B / min(ts[1:]) * 1e3:9.0f} iters mean {it.mean():.2f} max {it.max():.0f} "
-              f"status {[int((st == s).sum()) for s in range(4)]} smem/warp {mpc.layout()['s_total'] * (4 if prec == 'f32' else 8)} B", flush=True)
+              f"status {[int((st == s).sum()) for s in range(4)]} smem/warp {mpc.layout()['s_total'] * (4 if prec == 'f32' else 8)} B "
+              f"slot {mpc.layout()['total'] * (4 if prec == 'f32' else 8) // 1024} KB nan-reasons {sorted(set(out['stats'][:, 3][st == 3].cpu().numpy().astype(int).tolist()))}", flush=True)

@@ -19,6 +19,7 @@ UB_MAX_PROJECTILE_LINKS = 8
 UB_MAX_NX = 27
 UB_BODY_PARAMS = 10
 UB_STATS = 8
+UB_MAX_GATHER = 8
 
 UB_PTRS_DEVICE = 0x1
 UB_WARM_START = 0x2
@@ -61,6 +62,15 @@ class ClosedLoopParams(C.Structure):
                 ("log_stride", C.c_int32), ("use_feedback", C.c_int32), ("cold_start", C.c_int32),
                 ("init_sqp_iteration", C.c_int32), ("sqp_iteration", C.c_int32),
                 ("kp", C.c_double), ("kv", C.c_double), ("ka", C.c_double)]
+
+
+UB_MAX_OBSTACLE_MODES = 8
+
+
+class ObstacleMode(C.Structure):
+    """ub_obstacle_mode_t"""
+    _fields_ = [("time", C.c_double), ("position", C.c_double * 3), ("velocity", C.c_double * 3),
+                ("acceleration", C.c_double * 3)]
 
 
 class ProblemDesc(C.Structure):
@@ -174,6 +184,12 @@ def load_library():
     lib.ub_last_solve_ms.argtypes = [vp]
     lib.ub_last_solve_ms.restype = C.c_float
     lib.ub_launch_count.restype = C.c_int64
+    lib.ub_closed_loop_set_obstacles.argtypes = [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(ObstacleMode), C.c_int32, vp]
+    lib.ub_closed_loop_set_obstacles.restype = C.c_int
+    lib.ub_set_gather_targets.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.c_int64]
+    lib.ub_set_gather_targets.restype = C.c_int
+    lib.ub_measure_fma_peak.argtypes = [C.POINTER(C.c_double)]
+    lib.ub_measure_fma_peak.restype = C.c_int
     _lib = lib
     return lib
 
@@ -182,6 +198,7 @@ EXPORTED_SYMBOLS = [
     "ub_last_error", "ub_version", "ub_problem_create", "ub_problem_destroy",
     "ub_problem_dims", "ub_workspace_bytes", "ub_solve_batch", "ub_eval",
     "ub_last_solve_ms", "ub_launch_count", "ub_set_option", "ub_workspace_layout", "ub_closed_loop",
+    "ub_measure_fma_peak", "ub_set_gather_targets", "ub_closed_loop_set_obstacles",
 ]
 
 

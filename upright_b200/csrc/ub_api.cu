@@ -330,6 +330,16 @@ struct ub_problem {
     size_t pinned_bytes = 0;
     void* cl_buf = nullptr;   // closed-loop arena
     size_t cl_buf_bytes = 0;
+    // peer-mapped gathered buffers every device-mode solve also writes into (ub_set_gather_targets)
+    // simulated dynamic obstacles of the closed loop (ub_closed_loop_set_obstacles)
+    std::vector<ub::ObstacleMode> cl_modes;     // [ndyn][UB_MAX_OBSTACLE_MODES]
+    std::vector<int> cl_n_modes;                // [ndyn]
+    std::vector<double> cl_offsets;             // [B, ndyn, 3] or empty
+    int cl_offsets_B = 0;
+    int n_gather = 0;
+    void* gather_X[UB_MAX_GATHER] = {};
+    void* gather_U[UB_MAX_GATHER] = {};
+    int64_t gather_row = 0;
 };
 
 namespace {
@@ -443,7 +453,7 @@ int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
 template <typename T>
 int solve_device(ub_problem* p, int B, const void* x0, const void* target, const void* body, void* X, void* U, void* K,
                  int32_t* status, void* stats, void* ws, int64_t ws_bytes, uint32_t flags, cudaStream_t stream,
-                 int gain_stages = -1, const void* Xin = nullptr, const void* Uin = nullptr) {
+                 int gain_stages = -1, const void* Xin = nullptr, const void* Uin = nullptr, bool gather = false) {
     const ub::Layout& L = Pick<T>::layout(p);
     if (ws_bytes < workspace_bytes<T>(p, B)) return fail(UB_E_INVALID, "workspace too small (see ub_workspace_bytes)");
     if (reinterpret_cast<uintptr_t>(ws) % 16 != 0) return fail(UB_E_INVALID, "workspace must be 16-byte aligned");
@@ -464,6 +474,12 @@ int solve_device(ub_problem* p, int B, const void* x0, const void* target, const
     A.stop_after = p->stop_after;
     A.gain_stages = gain_stages < 0 ? Pick<T>::host(p).N : gain_stages;
     A.nxt = Pick<T>::host(p).nx + Pick<T>::host(p).nxo;
+    A.ngather = gather ? p->n_gather : 0;   // the caller's device-mode solves only (not the host path, not the closed loop)
+    A.gather_row = p->gather_row;
+    for (int i = 0; i < UB_MAX_GATHER; ++i) {
+        A.Xg[i] = i < A.ngather ? static_cast<T*>(p->gather_X[i]) : nullptr;
+        A.Ug[i] = i < A.ngather ? static_cast<T*>(p->gather_U[i]) : nullptr;
+    }
     UB_CUDA(cudaEventRecord(p->ev0, stream));
     int rc = launch_solve<T>(p, A, stream);
     if (rc != UB_OK) return rc;
@@ -644,7 +660,7 @@ int closed_loop(ub_problem* p, int B, const double* x0, const double* target_tim
                 int32_t* n_replans, int32_t* status_counts, uint32_t flags, cudaStream_t stream) {
     const ub::DevProblem<T>& P = Pick<T>::host(p);
     const ub::Layout& L = Pick<T>::layout(p);
-    const int N = P.N, nx = P.nx, nu = P.nu, nq = P.nq;
+    const int N = P.N, nx = P.nx, nu = P.nu, nq = P.nq, ndyn = P.ndyn, nxt = P.nx + P.nxo;
     const int stride = std::max(1, prm.log_stride);
     const int n_log = (xs || us) ? (prm.n_steps + stride - 1) / stride : 0;
     const int gain_stages = prm.use_feedback ? std::min(N, int(std::floor(prm.replan_period / P.dt + 1e-9)) + 2) : 0;
@@ -657,14 +673,22 @@ int closed_loop(ub_problem* p, int B, const double* x0, const double* target_tim
             return base ? static_cast<void*>(base + at) : reinterpret_cast<void*>(uintptr_t(256));
         }
     } dev;
-    const size_t nX = size_t(B) * (N + 1) * nx, nU = size_t(B) * N * nu;
-    T *d_x, *d_pos, *d_body, *d_target, *d_X[2], *d_U[2], *d_K, *d_stats, *d_ws, *d_xs, *d_us;
+    const size_t nX = size_t(B) * (N + 1) * nxt, nU = size_t(B) * N * nu;
+    T *d_x, *d_pos, *d_body, *d_target, *d_X[2], *d_U[2], *d_K, *d_stats, *d_ws, *d_xs, *d_us, *d_off;
     double* d_times;
     int32_t *d_status, *d_counts;
+    ub::ObstacleMode* d_modes;
+    int *d_nmodes, *d_midx;
+    const bool plant = ndyn > 0 && int(p->cl_n_modes.size()) == ndyn;
+    const bool have_off = plant && !p->cl_offsets.empty() && p->cl_offsets_B == B;
     // the arena is one cached allocation per problem (grown on demand, freed with the problem): repeated rollouts do
     // not pay for cudaMalloc / cudaFree of the ~250 MB workspace.  The carve list runs twice: size, then place.
     auto carve = [&]() {
-        d_x = static_cast<T*>(dev.bytes((size_t(B) * nx) * sizeof(T)));
+        d_x = static_cast<T*>(dev.bytes((size_t(B) * nxt) * sizeof(T)));
+        d_modes = plant ? static_cast<ub::ObstacleMode*>(dev.bytes(size_t(ndyn) * UB_MAX_OBSTACLE_MODES * sizeof(ub::ObstacleMode))) : nullptr;
+        d_nmodes = plant ? static_cast<int*>(dev.bytes(size_t(ndyn) * sizeof(int))) : nullptr;
+        d_off = have_off ? static_cast<T*>(dev.bytes(size_t(B) * ndyn * 3 * sizeof(T))) : nullptr;
+        d_midx = static_cast<int*>(dev.bytes(size_t(B) * std::max(ndyn, 1) * sizeof(int)));
         d_pos = static_cast<T*>(dev.bytes((size_t(B) * M * 3) * sizeof(T)));
         d_times = static_cast<double*>(dev.bytes((M) * sizeof(double)));
         d_body = body ? static_cast<T*>(dev.bytes((size_t(B) * P.nb * UB_BODY_PARAMS) * sizeof(T))) : nullptr;
@@ -678,7 +702,7 @@ int closed_loop(ub_problem* p, int B, const double* x0, const double* target_tim
         d_status = static_cast<int32_t*>(dev.bytes((B) * sizeof(int32_t)));
         d_counts = static_cast<int32_t*>(dev.bytes((size_t(B) * 4) * sizeof(int32_t)));
         d_ws = static_cast<T*>(dev.bytes(size_t(workspace_bytes<T>(p, B)) + 64));
-        d_xs = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nx) * sizeof(T))) : nullptr;
+        d_xs = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nxt) * sizeof(T))) : nullptr;
         d_us = n_log ? static_cast<T*>(dev.bytes((size_t(B) * n_log * nq) * sizeof(T))) : nullptr;
     };
     carve();
@@ -694,10 +718,22 @@ int closed_loop(ub_problem* p, int B, const double* x0, const double* target_tim
     carve();
     while (reinterpret_cast<uintptr_t>(d_ws) % 16 != 0) ++d_ws;
     {
-        std::vector<T> h(std::max(std::max(size_t(B) * nx, size_t(B) * M * 3), body ? size_t(B) * P.nb * UB_BODY_PARAMS : size_t(0)));
-        convert_array(h.data(), x0, size_t(B) * nx);
-        UB_CUDA(cudaMemcpyAsync(d_x, h.data(), size_t(B) * nx * sizeof(T), cudaMemcpyHostToDevice, stream));
+        std::vector<T> h(std::max(std::max(std::max(size_t(B) * nxt, size_t(B) * M * 3), body ? size_t(B) * P.nb * UB_BODY_PARAMS : size_t(0)),
+                                  size_t(B) * std::max(ndyn, 1) * 3));
+        convert_array(h.data(), x0, size_t(B) * nxt);
+        UB_CUDA(cudaMemcpyAsync(d_x, h.data(), size_t(B) * nxt * sizeof(T), cudaMemcpyHostToDevice, stream));
         UB_CUDA(cudaStreamSynchronize(stream));
+        UB_CUDA(cudaMemsetAsync(d_midx, 0, size_t(B) * std::max(ndyn, 1) * sizeof(int), stream));
+        if (plant) {
+            UB_CUDA(cudaMemcpyAsync(d_modes, p->cl_modes.data(), size_t(ndyn) * UB_MAX_OBSTACLE_MODES * sizeof(ub::ObstacleMode),
+                                    cudaMemcpyHostToDevice, stream));
+            UB_CUDA(cudaMemcpyAsync(d_nmodes, p->cl_n_modes.data(), size_t(ndyn) * sizeof(int), cudaMemcpyHostToDevice, stream));
+            if (have_off) {
+                convert_array(h.data(), p->cl_offsets.data(), size_t(B) * ndyn * 3);
+                UB_CUDA(cudaMemcpyAsync(d_off, h.data(), size_t(B) * ndyn * 3 * sizeof(T), cudaMemcpyHostToDevice, stream));
+            }
+            UB_CUDA(cudaStreamSynchronize(stream));
+        }
         convert_array(h.data(), target_pos, size_t(B) * M * 3);
         UB_CUDA(cudaMemcpyAsync(d_pos, h.data(), size_t(B) * M * 3 * sizeof(T), cudaMemcpyHostToDevice, stream));
         UB_CUDA(cudaStreamSynchronize(stream));
@@ -729,7 +765,7 @@ int closed_loop(ub_problem* p, int B, const double* x0, const double* target_tim
             ++g_launches;
             if (warm) {
                 const size_t tot = nX + nU;
-                ub::rh_shift_kernel<T><<<unsigned((tot + 255) / 256), 256, 0, stream>>>(B, N, nx, nu, double(P.dt), t0, t, d_X[cur],
+                ub::rh_shift_kernel<T><<<unsigned((tot + 255) / 256), 256, 0, stream>>>(B, N, nxt, nu, double(P.dt), t0, t, d_X[cur],
                                                                                    d_U[cur], d_X[cur ^ 1], d_U[cur ^ 1]);
                 ++g_launches;
                 cur ^= 1;
@@ -749,7 +785,8 @@ int closed_loop(ub_problem* p, int B, const double* x0, const double* target_tim
         int n_sub = 1;
         while (step + n_sub < prm.n_steps && !(prm.sim_dt * (step + n_sub) >= last_plan + prm.replan_period)) ++n_sub;
         ub::RolloutArgs<T> R;
-        R.B = B; R.N = N; R.nq = nq; R.nx = nx; R.nu = nu;
+        R.B = B; R.N = N; R.nq = nq; R.nx = nx; R.nu = nu; R.nxt = nxt; R.ndyn = ndyn;
+        R.modes = d_modes; R.n_modes = d_nmodes; R.max_modes = UB_MAX_OBSTACLE_MODES; R.offsets = d_off; R.mode_idx = d_midx;
         R.dt = double(P.dt); R.t0 = t0; R.t_first = t; R.sim_dt = prm.sim_dt;
         R.n_sub = n_sub; R.step0 = step; R.log_stride = stride; R.n_log = n_log;
         R.use_feedback = prm.use_feedback; R.gain_stages = gain_stages;
@@ -773,14 +810,30 @@ int closed_loop(ub_problem* p, int B, const double* x0, const double* target_tim
         convert_array(dst, h.data(), n);
         return UB_OK;
     };
-    if ((rc = fetch(xs, d_xs, size_t(B) * n_log * nx)) != UB_OK) return rc;
+    if ((rc = fetch(xs, d_xs, size_t(B) * n_log * nxt)) != UB_OK) return rc;
     if ((rc = fetch(us, d_us, size_t(B) * n_log * nq)) != UB_OK) return rc;
-    if ((rc = fetch(x_final, d_x, size_t(B) * nx)) != UB_OK) return rc;
+    if ((rc = fetch(x_final, d_x, size_t(B) * nxt)) != UB_OK) return rc;
     if (status_counts) UB_CUDA(cudaMemcpy(status_counts, d_counts, size_t(B) * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (n_replans) *n_replans = replans;
     return UB_OK;
 }
 
+}  // namespace
+
+namespace {
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = float(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += v[i];
+    if (s == 123.456f) out[0] = s;   // never true: keeps the chains alive
+}
 }  // namespace
 
 extern "C" {
@@ -927,6 +980,61 @@ int ub_set_option(ub_problem_t* p, const char* key, int value) {
     }
     return fail(UB_E_INVALID, std::string("unknown option ") + key);
 }
+int ub_closed_loop_set_obstacles(ub_problem_t* p, int32_t n_obstacles, const int32_t* n_modes, const ub_obstacle_mode_t* modes,
+                                 int32_t B, const double* offsets) {
+    if (!p) return fail(UB_E_INVALID, "null problem");
+    if (n_obstacles == 0) {
+        p->cl_modes.clear();
+        p->cl_n_modes.clear();
+        p->cl_offsets.clear();
+        p->cl_offsets_B = 0;
+        return UB_OK;
+    }
+    if (n_obstacles != p->hf.ndyn) return fail(UB_E_INVALID, "one simulated obstacle per dynamic obstacle of the problem");
+    if (!n_modes || !modes) return fail(UB_E_INVALID, "null argument");
+    p->cl_modes.assign(size_t(n_obstacles) * UB_MAX_OBSTACLE_MODES, ub::ObstacleMode{});
+    p->cl_n_modes.assign(n_obstacles, 0);
+    for (int j = 0; j < n_obstacles; ++j) {
+        if (n_modes[j] < 1 || n_modes[j] > UB_MAX_OBSTACLE_MODES) return fail(UB_E_INVALID, "1 .. UB_MAX_OBSTACLE_MODES modes per obstacle");
+        p->cl_n_modes[j] = n_modes[j];
+        for (int m = 0; m < n_modes[j]; ++m) {
+            const ub_obstacle_mode_t& s = modes[size_t(j) * UB_MAX_OBSTACLE_MODES + m];
+            if (m > 0 && !(s.time > modes[size_t(j) * UB_MAX_OBSTACLE_MODES + m - 1].time))
+                return fail(UB_E_INVALID, "mode times must increase");
+            ub::ObstacleMode& d = p->cl_modes[size_t(j) * UB_MAX_OBSTACLE_MODES + m];
+            d.time = s.time;
+            for (int c = 0; c < 3; ++c) {
+                d.p[c] = s.position[c];
+                d.v[c] = s.velocity[c];
+                d.a[c] = s.acceleration[c];
+            }
+        }
+    }
+    p->cl_offsets.clear();
+    p->cl_offsets_B = 0;
+    if (offsets) {
+        if (B <= 0) return fail(UB_E_INVALID, "offsets need the batch size");
+        p->cl_offsets.assign(offsets, offsets + size_t(B) * n_obstacles * 3);
+        p->cl_offsets_B = B;
+    }
+    return UB_OK;
+}
+
+int ub_set_gather_targets(ub_problem_t* p, int32_t n, void* const* X_bases, void* const* U_bases, int64_t row_offset) {
+    if (!p) return fail(UB_E_INVALID, "null problem");
+    if (n < 0 || n > UB_MAX_GATHER) return fail(UB_E_INVALID, "at most UB_MAX_GATHER gather targets");
+    if (n > 0 && (!X_bases || !U_bases)) return fail(UB_E_INVALID, "null gather targets");
+    if (row_offset < 0) return fail(UB_E_INVALID, "negative row offset");
+    for (int i = 0; i < n; ++i)
+        if (!X_bases[i] || !U_bases[i]) return fail(UB_E_INVALID, "null gather target");
+    p->n_gather = n;
+    p->gather_row = row_offset;
+    for (int i = 0; i < n; ++i) {
+        p->gather_X[i] = X_bases[i];
+        p->gather_U[i] = U_bases[i];
+    }
+    return UB_OK;
+}
 int ub_workspace_layout(const ub_problem_t* p, uint32_t flags, int32_t out[80]) {
     if (!p) return fail(UB_E_INVALID, "null problem");
     const ub::Layout& L = (flags & UB_COMPUTE_F64) ? p->Ld : p->Lf;
@@ -947,9 +1055,9 @@ int ub_solve_batch(ub_problem_t* p, int32_t B, const void* x0, const void* targe
     if (flags & UB_PTRS_DEVICE) {
         if (!workspace) return fail(UB_E_INVALID, "device mode needs a workspace");
         return f64 ? solve_device<double>(p, B, x0, target, body_params, X, U, K, status, stats, workspace,
-                                          workspace_bytes, flags, stream)
+                                          workspace_bytes, flags, stream, -1, nullptr, nullptr, true)
                    : solve_device<float>(p, B, x0, target, body_params, X, U, K, status, stats, workspace,
-                                         workspace_bytes, flags, stream);
+                                         workspace_bytes, flags, stream, -1, nullptr, nullptr, true);
     }
     return f64 ? solve_host<double>(p, B, static_cast<const double*>(x0), static_cast<const double*>(target),
                                     static_cast<const double*>(body_params), static_cast<double*>(X),
@@ -965,7 +1073,6 @@ int ub_closed_loop(ub_problem_t* p, int32_t B, const double* x0, const double* t
                    int32_t M, const double* body_params, const ub_closed_loop_params_t* params, double* xs, double* us,
                    double* x_final, int32_t* n_replans, int32_t* status_counts, uint32_t flags, void* cuda_stream) {
     if (!p || !x0 || !target_times || !target_pos || !params) return fail(UB_E_INVALID, "null argument");
-    if (p->hf.ndyn > 0) return fail(UB_E_INVALID, "ub_closed_loop does not simulate dynamic obstacles");
     if (B <= 0 || M <= 0) return fail(UB_E_INVALID, "B and M must be positive");
     if (!(params->sim_dt > 0) || !(params->replan_period > 0) || params->n_steps <= 0)
         return fail(UB_E_INVALID, "sim_dt, replan_period and n_steps must be positive");
@@ -979,6 +1086,38 @@ int ub_closed_loop(ub_problem_t* p, int32_t B, const double* x0, const double* t
                                      n_replans, status_counts, flags, stream)
                : closed_loop<float>(p, B, x0, target_times, target_pos, M, body_params, *params, xs, us, x_final,
                                     n_replans, status_counts, flags, stream);
+}
+
+// FP32 FMA throughput of the current device, measured: the denominator of the solve kernel's arithmetic roofline
+// (bench.py).  Every thread runs 16 independent multiply-add chains for `iters` rounds; 2 flops per FMA.
+int ub_measure_fma_peak(double* tflops) {
+    if (!tflops) return fail(UB_E_INVALID, "null argument");
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail(UB_E_NO_DEVICE, "no CUDA device");
+    UB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    float* d_out = nullptr;
+    UB_CUDA(cudaMalloc(&d_out, sizeof(float)));
+    cudaEvent_t e0, e1;
+    UB_CUDA(cudaEventCreate(&e0));
+    UB_CUDA(cudaEventCreate(&e1));
+    const int iters = 1 << 14, grid = sms * 8, block = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<<<grid, block>>>(d_out, iters, 1.0000001f, 1e-9f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ++g_launches;
+        if (rep > 0 && ms > 0.f) best = std::max(best, 2.0 * 16.0 * double(iters) * grid * block / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    UB_CUDA(cudaGetLastError());
+    *tflops = best;
+    return UB_OK;
 }
 
 float ub_last_solve_ms(const ub_problem_t* p) {
@@ -996,7 +1135,8 @@ float ub_last_solve_ms(const ub_problem_t* p) {
 // thread per sample.
 namespace {
 
-enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4, EV_EEBOX = 5, EV_IACOST = 6, EV_IACON = 7, EV_PROJ = 8 };
+enum { EV_OBJDYN = 0, EV_CONTACT = 1, EV_OBST = 2, EV_EEPOS = 3, EV_COST = 4, EV_EEBOX = 5, EV_IACOST = 6, EV_IACON = 7, EV_PROJ = 8,
+       EV_OBJDYN_JAC = 9, EV_EEJAC = 10 };
 
 __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int what, int M, int rows,
                             const double* __restrict__ x, const double* __restrict__ u,
@@ -1020,6 +1160,49 @@ __global__ void eval_kernel(const ub::DevProblem<double>* __restrict__ Pg, int w
     const int nq = P.nq;
     if (what == EV_EEPOS) {
         o[0] = K.r.x; o[1] = K.r.y; o[2] = K.r.z;
+    } else if (what == EV_EEJAC) {   // d r / d q, 3 x nq (the linear part of getPositionLinearApproximation)
+        for (int dir = 0; dir < nq; ++dir) {
+            ub::Kin<double> Kt;
+            ub::KinTan<double> Dt;
+            ub::forward_kinematics<double, true>(P, xm, dir, Kt, Dt, nullptr, nullptr);
+            o[dir] = Dt.r.x; o[nq + dir] = Dt.r.y; o[2 * nq + dir] = Dt.r.z;
+        }
+    } else if (what == EV_OBJDYN_JAC) {
+        // [d g / d x (nx) | d g / d u (nu)] per row of the object-dynamics constraint: what
+        // ObjectDynamicsConstraints::getLinearApproximation returns through CppAD (balancing_constraints.cpp:114-155)
+        const double scale = rsqrt(double(6 * P.nb));
+        const int w = P.nx + P.nu;
+        for (int i = 0; i < P.neq * w; ++i) o[i] = 0.0;
+        for (int dir = 0; dir < P.nx; ++dir) {
+            ub::Kin<double> Kt;
+            ub::KinTan<double> Dt;
+            ub::forward_kinematics<double, true>(P, xm, dir, Kt, Dt, nullptr, nullptr);
+            for (int b = 0; b < P.nb; ++b) {
+                const ub::BodyP<double> Bd = ub::load_body<double>(bp + b * UB_BODY_PARAMS);
+                double g6[6], dg6[6];
+                ub::object_dynamics_state_part<double, true>(P, Bd, Kt, Dt, scale, g6, dg6);
+                for (int i = 0; i < 6; ++i) o[(6 * b + i) * w + dir] = dg6[i];
+            }
+        }
+        for (int c = 0; c < P.nc; ++c)
+            for (int comp = 0; comp < P.nf; ++comp) {
+                const ub::V3<double> e = P.nf == 1 ? ub::ld3(P.cn[c])
+                                                   : ub::V3<double>(comp == 0 ? 1.0 : 0.0, comp == 1 ? 1.0 : 0.0, comp == 2 ? 1.0 : 0.0);
+                const int col = P.nx + nq + c * P.nf + comp;
+                const int b1 = P.cb1[c], b2 = P.cb2[c];
+                if (b1 >= 0) {
+                    const ub::BodyP<double> Bd = ub::load_body<double>(bp + b1 * UB_BODY_PARAMS);
+                    const ub::V3<double> tq = ub::cross(ub::ld3(P.cr1[c]) - Bd.com, e);
+                    const double s = -scale / Bd.m;
+                    o[(6 * b1) * w + col] = s * e.x; o[(6 * b1 + 1) * w + col] = s * e.y; o[(6 * b1 + 2) * w + col] = s * e.z;
+                    o[(6 * b1 + 3) * w + col] = s * tq.x; o[(6 * b1 + 4) * w + col] = s * tq.y; o[(6 * b1 + 5) * w + col] = s * tq.z;
+                }
+                const ub::BodyP<double> Bd = ub::load_body<double>(bp + b2 * UB_BODY_PARAMS);
+                const ub::V3<double> tq = ub::cross(ub::ld3(P.cr2[c]) - Bd.com, e);
+                const double s = scale / Bd.m;
+                o[(6 * b2) * w + col] = s * e.x; o[(6 * b2 + 1) * w + col] = s * e.y; o[(6 * b2 + 2) * w + col] = s * e.z;
+                o[(6 * b2 + 3) * w + col] = s * tq.x; o[(6 * b2 + 4) * w + col] = s * tq.y; o[(6 * b2 + 5) * w + col] = s * tq.z;
+            }
     } else if (what == EV_OBJDYN) {
         const double scale = rsqrt(double(6 * P.nb));
         for (int b = 0; b < P.nb; ++b) {
@@ -1115,6 +1298,8 @@ extern "C" int ub_eval(ub_problem_t* p, const char* name, int32_t M, const doubl
         if (rows && !target) return fail(UB_E_INVALID, "end_effector_box_constraint needs the desired position (target)");
     }
     else if (n == "end_effector_position") { what = EV_EEPOS; rows = 3; }
+    else if (n == "end_effector_jacobian") { what = EV_EEJAC; rows = 3 * P.nq; }
+    else if (n == "object_dynamics_jacobian") { what = EV_OBJDYN_JAC; rows = P.neq * (P.nx + P.nu); }
     else if (n == "cost") { what = EV_COST; rows = 1; }
     else if (n == "inertial_alignment_cost") { what = EV_IACOST; rows = 1; }
     else if (n == "inertial_alignment_constraint") { what = EV_IACON; rows = P.iacon ? 5 : 0; }

@@ -64,6 +64,14 @@ struct DevProblem {
 // formed with exact operations, so this only perturbs the step at rounding level.
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
 __device__ __forceinline__ double fdiv(double a, double b) { return a / b; }
+// Reciprocal of a double in the product kernels' residual arithmetic: float seed + one Newton step (relative error
+// ~4e-15, six instructions instead of the ~thirty of an IEEE division); exact outside the float range.
+static __device__ __noinline__ double slow_rcp(double d) { return 1.0 / d; }   // out of line: keeps the hot loops small
+__device__ __forceinline__ double fast_rcp(double d) {
+    if (!(fabs(d) > 1e-30) || !(fabs(d) < 1e30)) return slow_rcp(d);
+    const double r = double(__frcp_rn(float(d)));
+    return r * (2.0 - d * r);
+}
 
 // ------------------------------------------------------------------ vectors
 template <typename T>
@@ -165,9 +173,15 @@ template <>
 __device__ __forceinline__ void sincos_t<double>(double a, double* s, double* c) { sincos(a, s, c); }
 
 template <typename T>
+__device__ __forceinline__ void axis_angle_sc(const V3<T>& u, T s, T c, T* R);
+template <typename T>
 __device__ __forceinline__ void axis_angle(const V3<T>& u, T th, T* R) {
     T s, c;
     sincos_t<T>(th, &s, &c);
+    axis_angle_sc(u, s, c, R);
+}
+template <typename T>
+__device__ __forceinline__ void axis_angle_sc(const V3<T>& u, T s, T c, T* R) {
     const T t = T(1) - c;
     R[0] = c + t * u.x * u.x;
     R[1] = t * u.x * u.y - s * u.z;
@@ -271,9 +285,10 @@ __device__ __forceinline__ void inertial_alignment_rows(const DevProblem<T>& P, 
 // If TANGENT, also propagates d/dx_dir (dir = this lane's direction; dir >= nx
 // propagates zeros).  Sphere centres (and tangents) are written to sph / dsph
 // (3 values per sphere, registers of this lane) when non-null.
+// `sc`: optional [sin q_i, cos q_i] pairs computed beforehand (the linearisation shares them across the lanes).
 template <typename T, bool TANGENT, typename XT = T>
 __device__ void forward_kinematics(const DevProblem<T>& P, const XT* __restrict__ x, int dir, Kin<T>& K, KinTan<T>& D,
-                                   T* sph, T* dsph) {
+                                   T* sph, T* dsph, const T* sc = nullptr) {
     const int nq = P.nq;
     M3<T> R;
 #pragma unroll
@@ -339,7 +354,8 @@ __device__ void forward_kinematics(const DevProblem<T>& P, const XT* __restrict_
             al = al + qdd * z + qd * wz;
             w = w + qd * z;
             T Rq[9];
-            axis_angle(ul, qi, Rq);
+            if (sc != nullptr) axis_angle_sc(ul, sc[2 * i], sc[2 * i + 1], Rq);
+            else axis_angle(ul, qi, Rq);
             R = matmul(R, Rq);
         } else {
             const V3<T> d = qi * z;

@@ -77,9 +77,18 @@ __global__ void rh_count_status_kernel(int B, const int32_t* __restrict__ status
     if (s >= 0 && s < 4) counts[4 * b + s] += 1;
 }
 
+// Simulated dynamic obstacle of the closed loop (upright_sim/src/upright_sim/simulation.py:300-435 as restated by
+// upright_b200/plant.py::BallisticObstacles): free flight under the current mode's acceleration, state reset to the
+// next mode's initial values once its time has come (checked on the time at the START of a simulation step).
+struct ObstacleMode {
+    double time, p[3], v[3], a[3];
+};
+
 template <typename T>
 struct RolloutArgs {
     int B, N, nq, nx, nu;
+    int nxt;              // columns of x / X: robot state + 9 per dynamic obstacle
+    int ndyn;             // dynamic obstacles
     double dt;            // knot spacing of the plan
     double t0;            // start time of the current plan
     double t_first;       // time of the first simulation step of this launch
@@ -89,24 +98,35 @@ struct RolloutArgs {
     int log_stride, n_log;
     int use_feedback, gain_stages;
     T kp, kv, ka;
-    const T* X;           // [B, N+1, nx] current plan
+    const T* X;           // [B, N+1, nxt] current plan
     const T* U;           // [B, N, nu]
     const T* K;           // [B, gain_stages, nu, nx] or null
-    T* x;                 // [B, nx] plant state (in/out)
-    T* xs;                // [B, n_log, nx] or null
+    T* x;                 // [B, nxt] plant state (in/out)
+    T* xs;                // [B, n_log, nxt] or null
     T* us;                // [B, n_log, nq] or null
+    // obstacle plant: modes [ndyn][max_modes], n_modes [ndyn], offsets [B, ndyn, 3] or null, current mode [B, ndyn]
+    const ObstacleMode* modes;
+    const int* n_modes;
+    int max_modes;
+    const T* offsets;
+    int* mode_idx;
 };
 
-// One warp per instance, lane r < nq owns joint r (q_r, v_r, a_r).  n_sub simulation steps per launch.
+// One warp per instance, lane r < nq owns joint r (q_r, v_r, a_r); lane nq + 3 j + c owns axis c of obstacle j.
+// n_sub simulation steps per launch.
 template <typename T>
 __global__ void rh_rollout_kernel(RolloutArgs<T> A) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
     if (warp >= A.B) return;
-    const int b = warp, nq = A.nq, nx = A.nx, nu = A.nu, N = A.N;
+    const int b = warp, nq = A.nq, nx = A.nx, nxt = A.nxt, nu = A.nu, N = A.N;
     const bool own = lane < nq;
-    T* xg = A.x + size_t(b) * nx;
+    const int ol = lane - nq, oj = ol / 3, oc = ol % 3;          // obstacle lane: obstacle oj, axis oc
+    const bool obs = ol >= 0 && oj < A.ndyn;
+    T* xg = A.x + size_t(b) * nxt;
     T q = own ? xg[lane] : T(0), v = own ? xg[nq + lane] : T(0), a = own ? xg[2 * nq + lane] : T(0);
-    const T* X = A.X + size_t(b) * (N + 1) * nx;
+    T orr = obs ? xg[nx + 9 * oj + oc] : T(0), ov = obs ? xg[nx + 9 * oj + 3 + oc] : T(0), oa = obs ? xg[nx + 9 * oj + 6 + oc] : T(0);
+    int midx = obs ? A.mode_idx[b * A.ndyn + oj] : 0;
+    const T* X = A.X + size_t(b) * (N + 1) * nxt;
     const T* U = A.U + size_t(b) * N * nu;
     const T* K = A.K ? A.K + size_t(b) * A.gain_stages * nu * nx : nullptr;
     const unsigned FULLM = 0xffffffffu;
@@ -121,8 +141,8 @@ __global__ void rh_rollout_kernel(RolloutArgs<T> A) {
         const int j = (i + 1 > N - 1) ? N - 1 : i + 1;
         T dq = 0, dv = 0, da = 0, u = 0;
         if (own) {
-            const T* Xi = X + i * nx;
-            const T* Xj = Xi + nx;
+            const T* Xi = X + i * nxt;
+            const T* Xj = Xi + nxt;
             dq = q - (w1 * Xi[lane] + w * Xj[lane]);
             dv = v - (w1 * Xi[nq + lane] + w * Xj[nq + lane]);
             da = a - (w1 * Xi[2 * nq + lane] + w * Xj[2 * nq + lane]);
@@ -146,14 +166,21 @@ __global__ void rh_rollout_kernel(RolloutArgs<T> A) {
         // u_cmd = Kx (xd - x) + u   (mpc_sim.py:148), xd = x_nom
         const T ucmd = u - (A.kp * dq + A.kv * dv + A.ka * da);
         const int step = A.step0 + sub;
-        if (own && A.xs != nullptr && step % A.log_stride == 0) {
+        if (A.xs != nullptr && step % A.log_stride == 0) {
             const int l = step / A.log_stride;
             if (l < A.n_log) {
-                T* xo = A.xs + (size_t(b) * A.n_log + l) * nx;
-                xo[lane] = q;
-                xo[nq + lane] = v;
-                xo[2 * nq + lane] = a;
-                A.us[(size_t(b) * A.n_log + l) * nq + lane] = ucmd;
+                T* xo = A.xs + (size_t(b) * A.n_log + l) * nxt;
+                if (own) {
+                    xo[lane] = q;
+                    xo[nq + lane] = v;
+                    xo[2 * nq + lane] = a;
+                    A.us[(size_t(b) * A.n_log + l) * nq + lane] = ucmd;
+                }
+                if (obs) {
+                    xo[nx + 9 * oj + oc] = orr;
+                    xo[nx + 9 * oj + 3 + oc] = ov;
+                    xo[nx + 9 * oj + 6 + oc] = oa;
+                }
             }
         }
         // exact triple-integrator step over sim_dt with constant jerk
@@ -162,11 +189,31 @@ __global__ void rh_rollout_kernel(RolloutArgs<T> A) {
         const T vn = v + h * a + T(0.5) * h * h * ucmd;
         const T an = a + h * ucmd;
         q = qn; v = vn; a = an;
+        if (obs) {
+            // mode schedule, then free flight over the step (plant.py::BallisticObstacles.step)
+            if (A.modes != nullptr) {
+                const ObstacleMode* M = A.modes + oj * A.max_modes;
+                if (midx < A.n_modes[oj] - 1 && t >= M[midx + 1].time) {
+                    ++midx;
+                    orr = T(M[midx].p[oc]) + (A.offsets ? A.offsets[(size_t(b) * A.ndyn + oj) * 3 + oc] : T(0));
+                    ov = T(M[midx].v[oc]);
+                }
+                oa = T(M[midx].a[oc]);
+            }
+            orr = orr + h * ov + T(0.5) * h * h * oa;
+            ov = ov + h * oa;
+        }
     }
     if (own) {
         xg[lane] = q;
         xg[nq + lane] = v;
         xg[2 * nq + lane] = a;
+    }
+    if (obs) {
+        xg[nx + 9 * oj + oc] = orr;
+        xg[nx + 9 * oj + 3 + oc] = ov;
+        xg[nx + 9 * oj + 6 + oc] = oa;
+        if (oc == 0) A.mode_idx[b * A.ndyn + oj] = midx;
     }
 }
 

@@ -39,11 +39,14 @@ namespace ub {
 // immediate of the load/store instruction.  Blocks marked (R) hold doubles: rw = sizeof(double) / sizeof(F)
 // units per element, 16-byte aligned like every block.
 struct Layout {
-    int Z, DZ, GAP, LG, LC, LR, LJP, LHO, LJO, DF, DFC, RHOE, YE, RHOT, YT, TL, DD, GP, VE, FAC, WF, FBD, FBL, GS, GL, QF;
+    int Z, DZ, GAP, LG, LC, LR, LJP, LHO, LJO, DF, RHOE, YE, RHOT, YT, TL, DD, GP, VE, FAC, WF, FBB;
     int XN, UN, XW, UW, TG, BD, LIA, LJA, XO, DXO;
     int total;
+    // force bundle of one stage (workspace FBB + k * bsize, and the same layout in shared memory at sFB):
+    // G = L^-1 C [neq][nx] | L^-1 per group (double) | D^-1 per contact (double) | g_lambda (double) | q (double)
+    int bG, bL, bD, bGl, bQ, bsize;
     // shared memory (units of F, per warp)
-    int sM, sP, sPv, sC, sS, sD, sFq, sFv, sFg, sFl, sVec, sDst, sDxn, sRv, sScr, sTL, sDD, sSmZ, sSmX, sSmU, sSmJ, sSmW;
+    int sM, sP, sPv, sFB, sGf, sFv, sFl, sVec, sDst, sDxn, sRv, sScr, sDFC, sUS, sCst, sTL, sDD, sSmZ, sSmX, sSmU, sSmJ, sSmW;
     int s_total;
     int rw;   // units per double
 };
@@ -76,7 +79,6 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.LHO = o;  o += ub_round4((N + 1) * d.nobs);
     L.LJO = o;  o += ub_round4((N + 1) * d.nobs * (d.obsw > 0 ? d.obsw : nq));
     L.DF = o;   o += ub_round4(d.neq * d.nfc);              // d g / d f dense [neq][nfc] (constant over the solve)
-    L.DFC = o;  o += ub_round4(d.nc * 2 * 6 * d.nf);        // the same per contact and side: [c][side][6][nf]
     L.RHOE = o; o += ub_round4(rw * N * d.neq);             // (R) weights of the equality rows
     L.YE = o;   o += ub_round4(rw * N * d.neq);             // (R) their multipliers (hard rows)
     L.RHOT = o; o += ub_round4(rw * d.nterm);
@@ -87,11 +89,16 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.VE = o;   o += ub_round4(rw * N * d.neq);             // (R) e + y / rho of the equality rows
     L.FAC = o;  o += ub_round4(N * fstride);                // Riccati factor blocks [L; Y], column-major, column length nr + 1
     L.WF = o;   o += ub_round4(N * nq);
-    L.FBD = o;  o += ub_round4(rw * N * fbd);               // (R) D^-1 per contact
-    L.FBL = o;  o += ub_round4(rw * N * fbl);               // (R) L^-1 of S per group
-    L.GS = o;   o += ub_round4(N * d.neq * nx);             // G = L^-1 C
-    L.GL = o;   o += ub_round4(rw * N * d.neq);             // (R) L^-1 (e + y / rho - Df D^-1 m_f)
-    L.QF = o;   o += ub_round4(rw * N * d.nfc);             // (R) D^-1 m_f
+    {   // force bundle: one contiguous block per stage, fetched by one copy in the forward / corrector passes
+        int b = 0;
+        L.bG = b;  b += ub_round4(d.neq * nx);              // G = L^-1 C
+        L.bL = b;  b += ub_round4(rw * fbl);                // (R) L^-1 of S per group
+        L.bD = b;  b += ub_round4(rw * fbd);                // (R) D^-1 per contact
+        L.bGl = b; b += ub_round4(rw * d.neq);              // (R) g_lambda = L^-1 (e + y / rho - Df D^-1 m_f)
+        L.bQ = b;  b += ub_round4(rw * d.nfc);              // (R) q = D^-1 m_f
+        L.bsize = b;
+    }
+    L.FBB = o;  o += N * L.bsize;
     L.XN = o;   o += ub_round4((N + 1) * nx);
     L.UN = o;   o += ub_round4(N * nu);
     // the iterate, the desired positions and the body parameters live in the instance workspace too, so that
@@ -106,22 +113,25 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.DXO = o;  o += ub_round4((N + 1) * d.nxo);
     L.total = o;
     int s = 0;
-    L.sM = s;   s += ub_round4(ub_max(nr * (nr | 1), 2 * fstride));
+    // (the stage-matrix buffer doubles as the scratch of the S build when bodies share contacts: D^-1 N' per contact
+    // and side, [c][side][6][nf] doubles — the force block is eliminated before the matrix is built)
+    const int us = (d.ngrp == 1 && d.nb > 1) ? rw * d.nc * 2 * 6 * d.nf : 0;
+    L.sM = s;   s += ub_round4(ub_max(ub_max(nr * (nr | 1), 2 * fstride), us));
     L.sP = s;   s += ub_round4(nx * nx);
     L.sPv = s;  s += ub_round4(nx);
-    L.sC = s;   s += ub_round4(d.neq * (nx + 1));           // C rows of the stage, then G in place; column nx = g_lambda
-    L.sS = s;   s += ub_round4(rw * fbl);                   // (R) S, then L^-1
-    L.sD = s;   s += ub_round4(rw * fbd);                   // (R) D^-1
-    L.sFq = s;  s += ub_round4(rw * d.nfc);                 // (R) q = D^-1 m_f
+    L.sFB = s;  s += L.bsize;                               // force bundle of the stage (C rows first, G in place)
+    L.sGf = s;  s += ub_round4(d.neq);                      // g_lambda in F for the Schur update
     L.sFv = s;  s += ub_round4(rw * d.neq);                 // (R) v = e + y / rho, then rhs
-    L.sFg = s;  s += ub_round4(rw * d.neq);                 // (R) g_lambda
     L.sFl = s;  s += ub_round4(rw * d.neq);                 // (R) lambda / scratch
     L.sVec = s; s += ub_round4(rw * nz);                    // (R) stage gradient [j; f; x]
     L.sDst = s; s += ub_round4(nz);                         // stage direction [dj; df; dx]
     L.sDxn = s; s += ub_round4(nx);
     L.sRv = s;  s += ub_round4(nr + 1);                     // Riccati right-hand side [m_j; m_x]
     L.sScr = s; s += ub_round4(rw * ub_max(ub_max(d.neq, d.nobs), ub_max(d.nterm, 16)));   // (R) per-row scratch
+    L.sDFC = s; s += ub_round4(d.nc * 2 * 6 * d.nf);        // d g / d f per contact and side: [c][side][6][nf] (constant over the solve)
+    L.sUS = L.sM;
     const bool staged = d.nrow <= UB_STAGE_ROWS_MAX;
+    L.sCst = s; s += staged ? ub_round4(d.neq * nx) : 0;    // C rows of the stage a factor pass visits next
     L.sTL = s;  s += staged ? ub_round4(rw * d.nrow * 4) : 0;
     L.sDD = s;  s += staged ? ub_round4(d.nrow * 4) : 0;
     L.sSmZ = s; s += staged ? ub_round4(rw * nz) : 0;       // (R) staged z_k (or predictor gradient)
@@ -157,6 +167,14 @@ struct BatchArgs {
     int* queue;
     int n_slots;      // workspace slots (= warps that may work); B in the static mode
     int nxt;          // columns of x0 / X / Xin: robot state + dynamic-obstacle states
+    // Multi-GPU gather fused into the solve: besides X / U of this rank, every solved instance is
+    // stored straight into the gathered buffers of the peer GPUs (peer-mapped pointers, NVLink P2P stores from the
+    // epilogue) at row gather_row + b — the all-gather happens instance by instance while the rest of the batch is
+    // still being solved, with no collective kernel and no copy afterwards.
+    F* Xg[UB_MAX_GATHER];
+    F* Ug[UB_MAX_GATHER];
+    int ngather;
+    long long gather_row;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -247,9 +265,9 @@ struct Solver {
     // workspace / shared-memory offsets: immediates for the specialised kernels
 #define UB_OFF(name) \
     __device__ __forceinline__ int o##name() const { if constexpr (D::kStatic) { constexpr Layout l = D::template layout<F>(); return l.name; } else return L.name; }
-    UB_OFF(Z) UB_OFF(DZ) UB_OFF(GAP) UB_OFF(LG) UB_OFF(LC) UB_OFF(LR) UB_OFF(LJP) UB_OFF(LHO) UB_OFF(LJO) UB_OFF(DF) UB_OFF(DFC)
+    UB_OFF(Z) UB_OFF(DZ) UB_OFF(GAP) UB_OFF(LG) UB_OFF(LC) UB_OFF(LR) UB_OFF(LJP) UB_OFF(LHO) UB_OFF(LJO) UB_OFF(DF)
     UB_OFF(RHOE) UB_OFF(YE) UB_OFF(RHOT) UB_OFF(YT) UB_OFF(TL) UB_OFF(DD) UB_OFF(GP) UB_OFF(VE) UB_OFF(FAC) UB_OFF(WF)
-    UB_OFF(FBD) UB_OFF(FBL) UB_OFF(GS) UB_OFF(GL) UB_OFF(QF) UB_OFF(XN) UB_OFF(UN)
+    UB_OFF(FBB) UB_OFF(bG) UB_OFF(bL) UB_OFF(bD) UB_OFF(bGl) UB_OFF(bQ) UB_OFF(bsize) UB_OFF(XN) UB_OFF(UN)
     UB_OFF(XW) UB_OFF(UW) UB_OFF(TG) UB_OFF(BD) UB_OFF(LIA) UB_OFF(LJA) UB_OFF(XO) UB_OFF(DXO)
 #undef UB_OFF
     __device__ __forceinline__ static constexpr int LDM() { return D::nr | 1; }
@@ -271,13 +289,19 @@ struct Solver {
     F* sM;
     F* sP;
     F* sPv;
-    F* sC;
-    R* sS;
-    R* sD;
-    R* sFq;
+    F* sFB;   // force bundle of the current stage
+    F* sC;    //   G (C rows on entry of the factor pass), dense [neq][nx]
+    R* sS;    //   L^-1 per group
+    R* sD;    //   D^-1 per contact
+    R* sFg;   //   g_lambda
+    R* sFq;   //   q
+    F* sGf;
     R* sFv;
-    R* sFg;
     R* sFl;
+    F* sDFC;  // d g / d f per contact and side (constant over the solve)
+    R* sUS;   // scratch of the S build when bodies share contacts
+    F* sCst;  // C rows of the current stage in the factor pass of the staged kernels (cC points here or at sC)
+    F* cC;
     R* sVec;
     F* sDst;
     F* sDxn;
@@ -292,6 +316,12 @@ struct Solver {
     F* sSmW;
     template <typename T>
     __device__ __forceinline__ T* wsr(int off) const { return reinterpret_cast<T*>(ws + off); }
+    __device__ __forceinline__ F* bundle(int k) const { return ws + oFBB() + k * obsize(); }
+    // reciprocal in the residual arithmetic: exact in the fp64 validation kernels
+    __device__ __forceinline__ static R rinv(R d) {
+        if constexpr (std::is_same<F, R>::value) return R(1) / d;
+        else return fast_rcp(d);
+    }
 
     __device__ __forceinline__ void tsync() const { __syncwarp(); }
     template <typename T>
@@ -373,22 +403,22 @@ struct Solver {
         for (int j = 0; j < ow; ++j) v += R(J[j]) * zk[nu + j];
         return v;
     }
-    // a_r . d  for a stage direction d = [du; dx]
-    __device__ R row_dot(int k, int r, int fam, const F* d) const {
+    // a_r . d  for a stage direction d = [du; dx] (a direction: F arithmetic)
+    __device__ F row_dot(int k, int r, int fam, const F* d) const {
         const int nq = NQ(), nu = NU();
-        if (fam == 0) return R(d[r]);
-        if (fam == 1) return R(d[nu + r - NBOXU()]);
+        if (fam == 0) return d[r];
+        if (fam == 1) return d[nu + r - NBOXU()];
         if (fam == 2) {
             const int i = r - NBOXU() - NX(), c = i / 5;
             const V3<R> a = fric_coeff(c, i % 5);
             const F* df = d + nq + 3 * c;
-            return a.x * R(df[0]) + a.y * R(df[1]) + a.z * R(df[2]);
+            return F(a.x) * df[0] + F(a.y) * df[1] + F(a.z) * df[2];
         }
         const int i = r - NBOXU() - NX() - NFRIC();
         const int ow = OBSW();
         const F* J = ws + oLJO() + (k * NOBS() + i) * ow;
-        R v = 0;
-        for (int j = 0; j < ow; ++j) v += R(J[j]) * R(d[nu + j]);
+        F v = 0;
+        for (int j = 0; j < ow; ++j) v += J[j] * d[nu + j];
         return v;
     }
     // Slack/multiplier record of one inequality row: {t_lo, t_hi, lam_lo, lam_hi} (double) and the step
@@ -475,10 +505,13 @@ struct Solver {
     }
     // Newton data of one side: the coefficient that multiplies sgn*a in the stage gradient;
     // d = signed distance to the bound at the current iterate
-    __device__ __forceinline__ R side_coef(R t, R lam, R d, R eps, R target, R corr) const {
+    // Only the slack residual rd (operands O(1), result -> 0) and the accumulation of -lam need double: the
+    // remaining term is small near the solution and is formed in F.
+    __device__ __forceinline__ R side_coef(R t, R lam, R d, R eps, F target, F corr) const {
         const R rd = d + eps * lam - t;
-        const R rc = t * lam - target + corr;
-        return -lam + (rc + lam * rd) / (t + eps * lam);
+        const F tf = F(t), lf = F(lam);
+        const F rc = tf * lf - target + corr;
+        return -lam + R(fdiv(rc + lf * F(rd), tf + F(eps) * lf));
     }
     __device__ __forceinline__ int neq_of(int k) const { return k < NN() ? NEQ() : NTERM(); }
 
@@ -488,7 +521,7 @@ struct Solver {
     __device__ void build_Df() {
         const R scale = rsqrt(R(6 * NB()));
         F* Df = ws + oDF();
-        F* Dc = ws + oDFC();
+        F* Dc = sDFC;
         const int nf = NF(), nfc = NFC();
         for (int idx = lane; idx < NEQ() * nfc; idx += kTS) Df[idx] = F(0);
         for (int idx = lane; idx < NC() * 12 * nf; idx += kTS) Dc[idx] = F(0);
@@ -528,11 +561,13 @@ struct Solver {
     template <typename T>
     __device__ __forceinline__ R eq_force_dot(int row, const T* v) const {
         const int b = row / 6, rr = row - 6 * b, nf = NF();
-        const F* Dc = ws + oDFC();
+        const F* Dc = sDFC;
         R acc = 0;
+#pragma unroll 1
         for (int e = P.bc_start[b]; e < P.bc_start[b + 1]; ++e) {
             const int cs = P.bc_list[e], c = cs >> 1;
             const F* d = Dc + (cs * 6 + rr) * nf;
+#pragma unroll 1
             for (int i = 0; i < nf; ++i) acc += R(d[i]) * R(v[c * nf + i]);
         }
         return acc;
@@ -551,7 +586,16 @@ struct Solver {
             const F* x = X + k * nx;
             Kin<R> Kn;
             KinTan<R> Dt;
-            forward_kinematics<R, true, F>(PR, x, lane, Kn, Dt, SPHERES() ? sph : nullptr, dsph);
+            // sin / cos of the joint angles once per knot (lane i: joint i), shared through the scratch
+            tsync();
+            if (lane < nq) {
+                R sn, cs;
+                sincos(R(x[lane]), &sn, &cs);
+                sScr[2 * lane] = sn;
+                sScr[2 * lane + 1] = cs;
+            }
+            tsync();
+            forward_kinematics<R, true, F>(PR, x, lane, Kn, Dt, SPHERES() ? sph : nullptr, dsph, sScr);
             if (NXO() > 0) place_dynamic_spheres<R>(k, R(0), sph);
             if (lane == 0) {
                 R* lr = wsr<R>(oLR()) + 3 * k;
@@ -847,20 +891,51 @@ struct Solver {
     // over q (-Jp) and unit rows, kept as weighted terms of the state block.
     __device__ __forceinline__ R* rho_eq(int k) const { return k < NN() ? wsr<R>(oRHOE()) + k * NEQ() : wsr<R>(oRHOT()); }
     __device__ __forceinline__ R* y_eq(int k) const { return k < NN() ? wsr<R>(oYE()) + k * NEQ() : wsr<R>(oYT()); }
-    // the C rows of stage k into sC (row stride nx + 1)
+    // the C rows of stage k into shared memory (dense [neq][nx]): synchronously, or issued as cp.async (no commit)
     __device__ __forceinline__ void load_C(int k) {
         const int nx = NX(), ne = NEQ();
         const F* __restrict__ src = ws + oLC() + k * ne * nx;
-        for (int idx = lane; idx < ne * nx; idx += kTS) sC[(idx / nx) * (nx + 1) + idx % nx] = src[idx];
+        for (int idx = lane; idx < ne * nx; idx += kTS) cC[idx] = src[idx];
         tsync();
+    }
+    __device__ __forceinline__ void c_issue(int k) const {
+        if constexpr (kStageTT) {
+            if (NEQ() == 0 || k < 0 || k >= NN()) return;
+            cp_async_elems(sCst, ws + oLC() + k * D::neq * D::nx, D::neq * D::nx);   // stage blocks are only 4-byte aligned
+        }
+    }
+    // 1 / rho of equality row i of stage k < N (soft rows: the slack weight, no load)
+    __device__ __forceinline__ R rho_inv_stage(int k, int i) const {
+        if (C.soft_poly) return PR.invZ;
+        const R rho = rho_eq(k)[i];
+        return rho > R(0) ? rinv(rho) : R(1e30);
     }
     // value of equality row i of stage k < N at the QP iterate zk (C row from shared memory)
     __device__ __forceinline__ R eq_value_stage(int k, int i, const R* zk) const {
         const int nx = NX(), nu = NU(), nq = NQ();
         R v = wsr<R>(oLG())[k * NEQ() + i];
-        const F* c = sC + i * (nx + 1);
+        const F* c = cC + i * nx;
         for (int j = 0; j < nx; ++j) v += R(c[j]) * zk[nu + j];
         return v + eq_force_dot(i, zk + nq);
+    }
+    // values of all equality rows of stage k < N at zk -> out (shared memory).  Few rows (one body): four lanes share
+    // a row's 3 nq-long dot product, which cuts the dependent chain to a quarter.
+    __device__ __forceinline__ void eq_values_stage(int k, const R* zk, R* out) const {
+        const int nx = NX(), nu = NU(), nq = NQ(), ne = NEQ();
+        if (ne <= 8) {
+            const int i = lane >> 2, part = lane & 3;
+            R v = R(0);
+            if (i < ne) {
+                const F* c = cC + i * nx;
+                for (int j = part; j < nx; j += 4) v += R(c[j]) * zk[nu + j];
+                if (part == 0) v += wsr<R>(oLG())[k * ne + i] + eq_force_dot(i, zk + nq);
+            }
+            v += __shfl_xor_sync(FULL, v, 1);
+            v += __shfl_xor_sync(FULL, v, 2);
+            if (i < ne && part == 0) out[i] = v;
+        } else {
+            for (int i = lane; i < ne; i += kTS) out[i] = eq_value_stage(k, i, zk);
+        }
     }
     // value of terminal row i at the QP iterate zk
     __device__ __forceinline__ R eq_value_term(int i, const R* zk) const {
@@ -961,10 +1036,19 @@ struct Solver {
     }
 
     // barrier weight lam / (t + eps lam) of both sides of a box row / the one side of a polytopic row
-    __device__ __forceinline__ R box_weight(const QuadR& q, R eps) const {
-        return q.v[2] / (q.v[0] + eps * q.v[2]) + q.v[3] / (q.v[1] + eps * q.v[3]);
+    // (matrix entries: F arithmetic; the force block wants them in double: *_r)
+    __device__ __forceinline__ F box_weight(const QuadR& q, R eps) const {
+        const F e = F(eps), l0 = F(q.v[2]), l1 = F(q.v[3]);
+        return fdiv(l0, F(q.v[0]) + e * l0) + fdiv(l1, F(q.v[1]) + e * l1);
     }
-    __device__ __forceinline__ R one_weight(const QuadR& q, R eps) const { return q.v[2] / (q.v[0] + eps * q.v[2]); }
+    __device__ __forceinline__ F one_weight(const QuadR& q, R eps) const {
+        const F l0 = F(q.v[2]);
+        return fdiv(l0, F(q.v[0]) + F(eps) * l0);
+    }
+    __device__ __forceinline__ R box_weight_r(const QuadR& q, R eps) const {
+        return q.v[2] * rinv(q.v[0] + eps * q.v[2]) + q.v[3] * rinv(q.v[1] + eps * q.v[3]);
+    }
+    __device__ __forceinline__ R one_weight_r(const QuadR& q, R eps) const { return q.v[2] * rinv(q.v[0] + eps * q.v[2]); }
 
     // Build the REDUCED Newton matrix of stage k in sM (lower triangle, [j; x]): cost Hessian + barrier terms of the
     // jerk / state / obstacle rows (+ the weighted terminal rows at k = N).  The force block and the object-dynamics
@@ -983,7 +1067,7 @@ struct Solver {
             if (k < NN()) d = i < nq ? dt * P.Rd[i] + C.reg_input : dt * P.Qd[i - nq];
             const int r = i < nq ? i : nbu + (i - nq);          // the box row of this variable
             const int fam = i < nq ? 0 : 1;
-            if (row_valid(k, fam)) d += F(box_weight(recs_tl(k)[r], row_eps(fam)));
+            if (row_valid(k, fam)) d += box_weight(recs_tl(k)[r], row_eps(fam));
             sM[i * ld + i] += d;
         }
         tsync();
@@ -1030,7 +1114,7 @@ struct Solver {
             const R eps = row_eps(3);
             const int nbx = nbu + nx;
             F* wrow = reinterpret_cast<F*>(sScr);  // barrier weights of the obstacle rows
-            for (int i = lane; i < NOBS(); i += kTS) wrow[i] = F(one_weight(recs_tl(k)[nbx + NFRIC() + i], eps));
+            for (int i = lane; i < NOBS(); i += kTS) wrow[i] = one_weight(recs_tl(k)[nbx + NFRIC() + i], eps);
             tsync();
             const int ow = OBSW();
             for (int idx = lane; idx < ow * ow; idx += kTS) {
@@ -1055,16 +1139,16 @@ struct Solver {
         const R base = PR.dt * PR.fw + PR.reg_input;
         if (nf == 1) {
             const R eps = row_eps(0);
-            for (int c = lane; c < NC(); c += kTS) sD[c] = R(1) / (base + box_weight(recs_tl(k)[nq + c], eps));
+            for (int c = lane; c < NC(); c += kTS) sD[c] = rinv(base + box_weight_r(recs_tl(k)[nq + c], eps));
         } else {
             const R eps0 = row_eps(0), eps2 = row_eps(2);
             const int nbx = NBOXU() + NX();
             for (int c = lane; c < NC(); c += kTS) {
                 // symmetric 3 x 3: m00 m10 m11 m20 m21 m22
-                R m00 = base + box_weight(recs_tl(k)[nq + 3 * c], eps0), m11 = base + box_weight(recs_tl(k)[nq + 3 * c + 1], eps0),
-                  m22 = base + box_weight(recs_tl(k)[nq + 3 * c + 2], eps0), m10 = 0, m20 = 0, m21 = 0;
+                R m00 = base + box_weight_r(recs_tl(k)[nq + 3 * c], eps0), m11 = base + box_weight_r(recs_tl(k)[nq + 3 * c + 1], eps0),
+                  m22 = base + box_weight_r(recs_tl(k)[nq + 3 * c + 2], eps0), m10 = 0, m20 = 0, m21 = 0;
                 for (int which = 0; which < 5; ++which) {
-                    const R w = one_weight(recs_tl(k)[nbx + 5 * c + which], eps2);
+                    const R w = one_weight_r(recs_tl(k)[nbx + 5 * c + which], eps2);
                     const V3<R> a = fric_coeff(c, which);
                     m00 += w * a.x * a.x;
                     m10 += w * a.y * a.x;
@@ -1076,7 +1160,7 @@ struct Solver {
                 // inverse by cofactors (SPD)
                 const R c00 = m11 * m22 - m21 * m21, c10 = m20 * m21 - m10 * m22, c20 = m10 * m21 - m20 * m11;
                 const R det = m00 * c00 + m10 * c10 + m20 * c20;
-                const R id = R(1) / det;
+                const R id = rinv(det);
                 R* o = sD + 9 * c;
                 o[0] = c00 * id;
                 o[1] = o[3] = c10 * id;
@@ -1105,10 +1189,113 @@ struct Solver {
     }
     // S = R^-1 + Df D^-1 Df' per group -> sS (lower triangles, dense ng x ng per group), then its Cholesky factor
     // and the inverse of that factor (lower) in place.  Returns false on a non-positive / non-finite pivot.
+    // Groups of one body (ng = 6: every BASELINE configuration but the stacked one): lane g builds, factors and
+    // inverts the 6 x 6 block of body g entirely in registers (fully unrolled, no barriers).
+    __device__ bool force_block_S6(int k) {
+        const int ngrp = NGRP(), nf = NF();
+        const F* Dc = sDFC;
+        bool ok = true;
+        for (int g = lane; g < ngrp; g += kTS) {
+            R s[21];   // lower triangle, row-major: (a, b) at a (a + 1) / 2 + b
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = 0; b <= a; ++b) s[a * (a + 1) / 2 + b] = R(0);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) s[a * (a + 1) / 2 + a] = rho_inv_stage(k, 6 * g + a);
+            for (int l = P.bc_start[g]; l < P.bc_start[g + 1]; ++l) {
+                const int cs = P.bc_list[l], c = cs >> 1;
+                const F* n = Dc + cs * 6 * nf;
+                if (nf == 1) {
+                    const R d = sD[c];
+                    R na[6];
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) na[a] = R(n[a]);
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        const R da = d * na[a];
+#pragma unroll
+                        for (int b = 0; b <= a; ++b) s[a * (a + 1) / 2 + b] += da * na[b];
+                    }
+                } else {
+                    const R* o = sD + 9 * c;
+                    R na[6][3], ua[6][3];
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) na[a][i] = R(n[a * 3 + i]);
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) ua[a][i] = o[3 * i] * na[a][0] + o[3 * i + 1] * na[a][1] + o[3 * i + 2] * na[a][2];
+                    }
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+#pragma unroll
+                        for (int b = 0; b <= a; ++b)
+                            s[a * (a + 1) / 2 + b] += ua[a][0] * na[b][0] + ua[a][1] * na[b][1] + ua[a][2] * na[b][2];
+                }
+            }
+            // Cholesky; id[j] = 1 / L_jj
+            R id[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const R d = s[j * (j + 1) / 2 + j];
+                if (!(d > R(0)) || !(d < R(1e300))) ok = false;
+                id[j] = rsqrt(d);
+#pragma unroll
+                for (int i = j + 1; i < 6; ++i) s[i * (i + 1) / 2 + j] *= id[j];
+#pragma unroll
+                for (int i = j + 1; i < 6; ++i)
+#pragma unroll
+                    for (int l = j + 1; l <= i; ++l) s[i * (i + 1) / 2 + l] -= s[i * (i + 1) / 2 + j] * s[l * (l + 1) / 2 + j];
+            }
+            // inverse of the factor in place, column by column (column c of L^-1 needs the original columns > c only)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                s[c * (c + 1) / 2 + c] = id[c];
+#pragma unroll
+                for (int i = c + 1; i < 6; ++i) {
+                    R acc = s[i * (i + 1) / 2 + c] * id[c];
+#pragma unroll
+                    for (int l = c + 1; l < i; ++l) acc += s[i * (i + 1) / 2 + l] * s[l * (l + 1) / 2 + c];
+                    s[i * (i + 1) / 2 + c] = -acc * id[i];
+                }
+            }
+            R* Sg = sS + g * 36;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = 0; b < 6; ++b) Sg[a * 6 + b] = b <= a ? s[a * (a + 1) / 2 + b] : R(0);
+        }
+        tsync();
+        return __all_sync(FULL, ok);
+    }
+    // Bodies that share contacts, compile-time size (cfg3: 18 rows): Cholesky with lane = row, the row in registers
+    // and the pivot column travelling by warp shuffle (no barriers, no index arithmetic).  sS then holds L itself
+    // (lower, diagonal INVERTED), not its inverse: the products with L^-1 / L^-T become substitutions.
+    static constexpr bool kPanelS = D::kStatic && D::ng > 6 && D::ng <= 32;
     __device__ bool force_block_S(int k) {
         const int ng = NG(), ngrp = NGRP(), nf = NF();
-        const R* rho = rho_eq(k);
-        const F* Dc = ws + oDFC();
+        if (ng == 6) return force_block_S6(k);
+        const F* Dc = sDFC;
+        // U = D^-1 N' per contact and side (scratch): S_ab = sum_c N[a] . U[b] then costs nf multiply-adds per contact
+        for (int e = lane; e < NC() * 2; e += kTS) {
+            const int c = e >> 1;
+            if (((e & 1) == 0 ? P.cb2[c] : P.cb1[c]) < 0) continue;
+            const F* n = Dc + (e * 6) * nf;
+            R* u = sUS + (e * 6) * nf;
+            if (nf == 1) {
+                for (int rr = 0; rr < 6; ++rr) u[rr] = sD[c] * R(n[rr]);
+            } else {
+                const R* o = sD + 9 * c;
+                for (int rr = 0; rr < 6; ++rr) {
+                    const R n0 = R(n[3 * rr]), n1 = R(n[3 * rr + 1]), n2 = R(n[3 * rr + 2]);
+                    u[3 * rr] = o[0] * n0 + o[1] * n1 + o[2] * n2;
+                    u[3 * rr + 1] = o[3] * n0 + o[4] * n1 + o[5] * n2;
+                    u[3 * rr + 2] = o[6] * n0 + o[7] * n1 + o[8] * n2;
+                }
+            }
+        }
+        tsync();
         const int tri = ng * (ng + 1) / 2;
         for (int e = lane; e < ngrp * tri; e += kTS) {
             const int g = e / tri, t = e - g * tri;
@@ -1120,7 +1307,8 @@ struct Solver {
             const int ra = g * ng + a, rb = g * ng + b;
             const int ba = ra / 6, bb = rb / 6, ia = ra - 6 * ba, ib = rb - 6 * bb;
             R acc = R(0);
-            if (a == b) acc = rho[ra] > R(0) ? R(1) / rho[ra] : R(1e30);
+            if (a == b) acc = rho_inv_stage(k, ra);
+#pragma unroll 1
             for (int l = P.bc_start[ba]; l < P.bc_start[ba + 1]; ++l) {
                 const int cs = P.bc_list[l], c = cs >> 1;
                 // the side of contact c that touches body bb (if any)
@@ -1130,21 +1318,44 @@ struct Solver {
                 else if (P.cb1[c] == bb) cs_b = 2 * c + 1;
                 if (cs_b < 0) continue;
                 const F* na = Dc + (cs * 6 + ia) * nf;
-                const F* nb = Dc + (cs_b * 6 + ib) * nf;
-                if (nf == 1) acc += R(na[0]) * sD[c] * R(nb[0]);
-                else {
-                    const R* o = sD + 9 * c;
-                    const R b0 = R(nb[0]), b1 = R(nb[1]), b2 = R(nb[2]);
-                    acc += R(na[0]) * (o[0] * b0 + o[1] * b1 + o[2] * b2) + R(na[1]) * (o[3] * b0 + o[4] * b1 + o[5] * b2) +
-                           R(na[2]) * (o[6] * b0 + o[7] * b1 + o[8] * b2);
-                }
+                const R* ub = sUS + (cs_b * 6 + ib) * nf;
+                if (nf == 1) acc += R(na[0]) * ub[0];
+                else acc += R(na[0]) * ub[0] + R(na[1]) * ub[1] + R(na[2]) * ub[2];
             }
             sS[g * ng * ng + a * ng + b] = acc;
+            if constexpr (kPanelS) sS[g * ng * ng + b * ng + a] = acc;   // the panel reads whole rows
         }
         tsync();
         bool ok = true;
-        // Cholesky, all groups at once: lanes over (group, row) pairs for the column scaling and over
-        // (group, i, l) for the trailing update
+        if constexpr (kPanelS) {
+            constexpr int NG_ = D::ng;
+            R row[NG_];
+            const int a = lane < NG_ ? lane : NG_ - 1;    // lanes beyond the last row shadow it (their results are dropped)
+#pragma unroll
+            for (int b = 0; b < NG_; ++b) row[b] = sS[a * NG_ + b];
+#pragma unroll
+            for (int j = 0; j < NG_; ++j) {
+                const R d = __shfl_sync(FULL, row[j], j);
+                if (!(d > R(0)) || !(d < R(1e300))) ok = false;
+                const R inv = rsqrt(d);
+                const R lij = (lane > j) ? row[j] * inv : R(0);
+#pragma unroll
+                for (int c = j + 1; c < NG_; ++c) {
+                    const R lcj = __shfl_sync(FULL, lij, c);
+                    row[c] -= lij * lcj;
+                }
+                row[j] = (lane > j) ? lij : (lane == j ? inv : R(0));
+            }
+            tsync();
+            if (lane < NG_) {
+#pragma unroll
+                for (int b = 0; b < NG_; ++b) sS[lane * NG_ + b] = row[b];
+            }
+            tsync();
+            return __all_sync(FULL, ok);
+        } else {
+        // run-time size: Cholesky in shared memory, all groups at once: lanes over (group, row) pairs for the column
+        // scaling and over (group, i, l) for the trailing update
         for (int j = 0; j < ng; ++j) {
             const int nrow_j = ng - 1 - j;
             // pivots: every lane reads the pivot of the group it works on
@@ -1176,13 +1387,12 @@ struct Solver {
             }
             tsync();
         }
-        // inverse of the factor: lane (g, c) computes column c of L^-1 by forward substitution into its registers'
-        // worth of the UPPER triangle of the same block (row c, columns c..ng-1 hold column c of L^-1), then the
-        // block is rewritten as the lower-triangular L^-1
+        // inverse of the factor: lane (g, c) computes column c of L^-1 by forward substitution into the UPPER
+        // triangle of the same block (row c, columns c..ng-1 hold column c of L^-1), then the block is rewritten as
+        // the lower-triangular L^-1
         for (int e = lane; e < ngrp * ng; e += kTS) {
             const int g = e / ng, c = e - g * ng;
             R* Sg = sS + g * ng * ng;
-            // x_c = 1 / L_cc; x_i = -(sum_{l=c}^{i-1} L_il x_l) / L_ii
             Sg[c * ng + c] = R(1) / Sg[c * ng + c];   // the diagonal now holds 1 / L_cc = (L^-1)_cc
         }
         tsync();
@@ -1203,9 +1413,23 @@ struct Solver {
         }
         tsync();
         return __all_sync(FULL, ok);
+        }
     }
     // y = L^-1 x per group (rows over lanes); Lm = L^-1 blocks (lower), shared or global
     __device__ __forceinline__ void force_Linv_mul(const R* Lm, const R* x, R* y) const {
+        if constexpr (kPanelS) {   // Lm = L (diagonal inverted): forward substitution, lane = row, x_j broadcast by shuffle
+            constexpr int NG_ = D::ng;
+            R v = lane < NG_ ? x[lane] : R(0);
+            const R* row = Lm + (lane < NG_ ? lane : 0) * NG_;
+#pragma unroll
+            for (int j = 0; j < NG_; ++j) {
+                const R xj = __shfl_sync(FULL, v, j) * Lm[j * NG_ + j];
+                if (lane == j) v = xj;
+                else if (lane > j && lane < NG_) v -= row[j] * xj;
+            }
+            if (lane < NG_) y[lane] = v;
+            return;
+        }
         const int ng = NG();
         for (int r = lane; r < NEQ(); r += kTS) {
             const int g = r / ng, a = r - g * ng;
@@ -1217,6 +1441,18 @@ struct Solver {
     }
     // y = L^-T x per group
     __device__ __forceinline__ void force_LinvT_mul(const R* Lm, const R* x, R* y) const {
+        if constexpr (kPanelS) {   // back substitution with L' (row a of L read by the lanes below a)
+            constexpr int NG_ = D::ng;
+            R v = lane < NG_ ? x[lane] : R(0);
+#pragma unroll
+            for (int a = NG_ - 1; a >= 0; --a) {
+                const R ya = __shfl_sync(FULL, v, a) * Lm[a * NG_ + a];
+                if (lane == a) v = ya;
+                else if (lane < a) v -= Lm[a * NG_ + lane] * ya;
+            }
+            if (lane < NG_) y[lane] = v;
+            return;
+        }
         const int ng = NG();
         for (int r = lane; r < NEQ(); r += kTS) {
             const int g = r / ng, a = r - g * ng;
@@ -1227,8 +1463,8 @@ struct Solver {
         }
     }
     // Force block of stage k < N in the factor pass.  On entry: sC = C rows, sVec = stage gradient [j; f; x] (double),
-    // sFv = v = e + y / rho, records of the stage staged.  On exit: sD = D^-1, sS = L^-1, sFq = q, sFg = g_lambda,
-    // sC = [G | g_lambda] and all of them stored for the later passes.
+    // sFv = v = e + y / rho, sD = D^-1.  On exit the shared-memory bundle holds G (in place of C), L^-1, D^-1,
+    // g_lambda and q, sGf = g_lambda in F, and the bundle is stored for the later passes.
     __device__ bool force_block_factor(int k) {
         const int nq = NQ(), nx = NX(), ne = NEQ(), ng = NG();
         force_q(sD, sVec + nq, sFq);
@@ -1238,52 +1474,76 @@ struct Solver {
         for (int r = lane; r < ne; r += kTS) sFv[r] -= eq_force_dot(r, sFq);
         tsync();
         force_Linv_mul(sS, sFv, sFg);
-        // G = L^-1 C in place, bottom row first (row a needs the original rows <= a only); lanes over columns
+        if constexpr (kPanelS) {
+            // G = L^-1 C by forward substitution, lanes over columns, the column in registers
+            constexpr int NG_ = D::ng;
+            if (lane < nx) {
+                R gcol[NG_];
+#pragma unroll
+                for (int a = 0; a < NG_; ++a) {
+                    R sacc = R(cC[a * nx + lane]);
+#pragma unroll
+                    for (int l = 0; l < a; ++l) sacc -= sS[a * NG_ + l] * gcol[l];
+                    gcol[a] = sacc * sS[a * NG_ + a];
+                }
+#pragma unroll
+                for (int a = 0; a < NG_; ++a) sC[a * nx + lane] = F(gcol[a]);
+            }
+        } else
+        // G = L^-1 C, bottom row first (in place when the C rows sit in sC: row a needs the original rows <= a only);
+        // lanes over columns
         for (int j = lane; j < nx; j += kTS) {
             for (int g = 0; g < NGRP(); ++g) {
                 const R* blk = sS + g * ng * ng;
-                F* col = sC + (g * ng) * (nx + 1) + j;
+                const F* src = cC + (g * ng) * nx + j;
+                F* col = sC + (g * ng) * nx + j;
                 for (int a = ng - 1; a >= 0; --a) {
                     R s = 0;
-                    for (int l = 0; l <= a; ++l) s += blk[a * ng + l] * R(col[l * (nx + 1)]);
-                    col[a * (nx + 1)] = F(s);
+                    for (int l = 0; l <= a; ++l) s += blk[a * ng + l] * R(src[l * nx]);
+                    col[a * nx] = F(s);
                 }
             }
         }
         tsync();
-        for (int r = lane; r < ne; r += kTS) sC[r * (nx + 1) + nx] = F(sFg[r]);
-        // keep for the corrector / forward passes
-        R* Dg = wsr<R>(oFBD()) + k * FBDN();
-        for (int i = lane; i < FBDN(); i += kTS) Dg[i] = sD[i];
-        R* Lg = wsr<R>(oFBL()) + k * FBLN();
-        for (int i = lane; i < FBLN(); i += kTS) Lg[i] = sS[i];
-        F* Gg = ws + oGS() + k * ne * nx;
-        for (int idx = lane; idx < ne * nx; idx += kTS) Gg[idx] = sC[(idx / nx) * (nx + 1) + idx % nx];
-        R* gl = wsr<R>(oGL()) + k * ne;
-        for (int r = lane; r < ne; r += kTS) gl[r] = sFg[r];
-        R* qf = wsr<R>(oQF()) + k * NFC();
-        for (int i = lane; i < NFC(); i += kTS) qf[i] = sFq[i];
+        for (int r = lane; r < ne; r += kTS) sGf[r] = F(sFg[r]);
+        // keep for the corrector / forward passes: one coalesced copy of the bundle
+        {
+            const int4* src = reinterpret_cast<const int4*>(sFB);
+            int4* dst = reinterpret_cast<int4*>(bundle(k));
+            const int n16 = obsize() * int(sizeof(F)) / 16;
+            for (int i = lane; i < n16; i += kTS) dst[i] = src[i];
+        }
         tsync();
         return ok;
     }
     // Force step of stage k for the state step dx (sDst + nu): lambda = L^-T (g_lambda + G dx),
-    // df = -q - D^-1 Df' lambda  -> sDst[nq, nu).  sC = [G | .] and sS = L^-1 of the stage are in shared memory.
-    __device__ void force_block_step(int k) {
+    // df = -q - D^-1 Df' lambda  -> sDst[nq, nu).  The bundle of the stage is in shared memory.
+    __device__ void force_block_step() {
         const int nq = NQ(), nx = NX(), nu = NU(), ne = NEQ(), nf = NF();
         const F* dx = sDst + nu;
-        const R* gl = wsr<R>(oGL()) + k * ne;
-        for (int r = lane; r < ne; r += kTS) {
-            const F* g = sC + r * (nx + 1);
-            R s = gl[r];
-            for (int j = 0; j < nx; ++j) s += R(g[j]) * R(dx[j]);
-            sFv[r] = s;
+        if (ne <= 8) {
+            const int r = lane >> 2, part = lane & 3;
+            R s = R(0);
+            if (r < ne) {
+                const F* g = sC + r * nx;
+                for (int j = part; j < nx; j += 4) s += R(g[j]) * R(dx[j]);
+                if (part == 0) s += sFg[r];
+            }
+            s += __shfl_xor_sync(FULL, s, 1);
+            s += __shfl_xor_sync(FULL, s, 2);
+            if (r < ne && part == 0) sFv[r] = s;
+        } else {
+            for (int r = lane; r < ne; r += kTS) {
+                const F* g = sC + r * nx;
+                R s = sFg[r];
+                for (int j = 0; j < nx; ++j) s += R(g[j]) * R(dx[j]);
+                sFv[r] = s;
+            }
         }
         tsync();
         force_LinvT_mul(sS, sFv, sFl);
         tsync();
-        const R* Dg = wsr<R>(oFBD()) + k * FBDN();
-        const R* qf = wsr<R>(oQF()) + k * NFC();
-        const F* Dc = ws + oDFC();
+        const F* Dc = sDFC;
         for (int c = lane; c < NC(); c += kTS) {
             R u[3] = {0, 0, 0};
             for (int side = 0; side < 2; ++side) {
@@ -1295,26 +1555,31 @@ struct Solver {
                     for (int i = 0; i < nf; ++i) u[i] += R(blk[rr * nf + i]) * lm;
                 }
             }
-            if (nf == 1) sDst[nq + c] = F(-qf[c] - Dg[c] * u[0]);
+            if (nf == 1) sDst[nq + c] = F(-sFq[c] - sD[c] * u[0]);
             else {
-                const R* o = Dg + 9 * c;
-                sDst[nq + 3 * c] = F(-qf[3 * c] - (o[0] * u[0] + o[1] * u[1] + o[2] * u[2]));
-                sDst[nq + 3 * c + 1] = F(-qf[3 * c + 1] - (o[3] * u[0] + o[4] * u[1] + o[5] * u[2]));
-                sDst[nq + 3 * c + 2] = F(-qf[3 * c + 2] - (o[6] * u[0] + o[7] * u[1] + o[8] * u[2]));
+                const R* o = sD + 9 * c;
+                sDst[nq + 3 * c] = F(-sFq[3 * c] - (o[0] * u[0] + o[1] * u[1] + o[2] * u[2]));
+                sDst[nq + 3 * c + 1] = F(-sFq[3 * c + 1] - (o[3] * u[0] + o[4] * u[1] + o[5] * u[2]));
+                sDst[nq + 3 * c + 2] = F(-sFq[3 * c + 2] - (o[6] * u[0] + o[7] * u[1] + o[8] * u[2]));
             }
         }
         tsync();
     }
-    // G and L^-1 of stage k from the workspace into sC / sS (forward and corrector passes)
-    __device__ void load_force_block(int k, bool need_L) {
-        const int nx = NX(), ne = NEQ();
-        const F* __restrict__ Gg = ws + oGS() + k * ne * nx;
-        for (int idx = lane; idx < ne * nx; idx += kTS) sC[(idx / nx) * (nx + 1) + idx % nx] = Gg[idx];
-        if (need_L) {
-            const R* __restrict__ Lg = wsr<R>(oFBL()) + k * FBLN();
-            for (int i = lane; i < FBLN(); i += kTS) sS[i] = Lg[i];
-        }
+    // the force bundle of stage k from the workspace into shared memory: synchronously, or issued as cp.async
+    // (no commit) for the staged kernels
+    __device__ void load_force_block(int k) {
+        if (NFC() == 0 || k < 0 || k >= NN()) return;
+        const int4* __restrict__ src = reinterpret_cast<const int4*>(bundle(k));
+        int4* dst = reinterpret_cast<int4*>(sFB);
+        const int n16 = obsize() * int(sizeof(F)) / 16;
+        for (int i = lane; i < n16; i += kTS) dst[i] = src[i];
         tsync();
+    }
+    __device__ __forceinline__ void fb_issue(int k) const {
+        if constexpr (kStageTT) {
+            if (NFC() == 0 || k < 0 || k >= NN()) return;
+            cp_async_bytes(sFB, bundle(k), obsize() * int(sizeof(F)));
+        }
     }
 
     // Blocked factorisation of the AUGMENTED reduced stage matrix [M m; m' .]:
@@ -1391,7 +1656,8 @@ struct Solver {
         const int a = lane >> 2, b = lane & 3;
         int ri[TR];
         const F* ycp[TC];
-        int gci[TC];
+        const F* gcp[TC];   // column c of [G | g_lambda]: G (row stride nx) or the F copy of g_lambda (stride 1)
+        int gst[TC];
 #pragma unroll
         for (int ii = 0; ii < TR; ++ii) ri[ii] = min(a * TR + ii, NX_ - 1);
         F acc[TR][TC];
@@ -1400,7 +1666,8 @@ struct Solver {
             const int c = b * TC + cc;
             const int cl = min(c, NX_ - 1);
             ycp[cc] = (c == NX_) ? vec : sM + (NU_ + cl) * ld;
-            gci[cc] = min(c, NX_);
+            gcp[cc] = (c >= NX_) ? sGf : sC + cl;
+            gst[cc] = (c >= NX_) ? 1 : NX_;
 #pragma unroll
             for (int ii = 0; ii < TR; ++ii) {
                 const int hi = max(ri[ii], cl), lo = min(ri[ii], cl);
@@ -1421,12 +1688,12 @@ struct Solver {
         }
 #pragma unroll 1
         for (int m = 0; m < n_g; ++m) {   // + [G g]'[G g]: the force block's contribution
-            const F* gr = sC + m * (NX_ + 1);
+            const F* gr = sC + m * NX_;
             F yr[TR], yc[TC];
 #pragma unroll
             for (int ii = 0; ii < TR; ++ii) yr[ii] = gr[ri[ii]];
 #pragma unroll
-            for (int cc = 0; cc < TC; ++cc) yc[cc] = gr[gci[cc]];
+            for (int cc = 0; cc < TC; ++cc) yc[cc] = gcp[cc][m * gst[cc]];
 #pragma unroll
             for (int ii = 0; ii < TR; ++ii)
 #pragma unroll
@@ -1458,12 +1725,11 @@ struct Solver {
     // with rc = t lam - target (+ dt_aff dlam_aff in the corrector).  The object-dynamics rows of k < N are NOT in
     // it: their values e + y / rho go to sFv and meet the forces in the force block.
     // Every row family accumulates into distinct entries per lane (no atomics).
-    __device__ void stage_gradient(int k, bool corrector, R mu_target) {
+    __device__ void stage_gradient(int k, bool corrector, F mu_target) {
         const int nq = NQ(), nu = NU(), nx = NX(), nz = NZ();
         const R dt = PR.dt;
         const R* zk = st_z(k);
         R* vec = sVec;
-        const R cm = corrector ? R(1) : R(0);
         // cost part (zero at the terminal stage)
         if (k < NN()) {
             const F* x = st_x(k);
@@ -1523,23 +1789,23 @@ struct Solver {
             }
             const R eps = row_eps(fam);
             const QuadR q = recs_tl(k)[r];
-            R c0 = R(0), c1 = R(0);
+            F c0 = F(0), c1 = F(0);
             if (corrector) {
                 const QuadF dd = recs_dd(k)[r];
-                c0 = R(dd.v[0]) * R(dd.v[2]);
-                c1 = R(dd.v[1]) * R(dd.v[3]);
+                c0 = dd.v[0] * dd.v[2];
+                c1 = dd.v[1] * dd.v[3];
             }
-            vec[m] += side_coef(q.v[0], q.v[2], val - lb, eps, mu_target, cm * c0) -
-                      side_coef(q.v[1], q.v[3], ub - val, eps, mu_target, cm * c1);
+            vec[m] += side_coef(q.v[0], q.v[2], val - lb, eps, mu_target, c0) -
+                      side_coef(q.v[1], q.v[3], ub - val, eps, mu_target, c1);
         }
         tsync();
         // equality rows
         if (k < NN()) {
-            const R* rho = rho_eq(k);
-            const R* y = y_eq(k);
-            for (int i = lane; i < NEQ(); i += kTS) {
-                const R e = eq_value_stage(k, i, zk);
-                sFv[i] = e + (rho[i] > R(0) ? y[i] / rho[i] : R(0));
+            eq_values_stage(k, zk, sFv);
+            if (!C.soft_poly) {   // hard rows carry multipliers: v = e + y / rho
+                tsync();
+                const R* y = y_eq(k);
+                for (int i = lane; i < NEQ(); i += kTS) sFv[i] += y[i] * rho_inv_stage(k, i);
             }
         } else {
             // terminal rows: m_i = rho e_i + y_i; unit rows touch distinct entries, the three dense rows go through
@@ -1573,10 +1839,10 @@ struct Solver {
                     const V3<R> a = fric_coeff(c, which);
                     const R val = a.x * f0 + a.y * f1 + a.z * f2;
                     const QuadR q = recs_tl(k)[r];
-                    R corr = R(0);
+                    F corr = F(0);
                     if (corrector) {
                         const QuadF dd = recs_dd(k)[r];
-                        corr = R(dd.v[0]) * R(dd.v[2]);
+                        corr = dd.v[0] * dd.v[2];
                     }
                     const R cf = side_coef(q.v[0], q.v[2], val, eps, mu_target, corr);
                     g0 += cf * a.x;
@@ -1598,10 +1864,10 @@ struct Solver {
                 R val = R(ws[oLHO() + k * NOBS() + i]);
                 for (int j = 0; j < OBSW(); ++j) val += R(J[j]) * zk[nu + j];
                 const QuadR q = recs_tl(k)[r];
-                R corr = R(0);
+                F corr = F(0);
                 if (corrector) {
                     const QuadF dd = recs_dd(k)[r];
-                    corr = R(dd.v[0]) * R(dd.v[2]);
+                    corr = dd.v[0] * dd.v[2];
                 }
                 crow[i] = side_coef(q.v[0], q.v[2], val, eps, mu_target, corr);
             }
@@ -1653,9 +1919,9 @@ struct Solver {
         }
         for (int k = NN(); k >= 0; --k) {
             long long f0 = clock64();
-            if constexpr (kStageTT) cp_wait<0>();           // side records and vectors of stage k are staged
-            if (k < NN() && NEQ() > 0) load_C(k);
-            stage_gradient(k, false, R(0));
+            if constexpr (kStageTT) cp_wait<0>();           // side records, vectors and C rows of stage k are staged
+            else if (k < NN() && NEQ() > 0) load_C(k);
+            stage_gradient(k, false, F(0));
             R* gp = GPk(k);
             for (int i = lane; i < nz; i += kTS) gp[i] = sVec[i];
             if (k < NN()) {
@@ -1664,32 +1930,33 @@ struct Solver {
             }
             long long f1 = clock64();
             t_g += f1 - f0;
+            // the forces go first: their elimination uses the (still idle) stage-matrix buffer as scratch
+            bool fok = true;
+            if (k < NN() && NFC() > 0) {
+                force_block_D(k);
+                fok = force_block_factor(k);
+                if (!fok && nan_reason == 0) nan_reason = 6;
+            }
+            long long f2 = clock64();
+            t_f2 += f2 - f1;
             if (k < NN()) assign_dynamics_hessian();
             build_stage_matrix(k, k < NN());
-            if (k < NN() && NFC() > 0) force_block_D(k);
-            if constexpr (kStageTT) {                       // next stage's records / vectors arrive during the factorisation
+            if constexpr (kStageTT) {                       // next stage's records / vectors / C rows arrive during the factorisation
                 tsync();
                 tt_issue(k - 1, false);
                 sm_issue(k - 1, false, true);
+                c_issue(k - 1);
                 cp_commit();
             }
-            long long f2 = clock64();
-            t_f1 += f2 - f1;
+            long long f3 = clock64();
+            t_f1 += f3 - f2;
             if (k < NN()) {
-                bool fok = true;
-                if (NFC() > 0) {
-                    fok = force_block_factor(k);
-                    if (!fok && nan_reason == 0) nan_reason = 6;
-                    for (int i = lane; i < nq; i += kTS) sRv[i] = F(sVec[i]);
-                    for (int j = lane; j < nx; j += kTS) sRv[nq + j] = F(sVec[nu + j]);   // G' g_lambda joins in the Schur update
-                    tsync();
-                } else {
-                    reduced_rhs(k, nullptr, 0, nullptr);
-                }
+                // reduced right-hand side [m_j; m_x]; G' g_lambda joins in the Schur update
+                for (int i = lane; i < nq; i += kTS) sRv[i] = F(sVec[i]);
+                for (int j = lane; j < nx; j += kTS) sRv[nq + j] = F(sVec[nu + j]);
+                tsync();
                 ok &= fok;
                 add_dynamics_gradient(sRv);                  // uses p_{k+1} in sPv
-                long long f3 = clock64();
-                t_f2 += f3 - f2;
                 F* Fk = ws + oFAC() + k * FSTRIDE();
                 // factor, forward substitution (w in sRv[0, nq)), p -> sPv, P -> sP, factor block -> workspace
                 ok &= stage_factor_blocked(sRv, Fk, NFC() > 0 ? NEQ() : 0);
@@ -1707,14 +1974,14 @@ struct Solver {
 
     // Pass C (backward, corrector): gradient = stored predictor gradient + the side terms that change
     // with the centring target and the second-order correction; backward vector step with stored factors.
-    __device__ void pass_backward_corrector(R target_mu) {
+    __device__ void pass_backward_corrector(F target_mu) {
         constexpr int nq = D::nq, nx = D::nx;
         const int nu = NU(), nz = NZ();
         for (int i = lane; i < nx; i += kTS) sPv[i] = F(0);
         tsync();
         const int nbx = NBOXU() + nx;
-        // cp.async group schedule: TT(k) is committed before FAC(k); every wait leaves exactly one younger group
-        // in flight (none at the terminal stage)
+        // cp.async group schedule: [records, gradient, force bundle](k) is committed before FAC(k); every wait leaves
+        // exactly one younger group in flight (none at the terminal stage)
         if constexpr (kStageTT) {
             tt_issue(NN(), true);
             sm_issue(NN(), true, false);
@@ -1724,24 +1991,27 @@ struct Solver {
             if constexpr (kStageTT) {
                 if (k == NN()) cp_wait<0>();
                 else cp_wait<1>();
+            } else {
+                load_force_block(k);
             }
             const R* gpk = st_gp(k);
             for (int i = lane; i < nz; i += kTS) sVec[i] = gpk[i];
             tsync();
-            // (corr - target) / (t + eps lam) per side
+            // (corr - target) / (t + eps lam) per side: small terms, F arithmetic
             for (int r = lane; r < nbx; r += kTS) {
                 const int fam = r < NBOXU() ? 0 : 1;
                 if (!row_valid(k, fam)) continue;
                 const int m = fam == 0 ? r : nu + (r - NBOXU());
-                const R eps = row_eps(fam);
+                const F eps = F(row_eps(fam));
                 const QuadR q = recs_tl(k)[r];
                 const QuadF dd = recs_dd(k)[r];
-                sVec[m] += (R(dd.v[0]) * R(dd.v[2]) - target_mu) / (q.v[0] + eps * q.v[2]) -
-                           (R(dd.v[1]) * R(dd.v[3]) - target_mu) / (q.v[1] + eps * q.v[3]);
+                const F l0 = F(q.v[2]), l1 = F(q.v[3]);
+                sVec[m] += R(fdiv(dd.v[0] * dd.v[2] - target_mu, F(q.v[0]) + eps * l0) -
+                             fdiv(dd.v[1] * dd.v[3] - target_mu, F(q.v[1]) + eps * l1));
             }
             tsync();
             if (NFRIC() > 0 && k < NN()) {
-                const R eps = row_eps(2);
+                const F eps = F(row_eps(2));
                 for (int c = lane; c < NC(); c += kTS) {
                     R g0 = 0, g1 = 0, g2 = 0;
                     for (int which = 0; which < 5; ++which) {
@@ -1749,7 +2019,7 @@ struct Solver {
                         const V3<R> a = fric_coeff(c, which);
                         const QuadR q = recs_tl(k)[r];
                         const QuadF dd = recs_dd(k)[r];
-                        const R cf = (R(dd.v[0]) * R(dd.v[2]) - target_mu) / (q.v[0] + eps * q.v[2]);
+                        const R cf = R(fdiv(dd.v[0] * dd.v[2] - target_mu, F(q.v[0]) + eps * F(q.v[2])));
                         g0 += cf * a.x;
                         g1 += cf * a.y;
                         g2 += cf * a.z;
@@ -1761,13 +2031,13 @@ struct Solver {
                 tsync();
             }
             if (NOBS() > 0 && k >= 1 && k < NN()) {
-                const R eps = row_eps(3);
+                const F eps = F(row_eps(3));
                 R* crow = sScr;
                 for (int i = lane; i < NOBS(); i += kTS) {
                     const int r = nbx + NFRIC() + i;
                     const QuadR q = recs_tl(k)[r];
                     const QuadF dd = recs_dd(k)[r];
-                    crow[i] = (R(dd.v[0]) * R(dd.v[2]) - target_mu) / (q.v[0] + eps * q.v[2]);
+                    crow[i] = R(fdiv(dd.v[0] * dd.v[2] - target_mu, F(q.v[0]) + eps * F(q.v[2])));
                 }
                 tsync();
                 if (lane < OBSW()) {
@@ -1777,15 +2047,14 @@ struct Solver {
                 }
                 tsync();
             }
-            if constexpr (kStageTT) {
-                tsync();
-                tt_issue(k - 1, true);
-                sm_issue(k - 1, true, false);
-                cp_commit();
-            }
             if (k == NN()) {
                 for (int i = lane; i < nx; i += kTS) sPv[i] = F(sVec[nu + i]);
                 if constexpr (kStageTT) {
+                    tsync();
+                    tt_issue(k - 1, true);
+                    sm_issue(k - 1, true, false);
+                    fb_issue(k - 1);
+                    cp_commit();
                     fac_issue(k - 1, (k - 1) & 1);
                     cp_commit();
                 }
@@ -1793,22 +2062,29 @@ struct Solver {
                 continue;
             }
             if (NFC() > 0) {
-                // force block with the new gradient: q = D^-1 m_f, g_lambda = L^-1 (v - Df q)
-                const R* Dg = wsr<R>(oFBD()) + k * FBDN();
-                force_q(Dg, sVec + nq, sFq);
+                // force block with the new gradient: q = D^-1 m_f, g_lambda = L^-1 (v - Df q); both replace the
+                // predictor's in the stored bundle
+                force_q(sD, sVec + nq, sFq);
                 tsync();
                 const R* ve = wsr<R>(oVE()) + k * NEQ();
                 for (int r = lane; r < NEQ(); r += kTS) sFv[r] = ve[r] - eq_force_dot(r, sFq);
                 tsync();
-                force_Linv_mul(wsr<R>(oFBL()) + k * FBLN(), sFv, sFg);
+                force_Linv_mul(sS, sFv, sFg);
                 tsync();
-                R* gl = wsr<R>(oGL()) + k * NEQ();
+                R* gl = reinterpret_cast<R*>(bundle(k) + obGl());
                 for (int r = lane; r < NEQ(); r += kTS) gl[r] = sFg[r];
-                R* qf = wsr<R>(oQF()) + k * NFC();
+                R* qf = reinterpret_cast<R*>(bundle(k) + obQ());
                 for (int i = lane; i < NFC(); i += kTS) qf[i] = sFq[i];
-                reduced_rhs(k, ws + oGS() + k * NEQ() * nx, nx, sFg);
+                reduced_rhs(k, sC, nx, sFg);
             } else {
                 reduced_rhs(k, nullptr, 0, nullptr);
+            }
+            if constexpr (kStageTT) {
+                tsync();
+                tt_issue(k - 1, true);
+                sm_issue(k - 1, true, false);
+                fb_issue(k - 1);
+                cp_commit();
             }
             add_dynamics_gradient(sRv);
             const F* Fb = sM;
@@ -1842,36 +2118,40 @@ struct Solver {
     }
 
     // Side steps of the rows of ONE stage for the stage direction d = [du; dx] (shared memory):
-    // d lambda, d t per side, and the running maximum feasible step.
-    __device__ __forceinline__ void stage_side_steps(int k, const F* d, bool corrector, R target_mu, R& amax, R& rnd) {
+    // d lambda, d t per side, and the running maximum feasible step.  Directions: F arithmetic on the F images of
+    // t and lambda; only the slack residual rd = d + eps lam - t is formed in double.  `rnd`: bound on what the
+    // F arithmetic leaves of rd after a full step.
+    __device__ __forceinline__ void stage_side_steps(int k, const F* d, bool corrector, F target_mu, F& amax, F& rnd) {
         const R* zk = st_z(k);
-        const R cm = corrector ? R(1) : R(0);
+        const F cm = corrector ? F(1) : F(0);
+        constexpr F kEps = std::is_same<F, R>::value ? F(4.5e-16) : F(2.4e-7);
         for (int r = lane; r < NROW(); r += kTS) {
             const int fam = row_family(r);
             if (!row_valid(k, fam)) continue;
             R lb, ub;
             const R val = row_value(k, r, fam, zk, st_x(k), st_u(k), &lb, &ub);
-            const R adz = row_dot(k, r, fam, d);
+            const F adz = F(row_dot(k, r, fam, d));
             const R eps = row_eps(fam);
+            const F epsf = F(eps);
             const QuadR q = recs_tl(k)[r];
             QuadF dd = recs_dd(k)[r];
             const int nsd = fam >= 2 ? 1 : 2;
             for (int sd = 0; sd < nsd; ++sd) {
                 const R t = q.v[sd], lam = q.v[2 + sd];
-                const R sg = sd == 0 ? R(1) : R(-1);
+                const F sg = sd == 0 ? F(1) : F(-1);
                 const R dist = sd == 0 ? val - lb : ub - val;
-                const R rd = dist + eps * lam - t;
-                const R rc = t * lam - target_mu + cm * R(dd.v[sd]) * R(dd.v[2 + sd]);
-                const R iden = R(1) / (t + eps * lam);
-                const R dl = -(rc + lam * rd) * iden - (lam * iden) * sg * adz;
-                const R dtt = sg * adz + eps * dl + rd;
-                dd.v[sd] = F(dtt);
-                dd.v[2 + sd] = F(dl);
-                // what the rounding of the stored step leaves of the slack residual d + eps lam - t after a full step
-                rnd = max(rnd, fabs(dtt - R(dd.v[sd])) + eps * fabs(dl - R(dd.v[2 + sd])));
-                // the step that is applied is the stored (rounded) one
-                if (R(dd.v[sd]) < R(0)) amax = min(amax, -t / R(dd.v[sd]));
-                if (R(dd.v[2 + sd]) < R(0)) amax = min(amax, -lam / R(dd.v[2 + sd]));
+                const F rd = F(dist + eps * lam - t);
+                const F tf = F(t), lf = F(lam);
+                const F rc = tf * lf - target_mu + cm * dd.v[sd] * dd.v[2 + sd];
+                const F iden = fdiv(F(1), tf + epsf * lf);
+                const F dl = -(rc + lf * rd) * iden - (lf * iden) * sg * adz;
+                const F dtt = sg * adz + epsf * dl + rd;
+                dd.v[sd] = dtt;
+                dd.v[2 + sd] = dl;
+                rnd = max(rnd, kEps * (fabs(adz) + fabs(rd) + epsf * fabs(dl)));
+                if (!(fabs(dtt) + fabs(dl) < tinf<F>())) rnd = tinf<F>();   // a step outside the range of F: not applied
+                if (dtt < F(0)) amax = min(amax, fdiv(-tf, dtt));
+                if (dl < F(0)) amax = min(amax, fdiv(-lf, dl));
             }
             *side_dd(k, r) = dd;
         }
@@ -1879,24 +2159,25 @@ struct Solver {
 
     // Passes B / D (forward): direction from the stored factors and w, written to DZ, with the force steps and the
     // side steps of every stage fused in.  Returns the largest feasible step in (0, 1].
-    __device__ R pass_forward(bool corrector, R target_mu, R* rnd_out) {
+    __device__ R pass_forward(bool corrector, F target_mu, R* rnd_out) {
         constexpr int nq = D::nq, nx = D::nx;
         const int nu = NU(), nz = NZ();
         F* dxn = sDxn;          // [nx] next state direction
         F* dst = sDst;          // [nz] stage direction [dj; df; dx]
         F* dj = dst;
         F* dx = dst + nu;
-        R amax = R(1), rnd = R(0);
+        F amax = F(1), rnd = F(0);
         for (int i = lane; i < nz; i += kTS) dst[i] = F(0);
         tsync();
-        // cp.async group schedule: FAC(k) is committed before TT(k); every wait leaves exactly one younger group
-        // in flight (none for the records of the terminal stage)
+        // cp.async group schedule: FAC(k) is committed before [records, vectors, force bundle](k); every wait leaves
+        // exactly one younger group in flight (none for the records of the terminal stage)
         if constexpr (kStageTT) {
             fac_issue(0, 0);
             w_issue(0);
             cp_commit();
             tt_issue(0, true);
             sm_issue(0, false, false);
+            fb_issue(0);
             cp_commit();
         }
         for (int k = 0; k <= NN(); ++k) {
@@ -1933,25 +2214,22 @@ struct Solver {
                     if (lane == 0) dj[j] = uj;
                     tsync();
                 }
-                if (NFC() > 0) {
-                    load_force_block(k, true);
-                    force_block_step(k);
-                }
+                if constexpr (kStageTT) cp_wait<1>();       // records, vectors and the force bundle of stage k
+                else load_force_block(k);
+                if (NFC() > 0) force_block_step();
             } else {
+                if constexpr (kStageTT) cp_wait<0>();
                 for (int j = lane; j < nu; j += kTS) dst[j] = F(0);
                 tsync();
             }
             F* Dk = DZk(k);
             for (int i = lane; i < nz; i += kTS) Dk[i] = dst[i];
-            if constexpr (kStageTT) {
-                if (k == NN()) cp_wait<0>();
-                else cp_wait<1>();
-            }
             stage_side_steps(k, dst, corrector, target_mu, amax, rnd);
             if constexpr (kStageTT) {
                 tsync();
                 tt_issue(k + 1, true);
                 sm_issue(k + 1, false, false);
+                fb_issue(k + 1);
                 cp_commit();
             }
             if (k < NN()) {
@@ -1968,8 +2246,8 @@ struct Solver {
             }
         }
         if constexpr (kStageTT) cp_wait<0>();
-        *rnd_out = tmax(rnd);
-        return tmin(amax);
+        *rnd_out = R(tmax(rnd));
+        return R(tmin(amax));
     }
 
     // Interior-point QP solve around the current (X, U).  Leaves the step in Z
@@ -2135,9 +2413,9 @@ struct Solver {
                     long long c3 = clock64();
                     t_swp += c3 - c2;
                     c2 = c3;
-                    pass_backward_corrector(target_mu);
+                    pass_backward_corrector(F(target_mu));
                 }
-                a_fwd = pass_forward(pass == 1, pass == 1 ? target_mu : R(0), &rnd_gap);
+                a_fwd = pass_forward(pass == 1, pass == 1 ? F(target_mu) : F(0), &rnd_gap);
             }
             if (nsides > 0) alpha = min(R(1), R(0.995) * a_fwd);
             t_side += clock64() - c2;
@@ -2145,7 +2423,7 @@ struct Solver {
             R stepmax = 0;
             for (int idx = lane; idx < (N + 1) * nz; idx += kTS) stepmax = max(stepmax, fabs(alpha * R(ws[oDZ() + idx])));
             stepmax = tmax(stepmax);
-            if (!(stepmax < tinf<R>()) || !(alpha > R(0)) || !(alpha <= R(1))) {
+            if (!(stepmax < tinf<R>()) || !(alpha > R(0)) || !(alpha <= R(1)) || !(rnd_gap < tinf<R>())) {
                 if constexpr (std::is_same<F, R>::value) {
                     *finite = false;
                     if (nan_reason == 0) nan_reason = !(alpha <= R(1)) ? 5 : 2;
@@ -2198,7 +2476,7 @@ struct Solver {
             const F* Fg = ws + oFAC() + k * FSTRIDE();
             for (int idx = lane; idx < FSTRIDE(); idx += kTS) Fb[idx] = Fg[idx];
             tsync();
-            if (NFC() > 0) load_force_block(k, true);
+            load_force_block(k);
             for (int xcol = 0; xcol < nx; ++xcol) {
                 for (int j = lane; j < nq; j += kTS) col[j] = Fb[fidx(nq + xcol, j)];
                 tsync();
@@ -2214,12 +2492,12 @@ struct Solver {
                 if (NFC() > 0) {
                     // unit state step along xcol: lambda = L^-T G e, df = -D^-1 Df' lambda (no constant terms)
                     const int ne = NEQ(), nf = NF();
-                    for (int r = lane; r < ne; r += kTS) sFv[r] = R(sC[r * (nx + 1) + xcol]);
+                    for (int r = lane; r < ne; r += kTS) sFv[r] = R(sC[r * nx + xcol]);
                     tsync();
                     force_LinvT_mul(sS, sFv, sFl);
                     tsync();
-                    const R* Dg = wsr<R>(oFBD()) + k * FBDN();
-                    const F* Dc = ws + oDFC();
+                    const R* Dg = sD;
+                    const F* Dc = sDFC;
                     for (int c = lane; c < NC(); c += kTS) {
                         R u[3] = {0, 0, 0};
                         for (int side = 0; side < 2; ++side) {
@@ -2247,6 +2525,8 @@ struct Solver {
         constexpr int nq = D::nq, nx = D::nx;
         const int nu = NU(), N = NN(), nz = NZ();
         t_lin = t_fac = t_swp = t_side = t_ls = t_f1 = t_f2 = t_f3 = t_g = 0;
+        const long long t_run0 = clock64();
+        long long t_init = 0;
         nan_reason = 0;
         // initial guess: DefaultInitializer = zero input, state held
         // (controller_interface.cpp:385-386); x_0 is always the observation
@@ -2281,6 +2561,7 @@ struct Solver {
         tsync();
         if (NEQ() > 0) build_Df();
         Perf<F> base = performance(X, U);
+        t_init = clock64() - t_run0;
         int status = UB_STATUS_CONVERGED, qp_iters = 0, sqp_done = 0;
         F alpha = 0;
         R qp_res = 0;
@@ -2408,6 +2689,14 @@ struct Solver {
             }
             for (int idx = lane; idx < (N + 1) * nxo; idx += kTS) Xo[(idx / nxo) * nxt + nx + idx % nxo] = ws[oXO() + idx];
             for (int idx = lane; idx < N * nu; idx += kTS) Uo[idx] = U[idx];
+            // the same rows into the peers' gathered buffers (P2P stores over NVLink)
+            for (int p = 0; p < A.ngather; ++p) {
+                F* Xp = A.Xg[p] + size_t(A.gather_row + b) * (N + 1) * nxt;
+                F* Up = A.Ug[p] + size_t(A.gather_row + b) * N * nu;
+                for (int idx = lane; idx < (N + 1) * nx; idx += kTS) Xp[(idx / nx) * nxt + idx % nx] = X[idx];
+                for (int idx = lane; idx < (N + 1) * nxo; idx += kTS) Xp[(idx / nxo) * nxt + nx + idx % nxo] = ws[oXO() + idx];
+                for (int idx = lane; idx < N * nu; idx += kTS) Up[idx] = U[idx];
+            }
         }
         bad = tsum(bad);
         if (bad > F(0)) {
@@ -2430,6 +2719,13 @@ struct Solver {
                 s[5] = base.max_eq;
                 s[6] = base.min_margin;
                 s[7] = F(sqp_done);
+                if (A.stop_after == 8) {  // profile mode: linearisation, line search, whole solve, interior-point loop
+                    s[1] = F(t_lin);
+                    s[2] = F(t_ls);
+                    s[3] = F(clock64() - t_run0);
+                    s[4] = F(t_fac + t_swp + t_side);
+                    s[5] = F(t_init);
+                }
                 if (A.stop_after == 9) {  // profile mode: phase cycle counters replace stats[1..7]
                     s[1] = F(t_g);
                     s[2] = F(t_f1);
@@ -2493,12 +2789,18 @@ __global__ void __launch_bounds__(256, 2) solve_batch_kernel(const __grid_consta
     S.sM = sm + Lk.sM;
     S.sP = sm + Lk.sP;
     S.sPv = sm + Lk.sPv;
-    S.sC = sm + Lk.sC;
-    S.sS = reinterpret_cast<double*>(sm + Lk.sS);
-    S.sD = reinterpret_cast<double*>(sm + Lk.sD);
-    S.sFq = reinterpret_cast<double*>(sm + Lk.sFq);
+    S.sFB = sm + Lk.sFB;
+    S.sC = S.sFB + Lk.bG;
+    S.sS = reinterpret_cast<double*>(S.sFB + Lk.bL);
+    S.sD = reinterpret_cast<double*>(S.sFB + Lk.bD);
+    S.sFg = reinterpret_cast<double*>(S.sFB + Lk.bGl);
+    S.sFq = reinterpret_cast<double*>(S.sFB + Lk.bQ);
+    S.sGf = sm + Lk.sGf;
+    S.sDFC = sm + Lk.sDFC;
+    S.sUS = reinterpret_cast<double*>(sm + Lk.sUS);
+    S.sCst = sm + Lk.sCst;
+    S.cC = (D::kStatic && D::nrow <= UB_STAGE_ROWS_MAX) ? S.sCst : S.sC;
     S.sFv = reinterpret_cast<double*>(sm + Lk.sFv);
-    S.sFg = reinterpret_cast<double*>(sm + Lk.sFg);
     S.sFl = reinterpret_cast<double*>(sm + Lk.sFl);
     S.sVec = reinterpret_cast<double*>(sm + Lk.sVec);
     S.sDst = sm + Lk.sDst;

@@ -106,3 +106,75 @@ class PipelinedSolveGather:
 
     def finish(self):
         torch.cuda.current_stream().wait_stream(self.comm)
+
+
+def _share_cuda_tensor(t, group=None):
+    """Views of `t` of every rank of a single-node group in THIS process: CUDA IPC handles travel through
+    all_gather_object and are opened with torch's own rebuild function (peer ranks run on the other GPUs of the
+    node, so the views are peer-mapped device memory)."""
+    from torch.multiprocessing.reductions import reduce_tensor
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    fn, args = reduce_tensor(t)
+    packed = [None] * world
+    dist.all_gather_object(packed, (fn, args), group=group)
+    views = []
+    for r in range(world):
+        views.append(t if r == rank else packed[r][0](*packed[r][1]))
+    return views
+
+
+class FusedSolveGather:
+    """Sharded solves whose result exchange is done BY THE SOLVE KERNEL: every rank owns a gathered buffer
+    [world * B] for X and U; the buffers of all ranks are mapped into every process (CUDA IPC over NVLink) and
+    `ub_set_gather_targets` makes the kernel's epilogue store each solved instance into its row of every peer's
+    buffer (and, through the X / U arguments, of its own) while the rest of the batch is still being solved.  No
+    collective kernel, no copy engine work, nothing competing with the persistent solve grid for SMs.  Two buffer
+    sets alternate so that step s + 1 never overwrites rows a consumer of step s may still be reading;
+    `finish()` = local stream synchronisation + one barrier, after which `gathered_views(i)` is complete on every
+    rank."""
+
+    def __init__(self, mpc, batch, group=None):
+        import ctypes as C
+        self.mpc, self.B, self.group = mpc, batch, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world - 1 > 8:
+            raise ValueError("at most 8 peers")
+        dev, dt = torch.device("cuda", torch.cuda.current_device()), mpc.torch_dtype
+        W, B = self.world, batch
+        self.Xfull = [torch.zeros((W * B, mpc.N + 1, mpc.nx), dtype=dt, device=dev) for _ in range(2)]
+        self.Ufull = [torch.zeros((W * B, mpc.N, mpc.nu), dtype=dt, device=dev) for _ in range(2)]
+        self.status = torch.empty(B, dtype=torch.int32, device=dev)
+        self.stats = torch.empty((B, 8), dtype=dt, device=dev)
+        # peer views of both buffer sets (kept alive: closing an IPC mapping while kernels write to it is an error)
+        self._peerX = [_share_cuda_tensor(t, group) for t in self.Xfull]
+        self._peerU = [_share_cuda_tensor(t, group) for t in self.Ufull]
+        self._targets = []
+        for i in range(2):
+            xs = [self._peerX[i][r].data_ptr() for r in range(W) if r != self.rank]
+            us = [self._peerU[i][r].data_ptr() for r in range(W) if r != self.rank]
+            self._targets.append(((C.c_void_p * len(xs))(*xs), (C.c_void_p * len(us))(*us), len(xs)))
+        self.step_index = 0
+        dist.barrier(group)
+
+    def step(self, x0, target, body=None):
+        from . import bindings as Bd
+        i = self.step_index & 1
+        self.step_index += 1
+        lo = self.rank * self.B
+        xs, us, n = self._targets[i]
+        Bd.check(self.mpc.lib.ub_set_gather_targets(self.mpc.handle, n, xs, us, lo))
+        try:
+            self.mpc.solve_device(x0, target, body, X=self.Xfull[i][lo:lo + self.B], U=self.Ufull[i][lo:lo + self.B],
+                                  status=self.status, stats=self.stats)
+        finally:
+            Bd.check(self.mpc.lib.ub_set_gather_targets(self.mpc.handle, 0, None, None, 0))
+        return i
+
+    def gathered_views(self, i):
+        """(X [world, B, N+1, nx], U [world, B, N, nu]) of buffer set i."""
+        return (self.Xfull[i].view(self.world, self.B, self.mpc.N + 1, self.mpc.nx),
+                self.Ufull[i].view(self.world, self.B, self.mpc.N, self.mpc.nu))
+
+    def finish(self):
+        torch.cuda.current_stream().synchronize()
+        dist.barrier(self.group)

@@ -14,12 +14,12 @@ import numpy as np
 
 from . import bindings as B
 
-LAYOUT_FIELDS = ("Z", "DZ", "GAP", "LG", "LC", "LR", "LJP", "LHO", "LJO", "DF", "DFC", "RHOE", "YE", "RHOT", "YT", "TL", "DD",
-                 "GP", "VE", "FAC", "WF", "FBD", "FBL", "GS", "GL", "QF", "XN", "UN", "XW", "UW", "TG", "BD", "LIA", "LJA",
-                 "XO", "DXO", "total", "sM", "sP", "sPv", "sC", "sS", "sD", "sFq", "sFv", "sFg", "sFl", "sVec", "sDst",
-                 "sDxn", "sRv", "sScr", "sTL", "sDD", "sSmZ", "sSmX", "sSmU", "sSmJ", "sSmW", "s_total", "rw")
+LAYOUT_FIELDS = ("Z", "DZ", "GAP", "LG", "LC", "LR", "LJP", "LHO", "LJO", "DF", "RHOE", "YE", "RHOT", "YT", "TL", "DD",
+                 "GP", "VE", "FAC", "WF", "FBB", "XN", "UN", "XW", "UW", "TG", "BD", "LIA", "LJA", "XO", "DXO", "total",
+                 "bG", "bL", "bD", "bGl", "bQ", "bsize", "sM", "sP", "sPv", "sFB", "sGf", "sFv", "sFl", "sVec", "sDst", "sDxn",
+                 "sRv", "sScr", "sDFC", "sUS", "sCst", "sTL", "sDD", "sSmZ", "sSmX", "sSmU", "sSmJ", "sSmW", "s_total", "rw")
 # workspace blocks that hold doubles whatever the kernels' matrix type (ub_solver.cuh: compute_layout)
-LAYOUT_DOUBLE_BLOCKS = ("Z", "GAP", "LG", "LR", "RHOE", "YE", "RHOT", "YT", "TL", "GP", "VE", "FBD", "FBL", "GL", "QF")
+LAYOUT_DOUBLE_BLOCKS = ("Z", "GAP", "LG", "LR", "RHOE", "YE", "RHOT", "YT", "TL", "GP", "VE")
 
 
 def _ptr(a):
@@ -139,12 +139,36 @@ class BatchedMPC:
     # ----------------------------------------------------------- closed loop
     def closed_loop(self, x0, target_times, target_pos, n_steps, sim_dt, replan_period, body_params=None,
                     use_feedback=True, cold_start=False, init_sqp_iteration=1, sqp_iteration=1, gains=(0.0, 0.0, 0.0),
-                    log_stride=1, log=True):
+                    log_stride=1, log=True, obstacles=None, obstacle_offsets=None):
         """B closed-loop rollouts on the device (`ub_closed_loop`): replan gate, warm-start shift, policy
         evaluation and the triple-integrator plant as in `mpc_sim.py:118-160`.
 
         x0 [B, nx]; target_times [M]; target_pos [B, M, 3].  Returns dict(xs [B, n_log, nx], us [B, n_log, nq],
-        x_final [B, nx], n_replans, status_counts [B, 4])."""
+        x_final [B, nx], n_replans, status_counts [B, 4]).
+
+        Problems with dynamic obstacles (nx = 3 nq + 9 per obstacle): `obstacles` = one list of modes per obstacle,
+        each mode a dict(time, position, velocity, acceleration) as under `simulation.dynamic_obstacles.obstacles`
+        (obstacles/dynamic.yaml:38-75); `obstacle_offsets` [B, n, 3] places `relative` obstacles per instance.  The
+        obstacle columns of x0 are their states at the start."""
+        nobs = self.desc.n_dynamic_obstacles if self.desc.obstacles_enabled else 0
+        if obstacles is not None:
+            if len(obstacles) != nobs:
+                raise ValueError(f"the problem carries {nobs} dynamic obstacle(s)")
+            nm = (C.c_int32 * nobs)(*[len(m) for m in obstacles])
+            modes = (B.ObstacleMode * (nobs * B.UB_MAX_OBSTACLE_MODES))()
+            for j, ms in enumerate(obstacles):
+                if not 1 <= len(ms) <= B.UB_MAX_OBSTACLE_MODES:
+                    raise ValueError("1 .. UB_MAX_OBSTACLE_MODES modes per obstacle")
+                for m, md in enumerate(ms):
+                    e = modes[j * B.UB_MAX_OBSTACLE_MODES + m]
+                    e.time = float(md["time"])
+                    e.position[:] = [float(v) for v in md["position"]]
+                    e.velocity[:] = [float(v) for v in md["velocity"]]
+                    e.acceleration[:] = [float(v) for v in md["acceleration"]]
+            off = None if obstacle_offsets is None else np.ascontiguousarray(obstacle_offsets, dtype=np.float64).reshape(-1, nobs, 3)
+            B.check(self.lib.ub_closed_loop_set_obstacles(self.handle, nobs, nm, modes, 0 if off is None else off.shape[0], _ptr(off)))
+        else:
+            B.check(self.lib.ub_closed_loop_set_obstacles(self.handle, 0, None, None, 0, None))
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
         Bn = x0.shape[0]
         tt = np.ascontiguousarray(np.atleast_1d(target_times), dtype=np.float64)
@@ -174,7 +198,8 @@ class BatchedMPC:
         x = np.ascontiguousarray(np.atleast_2d(x), dtype=np.float64)
         u = np.ascontiguousarray(np.atleast_2d(u), dtype=np.float64)
         M = x.shape[0]
-        cap = M * max(self.n_eq, 5 * self.nc, self.desc.n_pairs, self.desc.n_projectile_links, 6, 1)
+        cap = M * max(self.n_eq * (self.nx_robot + self.nu), 5 * self.nc, self.desc.n_pairs, self.desc.n_projectile_links,
+                      3 * self.desc.nq, 6, 1)
         out = np.zeros(cap)
         rows = C.c_int32()
         tg = None if target is None else np.ascontiguousarray(target, dtype=np.float64).reshape(M, 3)

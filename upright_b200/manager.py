@@ -108,7 +108,56 @@ class ControllerInterface:
             raise RuntimeError(f"unknown cost {name}")
         total = self.cost(t, x, u)
         zero_w = self._engine.eval("cost", x, u)[0, 0]  # without the EE term
-        return float(zero_w if name == "state_input_cost" else total - zero_w)
+        if name == "end_effector_cost":
+            return float(total - zero_w)
+        # the quadratic state-input term alone (controller_interface.cpp:136): the "cost" probe also carries the
+        # inertial-alignment cost when that is enabled
+        ia = self._engine.eval("inertial_alignment_cost", x, u)[0, 0] if self.desc.ia_cost_enabled else 0.0
+        return float(zero_w - ia)
+
+    # ---- model queries of ocs2::PythonInterface bound at pybindings.cpp:388-397
+    def flowMap(self, t, x, u):
+        """x' = [v, a, jerk] for the robot, [v_o, a_o, 0] per dynamic obstacle (dynamics/system_dynamics.h:15-38,86-104);
+        the contact forces do not enter."""
+        x, u = np.asarray(x, dtype=float), np.asarray(u, dtype=float)
+        nq, no = self.desc.nq, self.desc.n_dynamic_obstacles if self.desc.obstacles_enabled else 0
+        out = np.concatenate((x[nq:3 * nq], u[:nq]))
+        for j in range(no):
+            o = x[3 * nq + 9 * j: 3 * nq + 9 * (j + 1)]
+            out = np.concatenate((out, o[3:9], np.zeros(3)))
+        return out
+
+    def flowMapLinearApproximation(self, t, x, u):
+        """-> object with f, dfdx, dfdu (ocs2::VectorFunctionLinearApproximation): the flow map is linear."""
+        nq, nx, nu = self.desc.nq, self.getStateDim(), self.getInputDim()
+        A, Bm = np.zeros((nx, nx)), np.zeros((nx, nu))
+        A[:2 * nq, nq:3 * nq] = np.eye(2 * nq)
+        Bm[2 * nq:3 * nq, :nq] = np.eye(nq)
+        for o in range(3 * nq, nx, 9):
+            A[o:o + 6, o + 3:o + 9] = np.eye(6)
+        return _Approximation(f=self.flowMap(t, x, u), dfdx=A, dfdu=Bm)
+
+    def costQuadraticApproximation(self, t, x, u):
+        """-> object with f, dfdx, dfdu, dfdxx, dfdux, dfduu of the intermediate cost: quadratic state-input cost
+        (quadratic_joint_state_input_cost.h:9-33) + end-effector cost with its Gauss-Newton Hessian
+        (end_effector_cost.h:48-84) [+ the inertial-alignment Gauss-Newton cost is not part of this query]."""
+        d = self.desc
+        x, u = np.asarray(x, dtype=float), np.asarray(u, dtype=float)
+        nq, nxr, nx, nu = d.nq, 3 * d.nq, self.getStateDim(), self.getInputDim()
+        Q = np.zeros(nx)
+        Q[:nxr] = np.array(d.state_weight[:nxr])
+        xd = np.zeros(nx)
+        xd[:nxr] = np.array(d.xd[:nxr])
+        Rw = np.concatenate((np.array(d.input_weight[:nq]), np.full(nu - nq, d.force_weight)))
+        W = np.array(d.ee_weight[:3])
+        tgt = self._core.targets[0].get_desired_state(t)[:3]
+        r = self._engine.eval("end_effector_position", x, u)[0]
+        J = np.zeros((3, nx))
+        J[:, :nq] = self._engine.eval("end_effector_jacobian", x, u)[0].reshape(3, nq)
+        e = r - tgt
+        f = 0.5 * Q @ (x - xd) ** 2 + 0.5 * Rw @ u ** 2 + 0.5 * W @ e ** 2
+        return _Approximation(f=float(f), dfdx=Q * (x - xd) + J.T @ (W * e), dfdu=Rw * u,
+                              dfdxx=np.diag(Q) + J.T @ (W[:, None] * J), dfdux=np.zeros((nu, nx)), dfduu=np.diag(Rw))
 
     def getStateInputEqualityConstraintValue(self, name, t, x, u):
         if name != "object_dynamics":
@@ -124,6 +173,38 @@ class ControllerInterface:
         if name == "end_effector_box_constraint":
             tgt = self._core.targets[0].get_desired_state(t)[:3][None]
         return self._engine.eval(name, x, u, target=tgt)[0]
+
+
+class _Approximation:
+    """Attribute bag with the field names of ocs2's Vector / ScalarFunction*Approximation bindings."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class BalancingConstraintWrapper:
+    """`bindings.BalancingConstraintWrapper` (balancing_constraint_wrapper.h:15-66; used by
+    upright_cmd/scripts/misc/balance_at_given_configuration.py:26): getLinearApproximation(t, x, u) -> f, dfdx with the
+    contact-force rows first and the object-dynamics rows behind them (`approx.f << a.f, b.f`); as in the reference
+    only the state Jacobian is carried (`approx(nv, state.size(), 0)`)."""
+
+    def __init__(self, settings, precision="f64"):
+        if not settings.balancing_settings.enabled:
+            raise RuntimeError("Balancing settings not enabled.")
+        self.desc = settings.to_desc()
+        self._engine = BatchedMPC(self.desc, precision)
+
+    def getLinearApproximation(self, t, x, u):
+        e = self._engine
+        nxr, nu = e.nx_robot, e.nu
+        x, u = np.asarray(x, dtype=float), np.asarray(u, dtype=float)
+        a_f = e.eval("contact_forces", x, u)[0] if self.desc.n_fric else np.zeros(0)
+        b_f = e.eval("object_dynamics", x, u)[0]
+        jac = e.eval("object_dynamics_jacobian", x, u)[0].reshape(e.n_eq, nxr + nu)
+        dfdx = np.zeros((a_f.size + b_f.size, e.nx))
+        dfdx[a_f.size:, :nxr] = jac[:, :nxr]
+        return _Approximation(f=np.concatenate((a_f, b_f)), dfdx=dfdx, dfdu=np.zeros((a_f.size + b_f.size, 0)),
+                              dfdu_dynamics=jac[:, nxr:])
 
 
 class _RecedingHorizon:
@@ -346,13 +427,15 @@ class BatchedControllerManager:
     def get_mpc_trajectory(self):
         return self.core.solution()
 
-    def rollout(self, x0, duration, sim_timestep, log_stride=1, log=True):
+    def rollout(self, x0, duration, sim_timestep, log_stride=1, log=True, obstacles=None, obstacle_offsets=None):
         """Closed loop for `duration` seconds entirely on the device (`ub_closed_loop`): the loop of
         `mpc_sim.py:118-160` — `step(t, x)`, `u_cmd = Kx (xd - x) + u`, integrate — for all B robots, with the
-        model's triple integrator as the plant.  The waypoint times must be shared by all targets."""
-        if self.desc.n_dynamic_obstacles > 0:
-            raise ValueError("problems with dynamic obstacles roll out through rollout_host (the obstacle plant and "
-                             "its mode schedule belong to the simulation)")
+        model's triple integrator as the plant.  The waypoint times must be shared by all targets.
+
+        With dynamic obstacles x0 carries their start states behind the robot state and `obstacles` their simulated
+        mode schedules (`simulation.dynamic_obstacles.obstacles[*].modes`, free flight + resets: the device-side
+        counterpart of `plant.BallisticObstacles`); the projectile gate of the ROS node stays a host matter
+        (`rollout_host`)."""
         tr = self.settings.tracking
         tt = self.core.targets[0].ts
         for tg in self.core.targets:
@@ -366,7 +449,8 @@ class BatchedControllerManager:
             x0, tt, pos, n_steps, sim_timestep, self.timestep, body_params=self.core.body_params,
             use_feedback=bool(self.settings.sqp.use_feedback_policy), cold_start=bool(self.settings.mpc.cold_start),
             init_sqp_iteration=self.settings.sqp.init_sqp_iteration, sqp_iteration=self.settings.sqp.sqp_iteration,
-            gains=(getattr(tr, "kp", 0.0), getattr(tr, "kv", 0.0), getattr(tr, "ka", 0.0)), log_stride=log_stride, log=log)
+            gains=(getattr(tr, "kp", 0.0), getattr(tr, "kv", 0.0), getattr(tr, "ka", 0.0)), log_stride=log_stride, log=log,
+            obstacles=obstacles, obstacle_offsets=obstacle_offsets)
 
     def rollout_host(self, x0, duration, sim_timestep, obstacles=None, gate=None, log_stride=1):
         """The loop of `mpc_sim.py:118-160` on the host, one `step(t, x)` per simulation step for all B robots, for
