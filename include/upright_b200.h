@@ -132,7 +132,8 @@ typedef struct ub_problem_desc {
     double gravity[3];
     double state_weight[UB_MAX_NX];  /* diag(Q)  (controller_interface.cpp:400-420) */
     double input_weight[UB_MAX_JOINTS]; /* diag(R) on the jerk                      */
-    double ee_weight[6];             /* diag(W); orientation part must be 0 (round 1) */
+    double ee_weight[6];             /* diag(W) of the end-effector cost: position (3), orientation error (3;
+                                        end_effector_cost.h:61-81, zero in every shipped configuration) */
     double force_weight;             /* balancing.force_weight                   */
     double xd[UB_MAX_NX];            /* desired joint state                      */
 
@@ -241,7 +242,8 @@ int64_t ub_workspace_bytes(const ub_problem_t* problem, int32_t B, uint32_t flag
  *
  *   x0      [B, nx]          observed state per instance
  *   target  [B, N+1, 3]      desired EE position at each knot time
- *                            (interpolate_end_effector_pose, reference_trajectory.h:18-47)
+ *                            (interpolate_end_effector_pose, reference_trajectory.h:18-47); [B, N+1, 7] with the
+ *                            desired quaternion [x y z w] behind it when ee_weight[3..5] != 0
  *   body_params [B, nb, 10]  per-instance inertial parameters or NULL (shared)
  *   X  [B, N+1, nx], U [B, N, nu]  solution (in/out when UB_WARM_START)
  *   K  [B, N, nu, 3 nq] Riccati feedback gains or NULL (over the ROBOT state: the dynamic-obstacle states that

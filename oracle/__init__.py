@@ -55,7 +55,7 @@ def solve_batch(desc, x0, target, body_params=None, X=None, U=None, warm=False, 
     d = dims(desc)
     x0 = _f64(np.atleast_2d(x0))
     Bn = x0.shape[0]
-    target = _f64(np.asarray(target).reshape(Bn, d["N"] + 1, 3))
+    target = _f64(np.asarray(target).reshape(Bn, d["N"] + 1, target_stride(desc)))
     body_params = _f64(body_params)
     if X is None or not warm:
         X = np.zeros((Bn, d["N"] + 1, d["nx"]))
@@ -97,6 +97,20 @@ def linearize(desc, x, u, body_params=None):
     o["Jobs_full"] = o["Jobs"]
     o["Jobs"] = o["Jobs"][:, :nq]
     return o
+
+
+def target_stride(desc):
+    """Columns of a target row: 3 (desired position), or 7 (+ desired quaternion x y z w) when the orientation part
+    of the end-effector weight is non-zero."""
+    return 7 if any(desc.ee_weight[i] != 0 for i in (3, 4, 5)) else 3
+
+
+def orientation_error(desc, x, qref):
+    """End-effector orientation error (ocs2 quaternionDistance of the measured against the desired quaternion
+    [x y z w]) and its Jacobian over q."""
+    e, J = np.zeros(3), np.zeros((3, desc.nq))
+    lib().oracle_orientation_error(C.byref(desc), _p(_f64(x)), _p(_f64(qref)), _p(e), _p(J))
+    return e, J
 
 
 def projectile(desc, x):

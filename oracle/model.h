@@ -219,6 +219,45 @@ void inertial_alignment_constraints(const ub_problem_desc_t& P, const Kinematics
 }
 
 // Sphere-sphere distances minus the minimum distance, h >= 0.  Closed form of
+// Orientation error of the end effector (end_effector_cost.h:61-67 -> ocs2 PinocchioEndEffectorKinematics::
+// getOrientationError -> ocs2::quaternionDistance [EXT: restated from upstream ocs2_robotic_tools
+// RotationTransforms.h]): with q the measured and r the desired quaternion,
+//     e = q_w r_v - r_w q_v + q_v x r_v        (the vector part of r * q^-1),
+// q from the rotation matrix by Eigen's matrix -> quaternion conversion (the branch on the trace decides the sign of
+// q, and with it of e, exactly as Eigen::Quaternion(R) does); target quaternions are stored [x, y, z, w]
+// (reference_trajectory.h:14-16: Quatd(target.segment<4>(3)) reads Eigen's coefficient order).
+template <typename S>
+void matrix_to_quaternion(const Mat3<S>& R, S q[4]) {   // q = [x, y, z, w]
+    const S tr = R.m[0][0] + R.m[1][1] + R.m[2][2];
+    if (value(tr) > 0.0) {
+        S t = sqrt(tr + S(1.0));
+        q[3] = S(0.5) * t;
+        t = S(0.5) / t;
+        q[0] = (R.m[2][1] - R.m[1][2]) * t;
+        q[1] = (R.m[0][2] - R.m[2][0]) * t;
+        q[2] = (R.m[1][0] - R.m[0][1]) * t;
+    } else {
+        int i = 0;
+        if (value(R.m[1][1]) > value(R.m[0][0])) i = 1;
+        if (value(R.m[2][2]) > value(R.m[i][i])) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        S t = sqrt(R.m[i][i] - R.m[j][j] - R.m[k][k] + S(1.0));
+        q[i] = S(0.5) * t;
+        t = S(0.5) / t;
+        q[3] = (R.m[k][j] - R.m[j][k]) * t;
+        q[j] = (R.m[j][i] + R.m[i][j]) * t;
+        q[k] = (R.m[k][i] + R.m[i][k]) * t;
+    }
+}
+template <typename S>
+Vec3<S> orientation_error(const Mat3<S>& C_we, const double* qref /* x y z w */) {
+    S q[4];
+    matrix_to_quaternion(C_we, q);
+    const Vec3<S> qv{q[0], q[1], q[2]};
+    const Vec3<S> rv{S(qref[0]), S(qref[1]), S(qref[2])};
+    return q[3] * rv - S(qref[3]) * qv + cross(qv, rv);
+}
+
 // ocs2::SelfCollisionConstraintCppAd + hpp-fcl for sphere pairs
 // (upright_control/src/controller_interface.cpp:450-481).
 // The `ground` object of the reference is a half-space (add_ground_plane, controller_interface.cpp:93-101:

@@ -120,6 +120,8 @@ struct KnotLin {
     Mat Ffric;                  // d hfric / d f (nfric x nfc)
     std::vector<double> hobs;   // obstacle rows value, nobs
     Mat Jobs;                   // d hobs / d q (nobs x nq)
+    double eo[3] = {0, 0, 0};   // end-effector orientation error (quaternion distance to the target)
+    Mat Jo;                     // d eo / d q (3 x nq)
     double ea[2] = {0, 0};      // inertial-alignment residual
     Mat Jea;                    // d ea / d x (2 x nx)
     double hia[5] = {0, 0, 0, 0, 0};  // inertial-alignment constraint rows
@@ -128,8 +130,15 @@ struct KnotLin {
     Mat Jproj;                  // d hproj / d x (nproj x nx): robot q block and the last obstacle's nine states
 };
 
+static inline bool orientation_weighted(const ub_problem_desc_t& P) {
+    return P.ee_weight[3] != 0.0 || P.ee_weight[4] != 0.0 || P.ee_weight[5] != 0.0;
+}
+// columns of a target row: desired position, and the desired quaternion [x y z w] behind it when the orientation
+// part of the end-effector weight is non-zero (wrappers.py:36-42: target states are [r, quat, s])
+static inline int target_stride(const ub_problem_desc_t& P) { return orientation_weighted(P) ? 7 : 3; }
+
 static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const double* body_params, const double* x,
-                           const double* u, KnotLin& L) {
+                           const double* u, KnotLin& L, const double* qref = nullptr) {
     const int nq = D.nq, nx = D.nx, nxr = D.nxr;
     std::vector<Dual> xd(nx);
     for (int i = 0; i < nx; ++i) xd[i] = i < nxr ? Dual::variable(x[i], i) : Dual(x[i]);  // AD over the robot state
@@ -138,6 +147,14 @@ static void linearize_knot(const ub_problem_desc_t& P, const Dims& D, const doub
     for (int i = 0; i < 3; ++i) {
         L.r[i] = K.r[i].v;
         for (int j = 0; j < nq; ++j) L.Jp(i, j) = K.r[i].d[j];
+    }
+    L.Jo = Mat(3, nq);
+    if (qref != nullptr) {   // end_effector_cost.h:61-67
+        const Vec3<Dual> eo = orientation_error<Dual>(K.C_we, qref);
+        for (int i = 0; i < 3; ++i) {
+            L.eo[i] = eo[i].v;
+            for (int j = 0; j < nq; ++j) L.Jo(i, j) = eo[i].d[j];
+        }
     }
     L.g.assign(D.neq, 0.0);
     L.C = Mat(D.neq, nx);
@@ -302,7 +319,7 @@ static Perf performance(const ub_problem_desc_t& P, const Dims& D, const Mat& A,
     for (int k = 0; k <= N; ++k) {
         const double* x = X + size_t(k) * nx;
         const Kinematics<double> K = forward_kinematics<double>(P, x);
-        const double* rd = target + 3 * k;
+        const double* rd = target + target_stride(P) * k;
         if (k == N) {
             for (int i = 0; i < 3; ++i) {
                 const double e = rd[i] - K.r[i];
@@ -327,6 +344,10 @@ static Perf performance(const ub_problem_desc_t& P, const Dims& D, const Mat& A,
         for (int i = 0; i < nq; ++i) c += 0.5 * P.input_weight[i] * sq(u[i]);
         for (int i = 0; i < D.nfc; ++i) c += 0.5 * P.force_weight * sq(u[nq + i]);
         for (int i = 0; i < 3; ++i) c += 0.5 * P.ee_weight[i] * sq(K.r[i] - rd[i]);
+        if (orientation_weighted(P)) {
+            const Vec3<double> eo = orientation_error<double>(K.C_we, rd + 3);
+            for (int i = 0; i < 3; ++i) c += 0.5 * P.ee_weight[3 + i] * sq(eo[i]);
+        }
         if (P.ia_cost_enabled) {   // inertial_alignment.cpp:118-124
             double e[2];
             inertial_alignment_error<double>(P, K, e);
@@ -424,7 +445,8 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
         const double* x = X + size_t(k) * nx;
         const double* u = (k < N) ? U + size_t(k) * nu : zero_u.data();
         KnotLin& L = W.lin[k];
-        linearize_knot(P, D, body_params, x, u, L);
+        const int ts = target_stride(P);
+        linearize_knot(P, D, body_params, x, u, L, ts == 7 ? target + ts * k + 3 : nullptr);
         if (const char* ne = std::getenv("ORACLE_LIN_NOISE")) {
             // precision study only (tools/precision_lab2.py): perturb every block of the linearisation by noise x its
             // largest magnitude — the size of the error an fp32 forward-kinematics pass leaves in it
@@ -452,7 +474,7 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
         const int xo = s.nu;  // offset of dx in z
         s.H = Mat(s.nz, s.nz);
         s.g.assign(s.nz, 0.0);
-        const double* rd = target + 3 * k;
+        const double* rd = target + ts * k;
         if (k < N) {
             // cost: dt * (1/2 (x-xd)'Q(x-xd) + 1/2 u'R u + 1/2 e'W e), Gauss-Newton in e
             // (end_effector_cost.h:48-84)
@@ -474,6 +496,13 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
                     s.g[xo + a] += w * (L.r[c] - rd[c]);
                     for (int b = 0; b < nq; ++b) s.H(xo + a, xo + b) += w * L.Jp(c, b);
                 }
+            if (ts == 7)   // orientation part of e (end_effector_cost.h:72-81)
+                for (int a = 0; a < nq; ++a)
+                    for (int c = 0; c < 3; ++c) {
+                        const double w = dt * P.ee_weight[3 + c] * L.Jo(c, a);
+                        s.g[xo + a] += w * L.eo[c];
+                        for (int b = 0; b < nq; ++b) s.H(xo + a, xo + b) += w * L.Jo(c, b);
+                    }
             // inertial-alignment cost, Gauss-Newton (inertial_alignment.cpp:126-149)
             if (P.ia_cost_enabled)
                 for (int a = 0; a < nx; ++a)
@@ -554,8 +583,8 @@ static void build_qp(const ub_problem_desc_t& P, Workspace& W, const double* bod
                         r.a.assign(s.nz, 0.0);
                         const double sg = side == 0 ? -1.0 : 1.0;
                         for (int j = 0; j < nq; ++j) r.a[xo + j] = sg * L.Jp(c, j);
-                        r.c = side == 0 ? target[3 * k + c] + P.ee_box_upper[c] - L.r[c]
-                                        : L.r[c] - target[3 * k + c] - P.ee_box_lower[c];
+                        r.c = side == 0 ? rd[c] + P.ee_box_upper[c] - L.r[c]
+                                        : L.r[c] - rd[c] - P.ee_box_lower[c];
                         r.lb = 0.0;
                         finish(r, soft_poly);
                         s.rows.push_back(r);
@@ -1768,7 +1797,7 @@ int oracle_solve_batch(const ub_problem_desc_t* P, int32_t B, const double* x0, 
             const int b = next.fetch_add(1);
             if (b >= B) return;
             const double* bp = body_params ? body_params + size_t(b) * P->nb * UB_BODY_PARAMS : &P->body_params[0][0];
-            orc::solve_one(*P, x0 + size_t(b) * D.nx, target + size_t(b) * (D.N + 1) * 3, bp,
+            orc::solve_one(*P, x0 + size_t(b) * D.nx, target + size_t(b) * (D.N + 1) * orc::target_stride(*P), bp,
                            (flags & UB_WARM_START) != 0, X + b * nxs, U + b * nus,
                            K ? K + size_t(b) * D.N * D.nu * D.nx : nullptr, status + b,
                            stats ? stats + size_t(b) * UB_STATS : nullptr);
@@ -1819,6 +1848,19 @@ int oracle_linearize(const ub_problem_desc_t* P, const double* x, const double* 
 }
 
 // Projectile-path rows of one knot: h[nproj], J[nproj*nx], tclose[nproj] (any may be NULL); returns nproj
+// End-effector orientation error against the target quaternion qref [x y z w] and its Jacobian over q (3 x nq).
+int oracle_orientation_error(const ub_problem_desc_t* P, const double* x, const double* qref, double* e, double* J) {
+    const orc::Dims D = orc::make_dims(*P);
+    orc::KnotLin L;
+    std::vector<double> u(D.nu, 0.0);
+    orc::linearize_knot(*P, D, &P->body_params[0][0], x, u.data(), L, qref);
+    for (int i = 0; i < 3; ++i) {
+        e[i] = L.eo[i];
+        for (int j = 0; j < D.nq; ++j) J[i * D.nq + j] = L.Jo(i, j);
+    }
+    return 0;
+}
+
 int oracle_projectile(const ub_problem_desc_t* P, const double* x, double* h, double* J, double* tclose) {
     const orc::Dims D = orc::make_dims(*P);
     if (D.nproj == 0) return 0;

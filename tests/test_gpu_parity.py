@@ -71,10 +71,22 @@ def test_probes_match_oracle(name):
         assert np.allclose(g[m], lin["g"], atol=1e-11)
     if desc.n_fric:
         h = mpc.eval("contact_forces", x, u)
-        assert np.allclose(h[0], oracle.linearize(desc, x[0], u[0])["hfric"], atol=1e-12)
+        for m in range(M):
+            assert np.allclose(h[m], oracle.linearize(desc, x[m], u[m])["hfric"], atol=1e-12)
     if desc.n_obs:
         h = mpc.eval("obstacle_avoidance", x, u)
-        assert np.allclose(h[3], oracle.linearize(desc, x[3], u[3])["hobs"], atol=1e-12)
+        for m in range(M):
+            assert np.allclose(h[m], oracle.linearize(desc, x[m], u[m])["hobs"], atol=1e-12)
+    # Jacobian probes (what the reference's CppAD tapes return): object dynamics [dg/dx | dg/du], tool position dr/dq
+    J = mpc.eval("end_effector_jacobian", x, u).reshape(M, 3, desc.nq)
+    for m in range(M):
+        assert np.allclose(J[m], oracle.linearize(desc, x[m], u[m])["Jp"], atol=1e-12)
+    if mpc.n_eq:
+        G = mpc.eval("object_dynamics_jacobian", x, u).reshape(M, mpc.n_eq, desc.nx + desc.nu)
+        for m in range(0, M, 5):
+            lin = oracle.linearize(desc, x[m], u[m])
+            assert np.allclose(G[m][:, :desc.nx], lin["C"], atol=1e-10)
+            assert np.allclose(G[m][:, desc.nx + desc.nq:], lin["Df"], atol=1e-12) and np.all(G[m][:, desc.nx:desc.nx + desc.nq] == 0)
 
 
 @pytest.mark.parametrize("name", CFGS)
@@ -724,6 +736,46 @@ def test_device_closed_loop_with_dynamic_obstacle_matches_host_rollout(prec):
     far = BatchedControllerManager(st, targets, timestep=0.05, precision=prec)
     keep = far.rollout(x0_full, duration, sim_dt, obstacles=[sim["modes"][:1]])
     assert np.abs(keep["x_final"][:, :27] - out["x_final"][:, :27]).max() > 1e-4
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_end_effector_orientation_cost_matches_oracle(prec):
+    """EndEffectorCost with a non-zero orientation weight (end_effector_cost.h:48-84: e = [r - r_d; quaternion
+    distance], Gauss-Newton Hessian): kernels against the oracle on 7-column targets (position + desired quaternion),
+    balancing on (soft rows), desired orientations tilted and turned away from the start."""
+    import copy
+    from upright_b200 import geometry as geo
+    d0, meta = problem_io.load_fixture("cfg2_thing_demo")
+    d = copy.deepcopy(d0)
+    d.ee_weight[3], d.ee_weight[4], d.ee_weight[5] = 1.0, 2.0, 0.5
+    b = batch_for("cfg2_thing_demo", 8, 23)
+    mpc = BatchedMPC(d, prec)
+    assert mpc.target_stride == 7
+    rng = np.random.default_rng(9)
+    tg = np.empty((8, d.N + 1, 7))
+    for i in range(8):
+        k = oracle.fk(d, b["x0"][i])
+        q0 = geo.rot_to_quat(np.array(k["C"]).reshape(3, 3))
+        ax = rng.standard_normal(3)
+        ax /= np.linalg.norm(ax)
+        ang = rng.uniform(0.1, 0.5)
+        qd = geo.quat_multiply(np.r_[np.sin(ang / 2) * ax, np.cos(ang / 2)], q0)
+        tg[i, :, :3] = b["target"][i]
+        tg[i, :, 3:] = qd
+    ref = oracle.solve_batch(d, b["x0"], tg, b["body_params"])
+    out = mpc.solve(b["x0"], tg, b["body_params"])
+    plain = oracle.solve_batch(d0, b["x0"], b["target"], b["body_params"])
+    assert (ref["status"] == 0).all() and (out["status"] == ref["status"]).all()
+    assert np.abs(ref["X"] - plain["X"]).max() > 1e-2                    # the orientation term acts
+    rx, ru = ranges(d)
+    ex = (np.abs(out["X"] - ref["X"]) / rx).max()
+    eu = (np.abs(out["U"] - ref["U"]) / ru).max()
+    print(f"orientation cost {prec}: scaled error X {ex:.2e} U {eu:.2e}")
+    if prec == "f64":
+        assert (out["stats"][:, 0] == ref["stats"][:, 0]).all() and np.abs(out["X"] - ref["X"]).max() < 1e-7
+        assert np.abs(out["stats"][:, 1] - ref["stats"][:, 1]).max() < 1e-8   # cost incl. the orientation term
+    else:
+        assert ex < 1e-3 and eu < 1e-3
 
 
 def _ground_desc():

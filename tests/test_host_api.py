@@ -69,13 +69,30 @@ def test_settings_surface_thing_demo():
     assert s.tracking.min_policy_update_time == 0.01
 
 
-def test_orientation_weight_is_rejected_loudly():
-    d, _ = problem_io.load_fixture("cfg2_thing_demo")
+def test_orientation_weight_reaches_the_description():
+    """A non-zero orientation weight (end_effector_cost.h:61-81; zero in every shipped configuration) is carried into
+    the problem description, and targets then hold the desired quaternion behind the position."""
     if REF.exists():
         cfg = config.load_config(REF / "upright_cmd/config/demos/thing_demo.yaml")["controller"]
-        cfg["weights"]["end_effector"]["diag"] = [1, 1, 1, 1, 0, 0]
-        with pytest.raises(NotImplementedError):
-            settings.ControllerSettings(cfg).to_desc()
+        cfg["weights"]["end_effector"]["diag"] = [1, 1, 1, 0.5, 0.25, 0]
+        d = settings.ControllerSettings(cfg).to_desc()
+        assert list(d.ee_weight) == [1, 1, 1, 0.5, 0.25, 0]
+
+
+def test_pose_targets_slerp_like_eigen():
+    """interpolate_end_effector_pose (reference_trajectory.h:18-47): position linear, orientation
+    q_lhs.slerp(1 - alpha, q_rhs); single waypoint constant; antipodal quaternions take the shortest arc."""
+    from upright_b200 import geometry as geo
+    from upright_b200.settings import quat_slerp
+    q0 = np.array([0.0, 0.0, 0.0, 1.0])
+    q1 = geo.rot_to_quat(geo.rotz(1.0))
+    tt = TargetTrajectories([0.0, 2.0], [np.r_[0, 0, 0, q0, 0], np.r_[2, 0, 0, q1, 0]], [np.zeros(3)] * 2)
+    p = tt.poses_at([-1.0, 0.0, 0.5, 2.0, 3.0])
+    assert np.allclose(p[0], np.r_[0, 0, 0, q0]) and np.allclose(p[4], np.r_[2, 0, 0, q1])
+    assert np.allclose(p[2][:3], [0.5, 0, 0]) and np.allclose(p[2][3:], geo.rot_to_quat(geo.rotz(0.25)), atol=1e-12)
+    assert np.allclose(quat_slerp(q0, -q1, 0.5), -geo.rot_to_quat(geo.rotz(0.5)) * np.sign(1.0), atol=1e-12) or \
+        np.allclose(quat_slerp(q0, -q1, 0.5), geo.rot_to_quat(geo.rotz(0.5)), atol=1e-12)
+    assert np.allclose(quat_slerp(q0, q0, 0.3), q0)
 
 
 def test_target_trajectories_interpolation():

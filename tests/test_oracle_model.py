@@ -176,3 +176,48 @@ def test_ground_half_space_row_in_the_oracle(oracle_lib):
         J[j] = (oracle.linearize(d, x + e, np.zeros(nu))["hobs"][-1] - oracle.linearize(d, x - e, np.zeros(nu))["hobs"][-1]) / 2e-6
     assert np.allclose(lin["Jobs"][-1], J, atol=1e-7)
     assert np.allclose(lin["hobs"][:-1], oracle.linearize(d0, x, np.zeros(nu))["hobs"], atol=1e-14)   # other rows untouched
+
+
+def test_end_effector_orientation_error(oracle_lib):
+    """ocs2 quaternionDistance of the measured against the desired quaternion (end_effector_cost.h:61-67 [EXT]):
+    zero at the target, sin(angle / 2) * axis for a desired orientation rotated by (axis, angle) in the world frame,
+    Jacobian = central differences; and the cost acts in a solve (7-column targets)."""
+    import copy
+    from upright_b200 import geometry as geo
+    oracle = oracle_lib
+    d0, meta = problem_io.load_fixture("cfg2_thing_demo")
+    d = copy.deepcopy(d0)
+    d.ee_weight[3] = d.ee_weight[4] = d.ee_weight[5] = 2.0
+    assert oracle.target_stride(d0) == 3 and oracle.target_stride(d) == 7
+    rng = np.random.default_rng(0)
+    x = np.array(meta["x0"], dtype=float)
+    x[:9] += 0.3 * rng.standard_normal(9)
+    k = oracle.fk(d, x)
+    q = geo.rot_to_quat(np.array(k["C"]).reshape(3, 3))
+    assert np.abs(oracle.orientation_error(d, x, q)[0]).max() < 1e-15
+    ang, ax = 0.2, np.array([0.3, -0.5, 0.8]) / np.linalg.norm([0.3, -0.5, 0.8])
+    qref = geo.quat_multiply(np.r_[np.sin(ang / 2) * ax, np.cos(ang / 2)], q)
+    e, J = oracle.orientation_error(d, x, qref)
+    assert np.allclose(e, np.sin(ang / 2) * ax, atol=1e-12)
+    Jn = np.zeros((3, 9))
+    for j in range(9):
+        dx = np.zeros(27)
+        dx[j] = 1e-6
+        Jn[:, j] = (oracle.orientation_error(d, x + dx, qref)[0] - oracle.orientation_error(d, x - dx, qref)[0]) / 2e-6
+    assert np.allclose(J, Jn, atol=1e-8)
+    # solves: the weighted problem turns the tray towards the desired orientation, the unweighted one does not care
+    # (balancing off: with it the tilt is dictated by the object)
+    for dd in (d, d0):
+        dd.balancing_enabled = 0
+    N = d.N
+    x0 = np.array(meta["x0"], dtype=float)
+    k0 = oracle.fk(d, x0)
+    q0 = geo.rot_to_quat(np.array(k0["C"]).reshape(3, 3))
+    qd = geo.quat_multiply(np.r_[0, 0, np.sin(0.15), np.cos(0.15)], q0)          # 0.3 rad about the world z axis
+    tg7 = np.tile(np.r_[k0["r"], qd], (1, N + 1, 1))
+    out = oracle.solve_batch(d, x0[None], tg7)
+    ref = oracle.solve_batch(d0, x0[None], tg7[:, :, :3])
+    assert out["status"][0] == 0 and ref["status"][0] == 0
+    e_w = np.linalg.norm(oracle.orientation_error(d, out["X"][0, -1], qd)[0])
+    e_0 = np.linalg.norm(oracle.orientation_error(d, ref["X"][0, -1], qd)[0])
+    assert e_0 == pytest.approx(np.sin(0.15), abs=1e-6) and e_w < 0.5 * e_0

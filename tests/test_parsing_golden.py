@@ -210,3 +210,47 @@ def test_fixture_contacts_match_reference_outputs():
             assert np.allclose(list(c.r_co_o1), gc["r_co_o1"], atol=1e-12)
             assert np.allclose(list(c.r_co_o2), gc["r_co_o2"], atol=1e-12)
             assert np.allclose(list(c.span), np.array(gc["span"]).ravel(), atol=1e-12)
+
+
+def _polyhedron_cases():
+    """The contact cases of upright_core/tests/test_polyhedron.py:182-243, built with this repo's geometry."""
+    P = geo.ConvexPolyhedron
+    box1 = P.box([1, 1, 1])
+    box2 = P.box([0.5, 0.5, 0.5]).transform(translation=[0.5, 0.5, 1.5])
+    n = np.array([1.0, 0, 1.0]) / np.sqrt(2.0)
+    thin = P.box([0.03, 0.03, 0.3]).transform(rotation=geo.rotz(np.pi / 4))
+    dx = thin.distance_from_centroid_to_boundary(np.array([1.0, 0, 0]))
+    return {
+        "test_box_box_contact": (box1, box2),
+        "test_box_box_contact/penetrating": (box1, box2.transform(translation=[0, 0, -0.1])),
+        "test_box_box_contact/separated": (box1, box2.transform(translation=[0, 0, 0.1])),
+        "test_wedge_box_contact": (P.wedge([1, 1, 1]), P.box([1, 1, 1]).transform(rotation=geo.roty(-np.pi / 4), translation=n)),
+        "test_line_contact": (thin, P.box([0.1, 0.1, 0.1]).transform(translation=[dx + 0.1, 0, 0])),
+        "box_box_offset": (P.box([0.5, 0.5, 0.5]), P.box([0.5, 0.5, 0.5]).transform(translation=[0.5, 0.5, 1.0])),
+    }, dx
+
+
+def test_polyhedron_contact_manifolds_against_the_reference():
+    """Contact points and normals of every case of the reference's own polyhedron tests: the golden file holds what
+    `upright_core.polyhedron.axis_aligned_contact` itself returns for them (tools/gen_golden.py), and the known
+    answers written in test_polyhedron.py:182-243 are asserted on top."""
+    gold = json.loads((GOLD / "contacts_polyhedron.json").read_text())
+    cases, dx = _polyhedron_cases()
+    for name, (a, b) in cases.items():
+        V, n = geo.axis_aligned_contact(a, b)
+        want = gold[name]
+        if want is None:
+            assert V is None and n is None, name
+            continue
+        assert V is not None, name
+        assert np.allclose(n, want["normal"], atol=1e-12), name
+        assert unordered_close(V, want["points"]), name
+    assert gold["test_line_contact"]["dx"] == pytest.approx(dx, abs=1e-12)
+    # the answers the reference's tests state
+    V, n = geo.axis_aligned_contact(*cases["test_box_box_contact"])
+    assert np.allclose(n, [0, 0, -1]) and unordered_close(V, [[0, 0, 1], [0, 1, 1], [1, 1, 1], [1, 0, 1]])
+    V, n = geo.axis_aligned_contact(*cases["test_wedge_box_contact"])
+    a = np.sqrt(2) / 2
+    assert np.allclose(n, -np.array([a, 0, a])) and unordered_close(V, [[-a, 1, a], [-a, -1, a], [a, -1, -a], [a, 1, -a]])
+    V, n = geo.axis_aligned_contact(*cases["test_line_contact"])
+    assert np.allclose(n, [-1, 0, 0]) and unordered_close(V, [[dx, 0, -0.1], [dx, 0, 0.1]])

@@ -154,6 +154,23 @@ def main():
     b3 = b3.transform(translation=-b3.max_vertex_along_axis(np.array([-1.0, 0, -1.0])) * 0 + np.array([0.25 * np.sqrt(2), 0, 0.25 * np.sqrt(2)]))
     V, n = polyhedron.axis_aligned_contact(w, b3)
     cases["wedge_box_slope"] = None if V is None else {"points": V.tolist(), "normal": n.tolist()}
+    # the cases of upright_core/tests/test_polyhedron.py:182-243, as written there
+    def record(name, a, b):
+        V, n = polyhedron.axis_aligned_contact(a, b)
+        cases[name] = None if V is None else {"points": np.asarray(V).tolist(), "normal": np.asarray(n).tolist()}
+
+    roty, rotz = sys.modules["spatialmath.base"].roty, sys.modules["spatialmath.base"].rotz
+    box1 = P.box([1, 1, 1])
+    box2 = P.box([0.5, 0.5, 0.5]).transform(translation=[0.5, 0.5, 1.5])
+    record("test_box_box_contact", box1, box2)
+    record("test_box_box_contact/penetrating", box1, box2.transform(translation=[0, 0, -0.1]))
+    record("test_box_box_contact/separated", box1, box2.transform(translation=[0, 0, 0.1]))
+    nrm = np.array([1.0, 0, 1.0]) / np.sqrt(2.0)
+    record("test_wedge_box_contact", P.wedge([1, 1, 1]), P.box([1, 1, 1]).transform(rotation=roty(-np.pi / 4), translation=nrm))
+    thin = P.box([0.03, 0.03, 0.3]).transform(rotation=rotz(np.pi / 4))
+    dx = thin.distance_from_centroid_to_boundary([1, 0, 0])
+    record("test_line_contact", thin, P.box([0.1, 0.1, 0.1]).transform(translation=[dx + 0.1, 0, 0]))
+    cases["test_line_contact"]["dx"] = float(dx)
     with open(OUT / "contacts_polyhedron.json", "w") as f:
         json.dump(cases, f, indent=1)
     print("golden files written to", OUT)

@@ -247,6 +247,8 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
         P.xub[i] = T(d.state_ub[i]);
     }
     P.fw = T(d.force_weight);
+    P.ori = (d.ee_weight[3] != 0 || d.ee_weight[4] != 0 || d.ee_weight[5] != 0) ? 1 : 0;
+    for (int j = 0; j < 3; ++j) P.Wo[j] = T(d.ee_weight[3 + j]);
     P.flb = T(d.force_lb);
     P.fub = T(d.force_ub);
     for (int b = 0; b < d.nb; ++b)
@@ -304,7 +306,7 @@ void convert_problem(const ub_problem_desc_t& d, ub::DevProblem<T>& P) {
 template <typename T>
 ub::Layout make_layout(const ub::DevProblem<T>& P) {
     return ub::compute_layout(ub::LayoutDims{P.N, P.nq, P.nx, P.nu, P.neq, P.nfc, P.nterm, P.nrow, P.nobs, P.nb, P.nc, P.nf,
-                                             int(sizeof(double) / sizeof(T)), P.ngrp, P.ng, P.iacost ? 2 : 0, P.obsw, P.nxo});
+                                             int(sizeof(double) / sizeof(T)), P.ngrp, P.ng, P.ori, P.iacost ? 2 : 0, P.obsw, P.nxo});
 }
 
 }  // namespace
@@ -377,7 +379,7 @@ ub::LaunchFn<T> select_kernel(const ub_problem* p) {
     const ub::DevProblem<T>& H = Pick<T>::host(p);
     ub::LaunchFn<T> fn = H.nq == 9 ? Pick<T>::generic9() : Pick<T>::generic6();
     if (std::getenv("UB_FORCE_GENERIC") != nullptr) return fn;
-    if (!(H.balancing && H.N == 20 && !H.iacost && !H.iacon && H.ndyn == 0 && !H.eebox && H.nproj == 0)) return fn;
+    if (!(H.balancing && H.N == 20 && !H.iacost && !H.iacon && H.ndyn == 0 && !H.eebox && H.nproj == 0 && !H.ori)) return fn;
     const bool no_obs = H.nobs == 0, per_body = H.ngrp == H.nb;
     if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && no_obs) fn = Pick<T>::thing_1obj();
     if (H.nq == 9 && H.nf == 1 && H.nc == 4 && H.nb == 1 && H.nobs == 12) fn = Pick<T>::thing_obs12();
@@ -474,6 +476,7 @@ int solve_device(ub_problem* p, int B, const void* x0, const void* target, const
     A.stop_after = p->stop_after;
     A.gain_stages = gain_stages < 0 ? Pick<T>::host(p).N : gain_stages;
     A.nxt = Pick<T>::host(p).nx + Pick<T>::host(p).nxo;
+    A.tstride = Pick<T>::host(p).ori ? 7 : 3;
     A.ngather = gather ? p->n_gather : 0;   // the caller's device-mode solves only (not the host path, not the closed loop)
     A.gather_row = p->gather_row;
     for (int i = 0; i < UB_MAX_GATHER; ++i) {
@@ -494,7 +497,7 @@ int solve_host(ub_problem* p, int B, const double* x0, const double* target, con
     const ub::DevProblem<T>& P = Pick<T>::host(p);
     const ub::Layout& L = Pick<T>::layout(p);
     const size_t nxt = size_t(P.nx + P.nxo);   // robot state + dynamic-obstacle states
-    const size_t n_x0 = size_t(B) * nxt, n_tg = size_t(B) * (P.N + 1) * 3, n_bd = body ? size_t(B) * P.nb * UB_BODY_PARAMS : 0;
+    const size_t n_x0 = size_t(B) * nxt, n_tg = size_t(B) * (P.N + 1) * (P.ori ? 7 : 3), n_bd = body ? size_t(B) * P.nb * UB_BODY_PARAMS : 0;
     const size_t n_X = size_t(B) * (P.N + 1) * nxt, n_U = size_t(B) * P.N * P.nu;
     const size_t n_K = K ? size_t(B) * P.N * P.nu * P.nx : 0, n_st = size_t(B) * UB_STATS;
     const size_t n_ws = size_t(workspace_bytes<T>(p, B)) / sizeof(T);
@@ -894,8 +897,6 @@ int ub_problem_create(const ub_problem_desc_t* desc, ub_problem_t** out) {
         for (int c = 0; c < 3; ++c)
             if (!(desc->ee_box_lower[c] < desc->ee_box_upper[c]))
                 return fail(UB_E_INVALID, "end-effector box: xyz_lower must be below xyz_upper");
-    if (desc->ee_weight[3] != 0 || desc->ee_weight[4] != 0 || desc->ee_weight[5] != 0)
-        return fail(UB_E_INVALID, "end-effector orientation weight is not supported yet");
     if (desc->qp_method != 0) return fail(UB_E_INVALID, "only qp_method 0 (interior point) exists on the device");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -1027,6 +1028,24 @@ int ub_set_gather_targets(ub_problem_t* p, int32_t n, void* const* X_bases, void
     if (row_offset < 0) return fail(UB_E_INVALID, "negative row offset");
     for (int i = 0; i < n; ++i)
         if (!X_bases[i] || !U_bases[i]) return fail(UB_E_INVALID, "null gather target");
+    // the solve kernel of THIS device stores into memory of the peers: peer access must be on (a handle opened by
+    // another library, e.g. torch's IPC rebuild, maps the memory but does not enable it)
+    UB_CUDA(cudaSetDevice(p->device));
+    for (int i = 0; i < n; ++i) {
+        for (const void* ptr : {X_bases[i], U_bases[i]}) {
+            cudaPointerAttributes at{};
+            if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess || at.type != cudaMemoryTypeDevice)
+                return fail(UB_E_INVALID, "gather target is not device memory known to this process");
+            if (at.device == p->device) continue;
+            int can = 0;
+            UB_CUDA(cudaDeviceCanAccessPeer(&can, p->device, at.device));
+            if (!can) return fail(UB_E_INVALID, "no peer access to the device of a gather target");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(UB_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+            cudaGetLastError();   // clear the sticky "already enabled"
+        }
+    }
     p->n_gather = n;
     p->gather_row = row_offset;
     for (int i = 0; i < n; ++i) {
@@ -1074,6 +1093,7 @@ int ub_closed_loop(ub_problem_t* p, int32_t B, const double* x0, const double* t
                    double* x_final, int32_t* n_replans, int32_t* status_counts, uint32_t flags, void* cuda_stream) {
     if (!p || !x0 || !target_times || !target_pos || !params) return fail(UB_E_INVALID, "null argument");
     if (B <= 0 || M <= 0) return fail(UB_E_INVALID, "B and M must be positive");
+    if (p->hf.ori) return fail(UB_E_INVALID, "ub_closed_loop interpolates positions only: orientation-weighted problems go through ub_solve_batch");
     if (!(params->sim_dt > 0) || !(params->replan_period > 0) || params->n_steps <= 0)
         return fail(UB_E_INVALID, "sim_dt, replan_period and n_steps must be positive");
     if ((xs == nullptr) != (us == nullptr)) return fail(UB_E_INVALID, "xs and us are logged together");

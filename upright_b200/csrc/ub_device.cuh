@@ -28,6 +28,10 @@ struct DevProblem {
     T jR[UB_MAX_JOINTS][9], jp[UB_MAX_JOINTS][3], jaxis[UB_MAX_JOINTS][3];
     T toolR[9], toolp[3], grav[3];
     T Qd[UB_MAX_NX], Rd[UB_MAX_JOINTS], Wd[3], fw, xd[UB_MAX_NX];
+    // orientation part of the end-effector weight (end_effector_cost.h:61-81); ori != 0: targets carry the desired
+    // quaternion [x y z w] behind the position (7 columns)
+    int ori;
+    T Wo[3];
     T xlb[UB_MAX_NX], xub[UB_MAX_NX], ulb[UB_MAX_JOINTS], uub[UB_MAX_JOINTS], flb, fub;
     T body[UB_MAX_BODIES][UB_BODY_PARAMS];
     int cb1[UB_MAX_CONTACTS], cb2[UB_MAX_CONTACTS];
@@ -165,6 +169,51 @@ __device__ __forceinline__ M3<T> matmul(const M3<T>& A, const T* B) {
         for (int j = 0; j < 3; ++j) C.m[3 * i + j] = A.m[3 * i] * B[j] + A.m[3 * i + 1] * B[3 + j] + A.m[3 * i + 2] * B[6 + j];
     return C;
 }
+// Quaternion [x y z w] of a rotation matrix by Eigen's conversion (the branch on the trace decides its sign), and
+// the end-effector orientation error of ocs2::quaternionDistance against the desired quaternion r:
+//     e = q_w r_v - r_w q_v + q_v x r_v      (end_effector_cost.h:61-67 [EXT: ocs2_robotic_tools])
+// de: its derivative along a world-frame angular tangent dth of the rotation (q' = 1/2 [dth, 0] * q).
+template <typename T>
+__device__ inline void matrix_to_quaternion(const M3<T>& R, T q[4]) {
+    const T tr = R.m[0] + R.m[4] + R.m[8];
+    if (tr > T(0)) {
+        T t = sqrt(tr + T(1));
+        q[3] = T(0.5) * t;
+        t = T(0.5) / t;
+        q[0] = (R.m[7] - R.m[5]) * t;
+        q[1] = (R.m[2] - R.m[6]) * t;
+        q[2] = (R.m[3] - R.m[1]) * t;
+    } else {
+        int i = 0;
+        if (R.m[4] > R.m[0]) i = 1;
+        if (R.m[8] > R.m[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        T t = sqrt(R.m[4 * i] - R.m[4 * j] - R.m[4 * k] + T(1));
+        T qq[3];
+        qq[i] = T(0.5) * t;
+        t = T(0.5) / t;
+        q[3] = (R.m[3 * k + j] - R.m[3 * j + k]) * t;
+        qq[j] = (R.m[3 * j + i] + R.m[3 * i + j]) * t;
+        qq[k] = (R.m[3 * k + i] + R.m[3 * i + k]) * t;
+        q[0] = qq[0];
+        q[1] = qq[1];
+        q[2] = qq[2];
+    }
+}
+template <typename T, bool TANGENT>
+__device__ inline V3<T> orientation_error(const M3<T>& Cwe, const V3<T>& dth, const T* qref, V3<T>* de) {
+    T q[4];
+    matrix_to_quaternion(Cwe, q);
+    const V3<T> qv(q[0], q[1], q[2]), rv(qref[0], qref[1], qref[2]);
+    const T qw = q[3], rw = qref[3];
+    if (TANGENT) {
+        const T dqw = T(-0.5) * dot(dth, qv);
+        const V3<T> dqv = T(0.5) * (qw * dth + cross(dth, qv));
+        *de = dqw * rv - rw * dqv + cross(dqv, rv);
+    }
+    return qw * rv - rw * qv + cross(qv, rv);
+}
+
 template <typename T>
 __device__ __forceinline__ void sincos_t(T a, T* s, T* c);
 template <>

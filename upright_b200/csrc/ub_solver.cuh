@@ -41,6 +41,7 @@ namespace ub {
 struct Layout {
     int Z, DZ, GAP, LG, LC, LR, LJP, LHO, LJO, DF, RHOE, YE, RHOT, YT, TL, DD, GP, VE, FAC, WF, FBB;
     int XN, UN, XW, UW, TG, BD, LIA, LJA, XO, DXO;
+    int TGQ, LRO, LJQ;   // end-effector orientation cost: target quaternions [N+1, 4], error (R) [N+1, 3], Jacobian [N+1, 3, nq]
     int total;
     // force bundle of one stage (workspace FBB + k * bsize, and the same layout in shared memory at sFB):
     // G = L^-1 C [neq][nx] | L^-1 per group (double) | D^-1 per contact (double) | g_lambda (double) | q (double)
@@ -56,6 +57,7 @@ struct LayoutDims {
     int N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, nb, nc, nf;
     int rw;          // sizeof(double) / sizeof(F)
     int ngrp, ng;    // force block: ngrp groups of ng equality rows (per body: nb x 6; bodies sharing contacts: 1 x 6 nb)
+    int ori = 0;     // end-effector orientation cost enabled
     int nia = 0;     // rows of the inertial-alignment cost (0 or 2)
     int obsw = 0;    // width of the obstacle-family rows (0 -> nq)
     int nxo = 0;     // dynamic-obstacle states (9 per obstacle)
@@ -111,6 +113,9 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.LJA = o;  o += ub_round4(N * d.nia * nx);
     L.XO = o;   o += ub_round4((N + 1) * d.nxo);
     L.DXO = o;  o += ub_round4((N + 1) * d.nxo);
+    L.TGQ = o;  o += d.ori ? ub_round4((N + 1) * 4) : 0;
+    L.LRO = o;  o += d.ori ? ub_round4(rw * (N + 1) * 3) : 0;
+    L.LJQ = o;  o += d.ori ? ub_round4((N + 1) * 3 * nq) : 0;
     L.total = o;
     int s = 0;
     // (the stage-matrix buffer doubles as the scratch of the S build when bodies share contacts: D^-1 N' per contact
@@ -167,6 +172,7 @@ struct BatchArgs {
     int* queue;
     int n_slots;      // workspace slots (= warps that may work); B in the static mode
     int nxt;          // columns of x0 / X / Xin: robot state + dynamic-obstacle states
+    int tstride;      // columns of a target row: 3, or 7 with the desired quaternion [x y z w]
     // Multi-GPU gather fused into the solve: besides X / U of this rank, every solved instance is
     // stored straight into the gathered buffers of the peer GPUs (peer-mapped pointers, NVLink P2P stores from the
     // epilogue) at row gather_row + b — the all-gather happens instance by instance while the rest of the batch is
@@ -261,6 +267,8 @@ struct Solver {
     }
     // the inertial-alignment cost likewise (run-time-dimension kernel only)
     __device__ __forceinline__ bool IALIGN() const { if constexpr (D::kStatic) return false; else return P.iacost != 0; }
+    // end-effector orientation cost (run-time-dimension kernel only; zero weight in every shipped configuration)
+    __device__ __forceinline__ bool ORI() const { if constexpr (D::kStatic) return false; else return P.ori != 0; }
     __device__ __forceinline__ int NPAIRS() const { if constexpr (D::kStatic) return D::nobs; else return P.npairs; }
     // workspace / shared-memory offsets: immediates for the specialised kernels
 #define UB_OFF(name) \
@@ -268,7 +276,7 @@ struct Solver {
     UB_OFF(Z) UB_OFF(DZ) UB_OFF(GAP) UB_OFF(LG) UB_OFF(LC) UB_OFF(LR) UB_OFF(LJP) UB_OFF(LHO) UB_OFF(LJO) UB_OFF(DF)
     UB_OFF(RHOE) UB_OFF(YE) UB_OFF(RHOT) UB_OFF(YT) UB_OFF(TL) UB_OFF(DD) UB_OFF(GP) UB_OFF(VE) UB_OFF(FAC) UB_OFF(WF)
     UB_OFF(FBB) UB_OFF(bG) UB_OFF(bL) UB_OFF(bD) UB_OFF(bGl) UB_OFF(bQ) UB_OFF(bsize) UB_OFF(XN) UB_OFF(UN)
-    UB_OFF(XW) UB_OFF(UW) UB_OFF(TG) UB_OFF(BD) UB_OFF(LIA) UB_OFF(LJA) UB_OFF(XO) UB_OFF(DXO)
+    UB_OFF(XW) UB_OFF(UW) UB_OFF(TG) UB_OFF(BD) UB_OFF(LIA) UB_OFF(LJA) UB_OFF(XO) UB_OFF(DXO) UB_OFF(TGQ) UB_OFF(LRO) UB_OFF(LJQ)
 #undef UB_OFF
     __device__ __forceinline__ static constexpr int LDM() { return D::nr | 1; }
     __device__ __forceinline__ int NROW() const { return NBOXU() + NX() + NFRIC() + NOBS(); }
@@ -609,6 +617,24 @@ struct Solver {
                 Jp[nq + lane] = F(Dt.r.y);
                 Jp[2 * nq + lane] = F(Dt.r.z);
             }
+            if (ORI() && k < N) {
+                R qr[4];
+                for (int c = 0; c < 4; ++c) qr[c] = R(ws[oTGQ() + 4 * k + c]);
+                V3<R> de;
+                const V3<R> eo = orientation_error<R, true>(Kn.C, Dt.th, qr, &de);
+                if (lane == 0) {
+                    R* lo = wsr<R>(oLRO()) + 3 * k;
+                    lo[0] = eo.x;
+                    lo[1] = eo.y;
+                    lo[2] = eo.z;
+                }
+                if (lane < nq) {
+                    F* Jq = ws + oLJQ() + k * 3 * nq;
+                    Jq[lane] = F(de.x);
+                    Jq[nq + lane] = F(de.y);
+                    Jq[2 * nq + lane] = F(de.z);
+                }
+            }
             if (k < N && NEQ() > 0) {
                 for (int b = 0; b < NB(); ++b) {
                     const BodyP<R> Bd = load_body<R>(body + b * UB_BODY_PARAMS);
@@ -792,6 +818,10 @@ struct Solver {
                 F e2[2];
                 inertial_alignment_error<F, false>(P, Kn, Dn, e2, nullptr);
                 c += F(0.5) * P.ia_w * (e2[0] * e2[0] + e2[1] * e2[1]);
+            }
+            if (ORI()) {
+                const V3<F> eo = orientation_error<F, false>(Kn.C, V3<F>(), ws + oTGQ() + 4 * k, nullptr);
+                c += F(0.5) * (P.Wo[0] * eo.x * eo.x + P.Wo[1] * eo.y * eo.y + P.Wo[2] * eo.z * eo.z);
             }
             cost += dt * c;
             const F* xn = Xt + (k + 1) * nx;
@@ -1079,6 +1109,10 @@ struct Solver {
                 if (b > a) continue;
                 F acc = 0;
                 for (int c = 0; c < 3; ++c) acc += C.Wd[c] * Jp[c * nq + a] * Jp[c * nq + b];
+                if (ORI()) {
+                    const F* Jq = ws + oLJQ() + k * 3 * nq;
+                    for (int c = 0; c < 3; ++c) acc += P.Wo[c] * Jq[c * nq + a] * Jq[c * nq + b];
+                }
                 sM[(nq + a) * ld + nq + b] += dt * acc;
             }
             tsync();
@@ -1742,6 +1776,16 @@ struct Solver {
                 const R part = lane < nq ? R(Jp[c * nq + lane]) * zk[nu + lane] : R(0);
                 e3[c] = tsum(part) + wsr<R>(oLR())[3 * k + c] - R(target[3 * k + c]);
             }
+            // orientation error at the QP iterate: e_o + Jq dq
+            R eo3[3] = {R(0), R(0), R(0)};
+            const F* Jq = ws + oLJQ() + k * 3 * nq;
+            if (ORI()) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const R part = lane < nq ? R(Jq[c * nq + lane]) * zk[nu + lane] : R(0);
+                    eo3[c] = tsum(part) + wsr<R>(oLRO())[3 * k + c];
+                }
+            }
             // inertial-alignment residual at the QP iterate: e + Je dx
             R ea[2] = {R(0), R(0)};
             const F* Ja = ws + oLJA() + 2 * k * nx;
@@ -1762,6 +1806,8 @@ struct Solver {
                     g = dt * PR.Qd[xi] * (R(x[xi]) + zk[i] - PR.xd[xi]);
                     if (xi < nq)
                         g += dt * (PR.Wd[0] * R(Jp[xi]) * e3[0] + PR.Wd[1] * R(Jp[nq + xi]) * e3[1] + PR.Wd[2] * R(Jp[2 * nq + xi]) * e3[2]);
+                    if (ORI() && xi < nq)
+                        g += dt * (PR.Wo[0] * R(Jq[xi]) * eo3[0] + PR.Wo[1] * R(Jq[nq + xi]) * eo3[1] + PR.Wo[2] * R(Jq[2 * nq + xi]) * eo3[2]);
                     if (IALIGN()) g += dt * PR.ia_w * (R(Ja[xi]) * ea[0] + R(Ja[nx + xi]) * ea[1]);
                 }
                 vec[i] = g;
@@ -2551,9 +2597,11 @@ struct Solver {
                     XOw[idx] = k == 0 ? x0[nx + i] : Xin[k * nxt + nx + i];
                 }
             }
-            const F* tg = A.target + size_t(b) * (N + 1) * 3;
+            const F* tg = A.target + size_t(b) * (N + 1) * A.tstride;
             F* tgl = ws + oTG();
-            for (int idx = lane; idx < (N + 1) * 3; idx += kTS) tgl[idx] = tg[idx];
+            for (int idx = lane; idx < (N + 1) * 3; idx += kTS) tgl[idx] = tg[(idx / 3) * A.tstride + idx % 3];
+            if (ORI())
+                for (int idx = lane; idx < (N + 1) * 4; idx += kTS) ws[oTGQ() + idx] = tg[(idx / 4) * A.tstride + 3 + idx % 4];
             const F* bd = A.body ? A.body + size_t(b) * NB() * UB_BODY_PARAMS : &P.body[0][0];
             F* bdl = ws + oBD();
             for (int idx = lane; idx < NB() * UB_BODY_PARAMS; idx += kTS) bdl[idx] = bd[idx];
@@ -2613,6 +2661,9 @@ struct Solver {
                         if (xi < nq)
                             for (int c = 0; c < 3; ++c)
                                 g += C.dt * C.Wd[c] * Jp[c * nq + xi] * (F(wsr<R>(oLR())[3 * k + c]) - target[3 * k + c]);
+                        if (ORI() && xi < nq)
+                            for (int c = 0; c < 3; ++c)
+                                g += C.dt * P.Wo[c] * ws[oLJQ() + (k * 3 + c) * nq + xi] * F(wsr<R>(oLRO())[3 * k + c]);
                         if (IALIGN())
                             for (int r = 0; r < 2; ++r)
                                 g += C.dt * P.ia_w * ws[oLJA() + (2 * k + r) * nx + xi] * ws[oLIA() + 2 * k + r];

@@ -46,6 +46,9 @@ class BatchedMPC:
         self.nx, self.nu, self.n_eq, self.n_ineq, self.n_term, self.N, self.nb, self.nc = list(dims)
         # nx counts the dynamic-obstacle states too (9 each, behind the robot state); gains act on the robot state
         self.nx_robot = 3 * desc.nq
+        # columns of a target row: desired position (3), + desired quaternion [x y z w] when the orientation part of
+        # the end-effector weight is non-zero (7)
+        self.target_stride = 7 if any(desc.ee_weight[i] != 0 for i in (3, 4, 5)) else 3
         self._ws = None
 
     def __del__(self):
@@ -67,7 +70,7 @@ class BatchedMPC:
         x0 = np.ascontiguousarray(np.atleast_2d(x0), dtype=np.float64)
         Bn = x0.shape[0]
         assert x0.shape == (Bn, self.nx)
-        target = np.ascontiguousarray(np.asarray(target, dtype=np.float64).reshape(Bn, self.N + 1, 3))
+        target = np.ascontiguousarray(np.asarray(target, dtype=np.float64).reshape(Bn, self.N + 1, self.target_stride))
         if body_params is not None:
             body_params = np.ascontiguousarray(body_params, dtype=np.float64).reshape(Bn, self.nb, 10)
         reuse = out is not None and out["X"].shape == (Bn, self.N + 1, self.nx) and (("K" in out) == bool(want_gains))

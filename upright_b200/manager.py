@@ -236,11 +236,14 @@ class _RecedingHorizon:
         self.t_obs, self.x_obs = float(t), np.array(x, dtype=float)
 
     def _knot_targets(self, t):
+        """Desired end-effector position at every knot — and, when the orientation part of the end-effector weight is
+        non-zero, the desired quaternion behind it (interpolate_end_effector_pose, reference_trajectory.h:18-47)."""
         times = t + self.dt * np.arange(self.N + 1)
-        tg = np.empty((self.B, self.N + 1, 3))
+        ts = self.engine.target_stride if hasattr(self.engine, "target_stride") else 3
+        tg = np.empty((self.B, self.N + 1, ts))
         for b in range(self.B):
             tt = self.targets[b if len(self.targets) > 1 else 0]
-            tg[b] = tt.positions_at(times)
+            tg[b] = tt.positions_at(times) if ts == 3 else tt.poses_at(times)
         return tg
 
     def operating_guess(self, t):

@@ -97,6 +97,39 @@ class TargetTrajectories:
         position part)."""
         return np.array([self.get_desired_state(t)[:3] for t in times])
 
+    def poses_at(self, times):
+        """[r(3), quat xyzw(4)] at each time: interpolate_end_effector_pose (reference_trajectory.h:18-47) — position
+        linear, orientation `q_lhs.slerp(1 - alpha, q_rhs)` with Eigen's slerp (shortest arc; linear blend when the
+        quaternions are nearly parallel)."""
+        out = np.empty((len(times), 7))
+        for n, t in enumerate(times):
+            if len(self.xs) == 1 or t <= self.ts[0]:
+                out[n] = self.xs[0][:7]
+                continue
+            if t >= self.ts[-1]:
+                out[n] = self.xs[-1][:7]
+                continue
+            i = int(np.searchsorted(self.ts, t, side="right")) - 1
+            a = (self.ts[i + 1] - t) / (self.ts[i + 1] - self.ts[i])
+            out[n, :3] = a * self.xs[i][:3] + (1 - a) * self.xs[i + 1][:3]
+            out[n, 3:] = quat_slerp(self.xs[i][3:7], self.xs[i + 1][3:7], 1 - a)
+        return out
+
+
+def quat_slerp(q0, q1, t):
+    """Eigen::Quaternion::slerp(t, other) for [x y z w] quaternions."""
+    q0, q1 = np.asarray(q0, dtype=float), np.asarray(q1, dtype=float)
+    d = float(q0 @ q1)
+    ad = abs(d)
+    if ad >= 1.0 - np.finfo(float).eps:
+        s0, s1 = 1.0 - t, t
+    else:
+        th = np.arccos(ad)
+        s0, s1 = np.sin((1.0 - t) * th) / np.sin(th), np.sin(t * th) / np.sin(th)
+    if d < 0:
+        s1 = -s1
+    return s0 * q0 + s1 * q1
+
 
 def _read_obstacle_xacro(path):
     """Sphere obstacles from an `obstacle_link` xacro scene such as
@@ -370,9 +403,6 @@ class ControllerSettings:
         for M in (self.state_weight, self.input_weight, self.end_effector_weight):
             if np.abs(M - np.diag(np.diag(M))).max() > 0:
                 raise NotImplementedError("only diagonal weights are supported")
-        if np.abs(Wd[3:]).max() > 0:
-            raise NotImplementedError(
-                "end-effector orientation weight != 0 is a 'next' item (all shipped configs use 0)")
         d.state_weight[: 3 * nq] = Qd
         d.input_weight[:nq] = Rd
         d.ee_weight[:] = Wd
