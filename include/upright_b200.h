@@ -337,6 +337,16 @@ int ub_closed_loop_set_obstacles(ub_problem_t* problem, int32_t n_obstacles, con
 int ub_set_gather_targets(ub_problem_t* problem, int32_t n, void* const* X_bases, void* const* U_bases,
                           int64_t row_offset);
 
+/* Gathered buffers for ub_set_gather_targets, shared between the processes (one per GPU) of a node.  The owner
+ * allocates device memory on ITS current device and gets an opaque handle to pass to its peers by any host channel;
+ * a peer opens the handle with ITS OWN device current (lazy peer access), which maps the owner's memory for stores from
+ * the peer's kernels over NVLink.  Close every opened mapping before the owner frees the buffer. */
+#define UB_IPC_HANDLE_BYTES 64
+int ub_gather_alloc(int64_t bytes, void** ptr, unsigned char handle[UB_IPC_HANDLE_BYTES]);
+int ub_gather_open(const unsigned char handle[UB_IPC_HANDLE_BYTES], void** ptr);
+int ub_gather_close(void* ptr);
+int ub_gather_free(void* ptr);
+
 /* Runtime options: "sqp_iteration" (init_sqp_iteration vs sqp_iteration,
  * controller.yaml:56-57), "projectile_active" (the target-state flag s of the
  * projectile path constraint, 0 or 1) and the test aid "stop_after" (0 full

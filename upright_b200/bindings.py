@@ -20,6 +20,7 @@ UB_MAX_NX = 27
 UB_BODY_PARAMS = 10
 UB_STATS = 8
 UB_MAX_GATHER = 8
+UB_IPC_HANDLE_BYTES = 64
 
 UB_PTRS_DEVICE = 0x1
 UB_WARM_START = 0x2
@@ -188,6 +189,14 @@ def load_library():
     lib.ub_closed_loop_set_obstacles.restype = C.c_int
     lib.ub_set_gather_targets.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(vp), C.c_int64]
     lib.ub_set_gather_targets.restype = C.c_int
+    lib.ub_gather_alloc.argtypes = [C.c_int64, C.POINTER(vp), C.c_char_p]
+    lib.ub_gather_alloc.restype = C.c_int
+    lib.ub_gather_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.ub_gather_open.restype = C.c_int
+    lib.ub_gather_close.argtypes = [vp]
+    lib.ub_gather_close.restype = C.c_int
+    lib.ub_gather_free.argtypes = [vp]
+    lib.ub_gather_free.restype = C.c_int
     lib.ub_measure_fma_peak.argtypes = [C.POINTER(C.c_double)]
     lib.ub_measure_fma_peak.restype = C.c_int
     _lib = lib
@@ -199,6 +208,7 @@ EXPORTED_SYMBOLS = [
     "ub_problem_dims", "ub_workspace_bytes", "ub_solve_batch", "ub_eval",
     "ub_last_solve_ms", "ub_launch_count", "ub_set_option", "ub_workspace_layout", "ub_closed_loop",
     "ub_measure_fma_peak", "ub_set_gather_targets", "ub_closed_loop_set_obstacles",
+    "ub_gather_alloc", "ub_gather_open", "ub_gather_close", "ub_gather_free",
 ]
 
 

@@ -1054,6 +1054,44 @@ int ub_set_gather_targets(ub_problem_t* p, int32_t n, void* const* X_bases, void
     }
     return UB_OK;
 }
+// Gathered buffers shared between the ranks of one node: allocated and exported by the owner, opened by the peers
+// with the OPENING device current and lazy peer access, which is what makes the mapping writable from kernels of that
+// device (a handle opened under the owner's device index, as torch's IPC rebuild does, is not).
+int ub_gather_alloc(int64_t bytes, void** ptr, unsigned char handle[UB_IPC_HANDLE_BYTES]) {
+    if (bytes <= 0 || !ptr || !handle) return fail(UB_E_INVALID, "ub_gather_alloc: bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == UB_IPC_HANDLE_BYTES, "IPC handle size");
+    void* d = nullptr;
+    UB_CUDA(cudaMalloc(&d, size_t(bytes)));
+    UB_CUDA(cudaMemset(d, 0, size_t(bytes)));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, d);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return fail(UB_E_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    UB_CUDA(cudaDeviceSynchronize());
+    std::memcpy(handle, &h, sizeof(h));
+    *ptr = d;
+    return UB_OK;
+}
+int ub_gather_open(const unsigned char handle[UB_IPC_HANDLE_BYTES], void** ptr) {
+    if (!ptr || !handle) return fail(UB_E_INVALID, "ub_gather_open: bad arguments");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void* d = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(&d, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(UB_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+    *ptr = d;
+    return UB_OK;
+}
+int ub_gather_close(void* ptr) {
+    if (ptr) UB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return UB_OK;
+}
+int ub_gather_free(void* ptr) {
+    if (ptr) UB_CUDA(cudaFree(ptr));
+    return UB_OK;
+}
 int ub_workspace_layout(const ub_problem_t* p, uint32_t flags, int32_t out[80]) {
     if (!p) return fail(UB_E_INVALID, "null problem");
     const ub::Layout& L = (flags & UB_COMPUTE_F64) ? p->Ld : p->Lf;

@@ -108,24 +108,20 @@ class PipelinedSolveGather:
         torch.cuda.current_stream().wait_stream(self.comm)
 
 
-def _share_cuda_tensor(t, group=None):
-    """Views of `t` of every rank of a single-node group in THIS process: CUDA IPC handles travel through
-    all_gather_object and are opened with torch's own rebuild function (peer ranks run on the other GPUs of the
-    node, so the views are peer-mapped device memory)."""
-    from torch.multiprocessing.reductions import reduce_tensor
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
-    fn, args = reduce_tensor(t)
-    packed = [None] * world
-    dist.all_gather_object(packed, (fn, args), group=group)
-    views = []
-    for r in range(world):
-        views.append(t if r == rank else packed[r][0](*packed[r][1]))
-    return views
+class _DeviceBuffer:
+    """A raw device allocation presented to torch through `__cuda_array_interface__` (torch.as_tensor wraps it
+    without a copy and keeps this object alive)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.ptr = ptr
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
 
 
 class FusedSolveGather:
     """Sharded solves whose result exchange is done BY THE SOLVE KERNEL: every rank owns a gathered buffer
-    [world * B] for X and U; the buffers of all ranks are mapped into every process (CUDA IPC over NVLink) and
+    [world * B] for X and U; the buffers of all ranks are mapped into every process (CUDA IPC through the library's
+    own `ub_gather_alloc` / `ub_gather_open`, opened with the accessing device current so that peer access is on) and
     `ub_set_gather_targets` makes the kernel's epilogue store each solved instance into its row of every peer's
     buffer (and, through the X / U arguments, of its own) while the rest of the batch is still being solved.  No
     collective kernel, no copy engine work, nothing competing with the persistent solve grid for SMs.  Two buffer
@@ -135,26 +131,58 @@ class FusedSolveGather:
 
     def __init__(self, mpc, batch, group=None):
         import ctypes as C
+        from . import bindings as Bd
         self.mpc, self.B, self.group = mpc, batch, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        if self.world - 1 > 8:
-            raise ValueError("at most 8 peers")
+        if self.world - 1 > Bd.UB_MAX_GATHER:
+            raise ValueError(f"at most {Bd.UB_MAX_GATHER} peers")
         dev, dt = torch.device("cuda", torch.cuda.current_device()), mpc.torch_dtype
-        W, B = self.world, batch
-        self.Xfull = [torch.zeros((W * B, mpc.N + 1, mpc.nx), dtype=dt, device=dev) for _ in range(2)]
-        self.Ufull = [torch.zeros((W * B, mpc.N, mpc.nu), dtype=dt, device=dev) for _ in range(2)]
+        W, B, lib = self.world, batch, mpc.lib
+        esz = torch.empty((), dtype=dt).element_size()
+        typestr = "<f4" if esz == 4 else "<f8"
+        nX, nU = W * B * (mpc.N + 1) * mpc.nx, W * B * mpc.N * mpc.nu
+        self._u_off = (nX * esz + 255) // 256 * 256
+        nbytes = self._u_off + nU * esz
+        self._own, self._opened, handles = [], [], []
+        self.Xfull, self.Ufull = [], []
+        for _ in range(2):
+            ptr, h = C.c_void_p(), C.create_string_buffer(Bd.UB_IPC_HANDLE_BYTES)
+            Bd.check(lib.ub_gather_alloc(nbytes, C.byref(ptr), h))
+            self._own.append(ptr.value)
+            handles.append(h.raw)
+            self.Xfull.append(torch.as_tensor(_DeviceBuffer(ptr.value, (W * B, mpc.N + 1, mpc.nx), typestr), device=dev))
+            self.Ufull.append(torch.as_tensor(_DeviceBuffer(ptr.value + self._u_off, (W * B, mpc.N, mpc.nu), typestr), device=dev))
         self.status = torch.empty(B, dtype=torch.int32, device=dev)
         self.stats = torch.empty((B, 8), dtype=dt, device=dev)
-        # peer views of both buffer sets (kept alive: closing an IPC mapping while kernels write to it is an error)
-        self._peerX = [_share_cuda_tensor(t, group) for t in self.Xfull]
-        self._peerU = [_share_cuda_tensor(t, group) for t in self.Ufull]
+        everyone = [None] * W
+        dist.all_gather_object(everyone, handles, group=group)
         self._targets = []
         for i in range(2):
-            xs = [self._peerX[i][r].data_ptr() for r in range(W) if r != self.rank]
-            us = [self._peerU[i][r].data_ptr() for r in range(W) if r != self.rank]
+            xs, us = [], []
+            for r in range(W):
+                if r == self.rank:
+                    continue
+                ptr = C.c_void_p()
+                Bd.check(lib.ub_gather_open(everyone[r][i], C.byref(ptr)))
+                self._opened.append(ptr.value)
+                xs.append(ptr.value)
+                us.append(ptr.value + self._u_off)
             self._targets.append(((C.c_void_p * len(xs))(*xs), (C.c_void_p * len(us))(*us), len(xs)))
         self.step_index = 0
         dist.barrier(group)
+
+    def close(self):
+        """Unmap the peers' buffers and, after a barrier, free the own ones (views handed out become invalid)."""
+        lib = self.mpc.lib
+        torch.cuda.synchronize()
+        for p in self._opened:
+            lib.ub_gather_close(p)
+        self._opened = []
+        dist.barrier(self.group)
+        self.Xfull, self.Ufull = [], []
+        for p in self._own:
+            lib.ub_gather_free(p)
+        self._own = []
 
     def step(self, x0, target, body=None):
         from . import bindings as Bd
