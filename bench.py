@@ -134,7 +134,10 @@ PER_GPU_BATCH = {   # BASELINE.json batch of a configuration on ONE GPU (cfg4: 1
 }
 
 
-def config_block(name, prec, world, dev, peak_tflops, seed=4321):
+FULL_BATCH_ONE_GPU = {"cfg4_thing_obstacles2": 16384, "cfg5_thing_robust8": 8192}   # BASELINE's whole batch on ONE GPU
+
+
+def config_block(name, prec, world, dev, peak_tflops, seed=4321, batch=None):
     """One BASELINE configuration at its per-GPU batch: kernel time (CUDA events, mean of 3 launches after a warm-up),
     iteration statistics, status counts and the arithmetic roofline fraction.  With world > 1 every rank solves its own
     shard (cfg4: 8 x 2048 = 16384, cfg5: 8 x 1024 = 8192 — BASELINE's split) and the packed results are all-gathered;
@@ -146,7 +149,7 @@ def config_block(name, prec, world, dev, peak_tflops, seed=4321):
     desc, meta = workload.load(name)
     mpc = BatchedMPC(desc, prec)
     dt = mpc.torch_dtype
-    B = PER_GPU_BATCH[name]
+    B = batch or PER_GPU_BATCH[name]
     rank = dist.get_rank() if world > 1 else 0
     ee = lambda x: mpc.eval("end_effector_position", x, np.zeros((x.shape[0], mpc.nu)))  # noqa: E731
     mg = (lambda x: mpc.eval("obstacle_avoidance", x, np.zeros((x.shape[0], mpc.nu)))) if desc.obstacles_enabled else None
@@ -197,6 +200,12 @@ def config_block(name, prec, world, dev, peak_tflops, seed=4321):
            "dram_bytes_per_launch": traffic, "dram_bytes_source": src,
            "nx": mpc.nx, "nu": mpc.nu, "dtype": prec}
     del mpc
+    if world == 1 and batch is None and name in FULL_BATCH_ONE_GPU:
+        # the 8-GPU configurations also as ONE batch on one GPU (several waves of the persistent grid instead of one)
+        full_one = config_block(name, prec, world, dev, peak_tflops, seed, batch=FULL_BATCH_ONE_GPU[name])
+        out["whole_baseline_batch_on_one_gpu"] = {k: full_one[k] for k in ("global_batch", "solves_per_s", "ms_per_batch", "kernel_ms",
+                                                                            "mean_ipm_iterations", "max_ipm_iterations",
+                                                                            "status_counts", "fp32_frac")}
     return out
 
 

@@ -1007,6 +1007,10 @@ struct Riccati {
                     for (int l = 0; l < nu; ++l) v += Mk(nu + i, l) * K[k](l, j);
                     Pm[k](i, j) = v;
                 }
+            // keep the cost-to-go exactly symmetric: the rounding asymmetry of Mxx + Mxu K is amplified from stage
+            // to stage and breaks the recursion after ~60 stages (the N = 100 robust-planner horizon)
+            for (int i = 0; i < nx; ++i)
+                for (int j = 0; j < i; ++j) Pm[k](i, j) = Pm[k](j, i) = 0.5 * (Pm[k](i, j) + Pm[k](j, i));
         }
         return true;
     }

@@ -915,3 +915,36 @@ def test_device_closed_loop_keeps_the_object_balanced():
             lin = oracle.linearize(desc, x, np.zeros(13))
             worst = max(worst, nnls(lin["Df"], -lin["g"])[1])
     assert worst < 0.05 * at_rest
+
+
+def test_robust_planner_shape_n100():
+    """The planner shape of the robust demos (upright_robust/config/demos/_base.yaml:62-66: time_horizon 10 s at
+    dt 0.1 -> N = 100 knots, init_sqp_iteration 3) on the robust 8-vertex constraint set (cfg5): fp64 kernels against
+    the oracle at the fp64 tolerance, the product kernels at the stated fp32 tolerance.  Runs the run-time-dimension
+    kernel (the specialised ones are built for N = 20)."""
+    import copy
+    base, meta = problem_io.load_fixture("cfg5_thing_robust8")
+    desc = copy.deepcopy(base)
+    desc.N, desc.sqp_iteration = 100, 3
+    B = 8
+    ee = lambda x: np.stack([oracle.fk(desc, xi)["r"] for xi in x])  # noqa: E731
+    b = workload.sample_batch("cfg5_thing_robust8", desc, meta, B, 11, ee)
+    assert b["target"].shape == (B, 101, 3)
+    ref = oracle.solve_batch(desc, b["x0"], b["target"], b["body_params"])
+    assert (ref["status"] == 0).all() and (ref["stats"][:, 7] == 3).all()
+    rx, ru = ranges(desc)
+    for prec, tol in (("f64", 1e-7), ("f32", 1e-3)):
+        mpc = BatchedMPC(desc, prec)
+        assert mpc.N == 100
+        out = mpc.solve(b["x0"], b["target"], b["body_params"])
+        assert (out["status"] == 0).all(), out["status"]
+        assert np.array_equal(out["stats"][:, 7], ref["stats"][:, 7])           # three SQP iterations each
+        ex = (np.abs(out["X"] - ref["X"]) / rx).max()
+        eu = (np.abs(out["U"] - ref["U"]) / ru).max()
+        print(f"N=100 robust planner {prec}: scaled error X {ex:.2e} U {eu:.2e}; interior-point iterations "
+              f"{out['stats'][:, 0].tolist()} (oracle {ref['stats'][:, 0].tolist()})")
+        if prec == "f64":
+            assert np.array_equal(out["stats"][:, 0], ref["stats"][:, 0])
+            assert np.abs(out["X"] - ref["X"]).max() <= tol and np.abs(out["U"] - ref["U"]).max() <= tol
+        else:
+            assert max(ex, eu) <= tol

@@ -438,3 +438,30 @@ def test_precision_study_modes():
     emx = (np.abs(rmx["dX"] - dX) / rx).max()
     assert r32["converged"] and rmx["converged"] and r32["failed"] == 0
     assert e32 < 1e-2 and emx < 1e-4 and emx <= e32
+
+
+def test_long_horizon_robust_planner_shape():
+    """N = 100 knots with three SQP iterations (upright_robust/config/demos/_base.yaml:62-66): the Riccati recursion
+    keeps the cost-to-go symmetric, so the 100-stage backward sweep stays positive definite (an unsymmetrised
+    recursion breaks down near stage 60) and the longer horizon reproduces the 20-knot plan where they overlap in
+    character: converged, dynamically consistent, objects balanced within the slack tolerance."""
+    import copy
+    import oracle
+    from upright_b200 import workload
+    base, meta = problem_io.load_fixture("cfg5_thing_robust8")
+    desc = copy.deepcopy(base)
+    desc.N, desc.sqp_iteration = 100, 3
+    ee = lambda x: np.stack([oracle.fk(desc, xi)["r"] for xi in x])  # noqa: E731
+    b = workload.sample_batch("cfg5_thing_robust8", desc, meta, 3, 11, ee)
+    out = oracle.solve_batch(desc, b["x0"], b["target"], b["body_params"])
+    assert (out["status"] == 0).all() and (out["stats"][:, 7] == 3).all()
+    X, U = out["X"], out["U"]
+    assert X.shape == (3, 101, desc.nx) and np.all(np.isfinite(X)) and np.all(np.isfinite(U))
+    A, Bm = _dynamics(desc)
+    for i in range(3):
+        gap = X[i, 1:] - X[i, :-1] @ A.T - U[i] @ Bm.T
+        assert np.abs(gap).max() < 1e-6
+        # three SQP iterations move the end of the plan towards the goal (soft terminal rows: not onto it)
+        r_end, r_start = oracle.fk(desc, X[i, -1])["r"], oracle.fk(desc, X[i, 0])["r"]
+        goal = b["target"][i, -1]
+        assert np.linalg.norm(r_end - goal) < 0.8 * np.linalg.norm(r_start - goal)

@@ -397,26 +397,42 @@ size_t problem_smem_bytes() {
     return sizeof(T) == 8 ? f : f + (sizeof(ub::DevProblem<double>) + 15) / 16 * 16;
 }
 
-// Launch geometry: warps per CTA — two CTAs per SM (the 128-register kernels allow 16 warps per SM), each taking
-// half of the SM's shared memory minus the 1 KB the driver reserves per CTA; at most 8 warps.
+// Launch geometry: warps (= instances) per CTA and CTAs per SM.  The kernels are latency bound, so what counts is the
+// number of resident warps per SM, and that is limited by shared memory (the 128-register kernels allow 16 warps):
+// either two CTAs per SM, each with half of the SM's shared memory minus the 1 KB the driver reserves per CTA, or ONE
+// CTA of up to 16 warps, which pays the CTA-shared problem constants once — whichever holds more warps.
+struct Geometry {
+    int wpc, ctas_per_sm;
+};
 template <typename T>
-int warps_per_cta(const ub_problem* p) {   // = instances per CTA
+Geometry launch_geometry(const ub_problem* p, int B = 0) {
     const ub::Layout& L = Pick<T>::layout(p);
     const size_t pbytes = problem_smem_bytes<T>();
     const size_t per_warp = size_t(L.s_total) * sizeof(T);
-    const size_t cta_budget = size_t(p->max_smem_sm) / 2 - 1024;
-    int wpc = cta_budget > pbytes ? int((cta_budget - pbytes) / per_warp) : 1;
-    if (wpc > 8) wpc = 8;
-    if (wpc < 1) wpc = 1;
-    const char* env = std::getenv("UB_WARPS_PER_CTA");
-    if (env) wpc = std::max(1, std::min(8, std::atoi(env)));
-    return wpc;
+    auto fit = [&](size_t budget) {
+        const int w = budget > pbytes ? int((budget - pbytes) / per_warp) : 0;
+        return std::max(1, std::min(16, w));
+    };
+    const int two = std::min(8, fit(size_t(p->max_smem_sm) / 2 - 1024));
+    const int one = fit(std::min(size_t(p->max_smem_optin), size_t(p->max_smem_sm) - 1024));
+    // (measured on the B200, profiles/r2_v5_geometry.txt: at equal warp counts the single CTA is the faster one)
+    Geometry g = one >= 2 * two ? Geometry{one, 1} : Geometry{two, 2};
+    if (const char* env = std::getenv("UB_CTAS_PER_SM")) g = std::atoi(env) == 1 ? Geometry{one, 1} : Geometry{two, 2};
+    if (const char* env = std::getenv("UB_WARPS_PER_CTA")) g.wpc = std::max(1, std::min(16, std::atoi(env)));
+    // A batch smaller than the resident warps is spread over ALL SMs (the work queue is greedy: with full-size CTAs the
+    // first SMs to start would take every instance and the rest of the chip would idle)
+    if (B > 0 && std::getenv("UB_NO_SPREAD") == nullptr) {
+        const int64_t ctas = int64_t(p->sm_count) * g.ctas_per_sm;
+        g.wpc = int(std::max<int64_t>(1, std::min<int64_t>(g.wpc, (B + ctas - 1) / ctas)));
+    }
+    return g;
 }
 // Workspace slots of a batch of B: the persistent grid holds one slot per resident warp; the static test mode
 // (option stop_after != 0) one per instance.
 template <typename T>
 int64_t workspace_slots(const ub_problem* p, int B) {
-    const int64_t resident = int64_t(p->sm_count) * 2 * warps_per_cta<T>(p);
+    const Geometry g = launch_geometry<T>(p, B);
+    const int64_t resident = int64_t(p->sm_count) * g.ctas_per_sm * g.wpc;
     return std::max<int64_t>(1, std::min<int64_t>(B, resident));
 }
 template <typename T>
@@ -430,7 +446,7 @@ int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
     const ub::Layout& L = Pick<T>::layout(p);
     const size_t pbytes = problem_smem_bytes<T>();
     const size_t per_warp = size_t(L.s_total) * sizeof(T);
-    const int wpc = warps_per_cta<T>(p);
+    const int wpc = p->stop_after == 0 ? launch_geometry<T>(p, A.B).wpc : launch_geometry<T>(p).wpc;
     const size_t smem = pbytes + per_warp * wpc;
     if (smem > size_t(p->max_smem_optin)) return fail(UB_E_INVALID, "problem too large for shared memory");
     const bool persistent = p->stop_after == 0;

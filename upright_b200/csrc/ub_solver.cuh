@@ -2794,7 +2794,7 @@ struct Solver {
 };
 
 template <typename F, typename D>
-__global__ void __launch_bounds__(256, 2) solve_batch_kernel(const __grid_constant__ DevProblem<F> Pc, const DevProblem<F>* __restrict__ Pg,
+__global__ void __launch_bounds__(512, 1) solve_batch_kernel(const __grid_constant__ DevProblem<F> Pc, const DevProblem<F>* __restrict__ Pg,
                                                           const DevProblem<double>* __restrict__ Pgr, Layout L, BatchArgs<F> A,
                                                           int teams_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
