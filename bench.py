@@ -137,7 +137,7 @@ PER_GPU_BATCH = {   # BASELINE.json batch of a configuration on ONE GPU (cfg4: 1
 FULL_BATCH_ONE_GPU = {"cfg4_thing_obstacles2": 16384, "cfg5_thing_robust8": 8192}   # BASELINE's whole batch on ONE GPU
 
 
-def config_block(name, prec, world, dev, peak_tflops, seed=4321, batch=None):
+def config_block(name, prec, world, dev, peak_tflops, seed=4321, batch=None, gather="fused"):
     """One BASELINE configuration at its per-GPU batch: kernel time (CUDA events, mean of 3 launches after a warm-up),
     iteration statistics, status counts and the arithmetic roofline fraction.  With world > 1 every rank solves its own
     shard (cfg4: 8 x 2048 = 16384, cfg5: 8 x 1024 = 8192 — BASELINE's split) and the packed results are all-gathered;
@@ -159,9 +159,13 @@ def config_block(name, prec, world, dev, peak_tflops, seed=4321, batch=None):
     nX, nU = (mpc.N + 1) * mpc.nx, mpc.N * mpc.nu
     packed = torch.empty(B * (nX + nU), dtype=dt, device=dev)
     X, U = packed[: B * nX].view(B, mpc.N + 1, mpc.nx), packed[B * nX:].view(B, mpc.N, mpc.nu)
-    full = torch.empty(world * B * (nX + nU), dtype=dt, device=dev) if world > 1 else None
-    status = torch.empty(B, dtype=torch.int32, device=dev)
-    stats = torch.empty((B, 8), dtype=dt, device=dev)
+    fused = None
+    if world > 1 and gather == "fused":   # results stored into every peer's gathered buffer by the solve kernel itself
+        from upright_b200.distributed import FusedSolveGather
+        fused = FusedSolveGather(mpc, B)
+    full = torch.empty(world * B * (nX + nU), dtype=dt, device=dev) if world > 1 and fused is None else None
+    status = torch.empty(B, dtype=torch.int32, device=dev) if fused is None else fused.status
+    stats = torch.empty((B, 8), dtype=dt, device=dev) if fused is None else fused.stats
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms, kms = [], []
     for it in range(4):
@@ -169,9 +173,13 @@ def config_block(name, prec, world, dev, peak_tflops, seed=4321, batch=None):
             dist.barrier()
         torch.cuda.synchronize()
         ev0.record()
-        mpc.solve_device(x0, tg, bp, X=X, U=U, status=status, stats=stats)
-        if world > 1:
-            dist.all_gather_into_tensor(full, packed)
+        if fused is not None:
+            fused.step(x0, tg, bp)
+            fused.finish()                # stream synchronisation + barrier: the gathered buffers are complete on every rank
+        else:
+            mpc.solve_device(x0, tg, bp, X=X, U=U, status=status, stats=stats)
+            if world > 1:
+                dist.all_gather_into_tensor(full, packed)
         ev1.record()
         torch.cuda.synchronize()
         if it > 0:
@@ -199,6 +207,11 @@ def config_block(name, prec, world, dev, peak_tflops, seed=4321, batch=None):
            "algorithmic_tflops": tf, "fp32_frac": tf / (peak_tflops * world) if peak_tflops else None,
            "dram_bytes_per_launch": traffic, "dram_bytes_source": src,
            "nx": mpc.nx, "nu": mpc.nu, "dtype": prec}
+    if fused is not None:
+        out["gather"] = "fused into the solve kernel"
+        fused.close()
+    elif world > 1:
+        out["gather"] = "ncclAllGather after the solve (not overlapped)"
     del mpc
     if world == 1 and batch is None and name in FULL_BATCH_ONE_GPU:
         # the 8-GPU configurations also as ONE batch on one GPU (several waves of the persistent grid instead of one)
@@ -425,7 +438,7 @@ def main():
         configs = {}
         for name in PER_GPU_BATCH:
             try:
-                configs[name.split("_")[0]] = config_block(name, args.precision, world, dev, fp32_peak)
+                configs[name.split("_")[0]] = config_block(name, args.precision, world, dev, fp32_peak, gather=args.gather)
             except Exception as e:  # noqa: BLE001 — a failing extra must not cost the headline line
                 configs[name.split("_")[0]] = {"error": str(e)[:300]}
 

@@ -6,8 +6,12 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from upright_b200 import workload
 from upright_b200.engine import BatchedMPC
-for name, B in [("cfg1_ur10_demo", 4096), ("cfg2_thing_demo", 4096), ("cfg3_thing_box_arch", 4096), ("cfg4_thing_obstacles2", 2048),
-                ("cfg5_thing_robust8", 1024)]:
+import os
+CASES = [("cfg1_ur10_demo", 4096), ("cfg2_thing_demo", 4096), ("cfg3_thing_box_arch", 4096), ("cfg4_thing_obstacles2", 2048),
+         ("cfg5_thing_robust8", 1024)]
+if os.environ.get("UB_SWEEP"):   # e.g. UB_SWEEP=cfg5_thing_robust8:8192,cfg3_thing_box_arch:4096
+    CASES = [(c.split(":")[0], int(c.split(":")[1])) for c in os.environ["UB_SWEEP"].split(",")]
+for name, B in CASES:
     desc, meta = workload.load(name)
     mpc = BatchedMPC(desc, "f32")
     ee = lambda x: mpc.eval("end_effector_position", x, np.zeros((x.shape[0], mpc.nu)))

@@ -51,8 +51,12 @@ struct Layout {
     int s_total;
     int rw;   // units per double
 };
-// side records of a stage are staged in shared memory (cp.async, one stage ahead) up to this many rows
-#define UB_STAGE_ROWS_MAX 64
+// side records of a stage are staged in shared memory (cp.async, one stage ahead) up to this many rows (72 covers cfg5's
+// 68-row stage: +18 % at 1024 instances; cfg3's 164-row stage loses more to the resident warps the buffers cost than it
+// gains, profiles/r2_v6_staging_ab.txt)
+#ifndef UB_STAGE_ROWS_MAX
+#define UB_STAGE_ROWS_MAX 72
+#endif
 struct LayoutDims {
     int N, nq, nx, nu, neq, nfc, nterm, nrow, nobs, nb, nc, nf;
     int rw;          // sizeof(double) / sizeof(F)
@@ -143,7 +147,7 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.sSmX = s; s += staged ? ub_round4(nx) : 0;
     L.sSmU = s; s += staged ? ub_round4(nu) : 0;
     L.sSmJ = s; s += staged ? ub_round4(3 * nq) : 0;
-    L.sSmW = s; s += staged ? ub_round4(nq) : 0;
+    L.sSmW = s; s += ub_round4(nq);
     L.s_total = s;
     return L;
 }
@@ -443,6 +447,9 @@ struct Solver {
     // Staging of the side records: the records of the stage a pass visits NEXT are copied into shared memory
     // with cp.async while the current stage computes.  Writers always store to the workspace.
     static constexpr bool kStageTT = D::kStatic && D::nrow <= UB_STAGE_ROWS_MAX;
+    // every specialised kernel prefetches the factor block (into the idle half of the stage-matrix buffer), the
+    // force bundle and w_k of the stage a sweep visits next: they need no buffer of their own
+    static constexpr bool kStageFB = D::kStatic;
     __device__ __forceinline__ const QuadR* recs_tl(int k) const {
         if constexpr (kStageTT) return reinterpret_cast<const QuadR*>(sTL);
         else return wsr<QuadR>(oTL()) + k * NROW();
@@ -472,7 +479,17 @@ struct Solver {
             if (k < 0 || k > NN()) return;
             cp_async_bytes(sTL, wsr<QuadR>(oTL()) + k * D::nrow, D::nrow * 4 * int(sizeof(R)));
             if (with_steps) cp_async_bytes(sDD, wsr<QuadF>(oDD()) + k * D::nrow, D::nrow * 4 * int(sizeof(F)));
+        } else if constexpr (kStageFB) {
+            // stages too wide to stage in shared memory (cfg3: 164 rows, cfg5: 68): pull the records of the next stage
+            // into L2 at least, so that the loads of the next stage do not wait for DRAM
+            if (k < 0 || k > NN()) return;
+            l2_prefetch(wsr<QuadR>(oTL()) + k * D::nrow, D::nrow * 4 * int(sizeof(R)));
+            if (with_steps) l2_prefetch(wsr<QuadF>(oDD()) + k * D::nrow, D::nrow * 4 * int(sizeof(F)));
         }
+    }
+    __device__ __forceinline__ void l2_prefetch(const void* src, int bytes) const {
+        const char* s = reinterpret_cast<const char*>(src);
+        for (int i = lane * 128; i < bytes; i += kTS * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(s + i));
     }
     // staged per-stage vectors (same schedule as the side records): the QP iterate z_k (or, in the corrector
     // pass, the stored predictor gradient), the linearisation point x_k, u_k, the position Jacobian and w_k
@@ -495,6 +512,10 @@ struct Solver {
     }
     // z_k (gp = false) or the predictor gradient of stage k (gp = true), x_k, u_k and optionally Jp_k
     __device__ __forceinline__ void sm_issue(int k, bool gp, bool jp) const {
+        if constexpr (!kStageTT && kStageFB) {
+            if (k < 0 || k > NN()) return;
+            l2_prefetch(gp ? GPk(k) : Zk(k), NZ() * int(sizeof(R)));
+        }
         if constexpr (kStageTT) {
             if (k < 0 || k > NN()) return;
             cp_async_elems(sSmZ, gp ? GPk(k) : Zk(k), NZ());
@@ -506,7 +527,7 @@ struct Solver {
         }
     }
     __device__ __forceinline__ void w_issue(int k) const {
-        if constexpr (kStageTT) {
+        if constexpr (kStageFB) {
             if (k < 0 || k >= NN()) return;
             cp_async_elems(sSmW, ws + oWF() + k * NQ(), NQ());
         }
@@ -929,6 +950,10 @@ struct Solver {
         tsync();
     }
     __device__ __forceinline__ void c_issue(int k) const {
+        if constexpr (!kStageTT && kStageFB) {
+            if (NEQ() == 0 || k < 0 || k >= NN()) return;
+            l2_prefetch(ws + oLC() + k * D::neq * D::nx, D::neq * D::nx * int(sizeof(F)));
+        }
         if constexpr (kStageTT) {
             if (NEQ() == 0 || k < 0 || k >= NN()) return;
             cp_async_elems(sCst, ws + oLC() + k * D::neq * D::nx, D::neq * D::nx);   // stage blocks are only 4-byte aligned
@@ -1610,7 +1635,7 @@ struct Solver {
         tsync();
     }
     __device__ __forceinline__ void fb_issue(int k) const {
-        if constexpr (kStageTT) {
+        if constexpr (kStageFB) {
             if (NFC() == 0 || k < 0 || k >= NN()) return;
             cp_async_bytes(sFB, bundle(k), obsize() * int(sizeof(F)));
         }
@@ -1958,7 +1983,7 @@ struct Solver {
         bool ok = true;
         for (int i = lane; i < nx; i += kTS) sPv[i] = F(0);
         tsync();
-        if constexpr (kStageTT) {
+        if constexpr (kStageFB) {
             tt_issue(NN(), false);
             sm_issue(NN(), false, true);
             cp_commit();
@@ -1987,7 +2012,7 @@ struct Solver {
             t_f2 += f2 - f1;
             if (k < NN()) assign_dynamics_hessian();
             build_stage_matrix(k, k < NN());
-            if constexpr (kStageTT) {                       // next stage's records / vectors / C rows arrive during the factorisation
+            if constexpr (kStageFB) {                       // next stage's records / vectors / C rows arrive during the factorisation
                 tsync();
                 tt_issue(k - 1, false);
                 sm_issue(k - 1, false, true);
@@ -2028,13 +2053,13 @@ struct Solver {
         const int nbx = NBOXU() + nx;
         // cp.async group schedule: [records, gradient, force bundle](k) is committed before FAC(k); every wait leaves
         // exactly one younger group in flight (none at the terminal stage)
-        if constexpr (kStageTT) {
+        if constexpr (kStageFB) {
             tt_issue(NN(), true);
             sm_issue(NN(), true, false);
             cp_commit();
         }
         for (int k = NN(); k >= 0; --k) {
-            if constexpr (kStageTT) {
+            if constexpr (kStageFB) {
                 if (k == NN()) cp_wait<0>();
                 else cp_wait<1>();
             } else {
@@ -2095,7 +2120,7 @@ struct Solver {
             }
             if (k == NN()) {
                 for (int i = lane; i < nx; i += kTS) sPv[i] = F(sVec[nu + i]);
-                if constexpr (kStageTT) {
+                if constexpr (kStageFB) {
                     tsync();
                     tt_issue(k - 1, true);
                     sm_issue(k - 1, true, false);
@@ -2125,7 +2150,7 @@ struct Solver {
             } else {
                 reduced_rhs(k, nullptr, 0, nullptr);
             }
-            if constexpr (kStageTT) {
+            if constexpr (kStageFB) {
                 tsync();
                 tt_issue(k - 1, true);
                 sm_issue(k - 1, true, false);
@@ -2134,7 +2159,7 @@ struct Solver {
             }
             add_dynamics_gradient(sRv);
             const F* Fb = sM;
-            if constexpr (kStageTT) {
+            if constexpr (kStageFB) {
                 cp_wait<1>();
                 fac_issue(k - 1, (k - 1) & 1);
                 cp_commit();
@@ -2160,7 +2185,7 @@ struct Solver {
             }
             tsync();
         }
-        if constexpr (kStageTT) cp_wait<0>();
+        if constexpr (kStageFB) cp_wait<0>();
     }
 
     // Side steps of the rows of ONE stage for the stage direction d = [du; dx] (shared memory):
@@ -2217,7 +2242,7 @@ struct Solver {
         tsync();
         // cp.async group schedule: FAC(k) is committed before [records, vectors, force bundle](k); every wait leaves
         // exactly one younger group in flight (none for the records of the terminal stage)
-        if constexpr (kStageTT) {
+        if constexpr (kStageFB) {
             fac_issue(0, 0);
             w_issue(0);
             cp_commit();
@@ -2231,7 +2256,7 @@ struct Solver {
                 const F* Fb = sM;
                 const F* Wk = ws + oWF() + k * nq;
                 F wreg = F(0);
-                if constexpr (kStageTT) {
+                if constexpr (kStageFB) {
                     cp_wait<1>();
                     // w_k leaves its (single) staging slot before w_{k+1} is requested
                     if (lane < nq) wreg = sSmW[lane];
@@ -2260,18 +2285,18 @@ struct Solver {
                     if (lane == 0) dj[j] = uj;
                     tsync();
                 }
-                if constexpr (kStageTT) cp_wait<1>();       // records, vectors and the force bundle of stage k
+                if constexpr (kStageFB) cp_wait<1>();       // records, vectors and the force bundle of stage k
                 else load_force_block(k);
                 if (NFC() > 0) force_block_step();
             } else {
-                if constexpr (kStageTT) cp_wait<0>();
+                if constexpr (kStageFB) cp_wait<0>();
                 for (int j = lane; j < nu; j += kTS) dst[j] = F(0);
                 tsync();
             }
             F* Dk = DZk(k);
             for (int i = lane; i < nz; i += kTS) Dk[i] = dst[i];
             stage_side_steps(k, dst, corrector, target_mu, amax, rnd);
-            if constexpr (kStageTT) {
+            if constexpr (kStageFB) {
                 tsync();
                 tt_issue(k + 1, true);
                 sm_issue(k + 1, false, false);
@@ -2291,7 +2316,7 @@ struct Solver {
                 tsync();
             }
         }
-        if constexpr (kStageTT) cp_wait<0>();
+        if constexpr (kStageFB) cp_wait<0>();
         *rnd_out = R(tmax(rnd));
         return R(tmin(amax));
     }
@@ -2444,7 +2469,8 @@ struct Solver {
                     // mean complementarity after the affine step -> centring target (Mehrotra)
                     const R a_aff = a_fwd;
                     R acc = 0;
-                    for (int idx = lane; idx < (N + 1) * NROW(); idx += kTS) {
+#pragma unroll 4
+                    for (int idx = lane; idx < (N + 1) * NROW(); idx += kTS) {   // (unrolled: four records in flight per lane)
                         const int k = idx / NROW(), r = idx % NROW();
                         const int fam = row_family(r);
                         if (!row_valid(k, fam)) continue;
@@ -2478,19 +2504,37 @@ struct Solver {
             }
             // update z, t, lambda; new mean complementarity
             R musum = 0;
+#pragma unroll 4
             for (int idx = lane; idx < (N + 1) * nz; idx += kTS) Zall[idx] += alpha * R(ws[oDZ() + idx]);
-            for (int idx = lane; idx < (N + 1) * NROW(); idx += kTS) {
-                const int k = idx / NROW(), r = idx % NROW();
-                const int fam = row_family(r);
-                QuadR* rec = wsr<QuadR>(oTL()) + idx;
-                QuadR q = *rec;
-                const QuadF dd = wsr<QuadF>(oDD())[idx];
+            {   // two records per lane and round, both loaded before either is used (the loop is pure memory latency)
+                const int total = (N + 1) * NROW();
+                QuadR* const TLb = wsr<QuadR>(oTL());
+                const QuadF* const DDb = wsr<QuadF>(oDD());
+                for (int base = 0; base < total; base += 2 * kTS) {
+                    const int i0 = base + lane, i1 = i0 + kTS;
+                    const bool v0 = i0 < total, v1 = i1 < total;
+                    QuadR q0 = TLb[v0 ? i0 : 0], q1 = TLb[v1 ? i1 : 0];
+                    const QuadF d0 = DDb[v0 ? i0 : 0], d1 = DDb[v1 ? i1 : 0];
+                    if (v0) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) q.v[c] += alpha * R(dd.v[c]);
-                *rec = q;
-                if (row_valid(k, fam)) {
-                    musum += q.v[0] * q.v[2];
-                    if (fam < 2) musum += q.v[1] * q.v[3];
+                        for (int c = 0; c < 4; ++c) q0.v[c] += alpha * R(d0.v[c]);
+                        TLb[i0] = q0;
+                        const int fam = row_family(i0 % NROW());
+                        if (row_valid(i0 / NROW(), fam)) {
+                            musum += q0.v[0] * q0.v[2];
+                            if (fam < 2) musum += q0.v[1] * q0.v[3];
+                        }
+                    }
+                    if (v1) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) q1.v[c] += alpha * R(d1.v[c]);
+                        TLb[i1] = q1;
+                        const int fam = row_family(i1 % NROW());
+                        if (row_valid(i1 / NROW(), fam)) {
+                            musum += q1.v[0] * q1.v[2];
+                            if (fam < 2) musum += q1.v[1] * q1.v[3];
+                        }
+                    }
                 }
             }
             tsync();
