@@ -1135,7 +1135,8 @@ static QpResult solve_qp_ipm(const ub_problem_desc_t& P, Workspace& W, std::vect
     struct Dl { double dt[2], dlam[2]; };
     std::vector<std::vector<Dl>> stepv(N + 1);
     const bool trace = std::getenv("ORACLE_TRACE") != nullptr;
-    double last_alpha = 0.0, last_step = INF;
+    double last_alpha = 0.0, last_step = INF, pinf_prev = INF;
+    int stall = 0;
 
     for (int it = 0; it < P.qp_iter_max; ++it) {
         // residuals, barrier weights, base gradient
@@ -1171,11 +1172,26 @@ static QpResult solve_qp_ipm(const ub_problem_desc_t& P, Workspace& W, std::vect
             }
         }
         mu = nsides > 0 ? mu / nsides : 0.0;
-        if (it > 0 && mu <= 2.0 * P.qp_mu_target && rd_max <= P.qp_tol && last_alpha >= 0.5 &&
-            (pinf <= P.qp_tol || last_step <= P.qp_tol)) {
+        const bool central = it > 0 && mu <= 2.0 * P.qp_mu_target && rd_max <= P.qp_tol && last_alpha >= 0.5;
+        if (central && (pinf <= P.qp_tol || last_step <= P.qp_tol)) {
             res.converged = true;
             break;
         }
+        // Hopeless hard equality rows: from the fifth iteration on, at the linear rate the multiplier method shows
+        // (pinf / pinf_prev) the rows cannot reach the tolerance before the iteration cap — three iterations in a row.
+        // Such a QP (rows inconsistent at this linearisation point, e.g. a start state from which the object cannot be
+        // balanced) would creep towards its least-violation point until the cap; it ends here as NOT converged
+        // (DESIGN.md section 4, item 5).
+        {
+            bool hopeless = false;
+            if (it >= 4 && pinf > P.qp_tol && pinf_prev < INF) {
+                const double ratio = pinf / pinf_prev;
+                hopeless = ratio >= 1.0 || double(it) + std::log(P.qp_tol / pinf) / std::log(ratio) > double(P.qp_iter_max);
+            }
+            stall = hopeless ? stall + 1 : 0;
+        }
+        pinf_prev = pinf;
+        if (stall >= 3) break;
         res.iters = it + 1;
         if (!ric.factor(W, M)) {
             res.decrement = std::numeric_limits<double>::quiet_NaN();

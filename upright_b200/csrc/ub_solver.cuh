@@ -225,6 +225,14 @@ struct RuntimeDims {
     __host__ __device__ static constexpr Layout layout() { return Layout{}; }
 };
 
+// pinf * ratio^(iterations left) > tol: the residual of the hard equality rows cannot reach the tolerance before the
+// iteration cap at its present linear rate.  Out of line: two double logarithms that would otherwise sit (and take
+// registers) in the interior-point loop of every kernel.
+static __device__ __noinline__ bool hopeless_rate(double pinf, double pinf_prev, double tol, int it, int iter_max) {
+    const double ratio = pinf / pinf_prev;
+    return ratio >= 1.0 || double(it) + log(tol / pinf) / log(ratio) > double(iter_max);
+}
+
 template <typename F, typename D>
 struct Solver {
     using R = double;
@@ -2441,12 +2449,24 @@ struct Solver {
             return tmax(pv);
         };
         pinf = eq_pass(false);
+        R pinf_prev = tinf<R>();
+        int stall = 0;
         for (int it = 0; it < C.qp_iter_max; ++it) {
             const long long c_it = clock64();
             if (it > 0 && mu <= R(2) * PR.mu_target && rdmax <= PR.qp_tol && last_alpha >= R(0.5) &&
                 (pinf <= PR.qp_tol || last_step <= PR.qp_tol)) {
                 *converged = true;
                 break;
+            }
+            // hopeless hard equality rows (orc::solve_qp_ipm): at the observed linear rate they cannot reach the
+            // tolerance before the iteration cap, three iterations in a row -> the QP ends as not converged
+            {
+                bool hopeless = false;
+                if (!C.soft_poly && it >= 4 && pinf > PR.qp_tol && pinf_prev < tinf<R>())
+                    hopeless = hopeless_rate(pinf, pinf_prev, PR.qp_tol, it, C.qp_iter_max);
+                stall = hopeless ? stall + 1 : 0;
+                pinf_prev = pinf;
+                if (stall >= 3) break;
             }
             if (!pass_factor_predict()) {
                 if constexpr (std::is_same<F, R>::value) {   // validation kernels: as the oracle, a failed factorisation ends the solve
@@ -2469,8 +2489,7 @@ struct Solver {
                     // mean complementarity after the affine step -> centring target (Mehrotra)
                     const R a_aff = a_fwd;
                     R acc = 0;
-#pragma unroll 4
-                    for (int idx = lane; idx < (N + 1) * NROW(); idx += kTS) {   // (unrolled: four records in flight per lane)
+                    for (int idx = lane; idx < (N + 1) * NROW(); idx += kTS) {
                         const int k = idx / NROW(), r = idx % NROW();
                         const int fam = row_family(r);
                         if (!row_valid(k, fam)) continue;
@@ -2504,37 +2523,19 @@ struct Solver {
             }
             // update z, t, lambda; new mean complementarity
             R musum = 0;
-#pragma unroll 4
             for (int idx = lane; idx < (N + 1) * nz; idx += kTS) Zall[idx] += alpha * R(ws[oDZ() + idx]);
-            {   // two records per lane and round, both loaded before either is used (the loop is pure memory latency)
-                const int total = (N + 1) * NROW();
-                QuadR* const TLb = wsr<QuadR>(oTL());
-                const QuadF* const DDb = wsr<QuadF>(oDD());
-                for (int base = 0; base < total; base += 2 * kTS) {
-                    const int i0 = base + lane, i1 = i0 + kTS;
-                    const bool v0 = i0 < total, v1 = i1 < total;
-                    QuadR q0 = TLb[v0 ? i0 : 0], q1 = TLb[v1 ? i1 : 0];
-                    const QuadF d0 = DDb[v0 ? i0 : 0], d1 = DDb[v1 ? i1 : 0];
-                    if (v0) {
+            for (int idx = lane; idx < (N + 1) * NROW(); idx += kTS) {
+                const int k = idx / NROW(), r = idx % NROW();
+                const int fam = row_family(r);
+                QuadR* rec = wsr<QuadR>(oTL()) + idx;
+                QuadR q = *rec;
+                const QuadF dd = wsr<QuadF>(oDD())[idx];
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) q0.v[c] += alpha * R(d0.v[c]);
-                        TLb[i0] = q0;
-                        const int fam = row_family(i0 % NROW());
-                        if (row_valid(i0 / NROW(), fam)) {
-                            musum += q0.v[0] * q0.v[2];
-                            if (fam < 2) musum += q0.v[1] * q0.v[3];
-                        }
-                    }
-                    if (v1) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) q1.v[c] += alpha * R(d1.v[c]);
-                        TLb[i1] = q1;
-                        const int fam = row_family(i1 % NROW());
-                        if (row_valid(i1 / NROW(), fam)) {
-                            musum += q1.v[0] * q1.v[2];
-                            if (fam < 2) musum += q1.v[1] * q1.v[3];
-                        }
-                    }
+                for (int c = 0; c < 4; ++c) q.v[c] += alpha * R(dd.v[c]);
+                *rec = q;
+                if (row_valid(k, fam)) {
+                    musum += q.v[0] * q.v[2];
+                    if (fam < 2) musum += q.v[1] * q.v[3];
                 }
             }
             tsync();
