@@ -48,12 +48,16 @@ struct Layout {
     int bG, bL, bD, bGl, bQ, bsize;
     // shared memory (units of F, per warp)
     int sM, sP, sPv, sFB, sGf, sFv, sFl, sVec, sDst, sDxn, sRv, sScr, sDFC, sUS, sCst, sTL, sDD, sSmZ, sSmX, sSmU, sSmJ, sSmW;
+    int sBar;   // two mbarriers (UB_TMA_STAGE variant)
     int s_total;
     int rw;   // units per double
 };
 // side records of a stage are staged in shared memory (cp.async, one stage ahead) up to this many rows (72 covers cfg5's
 // 68-row stage: +18 % at 1024 instances; cfg3's 164-row stage loses more to the resident warps the buffers cost than it
 // gains, profiles/r2_v6_staging_ab.txt)
+#ifndef UB_TMA_STAGE
+#define UB_TMA_STAGE 0
+#endif
 #ifndef UB_STAGE_ROWS_MAX
 #define UB_STAGE_ROWS_MAX 72
 #endif
@@ -148,6 +152,7 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     L.sSmU = s; s += staged ? ub_round4(nu) : 0;
     L.sSmJ = s; s += staged ? ub_round4(3 * nq) : 0;
     L.sSmW = s; s += ub_round4(nq);
+    L.sBar = s; s += UB_TMA_STAGE ? 4 : 0;
     L.s_total = s;
     return L;
 }
@@ -469,6 +474,64 @@ struct Solver {
     __device__ __forceinline__ void cp_async16(void* dst, const void* src) const {
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
     }
+#if UB_TMA_STAGE
+    // Variant (A/B experiment, profiles/r2_v7_tma_ab.txt): the 16-byte-granular blocks of a stage (factor block, side
+    // records, force bundle) travel as ONE bulk copy each (cp.async.bulk, the non-tensor TMA path) issued by lane 0 and
+    // complete on an mbarrier of this warp; the small vectors stay on cp.async.  A "group" is what the commit-group
+    // mechanism calls one: group g completes on mbarrier g & 1 in phase (g >> 1) & 1; at most two groups are in flight
+    // (every third commit is preceded by a wait that retires the oldest).
+    mutable unsigned gcount = 0, gwaited = 0;
+    uint32_t bar0 = 0;   // shared-memory address of the two mbarriers of this warp
+    __device__ __forceinline__ void bar_init(void* bars) {
+        bar0 = smem_u32(bars);
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        tsync();
+    }
+    // every lane fences its own generic-proxy stores of the previous pass against the async-proxy reads of this one
+    __device__ __forceinline__ void pass_fence() const {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        tsync();
+    }
+    __device__ __forceinline__ void cp_commit() const {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (lane == 0) {
+            unsigned long long st;
+            asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(st) : "r"(bar0 + 8 * (gcount & 1)) : "memory");
+        }
+        ++gcount;
+        if (gcount - gwaited > 2) __trap();   // a barrier would be re-armed before its previous phase was retired
+    }
+    template <int NYOUNGER>
+    __device__ __forceinline__ void cp_wait() const {
+        asm volatile("cp.async.wait_group %0;" ::"n"(NYOUNGER) : "memory");
+        while (gwaited + NYOUNGER < gcount) {
+            const uint32_t bar = bar0 + 8 * (gwaited & 1), parity = (gwaited >> 1) & 1;
+            uint32_t done = 0;
+            int spins = 0;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                if (++spins > (1 << 20)) __trap();   // a lost completion must not hang the GPU
+            } while (!done);
+            ++gwaited;
+        }
+        tsync();
+    }
+    __device__ __forceinline__ void cp_async_bytes(void* dst, const void* src, int bytes) const {
+        if (lane == 0) {
+            const uint32_t bar = bar0 + 8 * (gcount & 1);
+            asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+        }
+    }
+#else
+    __device__ __forceinline__ void bar_init(void*) {}
+    __device__ __forceinline__ void pass_fence() const {}
     __device__ __forceinline__ void cp_commit() const { asm volatile("cp.async.commit_group;" ::: "memory"); }
     template <int NYOUNGER>
     __device__ __forceinline__ void cp_wait() const {
@@ -481,6 +544,7 @@ struct Solver {
         char* d = reinterpret_cast<char*>(dst);
         for (int i = lane; i < bytes / 16; i += kTS) cp_async16(d + 16 * i, s + 16 * i);
     }
+#endif
     // issue (no commit) the copy of the records of stage k; k outside [0, N] issues nothing
     __device__ __forceinline__ void tt_issue(int k, bool with_steps) const {
         if constexpr (kStageTT) {
@@ -1991,10 +2055,11 @@ struct Solver {
         bool ok = true;
         for (int i = lane; i < nx; i += kTS) sPv[i] = F(0);
         tsync();
+        pass_fence();
         if constexpr (kStageFB) {
             tt_issue(NN(), false);
             sm_issue(NN(), false, true);
-            cp_commit();
+            if constexpr (kStageTT) cp_commit();            // (the wide-stage kernels only issue L2 prefetches here)
         }
         for (int k = NN(); k >= 0; --k) {
             long long f0 = clock64();
@@ -2025,7 +2090,7 @@ struct Solver {
                 tt_issue(k - 1, false);
                 sm_issue(k - 1, false, true);
                 c_issue(k - 1);
-                cp_commit();
+                if constexpr (kStageTT) cp_commit();
             }
             long long f3 = clock64();
             t_f1 += f3 - f2;
@@ -2048,6 +2113,7 @@ struct Solver {
             }
             tsync();
         }
+        if constexpr (kStageTT) cp_wait<0>();               // retire the (empty) group issued at k = 0
         return ok;
     }
 
@@ -2059,6 +2125,7 @@ struct Solver {
         for (int i = lane; i < nx; i += kTS) sPv[i] = F(0);
         tsync();
         const int nbx = NBOXU() + nx;
+        pass_fence();
         // cp.async group schedule: [records, gradient, force bundle](k) is committed before FAC(k); every wait leaves
         // exactly one younger group in flight (none at the terminal stage)
         if constexpr (kStageFB) {
@@ -2248,6 +2315,7 @@ struct Solver {
         F amax = F(1), rnd = F(0);
         for (int i = lane; i < nz; i += kTS) dst[i] = F(0);
         tsync();
+        pass_fence();
         // cp.async group schedule: FAC(k) is committed before [records, vectors, force bundle](k); every wait leaves
         // exactly one younger group in flight (none for the records of the terminal stage)
         if constexpr (kStageFB) {
@@ -2910,6 +2978,7 @@ __global__ void __launch_bounds__(512, 1) solve_batch_kernel(const __grid_consta
     S.sSmU = sm + Lk.sSmU;
     S.sSmJ = sm + Lk.sSmJ;
     S.sSmW = sm + Lk.sSmW;
+    S.bar_init(sm + Lk.sBar);
     if (A.queue == nullptr) {   // static mode (test aid)
         S.run(A, slot);
         return;

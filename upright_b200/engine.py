@@ -17,7 +17,7 @@ from . import bindings as B
 LAYOUT_FIELDS = ("Z", "DZ", "GAP", "LG", "LC", "LR", "LJP", "LHO", "LJO", "DF", "RHOE", "YE", "RHOT", "YT", "TL", "DD",
                  "GP", "VE", "FAC", "WF", "FBB", "XN", "UN", "XW", "UW", "TG", "BD", "LIA", "LJA", "XO", "DXO", "TGQ", "LRO", "LJQ", "total",
                  "bG", "bL", "bD", "bGl", "bQ", "bsize", "sM", "sP", "sPv", "sFB", "sGf", "sFv", "sFl", "sVec", "sDst", "sDxn",
-                 "sRv", "sScr", "sDFC", "sUS", "sCst", "sTL", "sDD", "sSmZ", "sSmX", "sSmU", "sSmJ", "sSmW", "s_total", "rw")
+                 "sRv", "sScr", "sDFC", "sUS", "sCst", "sTL", "sDD", "sSmZ", "sSmX", "sSmU", "sSmJ", "sSmW", "sBar", "s_total", "rw")
 # workspace blocks that hold doubles whatever the kernels' matrix type (ub_solver.cuh: compute_layout)
 LAYOUT_DOUBLE_BLOCKS = ("Z", "GAP", "LG", "LR", "RHOE", "YE", "RHOT", "YT", "TL", "GP", "VE")
 
