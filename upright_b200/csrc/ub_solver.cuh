@@ -131,15 +131,14 @@ __host__ __device__ constexpr Layout compute_layout(const LayoutDims d) {
     const int us = (d.ngrp == 1 && d.nb > 1) ? rw * d.nc * 2 * 6 * d.nf : 0;
     L.sM = s;   s += ub_round4(ub_max(ub_max(nr * (nr | 1), 2 * fstride), us));
     L.sP = s;   s += ub_round4(nx * nx);
-    L.sPv = s;  s += ub_round4(nx);
     L.sFB = s;  s += L.bsize;                               // force bundle of the stage (C rows first, G in place)
     L.sGf = s;  s += ub_round4(d.neq);                      // g_lambda in F for the Schur update
     L.sFv = s;  s += ub_round4(rw * d.neq);                 // (R) v = e + y / rho, then rhs
     L.sFl = s;  s += ub_round4(rw * d.neq);                 // (R) lambda / scratch
     L.sVec = s; s += ub_round4(rw * nz);                    // (R) stage gradient [j; f; x]
-    L.sDst = s; s += ub_round4(nz);                         // stage direction [dj; df; dx]
-    L.sDxn = s; s += ub_round4(nx);
-    L.sRv = s;  s += ub_round4(nr + 1);                     // Riccati right-hand side [m_j; m_x]
+    // the forward sweeps (B, D) and the backward sweeps (A, C) never run at the same time: their vectors share storage
+    L.sDst = s; L.sRv = s; s += ub_round4(ub_max(nz, nr + 1));   // stage direction [dj; df; dx] | Riccati right-hand side [m_j; m_x]
+    L.sDxn = s; L.sPv = s; s += ub_round4(nx);                   // next state direction | cost-to-go gradient
     L.sScr = s; s += ub_round4(rw * ub_max(ub_max(d.neq, d.nobs), ub_max(d.nterm, 16)));   // (R) per-row scratch
     L.sDFC = s; s += ub_round4(d.nc * 2 * 6 * d.nf);        // d g / d f per contact and side: [c][side][6][nf] (constant over the solve)
     L.sUS = L.sM;
