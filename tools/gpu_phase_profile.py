@@ -18,7 +18,8 @@ for _ in range(2):
     out = mpc.solve_device(x0, tg, bp)
 torch.cuda.synchronize()
 print("normal ms", mpc.last_solve_ms())
-mpc.set_option("stop_after", 9)
+BASE = 10 if len(sys.argv) > 3 and sys.argv[3] == "persistent" else 0   # persistent: counters of the product grid
+mpc.set_option("stop_after", BASE + 9)
 out = mpc.solve_device(x0, tg, bp)
 torch.cuda.synchronize()
 st = out["stats"].double().cpu().numpy()
@@ -29,7 +30,7 @@ for i in range(1, 8):
     print(f"  {names[i]:14s} mean {st[:, i].mean() / 1e6:8.3f} Mcyc  ({100 * st[:, i].mean() / tot.mean():5.1f} %)  per-iter {st[:, i].mean() / st[:, 0].mean() / 1e3:8.1f} kcyc")
 print("  total per warp %.2f Mcyc" % (tot.mean() / 1e6))
 
-mpc.set_option("stop_after", 8)
+mpc.set_option("stop_after", BASE + 8)
 out = mpc.solve_device(x0, tg, bp)
 torch.cuda.synchronize()
 st = out["stats"].double().cpu().numpy()
@@ -38,3 +39,6 @@ print("whole-solve profile (Mcyc per warp): total %.2f | linearise %.2f (%.0f %%
       "init (Df + base performance) %.2f (%.0f %%)" % (tot / 1e6, st[:, 1].mean() / 1e6, 100 * st[:, 1].mean() / tot, st[:, 4].mean() / 1e6,
                                                      100 * st[:, 4].mean() / tot, st[:, 2].mean() / 1e6, 100 * st[:, 2].mean() / tot,
                                                      st[:, 5].mean() / 1e6, 100 * st[:, 5].mean() / tot))
+print("  waiting at the alignment meetings %.2f Mcyc (%.0f %%) | set-up of the interior-point iteration %.2f Mcyc (%.0f %%) | per iteration %.3f Mcyc | "
+      "kernel ms %.3f" % (st[:, 6].mean() / 1e6, 100 * st[:, 6].mean() / tot, st[:, 7].mean() / 1e6, 100 * st[:, 7].mean() / tot,
+                          st[:, 4].mean() / 1e6 / max(1e-9, st[:, 0].mean()), mpc.last_solve_ms()))

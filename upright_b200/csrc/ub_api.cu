@@ -394,7 +394,7 @@ ub::LaunchFn<T> select_kernel(const ub_problem* p) {
 template <typename T>
 size_t problem_smem_bytes() {
     const size_t f = (sizeof(ub::DevProblem<T>) + 15) / 16 * 16;
-    return sizeof(T) == 8 ? f : f + (sizeof(ub::DevProblem<double>) + 15) / 16 * 16;
+    return (sizeof(T) == 8 ? f : f + (sizeof(ub::DevProblem<double>) + 15) / 16 * 16) + sizeof(ub::CtaAlign);
 }
 
 // Launch geometry: warps (= instances) per CTA and CTAs per SM.  The kernels are latency bound, so what counts is the
@@ -427,6 +427,9 @@ Geometry launch_geometry(const ub_problem* p, int B = 0) {
     }
     return g;
 }
+// option stop_after: 1, 2, 8, 9 run the static test grid (one slot per instance); 18 / 19 export the cycle counters of
+// 8 / 9 from the persistent grid (work queue, alignment: the conditions of a product launch)
+static bool static_mode(const ub_problem* p) { return p->stop_after != 0 && p->stop_after < 10; }
 // Workspace slots of a batch of B: the persistent grid holds one slot per resident warp; the static test mode
 // (option stop_after != 0) one per instance.
 template <typename T>
@@ -437,7 +440,7 @@ int64_t workspace_slots(const ub_problem* p, int B) {
 }
 template <typename T>
 int64_t workspace_bytes(const ub_problem* p, int B) {
-    const int64_t slots = p->stop_after != 0 ? B : workspace_slots<T>(p, B);
+    const int64_t slots = static_mode(p) ? B : workspace_slots<T>(p, B);
     return slots * Pick<T>::layout(p).total * int64_t(sizeof(T)) + 256;  // + the work-queue counter
 }
 
@@ -446,10 +449,10 @@ int launch_solve(ub_problem* p, ub::BatchArgs<T> A, cudaStream_t stream) {
     const ub::Layout& L = Pick<T>::layout(p);
     const size_t pbytes = problem_smem_bytes<T>();
     const size_t per_warp = size_t(L.s_total) * sizeof(T);
-    const int wpc = p->stop_after == 0 ? launch_geometry<T>(p, A.B).wpc : launch_geometry<T>(p).wpc;
+    const int wpc = !static_mode(p) ? launch_geometry<T>(p, A.B).wpc : launch_geometry<T>(p).wpc;
     const size_t smem = pbytes + per_warp * wpc;
     if (smem > size_t(p->max_smem_optin)) return fail(UB_E_INVALID, "problem too large for shared memory");
-    const bool persistent = p->stop_after == 0;
+    const bool persistent = !static_mode(p);
     const int64_t slots = persistent ? workspace_slots<T>(p, A.B) : A.B;
     if (persistent) {
         // the counter sits behind the last slot
@@ -489,10 +492,16 @@ int solve_device(ub_problem* p, int B, const void* x0, const void* target, const
     A.ws = static_cast<T*>(ws);
     A.B = B;
     A.warm = (flags & UB_WARM_START) ? 1 : 0;
-    A.stop_after = p->stop_after;
+    A.stop_after = p->stop_after >= 10 ? p->stop_after - 10 : p->stop_after;   // 18 / 19: profile counters of the persistent grid
     A.gain_stages = gain_stages < 0 ? Pick<T>::host(p).N : gain_stages;
     A.nxt = Pick<T>::host(p).nx + Pick<T>::host(p).nxo;
     A.tstride = Pick<T>::host(p).ori ? 7 : 3;
+    // Phase alignment of the warps of a CTA (ub::CtaAlign) pays once the warps have drifted apart, i.e. from the second
+    // full wave of the persistent grid on (cfg2, 16384 instances: 38.7 -> 31.4 ms; cfg3, 4096: 89.5 -> 77.2 ms); below
+    // two waves the common start keeps them close anyway and the meetings only cost their waiting time (cfg2, 4096:
+    // 10.9 -> 11.2 ms; profiles/r2_v8_alignment.txt).  UB_ALIGN_GROUP = warps per group overrides (0: off).
+    A.align = int64_t(B) >= 2 * workspace_slots<T>(p, B) ? 16 : 0;
+    if (const char* env = std::getenv("UB_ALIGN_GROUP")) A.align = std::max(0, std::atoi(env));
     A.ngather = gather ? p->n_gather : 0;   // the caller's device-mode solves only (not the host path, not the closed loop)
     A.gather_row = p->gather_row;
     for (int i = 0; i < UB_MAX_GATHER; ++i) {

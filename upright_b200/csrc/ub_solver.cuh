@@ -55,6 +55,19 @@ struct Layout {
 // side records of a stage are staged in shared memory (cp.async, one stage ahead) up to this many rows (72 covers cfg5's
 // 68-row stage: +18 % at 1024 instances; cfg3's 164-row stage loses more to the resident warps the buffers cost than it
 // gains, profiles/r2_v6_staging_ab.txt)
+// cycle counters of the phases (tools/gpu_phase_profile.py): compiled in only for the profiling variant
+// (python tools/build_variant.py profile -DUB_PROFILE=1) — in the product build they cost registers and, once spilled, a
+// local-memory read-modify-write per stage
+#ifndef UB_PROFILE
+#define UB_PROFILE 0
+#endif
+#if UB_PROFILE
+#define UB_CLK() clock64()
+#define UB_ACC(var, expr) (var) += (expr)
+#else
+#define UB_CLK() 0LL
+#define UB_ACC(var, expr) ((void)0)
+#endif
 #ifndef UB_TMA_STAGE
 #define UB_TMA_STAGE 0
 #endif
@@ -181,6 +194,7 @@ struct BatchArgs {
     int n_slots;      // workspace slots (= warps that may work); B in the static mode
     int nxt;          // columns of x0 / X / Xin: robot state + dynamic-obstacle states
     int tstride;      // columns of a target row: 3, or 7 with the desired quaternion [x y z w]
+    int align;        // phase-align the warps of a CTA at every interior-point iteration: warps per group, 0 = off (CtaAlign)
     // Multi-GPU gather fused into the solve: besides X / U of this rank, every solved instance is
     // stored straight into the gathered buffers of the peer GPUs (peer-mapped pointers, NVLink P2P stores from the
     // epilogue) at row gather_row + b — the all-gather happens instance by instance while the rest of the batch is
@@ -237,9 +251,64 @@ static __device__ __noinline__ bool hopeless_rate(double pinf, double pinf_prev,
     return ratio >= 1.0 || double(it) + log(tol / pinf) / log(ratio) > double(iter_max);
 }
 
+// Phase alignment of the warps of a CTA: the interior-point loop is ~200 KB of SASS against a
+// 32 KB instruction cache, and warps that walk it at the same time share what is fetched — measured 1.36x between a
+// batch whose instances all take the same number of iterations and a mixed one (profiles/r2_v8_alignment_probe.txt).
+// Every warp therefore meets the others of its CTA at the top of each interior-point iteration (a software barrier in
+// shared memory: 16 warps, 7 meetings per solve).  Warps between two solves (line search, output, next linearisation)
+// arrive when they reach their next first iteration; warps out of work keep attending until all are.  A meeting that
+// does not complete within the spin limit switches the alignment off for the rest of the launch (never a hang).
+struct CtaAlign {
+    // one packed word per alignment group (up to four groups per CTA; group = warps with the same index modulo the
+    // number of groups, i.e. warps of the same SM sub-partition):
+    //   bits 0-5 arrivals of the current meeting | 6-11 warps of the group that still take instances | 12-17 warps of the
+    //   group | bit 18 "all out of work" (published by the last arriver) | bit 19 alignment switched off | 20-31 meeting
+    //   counter
+    static constexpr unsigned kDone = 1u << 18, kOff = 1u << 19;
+    unsigned word[4];
+};
+
 template <typename F, typename D>
 struct Solver {
     using R = double;
+    unsigned* al = nullptr;   // packed word of this warp's alignment group; null: no alignment
+    // returns true once every warp of the group is out of work (or the alignment has been switched off)
+    __device__ __forceinline__ bool align_wait() const {
+        if (al == nullptr) return true;
+        __syncwarp();
+        unsigned w = 0;
+        if (lane == 0) {
+            volatile unsigned* vw = al;
+            w = *vw;
+            if ((w & CtaAlign::kOff) == 0) {
+                const unsigned old = atomicAdd(al, 1u);
+                const unsigned g = old >> 20;
+                if ((old & 0x3fu) + 1u >= ((old >> 12) & 0x3fu)) {
+                    // last arriver: nobody else touches the word now (every other warp of the group waits)
+                    const unsigned working = (old >> 6) & 0x3fu;
+                    w = (((g + 1u) & 0xfffu) << 20) | (old & (CtaAlign::kOff | (0x3fu << 12) | (0x3fu << 6))) |
+                        (working == 0u ? CtaAlign::kDone : 0u);
+                    __threadfence_block();
+                    *vw = w;
+                } else {
+                    int spins = 0;
+                    for (;;) {
+                        w = *vw;
+                        if ((w >> 20) != g || (w & CtaAlign::kOff)) break;
+                        __nanosleep(40);
+                        if (++spins > (1 << 20)) {   // ~0.1 s: give the alignment up, never hang
+                            atomicOr(al, CtaAlign::kOff);
+                            w = *vw;
+                            break;
+                        }
+                    }
+                }
+                __threadfence_block();
+            }
+        }
+        w = __shfl_sync(FULL, w, 0);
+        return (w & (CtaAlign::kDone | CtaAlign::kOff)) != 0u;
+    }
     static constexpr int kTS = WARP;
     static constexpr int RW = int(sizeof(R) / sizeof(F));
     const DevProblem<F>& P;    // shared-memory copy: arrays indexed per lane
@@ -359,6 +428,7 @@ struct Solver {
     // passes, line search; and inside the factor pass: gradient, matrix build, force block, factorisation
     long long t_lin = 0, t_fac = 0, t_swp = 0, t_side = 0, t_ls = 0;
     long long t_g = 0, t_f1 = 0, t_f2 = 0, t_f3 = 0;
+    long long t_al = 0, t_qi = 0;   // waiting at the alignment meetings; set-up of the interior-point iteration
 
     __device__ Solver(const DevProblem<F>& P_, const DevProblem<F>& C_, const DevProblem<R>& PR_, const Layout& L_, int lane_)
         : P(P_), C(C_), PR(PR_), L(L_), lane(lane_) {}
@@ -2061,7 +2131,7 @@ struct Solver {
             if constexpr (kStageTT) cp_commit();            // (the wide-stage kernels only issue L2 prefetches here)
         }
         for (int k = NN(); k >= 0; --k) {
-            long long f0 = clock64();
+            long long f0 = UB_CLK();
             if constexpr (kStageTT) cp_wait<0>();           // side records, vectors and C rows of stage k are staged
             else if (k < NN() && NEQ() > 0) load_C(k);
             stage_gradient(k, false, F(0));
@@ -2071,8 +2141,8 @@ struct Solver {
                 R* ve = wsr<R>(oVE()) + k * NEQ();
                 for (int i = lane; i < NEQ(); i += kTS) ve[i] = sFv[i];
             }
-            long long f1 = clock64();
-            t_g += f1 - f0;
+            long long f1 = UB_CLK();
+            UB_ACC(t_g, f1 - f0);
             // the forces go first: their elimination uses the (still idle) stage-matrix buffer as scratch
             bool fok = true;
             if (k < NN() && NFC() > 0) {
@@ -2080,8 +2150,8 @@ struct Solver {
                 fok = force_block_factor(k);
                 if (!fok && nan_reason == 0) nan_reason = 6;
             }
-            long long f2 = clock64();
-            t_f2 += f2 - f1;
+            long long f2 = UB_CLK();
+            UB_ACC(t_f2, f2 - f1);
             if (k < NN()) assign_dynamics_hessian();
             build_stage_matrix(k, k < NN());
             if constexpr (kStageFB) {                       // next stage's records / vectors / C rows arrive during the factorisation
@@ -2091,8 +2161,8 @@ struct Solver {
                 c_issue(k - 1);
                 if constexpr (kStageTT) cp_commit();
             }
-            long long f3 = clock64();
-            t_f1 += f3 - f2;
+            long long f3 = UB_CLK();
+            UB_ACC(t_f1, f3 - f2);
             if (k < NN()) {
                 // reduced right-hand side [m_j; m_x]; G' g_lambda joins in the Schur update
                 for (int i = lane; i < nq; i += kTS) sRv[i] = F(sVec[i]);
@@ -2103,7 +2173,7 @@ struct Solver {
                 F* Fk = ws + oFAC() + k * FSTRIDE();
                 // factor, forward substitution (w in sRv[0, nq)), p -> sPv, P -> sP, factor block -> workspace
                 ok &= stage_factor_blocked(sRv, Fk, NFC() > 0 ? NEQ() : 0);
-                t_f3 += clock64() - f3;
+                UB_ACC(t_f3, UB_CLK() - f3);
                 F* Wk = ws + oWF() + k * nq;
                 for (int j = lane; j < nq; j += kTS) Wk[j] = sRv[j];
             } else {
@@ -2406,6 +2476,7 @@ struct Solver {
         const int nu = NU(), nz = NZ(), N = NN();
         *converged = false;
         *finite = true;
+        const long long c_qi = UB_CLK();
         // dynamics-feasible start: du = 0, dx_0 = 0, dx_{k+1} = A dx_k + gap_k
         R* Zall = wsr<R>(oZ());
         for (int idx = lane; idx < (N + 1) * nz; idx += kTS) Zall[idx] = R(0);
@@ -2516,10 +2587,14 @@ struct Solver {
             return tmax(pv);
         };
         pinf = eq_pass(false);
+        UB_ACC(t_qi, UB_CLK() - c_qi);
         R pinf_prev = tinf<R>();
         int stall = 0;
         for (int it = 0; it < C.qp_iter_max; ++it) {
-            const long long c_it = clock64();
+            const long long c_al = UB_CLK();
+            align_wait();   // meet the other warps of the CTA: same code at the same time (see CtaAlign)
+            const long long c_it = UB_CLK();
+            UB_ACC(t_al, c_it - c_al);
             if (it > 0 && mu <= R(2) * PR.mu_target && rdmax <= PR.qp_tol && last_alpha >= R(0.5) &&
                 (pinf <= PR.qp_tol || last_step <= PR.qp_tol)) {
                 *converged = true;
@@ -2544,8 +2619,8 @@ struct Solver {
                 break;
             }
             iters = it + 1;
-            long long c2 = clock64();
-            t_fac += c2 - c_it;
+            long long c2 = UB_CLK();
+            UB_ACC(t_fac, c2 - c_it);
             R target_mu = PR.mu_target;
             R alpha = R(1);
             // predictor (pass 0) and corrector (pass 1) share ONE inlined copy of the forward pass
@@ -2568,15 +2643,15 @@ struct Solver {
                     const R mu_aff = tsum(acc) / R(nsides);
                     const R ratio = mu_aff / mu;
                     target_mu = max(ratio * ratio * ratio * mu, PR.mu_target);
-                    long long c3 = clock64();
-                    t_swp += c3 - c2;
+                    long long c3 = UB_CLK();
+                    UB_ACC(t_swp, c3 - c2);
                     c2 = c3;
                     pass_backward_corrector(F(target_mu));
                 }
                 a_fwd = pass_forward(pass == 1, pass == 1 ? F(target_mu) : F(0), &rnd_gap);
             }
             if (nsides > 0) alpha = min(R(1), R(0.995) * a_fwd);
-            t_side += clock64() - c2;
+            UB_ACC(t_side, UB_CLK() - c2);
             // the step must be finite before it is applied
             R stepmax = 0;
             for (int idx = lane; idx < (N + 1) * nz; idx += kTS) stepmax = max(stepmax, fabs(alpha * R(ws[oDZ() + idx])));
@@ -2682,8 +2757,8 @@ struct Solver {
     __device__ void run(const BatchArgs<F>& A, int b) {
         constexpr int nq = D::nq, nx = D::nx;
         const int nu = NU(), N = NN(), nz = NZ();
-        t_lin = t_fac = t_swp = t_side = t_ls = t_f1 = t_f2 = t_f3 = t_g = 0;
-        const long long t_run0 = clock64();
+        t_lin = t_fac = t_swp = t_side = t_ls = t_f1 = t_f2 = t_f3 = t_g = t_al = t_qi = 0;
+        const long long t_run0 = UB_CLK();
         long long t_init = 0;
         nan_reason = 0;
         // initial guess: DefaultInitializer = zero input, state held
@@ -2721,7 +2796,7 @@ struct Solver {
         tsync();
         if (NEQ() > 0) build_Df();
         Perf<F> base = performance(X, U);
-        t_init = clock64() - t_run0;
+        UB_ACC(t_init, UB_CLK() - t_run0);
         int status = UB_STATUS_CONVERGED, qp_iters = 0, sqp_done = 0;
         F alpha = 0;
         R qp_res = 0;
@@ -2730,7 +2805,7 @@ struct Solver {
         const R* Zall = wsr<R>(oZ());
         for (int it = 0; it < max(1, C.sqp_iters); ++it) {
             ++sqp_done;
-            long long c0 = clock64();
+            long long c0 = UB_CLK();
             if (NXO() > 0) {
                 // Newton step of the obstacle states = exact constant-acceleration rollout of the observation - iterate
                 const F* o0 = ws + oXO();
@@ -2746,7 +2821,7 @@ struct Solver {
                 tsync();
             }
             linearize();
-            t_lin += clock64() - c0;
+            UB_ACC(t_lin, UB_CLK() - c0);
             if (A.stop_after == 1) break;
             bool conv, fin;
             qp_iters += solve_qp(&conv, &qp_res, &fin);
@@ -2784,7 +2859,7 @@ struct Solver {
                 }
             }
             desc = tsum(desc);
-            const long long c_ls = clock64();
+            const long long c_ls = UB_CLK();
             // filter line search (ocs2 FilterLinesearch [EXT])
             const F vb = base.violation();
             bool accepted = false;
@@ -2812,7 +2887,7 @@ struct Solver {
                 if (accepted) break;
                 alpha *= C.alpha_decay;
             }
-            t_ls += clock64() - c_ls;
+            UB_ACC(t_ls, UB_CLK() - c_ls);
             if (!accepted) {
                 status = UB_STATUS_LS_FAILED;
                 alpha = F(0);
@@ -2885,9 +2960,11 @@ struct Solver {
                 if (A.stop_after == 8) {  // profile mode: linearisation, line search, whole solve, interior-point loop
                     s[1] = F(t_lin);
                     s[2] = F(t_ls);
-                    s[3] = F(clock64() - t_run0);
+                    s[3] = F(UB_CLK() - t_run0);
                     s[4] = F(t_fac + t_swp + t_side);
                     s[5] = F(t_init);
+                    s[6] = F(t_al);
+                    s[7] = F(t_qi);
                 }
                 if (A.stop_after == 9) {  // profile mode: phase cycle counters replace stats[1..7]
                     s[1] = F(t_g);
@@ -2914,7 +2991,8 @@ __global__ void __launch_bounds__(512, 1) solve_batch_kernel(const __grid_consta
     // (one and the same for the fp64 validation kernels)
     constexpr bool kSame = std::is_same<F, double>::value;
     constexpr size_t offF = (sizeof(DevProblem<F>) + 15) / 16 * 16;
-    constexpr size_t off = offF + (kSame ? 0 : (sizeof(DevProblem<double>) + 15) / 16 * 16);
+    constexpr size_t offP = offF + (kSame ? 0 : (sizeof(DevProblem<double>) + 15) / 16 * 16);
+    constexpr size_t off = offP + sizeof(CtaAlign);   // (16 bytes: the launcher counts them in)
     DevProblem<F>* Ps = reinterpret_cast<DevProblem<F>*>(smem_raw);
     DevProblem<double>* Psr = kSame ? reinterpret_cast<DevProblem<double>*>(smem_raw) : reinterpret_cast<DevProblem<double>*>(smem_raw + offF);
     {
@@ -2928,6 +3006,16 @@ __global__ void __launch_bounds__(512, 1) solve_batch_kernel(const __grid_consta
             uint32_t* d2 = reinterpret_cast<uint32_t*>(Psr);
             for (int i = threadIdx.x; i < nw2; i += blockDim.x) d2[i] = s2[i];
         }
+    }
+    CtaAlign* al = reinterpret_cast<CtaAlign*>(smem_raw + offP);
+    const int cta_members = min(teams_per_cta, A.n_slots - int(blockIdx.x) * teams_per_cta);
+    // alignment groups: A.align = warps per group (0: off); at most four groups
+    int n_groups = A.align > 0 ? (cta_members + A.align - 1) / A.align : 1;
+    n_groups = max(1, min(4, n_groups));
+    if (threadIdx.x < 4) {
+        int members = 0;
+        for (int t = int(threadIdx.x); t < cta_members; t += n_groups) ++members;
+        al->word[threadIdx.x] = (unsigned(members) << 12) | (unsigned(members) << 6);   // all members still working
     }
     __syncthreads();
     const int team = int(threadIdx.x) / WARP, lane = threadIdx.x % WARP;
@@ -2982,6 +3070,12 @@ __global__ void __launch_bounds__(512, 1) solve_batch_kernel(const __grid_consta
         S.run(A, slot);
         return;
     }
+    if (A.align > 0) {
+        const int gid = team % n_groups;
+        int members = 0;
+        for (int t = gid; t < cta_members; t += n_groups) ++members;
+        if (members > 1) S.al = &al->word[gid];
+    }
     for (;;) {
         int b = 0;
         if (lane == 0) b = atomicAdd(A.queue, 1);
@@ -2989,6 +3083,13 @@ __global__ void __launch_bounds__(512, 1) solve_batch_kernel(const __grid_consta
         if (b >= A.B) break;
         S.run(A, b);
         S.tsync();
+    }
+    // out of work: keep attending the meetings of the CTA until every warp is
+    if (S.al != nullptr) {
+        if (lane == 0) atomicSub(S.al, 1u << 6);
+        __syncwarp();
+        while (!S.align_wait()) {
+        }
     }
 }
 
