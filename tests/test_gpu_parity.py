@@ -948,3 +948,36 @@ def test_robust_planner_shape_n100():
             assert np.abs(out["X"] - ref["X"]).max() <= tol and np.abs(out["U"] - ref["U"]).max() <= tol
         else:
             assert max(ex, eu) <= tol
+
+
+def test_phase_alignment_does_not_change_results():
+    """The meetings that keep the warps of a CTA in step (ub::CtaAlign; on by default from two waves of the persistent
+    grid) only order the work in time: forced on and forced off give bitwise identical trajectories, on a batch of
+    several waves with mixed iteration counts and with the batch tail (warps out of work that keep attending)."""
+    import os
+    name = "cfg2_thing_demo"
+    mpc, desc, meta = engine(name, "f32")
+    B = 6100                                   # 2.6 waves of the 2368 resident warps of a B200, not a multiple of anything
+    b = batch_for(name, B, 31)
+    dev = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")  # noqa: E731
+    x0, tg, bp = dev(b["x0"]), dev(b["target"]), dev(b["body_params"])
+    outs = {}
+    old = os.environ.get("UB_ALIGN_GROUP")
+    try:
+        for mode in ("0", "16", "4"):
+            os.environ["UB_ALIGN_GROUP"] = mode
+            o = mpc.solve_device(x0, tg, bp)
+            torch.cuda.synchronize()
+            outs[mode] = {k: o[k].clone() for k in ("X", "U", "status")}
+    finally:
+        if old is None:
+            os.environ.pop("UB_ALIGN_GROUP", None)
+        else:
+            os.environ["UB_ALIGN_GROUP"] = old
+    o = mpc.solve_device(x0, tg, bp)           # default: on for this batch size
+    torch.cuda.synchronize()
+    assert (outs["0"]["status"] == 0).float().mean() > 0.98
+    for mode in ("16", "4"):
+        for k in ("X", "U", "status"):
+            assert torch.equal(outs["0"][k], outs[mode][k]), (mode, k)
+    assert torch.equal(outs["0"]["X"], o["X"]) and torch.equal(outs["0"]["U"], o["U"])
