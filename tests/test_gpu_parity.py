@@ -981,3 +981,39 @@ def test_phase_alignment_does_not_change_results():
         for k in ("X", "U", "status"):
             assert torch.equal(outs["0"][k], outs[mode][k]), (mode, k)
     assert torch.equal(outs["0"]["X"], o["X"]) and torch.equal(outs["0"]["U"], o["U"])
+
+
+def test_wrench_cone_verification_of_planned_trajectories():
+    """SURVEY.md §8f rank 4 (process_sim_runs.py:208-246, exact parameters): the contact-wrench-cone face form of the
+    arrangement checked at every knot of a batch of PLANNED trajectories — wrenches from the probe kernel, the check one
+    GEMM on the GPU — against the same quantity computed knot by knot with the oracle; planned motions stay inside the
+    cone up to the slack of the soft rows, an unplanned violent motion does not."""
+    from upright_b200.robust import WrenchConeVerifier
+    name = "cfg2_thing_demo"
+    mpc, desc, meta = engine(name, "f32")
+    B = 64
+    b = workload.sample_batch(name, desc, meta, B, 5, lambda x: mpc.eval("end_effector_position", x, np.zeros((x.shape[0], mpc.nu))),
+                              vary_bodies=False)
+    out = mpc.solve(b["x0"], b["target"], None)
+    ver = WrenchConeVerifier(mpc, desc)
+    V = ver.violation(out["X"][:, :-1])                     # the rows exist at the intermediate knots
+    assert V.shape == (B, desc.N)
+    # parity with the CPU evaluation of the same face form
+    for i in (0, 17, 63):
+        for k in (0, 7, 19):
+            w = -oracle.linearize(desc, out["X"][i, k], np.zeros(desc.nu))["g"]
+            assert abs(float((ver.A @ w).max()) - V[i, k]) < 1e-9
+    # Planned knots (k >= 1; knot 0 is the observation: the seeded start states tilt the tray, which frictionless
+    # contacts cannot carry) approach the cone as the SQP iterations converge (gravity row of the wrench: 4.0)
+    med = [np.median(V[:, 1:].max(1))]
+    for _ in range(3):
+        out = mpc.solve(b["x0"], b["target"], None, X=out["X"], U=out["U"], warm=True)
+        med.append(np.median(ver.violation(out["X"][:, :-1])[:, 1:].max(1)))
+    print("wrench cone: median over instances of the largest planned violation, per SQP iteration:", ["%.3e" % m for m in med])
+    assert med[1] < 0.5 * med[0] and med[2] < 0.5 * med[1] and med[3] < 0.05
+    # an unplanned motion: 1 g of base acceleration at every knot
+    Xbad = out["X"][:4, :-1].copy()
+    Xbad[:, :, 2 * desc.nq:] = 0.0
+    Xbad[:, :, 2 * desc.nq] = 9.81
+    Vbad = ver.violation(Xbad)
+    assert np.median(Vbad) > 2.0 and Vbad.min() > 0.5
