@@ -2118,6 +2118,22 @@ struct Solver {
     // Pass A (backward): per stage form the predictor gradient (sigma = 0), keep it in GP for the corrector,
     // build the reduced stage matrix, eliminate the forces, factor and do the backward vector step with the
     // factor still in shared memory.
+    // t, lambda of stage k += pend_alpha * (dt, dlam) of the last step (records and steps of the stage are staged or
+    // read from the workspace); the updated records go back to the workspace for the later passes
+    R pend_alpha = R(0);
+    __device__ __forceinline__ void apply_pending_update(int k) {
+        if (pend_alpha == R(0)) return;
+        const R a = pend_alpha;
+        for (int r = lane; r < NROW(); r += kTS) {
+            QuadR q = recs_tl(k)[r];
+            const QuadF dd = recs_dd(k)[r];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) q.v[c] += a * R(dd.v[c]);
+            if constexpr (kStageTT) reinterpret_cast<QuadR*>(sTL)[r] = q;
+            *side_tl(k, r) = q;
+        }
+        tsync();
+    }
     __device__ bool pass_factor_predict() {
         constexpr int nq = D::nq, nx = D::nx;
         const int nu = NU(), nz = NZ();
@@ -2126,7 +2142,7 @@ struct Solver {
         tsync();
         pass_fence();
         if constexpr (kStageFB) {
-            tt_issue(NN(), false);
+            tt_issue(NN(), true);
             sm_issue(NN(), false, true);
             if constexpr (kStageTT) cp_commit();            // (the wide-stage kernels only issue L2 prefetches here)
         }
@@ -2134,6 +2150,7 @@ struct Solver {
             long long f0 = UB_CLK();
             if constexpr (kStageTT) cp_wait<0>();           // side records, vectors and C rows of stage k are staged
             else if (k < NN() && NEQ() > 0) load_C(k);
+            apply_pending_update(k);
             stage_gradient(k, false, F(0));
             R* gp = GPk(k);
             for (int i = lane; i < nz; i += kTS) gp[i] = sVec[i];
@@ -2156,7 +2173,7 @@ struct Solver {
             build_stage_matrix(k, k < NN());
             if constexpr (kStageFB) {                       // next stage's records / vectors / C rows arrive during the factorisation
                 tsync();
-                tt_issue(k - 1, false);
+                tt_issue(k - 1, true);
                 sm_issue(k - 1, false, true);
                 c_issue(k - 1);
                 if constexpr (kStageTT) cp_commit();
@@ -2336,7 +2353,7 @@ struct Solver {
     // d lambda, d t per side, and the running maximum feasible step.  Directions: F arithmetic on the F images of
     // t and lambda; only the slack residual rd = d + eps lam - t is formed in double.  `rnd`: bound on what the
     // F arithmetic leaves of rd after a full step.
-    __device__ __forceinline__ void stage_side_steps(int k, const F* d, bool corrector, F target_mu, F& amax, F& rnd) {
+    __device__ __forceinline__ void stage_side_steps(int k, const F* d, bool corrector, F target_mu, F& amax, F& rnd, R& s1, R& s2) {
         const R* zk = st_z(k);
         const F cm = corrector ? F(1) : F(0);
         constexpr F kEps = std::is_same<F, R>::value ? F(4.5e-16) : F(2.4e-7);
@@ -2363,6 +2380,10 @@ struct Solver {
                 const F dtt = sg * adz + epsf * dl + rd;
                 dd.v[sd] = dtt;
                 dd.v[2 + sd] = dl;
+                // sum (t + a dt)(lam + a dlam) = sum t lam + a s1 + a^2 s2: the mean complementarity after a step of any
+                // length without another pass over the records
+                s1 += t * R(dl) + lam * R(dtt);
+                s2 += R(dtt) * R(dl);
                 rnd = max(rnd, kEps * (fabs(adz) + fabs(rd) + epsf * fabs(dl)));
                 if (!(fabs(dtt) + fabs(dl) < tinf<F>())) rnd = tinf<F>();   // a step outside the range of F: not applied
                 if (dtt < F(0)) amax = min(amax, fdiv(-tf, dtt));
@@ -2374,7 +2395,7 @@ struct Solver {
 
     // Passes B / D (forward): direction from the stored factors and w, written to DZ, with the force steps and the
     // side steps of every stage fused in.  Returns the largest feasible step in (0, 1].
-    __device__ R pass_forward(bool corrector, F target_mu, R* rnd_out) {
+    __device__ R pass_forward(bool corrector, F target_mu, R* rnd_out, R* s1_out, R* s2_out) {
         constexpr int nq = D::nq, nx = D::nx;
         const int nu = NU(), nz = NZ();
         F* dxn = sDxn;          // [nx] next state direction
@@ -2382,6 +2403,7 @@ struct Solver {
         F* dj = dst;
         F* dx = dst + nu;
         F amax = F(1), rnd = F(0);
+        R s1 = R(0), s2 = R(0);
         for (int i = lane; i < nz; i += kTS) dst[i] = F(0);
         tsync();
         pass_fence();
@@ -2440,7 +2462,7 @@ struct Solver {
             }
             F* Dk = DZk(k);
             for (int i = lane; i < nz; i += kTS) Dk[i] = dst[i];
-            stage_side_steps(k, dst, corrector, target_mu, amax, rnd);
+            stage_side_steps(k, dst, corrector, target_mu, amax, rnd, s1, s2);
             if constexpr (kStageFB) {
                 tsync();
                 tt_issue(k + 1, true);
@@ -2463,6 +2485,8 @@ struct Solver {
         }
         if constexpr (kStageFB) cp_wait<0>();
         *rnd_out = R(tmax(rnd));
+        *s1_out = tsum(s1);
+        *s2_out = tsum(s2);
         return R(tmin(amax));
     }
 
@@ -2528,6 +2552,7 @@ struct Solver {
         const int nsides = int(tsum(R(nsides_l)) + R(0.5));
         tsync();
         R last_alpha = R(0), last_step = tinf<R>();
+        pend_alpha = R(0);
         int iters = 0;
         // residual summary of the current iterate: mean complementarity and the largest slack residual
         R mu = 0, rdmax = 0;
@@ -2624,23 +2649,13 @@ struct Solver {
             R target_mu = PR.mu_target;
             R alpha = R(1);
             // predictor (pass 0) and corrector (pass 1) share ONE inlined copy of the forward pass
-            R a_fwd = R(1), rnd_gap = R(0);
+            R a_fwd = R(1), rnd_gap = R(0), cs1 = R(0), cs2 = R(0);
 #pragma unroll 1
             for (int pass = 0; pass < (nsides > 0 ? 2 : 1); ++pass) {
                 if (pass == 1) {
                     // mean complementarity after the affine step -> centring target (Mehrotra)
                     const R a_aff = a_fwd;
-                    R acc = 0;
-                    for (int idx = lane; idx < (N + 1) * NROW(); idx += kTS) {
-                        const int k = idx / NROW(), r = idx % NROW();
-                        const int fam = row_family(r);
-                        if (!row_valid(k, fam)) continue;
-                        const QuadR q = wsr<QuadR>(oTL())[idx];
-                        const QuadF dd = wsr<QuadF>(oDD())[idx];
-                        acc += (q.v[0] + a_aff * R(dd.v[0])) * (q.v[2] + a_aff * R(dd.v[2]));
-                        if (fam < 2) acc += (q.v[1] + a_aff * R(dd.v[1])) * (q.v[3] + a_aff * R(dd.v[3]));
-                    }
-                    const R mu_aff = tsum(acc) / R(nsides);
+                    const R mu_aff = mu + (a_aff * cs1 + a_aff * a_aff * cs2) / R(nsides);
                     const R ratio = mu_aff / mu;
                     target_mu = max(ratio * ratio * ratio * mu, PR.mu_target);
                     long long c3 = UB_CLK();
@@ -2648,7 +2663,7 @@ struct Solver {
                     c2 = c3;
                     pass_backward_corrector(F(target_mu));
                 }
-                a_fwd = pass_forward(pass == 1, pass == 1 ? F(target_mu) : F(0), &rnd_gap);
+                a_fwd = pass_forward(pass == 1, pass == 1 ? F(target_mu) : F(0), &rnd_gap, &cs1, &cs2);
             }
             if (nsides > 0) alpha = min(R(1), R(0.995) * a_fwd);
             UB_ACC(t_side, UB_CLK() - c2);
@@ -2663,25 +2678,12 @@ struct Solver {
                 }
                 break;
             }
-            // update z, t, lambda; new mean complementarity
-            R musum = 0;
+            // update z; t and lambda follow lazily, stage by stage, when the next factor pass visits them
+            // (apply_pending_update), and their new mean complementarity comes from the sums of the forward pass
             for (int idx = lane; idx < (N + 1) * nz; idx += kTS) Zall[idx] += alpha * R(ws[oDZ() + idx]);
-            for (int idx = lane; idx < (N + 1) * NROW(); idx += kTS) {
-                const int k = idx / NROW(), r = idx % NROW();
-                const int fam = row_family(r);
-                QuadR* rec = wsr<QuadR>(oTL()) + idx;
-                QuadR q = *rec;
-                const QuadF dd = wsr<QuadF>(oDD())[idx];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) q.v[c] += alpha * R(dd.v[c]);
-                *rec = q;
-                if (row_valid(k, fam)) {
-                    musum += q.v[0] * q.v[2];
-                    if (fam < 2) musum += q.v[1] * q.v[3];
-                }
-            }
+            pend_alpha = alpha;
             tsync();
-            mu = nsides > 0 ? tsum(musum) / R(nsides) : R(0);
+            mu = nsides > 0 ? mu + (alpha * cs1 + alpha * alpha * cs2) / R(nsides) : R(0);
             // the rows are linear: the slack residual contracts by (1 - alpha), up to the rounding of the stored steps
             // (zero in the fp64 kernels, where this is the exact recursion)
             rdmax = (R(1) - alpha) * rdmax + alpha * rnd_gap;
