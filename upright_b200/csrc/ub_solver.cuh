@@ -752,8 +752,49 @@ struct Solver {
         const int nq = NQ(), nx = NX(), nu = NU(), N = NN();
         const R scale = rsqrt(R(6 * max(NB(), 1)));
         R sph[3 * UB_MAX_SPHERES], dsph[3 * UB_MAX_SPHERES];
+        // dynamics gap b_k = A x_k + B u_k - x_{k+1}  (exact triple integrator, system_dynamics.h:15-26)
+        auto write_gap = [&](int k) {
+            if (k < N && lane < nq) {
+                const F* x = X + k * nx;
+                const R dt = PR.dt;
+                const F* xn = X + (k + 1) * nx;
+                const R q = R(x[lane]), v = R(x[nq + lane]), a = R(x[2 * nq + lane]), j = R(U[k * nu + lane]);
+                R* gap = wsr<R>(oGAP()) + k * nx;
+                gap[lane] = q + dt * v + R(0.5) * dt * dt * a + dt * dt * dt / R(6) * j - R(xn[lane]);
+                gap[nq + lane] = v + dt * a + R(0.5) * dt * dt * j - R(xn[nq + lane]);
+                gap[2 * nq + lane] = a + dt * j - R(xn[2 * nq + lane]);
+            }
+        };
+        // A knot whose (x, u) equals the previous knot's bit for bit has the same linearisation: copied, not recomputed.
+        // (Every knot of a cold start — DefaultInitializer: state held, zero input — is such a knot.)  Rows that depend
+        // on the knot index itself (orientation / box targets, dynamic obstacles, projectile) switch the shortcut off.
+        const bool memo_ok = !(ORI() || IALIGN() || IACON() || EEBOX() || NXO() > 0 || NPROJ() > 0);
         for (int k = 0; k <= N; ++k) {
             const F* x = X + k * nx;
+            if (memo_ok && k > 0) {
+                bool eq = true;
+                const F* xp = x - nx;
+                for (int i = lane; i < nx; i += kTS) eq = eq && (x[i] == xp[i]);
+                if (k < N) {
+                    const F* u = U + k * nu;
+                    for (int i = lane; i < nu; i += kTS) eq = eq && (u[i] == u[i - nu]);
+                }
+                if (__all_sync(FULL, eq)) {
+                    tsync();   // the blocks of knot k - 1 were written by other lanes
+                    const int no = NOBS(), ne = NEQ();
+                    if (lane < 3) wsr<R>(oLR())[3 * k + lane] = wsr<R>(oLR())[3 * (k - 1) + lane];
+                    for (int i = lane; i < 3 * nq; i += kTS) ws[oLJP() + k * 3 * nq + i] = ws[oLJP() + (k - 1) * 3 * nq + i];
+                    for (int i = lane; i < no; i += kTS) ws[oLHO() + k * no + i] = ws[oLHO() + (k - 1) * no + i];
+                    for (int i = lane; i < no * OBSW(); i += kTS) ws[oLJO() + k * no * OBSW() + i] = ws[oLJO() + (k - 1) * no * OBSW() + i];
+                    if (k < N) {
+                        for (int i = lane; i < ne * nx; i += kTS) ws[oLC() + k * ne * nx + i] = ws[oLC() + (k - 1) * ne * nx + i];
+                        for (int i = lane; i < ne; i += kTS) wsr<R>(oLG())[k * ne + i] = wsr<R>(oLG())[(k - 1) * ne + i];
+                    }
+                    write_gap(k);
+                    tsync();
+                    continue;
+                }
+            }
             Kin<R> Kn;
             KinTan<R> Dt;
             // sin / cos of the joint angles once per knot (lane i: joint i), shared through the scratch
@@ -902,16 +943,7 @@ struct Solver {
                     }
                 }
             }
-            // dynamics gap b_k = A x_k + B u_k - x_{k+1}  (exact triple integrator, system_dynamics.h:15-26)
-            if (k < N && lane < nq) {
-                const R dt = PR.dt;
-                const F* xn = X + (k + 1) * nx;
-                const R q = R(x[lane]), v = R(x[nq + lane]), a = R(x[2 * nq + lane]), j = R(U[k * nu + lane]);
-                R* gap = wsr<R>(oGAP()) + k * nx;
-                gap[lane] = q + dt * v + R(0.5) * dt * dt * a + dt * dt * dt / R(6) * j - R(xn[lane]);
-                gap[nq + lane] = v + dt * a + R(0.5) * dt * dt * j - R(xn[nq + lane]);
-                gap[2 * nq + lane] = a + dt * j - R(xn[2 * nq + lane]);
-            }
+            write_gap(k);
         }
         tsync();
     }
@@ -2395,7 +2427,7 @@ struct Solver {
 
     // Passes B / D (forward): direction from the stored factors and w, written to DZ, with the force steps and the
     // side steps of every stage fused in.  Returns the largest feasible step in (0, 1].
-    __device__ R pass_forward(bool corrector, F target_mu, R* rnd_out, R* s1_out, R* s2_out) {
+    __device__ R pass_forward(bool corrector, F target_mu, R* rnd_out, R* s1_out, R* s2_out, R* smax_out) {
         constexpr int nq = D::nq, nx = D::nx;
         const int nu = NU(), nz = NZ();
         F* dxn = sDxn;          // [nx] next state direction
@@ -2404,6 +2436,7 @@ struct Solver {
         F* dx = dst + nu;
         F amax = F(1), rnd = F(0);
         R s1 = R(0), s2 = R(0);
+        F smax = F(0);   // largest entry of the direction (the step must be finite before it is applied)
         for (int i = lane; i < nz; i += kTS) dst[i] = F(0);
         tsync();
         pass_fence();
@@ -2461,7 +2494,10 @@ struct Solver {
                 tsync();
             }
             F* Dk = DZk(k);
-            for (int i = lane; i < nz; i += kTS) Dk[i] = dst[i];
+            for (int i = lane; i < nz; i += kTS) {
+                Dk[i] = dst[i];
+                smax = max(smax, fabs(dst[i]));
+            }
             stage_side_steps(k, dst, corrector, target_mu, amax, rnd, s1, s2);
             if constexpr (kStageFB) {
                 tsync();
@@ -2487,6 +2523,7 @@ struct Solver {
         *rnd_out = R(tmax(rnd));
         *s1_out = tsum(s1);
         *s2_out = tsum(s2);
+        *smax_out = R(tmax(smax));
         return R(tmin(amax));
     }
 
@@ -2522,8 +2559,10 @@ struct Solver {
         }
         tsync();
         init_eq_weights();
-        // slack / multiplier initialisation
+        // slack / multiplier initialisation, with the residual summary of the starting point (mean complementarity and
+        // the largest slack residual) collected on the way
         int nsides_l = 0;
+        R m_l = 0, rd_l = 0;
         for (int k = 0; k <= N; ++k) {
             const R* zk = Zk(k);
             for (int r = lane; r < NROW(); r += kTS) {
@@ -2536,12 +2575,17 @@ struct Solver {
                 if (row_valid(k, fam)) {
                     R lb, ub;
                     const R val = row_value(k, r, fam, zk, X + k * NX(), U + k * NU(), &lb, &ub);
+                    const R eps = row_eps(fam);
                     q.v[0] = max(val - lb, PR.thr0);
                     q.v[2] = PR.mu0 / q.v[0];
+                    rd_l = max(rd_l, fabs(val - lb + eps * q.v[2] - q.v[0]));
+                    m_l += q.v[0] * q.v[2];
                     ++nsides_l;
                     if (fam < 2) {
                         q.v[1] = max(ub - val, PR.thr0);
                         q.v[3] = PR.mu0 / q.v[1];
+                        rd_l = max(rd_l, fabs(ub - val + eps * q.v[3] - q.v[1]));
+                        m_l += q.v[1] * q.v[3];
                         ++nsides_l;
                     }
                 }
@@ -2554,31 +2598,7 @@ struct Solver {
         R last_alpha = R(0), last_step = tinf<R>();
         pend_alpha = R(0);
         int iters = 0;
-        // residual summary of the current iterate: mean complementarity and the largest slack residual
-        R mu = 0, rdmax = 0;
-        auto summarise = [&]() {
-            R m = 0, rd = 0;
-            for (int k = 0; k <= N; ++k) {
-                const R* zk = Zk(k);
-                for (int r = lane; r < NROW(); r += kTS) {
-                    const int fam = row_family(r);
-                    if (!row_valid(k, fam)) continue;
-                    R lb, ub;
-                    const R val = row_value(k, r, fam, zk, X + k * NX(), U + k * NU(), &lb, &ub);
-                    const R eps = row_eps(fam);
-                    const QuadR q = *side_tl(k, r);
-                    rd = max(rd, fabs(val - lb + eps * q.v[2] - q.v[0]));
-                    m += q.v[0] * q.v[2];
-                    if (fam < 2) {
-                        rd = max(rd, fabs(ub - val + eps * q.v[3] - q.v[1]));
-                        m += q.v[1] * q.v[3];
-                    }
-                }
-            }
-            mu = nsides > 0 ? tsum(m) / R(nsides) : R(0);
-            rdmax = tmax(rd);
-        };
-        summarise();
+        R mu = nsides > 0 ? tsum(m_l) / R(nsides) : R(0), rdmax = tmax(rd_l);
         R pinf = R(0);
         // hard equality rows: multiplier update y += rho e (update = true) and their largest residual
         auto eq_pass = [&](bool update) {
@@ -2649,7 +2669,7 @@ struct Solver {
             R target_mu = PR.mu_target;
             R alpha = R(1);
             // predictor (pass 0) and corrector (pass 1) share ONE inlined copy of the forward pass
-            R a_fwd = R(1), rnd_gap = R(0), cs1 = R(0), cs2 = R(0);
+            R a_fwd = R(1), rnd_gap = R(0), cs1 = R(0), cs2 = R(0), dzmax = R(0);
 #pragma unroll 1
             for (int pass = 0; pass < (nsides > 0 ? 2 : 1); ++pass) {
                 if (pass == 1) {
@@ -2663,14 +2683,12 @@ struct Solver {
                     c2 = c3;
                     pass_backward_corrector(F(target_mu));
                 }
-                a_fwd = pass_forward(pass == 1, pass == 1 ? F(target_mu) : F(0), &rnd_gap, &cs1, &cs2);
+                a_fwd = pass_forward(pass == 1, pass == 1 ? F(target_mu) : F(0), &rnd_gap, &cs1, &cs2, &dzmax);
             }
             if (nsides > 0) alpha = min(R(1), R(0.995) * a_fwd);
             UB_ACC(t_side, UB_CLK() - c2);
             // the step must be finite before it is applied
-            R stepmax = 0;
-            for (int idx = lane; idx < (N + 1) * nz; idx += kTS) stepmax = max(stepmax, fabs(alpha * R(ws[oDZ() + idx])));
-            stepmax = tmax(stepmax);
+            const R stepmax = fabs(alpha * dzmax);   // = max |alpha dz| (collected by the forward pass)
             if (!(stepmax < tinf<R>()) || !(alpha > R(0)) || !(alpha <= R(1)) || !(rnd_gap < tinf<R>())) {
                 if constexpr (std::is_same<F, R>::value) {
                     *finite = false;
