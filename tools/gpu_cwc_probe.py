@@ -1,5 +1,6 @@
+"""Contact-wrench-cone violation of the planned knots of cfg2 over successive SQP iterations (upright_b200/robust.py)."""
 import sys, numpy as np
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent))
 from upright_b200 import workload, problem_io
 from upright_b200.engine import BatchedMPC
 from upright_b200.robust import WrenchConeVerifier

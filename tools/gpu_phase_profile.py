@@ -1,4 +1,6 @@
-"""Per-phase cycle breakdown of the solve kernel (profile mode, stop_after=9)."""
+"""Per-phase cycle breakdown of the solve kernel (needs a library built with -DUB_PROFILE=1: tools/build_variant.py profile
+-DUB_PROFILE=1, UB_LIBRARY=variants/profile/libupright_b200.so).  Third argument "persistent": counters of the product
+grid (work queue, alignment) instead of the static test grid."""
 import sys
 from pathlib import Path
 import numpy as np

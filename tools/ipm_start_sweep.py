@@ -1,5 +1,7 @@
+"""CPU oracle: interior-point iterations of every BASELINE configuration against the start values of the slacks and
+multipliers (qp_mu0, qp_thr0) — profiles/r2_v5_ipm_start_sweep.txt."""
 import sys, numpy as np, itertools
-sys.path.insert(0,'/root/repo')
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent))
 import oracle
 from upright_b200 import workload
 names = ["cfg1_ur10_demo","cfg2_thing_demo","cfg3_thing_box_arch","cfg4_thing_obstacles2","cfg5_thing_robust8"]
