@@ -2604,6 +2604,30 @@ struct Solver {
         auto eq_pass = [&](bool update) {
             R pv = R(0);
             if (!C.soft_poly) {
+                if (NEQ() > 0 && NEQ() <= 8) {
+                    // one body: four lanes share a row's dot product and read the C rows straight from the workspace
+                    // (no staging copy, no barrier: the loads of all stages are independent)
+                    const int ne = NEQ(), i = lane >> 2, part = lane & 3;
+                    for (int k = 0; k < N; ++k) {
+                        const R* zk = Zk(k);
+                        R v = R(0);
+                        if (i < ne) {
+                            const F* c = ws + oLC() + (k * ne + i) * nx;
+                            for (int j = part; j < nx; j += 4) v += R(c[j]) * zk[nu + j];
+                            if (part == 0) v += wsr<R>(oLG())[k * ne + i] + eq_force_dot(i, zk + nq);
+                        }
+                        v += __shfl_xor_sync(FULL, v, 1);
+                        v += __shfl_xor_sync(FULL, v, 2);
+                        if (i < ne && part == 0) {
+                            const R rho = rho_eq(k)[i];
+                            if (rho > R(0)) {
+                                if (update) y_eq(k)[i] += rho * v;
+                                pv = max(pv, fabs(v));
+                            }
+                        }
+                    }
+                    tsync();
+                } else
                 for (int k = 0; k < N; ++k) {
                     if (NEQ() == 0) break;
                     load_C(k);
