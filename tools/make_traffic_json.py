@@ -12,7 +12,8 @@ tag = sys.argv[1]
 names = {"cfg1": ("cfg1_ur10_demo", 4096), "cfg2": ("cfg2_thing_demo", 4096), "cfg3": ("cfg3_thing_box_arch", 4096),
          "cfg4": ("cfg4_thing_obstacles2", 2048), "cfg5": ("cfg5_thing_robust8", 1024)}
 unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-out = {}
+path = root / "profiles" / "traffic.json"
+out = json.load(open(path)) if path.exists() else {}   # entries of other captures are kept
 for short, (name, batch) in names.items():
     f = root / "profiles" / f"{tag}_{short}_raw.csv"
     if not f.exists():
@@ -25,5 +26,5 @@ for short, (name, batch) in names.items():
     out[name] = {"batch": batch, "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
                  "kernel_ms_under_ncu": ms,
                  "source": f"profiles/{f.name} (ncu --set full, one launch of ub::solve_batch_kernel, {short}, B={batch})"}
-json.dump(out, open(root / "profiles" / "traffic.json", "w"), indent=1)
+json.dump(out, open(path, "w"), indent=1)
 print(json.dumps({k: round(v["dram_bytes_per_launch"] / 1e9, 3) for k, v in out.items()}))
